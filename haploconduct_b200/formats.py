@@ -1,0 +1,301 @@
+"""Host-side containers and file formats of the path (numpy only, no device code).
+
+Mirrors, for the Python tests / bench harness, what the reference keeps in
+``FastqStorage`` (src/FastqStorage.h:58-98, src/FastqStorage.cpp:92-235) and ``Overlap``
+(src/Overlap.h:20-59): reads in ``m_read_vec`` order (singles first, then pairs), and the
+13-column overlaps text format ``ID1 ID2 POS1 POS2 ORD ORI1 ORI2 PERC1 PERC2 LEN1 LEN2 TYPE1 TYPE2``
+(scripts/sfo2overlaps.py:153).  The numpy dtypes below are byte-for-byte the C structs of
+``include/hc_b200.h``.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+
+# ---- C-ABI mirrors (include/hc_b200.h) -------------------------------------------------------
+READ_DESC = np.dtype([("seq_off", "<u8", (2,)), ("seq_len", "<u4", (2,))])
+CANDIDATE = np.dtype(
+    [
+        ("idx1", "<u4"), ("idx2", "<u4"), ("pos1", "<u4"), ("pos2", "<u4"), ("len1", "<u4"), ("len2", "<u4"),
+        ("perc1", "u1"), ("perc2", "u1"), ("ord", "u1"), ("ori1", "u1"), ("ori2", "u1"),
+        ("type1", "u1"), ("type2", "u1"), ("reserved", "u1"),
+    ]
+)
+PARAMS = np.dtype(
+    [
+        ("edge_threshold", "<f8"), ("ov_threshold", "<f8"), ("merge_contigs", "<f8"), ("mismatch", "<f8"),
+        ("min_read_len", "<u4"), ("flags", "<u4"),
+    ]
+)
+RESULT = np.dtype(
+    [
+        ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos3", "<i4"), ("pos4", "<i4"),
+        ("mismatches", "<u4", (2,)), ("compared", "<u4", (2,)),
+        ("cls", "u1"), ("status", "u1", (2,)), ("exact", "u1"), ("reserved", "<u4"),
+    ]
+)
+EDGE = np.dtype([("cand", "<u8"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos3", "<i4"), ("pos4", "<i4")])
+BATCH_STATS = np.dtype(
+    [
+        ("n_candidates", "<u8"), ("n_edges", "<u8"), ("n_nonedges", "<u8"), ("n_exact", "<u8"),
+        ("n_windows", "<u8"), ("n_positions", "<u8"), ("algorithmic_bytes", "<u8"),
+        ("kernel_ms", "<f4"), ("total_ms", "<f4"), ("kernel_launches", "<u4"), ("reserved", "<u4"),
+    ]
+)
+assert READ_DESC.itemsize == 24 and CANDIDATE.itemsize == 32 and PARAMS.itemsize == 40
+assert RESULT.itemsize == 48 and EDGE.itemsize == 32 and BATCH_STATS.itemsize == 72
+
+CLASS_DISCARD, CLASS_EDGE, CLASS_NONEDGE = 0, 1, 2
+FLAG_EXACT_EDGE_SCORES = 1
+
+
+def make_params(edge_threshold=0.99, ov_threshold=0.9, merge_contigs=0.0, mismatch=0.0, min_read_len=0, flags=0):
+    """Defaults are the option-table defaults of src/ViralQuasispecies.cpp:63-64,81,83,88."""
+    p = np.zeros(1, dtype=PARAMS)
+    p["edge_threshold"] = edge_threshold
+    p["ov_threshold"] = ov_threshold
+    p["merge_contigs"] = merge_contigs
+    p["mismatch"] = mismatch
+    p["min_read_len"] = min_read_len
+    p["flags"] = flags
+    return p
+
+
+# ---- reads -------------------------------------------------------------------------------------
+@dataclass
+class ReadSet:
+    """Reads in m_read_vec order: ``n_single`` singles, then pairs (src/FastqStorage.h:88-97)."""
+
+    ids: np.ndarray          # uint64 read IDs as used in the overlaps file
+    descs: np.ndarray        # READ_DESC per read
+    bases: np.ndarray        # uint8 ASCII blob
+    quals: np.ndarray        # uint8 ASCII blob (raw FASTQ characters)
+    n_single: int
+    _id_to_index: Optional[Dict[int, int]] = field(default=None, repr=False)
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.descs.shape[0])
+
+    def id_to_index(self) -> Dict[int, int]:
+        if self._id_to_index is None:
+            self._id_to_index = {int(v): i for i, v in enumerate(self.ids)}
+        return self._id_to_index
+
+    def seq(self, idx: int, mate: int = 0) -> str:
+        d = self.descs[idx]
+        o, n = int(d["seq_off"][mate]), int(d["seq_len"][mate])
+        return self.bases[o:o + n].tobytes().decode()
+
+    def qual(self, idx: int, mate: int = 0) -> str:
+        d = self.descs[idx]
+        o, n = int(d["seq_off"][mate]), int(d["seq_len"][mate])
+        return self.quals[o:o + n].tobytes().decode()
+
+    def is_paired(self, idx: int) -> bool:
+        return int(self.descs[idx]["seq_len"][1]) > 0
+
+    @staticmethod
+    def from_lists(singles: List[Tuple[int, str, str]], pairs: List[Tuple[int, str, str, str, str]]) -> "ReadSet":
+        """singles: (id, seq, qual); pairs: (id, seq1, qual1, seq2, qual2)."""
+        n = len(singles) + len(pairs)
+        descs = np.zeros(n, dtype=READ_DESC)
+        ids = np.zeros(n, dtype=np.uint64)
+        chunks_b: List[bytes] = []
+        chunks_q: List[bytes] = []
+        off = 0
+        for i, (rid, s, q) in enumerate(singles):
+            assert len(s) == len(q) and len(s) > 0
+            ids[i] = rid
+            descs[i]["seq_off"][0] = off
+            descs[i]["seq_len"][0] = len(s)
+            chunks_b.append(s.encode())
+            chunks_q.append(q.encode())
+            off += len(s)
+        for j, (rid, s1, q1, s2, q2) in enumerate(pairs):
+            i = len(singles) + j
+            assert len(s1) == len(q1) and len(s2) == len(q2) and len(s1) > 0 and len(s2) > 0
+            ids[i] = rid
+            descs[i]["seq_off"][0] = off
+            descs[i]["seq_len"][0] = len(s1)
+            off += len(s1)
+            descs[i]["seq_off"][1] = off
+            descs[i]["seq_len"][1] = len(s2)
+            off += len(s2)
+            chunks_b += [s1.encode(), s2.encode()]
+            chunks_q += [q1.encode(), q2.encode()]
+        bases = np.frombuffer(b"".join(chunks_b), dtype=np.uint8).copy()
+        quals = np.frombuffer(b"".join(chunks_q), dtype=np.uint8).copy()
+        return ReadSet(ids=ids, descs=descs, bases=bases, quals=quals, n_single=len(singles))
+
+    def subset(self, keep: Iterable[int]) -> "ReadSet":
+        keep = sorted(set(int(k) for k in keep))
+        singles = [(int(self.ids[i]), self.seq(i), self.qual(i)) for i in keep if not self.is_paired(i)]
+        pairs = [
+            (int(self.ids[i]), self.seq(i, 0), self.qual(i, 0), self.seq(i, 1), self.qual(i, 1))
+            for i in keep if self.is_paired(i)
+        ]
+        return ReadSet.from_lists(singles, pairs)
+
+
+def _read_fastq_records(path: str) -> List[Tuple[str, str, str]]:
+    out = []
+    with open(path, "r") as f:
+        lines = f.read().split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    for k in range(0, len(lines) - 3, 4):
+        if not lines[k].startswith("@"):
+            raise ValueError("Read ID does not start with @")
+        name = lines[k][1:].split()[0] if lines[k][1:].split() else ""
+        out.append((name, lines[k + 1], lines[k + 3]))
+    return out
+
+
+def _parse_id(s: str) -> int:
+    """str_to_read_id = strtoul(s, NULL, 0) (src/Types.h:99-102): base auto-detection."""
+    s = s.strip()
+    try:
+        return int(s, 0)
+    except ValueError:
+        # strtoul parses the longest valid prefix, 0 if none
+        digits = ""
+        for ch in s:
+            if ch.isdigit():
+                digits += ch
+            else:
+                break
+        return int(digits) if digits else 0
+
+
+def load_fastq_set(singles: Optional[str], paired1: Optional[str], paired2: Optional[str]) -> ReadSet:
+    """FastqStorage semantics: singles are upper-cased (src/FastqStorage.cpp:123), pairs are taken
+    verbatim (:196-197); empty sequences are an error (:143-146,:222-225)."""
+    s_list: List[Tuple[int, str, str]] = []
+    p_list: List[Tuple[int, str, str, str, str]] = []
+    if singles and singles != "None":
+        for name, s, q in _read_fastq_records(singles):
+            if len(s) == 0:
+                raise ValueError("single read with an empty sequence")
+            s_list.append((_parse_id(name), s.upper(), q))
+    if paired1 and paired1 != "None":
+        r1 = _read_fastq_records(paired1)
+        r2 = _read_fastq_records(paired2)
+        for (n1, s1, q1), (n2, s2, q2) in zip(r1, r2):
+            if n1 != n2:
+                raise ValueError("Fastq files /1 /2 are not ordered identically")
+            if len(s1) == 0 or len(s2) == 0:
+                raise ValueError("paired read with an empty sequence")
+            p_list.append((_parse_id(n1), s1, q1, s2, q2))
+    return ReadSet.from_lists(s_list, p_list)
+
+
+def write_fastq_set(rs: ReadSet, singles: str, paired1: str, paired2: str) -> None:
+    with open(singles, "w") as fs, open(paired1, "w") as f1, open(paired2, "w") as f2:
+        for i in range(rs.n_reads):
+            rid = int(rs.ids[i])
+            if not rs.is_paired(i):
+                fs.write("@%d\n%s\n+\n%s\n" % (rid, rs.seq(i), rs.qual(i)))
+            else:
+                f1.write("@%d\n%s\n+\n%s\n" % (rid, rs.seq(i, 0), rs.qual(i, 0)))
+                f2.write("@%d\n%s\n+\n%s\n" % (rid, rs.seq(i, 1), rs.qual(i, 1)))
+
+
+# ---- overlaps file -------------------------------------------------------------------------------
+def candidates_to_lines(cands: np.ndarray, ids: np.ndarray) -> List[str]:
+    """Overlap::get_overlap_line (src/Overlap.h:234-237): every numeric field printed, '-' never
+    re-emitted for POS2/PERC2/LEN2 (they were folded to 0 by the constructor, :55-59)."""
+    out = []
+    for c in cands:
+        out.append(
+            "%d\t%d\t%d\t%d\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%s\n"
+            % (
+                int(ids[c["idx1"]]), int(ids[c["idx2"]]), c["pos1"], c["pos2"], chr(c["ord"]),
+                "+" if c["ori1"] else "-", "+" if c["ori2"] else "-", c["perc1"], c["perc2"], c["len1"], c["len2"],
+                chr(c["type1"]), chr(c["type2"]),
+            )
+        )
+    return out
+
+
+def write_overlaps(path: str, cands: np.ndarray, ids: np.ndarray, dash_for_single: bool = True) -> None:
+    """Writes the producer-side format (scripts/sfo2overlaps.py:153,186-199): S-S lines carry '-' in
+    POS2/PERC2/LEN2."""
+    with open(path, "w") as f:
+        for c in cands:
+            ss = dash_for_single and c["type1"] == ord("s") and c["type2"] == ord("s")
+            f.write(
+                "%d\t%d\t%d\t%s\t%s\t%s\t%s\t%d\t%s\t%d\t%s\t%s\t%s\n"
+                % (
+                    int(ids[c["idx1"]]), int(ids[c["idx2"]]), c["pos1"], "-" if ss else str(int(c["pos2"])),
+                    chr(c["ord"]), "+" if c["ori1"] else "-", "+" if c["ori2"] else "-", c["perc1"],
+                    "-" if ss else str(int(c["perc2"])), c["len1"], "-" if ss else str(int(c["len2"])),
+                    chr(c["type1"]), chr(c["type2"]),
+                )
+            )
+
+
+def _atoi(s: str) -> int:
+    s = s.strip()
+    sign = 1
+    k = 0
+    if k < len(s) and s[k] in "+-":
+        sign = -1 if s[k] == "-" else 1
+        k += 1
+    v = 0
+    while k < len(s) and s[k].isdigit():
+        v = v * 10 + ord(s[k]) - 48
+        k += 1
+    return sign * v
+
+
+def parse_overlaps(path: str, id_to_index: Dict[int, int], max_overlaps: int = 100000000) -> Tuple[np.ndarray, np.ndarray]:
+    """The parsing half of EdgeCalculator::construct_edges (src/EdgeCalculator.cpp:581-607, tab-split
+    branch) + Overlap's constructor (src/Overlap.h:39-73).  Returns (candidates, 1-based line numbers);
+    self-overlaps and lines without exactly 13 fields are skipped like the reference does."""
+    recs = []
+    lines_no = []
+    with open(path, "r") as f:
+        for i, line in enumerate(f, start=1):
+            if i > max_overlaps:
+                break
+            t = line.rstrip("\n").strip("\t ")
+            fld = t.split("\t")
+            if len(fld) != 13:
+                continue
+            id1, id2 = _parse_id(fld[0]), _parse_id(fld[1])
+            if id1 == id2:
+                continue
+            pos2, perc2, len2 = _atoi(fld[3]), _atoi(fld[8]), _atoi(fld[10])
+            if fld[3] == "-":
+                pos2 = perc2 = len2 = 0
+            recs.append(
+                (
+                    id_to_index[id1], id_to_index[id2], _atoi(fld[2]), pos2, _atoi(fld[9]), len2, _atoi(fld[7]), perc2,
+                    ord(fld[4].replace(" ", "")[0]), 1 if fld[5].strip() == "+" else 0, 1 if fld[6].strip() == "+" else 0,
+                    ord(fld[11].strip()[0]), ord(fld[12].strip()[0]), 0,
+                )
+            )
+            lines_no.append(i)
+    return np.array(recs, dtype=CANDIDATE), np.array(lines_no, dtype=np.int64)
+
+
+def prefilter(cands: np.ndarray, min_overlap_len: int, min_overlap_perc: int = 0, relax_PE_edges: bool = False) -> np.ndarray:
+    """Vectorised src/EdgeCalculator.cpp:605-635.  Returns int8: 1 = scored, 0 = filtered non-edge
+    (written back to nonedge_overlaps.txt, :633-635,:654-660), -1 = silently dropped."""
+    c = cands
+    perc = np.where(c["perc2"] > 0, (0.5 * (c["perc1"].astype(np.float64) + c["perc2"])).astype(np.uint32), c["perc1"])
+    anyp = (c["type1"] == ord("p")) | (c["type2"] == ord("p"))
+    ss = (c["type1"] == ord("s")) & (c["type2"] == ord("s"))
+    b1 = (c["len1"] >= min_overlap_len) & ss
+    b2 = ~b1 & (c["len1"] >= 0.5 * min_overlap_len) & (c["len2"] >= 0.5 * min_overlap_len) & anyp
+    b3 = ~b1 & ~b2 & bool(relax_PE_edges) & ((c["len1"].astype(np.int64) + c["len2"]) >= min_overlap_len) & anyp
+    inb = b1 | b2 | b3
+    out = np.zeros(len(c), dtype=np.int8)
+    out[inb & (perc >= min_overlap_perc)] = 1
+    out[inb & (perc < min_overlap_perc)] = -1
+    out[c["idx1"] == c["idx2"]] = -1
+    return out

@@ -1,0 +1,196 @@
+/* hc_b200.h -- C ABI of the B200-native overlap-edge scoring path.
+ *
+ * This is the drop-in boundary underneath the reference's two C++ interfaces
+ *   EdgeCalculator::construct_edges()/process_overlaps()   src/EdgeCalculator.h:44-63, src/EdgeCalculator.cpp:389-423
+ *   FastqStorage                                           src/FastqStorage.h:58-98
+ * (FindNextOverlaps entry points are declared further down when that row is built).
+ * Plain pointers and sizes only; no C++ or torch types cross it.  The library owns all device
+ * memory; the caller owns every host buffer; no pointer handed out by the library outlives the
+ * object it belongs to.  There is NO CPU fallback: every compute entry point fails with
+ * HC_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Error convention: every int-returning function returns HC_OK (0) or a negative HC_ERR_*;
+ * hc_last_error() returns a thread-local, human readable description of the last failure.
+ * The reference prints to stderr and exit(1)s (src/Overlap.h:109-163, src/EdgeCalculator.cpp:662-665);
+ * the host shim above this ABI maps a negative return to exactly that behaviour.
+ */
+#ifndef HC_B200_H_
+#define HC_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HC_OK              0
+#define HC_ERR_ARG        -1   /* bad argument (NULL pointer, index out of range, bad ord/ori) */
+#define HC_ERR_CUDA       -2   /* CUDA runtime/driver failure or no usable device */
+#define HC_ERR_NOMEM      -3   /* host or device allocation failed */
+#define HC_ERR_INPUT      -4   /* input the reference would exit(1)/assert on (invalid base, empty read, bad quality) */
+#define HC_ERR_CAPACITY   -5   /* caller-provided output buffer too small */
+
+/* ------------------------------------------------------------------------------------------
+ * Read store  (replaces FastqStorage, src/FastqStorage.h:58-98 + src/Read.h:30-31)
+ *
+ * Reads are addressed by their dense index in the reference's m_read_vec order: all single-end
+ * reads first, then all pairs (src/FastqStorage.h:88-97).  A single read has one sequence
+ * (mate slot 0); a paired read has two (mate slots 0 and 1 = /1 and /2, stored exactly as read,
+ * i.e. NOT reverse-complemented -- src/FastqStorage.cpp:196-205).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hc_store hc_store;
+
+typedef struct {
+    uint64_t seq_off[2];   /* byte offset of mate 0 / mate 1 in the bases[] and quals[] blobs        */
+    uint32_t seq_len[2];   /* length of mate 0 / mate 1; seq_len[1] == 0  <=>  single-end read       */
+} hc_read_desc;
+
+/* Pack n_reads reads (n_single singles first, then pairs) into the device-resident SoA store
+ * and replicate it on `n_devices` devices starting at `first_device` (pass n_devices = 1 and the
+ * rank's local device in a one-process-per-GPU launch).
+ *   bases: ASCII, upper-case A/C/G/T/N only (anything else -> HC_ERR_INPUT; the reference asserts
+ *          on it in EdgeCalculator::score, src/EdgeCalculator.cpp:29-30).
+ *   quals: raw FASTQ quality characters; Q = c - 33 must lie in [0, 93]
+ *          (src/EdgeCalculator.cpp:93-96; outside it the reference's asserts :61,:97 fire).
+ * Returns NULL on failure (see hc_last_error()). */
+hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t n_single,
+                          const char* bases, const char* quals,
+                          int first_device, int n_devices);
+void      hc_store_destroy(hc_store* s);
+
+uint64_t  hc_store_n_reads(const hc_store* s);
+uint64_t  hc_store_n_single(const hc_store* s);
+int       hc_store_n_devices(const hc_store* s);
+/* bytes of device memory one replica occupies (bases 2-bit + N-mask 1-bit + quality bytes, both strands) */
+uint64_t  hc_store_device_bytes(const hc_store* s);
+/* number of distinct quality values present (decides the 6-bit "narrow" vs 7-bit "wide" kernel) */
+int       hc_store_quality_alphabet(const hc_store* s);
+
+/* ------------------------------------------------------------------------------------------
+ * Candidates  (replaces Overlap, src/Overlap.h:20-59; one record = one line of the 13-column
+ * overlaps file after the host has mapped read IDs to dense indices)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint32_t idx1, idx2;     /* dense read indices of ID1 / ID2                                   */
+    uint32_t pos1, pos2;     /* POS1 / POS2 ("-" -> 0, src/Overlap.h:55-59)                        */
+    uint32_t len1, len2;     /* LEN1 / LEN2                                                        */
+    uint8_t  perc1, perc2;   /* PERC1 / PERC2                                                      */
+    uint8_t  ord;            /* '1', '2' or '-'                                                    */
+    uint8_t  ori1, ori2;     /* 1 = '+', 0 = '-'                                                   */
+    uint8_t  type1, type2;   /* 's' / 'p' as written in the file (host pre-filter only)           */
+    uint8_t  reserved;       /* must be 0                                                          */
+} hc_candidate;              /* 32 bytes */
+
+/* Scoring parameters = the ProgramSettings fields the path reads (src/Types.h:19-67). */
+typedef struct {
+    double   edge_threshold;   /* src/EdgeCalculator.cpp:404 and per half :256,:294,:355 */
+    double   ov_threshold;     /* :410 */
+    double   merge_contigs;    /* :407 */
+    double   mismatch;         /* :49  */
+    uint32_t min_read_len;     /* :82  */
+    uint32_t flags;            /* HC_FLAG_* */
+} hc_params;
+
+#define HC_FLAG_EXACT_EDGE_SCORES 1u  /* re-sum every accepted edge in the reference's order (slower) */
+
+/* class of a candidate, src/EdgeCalculator.cpp:404-413 */
+#define HC_CLASS_DISCARD 0
+#define HC_CLASS_EDGE    1
+#define HC_CLASS_NONEDGE 2
+
+/* per-window status */
+#define HC_WIN_UNUSED     0   /* S-S candidates have one window only                      */
+#define HC_WIN_SCORED     1
+#define HC_WIN_POS_OOR    2   /* pos >= len(A)            -> score 0, src/EdgeCalculator.cpp:76-79  */
+#define HC_WIN_SHORT      3   /* a read < min_read_len    -> score 0, :82-84                          */
+#define HC_WIN_VOID       4   /* some p < ps.mismatch     -> score 0, :49-51,:125-127                 */
+#define HC_WIN_EMPTY      5   /* no non-N compared base   -> score 0, :129-131                        */
+
+/* Optional per-candidate record (debug / parity); every field is what the reference's Edge holds
+ * after compute_overlap (src/EdgeCalculator.cpp:143-385) plus the integer counts behind it. */
+typedef struct {
+    double   score;            /* Edge::score                                                       */
+    double   mismatch_rate;    /* Edge::mismatch_rate                                               */
+    int32_t  pos3, pos4;       /* Edge::pos3 / pos4 (src/EdgeCalculator.cpp:222,262-263,300-301,361-372) */
+    uint32_t mismatches[2];    /* mismatch_count of window 1 / 2 (src/EdgeCalculator.cpp:105)       */
+    uint32_t compared[2];      /* total_len of window 1 / 2 (non-N compared positions, :104)        */
+    uint8_t  cls;              /* HC_CLASS_*                                                        */
+    uint8_t  status[2];        /* HC_WIN_* per window                                               */
+    uint8_t  exact;            /* 1 if the reference-order re-summation decided this candidate      */
+    uint32_t reserved;
+} hc_result;                   /* 48 bytes */
+
+/* One accepted edge, emitted in INPUT ORDER (= the reference's 1-thread order). */
+typedef struct {
+    uint64_t cand;             /* index into the candidate array of the call                        */
+    double   score;
+    double   mismatch_rate;
+    int32_t  pos3, pos4;
+} hc_edge;                     /* 32 bytes */
+
+typedef struct {
+    uint64_t n_candidates;
+    uint64_t n_edges;
+    uint64_t n_nonedges;
+    uint64_t n_exact;          /* candidates re-summed in reference order (threshold-boundary cases) */
+    uint64_t n_windows;        /* windows actually compared                                         */
+    uint64_t n_positions;      /* sum of window lengths L = min(len(A)-pos, len(B))                 */
+    uint64_t algorithmic_bytes;/* sum over candidates of 32 + sum_w(2*ceil(L/4)+2*ceil(L/8)+2L) + 16 */
+    float    kernel_ms;        /* device time of the scoring kernels of this call (CUDA events)     */
+    float    total_ms;         /* device time of the whole call incl. copies (CUDA events)          */
+    uint32_t kernel_launches;  /* kernels launched by this call                                     */
+    uint32_t reserved;
+} hc_batch_stats;
+
+/* Score a batch of HOST candidates: the body of the omp-parallel region of
+ * EdgeCalculator::process_overlaps (src/EdgeCalculator.cpp:395-423).
+ * The batch is sharded by contiguous index range over the store's devices; outputs are gathered
+ * in input order.
+ *   per_cand      nullable; if given must hold n records.
+ *   edges         must hold *edges_cap records; on return *n_edges are valid.
+ *   nonedge_idx   candidate indices classified "non-edge overlap" (:410-413), input order.
+ * Returns HC_ERR_CAPACITY (and the required sizes in *n_edges / *n_nonedges) if a buffer is too small. */
+int hc_score_batch(hc_store* s, const hc_params* p,
+                   const hc_candidate* cand, uint64_t n,
+                   hc_result* per_cand,
+                   hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges,
+                   uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
+                   hc_batch_stats* stats /* nullable */);
+
+/* Same, but every buffer is DEVICE memory on device `device` (one of the store's devices) and the
+ * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ * d_counts receives {n_edges, n_nonedges, n_exact, 0} as uint64_t[4].  Asynchronous unless stats != NULL.
+ * This is what the throughput benchmark times with inputs resident in HBM, and what a
+ * device-side consumer (NCCL gather, GPU FindNextOverlaps) calls. */
+int hc_score_batch_device(hc_store* s, int device, void* stream, const hc_params* p,
+                          const hc_candidate* d_cand, uint64_t n,
+                          hc_result* d_per_cand /* nullable */,
+                          hc_edge* d_edges, uint64_t edges_cap,
+                          uint64_t* d_nonedge_idx, uint64_t nonedge_cap,
+                          uint64_t* d_counts,
+                          hc_batch_stats* stats /* nullable; non-NULL makes the call synchronous */);
+
+/* The scoring primitive on its own: EdgeCalculator::overlap_score (src/EdgeCalculator.cpp:67-139),
+ * second caller SRBuilder::merge_self_overlap (src/SRBuilder.cpp:872-888).  Sequences are ASCII
+ * host strings; runs one window on device 0 of a transient store.  Returns the score, writes the
+ * mismatch rate; on error returns -1 and sets hc_last_error(). */
+double hc_overlap_score(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2,
+                        const char* qual1, const char* qual2, uint32_t pos,
+                        const hc_params* p, double* mismatch_rate);
+
+/* EdgeCalculator::phred_to_prob (src/EdgeCalculator.cpp:59-63), host arithmetic: pow(10, -Q/10.0). */
+double hc_phred_to_prob(int phred);
+
+/* Smallest double x with exp(x) > threshold under the host libm (the decision
+ * "exp(mean) > threshold" of src/EdgeCalculator.cpp:138,404 is evaluated as "mean >= x" on the device). */
+double hc_exp_threshold(double threshold);
+
+int         hc_device_count(void);
+const char* hc_last_error(void);
+const char* hc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HC_B200_H_ */

@@ -1,0 +1,149 @@
+"""ctypes binding of oracle/liboracle.so (the plain-C restatement, edgecalc_oracle.c) and a thin
+runner for oracle/_ref/ref_driver (the UNMODIFIED reference C++).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import subprocess
+import tempfile
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_DRIVER = os.path.join(HERE, "_ref", "ref_driver")
+REFERENCE_ROOT = "/root/reference"
+
+_lib = None
+
+
+def build(force: bool = False, with_ref: bool = True) -> None:
+    """make port (+ make ref when the reference tree is present; on the GPU box only the prebuilt
+    oracle/_ref/ref_driver that travelled with the snapshot is used)."""
+    targets = []
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "edgecalc_oracle.c")):
+        targets.append("port")
+    if with_ref and os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        targets.append("ref")
+    if targets:
+        subprocess.check_call(["make", "-s", "-C", HERE] + targets)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build(with_ref=False)
+        L = ctypes.CDLL(LIB_PATH)
+        L.hco_score_batch.restype = ctypes.c_int
+        L.hco_score_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+        L.hco_overlap_score.restype = ctypes.c_double
+        L.hco_overlap_score.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p,
+                                        ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        L.hco_phred_to_prob.restype = ctypes.c_double
+        L.hco_phred_to_prob.argtypes = [ctypes.c_int]
+        L.hco_prefilter.restype = ctypes.c_int
+        L.hco_prefilter.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def score_batch(rs, params: np.ndarray, cands: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """hco_score_batch: per-candidate RESULT records (+ per-window mean logs) in input order, 1 thread."""
+    from haploconduct_b200.formats import RESULT
+
+    n = len(cands)
+    res = np.zeros(n, dtype=RESULT)
+    means = np.zeros((n, 2), dtype=np.float64)
+    cands = np.ascontiguousarray(cands)
+    descs = np.ascontiguousarray(rs.descs)
+    rc = lib().hco_score_batch(descs.ctypes.data, rs.n_reads, rs.n_single, rs.bases.ctypes.data, rs.quals.ctypes.data,
+                               params.ctypes.data, cands.ctypes.data, n, res.ctypes.data, means.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle hco_score_batch failed with %d" % rc)
+    return res, means
+
+
+def overlap_score(seq1: str, seq2: str, q1: str, q2: str, pos: int, params: np.ndarray) -> Tuple[float, float]:
+    mm = ctypes.c_double(0)
+    s = lib().hco_overlap_score(seq1.encode(), len(seq1), seq2.encode(), len(seq2), q1.encode(), q2.encode(), pos,
+                                params.ctypes.data, ctypes.byref(mm))
+    return s, mm.value
+
+
+def window_lengths(res: np.ndarray) -> np.ndarray:
+    """sum of window lengths per candidate (the oracle parks it in RESULT.reserved)."""
+    return res["reserved"].astype(np.int64)
+
+
+# ---- the compiled reference ------------------------------------------------------------------------
+def have_ref() -> bool:
+    return os.path.exists(REF_DRIVER) and os.access(REF_DRIVER, os.X_OK)
+
+
+def run_ref(workdir: str, overlaps: str, singles: Optional[str] = None, paired1: Optional[str] = None,
+            paired2: Optional[str] = None, threads: int = 1, dump_cands: bool = False, run: bool = False,
+            dump_graph: bool = False, time_scoring: bool = False, reps: int = 1, **ps) -> Dict:
+    """Runs oracle/_ref/ref_driver with cwd=workdir (the reference writes nonedge_overlaps.txt into
+    its cwd, src/EdgeCalculator.cpp:566,549).  Returns the JSON summary plus parsed dumps."""
+    cmd = [REF_DRIVER, "--overlaps", overlaps, "--threads", str(threads)]
+    if singles:
+        cmd += ["--singles", singles]
+    if paired1:
+        cmd += ["--paired1", paired1, "--paired2", paired2]
+    for k, v in ps.items():
+        cmd += ["--" + k, str(int(v) if isinstance(v, bool) else v)]
+    if dump_cands:
+        cmd += ["--dump-cands", os.path.join(workdir, "ref_cands.tsv")]
+    if run:
+        cmd += ["--run"]
+    if dump_graph:
+        cmd += ["--dump-graph", os.path.join(workdir, "ref_graph.tsv")]
+    if time_scoring:
+        cmd += ["--time-scoring", "--reps", str(reps)]
+    out = subprocess.run(cmd, cwd=workdir, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
+    summary = json.loads([l for l in out.split("\n") if l.startswith("{")][-1])
+    if dump_cands:
+        summary["cands"] = parse_cand_dump(os.path.join(workdir, "ref_cands.tsv"))
+    if dump_graph:
+        summary["graph"] = parse_graph_dump(os.path.join(workdir, "ref_graph.tsv"))
+    if run and os.path.exists(os.path.join(workdir, "nonedge_overlaps.txt")):
+        with open(os.path.join(workdir, "nonedge_overlaps.txt")) as f:
+            summary["nonedge_lines"] = f.read().split("\n")[:-1]
+    return summary
+
+
+REF_CAND = np.dtype([("line", "<i8"), ("cls", "u1"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos1", "<i4"),
+                     ("pos2", "<i4"), ("pos3", "<i4"), ("pos4", "<i4"), ("v1", "<u8"), ("v2", "<u8"), ("ori1", "u1"),
+                     ("ori2", "u1"), ("ord", "u1"), ("perc", "<i4"), ("len1", "<i4"), ("len2", "<i4")])
+REF_EDGE = np.dtype([("v1", "<u8"), ("v2", "<u8"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos1", "<i4"),
+                     ("pos2", "<i4"), ("pos3", "<i4"), ("pos4", "<i4"), ("ori1", "u1"), ("ori2", "u1"), ("ord", "u1"),
+                     ("perc", "<i4"), ("len1", "<i4"), ("len2", "<i4")])
+_CLS = {"D": 0, "E": 1, "N": 2}
+
+
+def parse_cand_dump(path: str) -> np.ndarray:
+    rows = []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            rows.append((int(t[0]), _CLS[t[1]], float.fromhex(t[2]), float.fromhex(t[3]), int(t[4]), int(t[5]), int(t[6]),
+                         int(t[7]), int(t[8]), int(t[9]), int(t[10]), int(t[11]), ord(t[12]) if t[12] else 0, int(t[13]),
+                         int(t[14]), int(t[15])))
+    return np.array(rows, dtype=REF_CAND)
+
+
+def parse_graph_dump(path: str) -> np.ndarray:
+    rows = []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            t = line.rstrip("\n").split("\t")
+            rows.append((int(t[0]), int(t[1]), float.fromhex(t[2]), float.fromhex(t[3]), int(t[4]), int(t[5]), int(t[6]),
+                         int(t[7]), int(t[8]), int(t[9]), ord(t[10]) if t[10] else 0, int(t[11]), int(t[12]), int(t[13])))
+    return np.array(rows, dtype=REF_EDGE)

@@ -1,0 +1,262 @@
+// ref_driver.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Drives the UNMODIFIED reference sources (compiled where they lie under
+// /root/reference/src, see oracle/Makefile) through the EdgeCalculator stage and
+// dumps what the parity tests and the CPU baseline need.  It replaces
+// src/ViralQuasispecies.cpp (which needs boost::program_options) by filling
+// ProgramSettings by hand and replaying src/ViralQuasispecies.cpp:233-281:
+// FastqStorage -> OverlapGraph + addVertex per read -> EdgeCalculator.
+//
+// Modes (combine freely):
+//   --dump-cands F   per pre-filtered candidate, in input order, the Edge that
+//                    EdgeCalculator::compute_overlap (src/EdgeCalculator.cpp:143)
+//                    returns plus the class of src/EdgeCalculator.cpp:404-413.
+//   --run            the real EdgeCalculator::construct_edges() (src/EdgeCalculator.cpp:561),
+//                    timed as src/ViralQuasispecies.cpp:280-283 times it; writes
+//                    nonedge_overlaps.txt into the cwd like the reference does.
+//   --dump-graph F   after --run: adjacency lists (adj_out, in order) with all Edge fields.
+//   --time-scoring   time only the parallel scoring region (src/EdgeCalculator.cpp:395-423)
+//                    on an already parsed batch.
+//
+// compute_overlap / adj_out are private in the reference headers; the dump TU sees them
+// through "#define private public" (class layout is unchanged, it links against the
+// unmodified objects).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <map>
+#include <set>
+#include <list>
+#include <stack>
+#include <unordered_map>
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <memory>
+#include <deque>
+#include <functional>
+#include <algorithm>
+#include <sys/time.h>
+#include <omp.h>
+
+#define private public
+#include "EdgeCalculator.h"
+#undef private
+
+static double now_s() {
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+static void usage() {
+    std::fprintf(stderr,
+        "ref_driver --overlaps F [--singles F] [--paired1 F --paired2 F] [--threads N]\n"
+        "  [--edge_threshold X] [--ov_threshold X] [--min_overlap_len N] [--min_overlap_perc N]\n"
+        "  [--merge_contigs X] [--mismatch X] [--min_read_len N] [--relax_PE_edges 0|1]\n"
+        "  [--ignore_inclusions 0|1] [--max_ov N]\n"
+        "  [--dump-cands F] [--run] [--dump-graph F] [--time-scoring] [--reps N]\n");
+}
+
+int main(int argc, char** argv) {
+    ProgramSettings ps = ProgramSettings();  // zero-init: the struct has no defaults of its own
+    // defaults of the option table, src/ViralQuasispecies.cpp:52-98
+    ps.max_overlaps = 100000000UL;
+    ps.max_reads = 100000000UL;
+    ps.n_threads = 1;
+    ps.min_clique_size = 4;
+    ps.min_qual = 0.9;
+    ps.min_overlap_perc = 0;
+    ps.min_overlap_len = 150;
+    ps.edge_threshold = 0.99;
+    ps.ov_threshold = 0.9;
+    ps.allow_spaces = false;
+    ps.first_it = true;
+    ps.add_duplicates = false;
+    ps.resolve_orientations = true;
+    ps.mismatch = 0;
+    ps.optimize = true;
+    ps.merge_contigs = 0;
+    ps.remove_tips = true;
+    ps.max_tip_len = 150;
+    ps.store_tips_separately = true;
+    ps.base_path = ".";
+    ps.careful = true;
+    ps.fno = 2;
+    ps.output_dir = "";
+
+    std::string dump_cands, dump_graph;
+    bool do_run = false, do_time = false;
+    int reps = 1;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto need = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", name); std::exit(2); }
+            return argv[++i];
+        };
+        if (a == "--overlaps") ps.overlaps_file = need("--overlaps");
+        else if (a == "--singles") ps.singles_file = need("--singles");
+        else if (a == "--paired1") ps.paired1_file = need("--paired1");
+        else if (a == "--paired2") ps.paired2_file = need("--paired2");
+        else if (a == "--threads") ps.n_threads = std::atoi(need("--threads"));
+        else if (a == "--edge_threshold") ps.edge_threshold = std::atof(need("--edge_threshold"));
+        else if (a == "--ov_threshold") ps.ov_threshold = std::atof(need("--ov_threshold"));
+        else if (a == "--min_overlap_len") ps.min_overlap_len = std::atoi(need("--min_overlap_len"));
+        else if (a == "--min_overlap_perc") ps.min_overlap_perc = std::atoi(need("--min_overlap_perc"));
+        else if (a == "--merge_contigs") ps.merge_contigs = std::atof(need("--merge_contigs"));
+        else if (a == "--mismatch") ps.mismatch = std::atof(need("--mismatch"));
+        else if (a == "--min_read_len") ps.min_read_len = std::atoi(need("--min_read_len"));
+        else if (a == "--relax_PE_edges") ps.relax_PE_edges = std::atoi(need("--relax_PE_edges")) != 0;
+        else if (a == "--ignore_inclusions") ps.ignore_inclusions = std::atoi(need("--ignore_inclusions")) != 0;
+        else if (a == "--allow_spaced_overlaps") ps.allow_spaces = std::atoi(need("--allow_spaced_overlaps")) != 0;
+        else if (a == "--max_ov") ps.max_overlaps = std::strtoul(need("--max_ov"), NULL, 10);
+        else if (a == "--dump-cands") dump_cands = need("--dump-cands");
+        else if (a == "--dump-graph") dump_graph = need("--dump-graph");
+        else if (a == "--run") do_run = true;
+        else if (a == "--time-scoring") do_time = true;
+        else if (a == "--reps") reps = std::atoi(need("--reps"));
+        else { usage(); return 2; }
+    }
+    if (ps.overlaps_file.empty()) { usage(); return 2; }
+
+    double t0 = now_s();
+    std::shared_ptr<FastqStorage> fastq(new FastqStorage(ps));
+    double t_fastq = now_s() - t0;
+    std::shared_ptr<OverlapGraph> graph(new OverlapGraph(fastq->get_readcount(), fastq, ps));
+    for (auto r : fastq->m_read_vec) {
+        node_id_t v = graph->addVertex(r->get_read_id());
+        r->set_vertex_id(true, v);
+    }
+    EdgeCalculator ec(fastq, graph, ps);
+
+    // Parse + pre-filter exactly as src/EdgeCalculator.cpp:581-635 (tab-split branch), keeping
+    // the 1-based line number of every candidate that reaches process_overlaps.
+    std::vector<Overlap> batch;
+    std::vector<unsigned long> batch_line;
+    unsigned long n_lines = 0, n_self = 0, n_lenfiltered = 0, n_percdropped = 0, n_bad = 0;
+    if (!dump_cands.empty() || do_time) {
+        std::ifstream in(ps.overlaps_file.c_str());
+        if (!in.is_open()) { std::fprintf(stderr, "cannot open %s\n", ps.overlaps_file.c_str()); return 1; }
+        std::string line;
+        unsigned long i = 0;
+        while (getline(in, line) && i < ps.max_overlaps) {
+            i++;
+            n_lines++;
+            boost::trim_if(line, boost::is_any_of("\t "));
+            std::vector<std::string> f;
+            if (ps.allow_spaces) {
+                boost::algorithm::split(f, line, boost::is_any_of("\t "), boost::token_compress_on);
+            } else {
+                std::stringstream ss(line);
+                std::string tmp;
+                while (getline(ss, tmp, '\t')) f.push_back(tmp);
+            }
+            if (f.size() != 13) { n_bad++; continue; }
+            Overlap ov(f);
+            if (ov.get_id(1) == ov.get_id(2)) { n_self++; continue; }
+            bool pass = false, dropped = false;
+            if (ov.get_len(1) >= ps.min_overlap_len && ov.get_type(1) == "s" && ov.get_type(2) == "s") {
+                if (ov.get_perc() >= ps.min_overlap_perc) pass = true; else dropped = true;
+            } else if (ov.get_len(1) >= 0.5 * ps.min_overlap_len && ov.get_len(2) >= 0.5 * ps.min_overlap_len
+                       && (ov.get_type(1) == "p" || ov.get_type(2) == "p")) {
+                if (ov.get_perc() >= ps.min_overlap_perc) pass = true; else dropped = true;
+            } else if (ps.relax_PE_edges && ov.get_len(1) + ov.get_len(2) >= ps.min_overlap_len
+                       && (ov.get_type(1) == "p" || ov.get_type(2) == "p")) {
+                if (ov.get_perc() >= ps.min_overlap_perc) pass = true; else dropped = true;
+            } else {
+                n_lenfiltered++;
+            }
+            if (dropped) n_percdropped++;
+            if (pass) { batch.push_back(ov); batch_line.push_back(i); }
+        }
+    }
+
+    if (!dump_cands.empty()) {
+        FILE* fo = std::fopen(dump_cands.c_str(), "w");
+        if (!fo) { std::fprintf(stderr, "cannot write %s\n", dump_cands.c_str()); return 1; }
+        std::fprintf(fo, "#line\tclass\tscore\tmm_rate\tpos1\tpos2\tpos3\tpos4\tv1\tv2\tori1\tori2\tord\tperc\tlen1\tlen2\n");
+        for (size_t k = 0; k < batch.size(); k++) {
+            Edge e = ec.compute_overlap(batch[k]);
+            char cls = 'D';
+            if (e.get_score() > ps.edge_threshold) cls = 'E';
+            else if (e.get_mismatch_rate() != -1 && e.get_mismatch_rate() <= ps.merge_contigs) cls = 'E';
+            else if (e.get_score() > ps.ov_threshold && e.get_mismatch_rate() != -1) cls = 'N';
+            std::fprintf(fo, "%lu\t%c\t%a\t%a\t%d\t%d\t%d\t%d\t%lu\t%lu\t%d\t%d\t%c\t%d\t%d\t%d\n",
+                         batch_line[k], cls, e.get_score(), e.get_mismatch_rate(), e.get_pos(1), e.get_pos(2),
+                         e.get_extra_pos(1), e.get_extra_pos(2), e.get_vertex(1), e.get_vertex(2),
+                         (int)e.get_ori(1), (int)e.get_ori(2), e.get_ord(), e.get_perc(), e.get_len(1), e.get_len(2));
+        }
+        std::fclose(fo);
+    }
+
+    double t_scoring = -1;
+    unsigned long n_edges_t = 0, n_nonedges_t = 0;
+    if (do_time) {
+        // same loop shape as src/EdgeCalculator.cpp:395-423: static omp-for, per-thread vectors
+        // concatenated under critical sections.
+        double best = 1e300;
+        for (int r = 0; r < reps; r++) {
+            std::vector<Edge> edges;
+            std::vector<Overlap> nonedges;
+            double ts = now_s();
+            unsigned int size = batch.size();
+            #pragma omp parallel num_threads(ps.n_threads) shared(batch, edges, nonedges)
+            {
+                std::vector<Edge> e_t;
+                std::vector<Overlap> o_t;
+                #pragma omp for
+                for (unsigned int i = 0; i < size; i++) {
+                    Overlap overlap = batch.at(i);
+                    Edge edge = ec.compute_overlap(overlap);
+                    if (edge.get_score() > ps.edge_threshold) e_t.push_back(edge);
+                    else if (edge.get_mismatch_rate() != -1 && edge.get_mismatch_rate() <= ps.merge_contigs) e_t.push_back(edge);
+                    else if (edge.get_score() > ps.ov_threshold && edge.get_mismatch_rate() != -1) o_t.push_back(overlap);
+                }
+                #pragma omp critical(we)
+                { edges.insert(edges.end(), e_t.begin(), e_t.end()); }
+                #pragma omp critical(wo)
+                { nonedges.insert(nonedges.end(), o_t.begin(), o_t.end()); }
+            }
+            double dt = now_s() - ts;
+            if (dt < best) best = dt;
+            n_edges_t = edges.size();
+            n_nonedges_t = nonedges.size();
+        }
+        t_scoring = best;
+    }
+
+    double t_construct = -1;
+    if (do_run) {
+        double ts = now_s();
+        ec.construct_edges();
+        t_construct = now_s() - ts;
+        if (!dump_graph.empty()) {
+            FILE* fo = std::fopen(dump_graph.c_str(), "w");
+            if (!fo) { std::fprintf(stderr, "cannot write %s\n", dump_graph.c_str()); return 1; }
+            std::fprintf(fo, "#v1\tv2\tscore\tmm_rate\tpos1\tpos2\tpos3\tpos4\tori1\tori2\tord\tperc\tlen1\tlen2\n");
+            for (size_t v = 0; v < graph->adj_out.size(); v++) {
+                for (std::list<Edge>::iterator it = graph->adj_out[v].begin(); it != graph->adj_out[v].end(); ++it) {
+                    std::fprintf(fo, "%lu\t%lu\t%a\t%a\t%d\t%d\t%d\t%d\t%d\t%d\t%c\t%d\t%d\t%d\n",
+                                 it->get_vertex(1), it->get_vertex(2), it->get_score(), it->get_mismatch_rate(),
+                                 it->get_pos(1), it->get_pos(2), it->get_extra_pos(1), it->get_extra_pos(2),
+                                 (int)it->get_ori(1), (int)it->get_ori(2), it->get_ord(), it->get_perc(),
+                                 it->get_len(1), it->get_len(2));
+                }
+            }
+            std::fclose(fo);
+        }
+    }
+
+    std::printf("{\"reads_single\": %u, \"reads_paired\": %u, \"threads\": %u, \"lines\": %lu, \"scored\": %lu, "
+                "\"self\": %lu, \"len_filtered\": %lu, \"perc_dropped\": %lu, \"bad\": %lu, "
+                "\"t_fastq_s\": %.6f, \"t_scoring_s\": %.6f, \"scoring_edges\": %lu, \"scoring_nonedges\": %lu, "
+                "\"t_construct_edges_s\": %.6f, \"graph_edges\": %u, \"dup_count\": %u, \"inclusion_count\": %u}\n",
+                fastq->m_readcount_single, fastq->m_readcount_paired, ps.n_threads, n_lines,
+                (unsigned long)batch.size(), n_self, n_lenfiltered, n_percdropped, n_bad, t_fastq, t_scoring,
+                n_edges_t, n_nonedges_t, t_construct, do_run ? graph->getEdgeCount() : 0u, ec.dup_count,
+                ec.inclusion_count);
+    return 0;
+}
