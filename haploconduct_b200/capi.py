@@ -1,0 +1,176 @@
+"""ctypes binding of the C ABI in include/hc_b200.h (haploconduct_b200/lib/libhc_b200.so).
+
+The binding is deliberately thin: every call goes through the exported ``extern "C"`` symbols, the
+same ones a cgo/JNI/C++ host would bind.  There is no Python or CPU fallback: if the shared
+library is missing or no sm_100 device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import formats as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libhc_b200.so")
+
+# every symbol include/hc_b200.h declares
+EXPORTED = [
+    "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
+    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_device", "hc_overlap_score",
+    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version",
+]
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class HcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("hc_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "%s is missing: build it with `python -m haploconduct_b200.build` (there is no CPU fallback)" % LIB_PATH
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u64, i32, u32, dbl = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_double
+        L.hc_store_create.restype = vp
+        L.hc_store_create.argtypes = [vp, u64, u64, vp, vp, i32, i32]
+        L.hc_store_destroy.restype = None
+        L.hc_store_destroy.argtypes = [vp]
+        for name in ("hc_store_n_reads", "hc_store_n_single", "hc_store_device_bytes"):
+            getattr(L, name).restype = u64
+            getattr(L, name).argtypes = [vp]
+        for name in ("hc_store_n_devices", "hc_store_quality_alphabet"):
+            getattr(L, name).restype = i32
+            getattr(L, name).argtypes = [vp]
+        L.hc_score_batch.restype = i32
+        L.hc_score_batch.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
+        L.hc_score_batch_device.restype = i32
+        L.hc_score_batch_device.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, u64, vp, u64, vp, vp]
+        L.hc_overlap_score.restype = dbl
+        L.hc_overlap_score.argtypes = [ctypes.c_char_p, u32, ctypes.c_char_p, u32, ctypes.c_char_p, ctypes.c_char_p, u32, vp,
+                                       ctypes.POINTER(dbl)]
+        L.hc_phred_to_prob.restype = dbl
+        L.hc_phred_to_prob.argtypes = [i32]
+        L.hc_exp_threshold.restype = dbl
+        L.hc_exp_threshold.argtypes = [dbl]
+        L.hc_device_count.restype = i32
+        L.hc_device_count.argtypes = []
+        L.hc_last_error.restype = ctypes.c_char_p
+        L.hc_version.restype = ctypes.c_char_p
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().hc_last_error().decode()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise HcError(rc, last_error())
+
+
+class Store:
+    """Device-resident read store (hc_store_create / hc_store_destroy)."""
+
+    def __init__(self, rs: F.ReadSet, first_device: int = 0, n_devices: int = 1):
+        L = lib()
+        descs = np.ascontiguousarray(rs.descs)
+        self._h = L.hc_store_create(descs.ctypes.data, rs.n_reads, rs.n_single, rs.bases.ctypes.data, rs.quals.ctypes.data,
+                                    first_device, n_devices)
+        if not self._h:
+            raise HcError(-1, last_error())
+        self.first_device = first_device
+        self.n_devices = n_devices
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().hc_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().hc_store_device_bytes(self._h))
+
+    @property
+    def quality_alphabet(self) -> int:
+        return int(lib().hc_store_quality_alphabet(self._h))
+
+    def score_batch(self, params: np.ndarray, cands: np.ndarray, per_candidate: bool = True, edges_cap: Optional[int] = None,
+                    nonedge_cap: Optional[int] = None):
+        """hc_score_batch on HOST buffers.  Returns (edges, nonedge_idx, per_cand or None, stats)."""
+        L = lib()
+        cands = np.ascontiguousarray(cands)
+        n = len(cands)
+        ecap = n if edges_cap is None else edges_cap
+        ncap = n if nonedge_cap is None else nonedge_cap
+        edges = np.zeros(max(ecap, 1), dtype=F.EDGE)
+        nonedge = np.zeros(max(ncap, 1), dtype=np.uint64)
+        per = np.zeros(n, dtype=F.RESULT) if per_candidate else None
+        ne, nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        stats = np.zeros(1, dtype=F.BATCH_STATS)
+        rc = L.hc_score_batch(self._h, params.ctypes.data, cands.ctypes.data if n else None, n,
+                              per.ctypes.data if per is not None and n else None, edges.ctypes.data, ecap, ctypes.byref(ne),
+                              nonedge.ctypes.data, ncap, ctypes.byref(nn), stats.ctypes.data)
+        if rc != 0:
+            err = HcError(rc, last_error())
+            err.required = (int(ne.value), int(nn.value))
+            raise err
+        return edges[: ne.value], nonedge[: nn.value], per, stats[0]
+
+    def score_batch_device(self, device: int, stream: int, params: np.ndarray, d_cand: int, n: int, d_per_cand: int,
+                           d_edges: int, edges_cap: int, d_nonedge: int, nonedge_cap: int, d_counts: int, want_stats: bool):
+        """hc_score_batch_device on raw DEVICE pointers (e.g. torch tensors' data_ptr())."""
+        stats = np.zeros(1, dtype=F.BATCH_STATS) if want_stats else None
+        rc = lib().hc_score_batch_device(self._h, device, stream or None, params.ctypes.data, d_cand or None, n,
+                                         d_per_cand or None, d_edges, edges_cap, d_nonedge, nonedge_cap, d_counts,
+                                         stats.ctypes.data if want_stats else None)
+        _check(rc)
+        return stats[0] if want_stats else None
+
+
+def overlap_score(seq1: str, seq2: str, q1: str, q2: str, pos: int, params: np.ndarray) -> Tuple[float, float]:
+    mm = ctypes.c_double(0)
+    s = lib().hc_overlap_score(seq1.encode(), len(seq1), seq2.encode(), len(seq2), q1.encode(), q2.encode(), pos,
+                               params.ctypes.data, ctypes.byref(mm))
+    if s < 0:
+        raise HcError(-1, last_error())
+    return s, mm.value
+
+
+def phred_to_prob(q: int) -> float:
+    return lib().hc_phred_to_prob(q)
+
+
+def exp_threshold(thr: float) -> float:
+    return lib().hc_exp_threshold(thr)
+
+
+def device_count() -> int:
+    return lib().hc_device_count()

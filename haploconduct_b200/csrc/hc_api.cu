@@ -1,0 +1,551 @@
+// hc_api.cu -- the C ABI of include/hc_b200.h: read-store packing / replication, workspace
+// management and the batch entry points.  Host code here is plumbing; the arithmetic lives in
+// hc_kernels.cu (device) and hc_tables.cpp (score tables, host libm).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../include/hc_b200.h"
+#include "hc_layout.h"
+#include "hc_tables.h"
+#include "hc_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            return fail(HC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
+        }                                                                                                \
+    } while (0)
+
+struct DevCtx {
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_per_sm = 0;
+    // store planes
+    uint8_t* qual = nullptr;
+    uint32_t* base2 = nullptr;
+    uint32_t* nmask = nullptr;
+    hc_rdesc* rdesc = nullptr;
+    // tables
+    uint32_t* fx_table = nullptr;
+    double* dbl_table = nullptr;
+    bool tables_valid = false;
+    double tables_mismatch = 0.0;
+    bool has_void = false;
+    // workspace (grown on demand)
+    uint64_t ws_cap = 0;
+    hc_score16* tmp = nullptr;
+    uint8_t* cls = nullptr;
+    uint32_t* flagged = nullptr;
+    uint32_t* blockcounts = nullptr;
+    unsigned long long* counters = nullptr;
+    // staging for the host-buffer path
+    uint64_t st_cap = 0;
+    hc_candidate* d_cand = nullptr;
+    hc_edge* d_edges = nullptr;
+    uint64_t* d_nonedge = nullptr;
+    uint64_t pc_cap = 0;
+    hc_result* d_per_cand = nullptr;
+    uint64_t* d_counts = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    hc_launch_cfg cfg{};
+};
+
+}  // namespace
+
+struct hc_store {
+    uint64_t n_reads = 0, n_single = 0;
+    uint64_t total_positions = 0;
+    int ncodes = 0;
+    int code_to_q[HC_MAX_CODES + 1];
+    int q_to_code[256];
+    std::vector<DevCtx> devs;
+    hc_tables tables;
+    bool tables_built = false;
+    double tables_mismatch = 0.0;
+    std::mutex mu;
+};
+
+namespace {
+
+void free_ctx(DevCtx& d) {
+    if (d.device < 0) return;
+    cudaSetDevice(d.device);
+    cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc);
+    cudaFree(d.fx_table); cudaFree(d.dbl_table);
+    cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts); cudaFree(d.counters);
+    cudaFree(d.d_cand); cudaFree(d.d_edges); cudaFree(d.d_nonedge); cudaFree(d.d_per_cand); cudaFree(d.d_counts);
+    for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    d = DevCtx();
+}
+
+inline int base_code(unsigned char c) {
+    switch (c) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        case 'N': return 4;
+        default: return -1;
+    }
+}
+
+int ensure_tables(hc_store* s, DevCtx& d, double mismatch, cudaStream_t st) {
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->tables_built || s->tables_mismatch != mismatch) {
+            hc_build_tables(s->code_to_q, s->ncodes, mismatch, &s->tables);
+            s->tables_built = true;
+            s->tables_mismatch = mismatch;
+            for (auto& dd : s->devs) dd.tables_valid = false;
+        }
+    }
+    if (d.tables_valid && d.tables_mismatch == mismatch) return HC_OK;
+    // synchronous upload: tables change only when ps.mismatch changes (it never does in the drivers)
+    CU(cudaStreamSynchronize(st));
+    if (!d.fx_table) CU(cudaMalloc(&d.fx_table, s->tables.fx.size() * sizeof(uint32_t)));
+    if (!d.dbl_table) CU(cudaMalloc(&d.dbl_table, s->tables.dbl.size() * sizeof(double)));
+    CU(cudaMemcpy(d.fx_table, s->tables.fx.data(), s->tables.fx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.dbl_table, s->tables.dbl.data(), s->tables.dbl.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.tables_valid = true;
+    d.tables_mismatch = mismatch;
+    d.has_void = s->tables.has_void;
+    return HC_OK;
+}
+
+int ensure_workspace(DevCtx& d, uint64_t n) {
+    if (n <= d.ws_cap && d.counters) return HC_OK;
+    uint64_t cap = std::max<uint64_t>(n, 1024);
+    cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts);
+    d.tmp = nullptr; d.cls = nullptr; d.flagged = nullptr; d.blockcounts = nullptr;
+    d.ws_cap = 0;
+    CU(cudaMalloc(&d.tmp, cap * sizeof(hc_score16)));
+    CU(cudaMalloc(&d.cls, cap));
+    CU(cudaMalloc(&d.flagged, cap * sizeof(uint32_t)));
+    const uint64_t nb = hc_compact_blocks(cap) + 1;
+    CU(cudaMalloc(&d.blockcounts, nb * 2 * sizeof(uint32_t) + 8 + nb * 2 * sizeof(uint64_t)));
+    if (!d.counters) CU(cudaMalloc(&d.counters, HC_CNT_N * sizeof(unsigned long long)));
+    d.ws_cap = cap;
+    return HC_OK;
+}
+
+DevCtx* find_ctx(hc_store* s, int device) {
+    for (auto& d : s->devs) if (d.device == device) return &d;
+    return nullptr;
+}
+
+// Enqueue the whole scoring pipeline for one shard on (d, st).
+int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, const hc_candidate* d_cand, uint64_t n,
+                  hc_result* d_per_cand, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge, uint64_t nonedge_cap,
+                  uint64_t* d_counts, uint64_t cand_offset, cudaEvent_t k0, cudaEvent_t k1, uint32_t* launches) {
+    if (n > 0xffffffffull) return fail(HC_ERR_ARG, "more than 2^32-1 candidates in one device batch");
+    int rc = ensure_tables(s, d, p->mismatch, st);
+    if (rc != HC_OK) return rc;
+    rc = ensure_workspace(d, n);
+    if (rc != HC_OK) return rc;
+    int mono = 1;
+    hc_kparams P;
+    memset(&P, 0, sizeof(P));
+    P.qual = d.qual; P.base2 = d.base2; P.nmask = d.nmask; P.rdesc = d.rdesc;
+    P.n_reads = (uint32_t)s->n_reads; P.n_single = (uint32_t)s->n_single;
+    P.fx_table = d.fx_table; P.dbl_table = d.dbl_table; P.ncodes = (uint32_t)s->ncodes; P.has_void = d.has_void ? 1u : 0u;
+    P.cand = d_cand; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
+    P.counters = d.counters;
+    P.t_edge = hc_tables_exp_threshold(p->edge_threshold, &mono);
+    if (!mono) return fail(HC_ERR_ARG, "host exp() is not monotone around edge_threshold");
+    P.t_ov = hc_tables_exp_threshold(p->ov_threshold, &mono);
+    if (!mono) return fail(HC_ERR_ARG, "host exp() is not monotone around ov_threshold");
+    P.merge_contigs = p->merge_contigs;
+    P.min_read_len = p->min_read_len;
+    P.zero_above_edge = 0.0 > p->edge_threshold;
+    P.zero_above_ov = 0.0 > p->ov_threshold;
+    P.exact_edges = (p->flags & HC_FLAG_EXACT_EDGE_SCORES) ? 1u : 0u;
+    CU(cudaMemsetAsync(d.counters, 0, HC_CNT_N * sizeof(unsigned long long), st));
+    if (k0) CU(cudaEventRecord(k0, st));
+    uint32_t nl = 0;
+    if (n > 0) {
+        hc_launch_cfg cfg = d.cfg;
+        const uint64_t ntiles = (n + 31) / 32;
+        const uint64_t warps_per_block = cfg.threads / 32;
+        const uint64_t need_blocks = (ntiles + warps_per_block - 1) / warps_per_block;
+        if ((uint64_t)cfg.blocks > need_blocks) cfg.blocks = (int)need_blocks;
+        CU(hc_launch_score(P, cfg, st));
+        CU(hc_launch_exact(P, st));
+        nl += 2;
+    }
+    CU(hc_launch_compact(P, d_edges, edges_cap, d_nonedge, nonedge_cap, d.blockcounts, cand_offset, st));
+    nl += n > 0 ? 3 : 1;
+    if (k1) CU(cudaEventRecord(k1, st));
+    // {n_edges, n_nonedges, n_exact} are contiguous in the counter block; [3] = invalid candidates
+    CU(cudaMemcpyAsync(d_counts, d.counters + HC_CNT_EDGES, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d_counts + 3, d.counters + HC_CNT_ERRORS, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    if (launches) *launches = nl;
+    return HC_OK;
+}
+
+int read_stats(DevCtx& d, uint64_t n, hc_batch_stats* stats, cudaEvent_t k0, cudaEvent_t k1) {
+    unsigned long long h[HC_CNT_N];
+    CU(cudaMemcpy(h, d.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    if (stats) {
+        stats->n_candidates += n;
+        stats->n_edges += h[HC_CNT_EDGES];
+        stats->n_nonedges += h[HC_CNT_NONEDGES];
+        stats->n_exact += h[HC_CNT_EXACT];
+        stats->n_windows += h[HC_CNT_WINDOWS];
+        stats->n_positions += h[HC_CNT_POSITIONS];
+        stats->algorithmic_bytes += h[HC_CNT_ALGBYTES];
+        float ms = 0;
+        if (k0 && k1 && cudaEventElapsedTime(&ms, k0, k1) == cudaSuccess) stats->kernel_ms = std::max(stats->kernel_ms, ms);
+    }
+    if (h[HC_CNT_ERRORS]) {
+        return fail(HC_ERR_ARG, std::to_string(h[HC_CNT_ERRORS]) +
+                                    " candidate(s) with an invalid read index, a self overlap, or ORD not in {1,2} "
+                                    "for a paired-paired overlap (the reference asserts, src/EdgeCalculator.cpp:184,369)");
+    }
+    return HC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hc_last_error(void) { return g_err.c_str(); }
+const char* hc_version(void) { return "haploconduct_b200 0.1 (sm_100a)"; }
+
+int hc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+double hc_phred_to_prob(int phred) { return hc_tables_phred_to_prob(phred); }
+double hc_exp_threshold(double threshold) { return hc_tables_exp_threshold(threshold, nullptr); }
+
+uint64_t hc_store_n_reads(const hc_store* s) { return s ? s->n_reads : 0; }
+uint64_t hc_store_n_single(const hc_store* s) { return s ? s->n_single : 0; }
+int hc_store_n_devices(const hc_store* s) { return s ? (int)s->devs.size() : 0; }
+int hc_store_quality_alphabet(const hc_store* s) { return s ? s->ncodes : 0; }
+uint64_t hc_store_device_bytes(const hc_store* s) {
+    if (!s) return 0;
+    return s->total_positions + s->total_positions / 4 + s->total_positions / 8 + s->n_reads * sizeof(hc_rdesc);
+}
+
+void hc_store_destroy(hc_store* s) {
+    if (!s) return;
+    for (auto& d : s->devs) free_ctx(d);
+    delete s;
+}
+
+hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t n_single, const char* bases,
+                          const char* quals, int first_device, int n_devices) {
+    if (!reads || !bases || !quals || n_reads == 0 || n_single > n_reads || n_devices < 1 || first_device < 0) {
+        fail(HC_ERR_ARG, "hc_store_create: bad argument");
+        return nullptr;
+    }
+    if (n_reads >= 0xffffffffull) { fail(HC_ERR_ARG, "hc_store_create: too many reads"); return nullptr; }
+    int ndev = hc_device_count();
+    if (ndev == 0) { fail(HC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)"); return nullptr; }
+    if (first_device + n_devices > ndev) { fail(HC_ERR_ARG, "hc_store_create: device range exceeds the devices present"); return nullptr; }
+
+    hc_store* s = new hc_store();
+    s->n_reads = n_reads;
+    s->n_single = n_single;
+    // ---- pass 1: validate, quality alphabet, slot layout
+    bool seen[256];
+    memset(seen, 0, sizeof(seen));
+    std::vector<hc_rdesc> rd(n_reads);
+    uint64_t pos = 0;   // in positions
+    int bad = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const int paired = reads[r].seq_len[1] > 0;
+        if ((r < n_single) == (paired != 0)) bad = 1;       // singles first, then pairs (src/FastqStorage.h:88-97)
+        if (reads[r].seq_len[0] == 0) bad = 2;              // empty sequence (src/FastqStorage.cpp:143-146)
+        for (int m = 0; m < 2; m++) {
+            const uint32_t len = reads[r].seq_len[m];
+            if (len > HC_LEN_MASK / 2) bad = 3;
+            rd[r].slot16[m] = (uint32_t)(pos >> 4);
+            rd[r].len[m] = len;
+            if (len) pos += 2ull * hc_slot_size(len);
+            if ((pos >> 4) > 0xffffffffull) bad = 3;
+        }
+    }
+    if (bad) {
+        fail(bad == 1 ? HC_ERR_ARG : HC_ERR_INPUT,
+             bad == 1 ? "hc_store_create: reads must be ordered singles first, then pairs"
+                      : (bad == 2 ? "hc_store_create: read with an empty sequence" : "hc_store_create: store too large"));
+        delete s;
+        return nullptr;
+    }
+    const uint64_t total = (pos + 63) & ~63ull;
+    s->total_positions = total;
+    int input_err = 0;
+#pragma omp parallel
+    {
+        bool lseen[256];
+        memset(lseen, 0, sizeof(lseen));
+        int lerr = 0;
+#pragma omp for schedule(static)
+        for (int64_t r = 0; r < (int64_t)n_reads; r++) {
+            for (int m = 0; m < 2; m++) {
+                const uint32_t len = reads[r].seq_len[m];
+                const unsigned char* b = (const unsigned char*)bases + reads[r].seq_off[m];
+                const unsigned char* q = (const unsigned char*)quals + reads[r].seq_off[m];
+                for (uint32_t i = 0; i < len; i++) {
+                    if (base_code(b[i]) < 0) lerr = 1;
+                    if (q[i] < 33 || q[i] > 33 + 93) lerr = 2;
+                    lseen[q[i]] = true;
+                }
+            }
+        }
+#pragma omp critical
+        {
+            for (int k = 0; k < 256; k++) if (lseen[k]) seen[k] = true;
+            if (lerr) input_err = lerr;
+        }
+    }
+    if (input_err) {
+        fail(HC_ERR_INPUT, input_err == 1
+                               ? "invalid nucleotide (only upper-case A,C,G,T,N are accepted; the reference asserts in "
+                                 "EdgeCalculator::score, src/EdgeCalculator.cpp:29-30)"
+                               : "quality character outside '!'..'~' (Phred 0..93; src/EdgeCalculator.cpp:61,93-98)");
+        delete s;
+        return nullptr;
+    }
+    memset(s->q_to_code, 0, sizeof(s->q_to_code));
+    s->ncodes = 0;
+    s->code_to_q[0] = -1;
+    for (int c = 33; c <= 33 + 93; c++) {
+        if (seen[c]) {
+            s->ncodes++;
+            s->code_to_q[s->ncodes] = c - 33;
+            s->q_to_code[c] = s->ncodes;
+        }
+    }
+    // ---- pass 2: pack both strands
+    std::vector<uint8_t> hq;
+    std::vector<uint32_t> hb, hn;
+    try {
+        hq.assign(total, 0);
+        hb.assign(total / 16, 0);
+        hn.assign(total / 32, 0);
+    } catch (...) {
+        fail(HC_ERR_NOMEM, "hc_store_create: host staging allocation failed");
+        delete s;
+        return nullptr;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < (int64_t)n_reads; r++) {
+        for (int m = 0; m < 2; m++) {
+            const uint32_t len = reads[r].seq_len[m];
+            if (!len) continue;
+            const unsigned char* b = (const unsigned char*)bases + reads[r].seq_off[m];
+            const unsigned char* q = (const unsigned char*)quals + reads[r].seq_off[m];
+            const uint64_t fwd = 16ull * rd[r].slot16[m], rev = fwd + hc_slot_size(len);
+            bool hasN = false;
+            for (uint32_t i = 0; i < len; i++) {
+                const int bc = base_code(b[i]);
+                const uint64_t pf = fwd + i, pr = rev + (len - 1 - i);
+                if (bc == 4) {
+                    hasN = true;          // N: code 0 quality (contributes nothing), base bits 0, mask bit set
+                    hn[pf >> 5] |= 1u << (pf & 31);
+                    hn[pr >> 5] |= 1u << (pr & 31);
+                } else {
+                    const uint8_t code = (uint8_t)s->q_to_code[q[i]];
+                    hq[pf] = code;
+                    hq[pr] = code;                                   // reversed qualities, src/Read.h:187-201
+                    hb[pf >> 4] |= (uint32_t)bc << (2 * (pf & 15));
+                    hb[pr >> 4] |= (uint32_t)(3 - bc) << (2 * (pr & 15));   // complement, src/Types.h:109-129
+                }
+            }
+            if (hasN) rd[r].len[m] |= HC_HASN_BIT;
+        }
+    }
+    // ---- replicate on the devices
+    s->devs.resize(n_devices);
+    for (int k = 0; k < n_devices; k++) {
+        DevCtx& d = s->devs[k];
+        d.device = first_device + k;
+        cudaError_t e = cudaSetDevice(d.device);
+        cudaDeviceProp prop;
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.device);
+        if (e == cudaSuccess && prop.major < 10) {
+            fail(HC_ERR_CUDA, "device is not sm_100 class (this library ships sm_100a code only)");
+            hc_store_destroy(s);
+            return nullptr;
+        }
+        if (e == cudaSuccess) {
+            d.sm_count = prop.multiProcessorCount;
+            d.smem_per_sm = prop.sharedMemPerMultiprocessor;
+            e = hc_score_occupancy((uint32_t)s->ncodes, d.sm_count, d.smem_per_sm, &d.cfg);
+        }
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
+        if (e == cudaSuccess) e = cudaMalloc(&d.qual, total + 64);
+        if (e == cudaSuccess) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d.rdesc, n_reads * sizeof(hc_rdesc));
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_counts, 4 * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMemset(d.qual + total, 0, 64);
+        if (e == cudaSuccess) e = cudaMemset(d.base2 + total / 16, 0, 64);
+        if (e == cudaSuccess) e = cudaMemset(d.nmask + total / 32, 0, 64);
+        if (e == cudaSuccess) e = cudaMemcpy(d.qual, hq.data(), total, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d.base2, hb.data(), total / 16 * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d.nmask, hn.data(), total / 32 * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d.rdesc, rd.data(), n_reads * sizeof(hc_rdesc), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA,
+                 std::string("hc_store_create: ") + cudaGetErrorString(e));
+            hc_store_destroy(s);
+            return nullptr;
+        }
+    }
+    return s;
+}
+
+int hc_score_batch_device(hc_store* s, int device, void* stream, const hc_params* p, const hc_candidate* d_cand, uint64_t n,
+                          hc_result* d_per_cand, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge_idx,
+                          uint64_t nonedge_cap, uint64_t* d_counts, hc_batch_stats* stats) {
+    if (!s || !p || !d_counts || (n && !d_cand)) return fail(HC_ERR_ARG, "hc_score_batch_device: NULL argument");
+    DevCtx* d = find_ctx(s, device);
+    if (!d) return fail(HC_ERR_ARG, "hc_score_batch_device: the store has no replica on this device");
+    CU(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t nl = 0;
+    int rc = enqueue_batch(s, *d, st, p, d_cand, n, d_per_cand, d_edges, edges_cap, d_nonedge_idx, nonedge_cap, d_counts, 0,
+                           stats ? d->ev[0] : nullptr, stats ? d->ev[1] : nullptr, &nl);
+    if (rc != HC_OK) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        CU(cudaStreamSynchronize(st));
+        rc = read_stats(*d, n, stats, d->ev[0], d->ev[1]);
+        stats->total_ms = stats->kernel_ms;
+        stats->kernel_launches = nl;
+    }
+    return rc;
+}
+
+int hc_score_batch(hc_store* s, const hc_params* p, const hc_candidate* cand, uint64_t n, hc_result* per_cand,
+                   hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
+                   uint64_t* n_nonedges, hc_batch_stats* stats) {
+    if (!s || !p || !n_edges || !n_nonedges || (n && !cand)) return fail(HC_ERR_ARG, "hc_score_batch: NULL argument");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    *n_edges = 0;
+    *n_nonedges = 0;
+    const int G = (int)s->devs.size();
+    std::vector<uint64_t> lo(G + 1);
+    for (int g = 0; g <= G; g++) lo[g] = n * (uint64_t)g / (uint64_t)G;   // contiguous index ranges
+    uint32_t launches = 0;
+    // phase 1: enqueue everything on every device
+    for (int g = 0; g < G; g++) {
+        DevCtx& d = s->devs[g];
+        const uint64_t m = lo[g + 1] - lo[g];
+        CU(cudaSetDevice(d.device));
+        if (m > d.st_cap) {
+            cudaFree(d.d_cand); cudaFree(d.d_edges); cudaFree(d.d_nonedge);
+            d.d_cand = nullptr; d.d_edges = nullptr; d.d_nonedge = nullptr; d.st_cap = 0;
+            CU(cudaMalloc(&d.d_cand, m * sizeof(hc_candidate)));
+            CU(cudaMalloc(&d.d_edges, m * sizeof(hc_edge)));
+            CU(cudaMalloc(&d.d_nonedge, m * sizeof(uint64_t)));
+            d.st_cap = m;
+        }
+        if (per_cand && m > d.pc_cap) {
+            cudaFree(d.d_per_cand);
+            d.d_per_cand = nullptr; d.pc_cap = 0;
+            CU(cudaMalloc(&d.d_per_cand, m * sizeof(hc_result)));
+            d.pc_cap = m;
+        }
+        CU(cudaEventRecord(d.ev[2], d.stream));
+        if (m) CU(cudaMemcpyAsync(d.d_cand, cand + lo[g], m * sizeof(hc_candidate), cudaMemcpyHostToDevice, d.stream));
+        uint32_t nl = 0;
+        int rc = enqueue_batch(s, d, d.stream, p, d.d_cand, m, per_cand ? d.d_per_cand : nullptr, d.d_edges, d.st_cap,
+                               d.d_nonedge, d.st_cap, d.d_counts, lo[g], d.ev[0], d.ev[1], &nl);
+        if (rc != HC_OK) return rc;
+        launches += nl;
+        if (per_cand && m)
+            CU(cudaMemcpyAsync(per_cand + lo[g], d.d_per_cand, m * sizeof(hc_result), cudaMemcpyDeviceToHost, d.stream));
+    }
+    // phase 2: gather in rank order = input order
+    uint64_t te = 0, tn = 0;
+    int result = HC_OK;
+    for (int g = 0; g < G; g++) {
+        DevCtx& d = s->devs[g];
+        const uint64_t m = lo[g + 1] - lo[g];
+        CU(cudaSetDevice(d.device));
+        uint64_t hc[4];
+        CU(cudaMemcpyAsync(hc, d.d_counts, sizeof(hc), cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaStreamSynchronize(d.stream));
+        int rc = read_stats(d, m, stats, d.ev[0], d.ev[1]);
+        if (rc != HC_OK) result = rc;
+        if (te + hc[0] <= edges_cap && hc[0])
+            CU(cudaMemcpyAsync(edges + te, d.d_edges, hc[0] * sizeof(hc_edge), cudaMemcpyDeviceToHost, d.stream));
+        if (tn + hc[1] <= nonedge_cap && hc[1])
+            CU(cudaMemcpyAsync(nonedge_idx + tn, d.d_nonedge, hc[1] * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
+        CU(cudaEventRecord(d.ev[3], d.stream));
+        te += hc[0];
+        tn += hc[1];
+    }
+    float total_ms = 0;
+    for (int g = 0; g < G; g++) {
+        DevCtx& d = s->devs[g];
+        CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.stream));
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]) == cudaSuccess) total_ms = std::max(total_ms, ms);
+    }
+    *n_edges = te;
+    *n_nonedges = tn;
+    if (stats) { stats->total_ms = total_ms; stats->kernel_launches = launches; }
+    if (result != HC_OK) return result;
+    if (te > edges_cap || tn > nonedge_cap)
+        return fail(HC_ERR_CAPACITY, "hc_score_batch: output buffer too small (required sizes returned in n_edges/n_nonedges)");
+    return HC_OK;
+}
+
+double hc_overlap_score(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,
+                        const char* qual2, uint32_t pos, const hc_params* p, double* mismatch_rate) {
+    if (!seq1 || !seq2 || !qual1 || !qual2 || !p || len1 == 0 || len2 == 0) {
+        fail(HC_ERR_ARG, "hc_overlap_score: bad argument");
+        return -1;
+    }
+    std::string b(seq1, len1), q(qual1, len1);
+    b.append(seq2, len2);
+    q.append(qual2, len2);
+    hc_read_desc rd[2];
+    memset(rd, 0, sizeof(rd));
+    rd[0].seq_off[0] = 0; rd[0].seq_len[0] = len1;
+    rd[1].seq_off[0] = len1; rd[1].seq_len[0] = len2;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    hc_store* s = hc_store_create(rd, 2, 2, b.data(), q.data(), dev, 1);
+    if (!s) return -1;
+    hc_candidate c;
+    memset(&c, 0, sizeof(c));
+    c.idx1 = 0; c.idx2 = 1; c.pos1 = pos; c.ord = '-'; c.ori1 = 1; c.ori2 = 1; c.type1 = 's'; c.type2 = 's';
+    hc_result r;
+    hc_edge e;
+    uint64_t ne = 0, nn = 0, ni = 0;
+    int rc = hc_score_batch(s, p, &c, 1, &r, &e, 1, &ne, &ni, 1, &nn, nullptr);
+    hc_store_destroy(s);
+    if (rc != HC_OK) return -1;
+    if (mismatch_rate) *mismatch_rate = r.mismatch_rate;
+    return r.score;
+}
+
+}  // extern "C"

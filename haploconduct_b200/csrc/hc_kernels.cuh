@@ -1,0 +1,79 @@
+// hc_kernels.cuh -- kernel-side declarations shared by hc_kernels.cu and hc_api.cu
+#ifndef HC_KERNELS_CUH_
+#define HC_KERNELS_CUH_
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/hc_b200.h"
+#include "hc_layout.h"
+
+#define HC_WARPS_MAX 12
+#define HC_PARTMAX 512u          // chunk partials per warp round (x 8 B = 4 KB of shared memory)
+#define HC_BIG_CHUNKS 64u        // candidates with >= this many chunks are scored warp-cooperatively
+#define HC_WINSLOTS 64u          // 2 windows x 32 candidates
+// per-warp scratch: partials + window descriptors (16 B + 8 B per slot) + head bitmap
+#define HC_WARP_SCRATCH (HC_PARTMAX * 8u + HC_WINSLOTS * 16u + HC_WINSLOTS * 8u + (HC_PARTMAX / 32u) * 4u)
+
+struct hc_score16 {   // per-candidate scratch record: what the ordered compaction needs
+    double score;
+    double mismatch_rate;
+};
+
+struct hc_kparams {
+    // read store planes (one replica)
+    const uint8_t* qual;
+    const uint32_t* base2;
+    const uint32_t* nmask;
+    const hc_rdesc* rdesc;
+    uint32_t n_reads;
+    uint32_t n_single;
+    // tables
+    const uint32_t* fx_table;   // (ncodes+1)*256 entries
+    const double* dbl_table;    // (ncodes+1)^2*2 entries
+    uint32_t ncodes;
+    uint32_t has_void;
+    // batch
+    const hc_candidate* cand;
+    uint64_t n;
+    hc_score16* tmp;
+    uint8_t* cls;
+    hc_result* per_cand;        // nullable
+    uint32_t* flagged;          // candidate indices that need the reference-order pass
+    unsigned long long* counters;  // see HC_CNT_*
+    // decisions (src/EdgeCalculator.cpp:404-413, thresholds moved into log space on the host)
+    double t_edge;              // smallest mean with exp(mean) > edge_threshold
+    double t_ov;                // smallest mean with exp(mean) > ov_threshold
+    double merge_contigs;
+    uint32_t min_read_len;
+    uint32_t zero_above_edge;   // 0 > edge_threshold ?
+    uint32_t zero_above_ov;     // 0 > ov_threshold ?
+    uint32_t exact_edges;       // HC_FLAG_EXACT_EDGE_SCORES
+};
+
+enum {
+    HC_CNT_FLAGGED = 0,   // number of entries in flagged[]
+    HC_CNT_WINDOWS,
+    HC_CNT_POSITIONS,
+    HC_CNT_ALGBYTES,
+    HC_CNT_ERRORS,        // candidates with invalid indices / ord
+    HC_CNT_EDGES,         // written by the compaction
+    HC_CNT_NONEDGES,
+    HC_CNT_EXACT,
+    HC_CNT_N
+};
+
+struct hc_launch_cfg {
+    int blocks;
+    int threads;
+    size_t smem;
+};
+
+// host-callable launchers (hc_kernels.cu)
+cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaStream_t st);
+cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st);
+cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge,
+                              uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, cudaStream_t st);
+cudaError_t hc_score_occupancy(uint32_t ncodes, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg);
+uint32_t hc_compact_blocks(uint64_t n);
+
+#endif

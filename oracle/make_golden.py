@@ -1,0 +1,85 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref/ref_driver, built
+from /root/reference/src by oracle/Makefile) -- run in the build container only:
+
+    python -m oracle.make_golden
+
+Each fixture holds the reads, the candidates, the parameters and what the reference produced:
+per-candidate Edge fields + class (EdgeCalculator::compute_overlap, src/EdgeCalculator.cpp:143-385,
+404-413, one thread, input order), the adjacency lists after construct_edges() (:561-666) and the
+nonedge_overlaps.txt lines.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from haploconduct_b200 import formats as F, workloads as W  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+
+def run_case(name: str, rs: F.ReadSet, cands: np.ndarray, ps: dict) -> None:
+    d = tempfile.mkdtemp(prefix="hc_golden_")
+    F.write_fastq_set(rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    F.write_overlaps(d + "/ov.txt", cands, rs.ids)
+    kw = dict(singles=d + "/s.fastq" if rs.n_single else None,
+              paired1=d + "/p1.fastq" if rs.n_reads > rs.n_single else None,
+              paired2=d + "/p2.fastq" if rs.n_reads > rs.n_single else None)
+    out = O.run_ref(d, d + "/ov.txt", dump_cands=True, run=True, dump_graph=True, threads=1, **kw, **ps)
+    pre = F.prefilter(cands, ps.get("min_overlap_len", 150), ps.get("min_overlap_perc", 0), ps.get("relax_PE_edges", False))
+    assert int((pre == 1).sum()) == len(out["cands"]), (int((pre == 1).sum()), len(out["cands"]))
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        ids=rs.ids, descs=rs.descs, bases=rs.bases, quals=rs.quals, n_single=np.int64(rs.n_single), cands=cands,
+        ps_keys=np.array(sorted(ps.keys())), ps_vals=np.array([float(ps[k]) for k in sorted(ps.keys())]),
+        ref_cands=out["cands"], ref_graph=out["graph"], ref_nonedge=np.array(out.get("nonedge_lines", []), dtype=object).astype(str),
+        ref_counts=np.array([out["graph_edges"], out["dup_count"], out["inclusion_count"]], dtype=np.int64),
+    )
+    cls = np.bincount(out["cands"]["cls"], minlength=3)
+    print("%-28s reads=%d cands=%d scored=%d  discard/edge/nonedge=%s graph_edges=%d" %
+          (name, rs.n_reads, len(cands), len(out["cands"]), cls.tolist(), out["graph_edges"]))
+
+
+def main() -> None:
+    assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    os.makedirs(GOLDEN, exist_ok=True)
+    # C1: savage/example, stage-a parameters (savage.py:384-385, savage/README.md:303: -m 200)
+    R = REF + "/savage/example/input_fas/"
+    full = F.load_fastq_set(R + "singles.fastq", R + "paired1.fastq", R + "paired2.fastq")
+    sub = full.subset(list(range(0, 260)) + list(range(2000, 2120)))
+    c = W.seed_candidates(sub, k=24, max_cands=6000, seed=3)
+    run_case("c1_savage_example_stage_a", sub, c, dict(edge_threshold=0.97, min_overlap_len=200))
+    # C2: polyte/example, all reads as singles (polyte.py:280-288), iteration-1 parameters (polyte.py:599-602)
+    Rp = REF + "/polyte/example/input/"
+    fw = F._read_fastq_records(Rp + "forward.fastq")[:220]
+    rv = F._read_fastq_records(Rp + "reverse.fastq")[:220]
+    singles = [(i, s.upper(), q) for i, (_, s, q) in enumerate(fw + rv)]
+    rs2 = F.ReadSet.from_lists(singles, [])
+    c2 = W.seed_candidates(rs2, k=20, max_cands=6000, seed=4)
+    run_case("c2_polyte_example_it1", rs2, c2, dict(edge_threshold=0.95, min_overlap_len=126))
+    # synthetic: every TYPE x ORI x ORD case, junk candidates, N and Q=0 bases
+    ss = W.synth_readset(160, 160, seed=20261017, n_rate=0.002)
+    c3 = W.geometry_candidates(ss, 5000, seed=5)
+    run_case("synth_all_types", ss.rs, c3, dict(edge_threshold=0.97, min_overlap_len=60))
+    # stage-c like: contigs as singles with wide qualities, min_read_len, merge_contigs > 0
+    ss4 = W.synth_readset(120, 0, genome_len=6000, read_len=(400, 1800), qmax=93, q_lo=30, seed=20261019, n_rate=0.0)
+    c4 = W.geometry_candidates(ss4, 2500, seed=6, min_ov=60)
+    run_case("synth_stage_c_contigs", ss4.rs, c4,
+             dict(edge_threshold=0.995, min_overlap_len=100, min_read_len=500, merge_contigs=0.01))
+    # non-default ps.mismatch (void overlaps) and relaxed paired-end filter
+    ss5 = W.synth_readset(60, 120, seed=99, n_rate=0.001)
+    c5 = W.geometry_candidates(ss5, 2500, seed=8)
+    run_case("synth_mismatch_void", ss5.rs, c5, dict(edge_threshold=0.9, ov_threshold=0.5, min_overlap_len=120, mismatch=0.01,
+                                                      relax_PE_edges=True))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,51 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/hc_b200.h declares; the
+host-only entry points work without a GPU; the compute entry points fail loudly without one."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from haploconduct_b200 import capi, formats as F
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(built_lib, s), "libhc_b200.so does not export " + s
+    assert sorted(capi.EXPORTED) == syms
+
+
+def test_struct_sizes_match_header():
+    assert F.CANDIDATE.itemsize == 32 and F.RESULT.itemsize == 48 and F.EDGE.itemsize == 32 and F.READ_DESC.itemsize == 24
+
+
+def test_host_only_entry_points(built_lib):
+    for q in (0, 1, 2, 20, 41, 93):
+        assert capi.phred_to_prob(q) == O.lib().hco_phred_to_prob(q)
+    import math
+    for thr in (0.9, 0.95, 0.97, 0.99, 0.995, 0.5):
+        x = capi.exp_threshold(thr)
+        assert math.exp(x) > thr and not (math.exp(np.nextafter(x, -np.inf)) > thr)
+    assert capi.exp_threshold(1.0) > 0.0          # exp(mean) > 1 is impossible for mean <= 0 (POLYTE later iterations)
+    assert capi.exp_threshold(-0.5) == -np.inf
+    assert b"sm_100a" in built_lib.hc_version()
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    rs = F.ReadSet.from_lists([(0, "ACGT", "IIII"), (1, "ACGT", "IIII")], [])
+    with pytest.raises(capi.HcError) as e:
+        capi.Store(rs)
+    assert "no CPU fallback" in str(e.value)
