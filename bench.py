@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- candidate overlaps scored per second on config 4 of BASELINE.json.
+
+Workload (config.workload): synthetic 10 M 2x150 bp pairs replicated in each GPU's HBM, ~1e9 P-P
+candidate overlaps sharded in 8 contiguous ranges; every GPU scores one shard of 1.25e8 candidates
+per step ("weak" scaling: N GPUs score N shards; N = 8 is the whole list).
+
+  value     candidates/s with the candidate records already resident in HBM (CUDA events on the
+            launching stream, barrier + synchronize on both sides, max over ranks)
+  e2e       the same step through hc_score_batch() on HOST buffers: pinned host candidates -> device,
+            kernels, accepted edges + non-edge indices -> host, inside the timed region
+  roofline  hc_score_kernel: algorithmic bytes per launch / its CUDA-event duration vs the measured
+            HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the UNMODIFIED reference's scoring region (oracle/_ref/ref_driver --time-scoring,
+            OpenMP over all host cores) on a bounded sample of the same candidates
+  --impl reference   only that CPU measurement, as the driver's reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidate_overlaps_scored_per_sec"
+UNIT = "candidates/s"
+N_SHARDS = 8
+PARAMS = dict(edge_threshold=0.97, ov_threshold=0.9, merge_contigs=0.0, mismatch=0.0, min_read_len=0)   # SAVAGE stage a
+MIN_OVERLAP_LEN = 150
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_name(args) -> str:
+    return ("C4 synthetic %d 2x%dbp pairs (store replicated per GPU), P-P candidates, shard r of %d of the ~%.2g-candidate "
+            "list: %d candidates per GPU per step" % (args.pairs, args.read_len, N_SHARDS, args.pairs * 100.0, args.cands))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            for t, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- CPU arm: the unmodified reference's scoring region on a bounded sample -------------------------
+def write_sample_files(d: str, rs_bases: np.ndarray, rs_quals: np.ndarray, read_len: int, cands: np.ndarray):
+    """FASTQ pair + overlaps file for the reads the sampled candidates touch (ids renumbered densely)."""
+    from haploconduct_b200 import formats as F
+
+    used = np.unique(np.concatenate([cands["idx1"], cands["idx2"]]))
+    L = read_len
+    with open(os.path.join(d, "p1.fastq"), "w") as f1, open(os.path.join(d, "p2.fastq"), "w") as f2:
+        for new, old in enumerate(used):
+            o = int(old) * 2 * L
+            f1.write("@%d\n%s\n+\n%s\n" % (new, rs_bases[o:o + L].tobytes().decode(), rs_quals[o:o + L].tobytes().decode()))
+            f2.write("@%d\n%s\n+\n%s\n" % (new, rs_bases[o + L:o + 2 * L].tobytes().decode(),
+                                           rs_quals[o + L:o + 2 * L].tobytes().decode()))
+    c = cands.copy()
+    c["idx1"] = np.searchsorted(used, cands["idx1"]).astype(np.uint32)
+    c["idx2"] = np.searchsorted(used, cands["idx2"]).astype(np.uint32)
+    F.write_overlaps(os.path.join(d, "ov.txt"), c, np.arange(len(used), dtype=np.uint64))
+    return len(used)
+
+
+def run_cpu_reference(bases: np.ndarray, quals: np.ndarray, read_len: int, cands: np.ndarray, reps: int, threads: int):
+    from oracle import oracle as O
+
+    if not O.have_ref():
+        raise RuntimeError("oracle/_ref/ref_driver is missing (it is built by __graft_entry__.build() where /root/reference exists)")
+    d = tempfile.mkdtemp(prefix="hc_cpu_")
+    n_reads = write_sample_files(d, bases, quals, read_len, cands)
+    out = O.run_ref(d, os.path.join(d, "ov.txt"), None, os.path.join(d, "p1.fastq"), os.path.join(d, "p2.fastq"), threads=threads,
+                    time_scoring=True, reps=reps, edge_threshold=PARAMS["edge_threshold"], min_overlap_len=MIN_OVERLAP_LEN)
+    assert out["scored"] == len(cands), (out["scored"], len(cands))
+    return out, n_reads
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=10_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--cands", type=int, default=125_000_000, help="candidates per GPU per step")
+    ap.add_argument("--partners", type=int, default=140, help="D: rank window of candidate partners")
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="candidates in the CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=20261018)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    from haploconduct_b200 import formats as F, workloads_torch as WT
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.time()
+        n_pairs_s = min(args.pairs, 400_000)
+        genome_s = max(1000, 100_000 * n_pairs_s // max(args.pairs, 1))   # same coverage as the full configuration
+        pr = WT.make_paired_reads(n_pairs_s, read_len=args.read_len, genome_len=genome_s, seed=args.seed, device="cpu")
+        rec = WT.make_pp_candidates(pr, D=args.partners, shard=0, n_shards=N_SHARDS, max_cands=args.cpu_sample)
+        cands = WT.candidates_as_numpy(rec)
+        threads = os.cpu_count() or 1
+        out, n_reads = run_cpu_reference(pr.bases.numpy(), pr.quals.numpy(), args.read_len, cands, args.warmup + args.steps, threads)
+        times = out["rep_times_s"][args.warmup:]
+        ms = 1e3 * float(np.mean(times))
+        v = len(cands) / (ms / 1e3)
+        sample = ("%d candidates of the same generator at the same coverage (%d pairs on a %d bp genome), scoring region "
+                  "src/EdgeCalculator.cpp:395-423 only, per step" % (len(cands), n_pairs_s, genome_s))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args), "sample": sample},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+                                 "cpu": cpu_model()},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+                "setup_s": round(time.time() - t0, 1)}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    from haploconduct_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    t_setup = time.time()
+    pr = WT.make_paired_reads(args.pairs, read_len=args.read_len, seed=args.seed, device=str(dev))
+    torch.cuda.synchronize()
+    log("[rank %d] reads generated in %.1fs" % (rank, time.time() - t_setup))
+    rs = pr.readset()
+    t1 = time.time()
+    store = capi.Store(rs, first_device=local_rank, n_devices=1)
+    log("[rank %d] store packed + uploaded in %.1fs (%.2f GB on device, %d quality codes)" %
+        (rank, time.time() - t1, store.device_bytes / 1e9, store.quality_alphabet))
+    t1 = time.time()
+    shard = rank % N_SHARDS
+    rec = WT.make_pp_candidates(pr, D=args.partners, shard=shard, n_shards=N_SHARDS, max_cands=args.cands)
+    n = rec.shape[0]
+    torch.cuda.synchronize()
+    log("[rank %d] %d candidates (shard %d/%d) generated in %.1fs" % (rank, n, shard, N_SHARDS, time.time() - t1))
+    params = F.make_params(**PARAMS)
+    d_edges = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    d_nonedge = torch.empty(n, dtype=torch.int64, device=dev)
+    d_counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(want_stats=False):
+        return store.score_batch_device(local_rank, stream.cuda_stream, params, rec.data_ptr(), n, 0, d_edges.data_ptr(), n,
+                                        d_nonedge.data_ptr(), n, d_counts.data_ptr(), want_stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    tw0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    tw1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    # dominant-kernel duration, measured live with CUDA events around hc_score_kernel on its stream
+    kms, stats = [], None
+    for _ in range(3):
+        stats = step(want_stats=True)
+        kms.append(float(stats["score_kernel_ms"]))
+    score_ms = float(np.mean(kms))
+    counts = d_counts.cpu().numpy()
+
+    # ---- e2e through the host-buffer entry point
+    e2e = None
+    if not args.no_e2e:
+        h_cand = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
+        h_cand.copy_(rec)
+        ne, nn = int(counts[0]), int(counts[1])
+        h_edges = torch.empty((max(ne, 1) + 1024, 32), dtype=torch.uint8, pin_memory=True)
+        h_nonedge = torch.empty(max(nn, 1) + 1024, dtype=torch.int64, pin_memory=True)
+        import ctypes
+        L = capi.lib()
+        c_ne, c_nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
+
+        def e2e_step():
+            rc = L.hc_score_batch(store.handle, params.ctypes.data, h_cand.data_ptr(), n, None, h_edges.data_ptr(),
+                                  h_edges.shape[0], ctypes.byref(c_ne), h_nonedge.data_ptr(), h_nonedge.shape[0],
+                                  ctypes.byref(c_nn), None)
+            if rc != 0:
+                raise RuntimeError(capi.last_error())
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        assert c_ne.value == ne and c_nn.value == nn
+        e2e = (e2e_ms, n * 32, ne * 32 + nn * 8 + 32)
+
+    ms_step = ms_total / args.steps
+    tvals = torch.tensor([ms_step, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([n], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step, e2e_ms = float(tvals[0]), float(tvals[1])
+    total_cands = int(tot[0])
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        alg = int(stats["algorithmic_bytes"])
+        achieved = alg / (score_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total_cands / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 fixed-point (2^-22) sums + f64 reference-order pass at threshold boundaries", "data": "synthetic",
+            "config": {"workload": workload_name(args), "l2": "inputs larger than L2: %.1f GB candidate stream + %.1f GB read store "
+                       "per step, no flush needed" % (n * 32 / 1e9, store.device_bytes / 1e9),
+                       "params": PARAMS, "candidates_per_gpu": n, "seed": args.seed},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "hc_score_kernel", "kernel_ms": score_ms,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "positions_per_launch": int(stats["n_positions"]), "all_kernels_ms": float(stats["kernel_ms"])},
+            "gpu_launches": int(stats["kernel_launches"]) * args.steps,
+            "clocks": clocks,
+            "results": {"edges": int(counts[0]), "nonedges": int(counts[1]), "reference_order_pass": int(counts[2])},
+            "setup_s": round(time.time() - t_setup, 1),
+        }
+        if e2e:
+            line["e2e"] = {"value": total_cands / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[1],
+                           "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms}
+        if world == 1 and not args.no_cpu:
+            try:
+                cs = WT.candidates_as_numpy(rec[: args.cpu_sample])
+                threads = os.cpu_count() or 1
+                out, n_reads = run_cpu_reference(pr.bases.numpy(), pr.quals.numpy(), args.read_len, cs, 3, threads)
+                t = float(np.mean(out["rep_times_s"][1:]))
+                t1 = None
+                try:
+                    out1, _ = run_cpu_reference(pr.bases.numpy(), pr.quals.numpy(), args.read_len, cs[: max(len(cs) // 16, 1)], 1, 1)
+                    t1 = (max(len(cs) // 16, 1)) / float(out1["rep_times_s"][0])
+                except Exception:
+                    pass
+                line["cpu_baseline"] = {"value": len(cs) / t, "unit": UNIT, "cores": threads, "kind": "reference",
+                                        "sample": "first %d candidates of this rank's shard (%d read pairs), 3 repetitions of the "
+                                                  "OpenMP scoring region src/EdgeCalculator.cpp:395-423 of the unmodified reference"
+                                                  % (len(cs), n_reads), "one_thread_value": t1, "cpu": cpu_model()}
+            except Exception as ex:   # the baseline is a reported number, never a reason to lose the GPU line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+        print(json.dumps(line), flush=True)
+    store.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,7 +63,7 @@ struct DevCtx {
     hc_result* d_per_cand = nullptr;
     uint64_t* d_counts = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     hc_launch_cfg cfg{};
 };
 
@@ -91,7 +91,7 @@ void free_ctx(DevCtx& d) {
     cudaFree(d.fx_table); cudaFree(d.dbl_table);
     cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts); cudaFree(d.counters);
     cudaFree(d.d_cand); cudaFree(d.d_edges); cudaFree(d.d_nonedge); cudaFree(d.d_per_cand); cudaFree(d.d_counts);
-    for (int k = 0; k < 4; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
+    for (int k = 0; k < 6; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
     if (d.stream) cudaStreamDestroy(d.stream);
     d = DevCtx();
 }
@@ -186,7 +186,9 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
         const uint64_t warps_per_block = cfg.threads / 32;
         const uint64_t need_blocks = (ntiles + warps_per_block - 1) / warps_per_block;
         if ((uint64_t)cfg.blocks > need_blocks) cfg.blocks = (int)need_blocks;
+        if (k0) CU(cudaEventRecord(d.ev[4], st));
         CU(hc_launch_score(P, cfg, st));
+        if (k0) CU(cudaEventRecord(d.ev[5], st));
         CU(hc_launch_exact(P, st));
         nl += 2;
     }
@@ -213,6 +215,8 @@ int read_stats(DevCtx& d, uint64_t n, hc_batch_stats* stats, cudaEvent_t k0, cud
         stats->algorithmic_bytes += h[HC_CNT_ALGBYTES];
         float ms = 0;
         if (k0 && k1 && cudaEventElapsedTime(&ms, k0, k1) == cudaSuccess) stats->kernel_ms = std::max(stats->kernel_ms, ms);
+        if (k0 && n > 0 && cudaEventElapsedTime(&ms, d.ev[4], d.ev[5]) == cudaSuccess)
+            stats->score_kernel_ms = std::max(stats->score_kernel_ms, ms);
     }
     if (h[HC_CNT_ERRORS]) {
         return fail(HC_ERR_ARG, std::to_string(h[HC_CNT_ERRORS]) +
@@ -396,7 +400,7 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
             e = hc_score_occupancy((uint32_t)s->ncodes, d.sm_count, d.smem_per_sm, &d.cfg);
         }
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-        for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
+        for (int j = 0; j < 6 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
         if (e == cudaSuccess) e = cudaMalloc(&d.qual, total + 64);
         if (e == cudaSuccess) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);

@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                         mmc[w] = acc[w].mm;
                         if (acc[w].vd) {
                             status = HC_WIN_VOID;               // :125-127, mismatch_rate stays 1.0
+                            mmc[w] = 0;                         // counts of a void window are not observable
                         } else if (tl == 0) {
                             status = HC_WIN_EMPTY;              // :129-131
                         } else {
@@ -492,7 +493,7 @@ __device__ void exact_window(const hc_kparams& P, const Win& w, double& mean, do
         const uint32_t mis = a != b;
         mm += mis;
         const double lp = P.dbl_table[hc_dbl_index(qa, qb, mis, n1)];
-        if (lp > 0.0) { status = HC_WIN_VOID; mmc = mm; return; }       // :125-127
+        if (lp > 0.0) { status = HC_WIN_VOID; mmc = 0; return; }        // :125-127
         total = __dadd_rn(total, lp);                                     // :119
         tl++;
     }

@@ -42,7 +42,7 @@ BATCH_STATS = np.dtype(
     [
         ("n_candidates", "<u8"), ("n_edges", "<u8"), ("n_nonedges", "<u8"), ("n_exact", "<u8"),
         ("n_windows", "<u8"), ("n_positions", "<u8"), ("algorithmic_bytes", "<u8"),
-        ("kernel_ms", "<f4"), ("total_ms", "<f4"), ("kernel_launches", "<u4"), ("reserved", "<u4"),
+        ("kernel_ms", "<f4"), ("total_ms", "<f4"), ("kernel_launches", "<u4"), ("score_kernel_ms", "<f4"),
     ]
 )
 assert READ_DESC.itemsize == 24 and CANDIDATE.itemsize == 32 and PARAMS.itemsize == 40

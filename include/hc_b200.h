@@ -140,7 +140,7 @@ typedef struct {
     float    kernel_ms;        /* device time of the scoring kernels of this call (CUDA events)     */
     float    total_ms;         /* device time of the whole call incl. copies (CUDA events)          */
     uint32_t kernel_launches;  /* kernels launched by this call                                     */
-    uint32_t reserved;
+    float    score_kernel_ms;  /* device time of the dominant kernel (hc_score_kernel) alone        */
 } hc_batch_stats;
 
 /* Score a batch of HOST candidates: the body of the omp-parallel region of

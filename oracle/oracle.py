@@ -104,7 +104,10 @@ def run_ref(workdir: str, overlaps: str, singles: Optional[str] = None, paired1:
     if time_scoring:
         cmd += ["--time-scoring", "--reps", str(reps)]
     out = subprocess.run(cmd, cwd=workdir, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
-    summary = json.loads([l for l in out.split("\n") if l.startswith("{")][-1])
+    jl = [json.loads(l) for l in out.split("\n") if l.startswith("{")]
+    summary = jl[-1]
+    for extra in jl[:-1]:
+        summary.update(extra)
     if dump_cands:
         summary["cands"] = parse_cand_dump(os.path.join(workdir, "ref_cands.tsv"))
     if dump_graph:

@@ -198,6 +198,7 @@ int main(int argc, char** argv) {
         // same loop shape as src/EdgeCalculator.cpp:395-423: static omp-for, per-thread vectors
         // concatenated under critical sections.
         double best = 1e300;
+        std::string rep_times;
         for (int r = 0; r < reps; r++) {
             std::vector<Edge> edges;
             std::vector<Overlap> nonedges;
@@ -222,10 +223,14 @@ int main(int argc, char** argv) {
             }
             double dt = now_s() - ts;
             if (dt < best) best = dt;
+            char buf[64];
+            std::snprintf(buf, sizeof(buf), "%s%.6f", r ? ", " : "", dt);
+            rep_times += buf;
             n_edges_t = edges.size();
             n_nonedges_t = nonedges.size();
         }
         t_scoring = best;
+        std::printf("{\"rep_times_s\": [%s]}\n", rep_times.c_str());
     }
 
     double t_construct = -1;
