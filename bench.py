@@ -167,6 +167,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--position-sorted-ids", action="store_true",
+                    help="diagnostic only: number the reads in genome order (cache-friendly, NOT the benchmark layout)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -215,7 +217,8 @@ def main() -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     t_setup = time.time()
-    pr = WT.make_paired_reads(args.pairs, read_len=args.read_len, seed=args.seed, device=str(dev))
+    pr = WT.make_paired_reads(args.pairs, read_len=args.read_len, seed=args.seed, device=str(dev),
+                              position_sorted_ids=args.position_sorted_ids)
     torch.cuda.synchronize()
     log("[rank %d] reads generated in %.1fs" % (rank, time.time() - t_setup))
     rs = pr.readset()

@@ -49,7 +49,7 @@ struct DevCtx {
     bool has_void = false;
     // workspace (grown on demand)
     uint64_t ws_cap = 0;
-    hc_score16* tmp = nullptr;
+    hc_tmp32* tmp = nullptr;
     uint8_t* cls = nullptr;
     uint32_t* flagged = nullptr;
     uint32_t* blockcounts = nullptr;
@@ -136,7 +136,7 @@ int ensure_workspace(DevCtx& d, uint64_t n) {
     cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts);
     d.tmp = nullptr; d.cls = nullptr; d.flagged = nullptr; d.blockcounts = nullptr;
     d.ws_cap = 0;
-    CU(cudaMalloc(&d.tmp, cap * sizeof(hc_score16)));
+    CU(cudaMalloc(&d.tmp, cap * sizeof(hc_tmp32)));
     CU(cudaMalloc(&d.cls, cap));
     CU(cudaMalloc(&d.flagged, cap * sizeof(uint32_t)));
     const uint64_t nb = hc_compact_blocks(cap) + 1;
@@ -172,6 +172,13 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     if (!mono) return fail(HC_ERR_ARG, "host exp() is not monotone around edge_threshold");
     P.t_ov = hc_tables_exp_threshold(p->ov_threshold, &mono);
     if (!mono) return fail(HC_ERR_ARG, "host exp() is not monotone around ov_threshold");
+    // fixed-point decision constants: mean = -S/(2^22*tl);  mean - margin >= t  <=>  S <= -(t+margin)*2^22 * tl
+    P.ce_up = -(P.t_edge + HC_FX_MARGIN) * HC_FX_SCALE;
+    P.ce_dn = -(P.t_edge - HC_FX_MARGIN) * HC_FX_SCALE;
+    P.co_up = -(P.t_ov + HC_FX_MARGIN) * HC_FX_SCALE;
+    P.co_dn = -(P.t_ov - HC_FX_MARGIN) * HC_FX_SCALE;
+    P.never_edge = P.t_edge > 0.0;   // a mean log-likelihood is <= 0
+    P.never_ov = P.t_ov > 0.0;
     P.merge_contigs = p->merge_contigs;
     P.min_read_len = p->min_read_len;
     P.zero_above_edge = 0.0 > p->edge_threshold;

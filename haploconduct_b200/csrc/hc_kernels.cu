@@ -8,19 +8,19 @@
 // How it is done here:
 //   * hc_score_kernel     one warp owns a tile of 32 candidates.  Lane = candidate for window
 //                         selection and for the final decision; in between, the tile's windows are
-//                         cut into 16-position chunks and the chunks are dealt to the 32 lanes round
-//                         robin, so short and long windows fill the warp equally well.  A chunk is
-//                         1 x 128-bit load (B side, always aligned) + 5 x 32-bit loads and 4 funnel
-//                         shifts (A side) of quality codes, 3 loads + 1 funnel shift + XOR/popc of
-//                         2-bit bases, and 16 shared-memory lookups of a fixed-point -log p table
-//                         indexed by (code_A, code_B, mismatch).  Sums are integers, hence exact and
-//                         order independent.  Candidates whose mean lands within HC_FX_MARGIN of a
-//                         threshold are queued for
+//                         cut into 32-position lane-chunks that are dealt round robin to the 32
+//                         lanes, so short and long windows fill the warp equally well.  A lane-chunk
+//                         is 2 aligned 128-bit loads of quality codes on the B side, up to 3 on the A
+//                         side (re-aligned in registers: word mux + funnel shifts), 2-bit bases
+//                         XOR/popc for the mismatch mask, and 32 shared-memory lookups of a
+//                         fixed-point -log p table indexed by (code_A, code_B, mismatch) through one
+//                         PRMT each.  Sums are integers, hence exact and order independent.
+//                         Candidates whose mean lands within HC_FX_MARGIN of a threshold are queued for
 //   * hc_exact_kernel     which re-adds the reference's own double addends in the reference's
 //                         order (one thread per queued candidate), so every decision is bit-exact.
 //   * hc_compact_*        order-preserving compaction of accepted edges / non-edge overlaps
 //                         (count -> scan -> scatter): output order = input order = the reference's
-//                         1-thread order.
+//                         1-thread order.  exp() of accepted edges is evaluated here, not per candidate.
 // No tensor cores: nothing here is a contraction.
 #include "hc_kernels.cuh"
 
@@ -38,27 +38,34 @@ struct Win {
 
 struct CandSetup {
     Win w[2];
-    int32_t pos3, pos4;
     uint32_t two;   // two windows (any paired read involved)
     uint32_t err;
 };
 
-__device__ __forceinline__ uint32_t d_len(const hc_rdesc& d, int m) { return m ? d.len[1] : d.len[0]; }
-__device__ __forceinline__ uint32_t d_slot(const hc_rdesc& d, int m) { return m ? d.slot16[1] : d.slot16[0]; }
+__device__ __forceinline__ hc_candidate load_candidate(const hc_candidate* p) {
+    const uint4* cp = reinterpret_cast<const uint4*>(p);
+    const uint4 a = __ldg(cp), b = __ldg(cp + 1);
+    hc_candidate c;
+    c.idx1 = a.x; c.idx2 = a.y; c.pos1 = a.z; c.pos2 = a.w;
+    c.len1 = b.x; c.len2 = b.y;
+    c.perc1 = b.z & 0xff; c.perc2 = (b.z >> 8) & 0xff; c.ord = (b.z >> 16) & 0xff; c.ori1 = (b.z >> 24) & 0xff;
+    c.ori2 = b.w & 0xff; c.type1 = (b.w >> 8) & 0xff; c.type2 = (b.w >> 16) & 0xff; c.reserved = 0;
+    return c;
+}
 
-// overlap_score's guards and window length, src/EdgeCalculator.cpp:74-88
-__device__ __forceinline__ void make_window(const hc_kparams& P, const hc_rdesc& dA, int mA, int rcA, const hc_rdesc& dB,
-                                            int mB, int rcB, uint32_t pos, Win& w) {
-    uint32_t rawA = d_len(dA, mA), rawB = d_len(dB, mB);
-    uint32_t lenA = rawA & HC_LEN_MASK, lenB = rawB & HC_LEN_MASK;
+// overlap_score's guards and window length, src/EdgeCalculator.cpp:74-88.
+// (rawA, slotA) / (rawB, slotB): length|HASN and forward slot start/16 of the two sequences.
+__device__ __forceinline__ void make_window(const hc_kparams& P, uint32_t rawA, uint32_t slotA, int rcA, uint32_t rawB,
+                                            uint32_t slotB, int rcB, uint32_t pos, Win& w) {
+    const uint32_t lenA = rawA & HC_LEN_MASK, lenB = rawB & HC_LEN_MASK;
     w.L = 0;
     w.xpos = 0;
     w.ypos16 = 0;
     w.hasN = 0;
     if (pos >= lenA) { w.status = HC_WIN_POS_OOR; return; }
     if (lenA < P.min_read_len || lenB < P.min_read_len) { w.status = HC_WIN_SHORT; return; }
-    u64 sa = 16ull * d_slot(dA, mA) + (rcA ? hc_slot_size(lenA) : 0u);
-    u64 sb = 16ull * d_slot(dB, mB) + (rcB ? hc_slot_size(lenB) : 0u);
+    const u64 sa = 16ull * slotA + (rcA ? hc_slot_size(lenA) : 0u);
+    const u64 sb = 16ull * slotB + (rcB ? hc_slot_size(lenB) : 0u);
     w.xpos = sa + pos;
     w.ypos16 = (uint32_t)(sb >> 4);
     w.L = min(lenA - pos, lenB);
@@ -66,120 +73,175 @@ __device__ __forceinline__ void make_window(const hc_kparams& P, const hc_rdesc&
     w.hasN = ((rawA | rawB) & HC_HASN_BIT) ? 1u : 0u;
 }
 
-// Window selection of EdgeCalculator::compute_overlap, src/EdgeCalculator.cpp:199-351, and the
-// extra positions :222,:262-263,:300-301,:361-372.
-__device__ __forceinline__ void setup_candidate(const hc_kparams& P, const hc_candidate& c, CandSetup& s) {
-    s.err = 0;
-    s.two = 0;
-    s.pos3 = s.pos4 = 0;
-    s.w[0].L = s.w[1].L = 0;
-    s.w[0].status = s.w[1].status = HC_WIN_UNUSED;
-    s.w[0].xpos = s.w[1].xpos = 0;
-    s.w[0].ypos16 = s.w[1].ypos16 = 0;
-    s.w[0].hasN = s.w[1].hasN = 0;
-    if (c.idx1 >= P.n_reads || c.idx2 >= P.n_reads || c.idx1 == c.idx2) { s.err = 1; return; }
-    const uint4 r1 = __ldg((const uint4*)(P.rdesc + c.idx1));
-    const uint4 r2 = __ldg((const uint4*)(P.rdesc + c.idx2));
-    hc_rdesc d1, d2;
-    d1.slot16[0] = r1.x; d1.slot16[1] = r1.y; d1.len[0] = r1.z; d1.len[1] = r1.w;
-    d2.slot16[0] = r2.x; d2.slot16[1] = r2.y; d2.len[0] = r2.z; d2.len[1] = r2.w;
-    const int p1 = (d1.len[1] & HC_LEN_MASK) != 0, p2 = (d2.len[1] & HC_LEN_MASK) != 0;  // Read::is_paired()
+// Window selection of EdgeCalculator::compute_overlap, src/EdgeCalculator.cpp:199-351, written
+// without the 13-way case split:
+//   "first"/"second" mate of a paired read in orientation ori: (/1,/2) if '+', (/2,/1) if '-'  (:316-351)
+//   window 1: A = read1.first (or its only sequence), B = read2.first                           pos1
+//   window 2: a = read1.second (or its only sequence), b = read2.second (or its only sequence)  pos2
+//             laid as (a, b), or as (b, a) for P-S (:278,:282,:286,:290) and for P-P with ord == 2
+//             (:322,:331,:340,:349).
+__device__ __forceinline__ void setup_windows(const hc_kparams& P, const hc_candidate& c, const uint4& r1, const uint4& r2,
+                                              CandSetup& s) {
+    // r.x/.y = slot16 of mate 0/1, r.z/.w = len|HASN of mate 0/1
+    const int p1 = (r1.w & HC_LEN_MASK) != 0, p2 = (r2.w & HC_LEN_MASK) != 0;   // Read::is_paired()
     const int rc1 = c.ori1 ? 0 : 1, rc2 = c.ori2 ? 0 : 1;
-    const int f1 = c.ori1 ? 0 : 1, s1 = 1 - f1, f2 = c.ori2 ? 0 : 1, s2 = 1 - f2;
-    const uint32_t l10 = d1.len[0] & HC_LEN_MASK, l11 = d1.len[1] & HC_LEN_MASK;
-    const uint32_t l20 = d2.len[0] & HC_LEN_MASK, l21 = d2.len[1] & HC_LEN_MASK;
-    if (!p1 && !p2) {                                    // S-S :199-233
-        if (P.n_single == 0) { s.err = 1; return; }
-        make_window(P, d1, 0, rc1, d2, 0, rc2, c.pos1, s.w[0]);
-        s.pos3 = (int32_t)(l10 - c.pos1 - l20);
-    } else if (!p1 && p2) {                              // S-P :234-271
-        if (P.n_single == 0) { s.err = 1; return; }
-        make_window(P, d1, 0, rc1, d2, f2, rc2, c.pos1, s.w[0]);
-        make_window(P, d1, 0, rc1, d2, s2, rc2, c.pos2, s.w[1]);
-        s.two = 1;
-        s.pos3 = (int32_t)(l10 - c.pos2 - l21);
-        s.pos4 = (int32_t)(l10 - c.pos1 - l20);
-    } else if (p1 && !p2) {                              // P-S :272-309
-        if (P.n_single == 0) { s.err = 1; return; }
-        make_window(P, d1, f1, rc1, d2, 0, rc2, c.pos1, s.w[0]);
-        make_window(P, d2, 0, rc2, d1, s1, rc1, c.pos2, s.w[1]);
-        s.two = 1;
-        s.pos3 = (int32_t)(l11 + c.pos2 - l20);
-        s.pos4 = (int32_t)(l20 + c.pos1 - l10);
-    } else {                                             // P-P :312-380
-        if (c.ord != '1' && c.ord != '2') { s.err = 1; return; }   // assert :369
-        make_window(P, d1, f1, rc1, d2, f2, rc2, c.pos1, s.w[0]);
-        if (c.ord == '1') {
-            make_window(P, d1, s1, rc1, d2, s2, rc2, c.pos2, s.w[1]);
-            s.pos3 = (int32_t)(l11 - c.pos2 - l21);
-        } else {
-            make_window(P, d2, s2, rc2, d1, s1, rc1, c.pos2, s.w[1]);
-            s.pos3 = (int32_t)(l11 + c.pos2 - l21);
-        }
-        s.two = 1;
-        s.pos4 = (int32_t)(l10 - c.pos1 - l20);
+    const int f1 = p1 ? rc1 : 0, s1 = p1 ? 1 - rc1 : 0;   // mate slot of first / second sequence of read 1
+    const int f2 = p2 ? rc2 : 0, s2 = p2 ? 1 - rc2 : 0;
+    s.two = (p1 | p2) ? 1u : 0u;
+    s.err = 0;
+    s.w[1].L = 0; s.w[1].xpos = 0; s.w[1].ypos16 = 0; s.w[1].hasN = 0; s.w[1].status = HC_WIN_UNUSED;
+    if (p1 && p2) { if (c.ord != '1' && c.ord != '2') s.err = 1; }            // assert :369
+    else if (P.n_single == 0) s.err = 1;                                        // :197, "Read types not recognized" :381
+    make_window(P, f1 ? r1.w : r1.z, f1 ? r1.y : r1.x, rc1, f2 ? r2.w : r2.z, f2 ? r2.y : r2.x, rc2, c.pos1, s.w[0]);
+    if (s.two) {
+        const uint32_t ra = s1 ? r1.w : r1.z, sa = s1 ? r1.y : r1.x;
+        const uint32_t rb = s2 ? r2.w : r2.z, sb = s2 ? r2.y : r2.x;
+        const bool swapped = p1 && (!p2 || c.ord == '2');
+        if (swapped) make_window(P, rb, sb, rc2, ra, sa, rc1, c.pos2, s.w[1]);
+        else make_window(P, ra, sa, rc1, rb, sb, rc2, c.pos2, s.w[1]);
+    }
+    if (s.err) { s.w[0].L = s.w[1].L = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED; }
+}
+
+// Edge::pos3 / pos4, src/EdgeCalculator.cpp:222, :262-263, :300-301, :361-372 (size_t arithmetic
+// truncated to int == 32-bit wrap-around).
+__device__ __forceinline__ void extra_pos(const hc_candidate& c, const uint4& r1, const uint4& r2, int32_t& pos3, int32_t& pos4) {
+    const uint32_t l10 = r1.z & HC_LEN_MASK, l11 = r1.w & HC_LEN_MASK, l20 = r2.z & HC_LEN_MASK, l21 = r2.w & HC_LEN_MASK;
+    const int p1 = l11 != 0, p2 = l21 != 0;
+    if (!p1 && !p2) { pos3 = (int32_t)(l10 - c.pos1 - l20); pos4 = 0; }
+    else if (!p1) { pos3 = (int32_t)(l10 - c.pos2 - l21); pos4 = (int32_t)(l10 - c.pos1 - l20); }
+    else if (!p2) { pos3 = (int32_t)(l11 + c.pos2 - l20); pos4 = (int32_t)(l20 + c.pos1 - l10); }
+    else {
+        pos3 = c.ord == '1' ? (int32_t)(l11 - c.pos2 - l21) : (int32_t)(l11 + c.pos2 - l21);
+        pos4 = (int32_t)(l10 - c.pos1 - l20);
     }
 }
 
-// One 16-position chunk of one window.  Returns the fixed-point sum of -log p over the chunk,
-// the mismatch count, the number of N positions and whether a void (p < ps.mismatch) pair was hit.
-template <bool HAS_VOID>
-__device__ __forceinline__ void process_chunk(const hc_kparams& P, const uint32_t* __restrict__ T, u64 xpos, uint32_t ypos16,
-                                              uint32_t L, uint32_t hasN, uint32_t k, uint32_t& sum, uint32_t& mm,
-                                              uint32_t& ncnt, uint32_t& vd) {
-    const u64 xp = xpos + 16ull * k;
-    const uint32_t rem = L - 16u * k;   // >= 1 positions left in the window
-    const uint32_t yq = ypos16 + k;
-    // ---- loads (all issued before first use)
-    const uint32_t* qa = reinterpret_cast<const uint32_t*>(P.qual + (xp & ~3ull));
-    const uint32_t w0 = __ldg(qa), w1 = __ldg(qa + 1), w2 = __ldg(qa + 2), w3 = __ldg(qa + 3), w4 = __ldg(qa + 4);
-    const uint4 wb = __ldg(reinterpret_cast<const uint4*>(P.qual) + yq);
-    const uint32_t* bap = P.base2 + (xp >> 4);
-    const uint32_t b0 = __ldg(bap), b1 = __ldg(bap + 1);
-    const uint32_t bb = __ldg(P.base2 + yq);
-    // ---- mismatch mask in the 2-bit domain: XOR, fold pairs, popc
-    const uint32_t ba = __funnelshift_r(b0, b1, ((uint32_t)xp & 15u) * 2u);
-    const uint32_t x2 = ba ^ bb;
-    uint32_t m = (x2 | (x2 >> 1)) & 0x55555555u;
-    if (rem < 16u) m &= (1u << (2u * rem)) - 1u;
-    ncnt = 0;
-    if (hasN) {   // rare: either read contains an N (skipped positions, src/EdgeCalculator.cpp:35-39,122-124)
-        const uint32_t* nap = P.nmask + (xp >> 5);
-        const uint32_t n0 = __ldg(nap), n1 = __ldg(nap + 1);
-        const uint32_t nA = __funnelshift_r(n0, n1, (uint32_t)xp & 31u) & 0xffffu;
-        const uint32_t nB = (__ldg(P.nmask + (yq >> 1)) >> ((yq & 1u) * 16u)) & 0xffffu;
-        uint32_t nn = nA | nB;
-        if (rem < 16u) nn &= (1u << rem) - 1u;
-        ncnt = __popc(nn);
-        uint32_t s = nn;   // spread 16 bits to the even bit positions
-        s = (s | (s << 8)) & 0x00ff00ffu;
-        s = (s | (s << 4)) & 0x0f0f0f0fu;
-        s = (s | (s << 2)) & 0x33333333u;
-        s = (s | (s << 1)) & 0x55555555u;
-        m &= ~s;
+__device__ __forceinline__ bool load_and_setup(const hc_kparams& P, const hc_candidate& c, CandSetup& s, uint4& r1, uint4& r2) {
+    if (c.idx1 >= P.n_reads || c.idx2 >= P.n_reads || c.idx1 == c.idx2) {
+        s.err = 1; s.two = 0;
+        s.w[0].L = s.w[1].L = 0; s.w[0].xpos = s.w[1].xpos = 0; s.w[0].ypos16 = s.w[1].ypos16 = 0;
+        s.w[0].hasN = s.w[1].hasN = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED;
+        r1 = r2 = make_uint4(0, 0, 0, 0);
+        return false;
     }
-    mm = __popc(m);
-    // ---- quality codes: align the A side, build (row, column) byte pairs, look up
-    const uint32_t sh = ((uint32_t)xp & 3u) * 8u;
-    uint32_t wa[4];
-    wa[0] = __funnelshift_r(w0, w1, sh);
-    wa[1] = __funnelshift_r(w1, w2, sh);
-    wa[2] = __funnelshift_r(w2, w3, sh);
-    wa[3] = __funnelshift_r(w3, w4, sh);
-    const uint32_t wbv[4] = {wb.x, wb.y, wb.z, wb.w};
-    uint32_t acc = 0, orv = 0;
+    r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx1));
+    r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx2));
+    setup_windows(P, c, r1, r2, s);
+    return !s.err;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Pull the (randomly located) window data towards L2 while the tile is still being set up.
+__device__ __forceinline__ void prefetch_window(const hc_kparams& P, const Win& w) {
+    if (w.L == 0) return;
+    const uint32_t n = min(w.L, 512u);
+    const uint8_t* xa = P.qual + (w.xpos & ~127ull);
+    const uint32_t xe = (uint32_t)(w.xpos & 127ull) + n;
+    for (uint32_t o = 0; o < xe; o += 128) prefetch_l2(xa + o);
+    const uint8_t* ya = P.qual + 16ull * w.ypos16;
+    for (uint32_t o = 0; o < n; o += 128) prefetch_l2(ya + o);
+    prefetch_l2(P.base2 + (w.xpos >> 4));
+    prefetch_l2(P.base2 + ((w.xpos + n) >> 4));
+    prefetch_l2(P.base2 + w.ypos16);
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// 16 positions: (A codes ^ swizzle(B codes)) | mismatch<<7 -> column byte, B code -> row byte,
+// one PRMT per position builds the table index (upper bytes zero through PRMT's sign-replicate
+// mode on the row byte, whose msb is always 0), 16 shared-memory lookups.
+template <bool HAS_VOID>
+__device__ __forceinline__ void lookup16(const uint32_t* __restrict__ T, const uint32_t* wa, const uint32_t* wy, uint32_t m,
+                                         uint32_t& acc, uint32_t& orv) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         // mismatch bits of positions 4j..4j+3 (bits 0,2,4,6 of byte j of m) -> bit 7 of bytes 0..3
         const uint32_t mj = (m >> (8 * j)) & 0x55u;
         const uint32_t dep = (mj * 0x02082080u) & 0x80808080u;
-        const uint32_t col = (wa[j] ^ hc_swz4(wbv[j])) | dep;
-        const uint32_t lo = __byte_perm(col, wbv[j], 0x5140);
-        const uint32_t hi = __byte_perm(col, wbv[j], 0x7362);
-        const uint32_t t0 = T[lo & 0xffffu], t1 = T[lo >> 16], t2 = T[hi & 0xffffu], t3 = T[hi >> 16];
+        const uint32_t col = (wa[j] ^ hc_swz4(wy[j])) | dep;
+        const uint32_t t0 = T[prmt(col, wy[j], 0xCC40u)];
+        const uint32_t t1 = T[prmt(col, wy[j], 0xDD51u)];
+        const uint32_t t2 = T[prmt(col, wy[j], 0xEE62u)];
+        const uint32_t t3 = T[prmt(col, wy[j], 0xFF73u)];
         acc += (t0 + t1) + (t2 + t3);
         if (HAS_VOID) orv |= (t0 | t1) | (t2 | t3);
     }
+}
+
+// One 32-position lane-chunk of one window.  Returns the fixed-point sum of -log p over the chunk,
+// the mismatch count, the number of N positions and whether a void (p < ps.mismatch) pair was hit.
+template <bool HAS_VOID>
+__device__ __forceinline__ void process32(const hc_kparams& P, const uint32_t* __restrict__ T, u64 xpos, uint32_t ypos16,
+                                          uint32_t L, uint32_t hasN, uint32_t k, uint32_t& sum, uint32_t& mm, uint32_t& ncnt,
+                                          uint32_t& vd) {
+    const u64 xp = xpos + 32ull * k;
+    const uint32_t n = min(L - 32u * k, 32u);   // 1..32 valid positions
+    const uint32_t yq = ypos16 + 2u * k;        // even: slots start at multiples of 64 positions
+    const uint32_t off = (uint32_t)xp & 15u;
+    const bool two = n > 16u, x1 = off + n > 16u, x2 = off + n > 32u;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    // ---- loads, all issued before first use; blocks beyond the window are not touched
+    const uint4* xq = reinterpret_cast<const uint4*>(P.qual + (xp & ~15ull));
+    const uint4 q0 = __ldg(xq);
+    const uint4 q1 = x1 ? __ldg(xq + 1) : z4;
+    const uint4 q2 = x2 ? __ldg(xq + 2) : z4;
+    const uint4* yqp = reinterpret_cast<const uint4*>(P.qual) + yq;
+    const uint4 y0 = __ldg(yqp);
+    const uint4 y1 = two ? __ldg(yqp + 1) : z4;
+    const uint32_t* bxp = P.base2 + (xp >> 4);
+    const uint32_t b0 = __ldg(bxp);
+    const uint32_t b1 = x1 ? __ldg(bxp + 1) : 0u;
+    const uint32_t b2 = x2 ? __ldg(bxp + 2) : 0u;
+    const uint2 by = __ldg(reinterpret_cast<const uint2*>(P.base2 + yq));
+    // ---- mismatch masks in the 2-bit domain: XOR, fold pairs, popc
+    const uint32_t bsh = off * 2u;
+    const uint32_t xa0 = __funnelshift_r(b0, b1, bsh) ^ by.x;
+    const uint32_t xa1 = __funnelshift_r(b1, b2, bsh) ^ by.y;
+    uint32_t m0 = (xa0 | (xa0 >> 1)) & 0x55555555u;
+    uint32_t m1 = (xa1 | (xa1 >> 1)) & 0x55555555u;
+    if (n < 32u) {
+        const uint32_t n0 = min(n, 16u), n1 = n - n0;
+        m0 &= n0 >= 16u ? 0xffffffffu : ((1u << (2u * n0)) - 1u);
+        m1 &= (1u << (2u * n1)) - 1u;   // n1 <= 15
+    }
+    ncnt = 0;
+    if (hasN) {   // rare: either read contains an N (skipped positions, src/EdgeCalculator.cpp:35-39,122-124)
+        const uint32_t* nap = P.nmask + (xp >> 5);
+        const uint32_t na0 = __ldg(nap), na1 = __ldg(nap + 1);
+        uint32_t nn = __funnelshift_r(na0, na1, (uint32_t)xp & 31u) | __ldg(P.nmask + (yq >> 1));
+        if (n < 32u) nn &= (1u << n) - 1u;
+        ncnt = __popc(nn);
+        uint32_t s0 = nn & 0xffffu, s1 = nn >> 16;   // spread 16 bits to the even bit positions
+        s0 = (s0 | (s0 << 8)) & 0x00ff00ffu; s1 = (s1 | (s1 << 8)) & 0x00ff00ffu;
+        s0 = (s0 | (s0 << 4)) & 0x0f0f0f0fu; s1 = (s1 | (s1 << 4)) & 0x0f0f0f0fu;
+        s0 = (s0 | (s0 << 2)) & 0x33333333u; s1 = (s1 | (s1 << 2)) & 0x33333333u;
+        s0 = (s0 | (s0 << 1)) & 0x55555555u; s1 = (s1 | (s1 << 1)) & 0x55555555u;
+        m0 &= ~s0;
+        m1 &= ~s1;
+    }
+    mm = __popc(m0) + __popc(m1);
+    // ---- A-side quality codes: select 9 of the 12 loaded words (word offset 0..3), then funnel by bytes
+    const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    const bool s2 = (off & 8u) != 0, s1 = (off & 4u) != 0;
+    uint32_t V1[10], V[9];
+#pragma unroll
+    for (int i = 0; i < 10; i++) V1[i] = s2 ? W[i + 2] : W[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
+    const uint32_t sh = (off & 3u) * 8u;
+    uint32_t wa[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) wa[i] = __funnelshift_r(V[i], V[i + 1], sh);
+    const uint32_t wy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    uint32_t acc = 0, orv = 0;
+    lookup16<HAS_VOID>(T, wa, wy, m0, acc, orv);
+    lookup16<HAS_VOID>(T, wa + 4, wy + 4, m1, acc, orv);
     sum = acc;
     vd = HAS_VOID ? ((orv & HC_VOID_BIT) ? 1u : 0u) : 0u;
 }
@@ -200,54 +262,53 @@ struct WinAcc {
     uint32_t vd;    // void
 };
 
-// The decision of src/EdgeCalculator.cpp:254-261 (two windows) and :404-413, on per-window
-// "mean above threshold" flags.  ov[] are the per-window scores (0 for the early outs).
-__device__ __forceinline__ void combine(const hc_kparams& P, uint32_t two, const double ov[2], const double mmr[2],
-                                        const int ae[2], const int ao[2], double& score, double& mmrate, uint32_t& cls) {
-    int edge_by_score, ov_ok;
+// src/EdgeCalculator.cpp:254-261 (two windows) and :404-413, on per-window "above threshold" flags.
+__device__ __forceinline__ uint32_t classify(const hc_kparams& P, uint32_t two, const double mmr[2], const int ae[2],
+                                             const int ao[2], double& mmrate) {
+    int both, ov_ok;
     if (two) {
         mmrate = fmax(mmr[0], mmr[1]);
-        const int both = ae[0] && ae[1];
-        score = both ? 0.5 * (ov[0] + ov[1]) : fmin(ov[0], ov[1]);
-        edge_by_score = both;
+        both = ae[0] && ae[1];
         ov_ok = ao[0] && ao[1];
     } else {
         mmrate = mmr[0];
-        score = ov[0];
-        edge_by_score = ae[0];
+        both = ae[0];
         ov_ok = ao[0];
     }
-    if (edge_by_score) cls = HC_CLASS_EDGE;
+    uint32_t cls;
+    if (both) cls = HC_CLASS_EDGE;
     else if (mmrate <= P.merge_contigs) cls = HC_CLASS_EDGE;
     else if (ov_ok) cls = HC_CLASS_NONEDGE;
     else cls = HC_CLASS_DISCARD;
+    return cls | (both ? HC_CLS_BOTH : 0u);
 }
 
-__device__ __forceinline__ void write_result(const hc_kparams& P, u64 i, const CandSetup& s, double score, double mmrate,
-                                             uint32_t cls, const uint32_t mmc[2], const uint32_t cmp[2],
-                                             const uint32_t st[2], uint32_t exact) {
-    hc_score16 t;
-    t.score = score;
-    t.mismatch_rate = mmrate;
-    P.tmp[i] = t;
-    P.cls[i] = (uint8_t)cls;
-    if (P.per_cand) {
-        hc_result r;
-        r.score = score;
-        r.mismatch_rate = mmrate;
-        r.pos3 = s.pos3;
-        r.pos4 = s.pos4;
-        r.mismatches[0] = mmc[0];
-        r.mismatches[1] = mmc[1];
-        r.compared[0] = cmp[0];
-        r.compared[1] = cmp[1];
-        r.cls = (uint8_t)cls;
-        r.status[0] = (uint8_t)st[0];
-        r.status[1] = (uint8_t)st[1];
-        r.exact = (uint8_t)exact;
-        r.reserved = 0;
-        P.per_cand[i] = r;
-    }
+// score of :138 / :256-261 from per-window scores
+__device__ __forceinline__ double combine_score(uint32_t two, uint32_t both, double ov0, double ov1) {
+    if (!two) return ov0;
+    return both ? 0.5 * (ov0 + ov1) : fmin(ov0, ov1);
+}
+
+__device__ __forceinline__ double fx_mean(u64 S, uint32_t tl) { return -((double)S * (1.0 / HC_FX_SCALE)) / (double)tl; }
+
+__device__ __forceinline__ void write_per_cand(const hc_kparams& P, u64 i, const hc_candidate& c, const uint4& r1,
+                                               const uint4& r2, double score, double mmrate, uint32_t cls,
+                                               const uint32_t mmc[2], const uint32_t cmp[2], const uint32_t st[2],
+                                               uint32_t exact) {
+    hc_result r;
+    r.score = score;
+    r.mismatch_rate = mmrate;
+    extra_pos(c, r1, r2, r.pos3, r.pos4);
+    r.mismatches[0] = mmc[0];
+    r.mismatches[1] = mmc[1];
+    r.compared[0] = cmp[0];
+    r.compared[1] = cmp[1];
+    r.cls = (uint8_t)(cls & HC_CLS_MASK);
+    r.status[0] = (uint8_t)st[0];
+    r.status[1] = (uint8_t)st[1];
+    r.exact = (uint8_t)exact;
+    r.reserved = 0;
+    P.per_cand[i] = r;
 }
 
 template <bool HAS_VOID>
@@ -279,25 +340,23 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
         const u64 i = (tile << 5) + lane;
         const bool valid = i < P.n;
         CandSetup s;
-        s.err = 0; s.two = 0; s.pos3 = s.pos4 = 0;
+        hc_candidate c;
+        uint4 r1, r2;
+        s.err = 0; s.two = 0;
         s.w[0].L = s.w[1].L = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED;
         s.w[0].xpos = s.w[1].xpos = 0; s.w[0].ypos16 = s.w[1].ypos16 = 0; s.w[0].hasN = s.w[1].hasN = 0;
         if (valid) {
-            const uint4* cp = reinterpret_cast<const uint4*>(P.cand + i);
-            const uint4 ca = __ldg(cp), cb = __ldg(cp + 1);
-            hc_candidate c;
-            c.idx1 = ca.x; c.idx2 = ca.y; c.pos1 = ca.z; c.pos2 = ca.w;
-            c.len1 = cb.x; c.len2 = cb.y;
-            c.perc1 = cb.z & 0xff; c.perc2 = (cb.z >> 8) & 0xff; c.ord = (cb.z >> 16) & 0xff; c.ori1 = (cb.z >> 24) & 0xff;
-            c.ori2 = cb.w & 0xff; c.type1 = (cb.w >> 8) & 0xff; c.type2 = (cb.w >> 16) & 0xff; c.reserved = 0;
-            setup_candidate(P, c, s);
+            c = load_candidate(P.cand + i);
+            load_and_setup(P, c, s, r1, r2);
+            prefetch_window(P, s.w[0]);
+            prefetch_window(P, s.w[1]);
         }
-        const uint32_t c0 = (s.w[0].L + 15u) >> 4, c1 = (s.w[1].L + 15u) >> 4;
+        const uint32_t c0 = (s.w[0].L + 31u) >> 5, c1 = (s.w[1].L + 31u) >> 5;
         const uint32_t ct = c0 + c1;
         WinAcc acc[2];
         acc[0].S = acc[1].S = 0; acc[0].mm = acc[1].mm = 0; acc[0].nn = acc[1].nn = 0; acc[0].vd = acc[1].vd = 0;
 
-        // ---- big candidates (>= 64 chunks): the whole warp walks one window at a time
+        // ---- big candidates (>= 64 lane-chunks): the whole warp walks one window at a time
         uint32_t bigmask = __ballot_sync(0xffffffffu, ct >= HC_BIG_CHUNKS);
         while (bigmask) {
             const int src = __ffs(bigmask) - 1;
@@ -309,14 +368,14 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                 const uint32_t yp = __shfl_sync(0xffffffffu, s.w[w].ypos16, src);
                 const uint32_t Lw = __shfl_sync(0xffffffffu, s.w[w].L, src);
                 const uint32_t hn = __shfl_sync(0xffffffffu, s.w[w].hasN, src);
-                const uint32_t cw = (Lw + 15u) >> 4;
+                const uint32_t cw = (Lw + 31u) >> 5;
                 if (cw == 0) continue;
                 const u64 xpos = ((u64)xh << 32) | xl;
                 u64 S = 0;
                 uint32_t mm = 0, nn = 0, vd = 0;
                 for (uint32_t k = lane; k < cw; k += 32) {
                     uint32_t sum, m1, n1, v1;
-                    process_chunk<HAS_VOID>(P, T, xpos, yp, Lw, hn, k, sum, m1, n1, v1);
+                    process32<HAS_VOID>(P, T, xpos, yp, Lw, hn, k, sum, m1, n1, v1);
                     S += sum; mm += m1; nn += n1; vd |= v1;
                 }
 #pragma unroll
@@ -330,7 +389,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
             }
         }
 
-        // ---- small candidates: rounds of at most HC_PARTMAX chunks dealt round robin to the lanes
+        // ---- small candidates: rounds of at most HC_PARTMAX lane-chunks dealt round robin to the lanes
         uint32_t pending = __ballot_sync(0xffffffffu, ct > 0 && ct < HC_BIG_CHUNKS);
         while (pending) {
             const bool mine = (pending >> lane) & 1u;
@@ -370,7 +429,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                     const uint4 a = wdA[slot];
                     const uint2 b = wdB[slot];
                     uint32_t sum, m1, n1, v1;
-                    process_chunk<HAS_VOID>(P, T, ((u64)a.y << 32) | a.x, a.z, a.w, b.y, f - b.x, sum, m1, n1, v1);
+                    process32<HAS_VOID>(P, T, ((u64)a.y << 32) | a.x, a.z, a.w, b.y, f - b.x, sum, m1, n1, v1);
                     part[f] = make_uint2(sum, m1 | (n1 << 12) | (v1 << 24));
                 }
                 running += __popc(hw);
@@ -394,11 +453,14 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
         if (valid) {
             if (s.err) {
                 st_errors++;
-                const uint32_t z[2] = {0, 0};
-                const uint32_t stt[2] = {HC_WIN_UNUSED, HC_WIN_UNUSED};
-                write_result(P, i, s, 0.0, 1.0, HC_CLASS_DISCARD, z, z, stt, 0);
+                P.cls[i] = HC_CLASS_DISCARD;
+                if (P.per_cand) {
+                    const uint32_t z[2] = {0, 0};
+                    const uint32_t stt[2] = {HC_WIN_UNUSED, HC_WIN_UNUSED};
+                    write_per_cand(P, i, c, r1, r2, 0.0, 1.0, HC_CLASS_DISCARD, z, z, stt, 0);
+                }
             } else {
-                double ov[2] = {0.0, 0.0}, mmr[2] = {1.0, 1.0};
+                double mmr[2] = {1.0, 1.0};
                 int ae[2], ao[2];
                 uint32_t mmc[2] = {0, 0}, cmp[2] = {0, 0}, stt[2];
 #pragma unroll
@@ -408,23 +470,20 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                     ao[w] = P.zero_above_ov;
                     if (status == HC_WIN_SCORED) {
                         const uint32_t tl = s.w[w].L - acc[w].nn;
-                        mmc[w] = acc[w].mm;
                         if (acc[w].vd) {
                             status = HC_WIN_VOID;               // :125-127, mismatch_rate stays 1.0
-                            mmc[w] = 0;                         // counts of a void window are not observable
                         } else if (tl == 0) {
                             status = HC_WIN_EMPTY;              // :129-131
                         } else {
                             cmp[w] = tl;
-                            const double dl = (double)tl;
-                            mmr[w] = (double)(float)(int)acc[w].mm / dl;                       // :132
-                            const double mean = -((double)acc[w].S * (1.0 / HC_FX_SCALE)) / dl;  // :137 (fixed point)
-                            ov[w] = exp(mean);                                                  // :138
-                            const bool never_e = P.t_edge > 0.0, never_o = P.t_ov > 0.0;       // mean <= 0 always
-                            const bool up_e = !never_e && (mean - HC_FX_MARGIN >= P.t_edge);
-                            const bool dn_e = never_e || (mean + HC_FX_MARGIN < P.t_edge);
-                            const bool up_o = !never_o && (mean - HC_FX_MARGIN >= P.t_ov);
-                            const bool dn_o = never_o || (mean + HC_FX_MARGIN < P.t_ov);
+                            mmc[w] = acc[w].mm;
+                            const double dl = (double)tl, dS = (double)acc[w].S;
+                            mmr[w] = acc[w].mm ? (double)(float)(int)acc[w].mm / dl : 0.0;    // :132
+                            // mean = -S / (2^22 * tl) compared in the multiplied-out form (no division)
+                            const bool up_e = !P.never_edge && (dS <= P.ce_up * dl);
+                            const bool dn_e = P.never_edge || (dS > P.ce_dn * dl);
+                            const bool up_o = !P.never_ov && (dS <= P.co_up * dl);
+                            const bool dn_o = P.never_ov || (dS > P.co_dn * dl);
                             ae[w] = up_e;
                             ao[w] = up_o;
                             if (!(up_e || dn_e) || !(up_o || dn_o)) flag = true;
@@ -436,11 +495,23 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                     stt[w] = status;
                 }
                 st_bytes += 48;
-                double score, mmrate;
-                uint32_t cls;
-                combine(P, s.two, ov, mmr, ae, ao, score, mmrate, cls);
-                if (P.exact_edges && cls == HC_CLASS_EDGE) flag = true;
-                write_result(P, i, s, score, mmrate, cls, mmc, cmp, stt, 0);
+                double mmrate;
+                const uint32_t cls = classify(P, s.two, mmr, ae, ao, mmrate);
+                if (P.exact_edges && (cls & HC_CLS_MASK) == HC_CLASS_EDGE) flag = true;
+                P.cls[i] = (uint8_t)cls;
+                if ((cls & HC_CLS_MASK) == HC_CLASS_EDGE) {
+                    hc_tmp32 t;
+                    t.S[0] = acc[0].S; t.S[1] = acc[1].S;
+                    t.tl[0] = cmp[0]; t.tl[1] = cmp[1];
+                    t.mismatch_rate = mmrate;
+                    P.tmp[i] = t;
+                }
+                if (P.per_cand) {
+                    const double ov0 = cmp[0] ? exp(fx_mean(acc[0].S, cmp[0])) : 0.0;
+                    const double ov1 = cmp[1] ? exp(fx_mean(acc[1].S, cmp[1])) : 0.0;
+                    write_per_cand(P, i, c, r1, r2, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), mmrate, cls, mmc, cmp,
+                                   stt, 0);
+                }
             }
         }
         // queue boundary cases for the reference-order pass (warp-aggregated append)
@@ -493,12 +564,12 @@ __device__ void exact_window(const hc_kparams& P, const Win& w, double& mean, do
         const uint32_t mis = a != b;
         mm += mis;
         const double lp = P.dbl_table[hc_dbl_index(qa, qb, mis, n1)];
-        if (lp > 0.0) { status = HC_WIN_VOID; mmc = 0; return; }        // :125-127
+        if (lp > 0.0) { status = HC_WIN_VOID; return; }                  // :125-127
         total = __dadd_rn(total, lp);                                     // :119
         tl++;
     }
-    mmc = mm;
     if (tl == 0) { status = HC_WIN_EMPTY; return; }                      // :129-131
+    mmc = mm;
     cmp = tl;
     const double dl = (double)tl;
     mmrate = __ddiv_rn((double)(float)(int)mm, dl);                      // :132
@@ -509,30 +580,39 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
     const u64 nf = P.counters[HC_CNT_FLAGGED];
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nf; t += (u64)gridDim.x * blockDim.x) {
         const u64 i = P.flagged[t];
-        const hc_candidate c = P.cand[i];
+        const hc_candidate c = load_candidate(P.cand + i);
         CandSetup s;
-        setup_candidate(P, c, s);
-        if (s.err) continue;
-        double ov[2] = {0.0, 0.0}, mmr[2] = {1.0, 1.0};
+        uint4 r1, r2;
+        if (!load_and_setup(P, c, s, r1, r2)) continue;
+        double mean[2], mmr[2] = {1.0, 1.0};
         int ae[2], ao[2];
         uint32_t mmc[2], cmp[2], stt[2];
 #pragma unroll
         for (int w = 0; w < 2; w++) {
-            double mean;
-            exact_window(P, s.w[w], mean, mmr[w], mmc[w], cmp[w], stt[w]);
+            exact_window(P, s.w[w], mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
             if (stt[w] == HC_WIN_SCORED) {
-                ov[w] = exp(mean);
-                ae[w] = mean >= P.t_edge;   // <=> host-libm exp(mean) > edge_threshold
-                ao[w] = mean >= P.t_ov;
+                ae[w] = mean[w] >= P.t_edge;   // <=> host-libm exp(mean) > edge_threshold
+                ao[w] = mean[w] >= P.t_ov;
             } else {
                 ae[w] = P.zero_above_edge;
                 ao[w] = P.zero_above_ov;
             }
         }
-        double score, mmrate;
-        uint32_t cls;
-        combine(P, s.two, ov, mmr, ae, ao, score, mmrate, cls);
-        write_result(P, i, s, score, mmrate, cls, mmc, cmp, stt, 1);
+        double mmrate;
+        const uint32_t cls = classify(P, s.two, mmr, ae, ao, mmrate) | HC_CLS_EXACT;
+        P.cls[i] = (uint8_t)cls;
+        if ((cls & HC_CLS_MASK) == HC_CLASS_EDGE) {
+            hc_tmp32 tm;
+            tm.S[0] = (u64)__double_as_longlong(mean[0]);
+            tm.S[1] = (u64)__double_as_longlong(mean[1]);
+            tm.tl[0] = cmp[0]; tm.tl[1] = cmp[1];
+            tm.mismatch_rate = mmrate;
+            P.tmp[i] = tm;
+        }
+        if (P.per_cand) {
+            const double ov0 = cmp[0] ? exp(mean[0]) : 0.0, ov1 = cmp[1] ? exp(mean[1]) : 0.0;
+            write_per_cand(P, i, c, r1, r2, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), mmrate, cls, mmc, cmp, stt, 1);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[HC_CNT_EXACT] = nf;
 }
@@ -547,7 +627,7 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_count(const uint8_t*
     for (uint32_t k = threadIdx.x; k < HC_CB_ITEMS; k += HC_CB_THREADS) {
         const u64 i = base + k;
         if (i < n) {
-            const uint32_t c = cls[i];
+            const uint32_t c = cls[i] & HC_CLS_MASK;
             e += c == HC_CLASS_EDGE;
             o += c == HC_CLASS_NONEDGE;
         }
@@ -621,7 +701,8 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t k0 = 0; k0 < HC_CB_ITEMS; k0 += HC_CB_THREADS) {
         const u64 i = base + k0 + threadIdx.x;
-        const uint32_t c = i < P.n ? P.cls[i] : HC_CLASS_DISCARD;
+        const uint32_t cfull = i < P.n ? P.cls[i] : HC_CLASS_DISCARD;
+        const uint32_t c = cfull & HC_CLS_MASK;
         const uint32_t be = __ballot_sync(0xffffffffu, c == HC_CLASS_EDGE);
         const uint32_t bo = __ballot_sync(0xffffffffu, c == HC_CLASS_NONEDGE);
         if (lane == 0) { we[warp] = __popc(be); wo[warp] = __popc(bo); }
@@ -636,16 +717,24 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
         if (c == HC_CLASS_EDGE) {
             const u64 dst = eoff + pe + __popc(be & lt);
             if (dst < edges_cap) {
-                const hc_candidate cd = P.cand[i];
-                CandSetup s;
-                setup_candidate(P, cd, s);
-                const hc_score16 t = P.tmp[i];
+                // Edge::score (:138, :256-261) for accepted edges only
+                const hc_candidate cd = load_candidate(P.cand + i);
+                const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx1));
+                const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx2));
+                const hc_tmp32 t = P.tmp[i];
+                double ov[2];
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    if (t.tl[w] == 0) ov[w] = 0.0;
+                    else if (cfull & HC_CLS_EXACT) ov[w] = exp(__longlong_as_double((long long)t.S[w]));
+                    else ov[w] = exp(fx_mean(t.S[w], t.tl[w]));
+                }
+                const uint32_t two = ((r1.w | r2.w) & HC_LEN_MASK) != 0;
                 hc_edge e;
                 e.cand = i + cand_offset;
-                e.score = t.score;
+                e.score = combine_score(two, cfull & HC_CLS_BOTH, ov[0], ov[1]);
                 e.mismatch_rate = t.mismatch_rate;
-                e.pos3 = s.pos3;
-                e.pos4 = s.pos4;
+                extra_pos(cd, r1, r2, e.pos3, e.pos4);
                 edges[dst] = e;
             }
         } else if (c == HC_CLASS_NONEDGE) {

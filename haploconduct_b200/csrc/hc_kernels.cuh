@@ -8,14 +8,22 @@
 #include "hc_layout.h"
 
 #define HC_WARPS_MAX 12
-#define HC_PARTMAX 512u          // chunk partials per warp round (x 8 B = 4 KB of shared memory)
-#define HC_BIG_CHUNKS 64u        // candidates with >= this many chunks are scored warp-cooperatively
+#define HC_LANE_CHUNK 32u        // positions one lane handles per step (two 16-position halves)
+#define HC_PARTMAX 512u          // lane-chunk partials per warp round (x 8 B = 4 KB of shared memory)
+#define HC_BIG_CHUNKS 64u        // candidates with >= this many lane-chunks are scored warp-cooperatively
 #define HC_WINSLOTS 64u          // 2 windows x 32 candidates
 // per-warp scratch: partials + window descriptors (16 B + 8 B per slot) + head bitmap
 #define HC_WARP_SCRATCH (HC_PARTMAX * 8u + HC_WINSLOTS * 16u + HC_WINSLOTS * 8u + (HC_PARTMAX / 32u) * 4u)
 
-struct hc_score16 {   // per-candidate scratch record: what the ordered compaction needs
-    double score;
+// class byte written per candidate: HC_CLASS_* in bits 0-1
+#define HC_CLS_MASK 3u
+#define HC_CLS_BOTH 4u           // every window is above edge_threshold (selects 0.5*(ov1+ov2) vs min, :256-261)
+#define HC_CLS_EXACT 8u          // decided by the reference-order pass; hc_tmp32.S holds the exact mean logs
+
+// Scratch record, written for accepted edges only: what the ordered compaction needs to emit hc_edge.
+struct hc_tmp32 {
+    unsigned long long S[2];     // fixed-point sum of -log p per window, or bits of the exact mean log (HC_CLS_EXACT)
+    uint32_t tl[2];              // compared (non-N) positions per window; 0 = window not scored (score 0)
     double mismatch_rate;
 };
 
@@ -35,7 +43,7 @@ struct hc_kparams {
     // batch
     const hc_candidate* cand;
     uint64_t n;
-    hc_score16* tmp;
+    hc_tmp32* tmp;
     uint8_t* cls;
     hc_result* per_cand;        // nullable
     uint32_t* flagged;          // candidate indices that need the reference-order pass
@@ -43,10 +51,14 @@ struct hc_kparams {
     // decisions (src/EdgeCalculator.cpp:404-413, thresholds moved into log space on the host)
     double t_edge;              // smallest mean with exp(mean) > edge_threshold
     double t_ov;                // smallest mean with exp(mean) > ov_threshold
+    // fixed-point form: S <= c_up * total_len  <=>  surely above;  S > c_dn * total_len  <=>  surely below
+    double ce_up, ce_dn, co_up, co_dn;
     double merge_contigs;
     uint32_t min_read_len;
     uint32_t zero_above_edge;   // 0 > edge_threshold ?
     uint32_t zero_above_ov;     // 0 > ov_threshold ?
+    uint32_t never_edge;        // t_edge > 0: a mean (<= 0) can never reach it
+    uint32_t never_ov;
     uint32_t exact_edges;       // HC_FLAG_EXACT_EDGE_SCORES
 };
 

@@ -47,7 +47,8 @@ class PairedReads:
 
 def make_paired_reads(n_pairs: int, read_len: int = 150, genome_len: int = 100_000, n_hap: int = 4,
                       divergence=(0.0, 0.005, 0.01, 0.02), insert=(450.0, 50.0), n_rate: float = 0.0005,
-                      seed: int = 20261018, device: str = "cpu", chunk: int = 1 << 20) -> PairedReads:
+                      seed: int = 20261018, device: str = "cpu", chunk: int = 1 << 20,
+                      position_sorted_ids: bool = False) -> PairedReads:
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -66,11 +67,14 @@ def make_paired_reads(n_pairs: int, read_len: int = 150, genome_len: int = 100_0
     ar = torch.arange(L, device=dev)
     qmean = (36.0 - 8.0 * ar.float() / max(L - 1, 1))[None, :]
     acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    # diagnostic layout only: read IDs in genome-position order (partners become neighbours in memory)
+    u_all = torch.sort(torch.rand(n_pairs, generator=g, device=dev))[0] if position_sorted_ids else None
     for lo in range(0, n_pairs, chunk):
         m = min(chunk, n_pairs - lo)
         hap = torch.randint(0, n_hap, (m,), generator=g, device=dev)
         ins = torch.clamp(torch.round(insert[0] + insert[1] * torch.randn(m, generator=g, device=dev)), L, genome_len).long()
-        st = (torch.rand(m, generator=g, device=dev) * (genome_len - ins + 1).float()).long()
+        u = u_all[lo:lo + m] if position_sorted_ids else torch.rand(m, generator=g, device=dev)
+        st = (u * (genome_len - ins + 1).float()).long()
         st = torch.minimum(st, genome_len - ins)
         s1 = st
         s2 = st + ins - L
