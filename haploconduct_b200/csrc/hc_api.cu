@@ -37,7 +37,8 @@ struct DevCtx {
     int sm_count = 0;
     size_t smem_per_sm = 0;
     // store planes
-    uint8_t* qual = nullptr;
+    uint8_t* pk = nullptr;       // packed layout (code | base << 6), or
+    uint8_t* qual = nullptr;     // planar layout: quality codes, 2-bit bases, N mask
     uint32_t* base2 = nullptr;
     uint32_t* nmask = nullptr;
     hc_rdesc* rdesc = nullptr;
@@ -73,6 +74,7 @@ struct hc_store {
     uint64_t n_reads = 0, n_single = 0;
     uint64_t total_positions = 0;
     int ncodes = 0;
+    bool packed = false;          // one byte per position (<= 63 quality codes); else three planes
     int code_to_q[HC_MAX_CODES + 1];
     int q_to_code[256];
     std::vector<DevCtx> devs;
@@ -87,7 +89,7 @@ namespace {
 void free_ctx(DevCtx& d) {
     if (d.device < 0) return;
     cudaSetDevice(d.device);
-    cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc);
+    cudaFree(d.pk); cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc);
     cudaFree(d.fx_table); cudaFree(d.dbl_table);
     cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts); cudaFree(d.counters);
     cudaFree(d.d_cand); cudaFree(d.d_edges); cudaFree(d.d_nonedge); cudaFree(d.d_per_cand); cudaFree(d.d_counts);
@@ -120,9 +122,10 @@ int ensure_tables(hc_store* s, DevCtx& d, double mismatch, cudaStream_t st) {
     if (d.tables_valid && d.tables_mismatch == mismatch) return HC_OK;
     // synchronous upload: tables change only when ps.mismatch changes (it never does in the drivers)
     CU(cudaStreamSynchronize(st));
-    if (!d.fx_table) CU(cudaMalloc(&d.fx_table, s->tables.fx.size() * sizeof(uint32_t)));
+    const std::vector<uint32_t>& fx = s->packed ? s->tables.fx_packed : s->tables.fx;
+    if (!d.fx_table) CU(cudaMalloc(&d.fx_table, fx.size() * sizeof(uint32_t)));
     if (!d.dbl_table) CU(cudaMalloc(&d.dbl_table, s->tables.dbl.size() * sizeof(double)));
-    CU(cudaMemcpy(d.fx_table, s->tables.fx.data(), s->tables.fx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.fx_table, fx.data(), fx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.dbl_table, s->tables.dbl.data(), s->tables.dbl.size() * sizeof(double), cudaMemcpyHostToDevice));
     d.tables_valid = true;
     d.tables_mismatch = mismatch;
@@ -164,6 +167,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     hc_kparams P;
     memset(&P, 0, sizeof(P));
     P.qual = d.qual; P.base2 = d.base2; P.nmask = d.nmask; P.rdesc = d.rdesc;
+    P.pk = d.pk; P.packed = s->packed ? 1u : 0u;
     P.n_reads = (uint32_t)s->n_reads; P.n_single = (uint32_t)s->n_single;
     P.fx_table = d.fx_table; P.dbl_table = d.dbl_table; P.ncodes = (uint32_t)s->ncodes; P.has_void = d.has_void ? 1u : 0u;
     P.cand = d_cand; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
@@ -255,7 +259,8 @@ int hc_store_n_devices(const hc_store* s) { return s ? (int)s->devs.size() : 0; 
 int hc_store_quality_alphabet(const hc_store* s) { return s ? s->ncodes : 0; }
 uint64_t hc_store_device_bytes(const hc_store* s) {
     if (!s) return 0;
-    return s->total_positions + s->total_positions / 4 + s->total_positions / 8 + s->n_reads * sizeof(hc_rdesc);
+    const uint64_t planes = s->packed ? s->total_positions : s->total_positions + s->total_positions / 4 + s->total_positions / 8;
+    return planes + s->n_reads * sizeof(hc_rdesc);
 }
 
 void hc_store_destroy(hc_store* s) {
@@ -350,12 +355,17 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
         }
     }
     // ---- pass 2: pack both strands
+    const char* layout = getenv("HC_STORE_LAYOUT");   // "planar" forces the three-plane layout (tests)
+    s->packed = s->ncodes <= HC_PACKED_MAX_CODES && !(layout && strcmp(layout, "planar") == 0);
+    const bool packed = s->packed;
     std::vector<uint8_t> hq;
     std::vector<uint32_t> hb, hn;
     try {
         hq.assign(total, 0);
-        hb.assign(total / 16, 0);
-        hn.assign(total / 32, 0);
+        if (!packed) {
+            hb.assign(total / 16, 0);
+            hn.assign(total / 32, 0);
+        }
     } catch (...) {
         fail(HC_ERR_NOMEM, "hc_store_create: host staging allocation failed");
         delete s;
@@ -375,14 +385,21 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
                 const uint64_t pf = fwd + i, pr = rev + (len - 1 - i);
                 if (bc == 4) {
                     hasN = true;          // N: code 0 quality (contributes nothing), base bits 0, mask bit set
-                    hn[pf >> 5] |= 1u << (pf & 31);
-                    hn[pr >> 5] |= 1u << (pr & 31);
+                    if (!packed) {
+                        hn[pf >> 5] |= 1u << (pf & 31);
+                        hn[pr >> 5] |= 1u << (pr & 31);
+                    }
                 } else {
                     const uint8_t code = (uint8_t)s->q_to_code[q[i]];
-                    hq[pf] = code;
-                    hq[pr] = code;                                   // reversed qualities, src/Read.h:187-201
-                    hb[pf >> 4] |= (uint32_t)bc << (2 * (pf & 15));
-                    hb[pr >> 4] |= (uint32_t)(3 - bc) << (2 * (pr & 15));   // complement, src/Types.h:109-129
+                    if (packed) {
+                        hq[pf] = (uint8_t)(code | (bc << 6));
+                        hq[pr] = (uint8_t)(code | ((3 - bc) << 6));      // reversed qualities + complement
+                    } else {
+                        hq[pf] = code;
+                        hq[pr] = code;                                   // reversed qualities, src/Read.h:187-201
+                        hb[pf >> 4] |= (uint32_t)bc << (2 * (pf & 15));
+                        hb[pr >> 4] |= (uint32_t)(3 - bc) << (2 * (pr & 15));   // complement, src/Types.h:109-129
+                    }
                 }
             }
             if (hasN) rd[r].len[m] |= HC_HASN_BIT;
@@ -408,17 +425,18 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
         }
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
         for (int j = 0; j < 6 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
-        if (e == cudaSuccess) e = cudaMalloc(&d.qual, total + 64);
-        if (e == cudaSuccess) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);
+        uint8_t** qplane = packed ? &d.pk : &d.qual;
+        if (e == cudaSuccess) e = cudaMalloc(qplane, total + 64);
+        if (e == cudaSuccess && !packed) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
+        if (e == cudaSuccess && !packed) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);
         if (e == cudaSuccess) e = cudaMalloc(&d.rdesc, n_reads * sizeof(hc_rdesc));
         if (e == cudaSuccess) e = cudaMalloc(&d.d_counts, 4 * sizeof(uint64_t));
-        if (e == cudaSuccess) e = cudaMemset(d.qual + total, 0, 64);
-        if (e == cudaSuccess) e = cudaMemset(d.base2 + total / 16, 0, 64);
-        if (e == cudaSuccess) e = cudaMemset(d.nmask + total / 32, 0, 64);
-        if (e == cudaSuccess) e = cudaMemcpy(d.qual, hq.data(), total, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d.base2, hb.data(), total / 16 * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d.nmask, hn.data(), total / 32 * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(*qplane + total, 0, 64);
+        if (e == cudaSuccess && !packed) e = cudaMemset(d.base2 + total / 16, 0, 64);
+        if (e == cudaSuccess && !packed) e = cudaMemset(d.nmask + total / 32, 0, 64);
+        if (e == cudaSuccess) e = cudaMemcpy(*qplane, hq.data(), total, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && !packed) e = cudaMemcpy(d.base2, hb.data(), total / 16 * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && !packed) e = cudaMemcpy(d.nmask, hn.data(), total / 32 * 4, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(d.rdesc, rd.data(), n_reads * sizeof(hc_rdesc), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA,

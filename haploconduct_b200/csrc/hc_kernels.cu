@@ -137,6 +137,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void prefetch_window(const hc_kparams& P, const Win& w) {
     if (w.L == 0) return;
     const uint32_t n = min(w.L, 512u);
+    if (P.packed) {
+        const uint8_t* xa = P.pk + (w.xpos & ~127ull);
+        const uint32_t xe = (uint32_t)(w.xpos & 127ull) + n;
+        for (uint32_t o = 0; o < xe; o += 128) prefetch_l2(xa + o);
+        const uint8_t* ya = P.pk + 16ull * w.ypos16;
+        for (uint32_t o = 0; o < n; o += 128) prefetch_l2(ya + o);
+        return;
+    }
     const uint8_t* xa = P.qual + (w.xpos & ~127ull);
     const uint32_t xe = (uint32_t)(w.xpos & 127ull) + n;
     for (uint32_t o = 0; o < xe; o += 128) prefetch_l2(xa + o);
@@ -246,6 +254,78 @@ __device__ __forceinline__ void process32(const hc_kparams& P, const uint32_t* _
     vd = HAS_VOID ? ((orv & HC_VOID_BIT) ? 1u : 0u) : 0u;
 }
 
+// ---- packed layout (<= 63 quality codes): one byte per position = code | base << 6 ----------------------
+// Re-align the A side exactly as in the planar kernel; the XOR of A and (swizzled) B bytes is at
+// once the table column and, in bits 6-7, the base difference.  Mismatch flags of the 8 words are
+// gathered into one 32-bit word (OR_j flags_j >> j) so that a single popc counts them.
+template <bool HAS_VOID>
+__device__ __forceinline__ void process32_packed(const hc_kparams& P, const uint32_t* __restrict__ T,
+                                                 const uint32_t* __restrict__ VM, u64 xpos, uint32_t ypos16, uint32_t L,
+                                                 uint32_t hasN, uint32_t k, uint32_t& sum, uint32_t& mm, uint32_t& ncnt,
+                                                 uint32_t& vd) {
+    const u64 xp = xpos + 32ull * k;
+    const uint32_t n = min(L - 32u * k, 32u);   // 1..32 valid positions
+    const uint32_t yq = ypos16 + 2u * k;
+    const uint32_t off = (uint32_t)xp & 15u;
+    const bool two = n > 16u, x1 = off + n > 16u, x2 = off + n > 32u;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    const uint4* xq = reinterpret_cast<const uint4*>(P.pk + (xp & ~15ull));
+    const uint4 q0 = __ldg(xq);
+    const uint4 q1 = x1 ? __ldg(xq + 1) : z4;
+    const uint4 q2 = x2 ? __ldg(xq + 2) : z4;
+    const uint4* yqp = reinterpret_cast<const uint4*>(P.pk) + yq;
+    const uint4 y0 = __ldg(yqp);
+    const uint4 y1 = two ? __ldg(yqp + 1) : z4;
+    const uint32_t vm = VM[n];
+    const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    const bool s2 = (off & 8u) != 0, s1 = (off & 4u) != 0;
+    uint32_t V1[10], V[9];
+#pragma unroll
+    for (int i = 0; i < 10; i++) V1[i] = s2 ? W[i + 2] : W[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t wy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    uint32_t acc = 0, orv = 0, flags = 0, vw = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t wa = __funnelshift_r(V[j], V[j + 1], sh);
+        const uint32_t wb = wy[j];
+        const uint32_t col = wa ^ hc_swz4_packed(wb);
+        const uint32_t row = wb & 0x3f3f3f3fu;
+        flags |= ((col | (col << 1)) & 0x80808080u) >> j;
+        if (hasN) {   // a zero byte inside the window is an N (valid bases carry a code >= 1)
+            const uint32_t nzA = (((wa & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wa), nzB = (((wb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wb);
+            vw |= ((nzA & nzB) & 0x80808080u) >> j;
+        }
+        const uint32_t t0 = T[prmt(col, row, 0xCC40u)];
+        const uint32_t t1 = T[prmt(col, row, 0xDD51u)];
+        const uint32_t t2 = T[prmt(col, row, 0xEE62u)];
+        const uint32_t t3 = T[prmt(col, row, 0xFF73u)];
+        acc += (t0 + t1) + (t2 + t3);
+        if (HAS_VOID) orv |= (t0 | t1) | (t2 | t3);
+    }
+    ncnt = 0;
+    if (hasN) {
+        const uint32_t valid = vw & vm;
+        ncnt = n - __popc(valid);
+        flags &= valid;
+    } else {
+        flags &= vm;
+    }
+    mm = __popc(flags);
+    sum = acc;
+    vd = HAS_VOID ? ((orv & HC_VOID_BIT) ? 1u : 0u) : 0u;
+}
+
+template <bool HAS_VOID, bool PACKED>
+__device__ __forceinline__ void process_chunk(const hc_kparams& P, const uint32_t* __restrict__ T, const uint32_t* __restrict__ VM,
+                                              u64 xpos, uint32_t ypos16, uint32_t L, uint32_t hasN, uint32_t k, uint32_t& sum,
+                                              uint32_t& mm, uint32_t& ncnt, uint32_t& vd) {
+    if (PACKED) process32_packed<HAS_VOID>(P, T, VM, xpos, ypos16, L, hasN, k, sum, mm, ncnt, vd);
+    else process32<HAS_VOID>(P, T, xpos, ypos16, L, hasN, k, sum, mm, ncnt, vd);
+}
+
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -311,12 +391,14 @@ __device__ __forceinline__ void write_per_cand(const hc_kparams& P, u64 i, const
     P.per_cand[i] = r;
 }
 
-template <bool HAS_VOID>
+template <bool HAS_VOID, bool PACKED>
 __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc_kparams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* T = reinterpret_cast<uint32_t*>(smem);
-    const uint32_t tbl_entries = (P.ncodes + 1u) * 256u;
-    for (uint32_t i = threadIdx.x; i < tbl_entries; i += blockDim.x) T[i] = P.fx_table[i];
+    const uint32_t tbl_entries = (P.ncodes + 1u) * 256u + HC_VM_WORDS;   // score table, then the tail masks
+    uint32_t* VM = T + (tbl_entries - HC_VM_WORDS);
+    for (uint32_t i = threadIdx.x; i < tbl_entries - HC_VM_WORDS; i += blockDim.x) T[i] = P.fx_table[i];
+    if (threadIdx.x < HC_VM_WORDS) VM[threadIdx.x] = hc_packed_vmask(threadIdx.x);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -375,7 +457,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                 uint32_t mm = 0, nn = 0, vd = 0;
                 for (uint32_t k = lane; k < cw; k += 32) {
                     uint32_t sum, m1, n1, v1;
-                    process32<HAS_VOID>(P, T, xpos, yp, Lw, hn, k, sum, m1, n1, v1);
+                    process_chunk<HAS_VOID, PACKED>(P, T, VM, xpos, yp, Lw, hn, k, sum, m1, n1, v1);
                     S += sum; mm += m1; nn += n1; vd |= v1;
                 }
 #pragma unroll
@@ -429,7 +511,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                     const uint4 a = wdA[slot];
                     const uint2 b = wdB[slot];
                     uint32_t sum, m1, n1, v1;
-                    process32<HAS_VOID>(P, T, ((u64)a.y << 32) | a.x, a.z, a.w, b.y, f - b.x, sum, m1, n1, v1);
+                    process_chunk<HAS_VOID, PACKED>(P, T, VM, ((u64)a.y << 32) | a.x, a.z, a.w, b.y, f - b.x, sum, m1, n1, v1);
                     part[f] = make_uint2(sum, m1 | (n1 << 12) | (v1 << 24));
                 }
                 running += __popc(hw);
@@ -557,11 +639,18 @@ __device__ void exact_window(const hc_kparams& P, const Win& w, double& mean, do
     const u64 yp = 16ull * w.ypos16;
     for (uint32_t i = 0; i < w.L; i++) {
         const u64 xa = w.xpos + i, xb = yp + i;
-        const uint32_t nA = (P.nmask[xa >> 5] >> (xa & 31)) & 1u, nB = (P.nmask[xb >> 5] >> (xb & 31)) & 1u;
-        if (nA | nB) continue;                                            // :35-39,:122-124
-        const uint32_t a = (P.base2[xa >> 4] >> (2 * (xa & 15))) & 3u, b = (P.base2[xb >> 4] >> (2 * (xb & 15))) & 3u;
-        const uint32_t qa = P.qual[xa], qb = P.qual[xb];
-        const uint32_t mis = a != b;
+        uint32_t qa, qb, mis;
+        if (P.packed) {
+            const uint32_t a = P.pk[xa], b = P.pk[xb];
+            if (a == 0 || b == 0) continue;                                   // N, :35-39,:122-124
+            qa = a & 63u; qb = b & 63u; mis = (a >> 6) != (b >> 6);
+        } else {
+            const uint32_t nA = (P.nmask[xa >> 5] >> (xa & 31)) & 1u, nB = (P.nmask[xb >> 5] >> (xb & 31)) & 1u;
+            if (nA | nB) continue;                                            // :35-39,:122-124
+            const uint32_t a = (P.base2[xa >> 4] >> (2 * (xa & 15))) & 3u, b = (P.base2[xb >> 4] >> (2 * (xb & 15))) & 3u;
+            qa = P.qual[xa]; qb = P.qual[xb];
+            mis = a != b;
+        }
         mm += mis;
         const double lp = P.dbl_table[hc_dbl_index(qa, qb, mis, n1)];
         if (lp > 0.0) { status = HC_WIN_VOID; return; }                  // :125-127
@@ -751,7 +840,7 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
 
 // ---- launchers ----------------------------------------------------------------------------------------
 cudaError_t hc_score_occupancy(uint32_t ncodes, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg) {
-    const size_t table = (size_t)(ncodes + 1u) * 1024u;
+    const size_t table = (size_t)(ncodes + 1u) * 1024u + HC_VM_WORDS * 4u;
     int best_warps = 0, best_nw = 0, best_ctas = 0;
     const int options[2] = {HC_WARPS_MAX, 8};
     for (int o = 0; o < 2; o++) {
@@ -771,16 +860,11 @@ cudaError_t hc_score_occupancy(uint32_t ncodes, int sm_count, size_t smem_per_sm
 }
 
 cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaStream_t st) {
-    cudaError_t e;
-    if (P.has_void) {
-        e = cudaFuncSetAttribute(hc_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
-        if (e != cudaSuccess) return e;
-        hc_score_kernel<true><<<cfg.blocks, cfg.threads, cfg.smem, st>>>(P);
-    } else {
-        e = cudaFuncSetAttribute(hc_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
-        if (e != cudaSuccess) return e;
-        hc_score_kernel<false><<<cfg.blocks, cfg.threads, cfg.smem, st>>>(P);
-    }
+    void (*fn)(const hc_kparams) = P.packed ? (P.has_void ? hc_score_kernel<true, true> : hc_score_kernel<false, true>)
+                                            : (P.has_void ? hc_score_kernel<true, false> : hc_score_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    if (e != cudaSuccess) return e;
+    fn<<<cfg.blocks, cfg.threads, cfg.smem, st>>>(P);
     return cudaGetLastError();
 }
 

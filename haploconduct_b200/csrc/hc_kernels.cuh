@@ -12,6 +12,7 @@
 #define HC_PARTMAX 512u          // lane-chunk partials per warp round (x 8 B = 4 KB of shared memory)
 #define HC_BIG_CHUNKS 64u        // candidates with >= this many lane-chunks are scored warp-cooperatively
 #define HC_WINSLOTS 64u          // 2 windows x 32 candidates
+#define HC_VM_WORDS 64u          // tail-mask table of the packed layout (33 used), kept behind the score table
 // per-warp scratch: partials + window descriptors (16 B + 8 B per slot) + head bitmap
 #define HC_WARP_SCRATCH (HC_PARTMAX * 8u + HC_WINSLOTS * 16u + HC_WINSLOTS * 8u + (HC_PARTMAX / 32u) * 4u)
 
@@ -32,7 +33,9 @@ struct hc_kparams {
     const uint8_t* qual;
     const uint32_t* base2;
     const uint32_t* nmask;
+    const uint8_t* pk;          // packed layout: code | base << 6 per position (qual/base2/nmask are NULL then)
     const hc_rdesc* rdesc;
+    uint32_t packed;
     uint32_t n_reads;
     uint32_t n_single;
     // tables

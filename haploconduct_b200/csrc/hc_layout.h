@@ -61,6 +61,24 @@ HC_HD uint32_t hc_swz1(uint32_t cb) { return ((cb << 1) & 0x7eu) | (cb & 1u); }
 HC_HD uint32_t hc_fx_index(uint32_t ca, uint32_t cb, uint32_t mm) {
     return (cb << 8) | ((ca ^ hc_swz1(cb)) & 0x7fu) | (mm << 7);
 }
+// Packed ("narrow") layout, used when the store has at most 63 distinct quality values:
+//   one byte per position = quality code (bits 0-5, 0 = N or padding) | 2-bit base << 6.
+// XOR of an A byte with a B byte then carries the base difference in bits 6-7 for free; the table
+// column is ((code_A ^ g6(code_B)) & 63) | (base_A ^ base_B) << 6  (columns 64..255 = mismatch).
+#define HC_PACKED_MAX_CODES 63
+HC_HD uint32_t hc_swz4_packed(uint32_t wb) { return ((wb << 1) & 0x3e3e3e3eu) | (wb & 0xc1c1c1c1u); }
+HC_HD uint32_t hc_swz1_packed(uint32_t cb) { return ((cb << 1) & 0x3eu) | (cb & 1u); }
+HC_HD uint32_t hc_fx_index_packed(uint32_t ca, uint32_t cb, uint32_t bx) {
+    return (cb << 8) | ((ca ^ hc_swz1_packed(cb)) & 0x3fu) | (bx << 6);
+}
+// Mismatch flags of a 32-position lane-chunk are gathered as OR_j (flags(word j) >> j): position
+// p = 4j + t lands on bit 8t + 7 - j.  Mask of the first n positions in that bit order:
+HC_HD uint32_t hc_packed_vmask(uint32_t n) {
+    uint32_t m = 0;
+    for (uint32_t p = 0; p < n && p < 32u; p++) m |= 1u << (8u * (p & 3u) + 7u - (p >> 2));
+    return m;
+}
+
 // index into the double table used by the reference-order pass
 HC_HD uint32_t hc_dbl_index(uint32_t ca, uint32_t cb, uint32_t mm, uint32_t ncodes1) {
     return ((ca * ncodes1) + cb) * 2u + mm;

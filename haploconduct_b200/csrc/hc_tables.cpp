@@ -22,6 +22,8 @@ void hc_build_tables(const int* code_to_q, int ncodes, double mismatch_param, hc
     out->ncodes = ncodes;
     out->dbl.assign((size_t)n1 * n1 * 2, 0.0);
     out->fx.assign((size_t)n1 * 256, 0u);
+    const bool packed = ncodes <= HC_PACKED_MAX_CODES;
+    out->fx_packed.assign(packed ? (size_t)n1 * 256 : 0, 0u);
     out->has_void = false;
     for (int ca = 1; ca <= ncodes; ca++) {
         for (int cb = 1; cb <= ncodes; cb++) {
@@ -45,6 +47,10 @@ void hc_build_tables(const int* code_to_q, int ncodes, double mismatch_param, hc
                 }
                 out->dbl[hc_dbl_index(ca, cb, mm, n1)] = lp;
                 out->fx[hc_fx_index(ca, cb, mm)] = fx;
+                if (packed) {
+                    if (!mm) out->fx_packed[hc_fx_index_packed(ca, cb, 0)] = fx;
+                    else for (uint32_t bx = 1; bx < 4; bx++) out->fx_packed[hc_fx_index_packed(ca, cb, bx)] = fx;
+                }
             }
         }
     }

@@ -10,6 +10,7 @@ struct hc_tables {
     bool has_void;               // some (qa,qb,mm) has p < ps.mismatch
     std::vector<double> dbl;     // [(K+1)*(K+1)*2] log(p), exact reference addends (2.0 = void sentinel)
     std::vector<uint32_t> fx;    // [(K+1)*256] round(-log(p)*2^22), swizzled layout of hc_fx_index()
+    std::vector<uint32_t> fx_packed;  // same values in the hc_fx_index_packed() layout (K <= 63 only, else empty)
 };
 
 double hc_tables_phred_to_prob(int phred);

@@ -62,9 +62,11 @@ void      hc_store_destroy(hc_store* s);
 uint64_t  hc_store_n_reads(const hc_store* s);
 uint64_t  hc_store_n_single(const hc_store* s);
 int       hc_store_n_devices(const hc_store* s);
-/* bytes of device memory one replica occupies (bases 2-bit + N-mask 1-bit + quality bytes, both strands) */
+/* bytes of device memory one replica occupies: both strands of every sequence, either packed
+ * (<= 63 distinct quality values: one byte per base = 6-bit quality code | 2-bit base) or as three
+ * planes (quality code bytes, 2-bit bases, 1-bit N mask) */
 uint64_t  hc_store_device_bytes(const hc_store* s);
-/* number of distinct quality values present (decides the 6-bit "narrow" vs 7-bit "wide" kernel) */
+/* number of distinct quality values present (decides the packed vs three-plane layout) */
 int       hc_store_quality_alphabet(const hc_store* s);
 
 /* ------------------------------------------------------------------------------------------

@@ -14,6 +14,14 @@ from util import assert_results_match, golden_names, load_golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["packed", "planar"])
+def store_layout(request, monkeypatch):
+    """Every test runs on both device layouts: the packed one (one byte per base, used when the store
+    has <= 63 distinct quality values) and the three-plane one (forced through HC_STORE_LAYOUT)."""
+    monkeypatch.setenv("HC_STORE_LAYOUT", "planar" if request.param == "planar" else "auto")
+    return request.param
+
+
 def _check_lists(edges, nonedge, per, n):
     """edges / non-edges are exactly the class-1 / class-2 candidates, in input order."""
     ei = np.nonzero(per["cls"] == F.CLASS_EDGE)[0]
