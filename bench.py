@@ -233,7 +233,7 @@ def main() -> None:
     torch.cuda.synchronize()
     log("[rank %d] %d candidates (shard %d/%d) generated in %.1fs" % (rank, n, shard, N_SHARDS, time.time() - t1))
     params = F.make_params(**PARAMS)
-    d_edges = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    d_edges = torch.empty((n, 48), dtype=torch.uint8, device=dev)
     d_nonedge = torch.empty(n, dtype=torch.int64, device=dev)
     d_counts = torch.zeros(4, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream(dev)
@@ -279,7 +279,7 @@ def main() -> None:
         h_cand = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
         h_cand.copy_(rec)
         ne, nn = int(counts[0]), int(counts[1])
-        h_edges = torch.empty((max(ne, 1) + 1024, 32), dtype=torch.uint8, pin_memory=True)
+        h_edges = torch.empty((max(ne, 1) + 1024, 48), dtype=torch.uint8, pin_memory=True)
         h_nonedge = torch.empty(max(nn, 1) + 1024, dtype=torch.int64, pin_memory=True)
         import ctypes
         L = capi.lib()
@@ -301,7 +301,7 @@ def main() -> None:
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert c_ne.value == ne and c_nn.value == nn
-        e2e = (e2e_ms, n * 32, ne * 32 + nn * 8 + 32)
+        e2e = (e2e_ms, n * 32, ne * 48 + nn * 8 + 32)
 
     ms_step = ms_total / args.steps
     tvals = torch.tensor([ms_step, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)

@@ -26,7 +26,9 @@ def _newer(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "hc_b200.h")]
+    hostdir = os.path.join(HERE, "host")
+    deps = ([os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(hostdir, f) for f in os.listdir(hostdir)]
+            + [os.path.join(HERE, "..", "include", "hc_b200.h")])
     if not force and not _newer(LIB, deps):
         return LIB
     objs = []
@@ -50,7 +52,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    build_host(verbose)
     return LIB
+
+
+def build_host(verbose: bool = False) -> str:
+    """hc_edgecalc: the C++ host mirror of the reference's EdgeCalculator stage, linked against the C ABI."""
+    host = os.path.join(HERE, "host")
+    exe = os.path.join(LIBDIR, "hc_edgecalc")
+    cmd = [HOST_CXX, "-O2", "-std=c++14", "-Wall", "-o", exe, os.path.join(host, "hc_edgecalc_main.cpp"),
+           os.path.join(host, "hcb_host.cpp"), "-L" + LIBDIR, "-lhc_b200", "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return exe
 
 
 if __name__ == "__main__":

@@ -811,12 +811,13 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
                 const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx1));
                 const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx2));
                 const hc_tmp32 t = P.tmp[i];
-                double ov[2];
+                double ov[2], ml[2];
 #pragma unroll
                 for (int w = 0; w < 2; w++) {
-                    if (t.tl[w] == 0) ov[w] = 0.0;
-                    else if (cfull & HC_CLS_EXACT) ov[w] = exp(__longlong_as_double((long long)t.S[w]));
-                    else ov[w] = exp(fx_mean(t.S[w], t.tl[w]));
+                    if (t.tl[w] == 0) ml[w] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: window not scored
+                    else if (cfull & HC_CLS_EXACT) ml[w] = __longlong_as_double((long long)t.S[w]);
+                    else ml[w] = fx_mean(t.S[w], t.tl[w]);
+                    ov[w] = t.tl[w] ? exp(ml[w]) : 0.0;
                 }
                 const uint32_t two = ((r1.w | r2.w) & HC_LEN_MASK) != 0;
                 hc_edge e;
@@ -824,6 +825,8 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
                 e.score = combine_score(two, cfull & HC_CLS_BOTH, ov[0], ov[1]);
                 e.mismatch_rate = t.mismatch_rate;
                 extra_pos(cd, r1, r2, e.pos3, e.pos4);
+                e.mean_log[0] = ml[0];
+                e.mean_log[1] = ml[1];
                 edges[dst] = e;
             }
         } else if (c == HC_CLASS_NONEDGE) {

@@ -1,0 +1,61 @@
+"""One-process-per-GPU sharding of a candidate batch and the ordered gather of the results.
+
+Candidates are independent (src/EdgeCalculator.cpp:399-414), so the batch is cut into contiguous
+index ranges, rank r scores range r on its own replica of the read store, and the only exchange is
+the concatenation of the per-rank accepted-edge / non-edge lists IN RANK ORDER, which equals input
+order.  torch.distributed is plumbing: NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import formats as F
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous range of rank `rank`; the same split hc_score_batch uses across one process' devices."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def _gather_bytes(local: np.ndarray, device: torch.device, group=None) -> np.ndarray:
+    """all-gather of variable-length byte strings: counts first, then max-padded payloads."""
+    world = dist.get_world_size(group)
+    raw = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
+    cnt = torch.tensor([raw.size], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    sizes = [int(c.item()) for c in counts]
+    m = max(max(sizes), 1)
+    buf = torch.zeros(m, dtype=torch.uint8, device=device)
+    if raw.size:
+        buf[: raw.size] = torch.from_numpy(raw.copy()).to(device)
+    outs = [torch.zeros(m, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(outs, sizes)]) if sum(sizes) else np.zeros(0, np.uint8)
+
+
+def gather_results(edges: np.ndarray, nonedge_idx: np.ndarray, shard_start: int, device: Optional[torch.device] = None,
+                   group=None) -> Tuple[np.ndarray, np.ndarray]:
+    """`edges` (formats.EDGE) / `nonedge_idx` (uint64) hold indices local to this rank's shard;
+    returns the global lists, in input order, on every rank."""
+    device = device or torch.device("cpu")
+    e = edges.copy()
+    e["cand"] += np.uint64(shard_start)
+    ne = (nonedge_idx.astype(np.uint64) + np.uint64(shard_start)).astype(np.uint64)
+    ge = _gather_bytes(e, device, group).view(F.EDGE)
+    gn = _gather_bytes(ne, device, group).view(np.uint64)
+    return ge, gn
+
+
+def score_sharded(store, params: np.ndarray, cands: np.ndarray, device: Optional[torch.device] = None, group=None):
+    """Score this rank's contiguous share of `cands` on `store` (a capi.Store replica on the rank's
+    GPU) and return the globally gathered (edges, nonedge_idx)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = shard_range(len(cands), rank, world)
+    edges, nonedge, _, stats = store.score_batch(params, cands[lo:hi], per_candidate=False)
+    ge, gn = gather_results(edges, nonedge, lo, device=device, group=group)
+    return ge, gn, stats

@@ -37,7 +37,8 @@ RESULT = np.dtype(
         ("cls", "u1"), ("status", "u1", (2,)), ("exact", "u1"), ("reserved", "<u4"),
     ]
 )
-EDGE = np.dtype([("cand", "<u8"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos3", "<i4"), ("pos4", "<i4")])
+EDGE = np.dtype([("cand", "<u8"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos3", "<i4"), ("pos4", "<i4"),
+                 ("mean_log", "<f8", (2,))])
 BATCH_STATS = np.dtype(
     [
         ("n_candidates", "<u8"), ("n_edges", "<u8"), ("n_nonedges", "<u8"), ("n_exact", "<u8"),
@@ -46,7 +47,7 @@ BATCH_STATS = np.dtype(
     ]
 )
 assert READ_DESC.itemsize == 24 and CANDIDATE.itemsize == 32 and PARAMS.itemsize == 40
-assert RESULT.itemsize == 48 and EDGE.itemsize == 32 and BATCH_STATS.itemsize == 72
+assert RESULT.itemsize == 48 and EDGE.itemsize == 48 and BATCH_STATS.itemsize == 72
 
 CLASS_DISCARD, CLASS_EDGE, CLASS_NONEDGE = 0, 1, 2
 FLAG_EXACT_EDGE_SCORES = 1

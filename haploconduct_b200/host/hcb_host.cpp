@@ -1,0 +1,457 @@
+// hcb_host.cpp -- see hcb_host.h.  Host plumbing around the C ABI: FASTQ / overlaps-file parsing,
+// id -> index mapping, the ordered graph insert.  No score is computed here.
+#include "hcb_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+namespace hcb {
+
+void die(const std::string& msg) {
+    std::cerr << msg;
+    if (msg.empty() || msg.back() != '\n') std::cerr << std::endl;
+    std::exit(1);
+}
+
+static read_id_t str_to_read_id(const std::string& s) { return strtoul(s.c_str(), NULL, 0); }   // src/Types.h:99-102
+
+// ---------------------------------------------------------------------------------------------- reads
+static void slurp_lines(const std::string& path, unsigned long max_reads, std::vector<std::string>& out) {
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) die("Unable to open fastq file " + path);                   // src/FastqStorage.cpp:54-56
+    std::string line;
+    unsigned long count = 0;
+    while (count < 4 * max_reads && getline(f, line)) { out.push_back(line); count++; }
+}
+
+static std::string first_token(const std::string& s) {
+    std::stringstream st(s);
+    std::string t;
+    st >> t;
+    return t;
+}
+
+void FastqStorage::read_new_ids(const std::string& path) {                        // src/FastqStorage.cpp:60-90
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) die("Unable to open read-to-overlapID file");
+    std::string line;
+    while (getline(f, line)) {
+        std::stringstream ss(line);
+        std::string new_id, old_id;
+        getline(ss, new_id, '\t');
+        getline(ss, old_id, '\t');
+        if (!old_id.empty() && old_id[0] == '>') old_id = old_id.substr(1);
+        new_ids_.insert(std::make_pair(old_id, new_id));
+    }
+    have_new_ids_ = true;
+}
+
+void FastqStorage::read_singles(const std::string& path, unsigned long max_reads) {   // src/FastqStorage.cpp:92-152
+    std::vector<std::string> lines;
+    slurp_lines(path, max_reads, lines);
+    Read cur;
+    for (size_t k = 0; k < lines.size(); k++) {
+        const std::string& l = lines[k];
+        switch (k % 4) {
+            case 0: {
+                if (l.empty() || l[0] != '@') die("Read ID does not start with @. Exiting read_singles.");
+                const std::string tok = first_token(l.substr(1));
+                cur = Read();
+                cur.read_id = have_new_ids_ ? str_to_read_id(new_ids_.at(tok)) : str_to_read_id(tok);
+                break;
+            }
+            case 1:
+                cur.seq1 = l;
+                for (size_t i = 0; i < cur.seq1.size(); i++) cur.seq1[i] = (char)toupper((unsigned char)cur.seq1[i]);   // :123
+                break;
+            case 3:
+                cur.phred1 = l;
+                if (cur.seq1.empty()) die("single read with ID " + std::to_string(cur.read_id) + " has an empty sequence... exiting.");
+                cur.is_paired = false;
+                m_read_vec.push_back(cur);
+                break;
+            default: break;
+        }
+    }
+}
+
+void FastqStorage::read_pairs(const std::string& p1, const std::string& p2, unsigned long max_reads) {   // :154-235
+    std::vector<std::string> l1, l2;
+    slurp_lines(p1, max_reads, l1);
+    slurp_lines(p2, max_reads, l2);
+    Read cur;
+    const size_t n = std::min(l1.size(), l2.size());
+    for (size_t k = 0; k < n; k++) {
+        switch (k % 4) {
+            case 0: {
+                if (l1[k].empty() || l1[k][0] != '@') die("Read ID does not start with @. Exiting read_pairs.");
+                const std::string t1 = first_token(l1[k].substr(1));
+                const std::string t2 = l2[k].empty() ? std::string() : first_token(l2[k].substr(1));
+                if (t1 != t2) die("Fastq files /1 /2 are not ordered identically. Exiting read_pairs.");
+                cur = Read();
+                cur.read_id = have_new_ids_ ? str_to_read_id(new_ids_.at(t1)) : str_to_read_id(t1);
+                break;
+            }
+            case 1:
+                cur.seq1 = l1[k];   // pairs are NOT upper-cased by the reference (:196-197)
+                cur.seq2 = l2[k];
+                break;
+            case 3:
+                cur.phred1 = l1[k];
+                cur.phred2 = l2[k];
+                if (cur.seq1.empty() || cur.seq2.empty())
+                    die("paired read with ID " + std::to_string(cur.read_id) + " has an empty sequence... exiting.");
+                cur.is_paired = true;
+                m_read_vec.push_back(cur);
+                break;
+            default: break;
+        }
+    }
+}
+
+FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
+    if (!ps.id_correspondence.empty()) read_new_ids(ps.id_correspondence);
+    if (!ps.singles_file.empty() && ps.singles_file != "None") read_singles(ps.singles_file, ps.max_reads);
+    m_readcount_single = (unsigned int)m_read_vec.size();
+    if (!ps.paired1_file.empty() && ps.paired1_file != "None") read_pairs(ps.paired1_file, ps.paired2_file, ps.max_reads);
+    m_readcount_paired = (unsigned int)m_read_vec.size() - m_readcount_single;
+    if (ps.verbose) {
+        std::cout << "Singles: " << m_readcount_single << std::endl;
+        std::cout << "Pairs: " << m_readcount_paired << std::endl;
+    }
+    for (unsigned int i = 0; i < m_read_vec.size(); i++) m_ID_to_index.insert(std::make_pair(m_read_vec[i].read_id, i));
+    if (m_read_vec.empty()) return;
+    // ---- device replica: concatenate, describe, hand to the C ABI
+    std::vector<hc_read_desc> descs(m_read_vec.size());
+    std::string bases, quals;
+    size_t total = 0;
+    for (auto& r : m_read_vec) total += r.seq1.size() + r.seq2.size();
+    bases.reserve(total);
+    quals.reserve(total);
+    for (size_t i = 0; i < m_read_vec.size(); i++) {
+        const Read& r = m_read_vec[i];
+        if (r.seq1.size() != r.phred1.size() || r.seq2.size() != r.phred2.size())
+            die("read with ID " + std::to_string(r.read_id) + ": sequence and quality lengths differ");   // string::at would throw, :93-94
+        descs[i].seq_off[0] = bases.size();
+        descs[i].seq_len[0] = (uint32_t)r.seq1.size();
+        bases += r.seq1;
+        quals += r.phred1;
+        descs[i].seq_off[1] = bases.size();
+        descs[i].seq_len[1] = (uint32_t)r.seq2.size();
+        bases += r.seq2;
+        quals += r.phred2;
+    }
+    store_ = hc_store_create(descs.data(), descs.size(), m_readcount_single, bases.data(), quals.data(), ps.first_device,
+                             ps.n_devices);
+    if (!store_) die(std::string("hc_store_create: ") + hc_last_error());
+}
+
+FastqStorage::~FastqStorage() { hc_store_destroy(store_); }
+
+// ---------------------------------------------------------------------------------------------- Overlap
+static std::string strip(const std::string& s, const char* chars) {
+    std::string r;
+    for (char c : s) if (!strchr(chars, c)) r.push_back(c);
+    return r;
+}
+
+Overlap Overlap::from_fields(const std::vector<std::string>& f) {                // src/Overlap.h:39-73
+    Overlap o;
+    o.id1 = str_to_read_id(f[0]);
+    o.id2 = str_to_read_id(f[1]);
+    o.pos1 = (unsigned int)atoi(f[2].c_str());
+    o.pos2 = (unsigned int)atoi(f[3].c_str());
+    o.perc1 = (unsigned int)atoi(f[7].c_str());
+    o.perc2 = (unsigned int)atoi(f[8].c_str());
+    o.len1 = (unsigned int)atoi(f[9].c_str());
+    o.len2 = (unsigned int)atoi(f[10].c_str());
+    if (f[3] == "-") { o.pos2 = 0; o.perc2 = 0; o.len2 = 0; }                      // :55-59
+    if ((int)o.pos1 < 0 || (int)o.pos2 < 0) die("overlap.m_pos < 0; Exiting.");    // :107-112
+    std::string ori1 = f[5].size() == 1 ? f[5] : strip(f[5], " "), ori2 = f[6].size() == 1 ? f[6] : strip(f[6], " ");
+    if (ori1.size() != 1 || ori2.size() != 1 || (ori1 != "+" && ori1 != "-") || (ori2 != "+" && ori2 != "-"))
+        die("overlap.m_ori not of the right format (+, -). Exiting.");              // :125-134
+    for (unsigned int p : {o.perc1, o.perc2})
+        if ((int)p < 0 || (int)p > 100) die(std::to_string((int)p) + "\noverlap.m_perc not of the right format (0 <= perc <= 100). Exiting.");
+    if ((int)o.len1 < 0 || (int)o.len2 < 0) die("overlap.m_len < 0. Exiting.");    // :144-149
+    std::string t1 = f[11].size() == 1 ? f[11] : strip(f[11], "\n\t "), t2 = f[12].size() == 1 ? f[12] : strip(f[12], "\n\t ");
+    if (t1.size() != 1 || t2.size() != 1) die("overlap type field is not a single character (the reference asserts)");
+    if (t1 != "s" && t1 != "p") die(t1 + " not of the form 's' or 'p'. Exiting.");
+    if (t2 != "s" && t2 != "p") die(t2 + " not of the form 's' or 'p'. Exiting.");
+    std::string ord = f[4].size() == 1 ? f[4] : strip(f[4], " ");
+    bool ord_ok = ord.size() == 1 && (ord == "1" || ord == "2" || ord == "-");
+    if (ord_ok) ord_ok = (t1 == "s" || t2 == "s") ? ord == "-" : (ord == "1" || ord == "2");   // :114-123
+    if (!ord_ok) die("overlap ORD field inconsistent with the read types (the reference asserts, src/Overlap.h:114-123)");
+    o.ord = ord[0];
+    o.ori1 = ori1[0];
+    o.ori2 = ori2[0];
+    o.type1 = t1[0];
+    o.type2 = t2[0];
+    return o;
+}
+
+std::string Overlap::get_overlap_line() const {                                   // src/Overlap.h:234-237
+    std::string s = std::to_string(id1) + "\t" + std::to_string(id2) + "\t" + std::to_string(pos1) + "\t" +
+                    std::to_string(pos2) + "\t";
+    s.push_back(ord); s += "\t"; s.push_back(ori1); s += "\t"; s.push_back(ori2);
+    s += "\t" + std::to_string(perc1) + "\t" + std::to_string(perc2) + "\t" + std::to_string(len1) + "\t" +
+         std::to_string(len2) + "\t";
+    s.push_back(type1); s += "\t"; s.push_back(type2); s += "\n";
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------- Edge / graph
+void Edge::swap_reads() {                                                         // src/Edge.h:74-88
+    std::swap(vertex1, vertex2);
+    std::swap(ori1, ori2);
+    if (ord == '1') ord = '2';
+    else if (ord == '2') ord = '1';
+    pos3 = -pos3;
+    pos4 = -pos4;
+}
+
+OverlapGraph::OverlapGraph(unsigned int V) : inclusions(V, 0), adj_out(V) {}
+
+uint64_t OverlapGraph::key(node_id_t a, node_id_t b, bool same_ori) {
+    const uint64_t lo = std::min(a, b), hi = std::max(a, b);
+    return (lo << 33) | (hi << 1) | (same_ori ? 1u : 0u);
+}
+
+node_id_t OverlapGraph::addVertex(read_id_t id) {
+    vertex_to_read.push_back(id);
+    return vertex_to_read.size() - 1;
+}
+
+void OverlapGraph::addEdge(const Edge& e) {
+    adj_out[e.vertex1].push_back(e);
+    owner_[key(e.vertex1, e.vertex2, e.ori1 == e.ori2)] = e.vertex1;
+    edge_count_++;
+}
+
+const Edge* OverlapGraph::getEdgeInfoWithOri(node_id_t v, node_id_t w, bool same_ori) const {
+    auto it = owner_.find(key(v, w, same_ori));
+    if (it == owner_.end()) return nullptr;
+    const node_id_t from = it->second, to = from == v ? w : v;
+    for (const Edge& e : adj_out[from])
+        if (e.vertex2 == to && (e.ori1 == e.ori2) == same_ori) return &e;
+    return nullptr;
+}
+
+double OverlapGraph::checkEdgeWithOri(node_id_t v, node_id_t w, bool same_ori) const {
+    const Edge* e = getEdgeInfoWithOri(v, w, same_ori);
+    return e ? e->score : -1;
+}
+
+void OverlapGraph::removeEdgeWithOri(node_id_t v, node_id_t w, bool same_ori) {
+    std::vector<Edge>& lst = adj_out[v];
+    for (size_t i = 0; i < lst.size(); i++) {
+        if (lst[i].vertex2 == w && (lst[i].ori1 == lst[i].ori2) == same_ori) {
+            lst.erase(lst.begin() + i);
+            owner_.erase(key(v, w, same_ori));
+            edge_count_--;
+            return;
+        }
+    }
+    die("Edge to be removed not found...\n" + std::to_string(v) + " " + std::to_string(w));
+}
+
+void OverlapGraph::writeDiGraphToFile(const std::string& path) const {
+    std::ofstream f(path.c_str());
+    for (size_t v = 0; v < adj_out.size(); v++)
+        for (const Edge& e : adj_out[v]) f << v << "\t" << e.vertex2 << "\n";
+}
+
+void OverlapGraph::dumpAdjacency(const std::string& path) const {
+    FILE* fo = fopen(path.c_str(), "w");
+    if (!fo) die("cannot write " + path);
+    fprintf(fo, "#v1\tv2\tscore\tmm_rate\tpos1\tpos2\tpos3\tpos4\tori1\tori2\tord\tperc\tlen1\tlen2\n");
+    for (const auto& lst : adj_out)
+        for (const Edge& e : lst)
+            fprintf(fo, "%lu\t%lu\t%a\t%a\t%d\t%d\t%d\t%d\t%d\t%d\t%c\t%d\t%d\t%d\n", e.vertex1, e.vertex2, e.score,
+                    e.mismatch_rate, e.pos1, e.pos2, e.pos3, e.pos4, (int)e.ori1, (int)e.ori2, e.ord, e.overlap_perc,
+                    e.overlap_len1, e.overlap_len2);
+    fclose(fo);
+}
+
+// ---------------------------------------------------------------------------------------------- EdgeCalculator
+EdgeCalculator::EdgeCalculator(std::shared_ptr<FastqStorage> fastq, std::shared_ptr<OverlapGraph> graph, const ProgramSettings ps)
+    : ps_(ps), fastq_(fastq), graph_(graph) {}
+
+static hc_params to_params(const ProgramSettings& ps) {
+    hc_params p;
+    memset(&p, 0, sizeof(p));
+    p.edge_threshold = ps.edge_threshold;
+    p.ov_threshold = ps.ov_threshold;
+    p.merge_contigs = ps.merge_contigs;
+    p.mismatch = ps.mismatch;
+    p.min_read_len = ps.min_read_len;
+    p.flags = ps.exact_scores ? HC_FLAG_EXACT_EDGE_SCORES : 0u;
+    return p;
+}
+
+double EdgeCalculator::phred_to_prob(const int phred) { return hc_phred_to_prob(phred); }
+
+double EdgeCalculator::overlap_score(std::string seq1, std::string seq2, std::string score1, std::string score2,
+                                     const unsigned int pos, double& mismatch_rate) {
+    const hc_params p = to_params(ps_);
+    const double s = hc_overlap_score(seq1.data(), (uint32_t)seq1.size(), seq2.data(), (uint32_t)seq2.size(), score1.data(),
+                                      score2.data(), pos, &p, &mismatch_rate);
+    if (s < 0) die(std::string("hc_overlap_score: ") + hc_last_error());
+    return s;
+}
+
+// The body of src/EdgeCalculator.cpp:389-557: score the batch on the device (the omp-parallel
+// region), then the serial, ORDER-DEPENDENT graph insert (:429-545) and the non-edge append (:546-555).
+void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
+    const size_t n = batch.size();
+    if (n == 0) return;
+    std::vector<hc_candidate> cand(n);
+    for (size_t i = 0; i < n; i++) {
+        const Overlap& o = batch[i];
+        auto i1 = fastq_->m_ID_to_index.find(o.id1), i2 = fastq_->m_ID_to_index.find(o.id2);
+        if (i1 == fastq_->m_ID_to_index.end()) die(std::to_string(o.id1) + "\nread ID of the overlaps file is not in the fastq input");
+        if (i2 == fastq_->m_ID_to_index.end()) die(std::to_string(o.id2) + "\nread ID of the overlaps file is not in the fastq input");
+        hc_candidate& c = cand[i];
+        memset(&c, 0, sizeof(c));
+        c.idx1 = i1->second; c.idx2 = i2->second;
+        c.pos1 = o.pos1; c.pos2 = o.pos2; c.len1 = o.len1; c.len2 = o.len2;
+        c.perc1 = (uint8_t)o.perc1; c.perc2 = (uint8_t)o.perc2;
+        c.ord = (uint8_t)o.ord; c.ori1 = o.ori1 == '+'; c.ori2 = o.ori2 == '+';
+        c.type1 = (uint8_t)o.type1; c.type2 = (uint8_t)o.type2;
+    }
+    std::vector<hc_edge> edges(n);
+    std::vector<uint64_t> nonedge(n);
+    uint64_t ne = 0, nn = 0;
+    hc_batch_stats st;
+    const hc_params p = to_params(ps_);
+    const int rc = hc_score_batch(fastq_->device_store(), &p, cand.data(), n, nullptr, edges.data(), n, &ne, nonedge.data(), n,
+                                  &nn, &st);
+    if (rc != HC_OK) die(std::string("hc_score_batch: ") + hc_last_error());
+    scored_candidates += n;
+    device_ms += st.total_ms;
+
+    unsigned int doubles = 0;
+    for (uint64_t k = 0; k < ne; k++) {
+        const hc_edge& he = edges[k];
+        const Overlap& o = batch[he.cand];
+        const hc_candidate& c = cand[he.cand];
+        const Read& r1 = fastq_->m_read_vec[c.idx1];
+        const Read& r2 = fastq_->m_read_vec[c.idx2];
+        Edge e;
+        e.score = he.score;
+        if (ps_.exact_scores) {   // :138 and :256-261 with the host libm on the reference's own mean logs
+            const double ov1 = std::isnan(he.mean_log[0]) ? 0.0 : exp(he.mean_log[0]);
+            if (r1.is_paired || r2.is_paired) {
+                const double ov2 = std::isnan(he.mean_log[1]) ? 0.0 : exp(he.mean_log[1]);
+                e.score = (ov1 > ps_.edge_threshold && ov2 > ps_.edge_threshold) ? 0.5 * (ov1 + ov2) : std::min(ov1, ov2);
+            } else {
+                e.score = ov1;
+            }
+        }
+        e.pos1 = (int)o.pos1; e.pos2 = (int)o.pos2; e.pos3 = he.pos3; e.pos4 = he.pos4;
+        e.ori1 = o.ori1 == '+'; e.ori2 = o.ori2 == '+';
+        e.ord = o.ord;
+        e.vertex1 = r1.vertex_id; e.vertex2 = r2.vertex_id;
+        e.overlap_perc = (int)o.get_perc();
+        e.overlap_len1 = (int)o.len1;
+        e.overlap_len2 = (r1.is_paired || r2.is_paired) ? (int)o.len2 : 0;       // set_len(len1, 0) for S-S, :227
+        e.overlap_len = e.overlap_len1 + e.overlap_len2;
+        e.mismatch_rate = he.mismatch_rate;
+
+        node_id_t v1 = e.vertex1, v2 = e.vertex2;
+        if (e.pos1 == 0 && v1 > v2) { std::swap(v1, v2); e.swap_reads(); }         // :443-448
+        if (e.overlap_perc == 100) inclusion_count++;                              // :449-451
+        const bool same_ori = e.ori1 == e.ori2;
+        const double have = graph_->checkEdgeWithOri(v1, v2, same_ori);
+        if (have < 0) {                                                            // :455-469
+            graph_->addEdge(e);
+            if (ps_.ignore_inclusions && e.overlap_perc == 100 && e.mismatch_rate < 0.000001 && e.mismatch_rate >= 0) {
+                if (e.pos3 < 0) { if (e.pos1 == 0) graph_->inclusions[v1] = 1; }
+                else graph_->inclusions[v2] = 1;
+            }
+        } else if (e.score >= have) {                                              // :470-534
+            doubles++;
+            const Edge* old = graph_->getEdgeInfoWithOri(v1, v2, same_ori);
+            bool keep_old = false;
+            if (have == e.score) {   // the reference's deterministic tie-break, one criterion decides
+                if (old->overlap_len != e.overlap_len) keep_old = old->overlap_len > e.overlap_len;
+                else if (old->mismatch_rate != e.mismatch_rate) keep_old = old->mismatch_rate < e.mismatch_rate;
+                else if (old->vertex1 != e.vertex1) keep_old = old->vertex1 < e.vertex1;
+                else if (old->ori1 != e.ori1) keep_old = old->ori1;
+                else if (old->ori2 != e.ori2) keep_old = old->ori2;
+                else if (old->pos1 != e.pos1) keep_old = old->pos1 < e.pos1;
+                else if (old->pos2 != e.pos2) keep_old = old->pos2 < e.pos2;
+            }
+            if (keep_old) continue;
+            if (old->vertex1 == v1) graph_->removeEdgeWithOri(v1, v2, same_ori);
+            else graph_->removeEdgeWithOri(v2, v1, same_ori);
+            graph_->addEdge(e);
+        } else {
+            doubles++;                                                             // :535-538
+        }
+    }
+    dup_count += doubles;
+
+    std::ofstream out((ps_.output_dir + "nonedge_overlaps.txt").c_str(), std::fstream::out | std::fstream::app);
+    for (uint64_t k = 0; k < nn; k++) out << batch[nonedge[k]].get_overlap_line();
+}
+
+void EdgeCalculator::construct_edges() {                                          // src/EdgeCalculator.cpp:561-666
+    if (ps_.add_duplicates) die("add_duplicates=true is not supported by this build (no driver script uses it)");
+    std::remove("nonedge_overlaps.txt");                                          // :566 (cwd, like the reference)
+    std::ifstream in(ps_.overlaps_file.c_str());
+    if (!in.is_open()) { std::cerr << "Unable to open overlaps file"; std::exit(1); }
+    const size_t per_batch = 1000000;                                             // :571
+    std::vector<Overlap> batch, filtered;
+    batch.reserve(per_batch);
+    std::string line;
+    unsigned long i = 0;
+    while (i < ps_.max_overlaps && getline(in, line)) {
+        i++;
+        size_t b = 0, e = line.size();
+        while (b < e && (line[b] == '\t' || line[b] == ' ')) b++;                  // trim outer tabs/spaces, :584
+        while (e > b && (line[e - 1] == '\t' || line[e - 1] == ' ')) e--;
+        std::vector<std::string> f;
+        std::string cur;
+        if (b < e) {
+            for (size_t k = b; k < e; k++) {
+                const char ch = line[k];
+                const bool sep = ps_.allow_spaces ? (ch == '\t' || ch == ' ') : ch == '\t';
+                if (sep) {
+                    f.push_back(cur);
+                    cur.clear();
+                    if (ps_.allow_spaces) while (k + 1 < e && (line[k + 1] == '\t' || line[k + 1] == ' ')) k++;   // token_compress_on
+                } else cur.push_back(ch);
+            }
+            f.push_back(cur);
+        }
+        if (f.size() != 13) { std::cout << "incorrect overlap; skipping" << std::endl; continue; }   // :600-603
+        Overlap o = Overlap::from_fields(f);
+        if (o.id1 == o.id2) continue;                                              // :605-607
+        const bool any_p = o.type1 == 'p' || o.type2 == 'p';
+        bool in_band = false;
+        if (o.len1 >= ps_.min_overlap_len && o.type1 == 's' && o.type2 == 's') in_band = true;                   // :612-617
+        else if (o.len1 >= 0.5 * ps_.min_overlap_len && o.len2 >= 0.5 * ps_.min_overlap_len && any_p) in_band = true;   // :618-624
+        else if (ps_.relax_PE_edges && o.len1 + o.len2 >= ps_.min_overlap_len && any_p) in_band = true;          // :626-632
+        if (in_band) {
+            if (o.get_perc() >= ps_.min_overlap_perc) batch.push_back(o);
+        } else {
+            filtered.push_back(o);                                                 // :633-635
+        }
+        if (batch.size() == per_batch) { process_overlaps(batch); batch.clear(); }
+    }
+    if (!batch.empty()) { process_overlaps(batch); batch.clear(); }
+    if (ps_.verbose) {
+        std::cout << "Number of self-overlapping reads: " << self_overlap_count << "\n";
+        std::cout << "Number of inclusion edges: " << inclusion_count << "\n";
+    }
+    std::ofstream out((ps_.output_dir + "nonedge_overlaps.txt").c_str(), std::fstream::out | std::fstream::app);   // :654-660
+    for (const Overlap& o : filtered) out << o.get_overlap_line();
+}
+
+}  // namespace hcb

@@ -126,10 +126,14 @@ typedef struct {
 /* One accepted edge, emitted in INPUT ORDER (= the reference's 1-thread order). */
 typedef struct {
     uint64_t cand;             /* index into the candidate array of the call                        */
-    double   score;
+    double   score;            /* Edge::score, device exp()                                         */
     double   mismatch_rate;
     int32_t  pos3, pos4;
-} hc_edge;                     /* 32 bytes */
+    double   mean_log[2];      /* (1.0/total_len)*total_score per window (src/EdgeCalculator.cpp:137); NaN for a
+                                  window that was not scored.  With HC_FLAG_EXACT_EDGE_SCORES these are the
+                                  reference's doubles bit for bit, so a host that needs Edge::score
+                                  bit-identical to the reference evaluates exp() with its own libm (:138).  */
+} hc_edge;                     /* 48 bytes */
 
 typedef struct {
     uint64_t n_candidates;

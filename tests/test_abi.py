@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(built_lib):
 
 
 def test_struct_sizes_match_header():
-    assert F.CANDIDATE.itemsize == 32 and F.RESULT.itemsize == 48 and F.EDGE.itemsize == 32 and F.READ_DESC.itemsize == 24
+    assert F.CANDIDATE.itemsize == 32 and F.RESULT.itemsize == 48 and F.EDGE.itemsize == 48 and F.READ_DESC.itemsize == 24
 
 
 def test_host_only_entry_points(built_lib):

@@ -1,0 +1,69 @@
+"""GPU suite: the C++ host mirror of the reference's EdgeCalculator (haploconduct_b200/host/, built
+as lib/hc_edgecalc on top of the C ABI) against what the UNMODIFIED reference produced on the same
+files (tests/golden): the overlap graph after construct_edges() -- every Edge field of every
+adjacency list, in adjacency order -- nonedge_overlaps.txt byte for byte, and the public counters.
+With --exact_scores=true the Edge scores are bit-identical; in the default fast mode they are
+within 1e-6 relative and the graph (edges, order, integer fields) is still identical."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from haploconduct_b200 import build as B, formats as F
+from oracle import oracle as O
+from util import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(B.LIBDIR, "hc_edgecalc")
+
+
+def _run(g, tmp_path, exact):
+    d = str(tmp_path)
+    F.write_fastq_set(g.rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    F.write_overlaps(d + "/ov.txt", g.cands, g.rs.ids)
+    cmd = [EXE, "--overlaps", d + "/ov.txt", "--dump-graph", d + "/graph.tsv", "--digraph", d + "/digraph.txt",
+           "--exact_scores=" + ("true" if exact else "false")]
+    if g.rs.n_single:
+        cmd += ["--singles", d + "/s.fastq"]
+    if g.rs.n_reads > g.rs.n_single:
+        cmd += ["--paired1", d + "/p1.fastq", "--paired2", d + "/p2.fastq"]
+    for k, v in g.ps.items():
+        if k in ("min_overlap_len", "min_read_len", "min_overlap_perc"):
+            cmd += ["--" + k, str(int(v))]
+        elif k == "relax_PE_edges":
+            cmd += ["--" + k + "=" + ("true" if v else "false")]
+        else:
+            cmd += ["--" + k, repr(float(v))]
+    out = subprocess.run(cmd, cwd=d, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
+    summary = json.loads([l for l in out.split("\n") if l.startswith("{")][-1])
+    graph = O.parse_graph_dump(d + "/graph.tsv")
+    with open(d + "/nonedge_overlaps.txt") as f:
+        nonedge = f.read().split("\n")[:-1]
+    with open(d + "/digraph.txt") as f:
+        digraph = f.read()
+    return summary, graph, nonedge, digraph
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_graph_identical_to_reference_exact_scores(built_lib, tmp_path, name):
+    g = load_golden(name)
+    summary, graph, nonedge, digraph = _run(g, tmp_path, exact=True)
+    assert np.array_equal(graph, g.ref_graph), name     # every field incl. score and mismatch_rate bit for bit, adjacency order
+    assert nonedge == g.ref_nonedge
+    assert [summary["graph_edges"], summary["dup_count"], summary["inclusion_count"]] == g.ref_counts.tolist()
+    want = "".join("%d\t%d\n" % (a, b) for a, b in zip(g.ref_graph["v1"], g.ref_graph["v2"]))
+    assert digraph == want
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_graph_fast_mode(built_lib, tmp_path, name):
+    g = load_golden(name)
+    summary, graph, nonedge, digraph = _run(g, tmp_path, exact=False)
+    ref = g.ref_graph
+    assert nonedge == g.ref_nonedge
+    assert len(graph) == len(ref)
+    for f in ("v1", "v2", "pos1", "pos2", "pos3", "pos4", "ori1", "ori2", "ord", "perc", "len1", "len2", "mismatch_rate"):
+        assert np.array_equal(graph[f], ref[f]), f
+    assert np.allclose(graph["score"], ref["score"], rtol=1e-6, atol=0)
