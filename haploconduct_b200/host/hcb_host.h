@@ -48,7 +48,10 @@ struct ProgramSettings {           // names and defaults of src/Types.h:19-67 / 
     bool relax_PE_edges = false;
     bool verbose = false;
     // additions of this build
-    bool exact_scores = false;     // HC_FLAG_EXACT_EDGE_SCORES + host libm exp(): Edge::score bit-identical to the reference
+    // HC_FLAG_EXACT_EDGE_SCORES + host libm exp(): Edge::score bit-identical to the reference, which the
+    // duplicate-edge resolution of process_overlaps (score >= existing score, :470) needs to pick the
+    // same representative when two overlaps of one read pair score within 1e-7 of each other.
+    bool exact_scores = true;
     int first_device = 0;
     int n_devices = 1;
 };

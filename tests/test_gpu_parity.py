@@ -206,7 +206,7 @@ def test_empty_single_and_capacity(built_lib):
         assert ei.value.code == -1
         # the store is still usable afterwards
         e2, n2, _, _ = st.score_batch(g.params(), cands)
-        assert np.array_equal(e2, efull) and np.array_equal(n2, nfull)
+        assert e2.tobytes() == efull.tobytes() and np.array_equal(n2, nfull)   # bytes: mean_log of an unused window is NaN
 
 
 def test_invalid_input_is_rejected_like_the_reference(built_lib):
