@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libhc_b200.so")
 EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_device", "hc_overlap_score",
-    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version",
+    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
         L.hc_exp_threshold.argtypes = [dbl]
         L.hc_device_count.restype = i32
         L.hc_device_count.argtypes = []
+        L.hc_fno1.restype = i32
+        L.hc_fno1.argtypes = [vp, vp, u64, vp, u64, ctypes.POINTER(u64), i32]
         L.hc_last_error.restype = ctypes.c_char_p
         L.hc_version.restype = ctypes.c_char_p
         _lib = L
@@ -174,3 +176,30 @@ def exp_threshold(thr: float) -> float:
 
 def device_count() -> int:
     return lib().hc_device_count()
+
+
+class _FnoInputC(ctypes.Structure):     # hc_fno_input
+    _fields_ = [("n_vertices", ctypes.c_uint64), ("visited", ctypes.c_void_p), ("label", ctypes.c_void_p),
+                ("vertex_read", ctypes.c_void_p), ("sr_off", ctypes.c_void_p), ("sr_idx", ctypes.c_void_p),
+                ("sr_sub", ctypes.c_void_p), ("n_superreads", ctypes.c_uint64), ("superread", ctypes.c_void_p),
+                ("resolve_orientations", ctypes.c_uint8), ("no_inclusions", ctypes.c_uint8)]
+
+
+def fno1(fi: "F.FnoInput", device: int = 0) -> np.ndarray:
+    """hc_fno1: next-iteration overlaps derived on the GPU, in processing order (formats.FNO_OVERLAP)."""
+    keep = [np.ascontiguousarray(a) for a in (fi.visited, fi.label, fi.vertex_read, fi.sr_off, fi.sr_idx, fi.sr_sub, fi.superread)]
+    st = _FnoInputC(len(fi.visited), keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
+                    keep[4].ctypes.data, keep[5].ctypes.data, len(fi.superread), keep[6].ctypes.data, fi.resolve_orientations,
+                    fi.no_inclusions)
+    edges = np.ascontiguousarray(fi.edges)
+    cap = max(2 * len(edges), 1024)
+    while True:
+        out = np.zeros(cap, dtype=F.FNO_OVERLAP)
+        n = ctypes.c_uint64(0)
+        rc = lib().hc_fno1(ctypes.byref(st), edges.ctypes.data if len(edges) else None, len(edges), out.ctypes.data, cap,
+                           ctypes.byref(n), device)
+        if rc == 0:
+            return out[: n.value]
+        if rc != -5:
+            raise HcError(rc, last_error())
+        cap = int(n.value)

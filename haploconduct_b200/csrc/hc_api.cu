@@ -70,6 +70,8 @@ struct DevCtx {
 
 }  // namespace
 
+void hc_set_last_error(const char* msg) { g_err = msg ? msg : ""; }   // used by hc_fno.cu
+
 struct hc_store {
     uint64_t n_reads = 0, n_single = 0;
     uint64_t total_positions = 0;

@@ -1,0 +1,355 @@
+// hc_fno.cu -- FindNextOverlaps (FNO1) on the device: SRBuilder::findNextOverlaps,
+// src/FindNextOverlaps.cpp:890-958 (updateOverlap :25-327, findCliqueIndex :331-347,
+// computeOverlapData :351-565).
+//
+// The reference walks the edge stream sequentially; for every edge (u, v) it tries every pair
+// (new read of u) x (new read of v) and keeps, per unordered pair of new reads, the FIRST attempt in
+// processing order -- whether or not that attempt then succeeds (:84-97 precede :115-118).  Here:
+//   1. fno_count      attempts per edge                       -> exclusive scan = sequence numbers
+//   2. fno_claim      every keyed attempt does atomicMin(sequence number) on its pair's hash slot
+//   3. fno_flag       an attempt survives if it is a plain copy (:46-72) or holds its pair's minimum,
+//                     and computeOverlapData succeeds          -> exclusive scan = output positions
+//   4. fno_emit       survivors are written in processing order
+// All integer / float32 arithmetic, bit-identical to the reference (perc uses IEEE float division,
+// max, multiplication and floor, :375,:429,:487,:549).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/hc_b200.h"
+
+namespace {
+
+typedef unsigned long long u64;
+
+struct FnoDev {
+    u64 n_vertices;
+    const uint8_t* visited;
+    const uint8_t* label;
+    const hc_fno_read* vertex_read;
+    const u64* sr_off;
+    const uint32_t* sr_idx;
+    const hc_fno_subread* sr_sub;
+    const hc_fno_read* superread;
+    uint32_t resolve_orientations, no_inclusions;
+};
+
+__device__ __forceinline__ int perc_of(int t, int la, int lb) {
+    const float a = __fdiv_rn((float)t, (float)la), b = __fdiv_rn((float)t, (float)lb);
+    return (int)floorf(__fmul_rn(fmaxf(a, b), 100.0f));
+}
+
+struct Derived {
+    int pos1, pos2, perc, ol1, ol2;
+    char ord1, ord2, t1, t2;
+};
+
+// src/FindNextOverlaps.cpp:351-565
+__device__ bool compute_overlap_data(const hc_fno_read& r1, const hc_fno_read& r2, int idx1l, int idx1r, int idx2l, int idx2r,
+                                     const hc_fno_edge& e, Derived& d) {
+    const int pos1 = e.pos1, pos2 = e.pos2;
+    const bool p1 = r1.len2 > 0, p2 = r2.len2 > 0;
+    const int l11 = (int)r1.len1, l12 = (int)r1.len2, l21 = (int)r2.len1, l22 = (int)r2.len2;
+    d.pos2 = 0;
+    d.pos1 = (pos1 + idx1l) - idx2l;
+    if (!p1 && !p2) {                                              // S-S :357-385
+        d.t1 = 's'; d.t2 = 's';
+        int len;
+        if (d.pos1 < 0) { d.ord1 = '2'; d.pos1 = -d.pos1; len = l21; }
+        else { d.ord1 = '1'; len = l11; }
+        d.ol1 = min(min(len - d.pos1, l11), l21);
+        d.ol2 = 0;
+        d.perc = perc_of(d.ol1, l11, l21);
+        d.ord2 = '-';
+        return d.pos1 < len;
+    }
+    if (p1 && !p2) {                                               // P-S :387-443
+        d.t1 = 'p'; d.t2 = 's';
+        if (d.pos1 < 0) {
+            d.ord1 = '2'; d.pos1 = -d.pos1;
+            if (d.pos1 >= l21) return false;
+            d.ol1 = l11;
+        } else {
+            d.ord1 = '1';
+            if (d.pos1 >= l11) return false;
+            d.ol1 = l11 - d.pos1;
+        }
+        d.pos2 = e.ord == '1' ? idx2r - (idx1r + pos2) : (pos2 + idx2r) - idx1r;
+        if (d.pos2 >= l21 || d.pos2 < 0) return false;
+        d.ord2 = '-';
+        d.ol2 = min(l21 - d.pos2, l12);
+        d.perc = min(perc_of(d.ol1 + d.ol2, l11 + l12, l21), 100);
+        return true;
+    }
+    if (!p1 && p2) {                                               // S-P :445-489
+        d.t1 = 's'; d.t2 = 'p';
+        if (d.pos1 < 0) {
+            d.ord1 = '2'; d.pos1 = -d.pos1;
+            if (d.pos1 >= l21) return false;
+            d.ol1 = l21 - d.pos1;
+        } else {
+            d.ord1 = '1';
+            if (d.pos1 >= l11) return false;
+            d.ol1 = l21;
+        }
+        d.pos2 = e.ord == '2' ? idx1r - (pos2 + idx2r) : idx1r + pos2 - idx2r;
+        if (d.pos2 >= l11 || d.pos2 < 0) return false;
+        d.ord2 = '-';
+        d.ol2 = min(l11 - d.pos2, l22);
+        d.perc = min(perc_of(d.ol1 + d.ol2, l11, l21 + l22), 100);
+        return true;
+    }
+    d.t1 = 'p'; d.t2 = 'p';                                        // P-P :491-551
+    if (d.pos1 < 0) {
+        d.ord1 = '2'; d.pos1 = -d.pos1;
+        if (d.pos1 >= l21) return false;
+        d.ol1 = min(l11, l21 - d.pos1);
+    } else {
+        d.ord1 = '1';
+        if (d.pos1 >= l11) return false;
+        d.ol1 = min(l11 - d.pos1, l21);
+    }
+    d.pos2 = e.ord == '1' ? (pos2 + idx1r) - idx2r : idx1r - (pos2 + idx2r);
+    if (d.pos2 < 0) {
+        d.ord2 = d.ord1 == '1' ? '2' : '1';
+        d.pos2 = -d.pos2;
+        if (d.pos2 >= l22) return false;
+        d.ol2 = min(l12, l22 - d.pos2);
+    } else {
+        d.ord2 = d.ord1 == '1' ? '1' : '2';
+        if (d.pos2 >= l12) return false;
+        d.ol2 = min(l12 - d.pos2, l22);
+    }
+    d.perc = min(perc_of(d.ol1 + d.ol2, l11 + l12, l21 + l22), 100);
+    return true;
+}
+
+__device__ __forceinline__ u64 hash_slot(u64 key, u64 mask) { return (key * 0x9E3779B97F4A7C15ull) & mask; }
+
+// Iterates the attempts of one edge in the reference's order and calls f(seq, s1, s2, a, b, keyed).
+template <class F>
+__device__ __forceinline__ void for_each_attempt(const FnoDev& D, const hc_fno_edge& e, u64 seq0, F f) {
+    const bool vu = D.visited[e.u], vv = D.visited[e.v];
+    const u64 a0 = vu ? D.sr_off[e.u] : 0, a1 = vu ? D.sr_off[e.u + 1] : 1;
+    const u64 b0 = vv ? D.sr_off[e.v] : 0, b1 = vv ? D.sr_off[e.v + 1] : 1;
+    u64 seq = seq0;
+    for (u64 a = a0; a < a1; a++)
+        for (u64 b = b0; b < b1; b++, seq++) f(seq, a, b, vu, vv);
+}
+
+__global__ void fno_count(FnoDev D, const hc_fno_edge* edges, u64 n, uint32_t* cnt) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const hc_fno_edge e = edges[i];
+        const u64 a = D.visited[e.u] ? D.sr_off[e.u + 1] - D.sr_off[e.u] : 1;
+        const u64 b = D.visited[e.v] ? D.sr_off[e.v + 1] - D.sr_off[e.v] : 1;
+        cnt[i] = (uint32_t)(a * b);
+    }
+}
+
+// single-block exclusive scan uint32 -> u64 (inputs are small: <= 1e7-1e8 items)
+__global__ void __launch_bounds__(1024) scan_u32(const uint32_t* in, u64 n, u64* out, u64* total) {
+    __shared__ u64 wsum[32];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u64 b0 = 0; b0 < n; b0 += 1024) {
+        const u64 i = b0 + threadIdx.x;
+        const u64 v = i < n ? in[i] : 0;
+        u64 inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const u64 w = wsum[lane];
+            u64 s = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 t = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += t;
+            }
+            wsum[lane] = s - w;
+        }
+        __syncthreads();
+        const u64 c = carry;
+        if (i < n) out[i] = c + wsum[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wsum[31] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void fno_claim(FnoDev D, const hc_fno_edge* edges, u64 n, const u64* off, u64* keys, u64* mins, u64 mask) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const hc_fno_edge e = edges[i];
+        if (!D.visited[e.u] && !D.visited[e.v]) continue;          // plain copy, no first-found bookkeeping (:46-72)
+        for_each_attempt(D, e, off[i], [&](u64 seq, u64 a, u64 b, bool vu, bool vv) {
+            const u64 id1 = vu ? D.superread[D.sr_idx[a]].id : D.vertex_read[e.u].id;
+            const u64 id2 = vv ? D.superread[D.sr_idx[b]].id : D.vertex_read[e.v].id;
+            if (id1 == id2) return;                                 // :241-243
+            const u64 key = (min(id1, id2) << 32) | max(id1, id2);
+            u64 h = hash_slot(key, mask);
+            while (true) {
+                const u64 prev = atomicCAS(&keys[h], ~0ull, key);
+                if (prev == ~0ull || prev == key) break;
+                h = (h + 1) & mask;
+            }
+            atomicMin(&mins[h], seq);
+        });
+    }
+}
+
+template <bool EMIT>
+__global__ void fno_resolve(FnoDev D, const hc_fno_edge* edges, u64 n, const u64* off, const u64* keys, const u64* mins, u64 mask,
+                            uint32_t* flags, const u64* outpos, hc_fno_overlap* out, u64 out_cap) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const hc_fno_edge e = edges[i];
+        char ori1 = '+', ori2 = '+';
+        if (D.resolve_orientations && e.nonedge) {                  // :34-37
+            ori1 = (e.ori1 == D.label[e.u]) ? '+' : '-';
+            ori2 = (e.ori2 == D.label[e.v]) ? '+' : '-';
+        }
+        const hc_fno_read ru = D.vertex_read[e.u], rv = D.vertex_read[e.v];
+        const bool pu = ru.len2 > 0, pv = rv.len2 > 0;
+        if (!D.visited[e.u] && !D.visited[e.v]) {                   // :46-72
+            const u64 seq = off[i];
+            const bool ok = !(D.no_inclusions && e.perc == 100);
+            if (!EMIT) flags[seq] = ok;
+            else if (ok && outpos[seq] < out_cap) {
+                hc_fno_overlap o;
+                memset(&o, 0, sizeof(o));
+                o.id1 = ru.id; o.id2 = rv.id; o.pos1 = e.pos1; o.pos2 = e.pos2; o.ord = e.ord; o.ori1 = ori1; o.ori2 = ori2;
+                o.perc = e.perc; o.len1 = e.len1; o.len2 = e.len2; o.type1 = pu ? 'p' : 's'; o.type2 = pv ? 'p' : 's';
+                out[outpos[seq]] = o;
+            }
+            continue;
+        }
+        for_each_attempt(D, e, off[i], [&](u64 seq, u64 a, u64 b, bool vu, bool vv) {
+            const hc_fno_read s1 = vu ? D.superread[D.sr_idx[a]] : ru;
+            const hc_fno_read s2 = vv ? D.superread[D.sr_idx[b]] : rv;
+            bool ok = s1.id != s2.id;
+            Derived d;
+            if (ok) {
+                const u64 key = (min(s1.id, s2.id) << 32) | max(s1.id, s2.id);
+                u64 h = hash_slot(key, mask);
+                while (keys[h] != key) h = (h + 1) & mask;
+                ok = mins[h] == seq;                                // first found wins, even if it fails below
+            }
+            if (ok) {
+                int i1l = 0, i1r = 0, i2l = 0, i2r = 0;
+                if (vu) {                                           // findCliqueIndex :331-347
+                    const hc_fno_subread s = D.sr_sub[a];
+                    i1l = s.index1 - s.startpos1;
+                    i1r = (s1.len2 > 0 || pu) ? s.index2 - s.startpos2 : i1l;
+                }
+                if (vv) {
+                    const hc_fno_subread s = D.sr_sub[b];
+                    i2l = s.index1 - s.startpos1;
+                    i2r = (s2.len2 > 0 || pv) ? s.index2 - s.startpos2 : i2l;
+                }
+                ok = compute_overlap_data(s1, s2, i1l, i1r, i2l, i2r, e, d);
+                if (ok && D.no_inclusions && d.perc == 100) ok = false;
+            }
+            if (!EMIT) flags[seq] = ok;
+            else if (ok && outpos[seq] < out_cap) {
+                hc_fno_overlap o;
+                memset(&o, 0, sizeof(o));
+                if (d.ord1 == '1') { o.id1 = s1.id; o.id2 = s2.id; o.type1 = d.t1; o.type2 = d.t2; }
+                else { o.id1 = s2.id; o.id2 = s1.id; o.type1 = d.t2; o.type2 = d.t1; }
+                o.pos1 = d.pos1; o.pos2 = d.pos2; o.ord = d.ord2; o.ori1 = ori1; o.ori2 = ori2;
+                o.perc = d.perc; o.len1 = d.ol1; o.len2 = d.ol2;
+                out[outpos[seq]] = o;
+            }
+        });
+    }
+}
+
+thread_local std::string g_fno_err;
+
+}  // namespace
+
+extern "C" const char* hc_last_error(void);
+void hc_set_last_error(const char* msg);   // hc_api.cu
+
+#define FCU(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            hc_set_last_error((std::string(#call) + ": " + cudaGetErrorString(_e)).c_str()); \
+            rc = HC_ERR_CUDA;                                                             \
+            goto done;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_t n_edges, hc_fno_overlap* out, uint64_t out_cap,
+                       uint64_t* n_out, int device) {
+    if (!in || !n_out || (n_edges && !edges) || (out_cap && !out)) { hc_set_last_error("hc_fno1: NULL argument"); return HC_ERR_ARG; }
+    *n_out = 0;
+    const u64 V = in->n_vertices, NS = in->n_superreads;
+    for (u64 i = 0; i < n_edges; i++)
+        if (edges[i].u >= V || edges[i].v >= V) { hc_set_last_error("hc_fno1: edge vertex out of range"); return HC_ERR_ARG; }
+    const u64 nsr = V ? in->sr_off[V] : 0;
+    for (u64 i = 0; i < nsr; i++)
+        if (in->sr_idx[i] >= NS) { hc_set_last_error("hc_fno1: super-read index out of range"); return HC_ERR_ARG; }
+    int rc = HC_OK;
+    uint8_t *d_vis = nullptr, *d_lab = nullptr;
+    hc_fno_read *d_vr = nullptr, *d_sr = nullptr;
+    u64 *d_sroff = nullptr, *d_off = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr;
+    uint32_t *d_sridx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
+    hc_fno_subread* d_sub = nullptr;
+    hc_fno_edge* d_edges = nullptr;
+    hc_fno_overlap* d_out = nullptr;
+    u64 attempts = 0, produced = 0, cap = 64, ncopy;
+    FnoDev D;
+    const int threads = 256;
+    int blocks;
+    FCU(cudaSetDevice(device));
+    if (n_edges == 0) goto done;
+    blocks = (int)((n_edges + threads - 1) / threads < 4096 ? (n_edges + threads - 1) / threads : 4096);
+    FCU(cudaMalloc(&d_vis, V ? V : 1)); FCU(cudaMalloc(&d_lab, V ? V : 1));
+    FCU(cudaMalloc(&d_vr, (V ? V : 1) * sizeof(hc_fno_read))); FCU(cudaMalloc(&d_sr, (NS ? NS : 1) * sizeof(hc_fno_read)));
+    FCU(cudaMalloc(&d_sroff, (V + 1) * sizeof(u64))); FCU(cudaMalloc(&d_sridx, (nsr ? nsr : 1) * sizeof(uint32_t)));
+    FCU(cudaMalloc(&d_sub, (nsr ? nsr : 1) * sizeof(hc_fno_subread)));
+    FCU(cudaMalloc(&d_edges, n_edges * sizeof(hc_fno_edge))); FCU(cudaMalloc(&d_cnt, n_edges * sizeof(uint32_t)));
+    FCU(cudaMalloc(&d_off, n_edges * sizeof(u64))); FCU(cudaMalloc(&d_total, sizeof(u64)));
+    FCU(cudaMemcpy(d_vis, in->visited, V, cudaMemcpyHostToDevice)); FCU(cudaMemcpy(d_lab, in->label, V, cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_vr, in->vertex_read, V * sizeof(hc_fno_read), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_sr, in->superread, NS * sizeof(hc_fno_read), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_sroff, in->sr_off, (V + 1) * sizeof(u64), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_sridx, in->sr_idx, nsr * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_sub, in->sr_sub, nsr * sizeof(hc_fno_subread), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_edges, edges, n_edges * sizeof(hc_fno_edge), cudaMemcpyHostToDevice));
+    D.n_vertices = V; D.visited = d_vis; D.label = d_lab; D.vertex_read = d_vr; D.sr_off = d_sroff; D.sr_idx = d_sridx;
+    D.sr_sub = d_sub; D.superread = d_sr; D.resolve_orientations = in->resolve_orientations; D.no_inclusions = in->no_inclusions;
+    fno_count<<<blocks, threads>>>(D, d_edges, n_edges, d_cnt);
+    scan_u32<<<1, 1024>>>(d_cnt, n_edges, d_off, d_total);
+    FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
+    if (attempts == 0) goto done;
+    while (cap < 2 * attempts + 2) cap <<= 1;
+    FCU(cudaMalloc(&d_keys, cap * sizeof(u64))); FCU(cudaMalloc(&d_mins, cap * sizeof(u64)));
+    FCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); FCU(cudaMemset(d_mins, 0xff, cap * sizeof(u64)));
+    FCU(cudaMalloc(&d_flags, attempts * sizeof(uint32_t))); FCU(cudaMalloc(&d_outpos, attempts * sizeof(u64)));
+    FCU(cudaMemset(d_flags, 0, attempts * sizeof(uint32_t)));
+    fno_claim<<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1);
+    fno_resolve<false><<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
+    scan_u32<<<1, 1024>>>(d_flags, attempts, d_outpos, d_total);
+    FCU(cudaMemcpy(&produced, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
+    *n_out = produced;
+    if (produced > out_cap) { hc_set_last_error("hc_fno1: output buffer too small (required size returned in n_out)"); rc = HC_ERR_CAPACITY; goto done; }
+    if (produced == 0) goto done;
+    ncopy = produced;
+    FCU(cudaMalloc(&d_out, ncopy * sizeof(hc_fno_overlap)));
+    fno_resolve<true><<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, d_outpos, d_out, ncopy);
+    FCU(cudaGetLastError());
+    FCU(cudaMemcpy(out, d_out, ncopy * sizeof(hc_fno_overlap), cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_vis); cudaFree(d_lab); cudaFree(d_vr); cudaFree(d_sr); cudaFree(d_sroff); cudaFree(d_sridx); cudaFree(d_sub);
+    cudaFree(d_edges); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_total); cudaFree(d_keys); cudaFree(d_mins);
+    cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out);
+    return rc;
+}

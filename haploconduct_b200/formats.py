@@ -49,6 +49,16 @@ BATCH_STATS = np.dtype(
 assert READ_DESC.itemsize == 24 and CANDIDATE.itemsize == 32 and PARAMS.itemsize == 40
 assert RESULT.itemsize == 48 and EDGE.itemsize == 48 and BATCH_STATS.itemsize == 72
 
+# FindNextOverlaps (FNO1) records
+FNO_EDGE = np.dtype([("u", "<u4"), ("v", "<u4"), ("pos1", "<i4"), ("pos2", "<i4"), ("perc", "<i4"), ("len1", "<i4"),
+                     ("len2", "<i4"), ("ord", "u1"), ("ori1", "u1"), ("ori2", "u1"), ("nonedge", "u1")])
+FNO_READ = np.dtype([("id", "<u8"), ("len1", "<u4"), ("len2", "<u4")])
+FNO_SUBREAD = np.dtype([("index1", "<i4"), ("index2", "<i4"), ("startpos1", "<i4"), ("startpos2", "<i4")])
+FNO_OVERLAP = np.dtype([("id1", "<u8"), ("id2", "<u8"), ("pos1", "<i4"), ("pos2", "<i4"), ("perc", "<i4"), ("len1", "<i4"),
+                        ("len2", "<i4"), ("ord", "u1"), ("ori1", "u1"), ("ori2", "u1"), ("type1", "u1"), ("type2", "u1"),
+                        ("reserved", "u1", (7,))])
+assert FNO_EDGE.itemsize == 32 and FNO_READ.itemsize == 16 and FNO_SUBREAD.itemsize == 16 and FNO_OVERLAP.itemsize == 48
+
 CLASS_DISCARD, CLASS_EDGE, CLASS_NONEDGE = 0, 1, 2
 FLAG_EXACT_EDGE_SCORES = 1
 
@@ -300,3 +310,32 @@ def prefilter(cands: np.ndarray, min_overlap_len: int, min_overlap_perc: int = 0
     out[inb & (perc < min_overlap_perc)] = -1
     out[c["idx1"] == c["idx2"]] = -1
     return out
+
+
+# ---- FindNextOverlaps -------------------------------------------------------------------------------
+@dataclass
+class FnoInput:
+    """Array form of what SRBuilder::findNextOverlaps reads (src/FindNextOverlaps.cpp:890-913)."""
+
+    visited: np.ndarray       # uint8 [V]
+    label: np.ndarray         # uint8 [V]
+    vertex_read: np.ndarray   # FNO_READ [V]
+    sr_off: np.ndarray        # uint64 [V+1]
+    sr_idx: np.ndarray        # uint32
+    sr_sub: np.ndarray        # FNO_SUBREAD
+    superread: np.ndarray     # FNO_READ
+    resolve_orientations: int
+    no_inclusions: int
+    edges: np.ndarray         # FNO_EDGE, processing order
+
+
+def fno_lines(ov: np.ndarray) -> List[str]:
+    """The reference's overlap line (src/FindNextOverlaps.cpp:122-148): PERC2 is the literal 0."""
+    return ["%d\t%d\t%d\t%d\t%s\t%s\t%s\t%d\t0\t%d\t%d\t%s\t%s" % (
+        o["id1"], o["id2"], o["pos1"], o["pos2"], chr(o["ord"]), chr(o["ori1"]), chr(o["ori2"]), o["perc"], o["len1"], o["len2"],
+        chr(o["type1"]), chr(o["type2"])) for o in ov]
+
+
+def fno_output_file(ov: np.ndarray) -> List[str]:
+    """overlaps.txt = std::set<std::string> of the lines: unique, byte-lexicographic (:918,:946-948)."""
+    return sorted(set(fno_lines(ov)), key=lambda s: s.encode())

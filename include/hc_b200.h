@@ -192,6 +192,61 @@ double hc_phred_to_prob(int phred);
  * "exp(mean) > threshold" of src/EdgeCalculator.cpp:138,404 is evaluated as "mean >= x" on the device). */
 double hc_exp_threshold(double threshold);
 
+/* ------------------------------------------------------------------------------------------
+ * FindNextOverlaps (FNO1): SRBuilder::findNextOverlaps, src/FindNextOverlaps.cpp:890-958 with
+ * updateOverlap :25-327, findCliqueIndex :331-347, computeOverlapData :351-565.
+ *
+ * After an iteration has merged reads into super-reads, every edge / removed edge / non-edge overlap
+ * (u, v) of the old graph is re-expressed between the NEW reads: the unmerged read itself, or every
+ * super-read containing u resp. v, by index arithmetic on the sub-read positions.  Per unordered
+ * pair of new reads the FIRST derivation in processing order wins, even if it then fails
+ * (:84-97 precede :115-118).  The host keeps the graph walk that produces the edge stream
+ * (:605-631, :635-697, :816-887) and the sorted, de-duplicated text output (:937-953).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint32_t u, v;            /* old vertices                                                      */
+    int32_t  pos1, pos2;      /* Edge::pos1 / pos2                                                 */
+    int32_t  perc, len1, len2;/* Edge::overlap_perc / overlap_len1 / overlap_len2                  */
+    uint8_t  ord;             /* '1', '2' or '-'                                                   */
+    uint8_t  ori1, ori2;      /* Edge::ori1 / ori2 (1 = NORMAL)                                    */
+    uint8_t  nonedge;         /* Edge::score == 0: non-edge overlap, ORI taken against the vertex labels (:34-37) */
+} hc_fno_edge;                /* 32 bytes */
+
+typedef struct {
+    uint64_t id;              /* new read id: super-read id, or nodes_to_new_IDs[v] of an unmerged vertex */
+    uint32_t len1, len2;      /* sequence length(s); len2 == 0 <=> single-end                      */
+} hc_fno_read;                /* 16 bytes */
+
+typedef struct { int32_t index1, index2, startpos1, startpos2; } hc_fno_subread;   /* SubreadInfo, src/Types.h:77-82 */
+
+typedef struct {
+    uint64_t n_vertices;
+    const uint8_t*        visited;       /* [V] SRBuilder::visited                                   */
+    const uint8_t*        label;         /* [V] OverlapGraph::getOrientation(v)                      */
+    const hc_fno_read*    vertex_read;   /* [V] original read of the vertex: new id (if !visited) + lengths */
+    const uint64_t*       sr_off;        /* [V+1] CSR of nodes_to_SR (:898-913)                       */
+    const uint32_t*       sr_idx;        /* [sr_off[V]] super-read index per entry, list order        */
+    const hc_fno_subread* sr_sub;        /* [sr_off[V]] get_subread_info(v) of that super-read        */
+    uint64_t n_superreads;
+    const hc_fno_read*    superread;     /* [n_superreads]                                            */
+    uint8_t resolve_orientations;        /* ProgramSettings::resolve_orientations                     */
+    uint8_t no_inclusions;               /* ProgramSettings::no_inclusions (drop perc == 100)          */
+} hc_fno_input;
+
+typedef struct {
+    uint64_t id1, id2;        /* ID1 / ID2 of the emitted overlap line                             */
+    int32_t  pos1, pos2, perc, len1, len2;
+    uint8_t  ord, ori1, ori2, type1, type2;   /* characters: '1'/'2'/'-', '+'/'-', 's'/'p'          */
+    uint8_t  reserved[7];
+} hc_fno_overlap;             /* 48 bytes; line = id1 id2 pos1 pos2 ord ori1 ori2 perc 0 len1 len2 type1 type2 */
+
+/* Derives the next-iteration overlaps on `device`.  `out` receives the successful derivations in
+ * processing order (edge order, then super-read list order); the caller formats, sorts and
+ * de-duplicates the lines like the reference's std::set<std::string> (:918,:946-948).
+ * Returns HC_ERR_CAPACITY (required size in *n_out) if out_cap is too small. */
+int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_t n_edges,
+            hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out, int device);
+
 int         hc_device_count(void);
 const char* hc_last_error(void);
 const char* hc_version(void);

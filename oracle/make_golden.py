@@ -48,6 +48,29 @@ def run_case(name: str, rs: F.ReadSet, cands: np.ndarray, ps: dict) -> None:
           (name, rs.n_reads, len(cands), len(out["cands"]), cls.tolist(), out["graph_edges"]))
 
 
+def run_fno_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> None:
+    """Merge iteration + the reference's own findNextOverlaps(): keeps its inputs (array form) and its overlaps.txt."""
+    import subprocess
+
+    d = tempfile.mkdtemp(prefix="hc_golden_fno_")
+    F.write_fastq_set(rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    F.write_overlaps(d + "/ov.txt", cands, rs.ids)
+    cmd = [O.REF_DRIVER, "--overlaps", d + "/ov.txt", "--run", "--merge-fno1", d + "/fno_in.txt"] + args
+    if rs.n_single:
+        cmd += ["--singles", d + "/s.fastq"]
+    if rs.n_reads > rs.n_single:
+        cmd += ["--paired1", d + "/p1.fastq", "--paired2", d + "/p2.fastq"]
+    subprocess.run(cmd, cwd=d, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    fi = O.parse_fno_dump(d + "/fno_in.txt")
+    with open(d + "/overlaps.txt") as f:
+        ref = f.read().split("\n")[:-1]
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), visited=fi.visited, label=fi.label, vertex_read=fi.vertex_read,
+                        sr_off=fi.sr_off, sr_idx=fi.sr_idx, sr_sub=fi.sr_sub, superread=fi.superread,
+                        flags=np.array([fi.resolve_orientations, fi.no_inclusions]), edges=fi.edges, ref_lines=np.array(ref))
+    print("%-28s vertices=%d superreads=%d (paired %d) edges=%d -> %d overlap lines" %
+          (name, len(fi.visited), len(fi.superread), int((fi.superread["len2"] > 0).sum()), len(fi.edges), len(ref)))
+
+
 def main() -> None:
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -80,6 +103,15 @@ def main() -> None:
     run_case("synth_mismatch_void", ss5.rs, c5, dict(edge_threshold=0.9, ov_threshold=0.5, min_overlap_len=120, mismatch=0.01,
                                                       relax_PE_edges=True))
 
+    # ---- FindNextOverlaps (FNO1): the reference's overlaps.txt after one merge iteration
+    s700 = full.subset(range(0, 700))
+    cs = W.seed_candidates(s700, k=24, orientations=((1, 1),))
+    run_fno_case("fno1_savage_singles", s700, cs, ["--edge_threshold", "0.97", "--min_overlap_len", "200", "--keep_singletons", "200"])
+    for k, (seed, ns, npair, div) in enumerate(((5, 150, 250, (0.0, 0.0, 0.0)), (6, 0, 400, (0.0, 0.0)), (7, 300, 100, (0.0, 0.01)))):
+        sx = W.synth_readset(ns, npair, genome_len=1500, n_strains=len(div), divergence=div, seed=seed, n_rate=0.0002, flip_fraction=0.2)
+        cx = W.geometry_candidates(sx, 6000, seed=seed + 1, junk_fraction=0.02, min_ov=40)
+        run_fno_case("fno1_synth_paired_%d" % k, sx.rs, cx, ["--edge_threshold", "0.9", "--min_overlap_len", "80", "--keep_singletons", "0"]
+                     + (["--no_inclusion_overlaps", "1"] if k == 2 else []))
 
 if __name__ == "__main__":
     main()

@@ -150,3 +150,83 @@ def parse_graph_dump(path: str) -> np.ndarray:
             rows.append((int(t[0]), int(t[1]), float.fromhex(t[2]), float.fromhex(t[3]), int(t[4]), int(t[5]), int(t[6]),
                          int(t[7]), int(t[8]), int(t[9]), ord(t[10]) if t[10] else 0, int(t[11]), int(t[12]), int(t[13])))
     return np.array(rows, dtype=REF_EDGE)
+
+
+# ---- FindNextOverlaps (FNO1) ---------------------------------------------------------------------------
+def parse_fno_dump(path: str):
+    """Reads the --merge-fno1 dump of ref_driver into a formats.FnoInput."""
+    from haploconduct_b200 import formats as F
+
+    verts, srs, edges = [], [], []
+    ro = ni = 0
+    with open(path) as f:
+        for line in f:
+            t = line.rstrip("\n").split("\t")
+            if t[0] == "P":
+                ro, ni = int(t[1]), int(t[2])
+            elif t[0] == "S":
+                srs.append((int(t[2]), int(t[3]), int(t[4])))
+            elif t[0] == "V":
+                subs = [tuple(int(x) for x in s.split(":")) for s in t[7:]]
+                verts.append((int(t[2]), int(t[3]), int(t[4]), int(t[5]), int(t[6]), subs))
+            elif t[0] == "E":
+                edges.append((int(t[2]), int(t[3]), int(t[4]), int(t[5]), int(t[10]), int(t[11]), int(t[12]), ord(t[6]), int(t[7]),
+                              int(t[8]), int(t[9])))
+    V = len(verts)
+    visited = np.array([v[0] for v in verts], dtype=np.uint8)
+    label = np.array([v[2] for v in verts], dtype=np.uint8)
+    vr = np.zeros(V, dtype=F.FNO_READ)
+    vr["id"] = [max(v[1], 0) for v in verts]
+    vr["len1"] = [v[3] for v in verts]
+    vr["len2"] = [v[4] for v in verts]
+    off = np.zeros(V + 1, dtype=np.uint64)
+    idx, sub = [], []
+    for i, v in enumerate(verts):
+        for s in v[5]:
+            idx.append(s[0])
+            sub.append(s[1:])
+        off[i + 1] = len(idx)
+    sr = np.zeros(len(srs), dtype=F.FNO_READ)
+    if srs:
+        sr["id"], sr["len1"], sr["len2"] = zip(*srs)
+    return F.FnoInput(visited=visited, label=label, vertex_read=vr, sr_off=off, sr_idx=np.array(idx, dtype=np.uint32),
+                      sr_sub=np.array(sub, dtype=F.FNO_SUBREAD) if sub else np.zeros(0, dtype=F.FNO_SUBREAD), superread=sr,
+                      resolve_orientations=ro, no_inclusions=ni, edges=np.array(edges, dtype=F.FNO_EDGE))
+
+
+class _FnoInputC(ctypes.Structure):
+    _fields_ = [("n_vertices", ctypes.c_uint64), ("visited", ctypes.c_void_p), ("label", ctypes.c_void_p),
+                ("vertex_read", ctypes.c_void_p), ("sr_off", ctypes.c_void_p), ("sr_idx", ctypes.c_void_p),
+                ("sr_sub", ctypes.c_void_p), ("n_superreads", ctypes.c_uint64), ("superread", ctypes.c_void_p),
+                ("resolve_orientations", ctypes.c_uint8), ("no_inclusions", ctypes.c_uint8)]
+
+
+def fno_input_struct(fi):
+    """ctypes image of hc_fno_input; the numpy arrays of `fi` must stay alive while it is used."""
+    keep = [np.ascontiguousarray(a) for a in (fi.visited, fi.label, fi.vertex_read, fi.sr_off, fi.sr_idx, fi.sr_sub, fi.superread)]
+    st = _FnoInputC(len(fi.visited), keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
+                    keep[4].ctypes.data, keep[5].ctypes.data, len(fi.superread), keep[6].ctypes.data, fi.resolve_orientations,
+                    fi.no_inclusions)
+    return st, keep
+
+
+def fno1(fi) -> np.ndarray:
+    """hco_fno1: the derived overlaps in processing order."""
+    from haploconduct_b200 import formats as F
+
+    L = lib()
+    L.hco_fno1.restype = ctypes.c_int
+    L.hco_fno1.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                           ctypes.POINTER(ctypes.c_uint64)]
+    st, keep = fno_input_struct(fi)
+    edges = np.ascontiguousarray(fi.edges)
+    cap = 1024
+    while True:
+        out = np.zeros(cap, dtype=F.FNO_OVERLAP)
+        n = ctypes.c_uint64(0)
+        rc = L.hco_fno1(ctypes.byref(st), edges.ctypes.data, len(edges), out.ctypes.data, cap, ctypes.byref(n))
+        if rc == 0:
+            return out[: n.value]
+        if rc != -5:
+            raise RuntimeError("hco_fno1 failed with %d" % rc)
+        cap = int(n.value)

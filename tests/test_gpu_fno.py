@@ -1,0 +1,36 @@
+"""GPU suite: hc_fno1 (CUDA) against the reference's findNextOverlaps() output (golden) and, on
+dense random inputs, against the pinned C oracle -- records identical, in processing order."""
+import numpy as np
+import pytest
+
+from haploconduct_b200 import capi, formats as F
+from oracle import oracle as O
+from util import fno_golden_names, load_fno_golden, random_fno_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", fno_golden_names())
+def test_fno1_reference_file(built_lib, name):
+    fi, ref = load_fno_golden(name)
+    ov = capi.fno1(fi)
+    assert F.fno_output_file(ov) == ref
+    assert ov.tobytes() == O.fno1(fi).tobytes()      # same records, same (processing) order
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_fno1_random_dense_inputs(built_lib, seed):
+    fi = random_fno_input(seed, n_vertices=500, n_sr=150, n_edges=60000)
+    a, b = capi.fno1(fi), O.fno1(fi)
+    assert len(a) == len(b) and len(a) > 1000
+    assert a.tobytes() == b.tobytes()
+
+
+def test_fno1_empty_and_bad_input(built_lib):
+    fi = random_fno_input(9, n_edges=10)
+    fi.edges = fi.edges[:0]
+    assert len(capi.fno1(fi)) == 0
+    fi = random_fno_input(9, n_edges=10)
+    fi.edges["u"][3] = 10 ** 6
+    with pytest.raises(capi.HcError):
+        capi.fno1(fi)

@@ -35,7 +35,66 @@ class Golden:
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("fno1_"))
+
+
+def fno_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "fno1_*.npz")))
+
+
+def load_fno_golden(name):
+    """(FnoInput, reference overlaps.txt lines) -- inputs and output of the reference's own findNextOverlaps()."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    fi = F.FnoInput(visited=z["visited"], label=z["label"], vertex_read=z["vertex_read"], sr_off=z["sr_off"], sr_idx=z["sr_idx"],
+                    sr_sub=z["sr_sub"], superread=z["superread"], resolve_orientations=int(z["flags"][0]),
+                    no_inclusions=int(z["flags"][1]), edges=z["edges"])
+    return fi, [str(x) for x in z["ref_lines"]]
+
+
+def random_fno_input(seed, n_vertices=300, n_sr=120, n_edges=4000, paired_fraction=0.4):
+    """Random but self-consistent FNO1 input: many super-reads per vertex, so that the first-found-wins
+    rule, failing derivations and all four read-type combinations are exercised far more densely
+    than real merge iterations do."""
+    rng = np.random.RandomState(seed)
+    V = n_vertices
+    visited = (rng.random_sample(V) < 0.6).astype(np.uint8)
+    label = rng.randint(0, 2, size=V).astype(np.uint8)
+    vr = np.zeros(V, dtype=F.FNO_READ)
+    vr["id"] = rng.permutation(V) + n_sr          # new ids of unmerged reads follow the super-read ids
+    vr["len1"] = rng.randint(60, 300, size=V)
+    vr["len2"] = np.where(rng.random_sample(V) < paired_fraction, rng.randint(60, 300, size=V), 0)
+    sr = np.zeros(n_sr, dtype=F.FNO_READ)
+    sr["id"] = np.arange(n_sr)
+    sr["len1"] = rng.randint(100, 900, size=n_sr)
+    sr["len2"] = np.where(rng.random_sample(n_sr) < paired_fraction, rng.randint(100, 900, size=n_sr), 0)
+    off = np.zeros(V + 1, dtype=np.uint64)
+    idx, sub = [], []
+    for v in range(V):
+        if visited[v]:
+            k = int(rng.randint(0, 5))
+            for s in rng.choice(n_sr, size=k, replace=False):
+                idx.append(int(s))
+                i1, i2 = int(rng.randint(0, 400)), int(rng.randint(0, 400))
+                s1 = 0 if i1 > 0 and rng.random_sample() < 0.8 else int(rng.randint(0, 30))
+                s2 = 0 if i2 > 0 and rng.random_sample() < 0.8 else int(rng.randint(0, 30))
+                sub.append((i1, i2, s1, s2))
+        off[v + 1] = len(idx)
+    e = np.zeros(n_edges, dtype=F.FNO_EDGE)
+    e["u"] = rng.randint(0, V, size=n_edges)
+    e["v"] = (e["u"] + rng.randint(1, V, size=n_edges)) % V
+    e["pos1"] = rng.randint(0, 250, size=n_edges)
+    e["pos2"] = rng.randint(0, 250, size=n_edges)
+    e["perc"] = rng.randint(20, 101, size=n_edges)
+    e["len1"] = rng.randint(30, 250, size=n_edges)
+    e["len2"] = rng.randint(0, 250, size=n_edges)
+    pu, pv = vr["len2"][e["u"]] > 0, vr["len2"][e["v"]] > 0
+    e["ord"] = np.where(pu & pv, np.where(rng.random_sample(n_edges) < 0.5, ord("1"), ord("2")), ord("-"))
+    e["ori1"] = rng.randint(0, 2, size=n_edges)
+    e["ori2"] = rng.randint(0, 2, size=n_edges)
+    e["nonedge"] = rng.random_sample(n_edges) < 0.5
+    return F.FnoInput(visited=visited, label=label, vertex_read=vr, sr_off=off, sr_idx=np.array(idx, dtype=np.uint32),
+                      sr_sub=np.array(sub, dtype=F.FNO_SUBREAD) if sub else np.zeros(0, dtype=F.FNO_SUBREAD), superread=sr,
+                      resolve_orientations=1, no_inclusions=int(seed % 2), edges=e)
 
 
 def load_golden(name):
