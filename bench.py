@@ -167,6 +167,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--exact-edge-scores", action="store_true",
+                    help="HC_FLAG_EXACT_EDGE_SCORES: re-sum every accepted edge in the reference's order (diagnostic)")
     ap.add_argument("--position-sorted-ids", action="store_true",
                     help="diagnostic only: number the reads in genome order (cache-friendly, NOT the benchmark layout)")
     args = ap.parse_args()
@@ -232,7 +234,7 @@ def main() -> None:
     n = rec.shape[0]
     torch.cuda.synchronize()
     log("[rank %d] %d candidates (shard %d/%d) generated in %.1fs" % (rank, n, shard, N_SHARDS, time.time() - t1))
-    params = F.make_params(**PARAMS)
+    params = F.make_params(flags=F.FLAG_EXACT_EDGE_SCORES if args.exact_edge_scores else 0, **PARAMS)
     d_edges = torch.empty((n, 48), dtype=torch.uint8, device=dev)
     d_nonedge = torch.empty(n, dtype=torch.int64, device=dev)
     d_counts = torch.zeros(4, dtype=torch.int64, device=dev)

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libhc_b200.so")
 EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_device", "hc_overlap_score",
-    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1",
+    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -67,6 +67,8 @@ def lib() -> ctypes.CDLL:
         L.hc_device_count.argtypes = []
         L.hc_fno1.restype = i32
         L.hc_fno1.argtypes = [vp, vp, u64, vp, u64, ctypes.POINTER(u64), i32]
+        L.hc_fno3.restype = i32
+        L.hc_fno3.argtypes = [u64, vp, vp, vp, u64, vp, i32, vp, u64, ctypes.POINTER(u64), i32]
         L.hc_last_error.restype = ctypes.c_char_p
         L.hc_version.restype = ctypes.c_char_p
         _lib = L
@@ -198,6 +200,22 @@ def fno1(fi: "F.FnoInput", device: int = 0) -> np.ndarray:
         n = ctypes.c_uint64(0)
         rc = lib().hc_fno1(ctypes.byref(st), edges.ctypes.data if len(edges) else None, len(edges), out.ctypes.data, cap,
                            ctypes.byref(n), device)
+        if rc == 0:
+            return out[: n.value]
+        if rc != -5:
+            raise HcError(rc, last_error())
+        cap = int(n.value)
+
+
+def fno3(fi: "F.Fno3Input", device: int = 0) -> np.ndarray:
+    """hc_fno3: overlaps between new reads sharing an original read, in discovery order."""
+    off, idx, pos, reads = (np.ascontiguousarray(a) for a in (fi.off, fi.sr_idx, fi.sr_pos, fi.reads))
+    cap = 4096
+    while True:
+        out = np.zeros(cap, dtype=F.FNO_OVERLAP)
+        n = ctypes.c_uint64(0)
+        rc = lib().hc_fno3(len(off) - 1, off.ctypes.data, idx.ctypes.data, pos.ctypes.data, len(reads), reads.ctypes.data,
+                           fi.no_inclusions, out.ctypes.data, cap, ctypes.byref(n), device)
         if rc == 0:
             return out[: n.value]
         if rc != -5:

@@ -269,6 +269,109 @@ __global__ void fno_resolve(FnoDev D, const hc_fno_edge* edges, u64 n, const u64
     }
 }
 
+
+// ---- FindNextOverlaps3 (src/FindNextOverlaps3.cpp:90-406) ------------------------------------------------
+__device__ __forceinline__ int perc_one(int l, int a) { return (int)floorf(__fmul_rn(__fdiv_rn((float)l, (float)a), 100.0f)); }
+
+// deduceOverlap :176-406; false = "this overlap will be ignored"
+__device__ bool deduce_overlap(const hc_fno_read& A, const hc_fno_read& B, const hc_fno3_pos& pa, const hc_fno3_pos& pb,
+                               hc_fno_overlap& o) {
+    const bool pA = A.len2 > 0, pB = B.len2 > 0;
+    memset(&o, 0, sizeof(o));
+    o.ori1 = '+'; o.ori2 = '+'; o.ord = '-';
+    const int i1l = pa.index1, i1r = pa.index2, i2l = pb.index1, i2r = pb.index2;
+    const bool a_first = i1l - i2l >= 0;
+    o.id1 = a_first ? A.id : B.id;
+    o.id2 = a_first ? B.id : A.id;
+    o.pos1 = a_first ? i1l - i2l : i2l - i1l;
+    if (!pA && !pB) {                                                       // S-S :202-243
+        const int lenA = (int)A.len1, lenB = (int)B.len1;
+        if (o.pos1 > (a_first ? lenA : lenB)) return false;
+        o.len1 = a_first ? min(lenA - o.pos1, lenB) : min(lenA, lenB - o.pos1);
+        o.perc = perc_of(o.len1, lenA, lenB);
+        o.type1 = 's'; o.type2 = 's';
+        return true;
+    }
+    if (pA && !pB) {                                                        // P-S :244-287
+        const int lenA1 = (int)A.len1, lenA2 = (int)A.len2, lenB = (int)B.len1;
+        o.len1 = a_first ? lenA1 - o.pos1 : min(lenA1, lenB - o.pos1);
+        if (o.len1 <= 0) return false;
+        o.type1 = a_first ? 'p' : 's'; o.type2 = a_first ? 's' : 'p';
+        o.perc = perc_one(o.len1, lenA1);
+        o.pos2 = i2r - i1r;
+        o.len2 = min(lenA2, lenB - o.pos2);
+        if (o.len2 <= 0 || o.pos2 < 0) return false;
+        o.perc2 = perc_one(o.len2, lenA2);
+        return true;
+    }
+    if (!pA && pB) {                                                        // S-P :288-331
+        const int lenA = (int)A.len1, lenB1 = (int)B.len1, lenB2 = (int)B.len2;
+        o.len1 = a_first ? min(lenB1, lenA - o.pos1) : lenB1 - o.pos1;
+        if (o.len1 <= 0) return false;
+        o.type1 = a_first ? 's' : 'p'; o.type2 = a_first ? 'p' : 's';
+        o.perc = perc_one(o.len1, lenB1);
+        o.pos2 = i1r - i2r;
+        o.len2 = min(lenB2, lenA - o.pos2);
+        if (o.len2 <= 0 || o.pos2 < 0) return false;
+        o.perc2 = perc_one(o.len2, lenB2);
+        return true;
+    }
+    const int lenA = (int)A.len1, lenB = (int)B.len1, lenC = (int)A.len2, lenD = (int)B.len2;   // P-P :332-401
+    o.len1 = a_first ? min(lenA - o.pos1, lenB) : min(lenA, lenB - o.pos1);
+    const bool back = i1r - i2r >= 0;
+    o.pos2 = back ? i1r - i2r : i2r - i1r;
+    o.len2 = back ? min(lenC - o.pos2, lenD) : min(lenC, lenD - o.pos2);
+    if (o.len1 <= 0 || o.len2 <= 0) return false;
+    o.perc = perc_of(o.len1, lenA, lenB);
+    o.perc2 = perc_of(o.len2, lenC, lenD);
+    o.ord = (a_first == back) ? '1' : '2';
+    o.type1 = 'p'; o.type2 = 'p';
+    return true;
+}
+
+__global__ void fno3_count(const u64* off, u64 n, uint32_t* cnt) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (u64)gridDim.x * blockDim.x) {
+        const u64 c = off[k + 1] - off[k];
+        cnt[k] = (uint32_t)(c * (c - 1) / 2);
+    }
+}
+
+// MODE 0: claim (atomicMin of the sequence number per pair of new reads); 1: flag survivors; 2: emit
+template <int MODE>
+__global__ void fno3_pass(const u64* off, u64 n, const uint32_t* sr_idx, const hc_fno3_pos* sr_pos, const hc_fno_read* reads,
+                          uint32_t no_inclusions, const u64* seq0, u64* keys, u64* mins, u64 mask, uint32_t* flags,
+                          const u64* outpos, hc_fno_overlap* out, u64 out_cap) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (u64)gridDim.x * blockDim.x) {
+        u64 seq = seq0[k];
+        for (u64 i = off[k]; i < off[k + 1]; i++) {
+            for (u64 j = i + 1; j < off[k + 1]; j++, seq++) {
+                const hc_fno_read A = reads[sr_idx[i]], B = reads[sr_idx[j]];
+                const u64 key = (min(A.id, B.id) << 32) | max(A.id, B.id);
+                u64 h = hash_slot(key, mask);
+                if (MODE == 0) {
+                    while (true) {
+                        const u64 prev = atomicCAS(&keys[h], ~0ull, key);
+                        if (prev == ~0ull || prev == key) break;
+                        h = (h + 1) & mask;
+                    }
+                    atomicMin(&mins[h], seq);
+                    continue;
+                }
+                while (keys[h] != key) h = (h + 1) & mask;
+                bool ok = mins[h] == seq;                                   // first original wins, :116-121
+                hc_fno_overlap o;
+                if (ok) ok = deduce_overlap(A, B, sr_pos[i], sr_pos[j], o);
+                if (ok) {
+                    const unsigned perc = o.perc2 > 0 ? (unsigned)(0.5 * (o.perc + o.perc2)) : (unsigned)o.perc;   // Overlap::get_perc
+                    ok = !(no_inclusions && perc == 100) && o.len1 > 0;      // :157-165
+                }
+                if (MODE == 1) flags[seq] = ok;
+                else if (ok && outpos[seq] < out_cap) out[outpos[seq]] = o;
+            }
+        }
+    }
+}
+
 thread_local std::string g_fno_err;
 
 }  // namespace
@@ -351,5 +454,61 @@ done:
     cudaFree(d_vis); cudaFree(d_lab); cudaFree(d_vr); cudaFree(d_sr); cudaFree(d_sroff); cudaFree(d_sridx); cudaFree(d_sub);
     cudaFree(d_edges); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_total); cudaFree(d_keys); cudaFree(d_mins);
     cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out);
+    return rc;
+}
+
+
+extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t* sr_idx, const hc_fno3_pos* sr_pos, uint64_t n_reads,
+                       const hc_fno_read* reads, int no_inclusions, hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out,
+                       int device) {
+    if (!n_out || (n_originals && (!off || !sr_idx || !sr_pos || !reads)) || (out_cap && !out)) {
+        hc_set_last_error("hc_fno3: NULL argument");
+        return HC_ERR_ARG;
+    }
+    *n_out = 0;
+    if (n_originals == 0) return HC_OK;
+    const u64 nent = off[n_originals];
+    for (u64 i = 0; i < nent; i++)
+        if (sr_idx[i] >= n_reads) { hc_set_last_error("hc_fno3: read index out of range"); return HC_ERR_ARG; }
+    int rc = HC_OK;
+    u64 *d_off = nullptr, *d_seq = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr;
+    uint32_t *d_idx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
+    hc_fno3_pos* d_pos = nullptr;
+    hc_fno_read* d_reads = nullptr;
+    hc_fno_overlap* d_out = nullptr;
+    u64 attempts = 0, produced = 0, cap = 64;
+    const int threads = 128;
+    const int blocks = (int)((n_originals + threads - 1) / threads < 8192 ? (n_originals + threads - 1) / threads : 8192);
+    FCU(cudaSetDevice(device));
+    FCU(cudaMalloc(&d_off, (n_originals + 1) * sizeof(u64))); FCU(cudaMalloc(&d_idx, (nent ? nent : 1) * sizeof(uint32_t)));
+    FCU(cudaMalloc(&d_pos, (nent ? nent : 1) * sizeof(hc_fno3_pos))); FCU(cudaMalloc(&d_reads, (n_reads ? n_reads : 1) * sizeof(hc_fno_read)));
+    FCU(cudaMalloc(&d_cnt, n_originals * sizeof(uint32_t))); FCU(cudaMalloc(&d_seq, n_originals * sizeof(u64)));
+    FCU(cudaMalloc(&d_total, sizeof(u64)));
+    FCU(cudaMemcpy(d_off, off, (n_originals + 1) * sizeof(u64), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_idx, sr_idx, nent * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_pos, sr_pos, nent * sizeof(hc_fno3_pos), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(d_reads, reads, n_reads * sizeof(hc_fno_read), cudaMemcpyHostToDevice));
+    fno3_count<<<blocks, threads>>>(d_off, n_originals, d_cnt);
+    scan_u32<<<1, 1024>>>(d_cnt, n_originals, d_seq, d_total);
+    FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
+    if (attempts == 0) goto done;
+    while (cap < 2 * attempts + 2) cap <<= 1;
+    FCU(cudaMalloc(&d_keys, cap * sizeof(u64))); FCU(cudaMalloc(&d_mins, cap * sizeof(u64)));
+    FCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); FCU(cudaMemset(d_mins, 0xff, cap * sizeof(u64)));
+    FCU(cudaMalloc(&d_flags, attempts * sizeof(uint32_t))); FCU(cudaMalloc(&d_outpos, attempts * sizeof(u64)));
+    fno3_pass<0><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, nullptr, nullptr, nullptr, 0);
+    fno3_pass<1><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
+    scan_u32<<<1, 1024>>>(d_flags, attempts, d_outpos, d_total);
+    FCU(cudaMemcpy(&produced, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
+    *n_out = produced;
+    if (produced > out_cap) { hc_set_last_error("hc_fno3: output buffer too small (required size returned in n_out)"); rc = HC_ERR_CAPACITY; goto done; }
+    if (produced == 0) goto done;
+    FCU(cudaMalloc(&d_out, produced * sizeof(hc_fno_overlap)));
+    fno3_pass<2><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, d_outpos, d_out, produced);
+    FCU(cudaGetLastError());
+    FCU(cudaMemcpy(out, d_out, produced * sizeof(hc_fno_overlap), cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_off); cudaFree(d_idx); cudaFree(d_pos); cudaFree(d_reads); cudaFree(d_cnt); cudaFree(d_seq); cudaFree(d_total);
+    cudaFree(d_keys); cudaFree(d_mins); cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out);
     return rc;
 }

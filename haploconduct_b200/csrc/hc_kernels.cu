@@ -637,25 +637,46 @@ __device__ void exact_window(const hc_kparams& P, const Win& w, double& mean, do
     double total = 0.0;
     uint32_t tl = 0, mm = 0;
     const u64 yp = 16ull * w.ypos16;
-    for (uint32_t i = 0; i < w.L; i++) {
-        const u64 xa = w.xpos + i, xb = yp + i;
-        uint32_t qa, qb, mis;
-        if (P.packed) {
-            const uint32_t a = P.pk[xa], b = P.pk[xb];
-            if (a == 0 || b == 0) continue;                                   // N, :35-39,:122-124
-            qa = a & 63u; qb = b & 63u; mis = (a >> 6) != (b >> 6);
-        } else {
-            const uint32_t nA = (P.nmask[xa >> 5] >> (xa & 31)) & 1u, nB = (P.nmask[xb >> 5] >> (xb & 31)) & 1u;
-            if (nA | nB) continue;                                            // :35-39,:122-124
-            const uint32_t a = (P.base2[xa >> 4] >> (2 * (xa & 15))) & 3u, b = (P.base2[xb >> 4] >> (2 * (xb & 15))) & 3u;
-            qa = P.qual[xa]; qb = P.qual[xb];
-            mis = a != b;
+    if (P.packed) {
+        // 16 positions per step: B side one aligned 128-bit load, A side five words + funnel shifts;
+        // the additions stay strictly sequential in position order (:106-121).
+        const uint32_t sh = ((uint32_t)w.xpos & 3u) * 8u;
+        for (uint32_t i0 = 0; i0 < w.L; i0 += 16) {
+            const uint32_t* xa = reinterpret_cast<const uint32_t*>(P.pk + ((w.xpos + i0) & ~3ull));
+            const uint32_t x0 = __ldg(xa), x1 = __ldg(xa + 1), x2 = __ldg(xa + 2), x3 = __ldg(xa + 3), x4 = __ldg(xa + 4);
+            const uint4 yv = __ldg(reinterpret_cast<const uint4*>(P.pk + yp + i0));
+            const uint32_t A[4] = {__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                                   __funnelshift_r(x3, x4, sh)};
+            const uint32_t B[4] = {yv.x, yv.y, yv.z, yv.w};
+            const uint32_t lim = min(16u, w.L - i0);
+#pragma unroll
+            for (uint32_t j = 0; j < 16; j++) {
+                if (j < lim) {
+                    const uint32_t a = (A[j >> 2] >> (8 * (j & 3))) & 0xffu, b = (B[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    if (a != 0 && b != 0) {                                           // N, :35-39,:122-124
+                        const uint32_t mis = (a >> 6) != (b >> 6);
+                        mm += mis;
+                        const double lp = __ldg(P.dbl_table + hc_dbl_index(a & 63u, b & 63u, mis, n1));
+                        if (lp > 0.0) { status = HC_WIN_VOID; return; }              // :125-127
+                        total = __dadd_rn(total, lp);                                 // :119
+                        tl++;
+                    }
+                }
+            }
         }
-        mm += mis;
-        const double lp = P.dbl_table[hc_dbl_index(qa, qb, mis, n1)];
-        if (lp > 0.0) { status = HC_WIN_VOID; return; }                  // :125-127
-        total = __dadd_rn(total, lp);                                     // :119
-        tl++;
+    } else {
+        for (uint32_t i = 0; i < w.L; i++) {
+            const u64 xa = w.xpos + i, xb = yp + i;
+            const uint32_t nA = (P.nmask[xa >> 5] >> (xa & 31)) & 1u, nB = (P.nmask[xb >> 5] >> (xb & 31)) & 1u;
+            if (nA | nB) continue;                                                    // :35-39,:122-124
+            const uint32_t a = (P.base2[xa >> 4] >> (2 * (xa & 15))) & 3u, b = (P.base2[xb >> 4] >> (2 * (xb & 15))) & 3u;
+            const uint32_t mis = a != b;
+            mm += mis;
+            const double lp = P.dbl_table[hc_dbl_index(P.qual[xa], P.qual[xb], mis, n1)];
+            if (lp > 0.0) { status = HC_WIN_VOID; return; }                          // :125-127
+            total = __dadd_rn(total, lp);                                             // :119
+            tl++;
+        }
     }
     if (tl == 0) { status = HC_WIN_EMPTY; return; }                      // :129-131
     mmc = mm;
@@ -872,7 +893,7 @@ cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaS
 }
 
 cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st) {
-    hc_exact_kernel<<<296, 128, 0, st>>>(P);
+    hc_exact_kernel<<<148 * 8, 128, 0, st>>>(P);
     return cudaGetLastError();
 }
 

@@ -56,7 +56,8 @@ FNO_READ = np.dtype([("id", "<u8"), ("len1", "<u4"), ("len2", "<u4")])
 FNO_SUBREAD = np.dtype([("index1", "<i4"), ("index2", "<i4"), ("startpos1", "<i4"), ("startpos2", "<i4")])
 FNO_OVERLAP = np.dtype([("id1", "<u8"), ("id2", "<u8"), ("pos1", "<i4"), ("pos2", "<i4"), ("perc", "<i4"), ("len1", "<i4"),
                         ("len2", "<i4"), ("ord", "u1"), ("ori1", "u1"), ("ori2", "u1"), ("type1", "u1"), ("type2", "u1"),
-                        ("reserved", "u1", (7,))])
+                        ("reserved", "u1", (3,)), ("perc2", "<i4")])
+FNO3_POS = np.dtype([("index1", "<i4"), ("index2", "<i4")])
 assert FNO_EDGE.itemsize == 32 and FNO_READ.itemsize == 16 and FNO_SUBREAD.itemsize == 16 and FNO_OVERLAP.itemsize == 48
 
 CLASS_DISCARD, CLASS_EDGE, CLASS_NONEDGE = 0, 1, 2
@@ -331,11 +332,23 @@ class FnoInput:
 
 def fno_lines(ov: np.ndarray) -> List[str]:
     """The reference's overlap line (src/FindNextOverlaps.cpp:122-148): PERC2 is the literal 0."""
-    return ["%d\t%d\t%d\t%d\t%s\t%s\t%s\t%d\t0\t%d\t%d\t%s\t%s" % (
-        o["id1"], o["id2"], o["pos1"], o["pos2"], chr(o["ord"]), chr(o["ori1"]), chr(o["ori2"]), o["perc"], o["len1"], o["len2"],
-        chr(o["type1"]), chr(o["type2"])) for o in ov]
+    return ["%d\t%d\t%d\t%d\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%s" % (
+        o["id1"], o["id2"], o["pos1"], o["pos2"], chr(o["ord"]), chr(o["ori1"]), chr(o["ori2"]), o["perc"], o["perc2"], o["len1"],
+        o["len2"], chr(o["type1"]), chr(o["type2"])) for o in ov]
 
 
 def fno_output_file(ov: np.ndarray) -> List[str]:
     """overlaps.txt = std::set<std::string> of the lines: unique, byte-lexicographic (:918,:946-948)."""
     return sorted(set(fno_lines(ov)), key=lambda s: s.encode())
+
+
+@dataclass
+class Fno3Input:
+    """Array form of what findNextOverlaps3 reads: per original read (in the reference's iteration
+    order) the new reads containing it and its position inside each (src/FindNextOverlaps3.cpp:26-76)."""
+
+    off: np.ndarray        # uint64 [n_originals + 1]
+    sr_idx: np.ndarray     # uint32
+    sr_pos: np.ndarray     # FNO3_POS
+    reads: np.ndarray      # FNO_READ (super-reads, then trivial reads)
+    no_inclusions: int

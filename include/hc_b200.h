@@ -237,14 +237,28 @@ typedef struct {
     uint64_t id1, id2;        /* ID1 / ID2 of the emitted overlap line                             */
     int32_t  pos1, pos2, perc, len1, len2;
     uint8_t  ord, ori1, ori2, type1, type2;   /* characters: '1'/'2'/'-', '+'/'-', 's'/'p'          */
-    uint8_t  reserved[7];
-} hc_fno_overlap;             /* 48 bytes; line = id1 id2 pos1 pos2 ord ori1 ori2 perc 0 len1 len2 type1 type2 */
+    uint8_t  reserved[3];
+    int32_t  perc2;           /* PERC2: always 0 from hc_fno1 (the reference prints a literal 0, :136), set by hc_fno3 */
+} hc_fno_overlap;             /* 48 bytes; line = id1 id2 pos1 pos2 ord ori1 ori2 perc perc2 len1 len2 type1 type2 */
 
 /* Derives the next-iteration overlaps on `device`.  `out` receives the successful derivations in
  * processing order (edge order, then super-read list order); the caller formats, sorts and
  * de-duplicates the lines like the reference's std::set<std::string> (:918,:946-948).
  * Returns HC_ERR_CAPACITY (required size in *n_out) if out_cap is too small. */
 int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_t n_edges,
+            hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out, int device);
+
+/* FindNextOverlaps3: SRBuilder::findNextOverlaps3 / nodeDictApproach / deduceOverlap,
+ * src/FindNextOverlaps3.cpp:20-406.  Two new reads that share an ORIGINAL read overlap; the overlap
+ * is deduced from the position of that original read inside both (OriginalIndex::index1/2,
+ * src/Types.h:84-91).  Originals are visited in the iteration order of the reference's
+ * std::unordered_map (:101) -- the host passes them in that order -- and per pair of new reads the
+ * first original wins (:116-121).  Output = discovery order, not sorted (:139-166); entries the
+ * reference drops (len1 <= 0, or perc == 100 under no_inclusions, :157-165) are not emitted. */
+typedef struct { int32_t index1, index2; } hc_fno3_pos;
+
+int hc_fno3(uint64_t n_originals, const uint64_t* off /* [n_originals+1] */, const uint32_t* sr_idx, const hc_fno3_pos* sr_pos,
+            uint64_t n_reads, const hc_fno_read* reads /* super-reads and trivial reads */, int no_inclusions,
             hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out, int device);
 
 int         hc_device_count(void);

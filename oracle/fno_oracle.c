@@ -197,3 +197,120 @@ int hco_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_t n_edges,
     if (n > out_cap) rc = HC_ERR_CAPACITY;
     return rc;
 }
+
+/* ---- FindNextOverlaps3 ------------------------------------------------------------------------------
+ * src/FindNextOverlaps3.cpp: nodeDictApproach :90-173 (first original wins per pair of new reads,
+ * :116-121; drop rules :157-165) and deduceOverlap :176-406.  Originals arrive in the iteration
+ * order of the reference's unordered_map (dumped by ref_driver). */
+static int perc_max(int l, int a, int b) {
+    float x = l / (float)a, y = l / (float)b;
+    float m = x > y ? x : y;
+    return (int)floor(m * 100);
+}
+
+static int deduce_overlap(const hc_fno_read* A, const hc_fno_read* B, const hc_fno3_pos* pa, const hc_fno3_pos* pb,
+                          hc_fno_overlap* o) {   /* returns 0 for the reference's "this overlap will be ignored" */
+    const int pA = A->len2 > 0, pB = B->len2 > 0;
+    memset(o, 0, sizeof(*o));
+    o->ori1 = '+'; o->ori2 = '+'; o->ord = '-';
+    if (!pA && !pB) {                                                       /* S-S :202-243 */
+        const int idx1 = pa->index1, idx2 = pb->index1, lenA = (int)A->len1, lenB = (int)B->len1;
+        if (idx1 - idx2 >= 0) {
+            o->id1 = A->id; o->id2 = B->id; o->pos1 = idx1 - idx2;
+            if (o->pos1 > lenA) return 0;
+            o->len1 = imin(lenA - o->pos1, lenB);
+        } else {
+            o->id1 = B->id; o->id2 = A->id; o->pos1 = idx2 - idx1;
+            if (o->pos1 > lenB) return 0;
+            o->len1 = imin(lenA, lenB - o->pos1);
+        }
+        o->perc = perc_max(o->len1, lenA, lenB);
+        o->type1 = 's'; o->type2 = 's';
+        return 1;
+    }
+    const int i1l = pa->index1, i1r = pa->index2, i2l = pb->index1, i2r = pb->index2;
+    if (pA && !pB) {                                                        /* P-S :244-287 */
+        const int lenA1 = (int)A->len1, lenA2 = (int)A->len2, lenB = (int)B->len1;
+        if (i1l - i2l >= 0) {
+            o->id1 = A->id; o->id2 = B->id; o->pos1 = i1l - i2l; o->len1 = lenA1 - o->pos1;
+            if (o->len1 <= 0) return 0;
+            o->type1 = 'p'; o->type2 = 's';
+        } else {
+            o->id1 = B->id; o->id2 = A->id; o->pos1 = i2l - i1l; o->len1 = imin(lenA1, lenB - o->pos1);
+            if (o->len1 <= 0) return 0;
+            o->type1 = 's'; o->type2 = 'p';
+        }
+        o->perc = (int)floor(o->len1 / (float)lenA1 * 100);
+        o->pos2 = i2r - i1r;
+        o->len2 = imin(lenA2, lenB - o->pos2);
+        if (o->len2 <= 0 || o->pos2 < 0) return 0;
+        o->perc2 = (int)floor(o->len2 / (float)lenA2 * 100);
+        return 1;
+    }
+    if (!pA && pB) {                                                        /* S-P :288-331 */
+        const int lenA = (int)A->len1, lenB1 = (int)B->len1, lenB2 = (int)B->len2;
+        if (i1l - i2l >= 0) {
+            o->id1 = A->id; o->id2 = B->id; o->pos1 = i1l - i2l; o->len1 = imin(lenB1, lenA - o->pos1);
+            if (o->len1 <= 0) return 0;
+            o->type1 = 's'; o->type2 = 'p';
+        } else {
+            o->id1 = B->id; o->id2 = A->id; o->pos1 = i2l - i1l; o->len1 = lenB1 - o->pos1;
+            if (o->len1 <= 0) return 0;
+            o->type1 = 'p'; o->type2 = 's';
+        }
+        o->perc = (int)floor(o->len1 / (float)lenB1 * 100);
+        o->pos2 = i1r - i2r;
+        o->len2 = imin(lenB2, lenA - o->pos2);
+        if (o->len2 <= 0 || o->pos2 < 0) return 0;
+        o->perc2 = (int)floor(o->len2 / (float)lenB2 * 100);
+        return 1;
+    }
+    {                                                                       /* P-P :332-401 */
+        const int lenA = (int)A->len1, lenB = (int)B->len1, lenC = (int)A->len2, lenD = (int)B->len2;
+        int front, back;
+        if (i1l - i2l >= 0) { o->id1 = A->id; o->id2 = B->id; o->pos1 = i1l - i2l; o->len1 = imin(lenA - o->pos1, lenB); front = 1; }
+        else { o->id1 = B->id; o->id2 = A->id; o->pos1 = i2l - i1l; o->len1 = imin(lenA, lenB - o->pos1); front = 0; }
+        if (i1r - i2r >= 0) { o->pos2 = i1r - i2r; o->len2 = imin(lenC - o->pos2, lenD); back = 1; }
+        else { o->pos2 = i2r - i1r; o->len2 = imin(lenC, lenD - o->pos2); back = 0; }
+        if (o->len1 <= 0 || o->len2 <= 0) return 0;
+        o->perc = perc_max(o->len1, lenA, lenB);
+        o->perc2 = perc_max(o->len2, lenC, lenD);
+        o->ord = (front == back) ? '1' : '2';
+        o->type1 = 'p'; o->type2 = 'p';
+        return 1;
+    }
+}
+
+int hco_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t* sr_idx, const hc_fno3_pos* sr_pos, uint64_t n_reads,
+             const hc_fno_read* reads, int no_inclusions, hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out) {
+    uint64_t attempts = 0;
+    for (uint64_t k = 0; k < n_originals; k++) { uint64_t c = off[k + 1] - off[k]; attempts += c * (c - 1) / 2; }
+    keyset ks;
+    ks.cap = 64;
+    while (ks.cap < 2 * attempts + 2) ks.cap <<= 1;
+    ks.k = (uint64_t*)malloc(ks.cap * sizeof(uint64_t));
+    if (!ks.k) return HC_ERR_NOMEM;
+    memset(ks.k, 0xff, ks.cap * sizeof(uint64_t));
+    uint64_t n = 0;
+    (void)n_reads;
+    for (uint64_t k = 0; k < n_originals; k++) {
+        for (uint64_t i = off[k]; i < off[k + 1]; i++) {
+            for (uint64_t j = i + 1; j < off[k + 1]; j++) {
+                const hc_fno_read* A = &reads[sr_idx[i]];
+                const hc_fno_read* B = &reads[sr_idx[j]];
+                const uint64_t lo = A->id < B->id ? A->id : B->id, hi = A->id < B->id ? B->id : A->id;
+                if (keyset_test_and_set(&ks, (lo << 32) | hi)) continue;                      /* :116-121 */
+                hc_fno_overlap o;
+                if (!deduce_overlap(A, B, &sr_pos[i], &sr_pos[j], &o)) continue;             /* len1 == 0 -> not written, :160 */
+                const unsigned perc = o.perc2 > 0 ? (unsigned)(0.5 * (o.perc + o.perc2)) : (unsigned)o.perc;   /* Overlap::get_perc */
+                if (no_inclusions && perc == 100) continue;                                  /* :157-159 */
+                if (!(o.len1 > 0)) continue;
+                if (n < out_cap) out[n] = o;
+                n++;
+            }
+        }
+    }
+    free(ks.k);
+    *n_out = n;
+    return n > out_cap ? HC_ERR_CAPACITY : 0;
+}

@@ -71,6 +71,28 @@ def run_fno_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> Non
           (name, len(fi.visited), len(fi.superread), int((fi.superread["len2"] > 0).sum()), len(fi.edges), len(ref)))
 
 
+def run_fno3_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> None:
+    """Clique iteration + the reference's own findNextOverlaps3(): its inputs (array form, reference iteration order) and overlaps.txt."""
+    import subprocess
+
+    d = tempfile.mkdtemp(prefix="hc_golden_fno3_")
+    F.write_fastq_set(rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    F.write_overlaps(d + "/ov.txt", cands, rs.ids)
+    cmd = [O.REF_DRIVER, "--overlaps", d + "/ov.txt", "--run", "--merge-fno3", d + "/fno3_in.txt", "--cliques", "1",
+           "--remove_branches", "0"] + args
+    if rs.n_single:
+        cmd += ["--singles", d + "/s.fastq"]
+    if rs.n_reads > rs.n_single:
+        cmd += ["--paired1", d + "/p1.fastq", "--paired2", d + "/p2.fastq"]
+    subprocess.run(cmd, cwd=d, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    fi = O.parse_fno3_dump(d + "/fno3_in.txt")
+    with open(d + "/overlaps.txt") as f:
+        ref = f.read().split("\n")[:-1]
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), off=fi.off, sr_idx=fi.sr_idx, sr_pos=fi.sr_pos, reads=fi.reads,
+                        flags=np.array([fi.no_inclusions]), ref_lines=np.array(ref))
+    print("%-28s originals=%d reads=%d -> %d overlap lines" % (name, len(fi.off) - 1, len(fi.reads), len(ref)))
+
+
 def main() -> None:
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -112,6 +134,9 @@ def main() -> None:
         cx = W.geometry_candidates(sx, 6000, seed=seed + 1, junk_fraction=0.02, min_ov=40)
         run_fno_case("fno1_synth_paired_%d" % k, sx.rs, cx, ["--edge_threshold", "0.9", "--min_overlap_len", "80", "--keep_singletons", "0"]
                      + (["--no_inclusion_overlaps", "1"] if k == 2 else []))
+        if k != 1:
+            run_fno3_case("fno3_synth_cliques_%d" % k, sx.rs, cx, ["--edge_threshold", "0.9", "--min_overlap_len", "80", "--keep_singletons", "0"]
+                          + (["--no_inclusion_overlaps", "1"] if k == 2 else []))
 
 if __name__ == "__main__":
     main()

@@ -230,3 +230,53 @@ def fno1(fi) -> np.ndarray:
         if rc != -5:
             raise RuntimeError("hco_fno1 failed with %d" % rc)
         cap = int(n.value)
+
+
+# ---- FindNextOverlaps3 ------------------------------------------------------------------------------------
+def parse_fno3_dump(path: str):
+    from haploconduct_b200 import formats as F
+
+    srs, lists = [], []
+    ni = 0
+    with open(path) as f:
+        for line in f:
+            t = line.rstrip("\n").split("\t")
+            if t[0] == "P":
+                ni = int(t[1])
+            elif t[0] == "S":
+                srs.append((int(t[2]), int(t[3]), int(t[4])))
+            elif t[0] == "O":
+                lists.append([tuple(int(x) for x in s.split(":")) for s in t[2:]])
+    off = np.zeros(len(lists) + 1, dtype=np.uint64)
+    idx, pos = [], []
+    for k, l in enumerate(lists):
+        for s in l:
+            idx.append(s[0])
+            pos.append((s[1], s[2]))
+        off[k + 1] = len(idx)
+    reads = np.zeros(len(srs), dtype=F.FNO_READ)
+    if srs:
+        reads["id"], reads["len1"], reads["len2"] = zip(*srs)
+    return F.Fno3Input(off=off, sr_idx=np.array(idx, dtype=np.uint32), sr_pos=np.array(pos, dtype=F.FNO3_POS), reads=reads,
+                       no_inclusions=ni)
+
+
+def fno3(fi) -> np.ndarray:
+    from haploconduct_b200 import formats as F
+
+    L = lib()
+    L.hco_fno3.restype = ctypes.c_int
+    L.hco_fno3.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
+                           ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+    off, idx, pos, reads = (np.ascontiguousarray(a) for a in (fi.off, fi.sr_idx, fi.sr_pos, fi.reads))
+    cap = 1024
+    while True:
+        out = np.zeros(cap, dtype=F.FNO_OVERLAP)
+        n = ctypes.c_uint64(0)
+        rc = L.hco_fno3(len(off) - 1, off.ctypes.data, idx.ctypes.data, pos.ctypes.data, len(reads), reads.ctypes.data,
+                        fi.no_inclusions, out.ctypes.data, cap, ctypes.byref(n))
+        if rc == 0:
+            return out[: n.value]
+        if rc != -5:
+            raise RuntimeError("hco_fno3 failed with %d" % rc)
+        cap = int(n.value)

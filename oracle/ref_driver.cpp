@@ -23,6 +23,9 @@
 //                    state, super-reads with sub-read indices, and the edge stream in the order the
 //                    reference processes it -- then run the reference's findNextOverlaps() itself,
 //                    which writes overlaps.txt into the cwd.
+//   --merge-fno3 F   same iteration, but for SRBuilder::findNextOverlaps3 (src/FindNextOverlaps3.cpp:20-173):
+//                    dumps the original-read -> super-read lists in the iteration order of the
+//                    reference's std::unordered_map, then runs findNextOverlaps3() itself.
 //
 // compute_overlap / adj_out are private in the reference headers; the dump TU sees them
 // through "#define private public" (class layout is unchanged, it links against the
@@ -96,6 +99,7 @@ int main(int argc, char** argv) {
     ps.output_dir = "";
 
     std::string dump_cands, dump_graph, merge_fno1;
+    bool fno3 = false, use_cliques = false;
     ps.keep_singletons = 0;
     ps.remove_trans = 1;
     ps.remove_branches = true;
@@ -130,6 +134,9 @@ int main(int argc, char** argv) {
         else if (a == "--dump-cands") dump_cands = need("--dump-cands");
         else if (a == "--dump-graph") dump_graph = need("--dump-graph");
         else if (a == "--merge-fno1") merge_fno1 = need("--merge-fno1");
+        else if (a == "--merge-fno3") { merge_fno1 = need("--merge-fno3"); fno3 = true; }
+        else if (a == "--cliques") use_cliques = std::atoi(need("--cliques")) != 0;
+        else if (a == "--min_clique_size") ps.min_clique_size = std::atoi(need("--min_clique_size"));
         else if (a == "--keep_singletons") ps.keep_singletons = std::atoi(need("--keep_singletons"));
         else if (a == "--remove_branches") ps.remove_branches = std::atoi(need("--remove_branches")) != 0;
         else if (a == "--remove_trans") ps.remove_trans = std::atoi(need("--remove_trans"));
@@ -290,9 +297,87 @@ int main(int argc, char** argv) {
         if (ps.remove_branches) graph->removeBranches();
         graph->sortEdges();
         graph->cycleRemovalHeuristic(true);
+        if (fno3) ps.fno = 3;
         std::shared_ptr<SRBuilder> srb(new SRBuilder(fastq, graph, ps));
         graph->sortEdges();
-        srb->mergeAlongEdges();                                           // :441
+        if (use_cliques) {
+            // maximal cliques of the undirected overlap graph (the reference shells out to quick-cliques,
+            // src/ViralQuasispecies.cpp:400; here a plain Bron-Kerbosch with pivoting writes cliques.txt)
+            const size_t Vn = graph->getVertexCount();
+            std::vector<std::set<node_id_t>> nb(Vn);
+            for (size_t v = 0; v < Vn; v++) for (auto& e : graph->adj_out[v]) { nb[v].insert(e.get_vertex(2)); nb[e.get_vertex(2)].insert(v); }
+            std::ofstream cf("cliques.txt");
+            std::function<void(std::set<node_id_t>, std::set<node_id_t>, std::set<node_id_t>)> bk =
+                [&](std::set<node_id_t> R, std::set<node_id_t> Pn, std::set<node_id_t> X) {
+                    if (Pn.empty() && X.empty()) {
+                        if (R.size() >= 2) { for (auto v : R) cf << v << " "; cf << "\n"; }
+                        return;
+                    }
+                    node_id_t pivot = Pn.empty() ? *X.begin() : *Pn.begin();
+                    std::vector<node_id_t> cand;
+                    for (auto v : Pn) if (!nb[pivot].count(v)) cand.push_back(v);
+                    for (auto v : cand) {
+                        std::set<node_id_t> R2 = R, P2, X2;
+                        R2.insert(v);
+                        for (auto w : Pn) if (nb[v].count(w)) P2.insert(w);
+                        for (auto w : X) if (nb[v].count(w)) X2.insert(w);
+                        bk(R2, P2, X2);
+                        Pn.erase(v);
+                        X.insert(v);
+                    }
+                };
+            std::set<node_id_t> all;
+            for (size_t v = 0; v < Vn; v++) if (!nb[v].empty()) all.insert(v);
+            bk(std::set<node_id_t>(), all, std::set<node_id_t>());
+            cf.close();
+            srb->cliquesToSuperreads();                                   // :422
+        } else {
+            srb->mergeAlongEdges();                                       // :441
+        }
+        if (fno3) {
+            // what findNextOverlaps3 builds (src/FindNextOverlaps3.cpp:26-76), with the same container
+            // types and the same insertion sequence, hence the same iteration order
+            FILE* fo = std::fopen(merge_fno1.c_str(), "w");
+            if (!fo) { std::fprintf(stderr, "cannot write %s\n", merge_fno1.c_str()); return 1; }
+            std::fprintf(fo, "P\t%d\n", (int)ps.no_inclusions);
+            std::vector<Read*> srs;
+            std::map<Read*, size_t> sr_index;
+            for (auto& r : srb->single_SR_vec) { sr_index[&r] = srs.size(); srs.push_back(&r); }
+            for (auto& r : srb->paired_SR_vec) { sr_index[&r] = srs.size(); srs.push_back(&r); }
+            for (auto& r : srb->trivial_SR_vec) { sr_index[&r] = srs.size(); srs.push_back(&r); }
+            for (size_t k = 0; k < srs.size(); k++) {
+                Read* r = srs[k];
+                unsigned long l1 = r->is_paired() ? r->get_seq(1).size() : r->get_seq(0).size();
+                unsigned long l2 = r->is_paired() ? r->get_seq(2).size() : 0;
+                std::fprintf(fo, "S\t%lu\t%lu\t%lu\t%lu\n", (unsigned long)k, r->get_read_id(), l1, l2);
+            }
+            std::unordered_map<read_id_t, node_id_t> original_to_index;
+            std::vector<std::vector<Read*>> lists;
+            for (Read* rp : srs) {
+                std::unordered_map<read_id_t, OriginalIndex> originals = rp->get_original_reads();
+                for (auto it : originals) {
+                    auto ex = original_to_index.find(it.first);
+                    if (ex == original_to_index.end()) {
+                        original_to_index.insert(std::make_pair(it.first, (node_id_t)lists.size()));
+                        lists.push_back(std::vector<Read*>(1, rp));
+                    } else lists[ex->second].push_back(rp);
+                }
+            }
+            std::unordered_map<read_id_t, node_id_t> by_value(original_to_index);   // nodeDictApproach takes it by value (:90)
+            for (auto it : by_value) {
+                std::fprintf(fo, "O\t%lu", it.first);
+                for (Read* rp : lists[it.second]) {
+                    OriginalIndex oi = rp->get_original_reads().at(it.first);
+                    std::fprintf(fo, "\t%lu:%ld:%ld", (unsigned long)sr_index[rp], oi.index1, oi.index2);
+                }
+                std::fprintf(fo, "\n");
+            }
+            std::fclose(fo);
+            srb->findNextOverlaps3();                                     // the reference itself -> overlaps.txt
+            std::printf("{\"fno3_lines\": %lu}\n", (unsigned long)srb->next_overlaps_count);
+            merge_fno1.clear();
+        }
+        if (!merge_fno1.empty()) {
         // ---- dump what findNextOverlaps reads
         FILE* fo = std::fopen(merge_fno1.c_str(), "w");
         if (!fo) { std::fprintf(stderr, "cannot write %s\n", merge_fno1.c_str()); return 1; }
@@ -375,6 +460,7 @@ int main(int argc, char** argv) {
         }
         std::fclose(fo);
         fno_lines = srb->findNextOverlaps();                             // the reference itself -> overlaps.txt
+        }
     }
     std::printf("{\"fno1_lines\": %lu}\n", fno_lines);
     std::printf("{\"reads_single\": %u, \"reads_paired\": %u, \"threads\": %u, \"lines\": %lu, \"scored\": %lu, "

@@ -5,7 +5,7 @@ import pytest
 
 from haploconduct_b200 import formats as F
 from oracle import oracle as O
-from util import fno_golden_names, load_fno_golden, random_fno_input
+from util import fno3_golden_names, fno_golden_names, load_fno3_golden, load_fno_golden, random_fno3_input, random_fno_input
 
 
 @pytest.mark.parametrize("name", fno_golden_names())
@@ -39,3 +39,18 @@ def test_fno1_first_found_wins_is_order_dependent():
     fi.edges = fi.edges[::-1].copy()
     b = F.fno_output_file(O.fno1(fi))
     assert a != b and len(a) > 100
+
+
+@pytest.mark.parametrize("name", fno3_golden_names())
+def test_fno3_oracle_reproduces_reference_file(name):
+    """findNextOverlaps3 writes its lines in discovery order (no sorting): compare as a sequence."""
+    fi, ref = load_fno3_golden(name)
+    assert F.fno_lines(O.fno3(fi)) == ref
+
+
+def test_fno3_golden_covers_type_cases():
+    seen = set()
+    for name in fno3_golden_names():
+        _, ref = load_fno3_golden(name)
+        seen |= {(l.split("\t")[11], l.split("\t")[12], l.split("\t")[4]) for l in ref}
+    assert {("s", "s", "-"), ("s", "p", "-"), ("p", "s", "-"), ("p", "p", "1"), ("p", "p", "2")} <= seen

@@ -5,7 +5,7 @@ import pytest
 
 from haploconduct_b200 import capi, formats as F
 from oracle import oracle as O
-from util import fno_golden_names, load_fno_golden, random_fno_input
+from util import fno3_golden_names, fno_golden_names, load_fno3_golden, load_fno_golden, random_fno3_input, random_fno_input
 
 pytestmark = pytest.mark.gpu
 
@@ -34,3 +34,19 @@ def test_fno1_empty_and_bad_input(built_lib):
     fi.edges["u"][3] = 10 ** 6
     with pytest.raises(capi.HcError):
         capi.fno1(fi)
+
+
+@pytest.mark.parametrize("name", fno3_golden_names())
+def test_fno3_reference_file(built_lib, name):
+    fi, ref = load_fno3_golden(name)
+    ov = capi.fno3(fi)
+    assert F.fno_lines(ov) == ref                       # discovery order, like the reference's overlaps.txt
+    assert ov.tobytes() == O.fno3(fi).tobytes()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fno3_random_dense_inputs(built_lib, seed):
+    fi = random_fno3_input(seed, n_originals=30000, n_reads=2000)
+    a, b = capi.fno3(fi), O.fno3(fi)
+    assert len(a) == len(b) and len(a) > 1000
+    assert a.tobytes() == b.tobytes()

@@ -35,7 +35,7 @@ class Golden:
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("fno1_"))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("fno"))
 
 
 def fno_golden_names():
@@ -49,6 +49,34 @@ def load_fno_golden(name):
                     sr_sub=z["sr_sub"], superread=z["superread"], resolve_orientations=int(z["flags"][0]),
                     no_inclusions=int(z["flags"][1]), edges=z["edges"])
     return fi, [str(x) for x in z["ref_lines"]]
+
+
+def fno3_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "fno3_*.npz")))
+
+
+def load_fno3_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    fi = F.Fno3Input(off=z["off"], sr_idx=z["sr_idx"], sr_pos=z["sr_pos"], reads=z["reads"], no_inclusions=int(z["flags"][0]))
+    return fi, [str(x) for x in z["ref_lines"]]
+
+
+def random_fno3_input(seed, n_originals=2000, n_reads=600, paired_fraction=0.4):
+    rng = np.random.RandomState(seed)
+    reads = np.zeros(n_reads, dtype=F.FNO_READ)
+    reads["id"] = rng.permutation(n_reads)
+    reads["len1"] = rng.randint(80, 600, size=n_reads)
+    reads["len2"] = np.where(rng.random_sample(n_reads) < paired_fraction, rng.randint(80, 600, size=n_reads), 0)
+    off = np.zeros(n_originals + 1, dtype=np.uint64)
+    idx, pos = [], []
+    for k in range(n_originals):
+        c = int(rng.choice([1, 1, 2, 2, 3, 4, 6, 9]))
+        for s in rng.choice(n_reads, size=c, replace=False):
+            idx.append(int(s))
+            pos.append((int(rng.randint(-20, 500)), int(rng.randint(-20, 500))))
+        off[k + 1] = len(idx)
+    return F.Fno3Input(off=off, sr_idx=np.array(idx, dtype=np.uint32), sr_pos=np.array(pos, dtype=F.FNO3_POS), reads=reads,
+                       no_inclusions=int(seed % 2))
 
 
 def random_fno_input(seed, n_vertices=300, n_sr=120, n_edges=4000, paired_fraction=0.4):
