@@ -278,8 +278,15 @@ def main() -> None:
     # ---- e2e through the host-buffer entry point
     e2e = None
     if not args.no_e2e:
-        h_cand = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
-        h_cand.copy_(rec)
+        # the host-facing call on the 16-byte compact records (idx1, idx2, pos1|ori|ord, pos2)
+        r32 = rec.view(torch.int32).reshape(-1, 8)
+        ordc = torch.where(((r32[:, 6] >> 16) & 0xff) == ord("1"), 1, 2)
+        cc = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        cc[:, 0] = r32[:, 0]; cc[:, 1] = r32[:, 1]; cc[:, 3] = r32[:, 3]
+        cc[:, 2] = r32[:, 2] | (3 << 28) | (ordc << 30).to(torch.int32)      # POS1 | ORI1 '+' | ORI2 '+' | ORD
+        h_cand = torch.empty((n, 4), dtype=torch.int32, pin_memory=True)
+        h_cand.copy_(cc)
+        del cc
         ne, nn = int(counts[0]), int(counts[1])
         h_edges = torch.empty((max(ne, 1) + 1024, 48), dtype=torch.uint8, pin_memory=True)
         h_nonedge = torch.empty(max(nn, 1) + 1024, dtype=torch.int64, pin_memory=True)
@@ -288,7 +295,7 @@ def main() -> None:
         c_ne, c_nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
 
         def e2e_step():
-            rc = L.hc_score_batch(store.handle, params.ctypes.data, h_cand.data_ptr(), n, None, h_edges.data_ptr(),
+            rc = L.hc_score_batch_compact(store.handle, params.ctypes.data, h_cand.data_ptr(), n, None, h_edges.data_ptr(),
                                   h_edges.shape[0], ctypes.byref(c_ne), h_nonedge.data_ptr(), h_nonedge.shape[0],
                                   ctypes.byref(c_nn), None)
             if rc != 0:
@@ -303,7 +310,7 @@ def main() -> None:
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert c_ne.value == ne and c_nn.value == nn
-        e2e = (e2e_ms, n * 32, ne * 48 + nn * 8 + 32)
+        e2e = (e2e_ms, n * 16, ne * 48 + nn * 8 + 64)
 
     ms_step = ms_total / args.steps
     tvals = torch.tensor([ms_step, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)

@@ -55,15 +55,20 @@ struct DevCtx {
     uint32_t* flagged = nullptr;
     uint32_t* blockcounts = nullptr;
     unsigned long long* counters = nullptr;
-    // staging for the host-buffer path
-    uint64_t st_cap = 0;
-    hc_candidate* d_cand = nullptr;
-    hc_edge* d_edges = nullptr;
-    uint64_t* d_nonedge = nullptr;
+    // host-buffer path: two chunk slots (copy-in of chunk k+1 overlaps the kernels of chunk k), device-side
+    // accumulation of the ordered outputs, running totals on the device
+    uint64_t slot_cap = 0;                 // candidates per slot
+    void* d_cand[2] = {nullptr, nullptr};
     uint64_t pc_cap = 0;
-    hc_result* d_per_cand = nullptr;
+    hc_result* d_per_cand[2] = {nullptr, nullptr};
+    uint64_t acc_e_cap = 0, acc_n_cap = 0;
+    hc_edge* d_acc_edges = nullptr;
+    uint64_t* d_acc_nonedge = nullptr;
+    unsigned long long* d_run = nullptr;   // {edges, non-edges} emitted so far in this call
+    unsigned long long* h_cnt = nullptr;   // pinned: [2][HC_CNT_N] counter snapshots per slot
     uint64_t* d_counts = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_copy = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     hc_launch_cfg cfg{};
 };
@@ -94,9 +99,18 @@ void free_ctx(DevCtx& d) {
     cudaFree(d.pk); cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc);
     cudaFree(d.fx_table); cudaFree(d.dbl_table);
     cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts); cudaFree(d.counters);
-    cudaFree(d.d_cand); cudaFree(d.d_edges); cudaFree(d.d_nonedge); cudaFree(d.d_per_cand); cudaFree(d.d_counts);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(d.d_cand[k]); cudaFree(d.d_per_cand[k]);
+        if (d.ev_in[k]) cudaEventDestroy(d.ev_in[k]);
+        if (d.ev_done[k]) cudaEventDestroy(d.ev_done[k]);
+        if (d.ev_out[k]) cudaEventDestroy(d.ev_out[k]);
+    }
+    cudaFree(d.d_acc_edges); cudaFree(d.d_acc_nonedge); cudaFree(d.d_run); cudaFree(d.d_counts);
+    if (d.h_cnt) cudaFreeHost(d.h_cnt);
     for (int k = 0; k < 6; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
     if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.s_copy) cudaStreamDestroy(d.s_copy);
+    if (d.s_out) cudaStreamDestroy(d.s_out);
     d = DevCtx();
 }
 
@@ -157,9 +171,10 @@ DevCtx* find_ctx(hc_store* s, int device) {
 }
 
 // Enqueue the whole scoring pipeline for one shard on (d, st).
-int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, const hc_candidate* d_cand, uint64_t n,
+int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, const void* d_cand, int compact, uint64_t n,
                   hc_result* d_per_cand, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge, uint64_t nonedge_cap,
-                  uint64_t* d_counts, uint64_t cand_offset, cudaEvent_t k0, cudaEvent_t k1, uint32_t* launches) {
+                  uint64_t* d_counts, uint64_t cand_offset, unsigned long long* d_run, cudaEvent_t k0, cudaEvent_t k1,
+                  uint32_t* launches) {
     if (n > 0xffffffffull) return fail(HC_ERR_ARG, "more than 2^32-1 candidates in one device batch");
     int rc = ensure_tables(s, d, p->mismatch, st);
     if (rc != HC_OK) return rc;
@@ -172,7 +187,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     P.pk = d.pk; P.packed = s->packed ? 1u : 0u;
     P.n_reads = (uint32_t)s->n_reads; P.n_single = (uint32_t)s->n_single;
     P.fx_table = d.fx_table; P.dbl_table = d.dbl_table; P.ncodes = (uint32_t)s->ncodes; P.has_void = d.has_void ? 1u : 0u;
-    P.cand = d_cand; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
+    P.cand = d_cand; P.cand_compact = compact ? 1u : 0u; P.run = d_run; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
     P.counters = d.counters;
     P.t_edge = hc_tables_exp_threshold(p->edge_threshold, &mono);
     if (!mono) return fail(HC_ERR_ARG, "host exp() is not monotone around edge_threshold");
@@ -205,19 +220,26 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
         CU(hc_launch_exact(P, st));
         nl += 2;
     }
-    CU(hc_launch_compact(P, d_edges, edges_cap, d_nonedge, nonedge_cap, d.blockcounts, cand_offset, st));
-    nl += n > 0 ? 3 : 1;
+    CU(hc_launch_compact(P, d_edges, edges_cap, d_nonedge, nonedge_cap, d.blockcounts, cand_offset, d_run, st));
+    nl += (n > 0 ? 3 : 1) + (d_run ? 1 : 0);
     if (k1) CU(cudaEventRecord(k1, st));
-    // {n_edges, n_nonedges, n_exact} are contiguous in the counter block; [3] = invalid candidates
-    CU(cudaMemcpyAsync(d_counts, d.counters + HC_CNT_EDGES, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(d_counts + 3, d.counters + HC_CNT_ERRORS, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    if (d_counts) {   // {n_edges, n_nonedges, n_exact} are contiguous in the counter block; [3] = invalid candidates
+        CU(cudaMemcpyAsync(d_counts, d.counters + HC_CNT_EDGES, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(d_counts + 3, d.counters + HC_CNT_ERRORS, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    }
     if (launches) *launches = nl;
     return HC_OK;
 }
 
+int add_stats(DevCtx& d, const unsigned long long* h, uint64_t n, hc_batch_stats* stats, cudaEvent_t k0, cudaEvent_t k1);
+
 int read_stats(DevCtx& d, uint64_t n, hc_batch_stats* stats, cudaEvent_t k0, cudaEvent_t k1) {
     unsigned long long h[HC_CNT_N];
     CU(cudaMemcpy(h, d.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    return add_stats(d, h, n, stats, k0, k1);
+}
+
+int add_stats(DevCtx& d, const unsigned long long* h, uint64_t n, hc_batch_stats* stats, cudaEvent_t k0, cudaEvent_t k1) {
     if (stats) {
         stats->n_candidates += n;
         stats->n_edges += h[HC_CNT_EDGES];
@@ -426,6 +448,15 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
             e = hc_score_occupancy((uint32_t)s->ncodes, d.sm_count, d.smem_per_sm, &d.cfg);
         }
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.s_copy, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.s_out, cudaStreamNonBlocking);
+        for (int j = 0; j < 2 && e == cudaSuccess; j++) {
+            e = cudaEventCreateWithFlags(&d.ev_in[j], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_done[j], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_out[j], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&d.d_run, 2 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost(&d.h_cnt, 2 * HC_CNT_N * sizeof(unsigned long long));
         for (int j = 0; j < 6 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
         uint8_t** qplane = packed ? &d.pk : &d.qual;
         if (e == cudaSuccess) e = cudaMalloc(qplane, total + 64);
@@ -459,8 +490,8 @@ int hc_score_batch_device(hc_store* s, int device, void* stream, const hc_params
     CU(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t nl = 0;
-    int rc = enqueue_batch(s, *d, st, p, d_cand, n, d_per_cand, d_edges, edges_cap, d_nonedge_idx, nonedge_cap, d_counts, 0,
-                           stats ? d->ev[0] : nullptr, stats ? d->ev[1] : nullptr, &nl);
+    int rc = enqueue_batch(s, *d, st, p, d_cand, 0, n, d_per_cand, d_edges, edges_cap, d_nonedge_idx, nonedge_cap, d_counts, 0,
+                           nullptr, stats ? d->ev[0] : nullptr, stats ? d->ev[1] : nullptr, &nl);
     if (rc != HC_OK) return rc;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -472,73 +503,140 @@ int hc_score_batch_device(hc_store* s, int device, void* stream, const hc_params
     return rc;
 }
 
-int hc_score_batch(hc_store* s, const hc_params* p, const hc_candidate* cand, uint64_t n, hc_result* per_cand,
-                   hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
-                   uint64_t* n_nonedges, hc_batch_stats* stats) {
+// Host-buffer path.  The batch is cut into contiguous per-device shards (rank order = input order) and
+// every shard is streamed through its device in chunks: H2D of chunk k+1 (s_copy), kernels of chunk k
+// (stream) and D2H of what chunk k-1 produced (s_out) overlap.  Outputs are compacted on the device
+// behind the outputs of the earlier chunks (running totals stay on the device), so the host sees
+// one ordered list per device.
+static int score_host(hc_store* s, const hc_params* p, const void* cand, int compact, uint64_t n, hc_result* per_cand,
+                      hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
+                      uint64_t* n_nonedges, hc_batch_stats* stats) {
     if (!s || !p || !n_edges || !n_nonedges || (n && !cand)) return fail(HC_ERR_ARG, "hc_score_batch: NULL argument");
     if (stats) memset(stats, 0, sizeof(*stats));
     *n_edges = 0;
     *n_nonedges = 0;
+    const size_t rec = compact ? sizeof(hc_candidate_compact) : sizeof(hc_candidate);
     const int G = (int)s->devs.size();
+    uint64_t chunk = 16ull << 20;
+    if (const char* e = getenv("HC_HOST_CHUNK")) { const uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }   // tests
     std::vector<uint64_t> lo(G + 1);
     for (int g = 0; g <= G; g++) lo[g] = n * (uint64_t)g / (uint64_t)G;   // contiguous index ranges
     uint32_t launches = 0;
-    // phase 1: enqueue everything on every device
-    for (int g = 0; g < G; g++) {
-        DevCtx& d = s->devs[g];
-        const uint64_t m = lo[g + 1] - lo[g];
-        CU(cudaSetDevice(d.device));
-        if (m > d.st_cap) {
-            cudaFree(d.d_cand); cudaFree(d.d_edges); cudaFree(d.d_nonedge);
-            d.d_cand = nullptr; d.d_edges = nullptr; d.d_nonedge = nullptr; d.st_cap = 0;
-            CU(cudaMalloc(&d.d_cand, m * sizeof(hc_candidate)));
-            CU(cudaMalloc(&d.d_edges, m * sizeof(hc_edge)));
-            CU(cudaMalloc(&d.d_nonedge, m * sizeof(uint64_t)));
-            d.st_cap = m;
-        }
-        if (per_cand && m > d.pc_cap) {
-            cudaFree(d.d_per_cand);
-            d.d_per_cand = nullptr; d.pc_cap = 0;
-            CU(cudaMalloc(&d.d_per_cand, m * sizeof(hc_result)));
-            d.pc_cap = m;
-        }
-        CU(cudaEventRecord(d.ev[2], d.stream));
-        if (m) CU(cudaMemcpyAsync(d.d_cand, cand + lo[g], m * sizeof(hc_candidate), cudaMemcpyHostToDevice, d.stream));
-        uint32_t nl = 0;
-        int rc = enqueue_batch(s, d, d.stream, p, d.d_cand, m, per_cand ? d.d_per_cand : nullptr, d.d_edges, d.st_cap,
-                               d.d_nonedge, d.st_cap, d.d_counts, lo[g], d.ev[0], d.ev[1], &nl);
-        if (rc != HC_OK) return rc;
-        launches += nl;
-        if (per_cand && m)
-            CU(cudaMemcpyAsync(per_cand + lo[g], d.d_per_cand, m * sizeof(hc_result), cudaMemcpyDeviceToHost, d.stream));
-    }
-    // phase 2: gather in rank order = input order
-    uint64_t te = 0, tn = 0;
+    std::vector<uint64_t> dev_e(G, 0), dev_n(G, 0);
     int result = HC_OK;
+    // ---- allocate / reset
     for (int g = 0; g < G; g++) {
         DevCtx& d = s->devs[g];
         const uint64_t m = lo[g + 1] - lo[g];
+        const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(m, 1), chunk);
         CU(cudaSetDevice(d.device));
-        uint64_t hc[4];
-        CU(cudaMemcpyAsync(hc, d.d_counts, sizeof(hc), cudaMemcpyDeviceToHost, d.stream));
-        CU(cudaStreamSynchronize(d.stream));
-        int rc = read_stats(d, m, stats, d.ev[0], d.ev[1]);
-        if (rc != HC_OK) result = rc;
-        if (te + hc[0] <= edges_cap && hc[0])
-            CU(cudaMemcpyAsync(edges + te, d.d_edges, hc[0] * sizeof(hc_edge), cudaMemcpyDeviceToHost, d.stream));
-        if (tn + hc[1] <= nonedge_cap && hc[1])
-            CU(cudaMemcpyAsync(nonedge_idx + tn, d.d_nonedge, hc[1] * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
-        CU(cudaEventRecord(d.ev[3], d.stream));
-        te += hc[0];
-        tn += hc[1];
+        if (cap > d.slot_cap) {
+            for (int k = 0; k < 2; k++) { cudaFree(d.d_cand[k]); d.d_cand[k] = nullptr; }
+            d.slot_cap = 0;
+            for (int k = 0; k < 2; k++) CU(cudaMalloc(&d.d_cand[k], cap * sizeof(hc_candidate)));
+            d.slot_cap = cap;
+        }
+        if (per_cand && cap > d.pc_cap) {
+            for (int k = 0; k < 2; k++) { cudaFree(d.d_per_cand[k]); d.d_per_cand[k] = nullptr; }
+            d.pc_cap = 0;
+            for (int k = 0; k < 2; k++) CU(cudaMalloc(&d.d_per_cand[k], cap * sizeof(hc_result)));
+            d.pc_cap = cap;
+        }
+        const uint64_t need_e = std::max<uint64_t>(std::min<uint64_t>(m, edges_cap), 1), need_n = std::max<uint64_t>(std::min<uint64_t>(m, nonedge_cap), 1);
+        if (need_e > d.acc_e_cap) { cudaFree(d.d_acc_edges); d.d_acc_edges = nullptr; d.acc_e_cap = 0; CU(cudaMalloc(&d.d_acc_edges, need_e * sizeof(hc_edge))); d.acc_e_cap = need_e; }
+        if (need_n > d.acc_n_cap) { cudaFree(d.d_acc_nonedge); d.d_acc_nonedge = nullptr; d.acc_n_cap = 0; CU(cudaMalloc(&d.d_acc_nonedge, need_n * sizeof(uint64_t))); d.acc_n_cap = need_n; }
+        CU(cudaMemsetAsync(d.d_run, 0, 2 * sizeof(unsigned long long), d.stream));
+        CU(cudaEventRecord(d.ev[2], d.stream));
+    }
+    // ---- chunk loop, all devices interleaved
+    uint64_t max_chunks = 0;
+    for (int g = 0; g < G; g++) max_chunks = std::max<uint64_t>(max_chunks, (lo[g + 1] - lo[g] + chunk - 1) / chunk);
+    std::vector<uint64_t> out_e(G, 0), out_n(G, 0);   // already copied out (G == 1 streams results out while computing)
+    auto finalize_chunk = [&](int g, uint64_t k) -> int {   // chunk k of device g has been enqueued; wait for it, account, copy out
+        DevCtx& d = s->devs[g];
+        const int slot = (int)(k & 1);
+        const uint64_t c0 = lo[g] + k * chunk, cm = std::min<uint64_t>(chunk, lo[g + 1] - c0);
+        CU(cudaSetDevice(d.device));
+        CU(cudaEventSynchronize(d.ev_done[slot]));
+        const unsigned long long* h = d.h_cnt + slot * HC_CNT_N;
+        int rc = add_stats(d, h, cm, stats, nullptr, nullptr);
+        dev_e[g] += h[HC_CNT_EDGES];
+        dev_n[g] += h[HC_CNT_NONEDGES];
+        if (per_cand) {
+            CU(cudaStreamWaitEvent(d.s_out, d.ev_done[slot], 0));
+            CU(cudaMemcpyAsync(per_cand + c0, d.d_per_cand[slot], cm * sizeof(hc_result), cudaMemcpyDeviceToHost, d.s_out));
+        }
+        if (G == 1) {   // offsets in the caller's arrays are known: stream this chunk's results out now
+            const uint64_t e1 = std::min<uint64_t>(dev_e[g], d.acc_e_cap), n1 = std::min<uint64_t>(dev_n[g], d.acc_n_cap);
+            CU(cudaStreamWaitEvent(d.s_out, d.ev_done[slot], 0));
+            if (e1 > out_e[g] && e1 <= edges_cap)
+                CU(cudaMemcpyAsync(edges + out_e[g], d.d_acc_edges + out_e[g], (e1 - out_e[g]) * sizeof(hc_edge), cudaMemcpyDeviceToHost, d.s_out));
+            if (n1 > out_n[g] && n1 <= nonedge_cap)
+                CU(cudaMemcpyAsync(nonedge_idx + out_n[g], d.d_acc_nonedge + out_n[g], (n1 - out_n[g]) * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.s_out));
+            out_e[g] = std::max(out_e[g], e1);
+            out_n[g] = std::max(out_n[g], n1);
+        }
+        CU(cudaEventRecord(d.ev_out[slot], d.s_out));
+        return rc;
+    };
+    for (uint64_t k = 0; k < max_chunks; k++) {
+        for (int g = 0; g < G; g++) {
+            DevCtx& d = s->devs[g];
+            const uint64_t c0 = lo[g] + k * chunk;
+            if (c0 >= lo[g + 1]) continue;
+            const uint64_t cm = std::min<uint64_t>(chunk, lo[g + 1] - c0);
+            const int slot = (int)(k & 1);
+            CU(cudaSetDevice(d.device));
+            if (k >= 2) {   // the slot's previous user (chunk k-2) must have been computed and copied out
+                CU(cudaStreamWaitEvent(d.s_copy, d.ev_done[slot], 0));
+                CU(cudaStreamWaitEvent(d.stream, d.ev_out[slot], 0));
+            }
+            CU(cudaMemcpyAsync(d.d_cand[slot], (const char*)cand + c0 * rec, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
+            CU(cudaEventRecord(d.ev_in[slot], d.s_copy));
+            CU(cudaStreamWaitEvent(d.stream, d.ev_in[slot], 0));
+            uint32_t nl = 0;
+            int rc = enqueue_batch(s, d, d.stream, p, d.d_cand[slot], compact, cm, per_cand ? d.d_per_cand[slot] : nullptr,
+                                   d.d_acc_edges, d.acc_e_cap, d.d_acc_nonedge, d.acc_n_cap, nullptr, c0, d.d_run,
+                                   (stats && k == 0) ? d.ev[0] : nullptr, (stats && k == 0) ? d.ev[1] : nullptr, &nl);
+            if (rc != HC_OK) return rc;
+            launches += nl;
+            CU(cudaMemcpyAsync(d.h_cnt + slot * HC_CNT_N, d.counters, HC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+            CU(cudaEventRecord(d.ev_done[slot], d.stream));
+        }
+        if (k >= 1)
+            for (int g = 0; g < G; g++)
+                if (lo[g] + (k - 1) * chunk < lo[g + 1]) { int rc = finalize_chunk(g, k - 1); if (rc != HC_OK) result = rc; }
+    }
+    if (max_chunks >= 1)
+        for (int g = 0; g < G; g++)
+            if (lo[g] + (max_chunks - 1) * chunk < lo[g + 1]) { int rc = finalize_chunk(g, max_chunks - 1); if (rc != HC_OK) result = rc; }
+    // ---- gather: rank order = input order
+    uint64_t te = 0, tn = 0;
+    for (int g = 0; g < G; g++) {
+        DevCtx& d = s->devs[g];
+        CU(cudaSetDevice(d.device));
+        if (G > 1) {
+            const uint64_t e1 = std::min<uint64_t>(dev_e[g], d.acc_e_cap), n1 = std::min<uint64_t>(dev_n[g], d.acc_n_cap);
+            if (e1 && te + e1 <= edges_cap) CU(cudaMemcpyAsync(edges + te, d.d_acc_edges, e1 * sizeof(hc_edge), cudaMemcpyDeviceToHost, d.s_out));
+            if (n1 && tn + n1 <= nonedge_cap) CU(cudaMemcpyAsync(nonedge_idx + tn, d.d_acc_nonedge, n1 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.s_out));
+        }
+        te += dev_e[g];
+        tn += dev_n[g];
     }
     float total_ms = 0;
     for (int g = 0; g < G; g++) {
         DevCtx& d = s->devs[g];
         CU(cudaSetDevice(d.device));
+        CU(cudaStreamSynchronize(d.s_out));
         CU(cudaStreamSynchronize(d.stream));
+        CU(cudaEventRecord(d.ev[3], d.stream));
+        CU(cudaEventSynchronize(d.ev[3]));
         float ms = 0;
         if (cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]) == cudaSuccess) total_ms = std::max(total_ms, ms);
+        if (stats && lo[g + 1] > lo[g]) {
+            if (cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]) == cudaSuccess) stats->kernel_ms = std::max(stats->kernel_ms, ms);
+            if (cudaEventElapsedTime(&ms, d.ev[4], d.ev[5]) == cudaSuccess) stats->score_kernel_ms = std::max(stats->score_kernel_ms, ms);
+        }
     }
     *n_edges = te;
     *n_nonedges = tn;
@@ -547,6 +645,18 @@ int hc_score_batch(hc_store* s, const hc_params* p, const hc_candidate* cand, ui
     if (te > edges_cap || tn > nonedge_cap)
         return fail(HC_ERR_CAPACITY, "hc_score_batch: output buffer too small (required sizes returned in n_edges/n_nonedges)");
     return HC_OK;
+}
+
+int hc_score_batch(hc_store* s, const hc_params* p, const hc_candidate* cand, uint64_t n, hc_result* per_cand,
+                   hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
+                   uint64_t* n_nonedges, hc_batch_stats* stats) {
+    return score_host(s, p, cand, 0, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats);
+}
+
+int hc_score_batch_compact(hc_store* s, const hc_params* p, const hc_candidate_compact* cand, uint64_t n, hc_result* per_cand,
+                           hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
+                           uint64_t* n_nonedges, hc_batch_stats* stats) {
+    return score_host(s, p, cand, 1, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats);
 }
 
 double hc_overlap_score(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,

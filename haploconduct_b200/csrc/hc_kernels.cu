@@ -42,10 +42,19 @@ struct CandSetup {
     uint32_t err;
 };
 
-__device__ __forceinline__ hc_candidate load_candidate(const hc_candidate* p) {
-    const uint4* cp = reinterpret_cast<const uint4*>(p);
-    const uint4 a = __ldg(cp), b = __ldg(cp + 1);
+__device__ __forceinline__ hc_candidate load_candidate(const hc_kparams& P, u64 i) {
     hc_candidate c;
+    if (P.cand_compact) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.cand) + i);
+        c.idx1 = a.x; c.idx2 = a.y; c.pos1 = a.z & 0x0fffffffu; c.pos2 = a.w;
+        c.len1 = c.len2 = 0; c.perc1 = c.perc2 = 0; c.type1 = c.type2 = 0; c.reserved = 0;
+        c.ori1 = (a.z >> 28) & 1u; c.ori2 = (a.z >> 29) & 1u;
+        const uint32_t o = a.z >> 30;
+        c.ord = o == 1 ? '1' : (o == 2 ? '2' : '-');
+        return c;
+    }
+    const uint4* cp = reinterpret_cast<const uint4*>(P.cand) + 2 * i;
+    const uint4 a = __ldg(cp), b = __ldg(cp + 1);
     c.idx1 = a.x; c.idx2 = a.y; c.pos1 = a.z; c.pos2 = a.w;
     c.len1 = b.x; c.len2 = b.y;
     c.perc1 = b.z & 0xff; c.perc2 = (b.z >> 8) & 0xff; c.ord = (b.z >> 16) & 0xff; c.ori1 = (b.z >> 24) & 0xff;
@@ -428,7 +437,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
         s.w[0].L = s.w[1].L = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED;
         s.w[0].xpos = s.w[1].xpos = 0; s.w[0].ypos16 = s.w[1].ypos16 = 0; s.w[0].hasN = s.w[1].hasN = 0;
         if (valid) {
-            c = load_candidate(P.cand + i);
+            c = load_candidate(P, i);
             load_and_setup(P, c, s, r1, r2);
             prefetch_window(P, s.w[0]);
             prefetch_window(P, s.w[1]);
@@ -690,7 +699,7 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
     const u64 nf = P.counters[HC_CNT_FLAGGED];
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nf; t += (u64)gridDim.x * blockDim.x) {
         const u64 i = P.flagged[t];
-        const hc_candidate c = load_candidate(P.cand + i);
+        const hc_candidate c = load_candidate(P, i);
         CandSetup s;
         uint4 r1, r2;
         if (!load_and_setup(P, c, s, r1, r2)) continue;
@@ -807,7 +816,7 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
     __shared__ uint32_t we[HC_CB_THREADS / 32], wo[HC_CB_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 base = (u64)blockIdx.x * HC_CB_ITEMS;
-    u64 eoff = blockoffs[2 * blockIdx.x], ooff = blockoffs[2 * blockIdx.x + 1];
+    u64 eoff = blockoffs[2 * blockIdx.x] + (P.run ? P.run[0] : 0ull), ooff = blockoffs[2 * blockIdx.x + 1] + (P.run ? P.run[1] : 0ull);
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t k0 = 0; k0 < HC_CB_ITEMS; k0 += HC_CB_THREADS) {
         const u64 i = base + k0 + threadIdx.x;
@@ -828,7 +837,7 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
             const u64 dst = eoff + pe + __popc(be & lt);
             if (dst < edges_cap) {
                 // Edge::score (:138, :256-261) for accepted edges only
-                const hc_candidate cd = load_candidate(P.cand + i);
+                const hc_candidate cd = load_candidate(P, i);
                 const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx1));
                 const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx2));
                 const hc_tmp32 t = P.tmp[i];
@@ -858,6 +867,11 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
         ooff += to;
         __syncthreads();
     }
+}
+
+__global__ void hc_compact_advance(unsigned long long* run, const unsigned long long* counters) {
+    run[0] += counters[HC_CNT_EDGES];
+    run[1] += counters[HC_CNT_NONEDGES];
 }
 
 }  // namespace
@@ -901,7 +915,8 @@ uint32_t hc_compact_blocks(uint64_t n) { return (uint32_t)((n + HC_CB_ITEMS - 1)
 
 // d_blockcounts: uint32[2*nblocks] followed (8-byte aligned) by uint64[2*nblocks] block offsets
 cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge,
-                              uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, cudaStream_t st) {
+                              uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, unsigned long long* d_run,
+                              cudaStream_t st) {
     const uint32_t nb = hc_compact_blocks(P.n);
     u64* offs = reinterpret_cast<u64*>(d_blockcounts + 2ull * nb + (2ull * nb & 1ull));
     if (nb > 0) {
@@ -911,5 +926,6 @@ cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t ed
     if (nb > 0) {
         hc_compact_scatter<<<nb, HC_CB_THREADS, 0, st>>>(P, offs, d_edges, edges_cap, d_nonedge, nonedge_cap, cand_offset);
     }
+    if (d_run) hc_compact_advance<<<1, 1, 0, st>>>(d_run, P.counters);
     return cudaGetLastError();
 }

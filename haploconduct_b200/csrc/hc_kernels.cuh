@@ -44,7 +44,9 @@ struct hc_kparams {
     uint32_t ncodes;
     uint32_t has_void;
     // batch
-    const hc_candidate* cand;
+    const void* cand;           // hc_candidate[n] (cand_compact == 0) or hc_candidate_compact[n]
+    uint32_t cand_compact;
+    const unsigned long long* run;   // nullable: running {edges, non-edges} totals of earlier chunks = output base offsets
     uint64_t n;
     hc_tmp32* tmp;
     uint8_t* cls;
@@ -87,7 +89,8 @@ struct hc_launch_cfg {
 cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaStream_t st);
 cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st);
 cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge,
-                              uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, cudaStream_t st);
+                              uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, unsigned long long* d_run,
+                              cudaStream_t st);
 cudaError_t hc_score_occupancy(uint32_t ncodes, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg);
 uint32_t hc_compact_blocks(uint64_t n);
 

@@ -84,6 +84,15 @@ typedef struct {
     uint8_t  reserved;       /* must be 0                                                          */
 } hc_candidate;              /* 32 bytes */
 
+/* Compact 16-byte form of the same record: only what the device reads (read types come from the
+ * store).  Halves the host->device traffic of hc_score_batch_compact; LEN/PERC/TYPE stay with the
+ * caller, who finds them again through hc_edge.cand. */
+typedef struct {
+    uint32_t idx1, idx2;
+    uint32_t pos1_flags;     /* POS1 in bits 0-27; bit 28: ORI1 is '+'; bit 29: ORI2 is '+'; bits 30-31: ORD 0 '-', 1 '1', 2 '2' */
+    uint32_t pos2;
+} hc_candidate_compact;      /* 16 bytes */
+
 /* Scoring parameters = the ProgramSettings fields the path reads (src/Types.h:19-67). */
 typedef struct {
     double   edge_threshold;   /* src/EdgeCalculator.cpp:404 and per half :256,:294,:355 */
@@ -157,12 +166,22 @@ typedef struct {
  *   edges         must hold *edges_cap records; on return *n_edges are valid.
  *   nonedge_idx   candidate indices classified "non-edge overlap" (:410-413), input order.
  * Returns HC_ERR_CAPACITY (and the required sizes in *n_edges / *n_nonedges) if a buffer is too small. */
+/* Host batches are streamed through the device in chunks: the copy of chunk k+1, the kernels of
+ * chunk k and the copy-out of chunk k-1 overlap (chunk size: 16 M candidates). */
 int hc_score_batch(hc_store* s, const hc_params* p,
                    const hc_candidate* cand, uint64_t n,
                    hc_result* per_cand,
                    hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges,
                    uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
                    hc_batch_stats* stats /* nullable */);
+
+/* hc_score_batch on compact candidate records. */
+int hc_score_batch_compact(hc_store* s, const hc_params* p,
+                           const hc_candidate_compact* cand, uint64_t n,
+                           hc_result* per_cand,
+                           hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges,
+                           uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
+                           hc_batch_stats* stats /* nullable */);
 
 /* Same, but every buffer is DEVICE memory on device `device` (one of the store's devices) and the
  * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream).

@@ -244,3 +244,25 @@ def test_larger_random_batch_and_determinism(built_lib):
         e2, n2, per2, _ = st.score_batch(p, c[::-1].copy())
     # integer sums: the result of a candidate does not depend on its position in the batch
     assert np.array_equal(per1, per) and np.array_equal(per2[::-1], per1)
+
+
+@pytest.mark.parametrize("chunk", ["777", "100000000"])
+def test_chunked_pipeline_and_compact_records(built_lib, monkeypatch, chunk):
+    """hc_score_batch streams the batch through the device in chunks (3 streams, 2 slots); the chunk
+    size must not change anything, and the 16-byte compact records give the same results."""
+    g = load_golden("synth_all_types")
+    cands = np.tile(g.scored(), 3)
+    p = g.params()
+    with capi.Store(g.rs) as st:
+        monkeypatch.setenv("HC_HOST_CHUNK", "100000000")
+        e0, n0, per0, s0 = st.score_batch(p, cands)
+        monkeypatch.setenv("HC_HOST_CHUNK", chunk)
+        e1, n1, per1, s1 = st.score_batch(p, cands)
+        e2, n2, per2, s2 = st.score_batch(p, cands, compact=True)
+        e3, n3, _, _ = st.score_batch(p, cands, per_candidate=False, compact=True, edges_cap=len(e0), nonedge_cap=len(n0))
+    for e, n, per, s in ((e1, n1, per1, s1), (e2, n2, per2, s2)):
+        assert e.tobytes() == e0.tobytes() and np.array_equal(n, n0) and per.tobytes() == per0.tobytes()
+        assert int(s["n_positions"]) == int(s0["n_positions"]) and int(s["n_edges"]) == len(e0)
+    assert e3.tobytes() == e0.tobytes() and np.array_equal(n3, n0)
+    ref = np.tile(g.ref_cands, 3)
+    assert np.array_equal(per1["cls"], ref["cls"])
