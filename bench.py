@@ -100,6 +100,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(n_candidates: int, default_config: bool):
+    """dram__bytes_read.sum + dram__bytes_write.sum of hc_score_kernel per launch, from the committed
+    ncu --set full capture of this same configuration (bench.py cannot run under a profiler itself)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return (float(t["dram_bytes_per_candidate"]) * n_candidates, t["source"]) if default_config else (None, None)
+    except Exception:
+        return None, None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -325,6 +336,8 @@ def main() -> None:
         peak, peak_src = measured_hbm_peak()
         alg = int(stats["algorithmic_bytes"])
         achieved = alg / (score_ms * 1e-3) / 1e9
+        default_cfg = args.pairs == 10_000_000 and args.read_len == 150 and args.partners == 140 and not args.position_sorted_ids
+        traffic, traffic_src = measured_traffic(n, default_cfg)
         line = {
             "metric": METRIC, "value": total_cands / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -333,7 +346,7 @@ def main() -> None:
                        "per step, no flush needed" % (n * 32 / 1e9, store.device_bytes / 1e9),
                        "params": PARAMS, "candidates_per_gpu": n, "seed": args.seed},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "hc_score_kernel", "kernel_ms": score_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "hc_score_kernel", "kernel_ms": score_ms,
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                          "positions_per_launch": int(stats["n_positions"]), "all_kernels_ms": float(stats["kernel_ms"])},
             "gpu_launches": int(stats["kernel_launches"]) * args.steps,
