@@ -1,0 +1,77 @@
+"""GPU suite, larger than what the oracle can check exhaustively: size-independent properties on a
+config-4 shaped workload (2x150 bp pairs, P-P candidates, shuffled read ids) plus an oracle check on
+a random sample of it."""
+import numpy as np
+import pytest
+import torch
+
+from haploconduct_b200 import capi, formats as F, workloads_torch as WT
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c4_small():
+    pr = WT.make_paired_reads(200_000, genome_len=2_000, seed=20261018, device="cuda")
+    rec = WT.make_pp_candidates(pr, D=40, shard=0, n_shards=1, max_cands=5_000_000)
+    cands = WT.candidates_as_numpy(rec)
+    return pr.readset(), cands
+
+
+def test_shard_invariance_and_order(built_lib, c4_small):
+    """Scoring the list in one call equals scoring 8 contiguous shards and concatenating in rank
+    order (what N one-GPU ranks + the ordered gather produce): same edges, same order."""
+    rs, cands = c4_small
+    p = F.make_params(edge_threshold=0.97)
+    n = len(cands)
+    assert n >= 4_000_000
+    with capi.Store(rs) as st:
+        e_all, n_all, _, s_all = st.score_batch(p, cands, per_candidate=False)
+        parts_e, parts_n = [], []
+        for k in range(8):
+            lo, hi = n * k // 8, n * (k + 1) // 8
+            e, ne, _, _ = st.score_batch(p, cands[lo:hi], per_candidate=False, compact=(k % 2 == 1))
+            e = e.copy()
+            e["cand"] += np.uint64(lo)
+            parts_e.append(e)
+            parts_n.append(ne + np.uint64(lo))
+    assert np.concatenate(parts_e).tobytes() == e_all.tobytes()
+    assert np.array_equal(np.concatenate(parts_n), n_all)
+    assert np.all(np.diff(e_all["cand"].astype(np.int64)) > 0) and np.all(np.diff(n_all.astype(np.int64)) > 0)   # input order
+    assert 0 < len(e_all) < n and 0 < len(n_all) < n
+    # the kernel's own bookkeeping of algorithmic bytes: 32 + sum_w(2*ceil(L/4) + 2*ceil(L/8) + 2L) + 16 per candidate
+    L1 = 150 - cands["pos1"].astype(np.int64)
+    L2 = 150 - cands["pos2"].astype(np.int64)
+    want = (48 * n + sum(int((2 * ((L + 3) // 4) + 2 * ((L + 7) // 8) + 2 * L).sum()) for L in (L1, L2)))
+    assert int(s_all["algorithmic_bytes"]) == want and int(s_all["n_positions"]) == int((L1 + L2).sum())
+
+
+def test_random_sample_against_oracle(built_lib, c4_small):
+    rs, cands = c4_small
+    p = F.make_params(edge_threshold=0.97)
+    rng = np.random.RandomState(1)
+    pick = np.sort(rng.choice(len(cands), size=40_000, replace=False))
+    with capi.Store(rs) as st:
+        e_all, n_all, _, _ = st.score_batch(p, cands, per_candidate=False)
+        _, _, per, _ = st.score_batch(p, cands[pick])
+    ref, _ = O.score_batch(rs, p, cands[pick])
+    assert np.array_equal(per["cls"], ref["cls"])
+    assert np.array_equal(per["mismatch_rate"], ref["mismatch_rate"]) and np.array_equal(per["mismatches"], ref["mismatches"])
+    assert np.allclose(per["score"], ref["score"], rtol=1e-6, atol=0)
+    # membership of the sample in the full run's lists agrees with the oracle's classes
+    is_e = np.isin(pick.astype(np.uint64), e_all["cand"])
+    is_n = np.isin(pick.astype(np.uint64), n_all)
+    assert np.array_equal(is_e, ref["cls"] == 1) and np.array_equal(is_n, ref["cls"] == 2)
+
+
+def test_permutation_equivariance(built_lib, c4_small):
+    """Integer sums: a candidate's result does not depend on where it sits in the batch."""
+    rs, cands = c4_small
+    sub = cands[:300_000]
+    perm = np.random.RandomState(2).permutation(len(sub))
+    p = F.make_params(edge_threshold=0.97)
+    with capi.Store(rs) as st:
+        _, _, a, _ = st.score_batch(p, sub)
+        _, _, b, _ = st.score_batch(p, sub[perm])
+    assert a[perm].tobytes() == b.tobytes()
