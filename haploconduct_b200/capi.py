@@ -15,7 +15,7 @@ import numpy as np
 from . import formats as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhc_b200.so")
+LIB_PATH = os.environ.get("HC_B200_LIB") or os.path.join(HERE, "lib", "libhc_b200.so")   # override: kernel experiments only
 
 # every symbol include/hc_b200.h declares
 EXPORTED = [

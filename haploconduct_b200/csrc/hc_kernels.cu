@@ -439,8 +439,10 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
         if (valid) {
             c = load_candidate(P, i);
             load_and_setup(P, c, s, r1, r2);
+#ifndef HC_NO_PREFETCH
             prefetch_window(P, s.w[0]);
             prefetch_window(P, s.w[1]);
+#endif
         }
         const uint32_t c0 = (s.w[0].L + 31u) >> 5, c1 = (s.w[1].L + 31u) >> 5;
         const uint32_t ct = c0 + c1;

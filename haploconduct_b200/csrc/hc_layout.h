@@ -66,8 +66,13 @@ HC_HD uint32_t hc_fx_index(uint32_t ca, uint32_t cb, uint32_t mm) {
 // XOR of an A byte with a B byte then carries the base difference in bits 6-7 for free; the table
 // column is ((code_A ^ g6(code_B)) & 63) | (base_A ^ base_B) << 6  (columns 64..255 = mismatch).
 #define HC_PACKED_MAX_CODES 63
+#ifdef HC_NO_SWZ   // experiment: no bank swizzle (column = A code)
+HC_HD uint32_t hc_swz4_packed(uint32_t wb) { return wb & 0xc0c0c0c0u; }
+HC_HD uint32_t hc_swz1_packed(uint32_t cb) { (void)cb; return 0u; }
+#else
 HC_HD uint32_t hc_swz4_packed(uint32_t wb) { return ((wb << 1) & 0x3e3e3e3eu) | (wb & 0xc1c1c1c1u); }
 HC_HD uint32_t hc_swz1_packed(uint32_t cb) { return ((cb << 1) & 0x3eu) | (cb & 1u); }
+#endif
 HC_HD uint32_t hc_fx_index_packed(uint32_t ca, uint32_t cb, uint32_t bx) {
     return (cb << 8) | ((ca ^ hc_swz1_packed(cb)) & 0x3fu) | (bx << 6);
 }
