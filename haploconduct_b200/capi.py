@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("HC_B200_LIB") or os.path.join(HERE, "lib", "libhc_b20
 EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_device",
-    "hc_overlap_score",
+    "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
 ]
 
@@ -62,6 +62,9 @@ def lib() -> ctypes.CDLL:
         L.hc_overlap_score.restype = dbl
         L.hc_overlap_score.argtypes = [ctypes.c_char_p, u32, ctypes.c_char_p, u32, ctypes.c_char_p, ctypes.c_char_p, u32, vp,
                                        ctypes.POINTER(dbl)]
+        L.hc_overlap_score_multi.restype = i32
+        L.hc_overlap_score_multi.argtypes = [ctypes.c_char_p, u32, ctypes.c_char_p, u32, ctypes.c_char_p, ctypes.c_char_p, vp, u32, vp,
+                                             vp, vp, vp]
         L.hc_phred_to_prob.restype = dbl
         L.hc_phred_to_prob.argtypes = [i32]
         L.hc_exp_threshold.restype = dbl
@@ -171,6 +174,15 @@ def overlap_score(seq1: str, seq2: str, q1: str, q2: str, pos: int, params: np.n
     if s < 0:
         raise HcError(-1, last_error())
     return s, mm.value
+
+
+def overlap_score_multi(seq1: str, seq2: str, q1: str, q2: str, pos, params: np.ndarray):
+    """hc_overlap_score_multi: (scores, mismatch_rates, above_threshold) for many start positions."""
+    pos = np.ascontiguousarray(pos, dtype=np.uint32)
+    sc = np.zeros(len(pos)); mm = np.zeros(len(pos)); ab = np.zeros(len(pos), dtype=np.uint8)
+    _check(lib().hc_overlap_score_multi(seq1.encode(), len(seq1), seq2.encode(), len(seq2), q1.encode(), q2.encode(),
+                                        pos.ctypes.data, len(pos), params.ctypes.data, sc.ctypes.data, mm.ctypes.data, ab.ctypes.data))
+    return sc, mm, ab.astype(bool)
 
 
 def phred_to_prob(q: int) -> float:

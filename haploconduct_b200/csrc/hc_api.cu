@@ -659,12 +659,12 @@ int hc_score_batch_compact(hc_store* s, const hc_params* p, const hc_candidate_c
     return score_host(s, p, cand, 1, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats);
 }
 
-double hc_overlap_score(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,
-                        const char* qual2, uint32_t pos, const hc_params* p, double* mismatch_rate) {
-    if (!seq1 || !seq2 || !qual1 || !qual2 || !p || len1 == 0 || len2 == 0) {
-        fail(HC_ERR_ARG, "hc_overlap_score: bad argument");
-        return -1;
-    }
+int hc_overlap_score_multi(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,
+                           const char* qual2, const uint32_t* pos, uint32_t n_pos, const hc_params* p, double* scores,
+                           double* mismatch_rates, uint8_t* above) {
+    if (!seq1 || !seq2 || !qual1 || !qual2 || !p || len1 == 0 || len2 == 0 || (n_pos && !pos))
+        return fail(HC_ERR_ARG, "hc_overlap_score_multi: bad argument");
+    if (n_pos == 0) return HC_OK;
     std::string b(seq1, len1), q(qual1, len1);
     b.append(seq2, len2);
     q.append(qual2, len2);
@@ -675,18 +675,35 @@ double hc_overlap_score(const char* seq1, uint32_t len1, const char* seq2, uint3
     int dev = 0;
     cudaGetDevice(&dev);
     hc_store* s = hc_store_create(rd, 2, 2, b.data(), q.data(), dev, 1);
-    if (!s) return -1;
-    hc_candidate c;
-    memset(&c, 0, sizeof(c));
-    c.idx1 = 0; c.idx2 = 1; c.pos1 = pos; c.ord = '-'; c.ori1 = 1; c.ori2 = 1; c.type1 = 's'; c.type2 = 's';
-    hc_result r;
-    hc_edge e;
-    uint64_t ne = 0, nn = 0, ni = 0;
-    int rc = hc_score_batch(s, p, &c, 1, &r, &e, 1, &ne, &ni, 1, &nn, nullptr);
+    if (!s) return HC_ERR_CUDA;
+    std::vector<hc_candidate> c(n_pos);
+    memset(c.data(), 0, n_pos * sizeof(hc_candidate));
+    for (uint32_t i = 0; i < n_pos; i++) {
+        c[i].idx1 = 0; c[i].idx2 = 1; c[i].pos1 = pos[i]; c[i].ord = '-'; c[i].ori1 = 1; c[i].ori2 = 1; c[i].type1 = 's'; c[i].type2 = 's';
+    }
+    hc_params pp = *p;
+    pp.merge_contigs = -1.0;   // class EDGE <=> score > edge_threshold, nothing else
+    std::vector<hc_result> r(n_pos);
+    std::vector<hc_edge> e(n_pos);
+    std::vector<uint64_t> ni(n_pos);
+    uint64_t ne = 0, nn = 0;
+    int rc = hc_score_batch(s, &pp, c.data(), n_pos, r.data(), e.data(), n_pos, &ne, ni.data(), n_pos, &nn, nullptr);
     hc_store_destroy(s);
-    if (rc != HC_OK) return -1;
-    if (mismatch_rate) *mismatch_rate = r.mismatch_rate;
-    return r.score;
+    if (rc != HC_OK) return rc;
+    for (uint32_t i = 0; i < n_pos; i++) {
+        if (scores) scores[i] = r[i].score;
+        if (mismatch_rates) mismatch_rates[i] = r[i].mismatch_rate;
+        if (above) above[i] = r[i].cls == HC_CLASS_EDGE;
+    }
+    return HC_OK;
+}
+
+double hc_overlap_score(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,
+                        const char* qual2, uint32_t pos, const hc_params* p, double* mismatch_rate) {
+    double s = -1, mm = 1;
+    if (hc_overlap_score_multi(seq1, len1, seq2, len2, qual1, qual2, &pos, 1, p, &s, &mm, nullptr) != HC_OK) return -1;
+    if (mismatch_rate) *mismatch_rate = mm;
+    return s;
 }
 
 }  // extern "C"

@@ -204,6 +204,16 @@ double hc_overlap_score(const char* seq1, uint32_t len1, const char* seq2, uint3
                         const char* qual1, const char* qual2, uint32_t pos,
                         const hc_params* p, double* mismatch_rate);
 
+/* The same primitive for many start positions of one sequence pair in ONE device batch -- the
+ * access pattern of SRBuilder::merge_self_overlap (src/SRBuilder.cpp:880-888), which slides seq2 over
+ * seq1 from pos = len1-15 downwards until score > 0.99.  above[i] (nullable) receives the exact
+ * decision "overlap_score(pos[i]) > p->edge_threshold" (decided in the reference's own summation
+ * order when the score is within 1e-7 of the threshold), so the caller's loop can test above[i]
+ * instead of comparing a device exp() against the threshold. */
+int hc_overlap_score_multi(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2,
+                           const char* qual1, const char* qual2, const uint32_t* pos, uint32_t n_pos,
+                           const hc_params* p, double* scores, double* mismatch_rates, uint8_t* above);
+
 /* EdgeCalculator::phred_to_prob (src/EdgeCalculator.cpp:59-63), host arithmetic: pow(10, -Q/10.0). */
 double hc_phred_to_prob(int phred);
 

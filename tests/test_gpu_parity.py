@@ -266,3 +266,22 @@ def test_chunked_pipeline_and_compact_records(built_lib, monkeypatch, chunk):
     assert e3.tobytes() == e0.tobytes() and np.array_equal(n3, n0)
     ref = np.tile(g.ref_cands, 3)
     assert np.array_equal(per1["cls"], ref["cls"])
+
+
+def test_overlap_score_multi_self_overlap_scan(built_lib):
+    """The scan of SRBuilder::merge_self_overlap (src/SRBuilder.cpp:880-888): seq2 slid over seq1 from
+    pos = len1-15 downwards; first position whose score exceeds 0.99 -- same position as the oracle's loop."""
+    rng = np.random.RandomState(21)
+    left = "".join("ACGT"[k] for k in rng.randint(0, 4, size=180))
+    right = left[120:] + "".join("ACGT"[k] for k in rng.randint(0, 4, size=140))     # true overlap starts at 120
+    q1 = "".join(chr(33 + k) for k in rng.randint(25, 42, size=len(left)))
+    q2 = "".join(chr(33 + k) for k in rng.randint(25, 42, size=len(right)))
+    p = F.make_params(edge_threshold=0.99)
+    pos = np.array([len(left) - 15 - k for k in range(len(left) - 15)], dtype=np.uint32)
+    sc, mm, above = capi.overlap_score_multi(left, right, q1, q2, pos, p)
+    want = [O.overlap_score(left, right, q1, q2, int(x), p) for x in pos]
+    assert np.array_equal(mm, np.array([w[1] for w in want]))
+    assert np.allclose(sc, np.array([w[0] for w in want]), rtol=1e-6, atol=0)
+    assert np.array_equal(above, np.array([w[0] > 0.99 for w in want]))
+    first = int(pos[np.nonzero(above)[0][0]])
+    assert first == 120
