@@ -23,6 +23,7 @@ EXPORTED = [
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
+    "hc_dedup_edges",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -75,6 +76,8 @@ def lib() -> ctypes.CDLL:
         L.hc_fno1.argtypes = [vp, vp, u64, vp, u64, ctypes.POINTER(u64), i32]
         L.hc_fno3.restype = i32
         L.hc_fno3.argtypes = [u64, vp, vp, vp, u64, vp, i32, vp, u64, ctypes.POINTER(u64), i32]
+        L.hc_dedup_edges.restype = i32
+        L.hc_dedup_edges.argtypes = [vp, u64, i32, vp, vp, u64, vp, i32]
         L.hc_last_error.restype = ctypes.c_char_p
         L.hc_version.restype = ctypes.c_char_p
         _lib = L
@@ -238,3 +241,15 @@ def fno3(fi: "F.Fno3Input", device: int = 0) -> np.ndarray:
         if rc != -5:
             raise HcError(rc, last_error())
         cap = int(n.value)
+
+
+def dedup_edges(edges: np.ndarray, n_vertices: int, ignore_inclusions: bool = False, inclusions: Optional[np.ndarray] = None,
+                device: int = 0):
+    """hc_dedup_edges: (winner flags, inclusions marks, dup_count, inclusion_count) of the graph insert."""
+    edges = np.ascontiguousarray(edges, dtype=F.DEDUP_EDGE)
+    win = np.zeros(max(len(edges), 1), dtype=np.uint8)
+    inc = np.zeros(max(n_vertices, 1), dtype=np.uint8) if inclusions is None else np.ascontiguousarray(inclusions, dtype=np.uint8).copy()
+    counts = np.zeros(2, dtype=np.uint64)
+    _check(lib().hc_dedup_edges(edges.ctypes.data if len(edges) else None, len(edges), int(ignore_inclusions), win.ctypes.data,
+                                inc.ctypes.data, n_vertices, counts.ctypes.data, device))
+    return win[: len(edges)].astype(bool), inc[:n_vertices], int(counts[0]), int(counts[1])

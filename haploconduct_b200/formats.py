@@ -71,6 +71,10 @@ FNO_OVERLAP = np.dtype([("id1", "<u8"), ("id2", "<u8"), ("pos1", "<i4"), ("pos2"
                         ("len2", "<i4"), ("ord", "u1"), ("ori1", "u1"), ("ori2", "u1"), ("type1", "u1"), ("type2", "u1"),
                         ("reserved", "u1", (3,)), ("perc2", "<i4")])
 FNO3_POS = np.dtype([("index1", "<i4"), ("index2", "<i4")])
+DEDUP_EDGE = np.dtype([("vertex1", "<u4"), ("vertex2", "<u4"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos1", "<i4"),
+                       ("pos2", "<i4"), ("pos3", "<i4"), ("overlap_len", "<i4"), ("perc", "<i4"), ("ori1", "u1"), ("ori2", "u1"),
+                       ("reserved", "u1", (2,))])
+assert DEDUP_EDGE.itemsize == 48
 assert FNO_EDGE.itemsize == 32 and FNO_READ.itemsize == 16 and FNO_SUBREAD.itemsize == 16 and FNO_OVERLAP.itemsize == 48
 
 CLASS_DISCARD, CLASS_EDGE, CLASS_NONEDGE = 0, 1, 2

@@ -363,42 +363,48 @@ void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
         e.overlap_len = e.overlap_len1 + e.overlap_len2;
         e.mismatch_rate = he.mismatch_rate;
 
-        node_id_t v1 = e.vertex1, v2 = e.vertex2;
-        if (e.pos1 == 0 && v1 > v2) { std::swap(v1, v2); e.swap_reads(); }         // :443-448
-        if (e.overlap_perc == 100) inclusion_count++;                              // :449-451
-        const bool same_ori = e.ori1 == e.ori2;
-        const double have = graph_->checkEdgeWithOri(v1, v2, same_ori);
-        if (have < 0) {                                                            // :455-469
-            graph_->addEdge(e);
-            if (ps_.ignore_inclusions && e.overlap_perc == 100 && e.mismatch_rate < 0.000001 && e.mismatch_rate >= 0) {
-                if (e.pos3 < 0) { if (e.pos1 == 0) graph_->inclusions[v1] = 1; }
-                else graph_->inclusions[v2] = 1;
-            }
-        } else if (e.score >= have) {                                              // :470-534
-            doubles++;
-            const Edge* old = graph_->getEdgeInfoWithOri(v1, v2, same_ori);
-            bool keep_old = false;
-            if (have == e.score) {   // the reference's deterministic tie-break, one criterion decides
-                if (old->overlap_len != e.overlap_len) keep_old = old->overlap_len > e.overlap_len;
-                else if (old->mismatch_rate != e.mismatch_rate) keep_old = old->mismatch_rate < e.mismatch_rate;
-                else if (old->vertex1 != e.vertex1) keep_old = old->vertex1 < e.vertex1;
-                else if (old->ori1 != e.ori1) keep_old = old->ori1;
-                else if (old->ori2 != e.ori2) keep_old = old->ori2;
-                else if (old->pos1 != e.pos1) keep_old = old->pos1 < e.pos1;
-                else if (old->pos2 != e.pos2) keep_old = old->pos2 < e.pos2;
-            }
-            if (keep_old) continue;
-            if (old->vertex1 == v1) graph_->removeEdgeWithOri(v1, v2, same_ori);
-            else graph_->removeEdgeWithOri(v2, v1, same_ori);
-            graph_->addEdge(e);
-        } else {
-            doubles++;                                                             // :535-538
-        }
+        if (e.pos1 == 0 && e.vertex1 > e.vertex2) e.swap_reads();                  // :443-448
+        if (ps_.gpu_dedup) pending_.push_back(e);
+        else insert_edge(e, doubles);
     }
     dup_count += doubles;
 
     std::ofstream out((ps_.output_dir + "nonedge_overlaps.txt").c_str(), std::fstream::out | std::fstream::app);
     for (uint64_t k = 0; k < nn; k++) out << batch[nonedge[k]].get_overlap_line();
+}
+
+// One step of the sequential insert, src/EdgeCalculator.cpp:449-538 (the edge is already normalised).
+void EdgeCalculator::insert_edge(Edge& e, unsigned int& doubles) {
+    const node_id_t v1 = e.vertex1, v2 = e.vertex2;
+    if (e.overlap_perc == 100) inclusion_count++;                              // :449-451
+    const bool same_ori = e.ori1 == e.ori2;
+    const double have = graph_->checkEdgeWithOri(v1, v2, same_ori);
+    if (have < 0) {                                                            // :455-469
+        graph_->addEdge(e);
+        if (ps_.ignore_inclusions && e.overlap_perc == 100 && e.mismatch_rate < 0.000001 && e.mismatch_rate >= 0) {
+            if (e.pos3 < 0) { if (e.pos1 == 0) graph_->inclusions[v1] = 1; }
+            else graph_->inclusions[v2] = 1;
+        }
+    } else if (e.score >= have) {                                              // :470-534
+        doubles++;
+        const Edge* old = graph_->getEdgeInfoWithOri(v1, v2, same_ori);
+        bool keep_old = false;
+        if (have == e.score) {   // the reference's deterministic tie-break, one criterion decides
+            if (old->overlap_len != e.overlap_len) keep_old = old->overlap_len > e.overlap_len;
+            else if (old->mismatch_rate != e.mismatch_rate) keep_old = old->mismatch_rate < e.mismatch_rate;
+            else if (old->vertex1 != e.vertex1) keep_old = old->vertex1 < e.vertex1;
+            else if (old->ori1 != e.ori1) keep_old = old->ori1;
+            else if (old->ori2 != e.ori2) keep_old = old->ori2;
+            else if (old->pos1 != e.pos1) keep_old = old->pos1 < e.pos1;
+            else if (old->pos2 != e.pos2) keep_old = old->pos2 < e.pos2;
+        }
+        if (keep_old) return;
+        if (old->vertex1 == v1) graph_->removeEdgeWithOri(v1, v2, same_ori);
+        else graph_->removeEdgeWithOri(v2, v1, same_ori);
+        graph_->addEdge(e);
+    } else {
+        doubles++;                                                             // :535-538
+    }
 }
 
 void EdgeCalculator::construct_edges() {                                          // src/EdgeCalculator.cpp:561-666
@@ -446,6 +452,28 @@ void EdgeCalculator::construct_edges() {                                        
         if (batch.size() == per_batch) { process_overlaps(batch); batch.clear(); }
     }
     if (!batch.empty()) { process_overlaps(batch); batch.clear(); }
+    if (ps_.gpu_dedup && !pending_.empty()) {
+        // all accepted edges of the run at once: the per-key arg-max of hc_dedup_edges equals the sequential
+        // replace-if-better fold, and the survivors in input order are the final adjacency lists
+        std::vector<hc_dedup_edge> de(pending_.size());
+        for (size_t k = 0; k < pending_.size(); k++) {
+            const Edge& e = pending_[k];
+            hc_dedup_edge& d = de[k];
+            memset(&d, 0, sizeof(d));
+            d.vertex1 = (uint32_t)e.vertex1; d.vertex2 = (uint32_t)e.vertex2; d.score = e.score; d.mismatch_rate = e.mismatch_rate;
+            d.pos1 = e.pos1; d.pos2 = e.pos2; d.pos3 = e.pos3; d.overlap_len = e.overlap_len; d.perc = e.overlap_perc;
+            d.ori1 = e.ori1; d.ori2 = e.ori2;
+        }
+        std::vector<uint8_t> win(pending_.size());
+        uint64_t counts[2] = {0, 0};
+        const int rc = hc_dedup_edges(de.data(), de.size(), ps_.ignore_inclusions, win.data(), (uint8_t*)graph_->inclusions.data(),
+                                      graph_->inclusions.size(), counts, ps_.first_device);
+        if (rc != HC_OK) die(std::string("hc_dedup_edges: ") + hc_last_error());
+        for (size_t k = 0; k < pending_.size(); k++) if (win[k]) graph_->addEdge(pending_[k]);
+        dup_count += (unsigned int)counts[0];
+        inclusion_count += (unsigned int)counts[1];
+        pending_.clear();
+    }
     if (ps_.verbose) {
         std::cout << "Number of self-overlapping reads: " << self_overlap_count << "\n";
         std::cout << "Number of inclusion edges: " << inclusion_count << "\n";

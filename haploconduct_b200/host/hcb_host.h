@@ -52,6 +52,8 @@ struct ProgramSettings {           // names and defaults of src/Types.h:19-67 / 
     // duplicate-edge resolution of process_overlaps (score >= existing score, :470) needs to pick the
     // same representative when two overlaps of one read pair score within 1e-7 of each other.
     bool exact_scores = true;
+    // resolve duplicate edges on the GPU (hc_dedup_edges) instead of the sequential insert of :429-545
+    bool gpu_dedup = false;
     int first_device = 0;
     int n_devices = 1;
 };
@@ -152,6 +154,8 @@ public:
 
 private:
     void process_overlaps(std::vector<Overlap>& batch);                                          // :389-557
+    void insert_edge(Edge& e, unsigned int& doubles);                                            // :441-538
+    std::vector<Edge> pending_;   // gpu_dedup: accepted edges of all batches, normalised, in order
     ProgramSettings ps_;
     std::shared_ptr<FastqStorage> fastq_;
     std::shared_ptr<OverlapGraph> graph_;

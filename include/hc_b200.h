@@ -290,6 +290,38 @@ int hc_fno3(uint64_t n_originals, const uint64_t* off /* [n_originals+1] */, con
             uint64_t n_reads, const hc_fno_read* reads /* super-reads and trivial reads */, int no_inclusions,
             hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out, int device);
 
+/* ------------------------------------------------------------------------------------------
+ * Duplicate-edge resolution of the graph insert (first "next" row):
+ * EdgeCalculator::process_overlaps, serial section, src/EdgeCalculator.cpp:429-545.
+ *
+ * The reference inserts accepted edges one by one; an edge whose (unordered vertex pair, "both
+ * orientations equal" flag) already has an edge replaces it iff  score >= existing score, ties
+ * broken by longer overlap, lower mismatch rate, smaller vertex1, ori1 true, ori2 true, smaller
+ * pos1, smaller pos2, and -- everything equal -- the later one (:470-521).  That fold keeps, per
+ * key, the LAST maximum of a lexicographic order, so it is a per-key arg-max: here one atomicCAS
+ * loop per edge on a hash table.  The final adjacency lists are the survivors in input order
+ * (a replaced edge is erased and the new one appended, :522-531), so the host only appends
+ * `winner` edges, in order, to adj_out[vertex1].
+ * Records carry the fields AFTER the reference's normalisation (:443-448: if pos1 == 0 and
+ * v1 > v2, the reads are swapped and pos3/pos4 negated).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint32_t vertex1, vertex2;
+    double   score, mismatch_rate;
+    int32_t  pos1, pos2, pos3;
+    int32_t  overlap_len;      /* Edge::get_len(0) = len1 + len2                                   */
+    int32_t  perc;
+    uint8_t  ori1, ori2;
+    uint8_t  reserved[2];
+} hc_dedup_edge;               /* 48 bytes */
+
+/* winner[i] = 1 iff edge i is in the graph after all n edges have been inserted in order.
+ * inclusions (nullable, n_vertices bytes, caller-zeroed) receives OverlapGraph::inclusions as the
+ * reference sets it under ignore_inclusions (:459-468, decided by the FIRST edge of each key).
+ * counts[0] = dup_count increment (:472,:537,:544), counts[1] = inclusion_count increment (:449-451). */
+int hc_dedup_edges(const hc_dedup_edge* edges, uint64_t n, int ignore_inclusions, uint8_t* winner,
+                   uint8_t* inclusions, uint64_t n_vertices, uint64_t counts[2], int device);
+
 int         hc_device_count(void);
 const char* hc_last_error(void);
 const char* hc_version(void);

@@ -43,6 +43,11 @@ def run_case(name: str, rs: F.ReadSet, cands: np.ndarray, ps: dict) -> None:
         ref_cands=out["cands"], ref_graph=out["graph"], ref_nonedge=np.array(out.get("nonedge_lines", []), dtype=object).astype(str),
         ref_counts=np.array([out["graph_edges"], out["dup_count"], out["inclusion_count"]], dtype=np.int64),
     )
+    # the same run under --ignore_inclusions: OverlapGraph::inclusions as EdgeCalculator.cpp:459-468 sets it
+    # (the flag changes nothing else before the graph is handed on, src/ViralQuasispecies.cpp:304)
+    inc = O.run_ref(d, d + "/ov.txt", run=True, dump_graph=True, threads=1, ignore_inclusions=1, **kw, **ps)
+    assert inc["graph"].tobytes() == out["graph"].tobytes()
+    np.savez_compressed(os.path.join(GOLDEN, "insert_" + name + ".npz"), n_vertices=np.int64(rs.n_reads), ref_inclusions=inc["inclusions"])
     cls = np.bincount(out["cands"]["cls"], minlength=3)
     print("%-28s reads=%d cands=%d scored=%d  discard/edge/nonedge=%s graph_edges=%d" %
           (name, rs.n_reads, len(cands), len(out["cands"]), cls.tolist(), out["graph_edges"]))

@@ -112,6 +112,7 @@ def run_ref(workdir: str, overlaps: str, singles: Optional[str] = None, paired1:
         summary["cands"] = parse_cand_dump(os.path.join(workdir, "ref_cands.tsv"))
     if dump_graph:
         summary["graph"] = parse_graph_dump(os.path.join(workdir, "ref_graph.tsv"))
+        summary["inclusions"] = parse_graph_inclusions(os.path.join(workdir, "ref_graph.tsv"))
     if run and os.path.exists(os.path.join(workdir, "nonedge_overlaps.txt")):
         with open(os.path.join(workdir, "nonedge_overlaps.txt")) as f:
             summary["nonedge_lines"] = f.read().split("\n")[:-1]
@@ -150,6 +151,12 @@ def parse_graph_dump(path: str) -> np.ndarray:
             rows.append((int(t[0]), int(t[1]), float.fromhex(t[2]), float.fromhex(t[3]), int(t[4]), int(t[5]), int(t[6]),
                          int(t[7]), int(t[8]), int(t[9]), ord(t[10]) if t[10] else 0, int(t[11]), int(t[12]), int(t[13])))
     return np.array(rows, dtype=REF_EDGE)
+
+
+def parse_graph_inclusions(path: str) -> np.ndarray:
+    """The '#I' lines of a --dump-graph file: vertices with OverlapGraph::inclusions set."""
+    with open(path) as f:
+        return np.array([int(l.split("\t")[1]) for l in f if l.startswith("#I\t")], dtype=np.int64)
 
 
 # ---- FindNextOverlaps (FNO1) ---------------------------------------------------------------------------
@@ -280,3 +287,87 @@ def fno3(fi) -> np.ndarray:
         if rc != -5:
             raise RuntimeError("hco_fno3 failed with %d" % rc)
         cap = int(n.value)
+
+
+# ---- the serial graph insert (src/EdgeCalculator.cpp:429-545) ----------------------------------------------
+def normalise_ref_edges(rc: np.ndarray) -> np.ndarray:
+    """The accepted edges of a reference candidate dump (cls == 1) after the normalisation of :443-448 /
+    Edge::swap_reads (src/Edge.h:74-88), as REF_EDGE rows in input order."""
+    e = np.zeros(int((rc["cls"] == 1).sum()), dtype=REF_EDGE)
+    src = rc[rc["cls"] == 1]
+    for f in REF_EDGE.names:
+        e[f] = src[f]
+    sw = (e["pos1"] == 0) & (e["v1"] > e["v2"])
+    v1, o1 = e["v1"].copy(), e["ori1"].copy()
+    e["v1"][sw], e["v2"][sw] = e["v2"][sw], v1[sw]
+    e["ori1"][sw], e["ori2"][sw] = e["ori2"][sw], o1[sw]
+    od = e["ord"].copy()
+    e["ord"][sw & (od == ord("1"))] = ord("2")
+    e["ord"][sw & (od == ord("2"))] = ord("1")
+    e["pos3"][sw] = -e["pos3"][sw]
+    e["pos4"][sw] = -e["pos4"][sw]
+    return e
+
+
+def graph_insert(e: np.ndarray, n_vertices: int, ignore_inclusions: bool = False):
+    """Sequential restatement of the serial section of EdgeCalculator::process_overlaps
+    (src/EdgeCalculator.cpp:441-545) over normalised REF_EDGE rows: one pass, replace-if-not-worse.
+    Returns (winner flags, inclusions, dup_count, inclusion_count, adjacency-ordered winner indices)."""
+    have = {}                                  # (lo, hi, same_ori) -> index of the edge in the graph
+    inclusions = np.zeros(n_vertices, dtype=np.uint8)
+    dups = incl = 0
+    for i in range(len(e)):
+        x = e[i]
+        v1, v2 = int(x["v1"]), int(x["v2"])
+        if x["perc"] == 100:                                                   # :449-451
+            incl += 1
+        k = (min(v1, v2), max(v1, v2), bool(x["ori1"] == x["ori2"]))
+        if k not in have:                                                      # :455-469
+            have[k] = i
+            if ignore_inclusions and x["perc"] == 100 and 0 <= x["mismatch_rate"] < 0.000001:
+                if x["pos3"] < 0:
+                    if x["pos1"] == 0:
+                        inclusions[v1] = 1
+                else:
+                    inclusions[v2] = 1
+            continue
+        dups += 1                                                              # :472 / :537
+        o = e[have[k]]
+        if x["score"] < o["score"]:
+            continue
+        keep_old = False
+        if x["score"] == o["score"]:                                           # :474-521, first difference decides
+            ol, xl = int(o["len1"]) + int(o["len2"]), int(x["len1"]) + int(x["len2"])
+            if ol != xl:
+                keep_old = ol > xl
+            elif o["mismatch_rate"] != x["mismatch_rate"]:
+                keep_old = o["mismatch_rate"] < x["mismatch_rate"]
+            elif o["v1"] != x["v1"]:
+                keep_old = o["v1"] < x["v1"]
+            elif o["ori1"] != x["ori1"]:
+                keep_old = bool(o["ori1"])
+            elif o["ori2"] != x["ori2"]:
+                keep_old = bool(o["ori2"])
+            elif o["pos1"] != x["pos1"]:
+                keep_old = o["pos1"] < x["pos1"]
+            elif o["pos2"] != x["pos2"]:
+                keep_old = o["pos2"] < x["pos2"]
+        if not keep_old:
+            have[k] = i                                                        # :522-531 erase + append
+    win = np.zeros(len(e), dtype=bool)
+    win[list(have.values())] = True
+    idx = np.nonzero(win)[0]
+    adj = idx[np.argsort(e["v1"][idx], kind="stable")]       # adjacency dump order: by vertex1, then insertion time
+    return win, inclusions, dups, incl, adj
+
+
+def dedup_records(e: np.ndarray) -> np.ndarray:
+    """REF_EDGE rows -> formats.DEDUP_EDGE (hc_dedup_edge) records."""
+    from haploconduct_b200 import formats as F
+
+    d = np.zeros(len(e), dtype=F.DEDUP_EDGE)
+    d["vertex1"], d["vertex2"] = e["v1"], e["v2"]
+    for f in ("score", "mismatch_rate", "pos1", "pos2", "pos3", "perc", "ori1", "ori2"):
+        d[f] = e[f]
+    d["overlap_len"] = e["len1"] + e["len2"]
+    return d

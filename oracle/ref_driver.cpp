@@ -278,6 +278,9 @@ int main(int argc, char** argv) {
                                  it->get_len(1), it->get_len(2));
                 }
             }
+            // OverlapGraph::inclusions (src/OverlapGraph.h:80) as '#I' lines, set only under ignore_inclusions
+            for (size_t v = 0; v < graph->inclusions.size(); v++)
+                if (graph->inclusions[v]) std::fprintf(fo, "#I\t%zu\n", v);
             std::fclose(fo);
         }
     }

@@ -19,12 +19,12 @@ pytestmark = pytest.mark.gpu
 EXE = os.path.join(B.LIBDIR, "hc_edgecalc")
 
 
-def _run(g, tmp_path, exact):
+def _run(g, tmp_path, exact, gpu_dedup=False):
     d = str(tmp_path)
     F.write_fastq_set(g.rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", g.cands, g.rs.ids)
     cmd = [EXE, "--overlaps", d + "/ov.txt", "--dump-graph", d + "/graph.tsv", "--digraph", d + "/digraph.txt",
-           "--exact_scores=" + ("true" if exact else "false")]
+           "--exact_scores=" + ("true" if exact else "false"), "--gpu_dedup=" + ("true" if gpu_dedup else "false")]
     if g.rs.n_single:
         cmd += ["--singles", d + "/s.fastq"]
     if g.rs.n_reads > g.rs.n_single:
@@ -55,6 +55,16 @@ def test_graph_identical_to_reference_exact_scores(built_lib, tmp_path, name):
     assert [summary["graph_edges"], summary["dup_count"], summary["inclusion_count"]] == g.ref_counts.tolist()
     want = "".join("%d\t%d\n" % (a, b) for a, b in zip(g.ref_graph["v1"], g.ref_graph["v2"]))
     assert digraph == want
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_graph_identical_with_device_dedup(built_lib, tmp_path, name):
+    """--gpu_dedup=true: the serial insert (:429-545) replaced by hc_dedup_edges + an ordered append."""
+    g = load_golden(name)
+    summary, graph, nonedge, digraph = _run(g, tmp_path, exact=True, gpu_dedup=True)
+    assert np.array_equal(graph, g.ref_graph), name
+    assert nonedge == g.ref_nonedge
+    assert [summary["graph_edges"], summary["dup_count"], summary["inclusion_count"]] == g.ref_counts.tolist()
 
 
 @pytest.mark.parametrize("name", golden_names())

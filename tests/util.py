@@ -35,7 +35,7 @@ class Golden:
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("fno"))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("fno", "insert_")))
 
 
 def fno_golden_names():
@@ -141,3 +141,39 @@ def assert_results_match(res, ref_score, ref_mm, ref_pos3, ref_pos4, ref_cls, re
     bad = np.nonzero(err > tol)[0]
     assert len(bad) == 0, "%s: %d scores off by more than %g relative, first %s: %s vs %s" % (
         what, len(bad), rel, bad[:5], res["score"][bad[:5]], ref_score[bad[:5]])
+
+
+def load_insert_golden(name):
+    """(n_vertices, vertices the reference marked in OverlapGraph::inclusions under --ignore_inclusions)."""
+    z = np.load(os.path.join(GOLDEN, "insert_" + name + ".npz"), allow_pickle=False)
+    return int(z["n_vertices"]), z["ref_inclusions"]
+
+
+def random_insert_edges(seed, n, n_vertices):
+    """Dense duplicates with many exact ties on every level of the tie-break chain (oracle.REF_EDGE rows)."""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(seed)
+    e = np.zeros(n, dtype=O.REF_EDGE)
+    e["v1"] = rng.integers(0, n_vertices, n)
+    e["v2"] = (e["v1"] + 1 + rng.integers(0, min(4, n_vertices - 1), n)) % n_vertices
+    sw = rng.random(n) < 0.5
+    e["v1"][sw], e["v2"][sw] = e["v2"][sw].copy(), e["v1"][sw].copy()
+    e["score"] = rng.choice([0.97, 0.98, 0.99, 0.99 + 2.0 ** -40], n)
+    e["mismatch_rate"] = rng.choice([0.0, 0.0, 1e-7, 0.01], n)
+    e["pos1"] = rng.choice([0, 0, 5, 9], n)
+    e["pos2"] = rng.choice([0, 3, 7], n)
+    e["pos3"] = rng.choice([-4, 0, 6], n)
+    e["pos4"] = rng.choice([-2, 0, 2], n)
+    e["ori1"] = rng.integers(0, 2, n)
+    e["ori2"] = rng.integers(0, 2, n)
+    e["ord"] = rng.choice([ord("-"), ord("1"), ord("2")], n)
+    e["perc"] = rng.choice([60, 100, 100], n)
+    e["len1"] = rng.choice([100, 120], n)
+    e["len2"] = rng.choice([0, 20], n)
+    # the normalisation of :443-448 on the raw records
+    rc = np.zeros(n, dtype=O.REF_CAND)
+    for f in O.REF_EDGE.names:
+        rc[f] = e[f]
+    rc["cls"] = 1
+    return O.normalise_ref_edges(rc)
