@@ -23,7 +23,7 @@ EXPORTED = [
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
-    "hc_dedup_edges",
+    "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -78,6 +78,14 @@ def lib() -> ctypes.CDLL:
         L.hc_fno3.argtypes = [u64, vp, vp, vp, u64, vp, i32, vp, u64, ctypes.POINTER(u64), i32]
         L.hc_dedup_edges.restype = i32
         L.hc_dedup_edges.argtypes = [vp, u64, i32, vp, vp, u64, vp, i32]
+        L.hc_idmap_create.restype = vp
+        L.hc_idmap_create.argtypes = [vp, u64, i32]
+        L.hc_idmap_destroy.restype = None
+        L.hc_idmap_destroy.argtypes = [vp]
+        L.hc_ingest_overlaps.restype = i32
+        L.hc_ingest_overlaps.argtypes = [vp, vp, u64, vp, vp, vp, u64, vp, vp, u64, vp]
+        L.hc_ingest_overlaps_device.restype = i32
+        L.hc_ingest_overlaps_device.argtypes = [vp, vp, vp, u64, vp, vp, vp, u64, vp, vp, u64, vp]
         L.hc_last_error.restype = ctypes.c_char_p
         L.hc_version.restype = ctypes.c_char_p
         _lib = L
@@ -253,3 +261,49 @@ def dedup_edges(edges: np.ndarray, n_vertices: int, ignore_inclusions: bool = Fa
     _check(lib().hc_dedup_edges(edges.ctypes.data if len(edges) else None, len(edges), int(ignore_inclusions), win.ctypes.data,
                                 inc.ctypes.data, n_vertices, counts.ctypes.data, device))
     return win[: len(edges)].astype(bool), inc[:n_vertices], int(counts[0]), int(counts[1])
+
+
+class IdMap:
+    """hc_idmap: read id -> store index on the device (FastqStorage::m_ID_to_index)."""
+
+    def __init__(self, ids: np.ndarray, device: int = 0):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        self._h = lib().hc_idmap_create(ids.ctypes.data if len(ids) else None, len(ids), device)
+        if not self._h:
+            raise HcError(-1, last_error())
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().hc_idmap_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ingest(self, text: bytes, params: np.ndarray, cand_cap: Optional[int] = None, filtered_cap: Optional[int] = None):
+        """hc_ingest_overlaps on a host buffer of complete lines.
+        Returns (candidates, candidate line numbers, filtered OVERLAP_REC, their line numbers, stats)."""
+        buf = np.frombuffer(text, dtype=np.uint8) if len(text) else np.zeros(0, dtype=np.uint8)
+        guess = int(np.count_nonzero(buf == 10)) + 1
+        ccap = guess if cand_cap is None else cand_cap
+        fcap = guess if filtered_cap is None else filtered_cap
+        cand = np.zeros(max(ccap, 1), dtype=F.CANDIDATE)
+        cl = np.zeros(max(ccap, 1), dtype=np.uint64)
+        filt = np.zeros(max(fcap, 1), dtype=F.OVERLAP_REC)
+        fl = np.zeros(max(fcap, 1), dtype=np.uint64)
+        st = np.zeros(1, dtype=F.INGEST_STATS)
+        rc = lib().hc_ingest_overlaps(self._h, buf.ctypes.data if len(buf) else None, len(buf), params.ctypes.data, cand.ctypes.data,
+                                      cl.ctypes.data, ccap, filt.ctypes.data, fl.ctypes.data, fcap, st.ctypes.data)
+        if rc != 0:
+            err = HcError(rc, last_error())
+            err.required = (int(st[0]["n_scored"]), int(st[0]["n_filtered"]))
+            raise err
+        ns, nf = int(st[0]["n_scored"]), int(st[0]["n_filtered"])
+        return cand[:ns], cl[:ns], filt[:nf], fl[:nf], st[0]

@@ -1,0 +1,545 @@
+// hc_ingest.cu -- candidate ingestion on the device: the text loop of EdgeCalculator::construct_edges
+// (src/EdgeCalculator.cpp:581-645) with the Overlap constructor (src/Overlap.h:39-73) and the
+// id -> index map of FastqStorage (src/FastqStorage.h:90-93, used at src/EdgeCalculator.cpp:164-171).
+// See hc_b200.h for the contract.  Byte work, HBM/L2-bound: newline index (count -> scan -> mark),
+// one thread per line for the field parse, ordered compaction (count -> scan -> scatter).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/hc_b200.h"
+
+void hc_set_last_error(const char* msg);   // hc_api.cu
+
+struct hc_idmap {
+    int device;
+    uint64_t n;        // reads
+    uint64_t mask;     // table size - 1
+    unsigned long long* keys;
+    uint32_t* vals;
+};
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr int TILE = 4096;            // text bytes per block in the newline passes (256 threads x 16 B)
+constexpr int LINES_PER_BLOCK = 1024; // lines per block in the compaction passes
+constexpr u64 EMPTY = ~0ull;
+
+struct IngTmp {            // one parsed line
+    hc_overlap_rec r;
+    uint32_t idx1, idx2;
+};
+
+__device__ __forceinline__ u64 hash64(u64 k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+
+// ---- id map ------------------------------------------------------------------------------------
+__global__ void idmap_insert(const u64* ids, u64 n, u64* keys, uint32_t* vals, u64 mask) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 key = ids[i];
+        u64 h = hash64(key) & mask;
+        while (true) {
+            const u64 prev = atomicCAS(&keys[h], EMPTY, key);
+            if (prev == EMPTY || prev == key) { atomicMin(&vals[h], (uint32_t)i); break; }   // std::map::insert keeps the first
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t idmap_find(const u64* keys, const uint32_t* vals, u64 mask, u64 key) {
+    if (key == EMPTY) return 0xffffffffu;
+    u64 h = hash64(key) & mask;
+    while (true) {
+        const u64 k = keys[h];
+        if (k == key) return vals[h];
+        if (k == EMPTY) return 0xffffffffu;
+        h = (h + 1) & mask;
+    }
+}
+
+// ---- newline index -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nl_mask16(const char* text, u64 n, u64 p) {   // bit b = text[p + b] == '\n'
+    uint32_t m = 0;
+    if (p + 16 <= n && ((reinterpret_cast<uintptr_t>(text) & 15u) == 0)) {
+        const uint4 v = *reinterpret_cast<const uint4*>(text + p);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t x = w[j] ^ 0x0a0a0a0au;                      // zero byte <=> newline
+            uint32_t z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // exact zero-byte detector
+            z = (z >> 7) * 0x00204081u;                                 // gather bits 0,8,16,24 into bits 24..27
+            m |= ((z >> 21) & 0xfu) << (4 * j);
+        }
+    } else {
+        for (int b = 0; b < 16 && p + b < n; b++) m |= (uint32_t)(text[p + b] == '\n') << b;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256) nl_count(const char* text, u64 n, uint32_t* tile_cnt) {
+    const u64 p = (u64)blockIdx.x * TILE + 16ull * threadIdx.x;
+    const int c = p < n ? __popc(nl_mask16(text, n, p)) : 0;
+    __shared__ int wsum[8];
+    int v = c;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; w++) s += wsum[w];
+        tile_cnt[blockIdx.x] = (uint32_t)s;
+    }
+}
+
+// single-block exclusive scan of uint32 counts -> u64 offsets (the inputs are per-tile / per-block counts)
+__global__ void __launch_bounds__(1024) scan_counts(const uint32_t* in, u64 n, u64* out, u64* total) {
+    __shared__ u64 wsum[32];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (u64 b0 = 0; b0 < n; b0 += 1024) {
+        const u64 i = b0 + threadIdx.x;
+        const u64 v = i < n ? in[i] : 0;
+        u64 inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const u64 w = wsum[lane];
+            u64 s = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 t = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += t;
+            }
+            wsum[lane] = s - w;
+        }
+        __syncthreads();
+        const u64 c = carry;
+        if (i < n) out[i] = c + wsum[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wsum[31] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// line_start[k + 1] = offset behind the k-th newline (line_start[0] = 0 is set by the host)
+__global__ void __launch_bounds__(256) nl_mark(const char* text, u64 n, const u64* tile_off, u64* line_start) {
+    const u64 p = (u64)blockIdx.x * TILE + 16ull * threadIdx.x;
+    const uint32_t m = p < n ? nl_mask16(text, n, p) : 0u;
+    const int c = __popc(m);
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; w++) base += wsum[w];
+    u64 k = tile_off[blockIdx.x] + (u64)(base + inc - c);
+    uint32_t mm = m;
+    while (mm) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        line_start[++k] = p + b + 1;
+    }
+}
+
+// ---- field parsers (glibc semantics of what src/Types.h:99-102 and src/Overlap.h:42-50 call) -----
+__device__ __forceinline__ bool c_isspace(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+// strtoul(s, NULL, 0) on the field [p, q)
+__device__ u64 dev_strtoul0(const char* t, u64 p, u64 q) {
+    while (p < q && c_isspace(t[p])) p++;
+    bool neg = false;
+    if (p < q && (t[p] == '+' || t[p] == '-')) { neg = t[p] == '-'; p++; }
+    int base = 10;
+    if (p < q && t[p] == '0') {
+        if (p + 2 < q + 0 && (t[p + 1] == 'x' || t[p + 1] == 'X')) {
+            const char h = t[p + 2];
+            if ((h >= '0' && h <= '9') || (h >= 'a' && h <= 'f') || (h >= 'A' && h <= 'F')) { base = 16; p += 2; }
+            else base = 8;      // "0x" without a hex digit: the "0" is the number
+        } else base = 8;
+    }
+    u64 v = 0;
+    bool ovf = false;
+    for (; p < q; p++) {
+        const char c = t[p];
+        int d;
+        if (c >= '0' && c <= '9') d = c - '0';
+        else if (c >= 'a' && c <= 'z') d = c - 'a' + 10;
+        else if (c >= 'A' && c <= 'Z') d = c - 'A' + 10;
+        else break;
+        if (d >= base) break;
+        if (v > (~0ull - (u64)d) / (u64)base) ovf = true;
+        v = v * (u64)base + (u64)d;
+    }
+    if (ovf) return ~0ull;                     // ULONG_MAX, whatever the sign
+    return neg ? 0ull - v : v;
+}
+
+// (unsigned int)atoi(s) = (unsigned int)(int)strtol(s, NULL, 10) on the field [p, q)
+__device__ uint32_t dev_atoi(const char* t, u64 p, u64 q) {
+    while (p < q && c_isspace(t[p])) p++;
+    bool neg = false;
+    if (p < q && (t[p] == '+' || t[p] == '-')) { neg = t[p] == '-'; p++; }
+    u64 v = 0;
+    bool ovf = false;
+    const u64 lim = neg ? 0x8000000000000000ull : 0x7fffffffffffffffull;
+    for (; p < q; p++) {
+        const char c = t[p];
+        if (c < '0' || c > '9') break;
+        const u64 d = (u64)(c - '0');
+        if (!ovf && v > (lim - d) / 10ull) ovf = true;
+        if (!ovf) v = v * 10ull + d;
+    }
+    long long r;
+    if (ovf) r = neg ? (long long)0x8000000000000000ull : 0x7fffffffffffffffll;
+    else r = neg ? -(long long)v : (long long)v;
+    return (uint32_t)(int)r;
+}
+
+// one-character fields: ORI / ORD strip ' ' when the length is not 1 (src/Overlap.h:115-118,127-130), TYPE strips
+// '\n', '\t', ' ' (:152-156); the result must be one character (assert) -- returns 0 when it is not
+__device__ char dev_char_field(const char* t, u64 p, u64 q, bool is_type) {
+    if (q - p == 1) return t[p];
+    char out = 0;
+    int cnt = 0;
+    for (; p < q; p++) {
+        const char c = t[p];
+        const bool strip = c == ' ' || (is_type && (c == '\n' || c == '\t'));
+        if (!strip) { out = c; cnt++; }
+    }
+    return cnt == 1 ? out : (char)0;
+}
+
+struct IngDev {
+    const char* text;
+    u64 n_bytes;
+    const u64* line_start;
+    u64 n_lines;           // lines considered (already clamped to max_overlaps)
+    u64 n_newlines;
+    const u64* keys;
+    const uint32_t* vals;
+    u64 mask;
+    uint32_t min_overlap_len, min_overlap_perc;
+    int relax, allow_spaces;
+};
+
+// src/EdgeCalculator.cpp:583-635 for line i; fills tmp and returns the status
+__device__ uint8_t parse_line(const IngDev& D, u64 i, IngTmp& o) {
+    const char* t = D.text;
+    u64 s = D.line_start[i];
+    u64 e = i < D.n_newlines ? D.line_start[i + 1] - 1 : D.n_bytes;    // without the '\n'
+    while (s < e && (t[s] == '\t' || t[s] == ' ')) s++;                // trim_if(is_any_of("\t ")), :584
+    while (e > s && (t[e - 1] == '\t' || t[e - 1] == ' ')) e--;
+    if (s == e) return HC_LINE_SKIPPED;                                // no token at all
+    u64 id1 = 0, id2 = 0;
+    uint32_t num[6] = {0, 0, 0, 0, 0, 0};       // pos1 pos2 perc1 perc2 len1 len2
+    char ch[5] = {0, 0, 0, 0, 0};               // ord ori1 ori2 type1 type2
+    bool dash3 = false;
+    uint32_t nf = 0;
+    u64 p = s;
+    while (true) {
+        u64 q = p;
+        if (D.allow_spaces) while (q < e && t[q] != '\t' && t[q] != ' ') q++;
+        else while (q < e && t[q] != '\t') q++;
+        switch (nf) {
+            case 0: id1 = dev_strtoul0(t, p, q); break;
+            case 1: id2 = dev_strtoul0(t, p, q); break;
+            case 2: num[0] = dev_atoi(t, p, q); break;
+            case 3: num[1] = dev_atoi(t, p, q); dash3 = (q - p == 1) && t[p] == '-'; break;
+            case 4: ch[0] = dev_char_field(t, p, q, false); break;
+            case 5: ch[1] = dev_char_field(t, p, q, false); break;
+            case 6: ch[2] = dev_char_field(t, p, q, false); break;
+            case 7: num[2] = dev_atoi(t, p, q); break;
+            case 8: num[3] = dev_atoi(t, p, q); break;
+            case 9: num[4] = dev_atoi(t, p, q); break;
+            case 10: num[5] = dev_atoi(t, p, q); break;
+            case 11: ch[3] = dev_char_field(t, p, q, true); break;
+            case 12: ch[4] = dev_char_field(t, p, q, true); break;
+            default: break;
+        }
+        nf++;
+        if (q >= e) break;
+        p = q + 1;
+        if (D.allow_spaces) while (p < e && (t[p] == '\t' || t[p] == ' ')) p++;   // token_compress_on
+    }
+    if (nf != 13) return HC_LINE_SKIPPED;                              // :598-603
+    if (dash3) { num[1] = 0; num[3] = 0; num[5] = 0; }                 // src/Overlap.h:55-59
+    // the constructor's checks (:60-72); any failure ends the reference run
+    bool bad = (int)num[0] < 0 || (int)num[1] < 0;                                         // check_pos
+    bad |= (ch[1] != '+' && ch[1] != '-') || (ch[2] != '+' && ch[2] != '-');               // check_ori
+    bad |= (int)num[2] < 0 || (int)num[2] > 100 || (int)num[3] < 0 || (int)num[3] > 100;   // check_perc
+    bad |= (int)num[4] < 0 || (int)num[5] < 0;                                             // check_len
+    bad |= (ch[3] != 's' && ch[3] != 'p') || (ch[4] != 's' && ch[4] != 'p');               // check_type
+    if (!bad) {                                                                            // check_ord
+        if (ch[3] == 's' || ch[4] == 's') bad = ch[0] != '-';
+        else bad = ch[0] != '1' && ch[0] != '2';
+    }
+    if (bad) return HC_LINE_ERROR;
+    o.r.id1 = id1; o.r.id2 = id2;
+    o.r.pos1 = num[0]; o.r.pos2 = num[1]; o.r.perc1 = num[2]; o.r.perc2 = num[3]; o.r.len1 = num[4]; o.r.len2 = num[5];
+    o.r.ord = (uint8_t)ch[0]; o.r.ori1 = (uint8_t)ch[1]; o.r.ori2 = (uint8_t)ch[2]; o.r.type1 = (uint8_t)ch[3]; o.r.type2 = (uint8_t)ch[4];
+    o.r.reserved[0] = o.r.reserved[1] = o.r.reserved[2] = 0;
+    o.idx1 = o.idx2 = 0xffffffffu;
+    if (id1 == id2) return HC_LINE_DROPPED;                            // :605-607
+    const uint32_t perc = num[3] > 0 ? (uint32_t)(0.5 * (double)(num[2] + num[3])) : num[2];   // Overlap::get_perc, :203-210
+    const bool any_p = ch[3] == 'p' || ch[4] == 'p';
+    const double half = 0.5 * (double)D.min_overlap_len;
+    bool in_band;
+    if (num[4] >= D.min_overlap_len && !any_p) in_band = true;                                      // :612-617
+    else if ((double)num[4] >= half && (double)num[5] >= half && any_p) in_band = true;             // :618-624
+    else in_band = D.relax && (uint32_t)(num[4] + num[5]) >= D.min_overlap_len && any_p;            // :626-632
+    if (!in_band) return HC_LINE_NONEDGE;                                                           // :633-635
+    if (perc < D.min_overlap_perc) return HC_LINE_DROPPED;
+    o.idx1 = idmap_find(D.keys, D.vals, D.mask, id1);
+    o.idx2 = idmap_find(D.keys, D.vals, D.mask, id2);
+    if (o.idx1 == 0xffffffffu || o.idx2 == 0xffffffffu) return HC_LINE_UNKNOWN_ID;                  // map::at throws, :170-171
+    return HC_LINE_SCORE;
+}
+
+__global__ void __launch_bounds__(256) ing_parse(IngDev D, IngTmp* tmp, uint8_t* status, u64* first_error) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.n_lines) return;
+    IngTmp o;
+    const uint8_t st = parse_line(D, i, o);
+    status[i] = st;
+    if (st == HC_LINE_SCORE || st == HC_LINE_NONEDGE) tmp[i] = o;
+    if (st == HC_LINE_ERROR || st == HC_LINE_UNKNOWN_ID) atomicMin(first_error, i);
+}
+
+// per block of LINES_PER_BLOCK lines: number of scored and of filtered lines
+__global__ void __launch_bounds__(LINES_PER_BLOCK) ing_count(const uint8_t* status, u64 n, uint32_t* cnt_s, uint32_t* cnt_f,
+                                                             u64* by_status) {
+    const u64 i = (u64)blockIdx.x * LINES_PER_BLOCK + threadIdx.x;
+    const uint8_t st = i < n ? status[i] : 0;
+    const int a = __syncthreads_count(st == HC_LINE_SCORE);
+    const int b = __syncthreads_count(st == HC_LINE_NONEDGE);
+    const int c = __syncthreads_count(st == HC_LINE_SKIPPED);
+    const int d = __syncthreads_count(st == HC_LINE_DROPPED);
+    if (threadIdx.x == 0) {
+        cnt_s[blockIdx.x] = (uint32_t)a;
+        cnt_f[blockIdx.x] = (uint32_t)b;
+        if (c) atomicAdd(&by_status[0], (u64)c);
+        if (d) atomicAdd(&by_status[1], (u64)d);
+    }
+}
+
+__global__ void __launch_bounds__(LINES_PER_BLOCK) ing_scatter(const uint8_t* status, const IngTmp* tmp, u64 n, const u64* off_s,
+                                                               const u64* off_f, hc_candidate* cand, u64* cand_line,
+                                                               hc_overlap_rec* filt, u64* filt_line) {
+    __shared__ uint32_t ws[32], wf[32];
+    const u64 i = (u64)blockIdx.x * LINES_PER_BLOCK + threadIdx.x;
+    const uint8_t st = i < n ? status[i] : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bs = __ballot_sync(0xffffffffu, st == HC_LINE_SCORE), bf = __ballot_sync(0xffffffffu, st == HC_LINE_NONEDGE);
+    if (lane == 0) { ws[warp] = __popc(bs); wf[warp] = __popc(bf); }
+    __syncthreads();
+    uint32_t ps = 0, pf = 0;
+    for (int w = 0; w < warp; w++) { ps += ws[w]; pf += wf[w]; }
+    const uint32_t lt = (1u << lane) - 1u;
+    if (st == HC_LINE_SCORE) {
+        const u64 k = off_s[blockIdx.x] + ps + __popc(bs & lt);
+        const IngTmp t = tmp[i];
+        hc_candidate c;
+        c.idx1 = t.idx1; c.idx2 = t.idx2; c.pos1 = t.r.pos1; c.pos2 = t.r.pos2; c.len1 = t.r.len1; c.len2 = t.r.len2;
+        c.perc1 = (uint8_t)t.r.perc1; c.perc2 = (uint8_t)t.r.perc2; c.ord = t.r.ord;
+        c.ori1 = t.r.ori1 == '+'; c.ori2 = t.r.ori2 == '+'; c.type1 = t.r.type1; c.type2 = t.r.type2; c.reserved = 0;
+        cand[k] = c;
+        if (cand_line) cand_line[k] = i;
+    } else if (st == HC_LINE_NONEDGE) {
+        const u64 k = off_f[blockIdx.x] + pf + __popc(bf & lt);
+        filt[k] = tmp[i].r;
+        if (filt_line) filt_line[k] = i;
+    }
+}
+
+}  // namespace
+
+#define ICU(call)                                                                            \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            hc_set_last_error((std::string(#call) + ": " + cudaGetErrorString(_e)).c_str()); \
+            rc = HC_ERR_CUDA;                                                                \
+            goto done;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+extern "C" hc_idmap* hc_idmap_create(const uint64_t* ids, uint64_t n_reads, int device) {
+    if (n_reads && !ids) { hc_set_last_error("hc_idmap_create: NULL ids"); return nullptr; }
+    if (n_reads >= 0xffffffffull) { hc_set_last_error("hc_idmap_create: too many reads"); return nullptr; }
+    hc_idmap* m = new hc_idmap();
+    m->device = device; m->n = n_reads; m->keys = nullptr; m->vals = nullptr;
+    u64 cap = 64;
+    while (cap < 2 * n_reads + 2) cap <<= 1;
+    m->mask = cap - 1;
+    int rc = HC_OK;
+    u64* d_ids = nullptr;
+    ICU(cudaSetDevice(device));
+    ICU(cudaMalloc(&m->keys, cap * sizeof(u64)));
+    ICU(cudaMalloc(&m->vals, cap * sizeof(uint32_t)));
+    ICU(cudaMemset(m->keys, 0xff, cap * sizeof(u64)));
+    ICU(cudaMemset(m->vals, 0xff, cap * sizeof(uint32_t)));
+    if (n_reads) {
+        ICU(cudaMalloc(&d_ids, n_reads * sizeof(u64)));
+        ICU(cudaMemcpy(d_ids, ids, n_reads * sizeof(u64), cudaMemcpyHostToDevice));
+        idmap_insert<<<(int)std::min<u64>((n_reads + 255) / 256, 148 * 16), 256>>>(d_ids, n_reads, m->keys, m->vals, m->mask);
+        ICU(cudaGetLastError());
+        ICU(cudaDeviceSynchronize());
+    }
+done:
+    cudaFree(d_ids);
+    if (rc != HC_OK) { cudaFree(m->keys); cudaFree(m->vals); delete m; return nullptr; }
+    return m;
+}
+
+extern "C" void hc_idmap_destroy(hc_idmap* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->keys);
+    cudaFree(m->vals);
+    delete m;
+}
+
+// Device-side core: text already on the device.  Outputs are device buffers; counts[0..1] land in host memory.
+static int ingest_device(const hc_idmap* m, const char* d_text, u64 n_bytes, const hc_ingest_params* p, hc_candidate* d_cand,
+                         uint64_t* d_cand_line, u64 cand_cap, hc_overlap_rec* d_filt, uint64_t* d_filt_line, u64 filt_cap,
+                         hc_ingest_stats* st, cudaStream_t stream) {
+    int rc = HC_OK;
+    const u64 n_tiles = (n_bytes + TILE - 1) / TILE;
+    uint32_t *d_tcnt = nullptr, *d_cs = nullptr, *d_cf = nullptr;
+    u64 *d_toff = nullptr, *d_tot = nullptr, *d_ls = nullptr, *d_os = nullptr, *d_of = nullptr, *d_misc = nullptr;
+    IngTmp* d_tmp = nullptr;
+    uint8_t* d_status = nullptr;
+    u64 n_nl = 0, n_lines = 0, n_blocks = 0, misc[3] = {0, 0, EMPTY}, tot_s = 0, tot_f = 0;
+    char last = '\n';
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    IngDev D;
+    memset(st, 0, sizeof(*st));
+    st->first_error_line = EMPTY;
+    if (n_bytes == 0) return HC_OK;
+    ICU(cudaEventCreate(&e0)); ICU(cudaEventCreate(&e1));
+    ICU(cudaMalloc(&d_tcnt, n_tiles * sizeof(uint32_t)));
+    ICU(cudaMalloc(&d_toff, n_tiles * sizeof(u64)));
+    ICU(cudaMalloc(&d_tot, 2 * sizeof(u64)));
+    ICU(cudaEventRecord(e0, stream));
+    nl_count<<<(unsigned)n_tiles, 256, 0, stream>>>(d_text, n_bytes, d_tcnt);
+    scan_counts<<<1, 1024, 0, stream>>>(d_tcnt, n_tiles, d_toff, d_tot);
+    ICU(cudaMemcpyAsync(&n_nl, d_tot, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    ICU(cudaMemcpyAsync(&last, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, stream));
+    ICU(cudaStreamSynchronize(stream));
+    n_lines = n_nl + (last != '\n' ? 1 : 0);          // getline also returns an unterminated last line
+    ICU(cudaMalloc(&d_ls, (n_nl + 2) * sizeof(u64)));
+    ICU(cudaMemsetAsync(d_ls, 0, sizeof(u64), stream));
+    nl_mark<<<(unsigned)n_tiles, 256, 0, stream>>>(d_text, n_bytes, d_toff, d_ls);
+    if (n_lines > p->max_overlaps) n_lines = p->max_overlaps;   // while (getline(...) && i < max_overlaps), :581
+    st->n_lines = n_lines;
+    if (n_lines == 0) { ICU(cudaStreamSynchronize(stream)); goto done; }
+    n_blocks = (n_lines + LINES_PER_BLOCK - 1) / LINES_PER_BLOCK;
+    ICU(cudaMalloc(&d_tmp, n_lines * sizeof(IngTmp)));
+    ICU(cudaMalloc(&d_status, n_lines));
+    ICU(cudaMalloc(&d_cs, n_blocks * sizeof(uint32_t))); ICU(cudaMalloc(&d_cf, n_blocks * sizeof(uint32_t)));
+    ICU(cudaMalloc(&d_os, n_blocks * sizeof(u64))); ICU(cudaMalloc(&d_of, n_blocks * sizeof(u64)));
+    ICU(cudaMalloc(&d_misc, 3 * sizeof(u64)));
+    ICU(cudaMemcpyAsync(d_misc, misc, sizeof(misc), cudaMemcpyHostToDevice, stream));
+    D.text = d_text; D.n_bytes = n_bytes; D.line_start = d_ls; D.n_lines = n_lines; D.n_newlines = n_nl;
+    D.keys = m->keys; D.vals = m->vals; D.mask = m->mask;
+    D.min_overlap_len = p->min_overlap_len; D.min_overlap_perc = p->min_overlap_perc; D.relax = p->relax_PE_edges != 0;
+    D.allow_spaces = p->allow_spaces != 0;
+    ing_parse<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>(D, d_tmp, d_status, d_misc + 2);
+    ing_count<<<(unsigned)n_blocks, LINES_PER_BLOCK, 0, stream>>>(d_status, n_lines, d_cs, d_cf, d_misc);
+    scan_counts<<<1, 1024, 0, stream>>>(d_cs, n_blocks, d_os, d_tot);
+    scan_counts<<<1, 1024, 0, stream>>>(d_cf, n_blocks, d_of, d_tot + 1);
+    ICU(cudaMemcpyAsync(misc, d_misc, sizeof(misc), cudaMemcpyDeviceToHost, stream));
+    ICU(cudaMemcpyAsync(&tot_s, d_tot, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    ICU(cudaMemcpyAsync(&tot_f, d_tot + 1, sizeof(u64), cudaMemcpyDeviceToHost, stream));
+    ICU(cudaStreamSynchronize(stream));
+    st->n_scored = tot_s; st->n_filtered = tot_f; st->n_skipped = misc[0]; st->n_dropped = misc[1];
+    st->first_error_line = misc[2];
+    if (misc[2] != EMPTY) {
+        uint8_t es = 0;
+        u64 off[2] = {0, 0};
+        ICU(cudaMemcpy(&es, d_status + misc[2], 1, cudaMemcpyDeviceToHost));
+        ICU(cudaMemcpy(off, d_ls + misc[2], (misc[2] < n_nl ? 2 : 1) * sizeof(u64), cudaMemcpyDeviceToHost));
+        st->first_error_status = es;
+        st->first_error_offset = off[0];
+        st->first_error_length = (misc[2] < n_nl ? off[1] - 1 : n_bytes) - off[0];
+    }
+    if (tot_s > cand_cap || tot_f > filt_cap) {
+        hc_set_last_error("hc_ingest_overlaps: output buffer too small (required sizes returned in stats)");
+        rc = HC_ERR_CAPACITY;
+        goto done;
+    }
+    ing_scatter<<<(unsigned)n_blocks, LINES_PER_BLOCK, 0, stream>>>(d_status, d_tmp, n_lines, d_os, d_of, d_cand,
+                                                                    reinterpret_cast<u64*>(d_cand_line), d_filt,
+                                                                    reinterpret_cast<u64*>(d_filt_line));
+    ICU(cudaEventRecord(e1, stream));
+    ICU(cudaStreamSynchronize(stream));
+    ICU(cudaGetLastError());
+    ICU(cudaEventElapsedTime(&st->device_ms, e0, e1));
+done:
+    cudaFree(d_tcnt); cudaFree(d_toff); cudaFree(d_tot); cudaFree(d_ls); cudaFree(d_tmp); cudaFree(d_status);
+    cudaFree(d_cs); cudaFree(d_cf); cudaFree(d_os); cudaFree(d_of); cudaFree(d_misc);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}
+
+extern "C" int hc_ingest_overlaps_device(const hc_idmap* m, void* stream, const char* d_text, uint64_t n_bytes,
+                                         const hc_ingest_params* p, hc_candidate* d_cand, uint64_t* d_cand_line, uint64_t cand_cap,
+                                         hc_overlap_rec* d_filtered, uint64_t* d_filtered_line, uint64_t filtered_cap,
+                                         hc_ingest_stats* stats) {
+    if (!m || !p || !stats || (n_bytes && !d_text)) { hc_set_last_error("hc_ingest_overlaps_device: NULL argument"); return HC_ERR_ARG; }
+    if (cudaSetDevice(m->device) != cudaSuccess) { hc_set_last_error("hc_ingest_overlaps_device: cudaSetDevice failed"); return HC_ERR_CUDA; }
+    return ingest_device(m, d_text, n_bytes, p, d_cand, d_cand_line, cand_cap, d_filtered, d_filtered_line, filtered_cap, stats,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int hc_ingest_overlaps(const hc_idmap* m, const char* text, uint64_t n_bytes, const hc_ingest_params* p,
+                                  hc_candidate* cand, uint64_t* cand_line, uint64_t cand_cap, hc_overlap_rec* filtered,
+                                  uint64_t* filtered_line, uint64_t filtered_cap, hc_ingest_stats* stats) {
+    if (!m || !p || !stats || (n_bytes && !text)) { hc_set_last_error("hc_ingest_overlaps: NULL argument"); return HC_ERR_ARG; }
+    int rc = HC_OK;
+    char* d_text = nullptr;
+    hc_candidate* d_cand = nullptr;
+    hc_overlap_rec* d_filt = nullptr;
+    uint64_t *d_cl = nullptr, *d_fl = nullptr;
+    memset(stats, 0, sizeof(*stats));
+    stats->first_error_line = EMPTY;
+    if (n_bytes == 0) return HC_OK;
+    ICU(cudaSetDevice(m->device));
+    ICU(cudaMalloc(&d_text, n_bytes + 16));
+    ICU(cudaMemcpy(d_text, text, n_bytes, cudaMemcpyHostToDevice));
+    if (cand_cap) { ICU(cudaMalloc(&d_cand, cand_cap * sizeof(hc_candidate))); if (cand_line) ICU(cudaMalloc(&d_cl, cand_cap * sizeof(u64))); }
+    if (filtered_cap) { ICU(cudaMalloc(&d_filt, filtered_cap * sizeof(hc_overlap_rec))); if (filtered_line) ICU(cudaMalloc(&d_fl, filtered_cap * sizeof(u64))); }
+    rc = ingest_device(m, d_text, n_bytes, p, d_cand, d_cl, cand_cap, d_filt, d_fl, filtered_cap, stats, 0);
+    if (rc != HC_OK) goto done;
+    if (stats->n_scored) {
+        ICU(cudaMemcpy(cand, d_cand, stats->n_scored * sizeof(hc_candidate), cudaMemcpyDeviceToHost));
+        if (cand_line) ICU(cudaMemcpy(cand_line, d_cl, stats->n_scored * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    if (stats->n_filtered) {
+        ICU(cudaMemcpy(filtered, d_filt, stats->n_filtered * sizeof(hc_overlap_rec), cudaMemcpyDeviceToHost));
+        if (filtered_line) ICU(cudaMemcpy(filtered_line, d_fl, stats->n_filtered * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+done:
+    cudaFree(d_text); cudaFree(d_cand); cudaFree(d_filt); cudaFree(d_cl); cudaFree(d_fl);
+    return rc;
+}

@@ -75,6 +75,39 @@ DEDUP_EDGE = np.dtype([("vertex1", "<u4"), ("vertex2", "<u4"), ("score", "<f8"),
                        ("pos2", "<i4"), ("pos3", "<i4"), ("overlap_len", "<i4"), ("perc", "<i4"), ("ori1", "u1"), ("ori2", "u1"),
                        ("reserved", "u1", (2,))])
 assert DEDUP_EDGE.itemsize == 48
+INGEST_PARAMS = np.dtype([("max_overlaps", "<u8"), ("min_overlap_len", "<u4"), ("min_overlap_perc", "<u4"), ("relax_PE_edges", "u1"),
+                          ("allow_spaces", "u1"), ("reserved", "u1", (6,))])
+OVERLAP_REC = np.dtype([("id1", "<u8"), ("id2", "<u8"), ("pos1", "<u4"), ("pos2", "<u4"), ("perc1", "<u4"), ("perc2", "<u4"),
+                        ("len1", "<u4"), ("len2", "<u4"), ("ord", "u1"), ("ori1", "u1"), ("ori2", "u1"), ("type1", "u1"),
+                        ("type2", "u1"), ("reserved", "u1", (3,))])
+INGEST_STATS = np.dtype([("n_lines", "<u8"), ("n_scored", "<u8"), ("n_filtered", "<u8"), ("n_skipped", "<u8"), ("n_dropped", "<u8"),
+                         ("first_error_line", "<u8"), ("first_error_offset", "<u8"), ("first_error_length", "<u8"),
+                         ("first_error_status", "<u4"), ("device_ms", "<f4")])
+assert INGEST_PARAMS.itemsize == 24 and OVERLAP_REC.itemsize == 48 and INGEST_STATS.itemsize == 72
+LINE_SCORE, LINE_NONEDGE, LINE_DROPPED, LINE_SKIPPED, LINE_ERROR, LINE_UNKNOWN_ID = 1, 2, 3, 4, 5, 6
+
+
+def make_ingest_params(min_overlap_len: int, min_overlap_perc: int = 0, relax_PE_edges: bool = False, allow_spaces: bool = False,
+                       max_overlaps: int = 2 ** 64 - 1) -> np.ndarray:
+    p = np.zeros(1, dtype=INGEST_PARAMS)
+    p["max_overlaps"], p["min_overlap_len"], p["min_overlap_perc"] = max_overlaps, min_overlap_len, min_overlap_perc
+    p["relax_PE_edges"], p["allow_spaces"] = int(relax_PE_edges), int(allow_spaces)
+    return p
+
+
+def overlap_rec_lines(recs: np.ndarray) -> list:
+    """Overlap::get_overlap_line (src/Overlap.h:234-237) of OVERLAP_REC records, without the newline."""
+    return ["%d\t%d\t%d\t%d\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%s" % (
+        int(r["id1"]), int(r["id2"]), int(r["pos1"]), int(r["pos2"]), chr(r["ord"]), chr(r["ori1"]), chr(r["ori2"]), int(r["perc1"]),
+        int(r["perc2"]), int(r["len1"]), int(r["len2"]), chr(r["type1"]), chr(r["type2"])) for r in recs]
+
+
+def candidate_lines(cands: np.ndarray, ids: np.ndarray) -> list:
+    """The same line for CANDIDATE records (ids through the store's id table)."""
+    return ["%d\t%d\t%d\t%d\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%s" % (
+        int(ids[c["idx1"]]), int(ids[c["idx2"]]), int(c["pos1"]), int(c["pos2"]), chr(c["ord"]), "+" if c["ori1"] else "-",
+        "+" if c["ori2"] else "-", int(c["perc1"]), int(c["perc2"]), int(c["len1"]), int(c["len2"]), chr(c["type1"]), chr(c["type2"]))
+        for c in cands]
 assert FNO_EDGE.itemsize == 32 and FNO_READ.itemsize == 16 and FNO_SUBREAD.itemsize == 16 and FNO_OVERLAP.itemsize == 48
 
 CLASS_DISCARD, CLASS_EDGE, CLASS_NONEDGE = 0, 1, 2

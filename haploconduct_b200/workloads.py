@@ -370,3 +370,99 @@ def geometry_candidates(ss: SynthSet, n_target: int = 4000, seed: int = 11, junk
             cand = tuple(c)
         out.append(cand)
     return np.array(out, dtype=CANDIDATE)
+
+
+# ---- irregular overlaps-file text (ingestion tests) ---------------------------------------------------
+def fuzz_overlap_text(cands: np.ndarray, ids: np.ndarray, seed: int = 5, allow_spaces: bool = False, junk: bool = True,
+                      self_fraction: float = 0.03) -> bytes:
+    """The candidates as overlaps-file lines in every spelling the reference's parser accepts
+    (src/Overlap.h:39-73 over strtoul(s, NULL, 0) / atoi): hex / octal / signed / space-padded ids, zero-padded
+    numbers, numbers with trailing junk, empty numeric fields for 0, '-' for POS2/PERC2/LEN2, space-decorated
+    ORD/ORI/TYPE, outer tabs and spaces; plus lines the loop skips (blank, 12 or 14 fields) and self overlaps.
+    No line makes the reference exit."""
+    rng = np.random.RandomState(seed)
+
+    def ident(v: int) -> str:
+        k = rng.randint(0, 8)
+        if allow_spaces:
+            k = k if k not in (3, 4) else 0
+        if k == 1:
+            return hex(v)
+        if k == 2:
+            return "0" + oct(v)[2:] if v else "0"
+        if k == 3:
+            return " " + str(v)
+        if k == 4:
+            return str(v) + " x"
+        if k == 5:
+            return "+" + str(v)
+        if k == 6:
+            return "0X%X" % v
+        return str(v)
+
+    def num(v: int, may_empty: bool = True) -> str:
+        k = rng.randint(0, 8)
+        if allow_spaces:
+            k = k if k not in (2, 5) else 0
+        if k == 1:
+            return "00" + str(v)
+        if k == 2:
+            return " " + str(v)
+        if k == 3:
+            return str(v) + "abc"
+        if k == 4:
+            return "+" + str(v)
+        if k == 5 and v == 0 and may_empty:
+            return ""
+        if k == 6:
+            return str(v) + ".7"
+        return str(v)
+
+    def ch(c: str) -> str:
+        if allow_spaces:
+            return c
+        return [c, c, c, " " + c, c + " ", " " + c + "  "][rng.randint(0, 6)]
+
+    out = []
+    for c in cands:
+        i1, i2 = int(ids[c["idx1"]]), int(ids[c["idx2"]])
+        if rng.rand() < self_fraction:
+            i2 = i1
+        ss = c["type1"] == ord("s") and c["type2"] == ord("s")
+        dash = ss and int(c["pos2"]) == 0 and rng.rand() < 0.6
+        f = [ident(i1), ident(i2), num(int(c["pos1"]), False), "-" if dash else num(int(c["pos2"])), ch(chr(c["ord"])),
+             ch("+" if c["ori1"] else "-"), ch("+" if c["ori2"] else "-"), num(int(c["perc1"])),
+             (["-", "7", "55"][rng.randint(0, 3)] if dash else num(int(c["perc2"]))), num(int(c["len1"])),
+             (["-", "9", "120"][rng.randint(0, 3)] if dash else num(int(c["len2"]))), ch(chr(c["type1"])), ch(chr(c["type2"]))]
+        if allow_spaces:
+            f = [x if x != "" else "0" for x in f]
+            seps = ["\t", " ", "  ", "\t\t", " \t "]
+            line = f[0]
+            for x in f[1:]:
+                line += seps[rng.randint(0, len(seps))] + x
+        else:
+            line = "\t".join(f)
+        k = rng.randint(0, 10)
+        if k == 0:
+            line = "\t" + line
+        elif k == 1:
+            line = "  " + line + " \t"
+        elif k == 2:
+            line = line + "\t\t"
+        out.append(line)
+        if junk:
+            k = rng.randint(0, 40)
+            if k == 0:
+                out.append("")
+            elif k == 1:
+                out.append(" \t ")
+            elif k == 2:
+                out.append("\t".join(f[:12]))
+            elif k == 3:
+                out.append("\t".join(f + ["x"]))
+            elif k == 4:
+                out.append("# comment")
+    text = "\n".join(out)
+    if rng.rand() < 0.5:
+        text += "\n"
+    return text.encode()

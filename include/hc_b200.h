@@ -322,6 +322,75 @@ typedef struct {
 int hc_dedup_edges(const hc_dedup_edge* edges, uint64_t n, int ignore_inclusions, uint8_t* winner,
                    uint8_t* inclusions, uint64_t n_vertices, uint64_t counts[2], int device);
 
+/* ------------------------------------------------------------------------------------------
+ * Candidate ingestion (second "next" row): the text loop of
+ * EdgeCalculator::construct_edges, src/EdgeCalculator.cpp:581-645, on the device.
+ *
+ * Input is a buffer of complete lines of the 13-column overlaps file.  Every line is trimmed of
+ * outer tabs/spaces (:584), split on tabs (or, with allow_spaces, on runs of tabs/spaces, :585-587),
+ * must have 13 fields (:598-603), goes through the Overlap constructor (src/Overlap.h:39-73: ids by
+ * strtoul(s, NULL, 0), numbers by atoi, "-" in POS2 zeroes POS2/PERC2/LEN2, ORD/ORI/TYPE stripped of
+ * spaces when longer than one character), the self-overlap test (:605-607) and the length /
+ * percentage pre-filter (:612-635).  Ids are mapped to store indices through hc_idmap =
+ * FastqStorage::m_ID_to_index (src/FastqStorage.h:90-93, first insertion wins).
+ * Outputs, both in file order: the candidates that reach process_overlaps (ready for
+ * hc_score_batch*) and the overlaps the pre-filter sends to nonedge_overlaps.txt (:633-635).
+ * A line the reference would exit(1)/assert/throw on is reported in stats (first such line);
+ * nothing is guessed.
+ * ------------------------------------------------------------------------------------------ */
+#define HC_LINE_SCORE      1   /* passes the pre-filter -> process_overlaps                           */
+#define HC_LINE_NONEDGE    2   /* fails the length tests -> nonedge_overlaps.txt (:633-635)           */
+#define HC_LINE_DROPPED    3   /* self overlap (:605-607) or inside the band with perc < min_overlap_perc */
+#define HC_LINE_SKIPPED    4   /* != 13 fields: "incorrect overlap; skipping" (:598-603)              */
+#define HC_LINE_ERROR      5   /* a check of src/Overlap.h:107-165 fails: the reference exits/aborts  */
+#define HC_LINE_UNKNOWN_ID 6   /* would be scored but an id is not in the store (map::at throws, :170-171) */
+
+typedef struct hc_idmap hc_idmap;
+/* ids[i] = read_id of store read i (m_read_vec order). */
+hc_idmap* hc_idmap_create(const uint64_t* ids, uint64_t n_reads, int device);
+void      hc_idmap_destroy(hc_idmap* m);
+
+typedef struct {
+    uint64_t max_overlaps;       /* ProgramSettings::max_overlaps: lines read at most (:581)           */
+    uint32_t min_overlap_len;    /* :612,:618,:626                                                     */
+    uint32_t min_overlap_perc;   /* :614,:621,:629                                                     */
+    uint8_t  relax_PE_edges;     /* :626                                                               */
+    uint8_t  allow_spaces;       /* :585                                                               */
+    uint8_t  reserved[6];
+} hc_ingest_params;              /* 24 bytes */
+
+typedef struct {                 /* an Overlap as Overlap::get_overlap_line prints it (src/Overlap.h:234-237) */
+    uint64_t id1, id2;
+    uint32_t pos1, pos2, perc1, perc2, len1, len2;
+    uint8_t  ord, ori1, ori2, type1, type2;   /* the characters of the file */
+    uint8_t  reserved[3];
+} hc_overlap_rec;                /* 48 bytes */
+
+typedef struct {
+    uint64_t n_lines;            /* lines read (clamped to max_overlaps)                               */
+    uint64_t n_scored, n_filtered, n_skipped, n_dropped;
+    uint64_t first_error_line;   /* 0-based line of the first HC_LINE_ERROR / HC_LINE_UNKNOWN_ID, ~0 if none */
+    uint64_t first_error_offset; /* its byte offset and length in the buffer                           */
+    uint64_t first_error_length;
+    uint32_t first_error_status;
+    float    device_ms;          /* newline index + parse + compaction kernels                         */
+} hc_ingest_stats;               /* 72 bytes */
+
+/* Host buffers.  cand_line / filtered_line (nullable) receive the 0-based line number of every
+ * output record.  Returns HC_ERR_CAPACITY with the required sizes in stats->n_scored /
+ * stats->n_filtered when a buffer is too small.  Lines after the first error line are still
+ * classified; the caller decides (the host mirror dies with the reference's message). */
+int hc_ingest_overlaps(const hc_idmap* m, const char* text, uint64_t n_bytes, const hc_ingest_params* p,
+                       hc_candidate* cand, uint64_t* cand_line, uint64_t cand_cap,
+                       hc_overlap_rec* filtered, uint64_t* filtered_line, uint64_t filtered_cap,
+                       hc_ingest_stats* stats);
+/* The same on DEVICE buffers of the id map's device (d_text 16-byte aligned is fastest); the
+ * candidates can be handed to hc_score_batch_device without leaving HBM. */
+int hc_ingest_overlaps_device(const hc_idmap* m, void* stream, const char* d_text, uint64_t n_bytes,
+                              const hc_ingest_params* p, hc_candidate* d_cand, uint64_t* d_cand_line, uint64_t cand_cap,
+                              hc_overlap_rec* d_filtered, uint64_t* d_filtered_line, uint64_t filtered_cap,
+                              hc_ingest_stats* stats);
+
 int         hc_device_count(void);
 const char* hc_last_error(void);
 const char* hc_version(void);

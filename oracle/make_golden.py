@@ -98,6 +98,35 @@ def run_fno3_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> No
     print("%-28s originals=%d reads=%d -> %d overlap lines" % (name, len(fi.off) - 1, len(fi.reads), len(ref)))
 
 
+def run_ingest_case(name: str, rs: F.ReadSet, cands: np.ndarray, seed: int, allow_spaces: bool, ps: dict) -> None:
+    """Irregularly spelled overlaps file through the real construct_edges() with thresholds under which every
+    candidate that reaches process_overlaps is printed back as a non-edge (edge_threshold 2, merge_contigs -1,
+    ov_threshold -1): nonedge_overlaps.txt then holds, re-printed by Overlap::get_overlap_line, first every scored
+    line in order (:546-555), then every pre-filtered line in order (:654-660)."""
+    d = tempfile.mkdtemp(prefix="hc_golden_ing_")
+    F.write_fastq_set(rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    text = W.fuzz_overlap_text(cands, rs.ids, seed=seed, allow_spaces=allow_spaces)
+    with open(d + "/ov.txt", "wb") as f:
+        f.write(text)
+    kw = dict(singles=d + "/s.fastq" if rs.n_single else None,
+              paired1=d + "/p1.fastq" if rs.n_reads > rs.n_single else None,
+              paired2=d + "/p2.fastq" if rs.n_reads > rs.n_single else None)
+    out = O.run_ref(d, d + "/ov.txt", run=True, dump_cands=True, threads=1, edge_threshold=2, merge_contigs=-1, ov_threshold=-1,
+                    allow_spaced_overlaps=int(allow_spaces), **kw, **ps)
+    assert out["graph_edges"] == 0
+    lines = out.get("nonedge_lines", [])
+    n_f = int(out["len_filtered"])
+    assert len(lines) == int(out["scored"]) + n_f, (len(lines), out["scored"], n_f)
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"), ids=rs.ids, text=np.frombuffer(text, dtype=np.uint8),
+        ps_keys=np.array(sorted(ps.keys())), ps_vals=np.array([float(ps[k]) for k in sorted(ps.keys())]),
+        allow_spaces=np.int64(allow_spaces), ref_scored=np.array(lines[:len(lines) - n_f], dtype=object).astype(str),
+        ref_filtered=np.array(lines[len(lines) - n_f:], dtype=object).astype(str),
+        ref_counts=np.array([out["lines"], out["scored"], n_f, out["self"], out["perc_dropped"], out["bad"]], dtype=np.int64))
+    print("%-28s lines=%d scored=%d filtered=%d self=%d perc_dropped=%d skipped=%d" %
+          (name, out["lines"], out["scored"], n_f, out["self"], out["perc_dropped"], out["bad"]))
+
+
 def main() -> None:
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -129,6 +158,11 @@ def main() -> None:
     c5 = W.geometry_candidates(ss5, 2500, seed=8)
     run_case("synth_mismatch_void", ss5.rs, c5, dict(edge_threshold=0.9, ov_threshold=0.5, min_overlap_len=120, mismatch=0.01,
                                                       relax_PE_edges=True))
+
+    # ---- candidate ingestion: irregular spellings the parser accepts, through the real text loop
+    run_ingest_case("ingest_tabs", ss.rs, c3, 5, False, dict(min_overlap_len=60, min_overlap_perc=30))
+    run_ingest_case("ingest_tabs_relaxed", ss5.rs, c5, 6, False, dict(min_overlap_len=150, relax_PE_edges=True))
+    run_ingest_case("ingest_spaces", ss.rs, c3, 7, True, dict(min_overlap_len=60, min_overlap_perc=30))
 
     # ---- FindNextOverlaps (FNO1): the reference's overlaps.txt after one merge iteration
     s700 = full.subset(range(0, 700))

@@ -35,7 +35,7 @@ class Golden:
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("fno", "insert_")))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("fno", "insert_", "ingest_")))
 
 
 def fno_golden_names():
@@ -177,3 +177,27 @@ def random_insert_edges(seed, n, n_vertices):
         rc[f] = e[f]
     rc["cls"] = 1
     return O.normalise_ref_edges(rc)
+
+
+class IngestGolden:
+    """tests/golden/ingest_*.npz: an irregularly spelled overlaps file and what the reference's construct_edges()
+    printed back for it (oracle/make_golden.py: run_ingest_case)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+        self.name = name
+        self.ids = z["ids"]
+        self.text = z["text"].tobytes()
+        self.ps = {str(k): float(v) for k, v in zip(z["ps_keys"], z["ps_vals"])}
+        self.allow_spaces = bool(z["allow_spaces"])
+        self.ref_scored = [str(x) for x in z["ref_scored"]]
+        self.ref_filtered = [str(x) for x in z["ref_filtered"]]
+        self.ref_counts = z["ref_counts"]     # lines, scored, filtered, self overlaps, perc-dropped, skipped
+
+    def kw(self):
+        return dict(min_overlap_len=int(self.ps["min_overlap_len"]), min_overlap_perc=int(self.ps.get("min_overlap_perc", 0)),
+                    relax_PE_edges=bool(self.ps.get("relax_PE_edges", 0)), allow_spaces=self.allow_spaces)
+
+
+def ingest_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ingest_*.npz")))
