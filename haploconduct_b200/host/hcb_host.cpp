@@ -147,12 +147,26 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         bases += r.seq2;
         quals += r.phred2;
     }
+    first_device_ = ps.first_device;
     store_ = hc_store_create(descs.data(), descs.size(), m_readcount_single, bases.data(), quals.data(), ps.first_device,
                              ps.n_devices);
     if (!store_) die(std::string("hc_store_create: ") + hc_last_error());
 }
 
-FastqStorage::~FastqStorage() { hc_store_destroy(store_); }
+FastqStorage::~FastqStorage() {
+    hc_idmap_destroy(idmap_);
+    hc_store_destroy(store_);
+}
+
+hc_idmap* FastqStorage::device_idmap() {
+    if (!idmap_) {
+        std::vector<uint64_t> ids(m_read_vec.size());
+        for (size_t i = 0; i < ids.size(); i++) ids[i] = m_read_vec[i].read_id;
+        idmap_ = hc_idmap_create(ids.data(), ids.size(), first_device_);
+        if (!idmap_) die(std::string("hc_idmap_create: ") + hc_last_error());
+    }
+    return idmap_;
+}
 
 // ---------------------------------------------------------------------------------------------- Overlap
 static std::string strip(const std::string& s, const char* chars) {
@@ -313,12 +327,16 @@ void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
     std::vector<hc_candidate> cand(n);
     for (size_t i = 0; i < n; i++) {
         const Overlap& o = batch[i];
-        auto i1 = fastq_->m_ID_to_index.find(o.id1), i2 = fastq_->m_ID_to_index.find(o.id2);
-        if (i1 == fastq_->m_ID_to_index.end()) die(std::to_string(o.id1) + "\nread ID of the overlaps file is not in the fastq input");
-        if (i2 == fastq_->m_ID_to_index.end()) die(std::to_string(o.id2) + "\nread ID of the overlaps file is not in the fastq input");
         hc_candidate& c = cand[i];
         memset(&c, 0, sizeof(c));
-        c.idx1 = i1->second; c.idx2 = i2->second;
+        if (o.idx1 >= 0 && o.idx2 >= 0) {
+            c.idx1 = (uint32_t)o.idx1; c.idx2 = (uint32_t)o.idx2;
+        } else {
+            auto i1 = fastq_->m_ID_to_index.find(o.id1), i2 = fastq_->m_ID_to_index.find(o.id2);
+            if (i1 == fastq_->m_ID_to_index.end()) die(std::to_string(o.id1) + "\nread ID of the overlaps file is not in the fastq input");
+            if (i2 == fastq_->m_ID_to_index.end()) die(std::to_string(o.id2) + "\nread ID of the overlaps file is not in the fastq input");
+            c.idx1 = i1->second; c.idx2 = i2->second;
+        }
         c.pos1 = o.pos1; c.pos2 = o.pos2; c.len1 = o.len1; c.len2 = o.len2;
         c.perc1 = (uint8_t)o.perc1; c.perc2 = (uint8_t)o.perc2;
         c.ord = (uint8_t)o.ord; c.ori1 = o.ori1 == '+'; c.ori2 = o.ori2 == '+';
@@ -407,49 +425,126 @@ void EdgeCalculator::insert_edge(Edge& e, unsigned int& doubles) {
     }
 }
 
+int EdgeCalculator::handle_line(const std::string& line, std::vector<Overlap>& batch, std::vector<Overlap>& filtered) {
+    size_t b = 0, e = line.size();
+    while (b < e && (line[b] == '\t' || line[b] == ' ')) b++;                      // trim outer tabs/spaces, :584
+    while (e > b && (line[e - 1] == '\t' || line[e - 1] == ' ')) e--;
+    std::vector<std::string> f;
+    std::string cur;
+    if (b < e) {
+        for (size_t k = b; k < e; k++) {
+            const char ch = line[k];
+            const bool sep = ps_.allow_spaces ? (ch == '\t' || ch == ' ') : ch == '\t';
+            if (sep) {
+                f.push_back(cur);
+                cur.clear();
+                if (ps_.allow_spaces) while (k + 1 < e && (line[k + 1] == '\t' || line[k + 1] == ' ')) k++;   // token_compress_on
+            } else cur.push_back(ch);
+        }
+        f.push_back(cur);
+    }
+    if (f.size() != 13) { std::cout << "incorrect overlap; skipping" << std::endl; return 0; }   // :600-603
+    Overlap o = Overlap::from_fields(f);
+    if (o.id1 == o.id2) return 0;                                                  // :605-607
+    const bool any_p = o.type1 == 'p' || o.type2 == 'p';
+    bool in_band = false;
+    if (o.len1 >= ps_.min_overlap_len && o.type1 == 's' && o.type2 == 's') in_band = true;                   // :612-617
+    else if (o.len1 >= 0.5 * ps_.min_overlap_len && o.len2 >= 0.5 * ps_.min_overlap_len && any_p) in_band = true;   // :618-624
+    else if (ps_.relax_PE_edges && o.len1 + o.len2 >= ps_.min_overlap_len && any_p) in_band = true;          // :626-632
+    if (in_band) {
+        if (o.get_perc() >= ps_.min_overlap_perc) { batch.push_back(o); return 1; }
+        return 0;
+    }
+    filtered.push_back(o);                                                         // :633-635
+    return 2;
+}
+
+// The text loop on the device: the file goes to hc_ingest_overlaps in pieces that end at a line end; scored
+// candidates arrive with their store indices, pre-filtered overlaps as printable records, both in file order.
+void EdgeCalculator::ingest_on_device(std::vector<Overlap>& batch, std::vector<Overlap>& filtered) {
+    std::ifstream in(ps_.overlaps_file.c_str(), std::ios::binary);
+    if (!in.is_open()) { std::cerr << "Unable to open overlaps file"; std::exit(1); }
+    hc_idmap* idmap = fastq_->device_idmap();
+    const size_t piece = (size_t)64 << 20;
+    std::string buf, carry;
+    unsigned long lines_done = 0;
+    std::vector<hc_candidate> cand;
+    std::vector<hc_overlap_rec> filt;
+    while (lines_done < ps_.max_overlaps) {
+        buf = carry;
+        carry.clear();
+        const size_t have = buf.size();
+        buf.resize(have + piece);
+        in.read(&buf[have], (std::streamsize)piece);
+        buf.resize(have + (size_t)in.gcount());
+        if (buf.empty()) break;
+        if (!in.eof()) {                       // keep the unfinished last line for the next piece
+            const size_t nl = buf.rfind('\n');
+            if (nl == std::string::npos) { carry.swap(buf); continue; }
+            carry = buf.substr(nl + 1);
+            buf.resize(nl + 1);
+        }
+        const size_t cap = (size_t)std::count(buf.begin(), buf.end(), '\n') + 1;
+        cand.resize(cap);
+        filt.resize(cap);
+        hc_ingest_params ip;
+        memset(&ip, 0, sizeof(ip));
+        ip.max_overlaps = ps_.max_overlaps - lines_done;
+        ip.min_overlap_len = ps_.min_overlap_len; ip.min_overlap_perc = ps_.min_overlap_perc;
+        ip.relax_PE_edges = ps_.relax_PE_edges; ip.allow_spaces = ps_.allow_spaces;
+        hc_ingest_stats st;
+        const int rc = hc_ingest_overlaps(idmap, buf.data(), buf.size(), &ip, cand.data(), nullptr, cap, filt.data(), nullptr, cap, &st);
+        if (rc != HC_OK) die(std::string("hc_ingest_overlaps: ") + hc_last_error());
+        if (st.first_error_line != ~0ull) {    // the reference ends at this line: let the host parser say why
+            std::vector<Overlap> b2, f2;
+            handle_line(buf.substr(st.first_error_offset, st.first_error_length), b2, f2);
+            if (!b2.empty()) process_overlaps(b2);    // an id that is not in the store
+            die("overlaps file: line rejected by the device parser");
+        }
+        for (uint64_t k = 0; k < st.n_skipped; k++) std::cout << "incorrect overlap; skipping" << std::endl;   // :600-603
+        for (uint64_t k = 0; k < st.n_filtered; k++) {
+            const hc_overlap_rec& r = filt[k];
+            Overlap o;
+            o.id1 = r.id1; o.id2 = r.id2; o.pos1 = r.pos1; o.pos2 = r.pos2; o.perc1 = r.perc1; o.perc2 = r.perc2;
+            o.len1 = r.len1; o.len2 = r.len2; o.ord = (char)r.ord; o.ori1 = (char)r.ori1; o.ori2 = (char)r.ori2;
+            o.type1 = (char)r.type1; o.type2 = (char)r.type2;
+            filtered.push_back(o);
+        }
+        for (uint64_t k = 0; k < st.n_scored; k++) {
+            const hc_candidate& c = cand[k];
+            Overlap o;
+            o.idx1 = c.idx1; o.idx2 = c.idx2;
+            o.id1 = fastq_->m_read_vec[c.idx1].read_id; o.id2 = fastq_->m_read_vec[c.idx2].read_id;
+            o.pos1 = c.pos1; o.pos2 = c.pos2; o.perc1 = c.perc1; o.perc2 = c.perc2; o.len1 = c.len1; o.len2 = c.len2;
+            o.ord = (char)c.ord; o.ori1 = c.ori1 ? '+' : '-'; o.ori2 = c.ori2 ? '+' : '-';
+            o.type1 = (char)c.type1; o.type2 = (char)c.type2;
+            batch.push_back(o);
+            if (batch.size() == 1000000) { process_overlaps(batch); batch.clear(); }   // :636-644
+        }
+        lines_done += st.n_lines;
+        parse_device_ms += st.device_ms;
+        if (in.eof() && carry.empty()) break;
+    }
+}
+
 void EdgeCalculator::construct_edges() {                                          // src/EdgeCalculator.cpp:561-666
     if (ps_.add_duplicates) die("add_duplicates=true is not supported by this build (no driver script uses it)");
     std::remove("nonedge_overlaps.txt");                                          // :566 (cwd, like the reference)
-    std::ifstream in(ps_.overlaps_file.c_str());
-    if (!in.is_open()) { std::cerr << "Unable to open overlaps file"; std::exit(1); }
     const size_t per_batch = 1000000;                                             // :571
     std::vector<Overlap> batch, filtered;
     batch.reserve(per_batch);
-    std::string line;
-    unsigned long i = 0;
-    while (i < ps_.max_overlaps && getline(in, line)) {
-        i++;
-        size_t b = 0, e = line.size();
-        while (b < e && (line[b] == '\t' || line[b] == ' ')) b++;                  // trim outer tabs/spaces, :584
-        while (e > b && (line[e - 1] == '\t' || line[e - 1] == ' ')) e--;
-        std::vector<std::string> f;
-        std::string cur;
-        if (b < e) {
-            for (size_t k = b; k < e; k++) {
-                const char ch = line[k];
-                const bool sep = ps_.allow_spaces ? (ch == '\t' || ch == ' ') : ch == '\t';
-                if (sep) {
-                    f.push_back(cur);
-                    cur.clear();
-                    if (ps_.allow_spaces) while (k + 1 < e && (line[k + 1] == '\t' || line[k + 1] == ' ')) k++;   // token_compress_on
-                } else cur.push_back(ch);
-            }
-            f.push_back(cur);
+    if (ps_.gpu_parse) {
+        ingest_on_device(batch, filtered);
+    } else {
+        std::ifstream in(ps_.overlaps_file.c_str());
+        if (!in.is_open()) { std::cerr << "Unable to open overlaps file"; std::exit(1); }
+        std::string line;
+        unsigned long i = 0;
+        while (i < ps_.max_overlaps && getline(in, line)) {
+            i++;
+            handle_line(line, batch, filtered);
+            if (batch.size() == per_batch) { process_overlaps(batch); batch.clear(); }
         }
-        if (f.size() != 13) { std::cout << "incorrect overlap; skipping" << std::endl; continue; }   // :600-603
-        Overlap o = Overlap::from_fields(f);
-        if (o.id1 == o.id2) continue;                                              // :605-607
-        const bool any_p = o.type1 == 'p' || o.type2 == 'p';
-        bool in_band = false;
-        if (o.len1 >= ps_.min_overlap_len && o.type1 == 's' && o.type2 == 's') in_band = true;                   // :612-617
-        else if (o.len1 >= 0.5 * ps_.min_overlap_len && o.len2 >= 0.5 * ps_.min_overlap_len && any_p) in_band = true;   // :618-624
-        else if (ps_.relax_PE_edges && o.len1 + o.len2 >= ps_.min_overlap_len && any_p) in_band = true;          // :626-632
-        if (in_band) {
-            if (o.get_perc() >= ps_.min_overlap_perc) batch.push_back(o);
-        } else {
-            filtered.push_back(o);                                                 // :633-635
-        }
-        if (batch.size() == per_batch) { process_overlaps(batch); batch.clear(); }
     }
     if (!batch.empty()) { process_overlaps(batch); batch.clear(); }
     if (ps_.gpu_dedup && !pending_.empty()) {

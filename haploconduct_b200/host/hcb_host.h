@@ -52,6 +52,8 @@ struct ProgramSettings {           // names and defaults of src/Types.h:19-67 / 
     // duplicate-edge resolution of process_overlaps (score >= existing score, :470) needs to pick the
     // same representative when two overlaps of one read pair score within 1e-7 of each other.
     bool exact_scores = true;
+    // parse + pre-filter the overlaps file on the GPU (hc_ingest_overlaps) instead of the text loop of :581-645
+    bool gpu_parse = false;
     // resolve duplicate edges on the GPU (hc_dedup_edges) instead of the sequential insert of :429-545
     bool gpu_dedup = false;
     int first_device = 0;
@@ -80,6 +82,7 @@ public:
 
     unsigned int get_readcount() const { return (unsigned int)m_read_vec.size(); }
     hc_store* device_store() const { return store_; }
+    hc_idmap* device_idmap();     // m_ID_to_index on the device (hc_ingest_overlaps), built on first use
 
 private:
     void read_singles(const std::string& path, unsigned long max_reads);
@@ -88,6 +91,8 @@ private:
     std::map<std::string, std::string> new_ids_;
     bool have_new_ids_ = false;
     hc_store* store_ = nullptr;
+    hc_idmap* idmap_ = nullptr;
+    int first_device_ = 0;
 };
 
 struct Overlap {                   // src/Overlap.h:23-35
@@ -97,6 +102,7 @@ struct Overlap {                   // src/Overlap.h:23-35
     char ori1 = '+', ori2 = '+';
     unsigned int perc1 = 0, perc2 = 0, len1 = 0, len2 = 0;
     char type1 = 's', type2 = 's';
+    long idx1 = -1, idx2 = -1;     // store indices when the device parser resolved them already
 
     // constructor semantics of src/Overlap.h:39-73; exits like the reference on malformed fields
     static Overlap from_fields(const std::vector<std::string>& f);
@@ -150,11 +156,14 @@ public:
     unsigned int self_overlap_count = 0, inclusion_count = 0, dup_count = 0;
     // measurements of the last construct_edges() (not in the reference)
     unsigned long scored_candidates = 0;
-    double device_ms = 0;
+    double device_ms = 0, parse_device_ms = 0;
 
 private:
     void process_overlaps(std::vector<Overlap>& batch);                                          // :389-557
     void insert_edge(Edge& e, unsigned int& doubles);                                            // :441-538
+    // one line of the text loop (:583-635): 0 skipped / dropped, 1 appended to batch, 2 appended to filtered
+    int handle_line(const std::string& line, std::vector<Overlap>& batch, std::vector<Overlap>& filtered);
+    void ingest_on_device(std::vector<Overlap>& batch, std::vector<Overlap>& filtered);
     std::vector<Edge> pending_;   // gpu_dedup: accepted edges of all batches, normalised, in order
     ProgramSettings ps_;
     std::shared_ptr<FastqStorage> fastq_;

@@ -164,7 +164,9 @@ int main(int argc, char** argv) {
     std::vector<Overlap> batch;
     std::vector<unsigned long> batch_line;
     unsigned long n_lines = 0, n_self = 0, n_lenfiltered = 0, n_percdropped = 0, n_bad = 0;
+    double t_parse = -1;
     if (!dump_cands.empty() || do_time) {
+        const double tp0 = now_s();
         std::ifstream in(ps.overlaps_file.c_str());
         if (!in.is_open()) { std::fprintf(stderr, "cannot open %s\n", ps.overlaps_file.c_str()); return 1; }
         std::string line;
@@ -199,6 +201,7 @@ int main(int argc, char** argv) {
             if (dropped) n_percdropped++;
             if (pass) { batch.push_back(ov); batch_line.push_back(i); }
         }
+        t_parse = now_s() - tp0;   // the single-threaded text loop: getline, trim, split, Overlap ctor, pre-filter
     }
 
     if (!dump_cands.empty()) {
@@ -468,10 +471,10 @@ int main(int argc, char** argv) {
     std::printf("{\"fno1_lines\": %lu}\n", fno_lines);
     std::printf("{\"reads_single\": %u, \"reads_paired\": %u, \"threads\": %u, \"lines\": %lu, \"scored\": %lu, "
                 "\"self\": %lu, \"len_filtered\": %lu, \"perc_dropped\": %lu, \"bad\": %lu, "
-                "\"t_fastq_s\": %.6f, \"t_scoring_s\": %.6f, \"scoring_edges\": %lu, \"scoring_nonedges\": %lu, "
+                "\"t_fastq_s\": %.6f, \"t_parse_s\": %.6f, \"t_scoring_s\": %.6f, \"scoring_edges\": %lu, \"scoring_nonedges\": %lu, "
                 "\"t_construct_edges_s\": %.6f, \"graph_edges\": %u, \"dup_count\": %u, \"inclusion_count\": %u}\n",
                 fastq->m_readcount_single, fastq->m_readcount_paired, ps.n_threads, n_lines,
-                (unsigned long)batch.size(), n_self, n_lenfiltered, n_percdropped, n_bad, t_fastq, t_scoring,
+                (unsigned long)batch.size(), n_self, n_lenfiltered, n_percdropped, n_bad, t_fastq, t_parse, t_scoring,
                 n_edges_t, n_nonedges_t, t_construct, do_run ? graph->getEdgeCount() : 0u, ec.dup_count,
                 ec.inclusion_count);
     return 0;

@@ -19,12 +19,12 @@ pytestmark = pytest.mark.gpu
 EXE = os.path.join(B.LIBDIR, "hc_edgecalc")
 
 
-def _run(g, tmp_path, exact, gpu_dedup=False):
+def _run(g, tmp_path, exact, gpu_dedup=False, gpu_parse=False):
     d = str(tmp_path)
     F.write_fastq_set(g.rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", g.cands, g.rs.ids)
     cmd = [EXE, "--overlaps", d + "/ov.txt", "--dump-graph", d + "/graph.tsv", "--digraph", d + "/digraph.txt",
-           "--exact_scores=" + ("true" if exact else "false"), "--gpu_dedup=" + ("true" if gpu_dedup else "false")]
+           "--exact_scores=" + ("true" if exact else "false"), "--gpu_dedup=" + ("true" if gpu_dedup else "false"), "--gpu_parse=" + ("true" if gpu_parse else "false")]
     if g.rs.n_single:
         cmd += ["--singles", d + "/s.fastq"]
     if g.rs.n_reads > g.rs.n_single:
@@ -65,6 +65,40 @@ def test_graph_identical_with_device_dedup(built_lib, tmp_path, name):
     assert np.array_equal(graph, g.ref_graph), name
     assert nonedge == g.ref_nonedge
     assert [summary["graph_edges"], summary["dup_count"], summary["inclusion_count"]] == g.ref_counts.tolist()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_graph_identical_with_device_parse_and_dedup(built_lib, tmp_path, name):
+    """--gpu_parse=true --gpu_dedup=true: text loop (:581-645) and duplicate resolution (:429-545) on the device too."""
+    g = load_golden(name)
+    summary, graph, nonedge, digraph = _run(g, tmp_path, exact=True, gpu_dedup=True, gpu_parse=True)
+    assert np.array_equal(graph, g.ref_graph), name
+    assert nonedge == g.ref_nonedge
+    assert [summary["graph_edges"], summary["dup_count"], summary["inclusion_count"]] == g.ref_counts.tolist()
+
+
+@pytest.mark.parametrize("gpu_parse", [False, True])
+@pytest.mark.parametrize("name,reads", [("ingest_tabs", "synth_all_types"), ("ingest_tabs_relaxed", "synth_mismatch_void"),
+                                        ("ingest_spaces", "synth_all_types")])
+def test_irregular_overlaps_file(built_lib, tmp_path, name, reads, gpu_parse):
+    """An irregularly spelled overlaps file, with thresholds under which every surviving line is printed back:
+    nonedge_overlaps.txt must be what the reference's construct_edges() wrote (host parser and device parser)."""
+    from util import IngestGolden
+    ig, g = IngestGolden(name), load_golden(reads)
+    d = str(tmp_path)
+    F.write_fastq_set(g.rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    with open(d + "/ov.txt", "wb") as f:
+        f.write(ig.text)
+    cmd = [EXE, "--overlaps", d + "/ov.txt", "--edge_threshold", "2", "--merge_contigs", "-1", "--ov_threshold", "-1",
+           "--singles", d + "/s.fastq", "--paired1", d + "/p1.fastq", "--paired2", d + "/p2.fastq",
+           "--gpu_parse=" + ("true" if gpu_parse else "false"), "--allow_spaced_overlaps=" + ("true" if ig.allow_spaces else "false")]
+    for k, v in ig.ps.items():
+        cmd += ["--" + k + "=true"] if k == "relax_PE_edges" else ["--" + k, str(int(v))]
+    out = subprocess.run(cmd, cwd=d, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
+    assert out.count("incorrect overlap; skipping") == int(ig.ref_counts[5])
+    with open(d + "/nonedge_overlaps.txt") as f:
+        nonedge = f.read().split("\n")[:-1]
+    assert nonedge == ig.ref_scored + ig.ref_filtered
 
 
 @pytest.mark.parametrize("name", golden_names())
