@@ -23,7 +23,7 @@ EXPORTED = [
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
-    "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
+    "hc_store_create_fastq", "hc_store_read_ids", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -46,6 +46,10 @@ def lib() -> ctypes.CDLL:
         vp, u64, i32, u32, dbl = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_double
         L.hc_store_create.restype = vp
         L.hc_store_create.argtypes = [vp, u64, u64, vp, vp, i32, i32]
+        L.hc_store_create_fastq.restype = vp
+        L.hc_store_create_fastq.argtypes = [vp, u64, vp, u64, vp, u64, u64, i32, i32]
+        L.hc_store_read_ids.restype = i32
+        L.hc_store_read_ids.argtypes = [vp, vp, vp]
         L.hc_store_destroy.restype = None
         L.hc_store_destroy.argtypes = [vp]
         for name in ("hc_store_n_reads", "hc_store_n_single", "hc_store_device_bytes"):
@@ -113,6 +117,28 @@ class Store:
             raise HcError(-1, last_error())
         self.first_device = first_device
         self.n_devices = n_devices
+
+    @classmethod
+    def from_fastq(cls, singles: bytes = b"", paired1: bytes = b"", paired2: bytes = b"", max_reads: int = 2 ** 62,
+                   first_device: int = 0, n_devices: int = 1) -> "Store":
+        """hc_store_create_fastq: the store straight from the text of the FASTQ files."""
+        L = lib()
+        bufs = [np.frombuffer(t, dtype=np.uint8) if len(t) else None for t in (singles, paired1, paired2)]
+        self = cls.__new__(cls)
+        self._h = L.hc_store_create_fastq(*[x for b in bufs for x in ((b.ctypes.data, len(b)) if b is not None else (None, 0))],
+                                          max_reads, first_device, n_devices)
+        if not self._h:
+            raise HcError(-4, last_error())
+        self.first_device, self.n_devices = first_device, n_devices
+        return self
+
+    def read_ids(self):
+        """(ids, mate lengths [n, 2]) of a store built from FASTQ text."""
+        n = int(lib().hc_store_n_reads(self._h))
+        ids = np.zeros(n, dtype=np.uint64)
+        lens = np.zeros((n, 2), dtype=np.uint32)
+        _check(lib().hc_store_read_ids(self._h, ids.ctypes.data, lens.ctypes.data))
+        return ids, lens
 
     @property
     def handle(self):

@@ -14,6 +14,7 @@
 #include "hc_layout.h"
 #include "hc_tables.h"
 #include "hc_kernels.cuh"
+#include "hc_pack.cuh"
 
 namespace {
 
@@ -85,6 +86,8 @@ struct hc_store {
     int code_to_q[HC_MAX_CODES + 1];
     int q_to_code[256];
     std::vector<DevCtx> devs;
+    std::vector<uint64_t> ids;        // hc_store_create_fastq only: read ids and mate lengths parsed from the files
+    std::vector<uint32_t> lens;
     hc_tables tables;
     bool tables_built = false;
     double tables_mismatch = 0.0;
@@ -114,16 +117,6 @@ void free_ctx(DevCtx& d) {
     d = DevCtx();
 }
 
-inline int base_code(unsigned char c) {
-    switch (c) {
-        case 'A': return 0;
-        case 'C': return 1;
-        case 'G': return 2;
-        case 'T': return 3;
-        case 'N': return 4;
-        default: return -1;
-    }
-}
 
 int ensure_tables(hc_store* s, DevCtx& d, double mismatch, cudaStream_t st) {
     {
@@ -293,32 +286,18 @@ void hc_store_destroy(hc_store* s) {
     delete s;
 }
 
-hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t n_single, const char* bases,
-                          const char* quals, int first_device, int n_devices) {
-    if (!reads || !bases || !quals || n_reads == 0 || n_single > n_reads || n_devices < 1 || first_device < 0) {
-        fail(HC_ERR_ARG, "hc_store_create: bad argument");
-        return nullptr;
-    }
-    if (n_reads >= 0xffffffffull) { fail(HC_ERR_ARG, "hc_store_create: too many reads"); return nullptr; }
-    int ndev = hc_device_count();
-    if (ndev == 0) { fail(HC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)"); return nullptr; }
-    if (first_device + n_devices > ndev) { fail(HC_ERR_ARG, "hc_store_create: device range exceeds the devices present"); return nullptr; }
+namespace {
 
-    hc_store* s = new hc_store();
-    s->n_reads = n_reads;
-    s->n_single = n_single;
-    // ---- pass 1: validate, quality alphabet, slot layout
-    bool seen[256];
-    memset(seen, 0, sizeof(seen));
-    std::vector<hc_rdesc> rd(n_reads);
+// Slot layout of reads with the given mate lengths: forward strand, then reverse complement, each in a
+// zero-padded slot of hc_slot_size(len) positions.  0 ok, 2 empty first mate, 3 too large.
+int layout_slots(const uint32_t* len2, uint64_t n_reads, std::vector<hc_rdesc>& rd, uint64_t* total) {
+    rd.resize(n_reads);
     uint64_t pos = 0;   // in positions
     int bad = 0;
     for (uint64_t r = 0; r < n_reads; r++) {
-        const int paired = reads[r].seq_len[1] > 0;
-        if ((r < n_single) == (paired != 0)) bad = 1;       // singles first, then pairs (src/FastqStorage.h:88-97)
-        if (reads[r].seq_len[0] == 0) bad = 2;              // empty sequence (src/FastqStorage.cpp:143-146)
+        if (len2[2 * r] == 0) bad = 2;                      // empty sequence (src/FastqStorage.cpp:143-146)
         for (int m = 0; m < 2; m++) {
-            const uint32_t len = reads[r].seq_len[m];
+            const uint32_t len = len2[2 * r + m];
             if (len > HC_LEN_MASK / 2) bad = 3;
             rd[r].slot16[m] = (uint32_t)(pos >> 4);
             rd[r].len[m] = len;
@@ -326,6 +305,162 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
             if ((pos >> 4) > 0xffffffffull) bad = 3;
         }
     }
+    *total = (pos + 63) & ~63ull;
+    return bad;
+}
+
+cudaError_t init_ctx(hc_store* s, DevCtx& d, int device, bool* not_sm100) {
+    d.device = device;
+    cudaError_t e = cudaSetDevice(d.device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.device);
+    if (e == cudaSuccess && prop.major < 10) { *not_sm100 = true; return cudaErrorInvalidDevice; }
+    if (e == cudaSuccess) {
+        d.sm_count = prop.multiProcessorCount;
+        d.smem_per_sm = prop.sharedMemPerMultiprocessor;
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.s_copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.s_out, cudaStreamNonBlocking);
+    for (int j = 0; j < 2 && e == cudaSuccess; j++) {
+        e = cudaEventCreateWithFlags(&d.ev_in[j], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_done[j], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_out[j], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&d.d_run, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&d.h_cnt, 2 * HC_CNT_N * sizeof(unsigned long long));
+    for (int j = 0; j < 6 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
+    if (e == cudaSuccess) e = cudaMalloc(&d.rdesc, s->n_reads * sizeof(hc_rdesc));
+    if (e == cudaSuccess) e = cudaMalloc(&d.d_counts, 4 * sizeof(uint64_t));
+    return e;
+}
+
+cudaError_t alloc_planes(hc_store* s, DevCtx& d, cudaStream_t st) {
+    const uint64_t total = s->total_positions;
+    uint8_t** qplane = s->packed ? &d.pk : &d.qual;
+    cudaError_t e = cudaMalloc(qplane, total + 64);
+    if (e == cudaSuccess && !s->packed) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
+    if (e == cudaSuccess && !s->packed) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(*qplane, 0, total + 64, st);
+    if (e == cudaSuccess && !s->packed) e = cudaMemsetAsync(d.base2, 0, (total / 16 + 16) * 4, st);
+    if (e == cudaSuccess && !s->packed) e = cudaMemsetAsync(d.nmask, 0, (total / 32 + 16) * 4, st);
+    return e;
+}
+
+// Validate, find the quality alphabet, pack both strands on the first device (text and source offsets are already
+// there), then copy the planes to the other devices.  Returns HC_OK or an error code with the message set.
+int build_store(hc_store* s, std::vector<hc_rdesc>& rd, const uint8_t* d_text, const hc_pack_src* d_src, uint64_t n_upper,
+                int first_device, int n_devices) {
+    const uint64_t n_reads = s->n_reads;
+    s->devs.resize(n_devices);
+    for (int k = 0; k < n_devices; k++) {
+        bool not100 = false;
+        const cudaError_t e = init_ctx(s, s->devs[k], first_device + k, &not100);
+        if (not100) return fail(HC_ERR_CUDA, "device is not sm_100 class (this library ships sm_100a code only)");
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_store_create: ") + cudaGetErrorString(e));
+    }
+    DevCtx& d0 = s->devs[0];
+    CU(cudaSetDevice(d0.device));
+    uint32_t* d_flags = nullptr;    // [0..7] quality characters seen, [8] error bits
+    uint8_t* d_lut = nullptr;
+    uint32_t h_flags[9];
+    uint8_t lut[256];
+    cudaError_t e = cudaMalloc(&d_flags, 9 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_lut, 256);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, 9 * sizeof(uint32_t), d0.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d0.rdesc, rd.data(), n_reads * sizeof(hc_rdesc), cudaMemcpyHostToDevice, d0.stream);
+    if (e == cudaSuccess) e = hc_pack_validate_launch(d_text, d_src, d0.rdesc, n_reads, n_upper, d_flags, d_flags + 8, d0.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, d0.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d0.stream);
+    int rc = HC_OK;
+    if (e == cudaSuccess && h_flags[8]) {
+        rc = fail(HC_ERR_INPUT, (h_flags[8] & 1u)
+                                    ? "invalid nucleotide (only upper-case A,C,G,T,N are accepted; the reference asserts in "
+                                      "EdgeCalculator::score, src/EdgeCalculator.cpp:29-30)"
+                                    : "quality character outside '!'..'~' (Phred 0..93; src/EdgeCalculator.cpp:61,93-98)");
+    }
+    if (e == cudaSuccess && rc == HC_OK) {
+        memset(s->q_to_code, 0, sizeof(s->q_to_code));
+        memset(lut, 0, sizeof(lut));
+        s->ncodes = 0;
+        s->code_to_q[0] = -1;
+        for (int c = 33; c <= 33 + 93; c++) {
+            if ((h_flags[c >> 5] >> (c & 31)) & 1u) {
+                s->ncodes++;
+                s->code_to_q[s->ncodes] = c - 33;
+                s->q_to_code[c] = s->ncodes;
+                lut[c] = (uint8_t)s->ncodes;
+            }
+        }
+        const char* layout = getenv("HC_STORE_LAYOUT");   // "planar" forces the three-plane layout (tests)
+        s->packed = s->ncodes <= HC_PACKED_MAX_CODES && !(layout && strcmp(layout, "planar") == 0);
+        e = cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, d0.stream);
+        if (e == cudaSuccess) e = alloc_planes(s, d0, d0.stream);
+        if (e == cudaSuccess)
+            e = hc_pack_write_launch(d_text, d_src, d0.rdesc, n_reads, n_upper, d_lut, s->packed, s->packed ? d0.pk : d0.qual, d0.base2,
+                                     d0.nmask, d0.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d0.stream);
+    }
+    cudaFree(d_flags);
+    cudaFree(d_lut);
+    if (rc != HC_OK) return rc;
+    const uint64_t total = s->total_positions;
+    for (int k = 0; k < n_devices && e == cudaSuccess; k++) {
+        DevCtx& d = s->devs[k];
+        e = cudaSetDevice(d.device);
+        if (e == cudaSuccess) e = hc_score_occupancy((uint32_t)s->ncodes, d.sm_count, d.smem_per_sm, &d.cfg);
+        if (k == 0 || e != cudaSuccess) continue;
+        e = alloc_planes(s, d, d.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+        if (e == cudaSuccess) e = cudaMemcpyPeer(s->packed ? d.pk : d.qual, d.device, s->packed ? d0.pk : d0.qual, d0.device, total);
+        if (e == cudaSuccess && !s->packed) e = cudaMemcpyPeer(d.base2, d.device, d0.base2, d0.device, total / 16 * 4);
+        if (e == cudaSuccess && !s->packed) e = cudaMemcpyPeer(d.nmask, d.device, d0.nmask, d0.device, total / 32 * 4);
+        if (e == cudaSuccess) e = cudaMemcpyPeer(d.rdesc, d.device, d0.rdesc, d0.device, n_reads * sizeof(hc_rdesc));
+    }
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_store_create: ") + cudaGetErrorString(e));
+    return HC_OK;
+}
+
+bool check_devices(int first_device, int n_devices) {
+    if (n_devices < 1 || first_device < 0) { fail(HC_ERR_ARG, "hc_store_create: bad argument"); return false; }
+    const int ndev = hc_device_count();
+    if (ndev == 0) { fail(HC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)"); return false; }
+    if (first_device + n_devices > ndev) { fail(HC_ERR_ARG, "hc_store_create: device range exceeds the devices present"); return false; }
+    return true;
+}
+
+}  // namespace
+
+hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t n_single, const char* bases,
+                          const char* quals, int first_device, int n_devices) {
+    if (!reads || !bases || !quals || n_reads == 0 || n_single > n_reads) {
+        fail(HC_ERR_ARG, "hc_store_create: bad argument");
+        return nullptr;
+    }
+    if (n_reads >= 0xffffffffull) { fail(HC_ERR_ARG, "hc_store_create: too many reads"); return nullptr; }
+    if (!check_devices(first_device, n_devices)) return nullptr;
+
+    hc_store* s = new hc_store();
+    s->n_reads = n_reads;
+    s->n_single = n_single;
+    // ---- host: slot layout and where every mate's bytes lie in the two blobs
+    std::vector<uint32_t> len2(2 * n_reads);
+    std::vector<hc_pack_src> src(2 * n_reads);
+    uint64_t blob = 0;
+    int bad = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const int paired = reads[r].seq_len[1] > 0;
+        if ((r < n_single) == (paired != 0)) bad = 1;       // singles first, then pairs (src/FastqStorage.h:88-97)
+        for (int m = 0; m < 2; m++) {
+            len2[2 * r + m] = reads[r].seq_len[m];
+            if (reads[r].seq_len[m]) blob = std::max<uint64_t>(blob, reads[r].seq_off[m] + reads[r].seq_len[m]);
+        }
+    }
+    const uint64_t qbase = (blob + 15) & ~15ull;
+    for (uint64_t r = 0; r < n_reads; r++)
+        for (int m = 0; m < 2; m++) { src[2 * r + m].boff = reads[r].seq_off[m]; src[2 * r + m].qoff = qbase + reads[r].seq_off[m]; }
+    std::vector<hc_rdesc> rd;
+    if (!bad) bad = layout_slots(len2.data(), n_reads, rd, &s->total_positions);
     if (bad) {
         fail(bad == 1 ? HC_ERR_ARG : HC_ERR_INPUT,
              bad == 1 ? "hc_store_create: reads must be ordered singles first, then pairs"
@@ -333,152 +468,110 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
         delete s;
         return nullptr;
     }
-    const uint64_t total = (pos + 63) & ~63ull;
-    s->total_positions = total;
-    int input_err = 0;
-#pragma omp parallel
-    {
-        bool lseen[256];
-        memset(lseen, 0, sizeof(lseen));
-        int lerr = 0;
-#pragma omp for schedule(static)
-        for (int64_t r = 0; r < (int64_t)n_reads; r++) {
-            for (int m = 0; m < 2; m++) {
-                const uint32_t len = reads[r].seq_len[m];
-                const unsigned char* b = (const unsigned char*)bases + reads[r].seq_off[m];
-                const unsigned char* q = (const unsigned char*)quals + reads[r].seq_off[m];
-                for (uint32_t i = 0; i < len; i++) {
-                    if (base_code(b[i]) < 0) lerr = 1;
-                    if (q[i] < 33 || q[i] > 33 + 93) lerr = 2;
-                    lseen[q[i]] = true;
-                }
-            }
-        }
-#pragma omp critical
-        {
-            for (int k = 0; k < 256; k++) if (lseen[k]) seen[k] = true;
-            if (lerr) input_err = lerr;
-        }
-    }
-    if (input_err) {
-        fail(HC_ERR_INPUT, input_err == 1
-                               ? "invalid nucleotide (only upper-case A,C,G,T,N are accepted; the reference asserts in "
-                                 "EdgeCalculator::score, src/EdgeCalculator.cpp:29-30)"
-                               : "quality character outside '!'..'~' (Phred 0..93; src/EdgeCalculator.cpp:61,93-98)");
-        delete s;
-        return nullptr;
-    }
-    memset(s->q_to_code, 0, sizeof(s->q_to_code));
-    s->ncodes = 0;
-    s->code_to_q[0] = -1;
-    for (int c = 33; c <= 33 + 93; c++) {
-        if (seen[c]) {
-            s->ncodes++;
-            s->code_to_q[s->ncodes] = c - 33;
-            s->q_to_code[c] = s->ncodes;
-        }
-    }
-    // ---- pass 2: pack both strands
-    const char* layout = getenv("HC_STORE_LAYOUT");   // "planar" forces the three-plane layout (tests)
-    s->packed = s->ncodes <= HC_PACKED_MAX_CODES && !(layout && strcmp(layout, "planar") == 0);
-    const bool packed = s->packed;
-    std::vector<uint8_t> hq;
-    std::vector<uint32_t> hb, hn;
-    try {
-        hq.assign(total, 0);
-        if (!packed) {
-            hb.assign(total / 16, 0);
-            hn.assign(total / 32, 0);
-        }
-    } catch (...) {
-        fail(HC_ERR_NOMEM, "hc_store_create: host staging allocation failed");
-        delete s;
-        return nullptr;
-    }
-#pragma omp parallel for schedule(static)
-    for (int64_t r = 0; r < (int64_t)n_reads; r++) {
-        for (int m = 0; m < 2; m++) {
-            const uint32_t len = reads[r].seq_len[m];
-            if (!len) continue;
-            const unsigned char* b = (const unsigned char*)bases + reads[r].seq_off[m];
-            const unsigned char* q = (const unsigned char*)quals + reads[r].seq_off[m];
-            const uint64_t fwd = 16ull * rd[r].slot16[m], rev = fwd + hc_slot_size(len);
-            bool hasN = false;
-            for (uint32_t i = 0; i < len; i++) {
-                const int bc = base_code(b[i]);
-                const uint64_t pf = fwd + i, pr = rev + (len - 1 - i);
-                if (bc == 4) {
-                    hasN = true;          // N: code 0 quality (contributes nothing), base bits 0, mask bit set
-                    if (!packed) {
-                        hn[pf >> 5] |= 1u << (pf & 31);
-                        hn[pr >> 5] |= 1u << (pr & 31);
-                    }
-                } else {
-                    const uint8_t code = (uint8_t)s->q_to_code[q[i]];
-                    if (packed) {
-                        hq[pf] = (uint8_t)(code | (bc << 6));
-                        hq[pr] = (uint8_t)(code | ((3 - bc) << 6));      // reversed qualities + complement
-                    } else {
-                        hq[pf] = code;
-                        hq[pr] = code;                                   // reversed qualities, src/Read.h:187-201
-                        hb[pf >> 4] |= (uint32_t)bc << (2 * (pf & 15));
-                        hb[pr >> 4] |= (uint32_t)(3 - bc) << (2 * (pr & 15));   // complement, src/Types.h:109-129
-                    }
-                }
-            }
-            if (hasN) rd[r].len[m] |= HC_HASN_BIT;
-        }
-    }
-    // ---- replicate on the devices
-    s->devs.resize(n_devices);
-    for (int k = 0; k < n_devices; k++) {
-        DevCtx& d = s->devs[k];
-        d.device = first_device + k;
-        cudaError_t e = cudaSetDevice(d.device);
-        cudaDeviceProp prop;
-        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.device);
-        if (e == cudaSuccess && prop.major < 10) {
-            fail(HC_ERR_CUDA, "device is not sm_100 class (this library ships sm_100a code only)");
-            hc_store_destroy(s);
-            return nullptr;
-        }
-        if (e == cudaSuccess) {
-            d.sm_count = prop.multiProcessorCount;
-            d.smem_per_sm = prop.sharedMemPerMultiprocessor;
-            e = hc_score_occupancy((uint32_t)s->ncodes, d.sm_count, d.smem_per_sm, &d.cfg);
-        }
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.s_copy, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.s_out, cudaStreamNonBlocking);
-        for (int j = 0; j < 2 && e == cudaSuccess; j++) {
-            e = cudaEventCreateWithFlags(&d.ev_in[j], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_done[j], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_out[j], cudaEventDisableTiming);
-        }
-        if (e == cudaSuccess) e = cudaMalloc(&d.d_run, 2 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMallocHost(&d.h_cnt, 2 * HC_CNT_N * sizeof(unsigned long long));
-        for (int j = 0; j < 6 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
-        uint8_t** qplane = packed ? &d.pk : &d.qual;
-        if (e == cudaSuccess) e = cudaMalloc(qplane, total + 64);
-        if (e == cudaSuccess && !packed) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
-        if (e == cudaSuccess && !packed) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&d.rdesc, n_reads * sizeof(hc_rdesc));
-        if (e == cudaSuccess) e = cudaMalloc(&d.d_counts, 4 * sizeof(uint64_t));
-        if (e == cudaSuccess) e = cudaMemset(*qplane + total, 0, 64);
-        if (e == cudaSuccess && !packed) e = cudaMemset(d.base2 + total / 16, 0, 64);
-        if (e == cudaSuccess && !packed) e = cudaMemset(d.nmask + total / 32, 0, 64);
-        if (e == cudaSuccess) e = cudaMemcpy(*qplane, hq.data(), total, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && !packed) e = cudaMemcpy(d.base2, hb.data(), total / 16 * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && !packed) e = cudaMemcpy(d.nmask, hn.data(), total / 32 * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d.rdesc, rd.data(), n_reads * sizeof(hc_rdesc), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) {
-            fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA,
-                 std::string("hc_store_create: ") + cudaGetErrorString(e));
-            hc_store_destroy(s);
-            return nullptr;
-        }
-    }
+    // ---- device: raw bytes in, validate + pack there (no packed copy is ever built on the host)
+    uint8_t* d_text = nullptr;
+    hc_pack_src* d_src = nullptr;
+    cudaError_t e = cudaSetDevice(first_device);
+    if (e == cudaSuccess) e = cudaMalloc(&d_text, 2 * qbase + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_src, 2 * n_reads * sizeof(hc_pack_src));
+    if (e == cudaSuccess) e = cudaMemcpy(d_text, bases, blob, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_text + qbase, quals, blob, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_src, src.data(), 2 * n_reads * sizeof(hc_pack_src), cudaMemcpyHostToDevice);
+    int rc = HC_OK;
+    if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_store_create: ") + cudaGetErrorString(e));
+    else rc = build_store(s, rd, d_text, d_src, 0, first_device, n_devices);
+    cudaSetDevice(first_device);
+    cudaFree(d_text);
+    cudaFree(d_src);
+    if (rc != HC_OK) { const std::string keep = g_err; hc_store_destroy(s); g_err = keep; return nullptr; }
     return s;
+}
+
+// FastqStorage::FastqStorage (src/FastqStorage.h:58-98) from the text of the FASTQ files: the files go to the first
+// device as they are; line index, record scan (ids, lengths), validation and packing all run there.
+hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, const char* paired1, uint64_t paired1_bytes,
+                                const char* paired2, uint64_t paired2_bytes, uint64_t max_reads, int first_device, int n_devices) {
+    if ((singles_bytes && !singles) || (paired1_bytes && !paired1) || (paired2_bytes && !paired2)) {
+        fail(HC_ERR_ARG, "hc_store_create_fastq: NULL argument");
+        return nullptr;
+    }
+    if (!check_devices(first_device, n_devices)) return nullptr;
+    const char* file[3] = {singles, paired1, paired2};
+    const uint64_t bytes[3] = {singles_bytes, paired1_bytes, paired2_bytes};
+    uint64_t off[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 3; k++) off[k + 1] = off[k] + ((bytes[k] + 15) & ~15ull);
+    hc_store* s = new hc_store();
+    char* d_text = nullptr;
+    unsigned long long* d_ls[3] = {nullptr, nullptr, nullptr};
+    unsigned long long *d_ids = nullptr, *d_first = nullptr;
+    uint32_t* d_len = nullptr;
+    hc_pack_src* d_src = nullptr;
+    void* d_tok = nullptr;
+    uint64_t nl[3] = {0, 0, 0}, nrec[3] = {0, 0, 0};
+    unsigned long long first_err = ~0ull;
+    uint64_t n_single = 0, n_pairs = 0, n_reads = 0;
+    std::vector<hc_rdesc> rd;
+    int rc = HC_OK;
+    cudaError_t e = cudaSetDevice(first_device);
+    if (e == cudaSuccess) e = cudaMalloc(&d_text, off[3] + 16);
+    for (int k = 0; k < 3 && e == cudaSuccess; k++)
+        if (bytes[k]) e = cudaMemcpy(d_text + off[k], file[k], bytes[k], cudaMemcpyHostToDevice);
+    for (int k = 0; k < 3 && e == cudaSuccess; k++) e = hc_fastq_index(d_text + off[k], bytes[k], max_reads, &d_ls[k], &nl[k], &nrec[k], 0);
+    if (e == cudaSuccess) {
+        n_single = nrec[0];
+        n_pairs = std::min(nrec[1], nrec[2]);               // the loop runs while both files have lines, :176
+        n_reads = n_single + n_pairs;
+        if (n_reads == 0) rc = fail(HC_ERR_INPUT, "hc_store_create_fastq: no complete FASTQ record");
+        else if (n_reads >= 0xffffffffull) rc = fail(HC_ERR_ARG, "hc_store_create_fastq: too many reads");
+    }
+    if (e == cudaSuccess && rc == HC_OK) {
+        e = cudaMalloc(&d_ids, n_reads * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&d_len, 2 * n_reads * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&d_src, 2 * n_reads * sizeof(hc_pack_src));
+        if (e == cudaSuccess) e = cudaMalloc(&d_tok, n_reads * 16);
+        if (e == cudaSuccess) e = cudaMalloc(&d_first, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(d_len, 0, 2 * n_reads * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(d_src, 0, 2 * n_reads * sizeof(hc_pack_src));
+        if (e == cudaSuccess) e = cudaMemset(d_first, 0xff, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = hc_fastq_records_launch(d_text, off[0], bytes[0], d_ls[0], nl[0], n_single, d_ids, d_len, d_src, d_tok, 0, 0, d_first, 0);
+        if (e == cudaSuccess) e = hc_fastq_records_launch(d_text, off[1], bytes[1], d_ls[1], nl[1], n_pairs, d_ids, d_len, d_src, d_tok, 0, n_single, d_first, 0);
+        if (e == cudaSuccess) e = hc_fastq_records_launch(d_text, off[2], bytes[2], d_ls[2], nl[2], n_pairs, d_ids, d_len, d_src, d_tok, 1, n_single, d_first, 0);
+        if (e == cudaSuccess) e = cudaMemcpy(&first_err, d_first, sizeof(first_err), cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess && rc == HC_OK && first_err != ~0ull) {
+        // the reference exits at this record (src/FastqStorage.cpp:107-110,143-146,181-192,217-220)
+        const bool pair = first_err >= n_single;
+        rc = fail(HC_ERR_INPUT, std::string("FASTQ record ") + std::to_string(pair ? first_err - n_single : first_err) + " of the " +
+                                    (pair ? "paired" : "single-end") + " input is not acceptable: header without '@', mate headers "
+                                    "that differ, an empty sequence, or sequence and quality lines of different lengths");
+    }
+    if (e == cudaSuccess && rc == HC_OK) {
+        s->n_reads = n_reads;
+        s->n_single = n_single;
+        s->ids.resize(n_reads);
+        s->lens.resize(2 * n_reads);
+        e = cudaMemcpy(s->ids.data(), d_ids, n_reads * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(s->lens.data(), d_len, 2 * n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) {
+            const int bad = layout_slots(s->lens.data(), n_reads, rd, &s->total_positions);
+            if (bad) rc = fail(HC_ERR_INPUT, bad == 2 ? "hc_store_create_fastq: read with an empty sequence" : "hc_store_create_fastq: store too large");
+        }
+    }
+    if (e != cudaSuccess && rc == HC_OK) rc = fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_store_create_fastq: ") + cudaGetErrorString(e));
+    if (rc == HC_OK) rc = build_store(s, rd, (const uint8_t*)d_text, d_src, n_single, first_device, n_devices);   // singles are upper-cased, :123
+    cudaSetDevice(first_device);
+    cudaFree(d_text); cudaFree(d_ids); cudaFree(d_len); cudaFree(d_src); cudaFree(d_tok); cudaFree(d_first);
+    for (int k = 0; k < 3; k++) cudaFree(d_ls[k]);
+    if (rc != HC_OK) { const std::string keep = g_err; hc_store_destroy(s); g_err = keep; return nullptr; }
+    return s;
+}
+
+int hc_store_read_ids(const hc_store* s, uint64_t* ids, uint32_t* mate_lengths) {
+    if (!s) return fail(HC_ERR_ARG, "hc_store_read_ids: NULL store");
+    if (s->ids.size() != s->n_reads) return fail(HC_ERR_ARG, "hc_store_read_ids: the store was not built from FASTQ text");
+    if (ids) memcpy(ids, s->ids.data(), s->n_reads * sizeof(uint64_t));
+    if (mate_lengths) memcpy(mate_lengths, s->lens.data(), 2 * s->n_reads * sizeof(uint32_t));
+    return HC_OK;
 }
 
 int hc_score_batch_device(hc_store* s, int device, void* stream, const hc_params* p, const hc_candidate* d_cand, uint64_t n,

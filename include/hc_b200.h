@@ -57,6 +57,17 @@ typedef struct {
 hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t n_single,
                           const char* bases, const char* quals,
                           int first_device, int n_devices);
+/* The same store from the text of the FASTQ files, FastqStorage::FastqStorage (src/FastqStorage.h:58-98,
+ * src/FastqStorage.cpp:42-235) on the device: at most 4 * max_reads lines per file (:46), records of four lines,
+ * header = '@' + id token (first white-space delimited token, strtoul(.., 0), src/Types.h:99-102), single-end
+ * sequences upper-cased (:123), mates taken verbatim (:196-197) with equal header tokens (:189-192); singles
+ * first, then pairs.  Records the reference exits on give NULL + HC_ERR_INPUT.  Pass NULL / 0 for an absent
+ * file.  The id_correspondence table of the reference (--IDs) is not applied: use hc_store_create for that. */
+hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, const char* paired1, uint64_t paired1_bytes,
+                                const char* paired2, uint64_t paired2_bytes, uint64_t max_reads,
+                                int first_device, int n_devices);
+/* ids (n_reads) and mate lengths (2 * n_reads) of a store built by hc_store_create_fastq; either may be NULL */
+int       hc_store_read_ids(const hc_store* s, uint64_t* ids, uint32_t* mate_lengths);
 void      hc_store_destroy(hc_store* s);
 
 uint64_t  hc_store_n_reads(const hc_store* s);
