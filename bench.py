@@ -237,6 +237,7 @@ def main() -> None:
     rs = pr.readset()
     t1 = time.time()
     store = capi.Store(rs, first_device=local_rank, n_devices=1)
+    store_build_s = time.time() - t1
     log("[rank %d] store packed + uploaded in %.1fs (%.2f GB on device, %d quality codes)" %
         (rank, time.time() - t1, store.device_bytes / 1e9, store.quality_alphabet))
     t1 = time.time()
@@ -352,7 +353,7 @@ def main() -> None:
             "gpu_launches": int(stats["kernel_launches"]) * args.steps,
             "clocks": clocks,
             "results": {"edges": int(counts[0]), "nonedges": int(counts[1]), "reference_order_pass": int(counts[2])},
-            "setup_s": round(time.time() - t_setup, 1),
+            "setup_s": round(time.time() - t_setup, 1), "store_build_s": round(store_build_s, 2),
         }
         if e2e:
             line["e2e"] = {"value": total_cands / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[1],

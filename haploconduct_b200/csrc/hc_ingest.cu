@@ -15,10 +15,29 @@ void hc_set_last_error(const char* msg);   // hc_api.cu
 struct hc_idmap {
     int device;
     uint64_t n;        // reads
-    uint64_t mask;     // table size - 1
-    unsigned long long* keys;
-    uint32_t* vals;
+    uint64_t mask;     // hash table size - 1 (open addressing, one 16-byte slot {id, index} per entry)
+    ulonglong2* slots;
+    uint64_t direct_n; // > 0: ids are dense, direct[id] = index for id < direct_n (fits L2 for 1e7 reads)
+    uint32_t* direct;
+    // grow-only workspace of hc_ingest_overlaps* (one call at a time per handle)
+    void* ws[16];
+    size_t ws_cap[16];
+    cudaEvent_t e0, e1;
 };
+
+static cudaError_t ws_get(hc_idmap* m, int k, size_t bytes, void** out) {
+    if (bytes > m->ws_cap[k]) {
+        cudaFree(m->ws[k]);
+        m->ws[k] = nullptr;
+        m->ws_cap[k] = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        const cudaError_t e = cudaMalloc(&m->ws[k], want);
+        if (e != cudaSuccess) return e;
+        m->ws_cap[k] = want;
+    }
+    *out = m->ws[k];
+    return cudaSuccess;
+}
 
 #include "hc_text.cuh"
 
@@ -32,32 +51,52 @@ struct IngTmp {            // one parsed line
     uint32_t idx1, idx2;
 };
 
+__device__ __forceinline__ hc_candidate to_candidate(const IngTmp& t) {
+    hc_candidate c;
+    c.idx1 = t.idx1; c.idx2 = t.idx2; c.pos1 = t.r.pos1; c.pos2 = t.r.pos2; c.len1 = t.r.len1; c.len2 = t.r.len2;
+    c.perc1 = (uint8_t)t.r.perc1; c.perc2 = (uint8_t)t.r.perc2; c.ord = t.r.ord;
+    c.ori1 = t.r.ori1 == '+'; c.ori2 = t.r.ori2 == '+'; c.type1 = t.r.type1; c.type2 = t.r.type2; c.reserved = 0;
+    return c;
+}
+
 __device__ __forceinline__ u64 hash64(u64 k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
     return k;
 }
 
 // ---- id map ------------------------------------------------------------------------------------
-__global__ void idmap_insert(const u64* ids, u64 n, u64* keys, uint32_t* vals, u64 mask) {
+struct IdMapDev {
+    const ulonglong2* slots;
+    u64 mask;
+    const uint32_t* direct;
+    u64 direct_n;
+};
+
+__global__ void idmap_insert(const u64* ids, u64 n, ulonglong2* slots, u64 mask) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const u64 key = ids[i];
         u64 h = hash64(key) & mask;
         while (true) {
-            const u64 prev = atomicCAS(&keys[h], EMPTY, key);
-            if (prev == EMPTY || prev == key) { atomicMin(&vals[h], (uint32_t)i); break; }   // std::map::insert keeps the first
+            const u64 prev = atomicCAS(&slots[h].x, EMPTY, key);
+            if (prev == EMPTY || prev == key) { atomicMin(&slots[h].y, i); break; }   // std::map::insert keeps the first
             h = (h + 1) & mask;
         }
     }
 }
 
-__device__ __forceinline__ uint32_t idmap_find(const u64* keys, const uint32_t* vals, u64 mask, u64 key) {
+__global__ void idmap_insert_direct(const u64* ids, u64 n, uint32_t* direct) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) atomicMin(&direct[ids[i]], (uint32_t)i);
+}
+
+__device__ __forceinline__ uint32_t idmap_find(const IdMapDev& M, u64 key) {
+    if (M.direct_n) return key < M.direct_n ? __ldg(M.direct + key) : 0xffffffffu;
     if (key == EMPTY) return 0xffffffffu;
-    u64 h = hash64(key) & mask;
+    u64 h = hash64(key) & M.mask;
     while (true) {
-        const u64 k = keys[h];
-        if (k == key) return vals[h];
-        if (k == EMPTY) return 0xffffffffu;
-        h = (h + 1) & mask;
+        const ulonglong2 e = M.slots[h];
+        if (e.x == key) return (uint32_t)e.y;
+        if (e.x == EMPTY) return 0xffffffffu;
+        h = (h + 1) & M.mask;
     }
 }
 
@@ -102,9 +141,7 @@ struct IngDev {
     const u64* line_start;
     u64 n_lines;           // lines considered (already clamped to max_overlaps)
     u64 n_newlines;
-    const u64* keys;
-    const uint32_t* vals;
-    u64 mask;
+    IdMapDev ids;
     uint32_t min_overlap_len, min_overlap_perc;
     int relax, allow_spaces;
 };
@@ -176,19 +213,20 @@ __device__ uint8_t parse_line(const IngDev& D, u64 i, IngTmp& o) {
     else in_band = D.relax && (uint32_t)(num[4] + num[5]) >= D.min_overlap_len && any_p;            // :626-632
     if (!in_band) return HC_LINE_NONEDGE;                                                           // :633-635
     if (perc < D.min_overlap_perc) return HC_LINE_DROPPED;
-    o.idx1 = idmap_find(D.keys, D.vals, D.mask, id1);
-    o.idx2 = idmap_find(D.keys, D.vals, D.mask, id2);
+    o.idx1 = idmap_find(D.ids, id1);
+    o.idx2 = idmap_find(D.ids, id2);
     if (o.idx1 == 0xffffffffu || o.idx2 == 0xffffffffu) return HC_LINE_UNKNOWN_ID;                  // map::at throws, :170-171
     return HC_LINE_SCORE;
 }
 
-__global__ void __launch_bounds__(256) ing_parse(IngDev D, IngTmp* tmp, uint8_t* status, u64* first_error) {
+__global__ void __launch_bounds__(256) ing_parse(IngDev D, hc_candidate* tmp_c, hc_overlap_rec* tmp_f, uint8_t* status, u64* first_error) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D.n_lines) return;
     IngTmp o;
     const uint8_t st = parse_line(D, i, o);
     status[i] = st;
-    if (st == HC_LINE_SCORE || st == HC_LINE_NONEDGE) tmp[i] = o;
+    if (st == HC_LINE_SCORE) tmp_c[i] = to_candidate(o);      // only the record a line needs is written
+    else if (st == HC_LINE_NONEDGE) tmp_f[i] = o.r;
     if (st == HC_LINE_ERROR || st == HC_LINE_UNKNOWN_ID) atomicMin(first_error, i);
 }
 
@@ -209,7 +247,7 @@ __global__ void __launch_bounds__(LINES_PER_BLOCK) ing_count(const uint8_t* stat
     }
 }
 
-__global__ void __launch_bounds__(LINES_PER_BLOCK) ing_scatter(const uint8_t* status, const IngTmp* tmp, u64 n, const u64* off_s,
+__global__ void __launch_bounds__(LINES_PER_BLOCK) ing_scatter(const uint8_t* status, const hc_candidate* tmp_c, const hc_overlap_rec* tmp_f, u64 n, const u64* off_s,
                                                                const u64* off_f, hc_candidate* cand, u64* cand_line,
                                                                hc_overlap_rec* filt, u64* filt_line) {
     __shared__ uint32_t ws[32], wf[32];
@@ -224,16 +262,11 @@ __global__ void __launch_bounds__(LINES_PER_BLOCK) ing_scatter(const uint8_t* st
     const uint32_t lt = (1u << lane) - 1u;
     if (st == HC_LINE_SCORE) {
         const u64 k = off_s[blockIdx.x] + ps + __popc(bs & lt);
-        const IngTmp t = tmp[i];
-        hc_candidate c;
-        c.idx1 = t.idx1; c.idx2 = t.idx2; c.pos1 = t.r.pos1; c.pos2 = t.r.pos2; c.len1 = t.r.len1; c.len2 = t.r.len2;
-        c.perc1 = (uint8_t)t.r.perc1; c.perc2 = (uint8_t)t.r.perc2; c.ord = t.r.ord;
-        c.ori1 = t.r.ori1 == '+'; c.ori2 = t.r.ori2 == '+'; c.type1 = t.r.type1; c.type2 = t.r.type2; c.reserved = 0;
-        cand[k] = c;
+        cand[k] = tmp_c[i];
         if (cand_line) cand_line[k] = i;
     } else if (st == HC_LINE_NONEDGE) {
         const u64 k = off_f[blockIdx.x] + pf + __popc(bf & lt);
-        filt[k] = tmp[i].r;
+        filt[k] = tmp_f[i];
         if (filt_line) filt_line[k] = i;
     }
 }
@@ -250,88 +283,109 @@ __global__ void __launch_bounds__(LINES_PER_BLOCK) ing_scatter(const uint8_t* st
         }                                                                                    \
     } while (0)
 
+extern "C" void hc_idmap_destroy(hc_idmap* m);
+
 extern "C" hc_idmap* hc_idmap_create(const uint64_t* ids, uint64_t n_reads, int device) {
     if (n_reads && !ids) { hc_set_last_error("hc_idmap_create: NULL ids"); return nullptr; }
     if (n_reads >= 0xffffffffull) { hc_set_last_error("hc_idmap_create: too many reads"); return nullptr; }
     hc_idmap* m = new hc_idmap();
-    m->device = device; m->n = n_reads; m->keys = nullptr; m->vals = nullptr;
-    u64 cap = 64;
-    while (cap < 2 * n_reads + 2) cap <<= 1;
-    m->mask = cap - 1;
+    m->device = device; m->n = n_reads; m->slots = nullptr; m->direct = nullptr; m->direct_n = 0; m->mask = 0;
+    memset(m->ws, 0, sizeof(m->ws)); memset(m->ws_cap, 0, sizeof(m->ws_cap));
+    m->e0 = m->e1 = nullptr;
+    u64 max_id = 0;
+    for (u64 i = 0; i < n_reads; i++) max_id = std::max<u64>(max_id, ids[i]);
+    const bool dense = n_reads > 0 && max_id < 4 * n_reads + 1024;     // rename_fas.py numbers the reads 0..n-1
     int rc = HC_OK;
     u64* d_ids = nullptr;
+    const int blocks = (int)std::min<u64>((n_reads + 255) / 256 + 1, 148 * 16);
     ICU(cudaSetDevice(device));
-    ICU(cudaMalloc(&m->keys, cap * sizeof(u64)));
-    ICU(cudaMalloc(&m->vals, cap * sizeof(uint32_t)));
-    ICU(cudaMemset(m->keys, 0xff, cap * sizeof(u64)));
-    ICU(cudaMemset(m->vals, 0xff, cap * sizeof(uint32_t)));
     if (n_reads) {
         ICU(cudaMalloc(&d_ids, n_reads * sizeof(u64)));
         ICU(cudaMemcpy(d_ids, ids, n_reads * sizeof(u64), cudaMemcpyHostToDevice));
-        idmap_insert<<<(int)std::min<u64>((n_reads + 255) / 256, 148 * 16), 256>>>(d_ids, n_reads, m->keys, m->vals, m->mask);
-        ICU(cudaGetLastError());
-        ICU(cudaDeviceSynchronize());
     }
+    if (dense) {
+        m->direct_n = max_id + 1;
+        ICU(cudaMalloc(&m->direct, m->direct_n * sizeof(uint32_t)));
+        ICU(cudaMemset(m->direct, 0xff, m->direct_n * sizeof(uint32_t)));
+        idmap_insert_direct<<<blocks, 256>>>(d_ids, n_reads, m->direct);
+    } else {
+        u64 cap = 64;
+        while (cap < 2 * n_reads + 2) cap <<= 1;
+        m->mask = cap - 1;
+        ICU(cudaMalloc(&m->slots, cap * sizeof(ulonglong2)));
+        ICU(cudaMemset(m->slots, 0xff, cap * sizeof(ulonglong2)));
+        if (n_reads) idmap_insert<<<blocks, 256>>>(d_ids, n_reads, m->slots, m->mask);
+    }
+    ICU(cudaGetLastError());
+    ICU(cudaDeviceSynchronize());
+    ICU(cudaEventCreate(&m->e0));
+    ICU(cudaEventCreate(&m->e1));
 done:
     cudaFree(d_ids);
-    if (rc != HC_OK) { cudaFree(m->keys); cudaFree(m->vals); delete m; return nullptr; }
+    if (rc != HC_OK) { hc_idmap_destroy(m); return nullptr; }
     return m;
 }
 
 extern "C" void hc_idmap_destroy(hc_idmap* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->keys);
-    cudaFree(m->vals);
+    cudaFree(m->slots);
+    cudaFree(m->direct);
+    for (int k = 0; k < 16; k++) cudaFree(m->ws[k]);
+    if (m->e0) cudaEventDestroy(m->e0);
+    if (m->e1) cudaEventDestroy(m->e1);
     delete m;
 }
 
 // Device-side core: text already on the device.  Outputs are device buffers; counts[0..1] land in host memory.
-static int ingest_device(const hc_idmap* m, const char* d_text, u64 n_bytes, const hc_ingest_params* p, hc_candidate* d_cand,
+static int ingest_device(const hc_idmap* cm, const char* d_text, u64 n_bytes, const hc_ingest_params* p, hc_candidate* d_cand,
                          uint64_t* d_cand_line, u64 cand_cap, hc_overlap_rec* d_filt, uint64_t* d_filt_line, u64 filt_cap,
                          hc_ingest_stats* st, cudaStream_t stream) {
+    hc_idmap* m = const_cast<hc_idmap*>(cm);     // the workspace is the only thing a call changes
     int rc = HC_OK;
     const u64 n_tiles = (n_bytes + TILE - 1) / TILE;
     uint32_t *d_tcnt = nullptr, *d_cs = nullptr, *d_cf = nullptr;
     u64 *d_toff = nullptr, *d_tot = nullptr, *d_ls = nullptr, *d_os = nullptr, *d_of = nullptr, *d_misc = nullptr;
-    IngTmp* d_tmp = nullptr;
+    hc_candidate* d_tmp_c = nullptr;
+    hc_overlap_rec* d_tmp_f = nullptr;
     uint8_t* d_status = nullptr;
     u64 n_nl = 0, n_lines = 0, n_blocks = 0, misc[3] = {0, 0, EMPTY}, tot_s = 0, tot_f = 0;
     char last = '\n';
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
     IngDev D;
     memset(st, 0, sizeof(*st));
     st->first_error_line = EMPTY;
     if (n_bytes == 0) return HC_OK;
-    ICU(cudaEventCreate(&e0)); ICU(cudaEventCreate(&e1));
-    ICU(cudaMalloc(&d_tcnt, n_tiles * sizeof(uint32_t)));
-    ICU(cudaMalloc(&d_toff, n_tiles * sizeof(u64)));
-    ICU(cudaMalloc(&d_tot, 2 * sizeof(u64)));
-    ICU(cudaEventRecord(e0, stream));
+    ICU(ws_get(m, 0, n_tiles * sizeof(uint32_t), (void**)&d_tcnt));
+    ICU(ws_get(m, 1, n_tiles * sizeof(u64), (void**)&d_toff));
+    ICU(ws_get(m, 2, 8 * sizeof(u64), (void**)&d_tot));
+    d_misc = d_tot + 2;
+    ICU(cudaEventRecord(m->e0, stream));
     nl_count<<<(unsigned)n_tiles, 256, 0, stream>>>(d_text, n_bytes, d_tcnt);
     scan_counts<<<1, 1024, 0, stream>>>(d_tcnt, n_tiles, d_toff, d_tot);
     ICU(cudaMemcpyAsync(&n_nl, d_tot, sizeof(u64), cudaMemcpyDeviceToHost, stream));
     ICU(cudaMemcpyAsync(&last, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, stream));
     ICU(cudaStreamSynchronize(stream));
     n_lines = n_nl + (last != '\n' ? 1 : 0);          // getline also returns an unterminated last line
-    ICU(cudaMalloc(&d_ls, (n_nl + 2) * sizeof(u64)));
+    ICU(ws_get(m, 3, (n_nl + 2) * sizeof(u64), (void**)&d_ls));
     ICU(cudaMemsetAsync(d_ls, 0, sizeof(u64), stream));
     nl_mark<<<(unsigned)n_tiles, 256, 0, stream>>>(d_text, n_bytes, d_toff, d_ls);
     if (n_lines > p->max_overlaps) n_lines = p->max_overlaps;   // while (getline(...) && i < max_overlaps), :581
     st->n_lines = n_lines;
     if (n_lines == 0) { ICU(cudaStreamSynchronize(stream)); goto done; }
     n_blocks = (n_lines + LINES_PER_BLOCK - 1) / LINES_PER_BLOCK;
-    ICU(cudaMalloc(&d_tmp, n_lines * sizeof(IngTmp)));
-    ICU(cudaMalloc(&d_status, n_lines));
-    ICU(cudaMalloc(&d_cs, n_blocks * sizeof(uint32_t))); ICU(cudaMalloc(&d_cf, n_blocks * sizeof(uint32_t)));
-    ICU(cudaMalloc(&d_os, n_blocks * sizeof(u64))); ICU(cudaMalloc(&d_of, n_blocks * sizeof(u64)));
-    ICU(cudaMalloc(&d_misc, 3 * sizeof(u64)));
+    ICU(ws_get(m, 4, n_lines * sizeof(hc_candidate), (void**)&d_tmp_c));
+    ICU(ws_get(m, 5, n_lines * sizeof(hc_overlap_rec), (void**)&d_tmp_f));
+    ICU(ws_get(m, 6, n_lines, (void**)&d_status));
+    ICU(ws_get(m, 7, n_blocks * sizeof(uint32_t), (void**)&d_cs));
+    ICU(ws_get(m, 8, n_blocks * sizeof(uint32_t), (void**)&d_cf));
+    ICU(ws_get(m, 9, n_blocks * sizeof(u64), (void**)&d_os));
+    ICU(ws_get(m, 10, n_blocks * sizeof(u64), (void**)&d_of));
     ICU(cudaMemcpyAsync(d_misc, misc, sizeof(misc), cudaMemcpyHostToDevice, stream));
     D.text = d_text; D.n_bytes = n_bytes; D.line_start = d_ls; D.n_lines = n_lines; D.n_newlines = n_nl;
-    D.keys = m->keys; D.vals = m->vals; D.mask = m->mask;
+    D.ids.slots = m->slots; D.ids.mask = m->mask; D.ids.direct = m->direct; D.ids.direct_n = m->direct_n;
     D.min_overlap_len = p->min_overlap_len; D.min_overlap_perc = p->min_overlap_perc; D.relax = p->relax_PE_edges != 0;
     D.allow_spaces = p->allow_spaces != 0;
-    ing_parse<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>(D, d_tmp, d_status, d_misc + 2);
+    ing_parse<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>(D, d_tmp_c, d_tmp_f, d_status, d_misc + 2);
     ing_count<<<(unsigned)n_blocks, LINES_PER_BLOCK, 0, stream>>>(d_status, n_lines, d_cs, d_cf, d_misc);
     scan_counts<<<1, 1024, 0, stream>>>(d_cs, n_blocks, d_os, d_tot);
     scan_counts<<<1, 1024, 0, stream>>>(d_cf, n_blocks, d_of, d_tot + 1);
@@ -355,18 +409,14 @@ static int ingest_device(const hc_idmap* m, const char* d_text, u64 n_bytes, con
         rc = HC_ERR_CAPACITY;
         goto done;
     }
-    ing_scatter<<<(unsigned)n_blocks, LINES_PER_BLOCK, 0, stream>>>(d_status, d_tmp, n_lines, d_os, d_of, d_cand,
+    ing_scatter<<<(unsigned)n_blocks, LINES_PER_BLOCK, 0, stream>>>(d_status, d_tmp_c, d_tmp_f, n_lines, d_os, d_of, d_cand,
                                                                     reinterpret_cast<u64*>(d_cand_line), d_filt,
                                                                     reinterpret_cast<u64*>(d_filt_line));
-    ICU(cudaEventRecord(e1, stream));
+    ICU(cudaEventRecord(m->e1, stream));
     ICU(cudaStreamSynchronize(stream));
     ICU(cudaGetLastError());
-    ICU(cudaEventElapsedTime(&st->device_ms, e0, e1));
+    ICU(cudaEventElapsedTime(&st->device_ms, m->e0, m->e1));
 done:
-    cudaFree(d_tcnt); cudaFree(d_toff); cudaFree(d_tot); cudaFree(d_ls); cudaFree(d_tmp); cudaFree(d_status);
-    cudaFree(d_cs); cudaFree(d_cf); cudaFree(d_os); cudaFree(d_of); cudaFree(d_misc);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
     return rc;
 }
 
@@ -380,10 +430,11 @@ extern "C" int hc_ingest_overlaps_device(const hc_idmap* m, void* stream, const 
                          (cudaStream_t)stream);
 }
 
-extern "C" int hc_ingest_overlaps(const hc_idmap* m, const char* text, uint64_t n_bytes, const hc_ingest_params* p,
+extern "C" int hc_ingest_overlaps(const hc_idmap* cm, const char* text, uint64_t n_bytes, const hc_ingest_params* p,
                                   hc_candidate* cand, uint64_t* cand_line, uint64_t cand_cap, hc_overlap_rec* filtered,
                                   uint64_t* filtered_line, uint64_t filtered_cap, hc_ingest_stats* stats) {
-    if (!m || !p || !stats || (n_bytes && !text)) { hc_set_last_error("hc_ingest_overlaps: NULL argument"); return HC_ERR_ARG; }
+    if (!cm || !p || !stats || (n_bytes && !text)) { hc_set_last_error("hc_ingest_overlaps: NULL argument"); return HC_ERR_ARG; }
+    hc_idmap* m = const_cast<hc_idmap*>(cm);
     int rc = HC_OK;
     char* d_text = nullptr;
     hc_candidate* d_cand = nullptr;
@@ -393,10 +444,10 @@ extern "C" int hc_ingest_overlaps(const hc_idmap* m, const char* text, uint64_t 
     stats->first_error_line = EMPTY;
     if (n_bytes == 0) return HC_OK;
     ICU(cudaSetDevice(m->device));
-    ICU(cudaMalloc(&d_text, n_bytes + 16));
+    ICU(ws_get(m, 11, n_bytes + 16, (void**)&d_text));
     ICU(cudaMemcpy(d_text, text, n_bytes, cudaMemcpyHostToDevice));
-    if (cand_cap) { ICU(cudaMalloc(&d_cand, cand_cap * sizeof(hc_candidate))); if (cand_line) ICU(cudaMalloc(&d_cl, cand_cap * sizeof(u64))); }
-    if (filtered_cap) { ICU(cudaMalloc(&d_filt, filtered_cap * sizeof(hc_overlap_rec))); if (filtered_line) ICU(cudaMalloc(&d_fl, filtered_cap * sizeof(u64))); }
+    if (cand_cap) { ICU(ws_get(m, 12, cand_cap * sizeof(hc_candidate), (void**)&d_cand)); if (cand_line) ICU(ws_get(m, 14, cand_cap * sizeof(u64), (void**)&d_cl)); }
+    if (filtered_cap) { ICU(ws_get(m, 13, filtered_cap * sizeof(hc_overlap_rec), (void**)&d_filt)); if (filtered_line) ICU(ws_get(m, 15, filtered_cap * sizeof(u64), (void**)&d_fl)); }
     rc = ingest_device(m, d_text, n_bytes, p, d_cand, d_cl, cand_cap, d_filt, d_fl, filtered_cap, stats, 0);
     if (rc != HC_OK) goto done;
     if (stats->n_scored) {
@@ -408,6 +459,5 @@ extern "C" int hc_ingest_overlaps(const hc_idmap* m, const char* text, uint64_t 
         if (filtered_line) ICU(cudaMemcpy(filtered_line, d_fl, stats->n_filtered * sizeof(u64), cudaMemcpyDeviceToHost));
     }
 done:
-    cudaFree(d_text); cudaFree(d_cand); cudaFree(d_filt); cudaFree(d_cl); cudaFree(d_fl);
     return rc;
 }

@@ -50,6 +50,7 @@ int main(int argc, char** argv) {
         else if (a == "--exact_scores") ps.exact_scores = b(v);
         else if (a == "--gpu_dedup") ps.gpu_dedup = b(v);
         else if (a == "--gpu_parse") ps.gpu_parse = b(v);
+        else if (a == "--gpu_fastq") ps.gpu_fastq = b(v);
         else if (a == "--gpus") ps.n_devices = atoi(v.c_str());
         else if (a == "--dump-graph") dump_graph = v;
         else if (a == "--digraph") digraph = v;

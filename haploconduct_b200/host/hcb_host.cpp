@@ -115,7 +115,41 @@ void FastqStorage::read_pairs(const std::string& p1, const std::string& p2, unsi
     }
 }
 
+static std::string slurp_file(const std::string& path) {
+    if (path.empty() || path == "None") return std::string();
+    std::ifstream f(path.c_str(), std::ios::binary);
+    if (!f.is_open()) die("Unable to open fastq file " + path);                   // src/FastqStorage.cpp:54-56
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
 FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
+    if (ps.gpu_fastq) {
+        if (!ps.id_correspondence.empty()) die("--IDs is not supported together with --gpu_fastq");
+        const std::string s = slurp_file(ps.singles_file), p1 = slurp_file(ps.paired1_file), p2 = slurp_file(ps.paired2_file);
+        first_device_ = ps.first_device;
+        store_ = hc_store_create_fastq(s.data(), s.size(), p1.data(), p1.size(), p2.data(), p2.size(), ps.max_reads, ps.first_device,
+                                       ps.n_devices);
+        if (!store_) die(std::string("hc_store_create_fastq: ") + hc_last_error());
+        const uint64_t n = hc_store_n_reads(store_);
+        std::vector<uint64_t> ids(n);
+        std::vector<uint32_t> lens(2 * n);
+        if (hc_store_read_ids(store_, ids.data(), lens.data()) != HC_OK) die(hc_last_error());
+        m_readcount_single = (unsigned int)hc_store_n_single(store_);
+        m_readcount_paired = (unsigned int)(n - m_readcount_single);
+        m_read_vec.resize(n);
+        for (uint64_t i = 0; i < n; i++) {
+            m_read_vec[i].read_id = ids[i];
+            m_read_vec[i].is_paired = i >= m_readcount_single;
+            m_ID_to_index.insert(std::make_pair((read_id_t)ids[i], (unsigned int)i));
+        }
+        if (ps.verbose) {
+            std::cout << "Singles: " << m_readcount_single << std::endl;
+            std::cout << "Pairs: " << m_readcount_paired << std::endl;
+        }
+        return;
+    }
     if (!ps.id_correspondence.empty()) read_new_ids(ps.id_correspondence);
     if (!ps.singles_file.empty() && ps.singles_file != "None") read_singles(ps.singles_file, ps.max_reads);
     m_readcount_single = (unsigned int)m_read_vec.size();

@@ -52,6 +52,9 @@ struct ProgramSettings {           // names and defaults of src/Types.h:19-67 / 
     // duplicate-edge resolution of process_overlaps (score >= existing score, :470) needs to pick the
     // same representative when two overlaps of one read pair score within 1e-7 of each other.
     bool exact_scores = true;
+    // build the read store from the FASTQ text on the GPU (hc_store_create_fastq); m_read_vec then holds ids and
+    // read types only, no sequences (the id_correspondence table is not supported on this path)
+    bool gpu_fastq = false;
     // parse + pre-filter the overlaps file on the GPU (hc_ingest_overlaps) instead of the text loop of :581-645
     bool gpu_parse = false;
     // resolve duplicate edges on the GPU (hc_dedup_edges) instead of the sequential insert of :429-545

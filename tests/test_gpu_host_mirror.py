@@ -19,12 +19,13 @@ pytestmark = pytest.mark.gpu
 EXE = os.path.join(B.LIBDIR, "hc_edgecalc")
 
 
-def _run(g, tmp_path, exact, gpu_dedup=False, gpu_parse=False):
+def _run(g, tmp_path, exact, gpu_dedup=False, gpu_parse=False, gpu_fastq=False):
     d = str(tmp_path)
     F.write_fastq_set(g.rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", g.cands, g.rs.ids)
     cmd = [EXE, "--overlaps", d + "/ov.txt", "--dump-graph", d + "/graph.tsv", "--digraph", d + "/digraph.txt",
-           "--exact_scores=" + ("true" if exact else "false"), "--gpu_dedup=" + ("true" if gpu_dedup else "false"), "--gpu_parse=" + ("true" if gpu_parse else "false")]
+           "--exact_scores=" + ("true" if exact else "false"), "--gpu_dedup=" + ("true" if gpu_dedup else "false"), "--gpu_parse=" + ("true" if gpu_parse else "false"),
+           "--gpu_fastq=" + ("true" if gpu_fastq else "false")]
     if g.rs.n_single:
         cmd += ["--singles", d + "/s.fastq"]
     if g.rs.n_reads > g.rs.n_single:
@@ -69,9 +70,10 @@ def test_graph_identical_with_device_dedup(built_lib, tmp_path, name):
 
 @pytest.mark.parametrize("name", golden_names())
 def test_graph_identical_with_device_parse_and_dedup(built_lib, tmp_path, name):
-    """--gpu_parse=true --gpu_dedup=true: text loop (:581-645) and duplicate resolution (:429-545) on the device too."""
+    """--gpu_fastq --gpu_parse --gpu_dedup: FASTQ reading (src/FastqStorage.cpp:92-235), the overlaps-file text loop
+    (:581-645) and duplicate resolution (:429-545) on the device too: files in, graph out."""
     g = load_golden(name)
-    summary, graph, nonedge, digraph = _run(g, tmp_path, exact=True, gpu_dedup=True, gpu_parse=True)
+    summary, graph, nonedge, digraph = _run(g, tmp_path, exact=True, gpu_dedup=True, gpu_parse=True, gpu_fastq=True)
     assert np.array_equal(graph, g.ref_graph), name
     assert nonedge == g.ref_nonedge
     assert [summary["graph_edges"], summary["dup_count"], summary["inclusion_count"]] == g.ref_counts.tolist()

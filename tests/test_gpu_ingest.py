@@ -50,7 +50,7 @@ def test_ingest_reproduces_reference(built_lib, name):
 @pytest.mark.parametrize("seed,allow_spaces", [(11, False), (12, True), (13, False)])
 def test_ingest_fuzz_against_restatement(built_lib, seed, allow_spaces):
     g = load_golden("synth_all_types" if seed != 13 else "synth_mismatch_void")
-    ids = g.rs.ids * 3 + 1000 if seed == 13 else g.rs.ids       # sparse ids
+    ids = g.rs.ids * np.uint64(2 ** 40 + 12345) + np.uint64(7) if seed == 13 else g.rs.ids       # sparse ids: hash table, not the direct table
     text = W.fuzz_overlap_text(g.cands, ids, seed=seed, allow_spaces=allow_spaces)
     _check_against_oracle(text, ids, min_overlap_len=80, min_overlap_perc=20, relax_PE_edges=seed == 13, allow_spaces=allow_spaces)
     _check_against_oracle(text, ids, min_overlap_len=80, max_overlaps=1000, allow_spaces=allow_spaces)

@@ -77,8 +77,9 @@ def main():
     torch.cuda.synchronize()
     wall_dev = (time.perf_counter() - wall0) / a.steps * 1e3
     # host buffers end to end
-    cand = np.zeros(n_lines, dtype=F.CANDIDATE)
-    filt = np.zeros(n_lines, dtype=F.OVERLAP_REC)
+    h_cand = torch.empty(n_lines * 32, dtype=torch.uint8).pin_memory()       # pinned, like the text
+    h_filt = torch.empty(n_lines * 48, dtype=torch.uint8).pin_memory()
+    cand, filt = h_cand.numpy(), h_filt.numpy()
     buf = h_text.numpy()
 
     def host_step():
