@@ -228,6 +228,7 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=dev)
     t_setup = time.time()
     pr = WT.make_paired_reads(args.pairs, read_len=args.read_len, seed=args.seed, device=str(dev),
