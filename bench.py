@@ -39,6 +39,17 @@ PARAMS = dict(edge_threshold=0.97, ov_threshold=0.9, merge_contigs=0.0, mismatch
 MIN_OVERLAP_LEN = 150
 
 
+# stdout carries exactly one JSON line: everything libraries print to file descriptor 1 (NCCL prints its version
+# there when NCCL_DEBUG=VERSION) is sent to stderr, the line itself goes to the saved descriptor.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -216,7 +227,7 @@ def main() -> None:
                                  "cpu": cpu_model()},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
                 "setup_s": round(time.time() - t0, 1)}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -228,7 +239,6 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=dev)
     t_setup = time.time()
     pr = WT.make_paired_reads(args.pairs, read_len=args.read_len, seed=args.seed, device=str(dev),
@@ -377,7 +387,7 @@ def main() -> None:
                                                   % (len(cs), n_reads), "one_thread_value": t1, "cpu": cpu_model()}
             except Exception as ex:   # the baseline is a reported number, never a reason to lose the GPU line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     store.close()
     if world > 1:
         dist.destroy_process_group()
