@@ -7,9 +7,14 @@
 #include "../../include/hc_b200.h"
 #include "hc_layout.h"
 
+#ifndef HC_WARPS_MAX
 #define HC_WARPS_MAX 12
+#endif
 #define HC_LANE_CHUNK 32u        // positions one lane handles per step (two 16-position halves)
-#define HC_PARTMAX 512u          // lane-chunk partials per warp round (x 8 B = 4 KB of shared memory)
+#ifndef HC_PARTMAX
+#define HC_PARTMAX 512u
+#endif
+//                            // lane-chunk partials per warp round (x 8 B = 4 KB of shared memory)
 #define HC_BIG_CHUNKS 64u        // candidates with >= this many lane-chunks are scored warp-cooperatively
 #define HC_WINSLOTS 64u          // 2 windows x 32 candidates
 #define HC_VM_WORDS 64u          // tail-mask table of the packed layout (33 used), kept behind the score table
