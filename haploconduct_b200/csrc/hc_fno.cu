@@ -17,6 +17,7 @@
 #include <string>
 #include <cuda_runtime.h>
 #include "../../include/hc_b200.h"
+#include "hc_scan.cuh"
 
 namespace {
 
@@ -144,44 +145,6 @@ __global__ void fno_count(FnoDev D, const hc_fno_edge* edges, u64 n, uint32_t* c
         const u64 b = D.visited[e.v] ? D.sr_off[e.v + 1] - D.sr_off[e.v] : 1;
         cnt[i] = (uint32_t)(a * b);
     }
-}
-
-// single-block exclusive scan uint32 -> u64 (inputs are small: <= 1e7-1e8 items)
-__global__ void __launch_bounds__(1024) scan_u32(const uint32_t* in, u64 n, u64* out, u64* total) {
-    __shared__ u64 wsum[32];
-    __shared__ u64 carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (u64 b0 = 0; b0 < n; b0 += 1024) {
-        const u64 i = b0 + threadIdx.x;
-        const u64 v = i < n ? in[i] : 0;
-        u64 inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const u64 t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const u64 w = wsum[lane];
-            u64 s = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u64 t = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += t;
-            }
-            wsum[lane] = s - w;
-        }
-        __syncthreads();
-        const u64 c = carry;
-        if (i < n) out[i] = c + wsum[warp] + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = c + wsum[31] + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
 }
 
 __global__ void fno_claim(FnoDev D, const hc_fno_edge* edges, u64 n, const u64* off, u64* keys, u64* mins, u64 mask) {
@@ -402,7 +365,7 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     int rc = HC_OK;
     uint8_t *d_vis = nullptr, *d_lab = nullptr;
     hc_fno_read *d_vr = nullptr, *d_sr = nullptr;
-    u64 *d_sroff = nullptr, *d_off = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr;
+    u64 *d_sroff = nullptr, *d_off = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr, *d_bsum = nullptr;
     uint32_t *d_sridx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
     hc_fno_subread* d_sub = nullptr;
     hc_fno_edge* d_edges = nullptr;
@@ -430,7 +393,8 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     D.n_vertices = V; D.visited = d_vis; D.label = d_lab; D.vertex_read = d_vr; D.sr_off = d_sroff; D.sr_idx = d_sridx;
     D.sr_sub = d_sub; D.superread = d_sr; D.resolve_orientations = in->resolve_orientations; D.no_inclusions = in->no_inclusions;
     fno_count<<<blocks, threads>>>(D, d_edges, n_edges, d_cnt);
-    scan_u32<<<1, 1024>>>(d_cnt, n_edges, d_off, d_total);
+    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(n_edges) * sizeof(u64)));
+    hc_scan::exclusive_u32(d_cnt, n_edges, d_off, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     if (attempts == 0) goto done;
     while (cap < 2 * attempts + 2) cap <<= 1;
@@ -440,7 +404,9 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     FCU(cudaMemset(d_flags, 0, attempts * sizeof(uint32_t)));
     fno_claim<<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1);
     fno_resolve<false><<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
-    scan_u32<<<1, 1024>>>(d_flags, attempts, d_outpos, d_total);
+    cudaFree(d_bsum); d_bsum = nullptr;
+    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
+    hc_scan::exclusive_u32(d_flags, attempts, d_outpos, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&produced, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     *n_out = produced;
     if (produced > out_cap) { hc_set_last_error("hc_fno1: output buffer too small (required size returned in n_out)"); rc = HC_ERR_CAPACITY; goto done; }
@@ -453,7 +419,7 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
 done:
     cudaFree(d_vis); cudaFree(d_lab); cudaFree(d_vr); cudaFree(d_sr); cudaFree(d_sroff); cudaFree(d_sridx); cudaFree(d_sub);
     cudaFree(d_edges); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_total); cudaFree(d_keys); cudaFree(d_mins);
-    cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out);
+    cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out); cudaFree(d_bsum);
     return rc;
 }
 
@@ -471,7 +437,7 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     for (u64 i = 0; i < nent; i++)
         if (sr_idx[i] >= n_reads) { hc_set_last_error("hc_fno3: read index out of range"); return HC_ERR_ARG; }
     int rc = HC_OK;
-    u64 *d_off = nullptr, *d_seq = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr;
+    u64 *d_off = nullptr, *d_seq = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr, *d_bsum = nullptr;
     uint32_t *d_idx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
     hc_fno3_pos* d_pos = nullptr;
     hc_fno_read* d_reads = nullptr;
@@ -489,7 +455,8 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     FCU(cudaMemcpy(d_pos, sr_pos, nent * sizeof(hc_fno3_pos), cudaMemcpyHostToDevice));
     FCU(cudaMemcpy(d_reads, reads, n_reads * sizeof(hc_fno_read), cudaMemcpyHostToDevice));
     fno3_count<<<blocks, threads>>>(d_off, n_originals, d_cnt);
-    scan_u32<<<1, 1024>>>(d_cnt, n_originals, d_seq, d_total);
+    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(n_originals) * sizeof(u64)));
+    hc_scan::exclusive_u32(d_cnt, n_originals, d_seq, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     if (attempts == 0) goto done;
     while (cap < 2 * attempts + 2) cap <<= 1;
@@ -498,7 +465,9 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     FCU(cudaMalloc(&d_flags, attempts * sizeof(uint32_t))); FCU(cudaMalloc(&d_outpos, attempts * sizeof(u64)));
     fno3_pass<0><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, nullptr, nullptr, nullptr, 0);
     fno3_pass<1><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
-    scan_u32<<<1, 1024>>>(d_flags, attempts, d_outpos, d_total);
+    cudaFree(d_bsum); d_bsum = nullptr;
+    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
+    hc_scan::exclusive_u32(d_flags, attempts, d_outpos, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&produced, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     *n_out = produced;
     if (produced > out_cap) { hc_set_last_error("hc_fno3: output buffer too small (required size returned in n_out)"); rc = HC_ERR_CAPACITY; goto done; }
@@ -509,6 +478,6 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     FCU(cudaMemcpy(out, d_out, produced * sizeof(hc_fno_overlap), cudaMemcpyDeviceToHost));
 done:
     cudaFree(d_off); cudaFree(d_idx); cudaFree(d_pos); cudaFree(d_reads); cudaFree(d_cnt); cudaFree(d_seq); cudaFree(d_total);
-    cudaFree(d_keys); cudaFree(d_mins); cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out);
+    cudaFree(d_keys); cudaFree(d_mins); cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out); cudaFree(d_bsum);
     return rc;
 }

@@ -40,6 +40,7 @@ static cudaError_t ws_get(hc_idmap* m, int k, size_t bytes, void** out) {
 }
 
 #include "hc_text.cuh"
+#include "hc_scan.cuh"
 
 namespace {
 
@@ -357,11 +358,11 @@ static int ingest_device(const hc_idmap* cm, const char* d_text, u64 n_bytes, co
     if (n_bytes == 0) return HC_OK;
     ICU(ws_get(m, 0, n_tiles * sizeof(uint32_t), (void**)&d_tcnt));
     ICU(ws_get(m, 1, n_tiles * sizeof(u64), (void**)&d_toff));
-    ICU(ws_get(m, 2, 8 * sizeof(u64), (void**)&d_tot));
+    ICU(ws_get(m, 2, (8 + hc_scan::blocks_for(n_tiles)) * sizeof(u64), (void**)&d_tot));
     d_misc = d_tot + 2;
     ICU(cudaEventRecord(m->e0, stream));
     nl_count<<<(unsigned)n_tiles, 256, 0, stream>>>(d_text, n_bytes, d_tcnt);
-    scan_counts<<<1, 1024, 0, stream>>>(d_tcnt, n_tiles, d_toff, d_tot);
+    hc_scan::exclusive_u32(d_tcnt, n_tiles, d_toff, d_tot, d_tot + 8, stream);
     ICU(cudaMemcpyAsync(&n_nl, d_tot, sizeof(u64), cudaMemcpyDeviceToHost, stream));
     ICU(cudaMemcpyAsync(&last, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, stream));
     ICU(cudaStreamSynchronize(stream));
