@@ -75,3 +75,21 @@ def test_permutation_equivariance(built_lib, c4_small):
         _, _, a, _ = st.score_batch(p, sub)
         _, _, b, _ = st.score_batch(p, sub[perm])
     assert a[perm].tobytes() == b.tobytes()
+
+
+def test_store_replicated_on_two_devices(built_lib):
+    """n_devices = 2 in one process: the planes packed on the first device are copied to the second, the batch is cut into
+    two contiguous shards and the lists come back in input order -- identical to the one-device result."""
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from util import load_golden
+    g = load_golden("synth_all_types")
+    cands = np.tile(g.scored(), 5)
+    with capi.Store(g.rs) as st1:
+        e1, n1, p1, _ = st1.score_batch(g.params(), cands)
+    with capi.Store(g.rs, first_device=0, n_devices=2) as st2:
+        e2, n2, p2, _ = st2.score_batch(g.params(), cands)
+    assert p1.tobytes() == p2.tobytes() and e1.tobytes() == e2.tobytes() and np.array_equal(n1, n2)
+    with capi.Store(g.rs, first_device=1, n_devices=1) as st3:           # a store that lives on the second device only
+        e3, n3, p3, _ = st3.score_batch(g.params(), cands)
+    assert p1.tobytes() == p3.tobytes() and e1.tobytes() == e3.tobytes()
