@@ -188,6 +188,8 @@ def main() -> None:
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="candidates in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-records", default="short", choices=["short", "compact"],
+                    help="host record of the e2e leg: 12-byte hc_candidate_short (reads < 16384 bases) or 16-byte hc_candidate_compact")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--exact-edge-scores", action="store_true",
                     help="HC_FLAG_EXACT_EDGE_SCORES: re-sum every accepted edge in the reference's order (diagnostic)")
@@ -301,13 +303,20 @@ def main() -> None:
     # ---- e2e through the host-buffer entry point
     e2e = None
     if not args.no_e2e:
-        # the host-facing call on the 16-byte compact records (idx1, idx2, pos1|ori|ord, pos2)
+        # the host-facing call on the smallest record the reads allow: 12 bytes (idx1, idx2, pos1|pos2|ori|ord) when every
+        # position is below 2^14, else the 16-byte compact record (idx1, idx2, pos1|ori|ord, pos2)
         r32 = rec.view(torch.int32).reshape(-1, 8)
         ordc = torch.where(((r32[:, 6] >> 16) & 0xff) == ord("1"), 1, 2)
-        cc = torch.empty((n, 4), dtype=torch.int32, device=dev)
-        cc[:, 0] = r32[:, 0]; cc[:, 1] = r32[:, 1]; cc[:, 3] = r32[:, 3]
-        cc[:, 2] = r32[:, 2] | (3 << 28) | (ordc << 30).to(torch.int32)      # POS1 | ORI1 '+' | ORI2 '+' | ORD
-        h_cand = torch.empty((n, 4), dtype=torch.int32, pin_memory=True)
+        short = args.e2e_records == "short" and args.read_len < (1 << 14)
+        rec_bytes = 12 if short else 16
+        cc = torch.empty((n, rec_bytes // 4), dtype=torch.int32, device=dev)
+        cc[:, 0] = r32[:, 0]; cc[:, 1] = r32[:, 1]
+        if short:
+            cc[:, 2] = r32[:, 2] | (r32[:, 3] << 14) | (3 << 28) | (ordc << 30).to(torch.int32)   # POS1 | POS2 | ORI '+','+' | ORD
+        else:
+            cc[:, 3] = r32[:, 3]
+            cc[:, 2] = r32[:, 2] | (3 << 28) | (ordc << 30).to(torch.int32)      # POS1 | ORI1 '+' | ORI2 '+' | ORD
+        h_cand = torch.empty((n, rec_bytes // 4), dtype=torch.int32, pin_memory=True)
         h_cand.copy_(cc)
         del cc
         ne, nn = int(counts[0]), int(counts[1])
@@ -318,13 +327,14 @@ def main() -> None:
         c_ne, c_nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
 
         def e2e_step():
-            rc = L.hc_score_batch_compact(store.handle, params.ctypes.data, h_cand.data_ptr(), n, None, h_edges.data_ptr(),
+            fn = L.hc_score_batch_short if short else L.hc_score_batch_compact
+            rc = fn(store.handle, params.ctypes.data, h_cand.data_ptr(), n, None, h_edges.data_ptr(),
                                   h_edges.shape[0], ctypes.byref(c_ne), h_nonedge.data_ptr(), h_nonedge.shape[0],
                                   ctypes.byref(c_nn), None)
             if rc != 0:
                 raise RuntimeError(capi.last_error())
 
-        for _ in range(2):
+        for _ in range(max(args.warmup, 3)):
             e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -333,7 +343,7 @@ def main() -> None:
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert c_ne.value == ne and c_nn.value == nn
-        e2e = (e2e_ms, n * 16, ne * 48 + nn * 8 + 64)
+        e2e = (e2e_ms, n * rec_bytes, ne * 48 + nn * 8 + 64, "hc_candidate_short (12 B)" if short else "hc_candidate_compact (16 B)")
 
     ms_step = ms_total / args.steps
     tvals = torch.tensor([ms_step, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
@@ -368,7 +378,7 @@ def main() -> None:
         }
         if e2e:
             line["e2e"] = {"value": total_cands / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[1],
-                           "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms}
+                           "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms, "records": e2e[3]}
         if world == 1 and not args.no_cpu:
             try:
                 cs = WT.candidates_as_numpy(rec[: args.cpu_sample])

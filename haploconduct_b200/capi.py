@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("HC_B200_LIB") or os.path.join(HERE, "lib", "libhc_b20
 # every symbol include/hc_b200.h declares
 EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
-    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_device",
+    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
     "hc_store_create_fastq", "hc_store_read_ids", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
@@ -62,6 +62,8 @@ def lib() -> ctypes.CDLL:
         L.hc_score_batch.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
         L.hc_score_batch_compact.restype = i32
         L.hc_score_batch_compact.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
+        L.hc_score_batch_short.restype = i32
+        L.hc_score_batch_short.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
         L.hc_score_batch_device.restype = i32
         L.hc_score_batch_device.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, u64, vp, u64, vp, vp]
         L.hc_overlap_score.restype = dbl
@@ -171,10 +173,14 @@ class Store:
 
     def score_batch(self, params: np.ndarray, cands: np.ndarray, per_candidate: bool = True, edges_cap: Optional[int] = None,
                     nonedge_cap: Optional[int] = None, compact: bool = False):
-        """hc_score_batch (or hc_score_batch_compact) on HOST buffers.
-        Returns (edges, nonedge_idx, per_cand or None, stats)."""
+        """hc_score_batch on HOST buffers; compact=True -> hc_score_batch_compact (16-byte records), compact="short" ->
+        hc_score_batch_short (12-byte records).  Returns (edges, nonedge_idx, per_cand or None, stats)."""
         L = lib()
-        cands = np.ascontiguousarray(F.compact_candidates(cands) if compact else cands)
+        if compact == "short":
+            cands = F.short_candidates(cands)
+        elif compact:
+            cands = F.compact_candidates(cands)
+        cands = np.ascontiguousarray(cands)
         n = len(cands)
         ecap = n if edges_cap is None else edges_cap
         ncap = n if nonedge_cap is None else nonedge_cap
@@ -183,7 +189,7 @@ class Store:
         per = np.zeros(n, dtype=F.RESULT) if per_candidate else None
         ne, nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
         stats = np.zeros(1, dtype=F.BATCH_STATS)
-        fn = L.hc_score_batch_compact if compact else L.hc_score_batch
+        fn = L.hc_score_batch_short if compact == "short" else (L.hc_score_batch_compact if compact else L.hc_score_batch)
         rc = fn(self._h, params.ctypes.data, cands.ctypes.data if n else None, n,
                               per.ctypes.data if per is not None and n else None, edges.ctypes.data, ecap, ctypes.byref(ne),
                               nonedge.ctypes.data, ncap, ctypes.byref(nn), stats.ctypes.data)

@@ -180,7 +180,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     P.pk = d.pk; P.packed = s->packed ? 1u : 0u;
     P.n_reads = (uint32_t)s->n_reads; P.n_single = (uint32_t)s->n_single;
     P.fx_table = d.fx_table; P.dbl_table = d.dbl_table; P.ncodes = (uint32_t)s->ncodes; P.has_void = d.has_void ? 1u : 0u;
-    P.cand = d_cand; P.cand_compact = compact ? 1u : 0u; P.run = d_run; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
+    P.cand = d_cand; P.cand_compact = (uint32_t)compact; P.run = d_run; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
     P.counters = d.counters;
     P.t_edge = hc_tables_exp_threshold(p->edge_threshold, &mono);
     if (!mono) return fail(HC_ERR_ARG, "host exp() is not monotone around edge_threshold");
@@ -608,9 +608,9 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
     if (stats) memset(stats, 0, sizeof(*stats));
     *n_edges = 0;
     *n_nonedges = 0;
-    const size_t rec = compact ? sizeof(hc_candidate_compact) : sizeof(hc_candidate);
+    const size_t rec = compact == 2 ? sizeof(hc_candidate_short) : (compact ? sizeof(hc_candidate_compact) : sizeof(hc_candidate));
     const int G = (int)s->devs.size();
-    uint64_t chunk = 16ull << 20;
+    uint64_t chunk = 8ull << 20;   // candidates per pipeline step (measured: 8 M beats 2, 4 and 16 M end to end)
     if (const char* e = getenv("HC_HOST_CHUNK")) { const uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }   // tests
     std::vector<uint64_t> lo(G + 1);
     for (int g = 0; g <= G; g++) lo[g] = n * (uint64_t)g / (uint64_t)G;   // contiguous index ranges
@@ -750,6 +750,12 @@ int hc_score_batch_compact(hc_store* s, const hc_params* p, const hc_candidate_c
                            hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
                            uint64_t* n_nonedges, hc_batch_stats* stats) {
     return score_host(s, p, cand, 1, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats);
+}
+
+int hc_score_batch_short(hc_store* s, const hc_params* p, const hc_candidate_short* cand, uint64_t n, hc_result* per_cand,
+                         hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
+                         uint64_t* n_nonedges, hc_batch_stats* stats) {
+    return score_host(s, p, cand, 2, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats);
 }
 
 int hc_overlap_score_multi(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,

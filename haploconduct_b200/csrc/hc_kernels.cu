@@ -44,6 +44,16 @@ struct CandSetup {
 
 __device__ __forceinline__ hc_candidate load_candidate(const hc_kparams& P, u64 i) {
     hc_candidate c;
+    if (P.cand_compact == 2u) {   // hc_candidate_short: 12 bytes, positions below 2^14
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(P.cand) + 3 * i;
+        const uint32_t w = __ldg(sp + 2);
+        c.idx1 = __ldg(sp); c.idx2 = __ldg(sp + 1); c.pos1 = w & 0x3fffu; c.pos2 = (w >> 14) & 0x3fffu;
+        c.len1 = c.len2 = 0; c.perc1 = c.perc2 = 0; c.type1 = c.type2 = 0; c.reserved = 0;
+        c.ori1 = (w >> 28) & 1u; c.ori2 = (w >> 29) & 1u;
+        const uint32_t o = w >> 30;
+        c.ord = o == 1 ? '1' : (o == 2 ? '2' : '-');
+        return c;
+    }
     if (P.cand_compact) {
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.cand) + i);
         c.idx1 = a.x; c.idx2 = a.y; c.pos1 = a.z & 0x0fffffffu; c.pos2 = a.w;

@@ -49,7 +49,7 @@ struct hc_kparams {
     uint32_t ncodes;
     uint32_t has_void;
     // batch
-    const void* cand;           // hc_candidate[n] (cand_compact == 0) or hc_candidate_compact[n]
+    const void* cand;           // hc_candidate[n] (cand_compact == 0), hc_candidate_compact[n] (1) or hc_candidate_short[n] (2)
     uint32_t cand_compact;
     const unsigned long long* run;   // nullable: running {edges, non-edges} totals of earlier chunks = output base offsets
     uint64_t n;

@@ -37,6 +37,22 @@ def compact_candidates(c: np.ndarray) -> np.ndarray:
     return out
 
 
+CANDIDATE_SHORT = np.dtype([("idx1", "<u4"), ("idx2", "<u4"), ("pos", "<u4")])
+assert CANDIDATE_SHORT.itemsize == 12
+
+
+def short_candidates(c: np.ndarray) -> np.ndarray:
+    """hc_candidate -> hc_candidate_short (POS1 and POS2 must be below 2^14)."""
+    if len(c) and (int(c["pos1"].max()) >= (1 << 14) or int(c["pos2"].max()) >= (1 << 14)):
+        raise ValueError("positions do not fit the 12-byte candidate record")
+    out = np.zeros(len(c), dtype=CANDIDATE_SHORT)
+    out["idx1"], out["idx2"] = c["idx1"], c["idx2"]
+    ordc = np.where(c["ord"] == ord("1"), 1, np.where(c["ord"] == ord("2"), 2, 0)).astype(np.uint32)
+    out["pos"] = (c["pos1"] | (c["pos2"].astype(np.uint32) << 14) | ((c["ori1"] != 0).astype(np.uint32) << 28)
+                  | ((c["ori2"] != 0).astype(np.uint32) << 29) | (ordc << 30))
+    return out
+
+
 PARAMS = np.dtype(
     [
         ("edge_threshold", "<f8"), ("ov_threshold", "<f8"), ("merge_contigs", "<f8"), ("mismatch", "<f8"),

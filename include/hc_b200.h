@@ -104,6 +104,13 @@ typedef struct {
     uint32_t pos2;
 } hc_candidate_compact;      /* 16 bytes */
 
+/* 12-byte form for stores whose reads are shorter than 16384 bases (every short-read stage): three quarters of
+ * the compact record again.  Positions that do not fit must use hc_candidate_compact. */
+typedef struct {
+    uint32_t idx1, idx2;
+    uint32_t pos;            /* POS1 in bits 0-13, POS2 in bits 14-27; bit 28: ORI1 is '+'; bit 29: ORI2 is '+'; bits 30-31: ORD 0 '-', 1 '1', 2 '2' */
+} hc_candidate_short;        /* 12 bytes */
+
 /* Scoring parameters = the ProgramSettings fields the path reads (src/Types.h:19-67). */
 typedef struct {
     double   edge_threshold;   /* src/EdgeCalculator.cpp:404 and per half :256,:294,:355 */
@@ -193,6 +200,14 @@ int hc_score_batch_compact(hc_store* s, const hc_params* p,
                            hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges,
                            uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
                            hc_batch_stats* stats /* nullable */);
+
+/* hc_score_batch on 12-byte records (reads shorter than 16384 bases). */
+int hc_score_batch_short(hc_store* s, const hc_params* p,
+                         const hc_candidate_short* cand, uint64_t n,
+                         hc_result* per_cand,
+                         hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges,
+                         uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
+                         hc_batch_stats* stats /* nullable */);
 
 /* Same, but every buffer is DEVICE memory on device `device` (one of the store's devices) and the
  * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream).

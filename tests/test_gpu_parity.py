@@ -260,6 +260,14 @@ def test_chunked_pipeline_and_compact_records(built_lib, monkeypatch, chunk):
         e1, n1, per1, s1 = st.score_batch(p, cands)
         e2, n2, per2, s2 = st.score_batch(p, cands, compact=True)
         e3, n3, _, _ = st.score_batch(p, cands, per_candidate=False, compact=True, edges_cap=len(e0), nonedge_cap=len(n0))
+        fits = (cands["pos1"] < (1 << 14)) & (cands["pos2"] < (1 << 14))      # the 12-byte records hold 14-bit positions
+        e4, n4, per4, s4 = st.score_batch(p, cands[fits], compact="short")
+        e5, n5, per5, s5 = st.score_batch(p, cands[fits])
+    assert fits.sum() > 0.9 * len(cands) and not fits.all()
+    with pytest.raises(ValueError):
+        F.short_candidates(cands)
+    assert e4.tobytes() == e5.tobytes() and np.array_equal(n4, n5) and per4.tobytes() == per5.tobytes()
+    assert per4.tobytes() == per0[fits].tobytes()
     for e, n, per, s in ((e1, n1, per1, s1), (e2, n2, per2, s2)):
         assert e.tobytes() == e0.tobytes() and np.array_equal(n, n0) and per.tobytes() == per0.tobytes()
         assert int(s["n_positions"]) == int(s0["n_positions"]) and int(s["n_edges"]) == len(e0)
