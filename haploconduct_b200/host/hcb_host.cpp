@@ -142,6 +142,7 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         for (uint64_t i = 0; i < n; i++) {
             m_read_vec[i].read_id = ids[i];
             m_read_vec[i].is_paired = i >= m_readcount_single;
+            max_read_len = std::max(max_read_len, std::max(lens[2 * i], lens[2 * i + 1]));
             m_ID_to_index.insert(std::make_pair((read_id_t)ids[i], (unsigned int)i));
         }
         if (ps.verbose) {
@@ -172,6 +173,7 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         const Read& r = m_read_vec[i];
         if (r.seq1.size() != r.phred1.size() || r.seq2.size() != r.phred2.size())
             die("read with ID " + std::to_string(r.read_id) + ": sequence and quality lengths differ");   // string::at would throw, :93-94
+        max_read_len = std::max(max_read_len, (unsigned int)std::max(r.seq1.size(), r.seq2.size()));
         descs[i].seq_off[0] = bases.size();
         descs[i].seq_len[0] = (uint32_t)r.seq1.size();
         bases += r.seq1;
@@ -381,8 +383,21 @@ void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
     uint64_t ne = 0, nn = 0;
     hc_batch_stats st;
     const hc_params p = to_params(ps_);
-    const int rc = hc_score_batch(fastq_->device_store(), &p, cand.data(), n, nullptr, edges.data(), n, &ne, nonedge.data(), n,
-                                  &nn, &st);
+    int rc;
+    bool fits = fastq_->max_read_len < (1u << 14);
+    for (size_t i = 0; i < n && fits; i++) fits = cand[i].pos1 < (1u << 14) && cand[i].pos2 < (1u << 14);
+    if (fits) {   // 12-byte records: the device reads nothing else of a candidate, and the copy in is what bounds the call
+        std::vector<hc_candidate_short> sc(n);
+        for (size_t i = 0; i < n; i++) {
+            const hc_candidate& c = cand[i];
+            const uint32_t o = c.ord == '1' ? 1u : (c.ord == '2' ? 2u : 0u);
+            sc[i].idx1 = c.idx1; sc[i].idx2 = c.idx2;
+            sc[i].pos = c.pos1 | (c.pos2 << 14) | ((uint32_t)(c.ori1 != 0) << 28) | ((uint32_t)(c.ori2 != 0) << 29) | (o << 30);
+        }
+        rc = hc_score_batch_short(fastq_->device_store(), &p, sc.data(), n, nullptr, edges.data(), n, &ne, nonedge.data(), n, &nn, &st);
+    } else {
+        rc = hc_score_batch(fastq_->device_store(), &p, cand.data(), n, nullptr, edges.data(), n, &ne, nonedge.data(), n, &nn, &st);
+    }
     if (rc != HC_OK) die(std::string("hc_score_batch: ") + hc_last_error());
     scored_candidates += n;
     device_ms += st.total_ms;

@@ -82,6 +82,7 @@ public:
     std::vector<Read> m_read_vec;                     // singles first, then pairs (src/FastqStorage.h:88-97)
     std::map<read_id_t, unsigned int> m_ID_to_index;  // src/FastqStorage.h:54
     unsigned int m_readcount_single = 0, m_readcount_paired = 0;
+    unsigned int max_read_len = 0;                    // longest mate (decides the candidate record size)
 
     unsigned int get_readcount() const { return (unsigned int)m_read_vec.size(); }
     hc_store* device_store() const { return store_; }
