@@ -108,13 +108,14 @@ __device__ uint32_t dev_atoi(const char* t, u64 p, u64 q) {
     if (p < q && (t[p] == '+' || t[p] == '-')) { neg = t[p] == '-'; p++; }
     u64 v = 0;
     bool ovf = false;
-    const u64 lim = neg ? 0x8000000000000000ull : 0x7fffffffffffffffull;
+    const u64 cutoff = 0x7fffffffffffffffull / 10ull;            // LONG_MAX / 10 = |LONG_MIN| / 10
+    const u64 cutlim = neg ? 8ull : 7ull;                        // |LONG_MIN| % 10, LONG_MAX % 10
     for (; p < q; p++) {
         const char c = t[p];
         if (c < '0' || c > '9') break;
         const u64 d = (u64)(c - '0');
-        if (!ovf && v > (lim - d) / 10ull) ovf = true;
-        if (!ovf) v = v * 10ull + d;
+        if (v > cutoff || (v == cutoff && d > cutlim)) ovf = true;
+        else if (!ovf) v = v * 10ull + d;
     }
     long long r;
     if (ovf) r = neg ? (long long)0x8000000000000000ull : 0x7fffffffffffffffll;

@@ -127,6 +127,9 @@ __device__ u64 dev_strtoul0(const char* t, u64 p, u64 q) {
     }
     u64 v = 0;
     bool ovf = false;
+    // glibc's cutoff / cutlim test instead of a division per digit
+    const u64 cutoff = base == 10 ? ~0ull / 10ull : (base == 16 ? ~0ull >> 4 : ~0ull >> 3);
+    const int cutlim = base == 10 ? (int)(~0ull % 10ull) : base - 1;
     for (; p < q; p++) {
         const char c = t[p];
         int d;
@@ -135,8 +138,8 @@ __device__ u64 dev_strtoul0(const char* t, u64 p, u64 q) {
         else if (c >= 'A' && c <= 'Z') d = c - 'A' + 10;
         else break;
         if (d >= base) break;
-        if (v > (~0ull - (u64)d) / (u64)base) ovf = true;
-        v = v * (u64)base + (u64)d;
+        if (v > cutoff || (v == cutoff && d > cutlim)) ovf = true;
+        else v = v * (u64)base + (u64)d;
     }
     if (ovf) return ~0ull;                     // ULONG_MAX, whatever the sign
     return neg ? 0ull - v : v;
