@@ -7,11 +7,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <iostream>
 #include <sstream>
 
 namespace hcb {
+
+static double wall_s() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 void die(const std::string& msg) {
     std::cerr << msg;
@@ -245,6 +252,21 @@ Overlap Overlap::from_fields(const std::vector<std::string>& f) {               
     return o;
 }
 
+// Overlap::get_overlap_line appended to a buffer without the thirteen std::to_string temporaries
+static inline void put_u64(std::string& b, unsigned long v) {
+    char tmp[24];
+    int k = 0;
+    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (k) b.push_back(tmp[--k]);
+}
+
+void Overlap::append_overlap_line(std::string& b) const {                         // src/Overlap.h:234-237
+    put_u64(b, id1); b.push_back('\t'); put_u64(b, id2); b.push_back('\t'); put_u64(b, pos1); b.push_back('\t'); put_u64(b, pos2);
+    b.push_back('\t'); b.push_back(ord); b.push_back('\t'); b.push_back(ori1); b.push_back('\t'); b.push_back(ori2); b.push_back('\t');
+    put_u64(b, perc1); b.push_back('\t'); put_u64(b, perc2); b.push_back('\t'); put_u64(b, len1); b.push_back('\t'); put_u64(b, len2);
+    b.push_back('\t'); b.push_back(type1); b.push_back('\t'); b.push_back(type2); b.push_back('\n');
+}
+
 std::string Overlap::get_overlap_line() const {                                   // src/Overlap.h:234-237
     std::string s = std::to_string(id1) + "\t" + std::to_string(id2) + "\t" + std::to_string(pos1) + "\t" +
                     std::to_string(pos2) + "\t";
@@ -378,12 +400,15 @@ void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
         c.ord = (uint8_t)o.ord; c.ori1 = o.ori1 == '+'; c.ori2 = o.ori2 == '+';
         c.type1 = (uint8_t)o.type1; c.type2 = (uint8_t)o.type2;
     }
-    std::vector<hc_edge> edges(n);
-    std::vector<uint64_t> nonedge(n);
+    std::unique_ptr<hc_edge[]> edges_buf(new hc_edge[n]);       // written by the call, not zero-initialised here
+    std::unique_ptr<uint64_t[]> nonedge_buf(new uint64_t[n]);
+    hc_edge* edges = edges_buf.get();
+    uint64_t* nonedge = nonedge_buf.get();
     uint64_t ne = 0, nn = 0;
     hc_batch_stats st;
     const hc_params p = to_params(ps_);
     int rc;
+    const double ts0 = wall_s();
     bool fits = fastq_->max_read_len < (1u << 14);
     for (size_t i = 0; i < n && fits; i++) fits = cand[i].pos1 < (1u << 14) && cand[i].pos2 < (1u << 14);
     if (fits) {   // 12-byte records: the device reads nothing else of a candidate, and the copy in is what bounds the call
@@ -394,13 +419,15 @@ void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
             sc[i].idx1 = c.idx1; sc[i].idx2 = c.idx2;
             sc[i].pos = c.pos1 | (c.pos2 << 14) | ((uint32_t)(c.ori1 != 0) << 28) | ((uint32_t)(c.ori2 != 0) << 29) | (o << 30);
         }
-        rc = hc_score_batch_short(fastq_->device_store(), &p, sc.data(), n, nullptr, edges.data(), n, &ne, nonedge.data(), n, &nn, &st);
+        rc = hc_score_batch_short(fastq_->device_store(), &p, sc.data(), n, nullptr, edges, n, &ne, nonedge, n, &nn, &st);
     } else {
-        rc = hc_score_batch(fastq_->device_store(), &p, cand.data(), n, nullptr, edges.data(), n, &ne, nonedge.data(), n, &nn, &st);
+        rc = hc_score_batch(fastq_->device_store(), &p, cand.data(), n, nullptr, edges, n, &ne, nonedge, n, &nn, &st);
     }
     if (rc != HC_OK) die(std::string("hc_score_batch: ") + hc_last_error());
     scored_candidates += n;
     device_ms += st.total_ms;
+    const double ts1 = wall_s();
+    t_score_s += ts1 - ts0;
 
     unsigned int doubles = 0;
     for (uint64_t k = 0; k < ne; k++) {
@@ -435,9 +462,18 @@ void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
         else insert_edge(e, doubles);
     }
     dup_count += doubles;
+    const double ts2 = wall_s();
+    t_edges_s += ts2 - ts1;
 
     std::ofstream out((ps_.output_dir + "nonedge_overlaps.txt").c_str(), std::fstream::out | std::fstream::app);
-    for (uint64_t k = 0; k < nn; k++) out << batch[nonedge[k]].get_overlap_line();
+    std::string buf;
+    buf.reserve(1 << 22);
+    for (uint64_t k = 0; k < nn; k++) {
+        batch[nonedge[k]].append_overlap_line(buf);
+        if (buf.size() > (1u << 22) - 256) { out.write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
+    }
+    out.write(buf.data(), (std::streamsize)buf.size());
+    t_write_s += wall_s() - ts2;
 }
 
 // One step of the sequential insert, src/EdgeCalculator.cpp:449-538 (the edge is already normalised).
@@ -542,7 +578,9 @@ void EdgeCalculator::ingest_on_device(std::vector<Overlap>& batch, std::vector<O
         ip.min_overlap_len = ps_.min_overlap_len; ip.min_overlap_perc = ps_.min_overlap_perc;
         ip.relax_PE_edges = ps_.relax_PE_edges; ip.allow_spaces = ps_.allow_spaces;
         hc_ingest_stats st;
+        const double ti0 = wall_s();
         const int rc = hc_ingest_overlaps(idmap, buf.data(), buf.size(), &ip, cand.data(), nullptr, cap, filt.data(), nullptr, cap, &st);
+        t_ingest_s += wall_s() - ti0;
         if (rc != HC_OK) die(std::string("hc_ingest_overlaps: ") + hc_last_error());
         if (st.first_error_line != ~0ull) {    // the reference ends at this line: let the host parser say why
             std::vector<Overlap> b2, f2;
@@ -623,7 +661,13 @@ void EdgeCalculator::construct_edges() {                                        
         std::cout << "Number of inclusion edges: " << inclusion_count << "\n";
     }
     std::ofstream out((ps_.output_dir + "nonedge_overlaps.txt").c_str(), std::fstream::out | std::fstream::app);   // :654-660
-    for (const Overlap& o : filtered) out << o.get_overlap_line();
+    std::string buf;
+    buf.reserve(1 << 22);
+    for (const Overlap& o : filtered) {
+        o.append_overlap_line(buf);
+        if (buf.size() > (1u << 22) - 256) { out.write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
+    }
+    out.write(buf.data(), (std::streamsize)buf.size());
 }
 
 }  // namespace hcb

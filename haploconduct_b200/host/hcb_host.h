@@ -112,6 +112,7 @@ struct Overlap {                   // src/Overlap.h:23-35
     static Overlap from_fields(const std::vector<std::string>& f);
     unsigned int get_perc() const { return perc2 > 0 ? (unsigned int)(0.5 * (perc1 + perc2)) : perc1; }   // :203-210
     std::string get_overlap_line() const;                                                                // :234-237
+    void append_overlap_line(std::string& buf) const;    // the same line appended to a buffer
 };
 
 struct Edge {                      // src/Edge.h:21-37
@@ -161,6 +162,7 @@ public:
     // measurements of the last construct_edges() (not in the reference)
     unsigned long scored_candidates = 0;
     double device_ms = 0, parse_device_ms = 0;
+    double t_ingest_s = 0, t_score_s = 0, t_edges_s = 0, t_write_s = 0;   // host wall clock per phase
 
 private:
     void process_overlaps(std::vector<Overlap>& batch);                                          // :389-557

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Files in, overlap graph out: EdgeCalculator::construct_edges() of the UNMODIFIED reference (oracle/_ref/ref_driver
+--run, all host threads) next to the host mirror on the B200 (haploconduct_b200/lib/hc_edgecalc), once with the host
+parsers and once with FASTQ reading, overlaps-file parsing and duplicate resolution on the device.  The three graphs
+must be identical (adjacency dump compared byte for byte).
+
+    python tools/bench_pipeline.py [--pairs 100000] [--partners 20]
+Prints one JSON line.  Benchmark tool, not product code."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from haploconduct_b200 import build as B, formats as F, workloads_torch as WT  # noqa: E402
+
+
+def write_inputs(d, pairs, read_len, partners, seed):
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    pr = WT.make_paired_reads(pairs, read_len=read_len, genome_len=max(20000, pairs // 10), seed=seed, device=dev)
+    rec = WT.candidates_as_numpy(WT.make_pp_candidates(pr, D=partners))
+    L = read_len
+    b = pr.bases.numpy().reshape(pairs, 2, L)
+    q = pr.quals.numpy().reshape(pairs, 2, L)
+    for m, name in ((0, "p1.fastq"), (1, "p2.fastq")):
+        with open(os.path.join(d, name), "wb") as f:
+            for i in range(pairs):
+                f.write(b"@%d\n" % i + b[i, m].tobytes() + b"\n+\n" + q[i, m].tobytes() + b"\n")
+    with open(os.path.join(d, "ov.txt"), "w") as f:
+        for c in rec:
+            f.write("%d\t%d\t%d\t%d\t%s\t+\t+\t%d\t%d\t%d\t%d\tp\tp\n" % (c["idx1"], c["idx2"], c["pos1"], c["pos2"], chr(c["ord"]),
+                                                                       c["perc1"], c["perc2"], c["len1"], c["len2"]))
+    return len(rec)
+
+
+def run(cmd, cwd):
+    t0 = time.perf_counter()
+    out = subprocess.run(cmd, cwd=cwd, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
+    wall = time.perf_counter() - t0
+    js = [json.loads(l) for l in out.split("\n") if l.startswith("{")]
+    return wall, (js[-1] if js else {})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=100_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--partners", type=int, default=20)
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--one-thread-limit", type=int, default=6_000_000, help="also run the reference on 1 thread up to this many candidates")
+    a = ap.parse_args()
+    d = tempfile.mkdtemp(prefix="hc_pipe_")
+    n_cand = write_inputs(d, a.pairs, a.read_len, a.partners, a.seed)
+    common = ["--overlaps", "ov.txt", "--paired1", "p1.fastq", "--paired2", "p2.fastq", "--edge_threshold", "0.97", "--min_overlap_len", "150"]
+    res = {"metric": "construct_edges wall time, files in -> overlap graph out", "pairs": a.pairs, "candidates": n_cand,
+           "overlaps_file_bytes": os.path.getsize(d + "/ov.txt")}
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    threads = os.cpu_count() or 1
+    if os.path.exists(ref):
+        wall, js = run([ref] + common + ["--threads", str(threads), "--run", "--dump-graph", "ref.tsv"], d)
+        res["reference"] = {"wall_s": wall, "t_fastq_s": js.get("t_fastq_s"), "t_construct_edges_s": js.get("t_construct_edges_s"),
+                            "threads": threads, "graph_edges": js.get("graph_edges")}
+        if n_cand <= a.one_thread_limit:       # the canonical order (1 thread) for the exact comparison
+            wall1, js1 = run([ref] + common + ["--threads", "1", "--run", "--dump-graph", "ref1.tsv"], d)
+            res["reference_1_thread"] = {"wall_s": wall1, "t_construct_edges_s": js1.get("t_construct_edges_s")}
+    exe = os.path.join(B.LIBDIR, "hc_edgecalc")
+    for name, flags in (("mirror_host_parsers", []), ("mirror_device_ingest", ["--gpu_fastq=true", "--gpu_parse=true", "--gpu_dedup=true"])):
+        wall, js = run([exe] + common + flags + ["--dump-graph", name + ".tsv"], d)
+        res[name] = {"wall_s": wall, **{k: js.get(k) for k in ("t_fastq_s", "t_construct_edges_s", "graph_edges", "device_ms", "parse_device_ms", "t_ingest_s", "t_score_s", "t_edges_s", "t_write_s") if k in js}}
+        if os.path.exists(d + "/ref.tsv"):
+            from oracle import oracle as O      # only its dump parser: every Edge field of every adjacency list, in order
+            g_ref, g_own = O.parse_graph_dump(d + "/ref.tsv"), O.parse_graph_dump(d + "/" + name + ".tsv")
+            # the reference ran with all host threads: its edge vector, hence the adjacency order, follows the thread
+            # schedule; compare the edges as a set (all fields), and in order against a 1-thread run if there is one
+            def canon(g):
+                return np.sort(g, order=["v1", "v2", "ori1", "ori2", "pos1", "pos2"])
+            res[name]["same_edges_as_reference"] = bool(len(g_ref) == len(g_own) and canon(g_ref).tobytes() == canon(g_own).tobytes())
+            if os.path.exists(d + "/ref1.tsv"):
+                g1 = O.parse_graph_dump(d + "/ref1.tsv")
+                res[name]["identical_to_1_thread_reference"] = bool(len(g1) == len(g_own) and g1.tobytes() == g_own.tobytes())
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
