@@ -56,7 +56,8 @@ def log(*a):
 
 def workload_name(args) -> str:
     return ("C4 synthetic %d 2x%dbp pairs (store replicated per GPU), P-P candidates, shard r of %d of the ~%.2g-candidate "
-            "list: %d candidates per GPU per step" % (args.pairs, args.read_len, N_SHARDS, args.pairs * 100.0, args.cands))
+            "list: %d candidates per GPU per step%s" % (args.pairs, args.read_len, N_SHARDS, args.pairs * 100.0, args.cands,
+                                                         " [diagnostic: 4-bin qualities]" if getattr(args, "binned_qualities", False) else ""))
 
 
 class ClockSampler:
@@ -187,6 +188,8 @@ def main() -> None:
     ap.add_argument("--partners", type=int, default=140, help="D: rank window of candidate partners")
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="candidates in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--binned-qualities", action="store_true",
+                    help="diagnostic workload: qualities quantised to the four bins of current Illumina instruments")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-records", default="short", choices=["short", "compact"],
                     help="host record of the e2e leg: 12-byte hc_candidate_short (reads < 16384 bases) or 16-byte hc_candidate_compact")
@@ -244,7 +247,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
     t_setup = time.time()
     pr = WT.make_paired_reads(args.pairs, read_len=args.read_len, seed=args.seed, device=str(dev),
-                              position_sorted_ids=args.position_sorted_ids)
+                              position_sorted_ids=args.position_sorted_ids, binned_qualities=args.binned_qualities)
     torch.cuda.synchronize()
     log("[rank %d] reads generated in %.1fs" % (rank, time.time() - t_setup))
     rs = pr.readset()
@@ -358,7 +361,7 @@ def main() -> None:
         peak, peak_src = measured_hbm_peak()
         alg = int(stats["algorithmic_bytes"])
         achieved = alg / (score_ms * 1e-3) / 1e9
-        default_cfg = args.pairs == 10_000_000 and args.read_len == 150 and args.partners == 140 and not args.position_sorted_ids
+        default_cfg = args.pairs == 10_000_000 and args.read_len == 150 and args.partners == 140 and not args.position_sorted_ids and not args.binned_qualities
         traffic, traffic_src = measured_traffic(n, default_cfg)
         line = {
             "metric": METRIC, "value": total_cands / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -277,24 +277,35 @@ __device__ __forceinline__ void process32(const hc_kparams& P, const uint32_t* _
 // Re-align the A side exactly as in the planar kernel; the XOR of A and (swizzled) B bytes is at
 // once the table column and, in bits 6-7, the base difference.  Mismatch flags of the 8 words are
 // gathered into one 32-bit word (OR_j flags_j >> j) so that a single popc counts them.
-template <bool HAS_VOID>
-__device__ __forceinline__ void process32_packed(const hc_kparams& P, const uint32_t* __restrict__ T,
-                                                 const uint32_t* __restrict__ VM, u64 xpos, uint32_t ypos16, uint32_t L,
-                                                 uint32_t hasN, uint32_t k, uint32_t& sum, uint32_t& mm, uint32_t& ncnt,
-                                                 uint32_t& vd) {
+struct PkRow {          // the raw loads of one packed lane-chunk and what is needed to interpret them
+    uint4 q0, q1, q2, y0, y1;
+    uint32_t n, off, hasN;
+};
+
+__device__ __forceinline__ PkRow load32_packed(const hc_kparams& P, u64 xpos, uint32_t ypos16, uint32_t L, uint32_t hasN, uint32_t k) {
+    PkRow r;
     const u64 xp = xpos + 32ull * k;
-    const uint32_t n = min(L - 32u * k, 32u);   // 1..32 valid positions
+    r.n = min(L - 32u * k, 32u);   // 1..32 valid positions
     const uint32_t yq = ypos16 + 2u * k;
-    const uint32_t off = (uint32_t)xp & 15u;
-    const bool two = n > 16u, x1 = off + n > 16u, x2 = off + n > 32u;
+    r.off = (uint32_t)xp & 15u;
+    r.hasN = hasN;
+    const bool two = r.n > 16u, x1 = r.off + r.n > 16u, x2 = r.off + r.n > 32u;
     const uint4 z4 = make_uint4(0, 0, 0, 0);
     const uint4* xq = reinterpret_cast<const uint4*>(P.pk + (xp & ~15ull));
-    const uint4 q0 = __ldg(xq);
-    const uint4 q1 = x1 ? __ldg(xq + 1) : z4;
-    const uint4 q2 = x2 ? __ldg(xq + 2) : z4;
+    r.q0 = __ldg(xq);
+    r.q1 = x1 ? __ldg(xq + 1) : z4;
+    r.q2 = x2 ? __ldg(xq + 2) : z4;
     const uint4* yqp = reinterpret_cast<const uint4*>(P.pk) + yq;
-    const uint4 y0 = __ldg(yqp);
-    const uint4 y1 = two ? __ldg(yqp + 1) : z4;
+    r.y0 = __ldg(yqp);
+    r.y1 = two ? __ldg(yqp + 1) : z4;
+    return r;
+}
+
+template <bool HAS_VOID>
+__device__ __forceinline__ void compute32_packed(const uint32_t* __restrict__ T, const uint32_t* __restrict__ VM, const PkRow& r,
+                                                 uint32_t& sum, uint32_t& mm, uint32_t& ncnt, uint32_t& vd) {
+    const uint4 q0 = r.q0, q1 = r.q1, q2 = r.q2, y0 = r.y0, y1 = r.y1;
+    const uint32_t n = r.n, off = r.off, hasN = r.hasN;
     const uint32_t vm = VM[n];
     const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
     const bool s2 = (off & 8u) != 0, s1 = (off & 4u) != 0;
@@ -335,6 +346,15 @@ __device__ __forceinline__ void process32_packed(const hc_kparams& P, const uint
     mm = __popc(flags);
     sum = acc;
     vd = HAS_VOID ? ((orv & HC_VOID_BIT) ? 1u : 0u) : 0u;
+}
+
+template <bool HAS_VOID>
+__device__ __forceinline__ void process32_packed(const hc_kparams& P, const uint32_t* __restrict__ T,
+                                                 const uint32_t* __restrict__ VM, u64 xpos, uint32_t ypos16, uint32_t L,
+                                                 uint32_t hasN, uint32_t k, uint32_t& sum, uint32_t& mm, uint32_t& ncnt,
+                                                 uint32_t& vd) {
+    const PkRow r = load32_packed(P, xpos, ypos16, L, hasN, k);
+    compute32_packed<HAS_VOID>(T, VM, r, sum, mm, ncnt, vd);
 }
 
 template <bool HAS_VOID, bool PACKED>
@@ -390,13 +410,18 @@ __device__ __forceinline__ double combine_score(uint32_t two, uint32_t both, dou
 
 __device__ __forceinline__ double fx_mean(u64 S, uint32_t tl) { return -((double)S * (1.0 / HC_FX_SCALE)) / (double)tl; }
 
-__device__ __forceinline__ void write_per_cand(const hc_kparams& P, u64 i, const hc_candidate& c, const uint4& r1,
-                                               const uint4& r2, double score, double mmrate, uint32_t cls,
-                                               const uint32_t mmc[2], const uint32_t cmp[2], const uint32_t st[2],
-                                               uint32_t exact) {
+// (the candidate and its read descriptors are loaded again here rather than kept in registers across the chunk loops)
+__device__ __noinline__ void write_per_cand(const hc_kparams& P, u64 i, double score, double mmrate, uint32_t cls,
+                                            const uint32_t mmc[2], const uint32_t cmp[2], const uint32_t st[2], uint32_t exact) {
     hc_result r;
     r.score = score;
     r.mismatch_rate = mmrate;
+    const hc_candidate c = load_candidate(P, i);
+    uint4 r1 = make_uint4(0, 0, 0, 0), r2 = r1;
+    if (c.idx1 < P.n_reads && c.idx2 < P.n_reads) {
+        r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx1));
+        r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx2));
+    }
     extra_pos(c, r1, r2, r.pos3, r.pos4);
     r.mismatches[0] = mmc[0];
     r.mismatches[1] = mmc[1];
@@ -411,7 +436,7 @@ __device__ __forceinline__ void write_per_cand(const hc_kparams& P, u64 i, const
 }
 
 template <bool HAS_VOID, bool PACKED>
-__global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc_kparams P) {
+__global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kernel(const hc_kparams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* T = reinterpret_cast<uint32_t*>(smem);
     const uint32_t tbl_entries = (P.ncodes + 1u) * 256u + HC_VM_WORDS;   // score table, then the tail masks
@@ -434,8 +459,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
     const u64 twarps = (u64)gridDim.x * nwarps;
     const uint32_t lane_le = 0xffffffffu >> (31 - lane);
 
-    u64 st_windows = 0, st_positions = 0, st_bytes = 0;
-    uint32_t st_errors = 0;
+    uint32_t st_windows = 0, st_positions = 0, st_bytes = 0, st_errors = 0;   // per lane: far below 2^32 for any batch a device holds
 
     for (u64 tile = gwarp; tile < ntiles; tile += twarps) {
         const u64 i = (tile << 5) + lane;
@@ -560,7 +584,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                 if (P.per_cand) {
                     const uint32_t z[2] = {0, 0};
                     const uint32_t stt[2] = {HC_WIN_UNUSED, HC_WIN_UNUSED};
-                    write_per_cand(P, i, c, r1, r2, 0.0, 1.0, HC_CLASS_DISCARD, z, z, stt, 0);
+                    write_per_cand(P, i, 0.0, 1.0, HC_CLASS_DISCARD, z, z, stt, 0);
                 }
             } else {
                 double mmr[2] = {1.0, 1.0};
@@ -593,7 +617,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                         }
                         st_windows++;
                         st_positions += s.w[w].L;
-                        st_bytes += 2ull * ((s.w[w].L + 3u) >> 2) + 2ull * ((s.w[w].L + 7u) >> 3) + 2ull * s.w[w].L;
+                        st_bytes += 2u * ((s.w[w].L + 3u) >> 2) + 2u * ((s.w[w].L + 7u) >> 3) + 2u * s.w[w].L;
                     }
                     stt[w] = status;
                 }
@@ -612,8 +636,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
                 if (P.per_cand) {
                     const double ov0 = cmp[0] ? exp(fx_mean(acc[0].S, cmp[0])) : 0.0;
                     const double ov1 = cmp[1] ? exp(fx_mean(acc[1].S, cmp[1])) : 0.0;
-                    write_per_cand(P, i, c, r1, r2, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), mmrate, cls, mmc, cmp,
-                                   stt, 0);
+                    write_per_cand(P, i, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), mmrate, cls, mmc, cmp, stt, 0);
                 }
             }
         }
@@ -629,15 +652,19 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, 2) hc_score_kernel(const hc
     // per-warp statistics, one atomic each at the very end
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        st_windows += __shfl_xor_sync(0xffffffffu, st_windows, d);
-        st_positions += __shfl_xor_sync(0xffffffffu, st_positions, d);
-        st_bytes += __shfl_xor_sync(0xffffffffu, st_bytes, d);
         st_errors += __shfl_xor_sync(0xffffffffu, st_errors, d);
     }
+    u64 w_windows = st_windows, w_positions = st_positions, w_bytes = st_bytes;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        w_windows += __shfl_xor_sync(0xffffffffu, w_windows, d);
+        w_positions += __shfl_xor_sync(0xffffffffu, w_positions, d);
+        w_bytes += __shfl_xor_sync(0xffffffffu, w_bytes, d);
+    }
     if (lane == 0) {
-        atomicAdd(&P.counters[HC_CNT_WINDOWS], st_windows);
-        atomicAdd(&P.counters[HC_CNT_POSITIONS], st_positions);
-        atomicAdd(&P.counters[HC_CNT_ALGBYTES], st_bytes);
+        atomicAdd(&P.counters[HC_CNT_WINDOWS], w_windows);
+        atomicAdd(&P.counters[HC_CNT_POSITIONS], w_positions);
+        atomicAdd(&P.counters[HC_CNT_ALGBYTES], w_bytes);
         if (st_errors) atomicAdd(&P.counters[HC_CNT_ERRORS], (unsigned long long)st_errors);
     }
 }
@@ -742,7 +769,7 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
         }
         if (P.per_cand) {
             const double ov0 = cmp[0] ? exp(mean[0]) : 0.0, ov1 = cmp[1] ? exp(mean[1]) : 0.0;
-            write_per_cand(P, i, c, r1, r2, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), mmrate, cls, mmc, cmp, stt, 1);
+            write_per_cand(P, i, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), mmrate, cls, mmc, cmp, stt, 1);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[HC_CNT_EXACT] = nf;

@@ -10,6 +10,9 @@
 #ifndef HC_WARPS_MAX
 #define HC_WARPS_MAX 12
 #endif
+#ifndef HC_MIN_CTAS
+#define HC_MIN_CTAS 2             // resident CTAs per SM the register allocation aims at
+#endif
 #define HC_LANE_CHUNK 32u        // positions one lane handles per step (two 16-position halves)
 #ifndef HC_PARTMAX
 #define HC_PARTMAX 512u

@@ -48,7 +48,7 @@ class PairedReads:
 def make_paired_reads(n_pairs: int, read_len: int = 150, genome_len: int = 100_000, n_hap: int = 4,
                       divergence=(0.0, 0.005, 0.01, 0.02), insert=(450.0, 50.0), n_rate: float = 0.0005,
                       seed: int = 20261018, device: str = "cpu", chunk: int = 1 << 20,
-                      position_sorted_ids: bool = False) -> PairedReads:
+                      position_sorted_ids: bool = False, binned_qualities: bool = False) -> PairedReads:
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -88,6 +88,9 @@ def make_paired_reads(n_pairs: int, read_len: int = 150, genome_len: int = 100_0
             q = torch.clamp(torch.round(qmean + 4.0 * torch.randn((m, L), generator=g, device=dev)), 11, 41)
             low = torch.rand((m, L), generator=g, device=dev) < 0.01
             q = torch.where(low, torch.full_like(q, 2.0), q)
+            if binned_qualities:   # diagnostic: the four quality bins of current Illumina instruments (2, 12, 23, 37)
+                q = torch.where(q < 7, torch.full_like(q, 2.0), torch.where(q < 18, torch.full_like(q, 12.0),
+                                torch.where(q < 30, torch.full_like(q, 23.0), torch.full_like(q, 37.0))))
             err = torch.rand((m, L), generator=g, device=dev) < torch.pow(10.0, -q / 10.0)
             sub = torch.randint(1, 4, (m, L), generator=g, device=dev, dtype=torch.uint8)
             seg = torch.where(err, (seg + sub) % 4, seg)
