@@ -23,7 +23,7 @@ EXPORTED = [
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
-    "hc_store_create_fastq", "hc_store_read_ids", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
+    "hc_store_create_fastq", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -50,6 +50,8 @@ def lib() -> ctypes.CDLL:
         L.hc_store_create_fastq.argtypes = [vp, u64, vp, u64, vp, u64, u64, i32, i32]
         L.hc_store_read_ids.restype = i32
         L.hc_store_read_ids.argtypes = [vp, vp, vp]
+        L.hc_consensus.restype = i32
+        L.hc_consensus.argtypes = [vp, vp, u64, vp, u64, u32, dbl, vp, vp, u64, vp]
         L.hc_store_destroy.restype = None
         L.hc_store_destroy.argtypes = [vp]
         for name in ("hc_store_n_reads", "hc_store_n_single", "hc_store_device_bytes"):
@@ -133,6 +135,21 @@ class Store:
             raise HcError(-4, last_error())
         self.first_device, self.n_devices = first_device, n_devices
         return self
+
+    def consensus(self, problems, min_clique_size: int, min_qual: float):
+        """hc_consensus on a list of problem dicts (formats.consensus_arrays).  Returns [(ret, cons_seq, cons_qual)]."""
+        P, S = F.consensus_arrays(problems)
+        total = int(P["total_len"].sum()) if len(P) else 0
+        cs = np.zeros(max(total, 1), dtype=np.uint8)
+        cq = np.zeros(max(total, 1), dtype=np.uint8)
+        res = np.zeros(max(len(P), 1), dtype=F.CONS_RESULT)
+        _check(lib().hc_consensus(self._h, P.ctypes.data if len(P) else None, len(P), S.ctypes.data if len(S) else None, len(S),
+                                  min_clique_size, min_qual, cs.ctypes.data, cq.ctypes.data, total, res.ctypes.data))
+        out = []
+        for i in range(len(P)):
+            o, n = int(P[i]["out_offset"]), int(res[i]["length"])
+            out.append((int(res[i]["ret"]), cs[o:o + n].tobytes().decode(), cq[o:o + n].tobytes().decode()))
+        return out
 
     def read_ids(self):
         """(ids, mate lengths [n, 2]) of a store built from FASTQ text."""

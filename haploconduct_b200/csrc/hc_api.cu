@@ -15,6 +15,8 @@
 #include "hc_tables.h"
 #include "hc_kernels.cuh"
 #include "hc_pack.cuh"
+#include "hc_consensus.cuh"
+#include "hc_cons_final.h"
 
 namespace {
 
@@ -571,6 +573,93 @@ int hc_store_read_ids(const hc_store* s, uint64_t* ids, uint32_t* mate_lengths) 
     if (s->ids.size() != s->n_reads) return fail(HC_ERR_ARG, "hc_store_read_ids: the store was not built from FASTQ text");
     if (ids) memcpy(ids, s->ids.data(), s->n_reads * sizeof(uint64_t));
     if (mate_lengths) memcpy(mate_lengths, s->lens.data(), 2 * s->n_reads * sizeof(uint32_t));
+    return HC_OK;
+}
+
+namespace {
+__global__ void cons_lens(const hc_rdesc* __restrict__ rd, const hc_cons_seq* __restrict__ seqs, uint64_t n, uint32_t* len) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) len[j] = rd[seqs[j].read].len[seqs[j].mate] & HC_LEN_MASK;
+}
+}  // namespace
+
+int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_problems, const hc_cons_seq* seqs, uint64_t n_seqs,
+                 uint32_t min_clique_size, double min_qual, char* cons_seq, char* cons_qual, uint64_t out_bytes,
+                 hc_cons_result* results) {
+    if (!s || (n_problems && (!problems || !results)) || (n_seqs && !seqs) || (out_bytes && (!cons_seq || !cons_qual)))
+        return fail(HC_ERR_ARG, "hc_consensus: NULL argument");
+    if (n_problems == 0) return HC_OK;
+    // ---- validate, tile index
+    std::vector<unsigned long long> tile_off(n_problems + 1, 0);
+    for (uint64_t p = 0; p < n_problems; p++) {
+        const hc_cons_problem& P = problems[p];
+        if (P.seq_begin > P.seq_end || P.seq_end > n_seqs || P.total_len < 0 || P.out_offset + (uint64_t)P.total_len > out_bytes)
+            return fail(HC_ERR_ARG, "hc_consensus: problem " + std::to_string(p) + " is out of range");
+        for (uint64_t j = P.seq_begin; j < P.seq_end; j++) {
+            if (seqs[j].read >= s->n_reads || seqs[j].mate > 1 || seqs[j].pos < 0 || (j > P.seq_begin && seqs[j].pos < seqs[j - 1].pos))
+                return fail(HC_ERR_ARG, "hc_consensus: problem " + std::to_string(p) + ": bad sequence entry (read index, mate, or "
+                                        "start columns not ascending)");
+        }
+        if (P.seq_end > P.seq_begin && seqs[P.seq_begin].pos != 0)
+            return fail(HC_ERR_ARG, "hc_consensus: the first start column of a problem must be 0 (the reference asserts, :449)");
+        tile_off[p + 1] = tile_off[p] + (unsigned long long)((P.total_len + 255) / 256);
+    }
+    const uint64_t n_tiles = tile_off[n_problems];
+    DevCtx& d = s->devs[0];
+    CU(cudaSetDevice(d.device));
+    double addend[94 * 2];
+    hc_cons_addends(addend);
+    int8_t c2q[HC_MAX_CODES + 1];
+    for (int k = 0; k <= HC_MAX_CODES; k++) c2q[k] = (int8_t)(k <= s->ncodes && s->code_to_q[k] >= 0 ? s->code_to_q[k] : 0);
+    hc_cons_problem* d_prob = nullptr;
+    hc_cons_seq* d_seqs = nullptr;
+    unsigned long long* d_toff = nullptr;
+    double *d_add = nullptr, *d_sums = nullptr;
+    int8_t* d_c2q = nullptr;
+    uint16_t* d_cnt = nullptr;
+    uint32_t* d_len = nullptr;
+    std::vector<double> sums;
+    std::vector<uint16_t> cnt;
+    std::vector<uint32_t> lens(n_seqs ? n_seqs : 1);
+    int rc = HC_OK;
+    cudaError_t e = cudaMalloc(&d_prob, n_problems * sizeof(hc_cons_problem));
+    if (e == cudaSuccess) e = cudaMalloc(&d_seqs, (n_seqs ? n_seqs : 1) * sizeof(hc_cons_seq));
+    if (e == cudaSuccess) e = cudaMalloc(&d_toff, (n_problems + 1) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d_add, sizeof(addend));
+    if (e == cudaSuccess) e = cudaMalloc(&d_c2q, sizeof(c2q));
+    if (e == cudaSuccess) e = cudaMalloc(&d_sums, (out_bytes ? out_bytes : 1) * 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, (out_bytes ? out_bytes : 1) * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_len, (n_seqs ? n_seqs : 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_prob, problems, n_problems * sizeof(hc_cons_problem), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess && n_seqs) e = cudaMemcpyAsync(d_seqs, seqs, n_seqs * sizeof(hc_cons_seq), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_toff, tile_off.data(), (n_problems + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_add, addend, sizeof(addend), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c2q, c2q, sizeof(c2q), cudaMemcpyHostToDevice, d.stream);
+    if (e == cudaSuccess) {
+        hc_cons_dev D;
+        D.pk = d.pk; D.qual = d.qual; D.base2 = d.base2; D.nmask = d.nmask; D.rdesc = d.rdesc; D.packed = s->packed ? 1 : 0;
+        e = hc_launch_cons_sums(D, d_prob, n_problems, d_seqs, d_toff, n_tiles, d_add, d_c2q, d_sums, d_cnt, d.stream);
+        if (e == cudaSuccess && n_seqs) {
+            cons_lens<<<(unsigned)((n_seqs + 255) / 256), 256, 0, d.stream>>>(d.rdesc, d_seqs, n_seqs, d_len);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) {
+        try { sums.resize((size_t)out_bytes * 4); cnt.resize((size_t)out_bytes); } catch (...) { rc = fail(HC_ERR_NOMEM, "hc_consensus: host allocation failed"); }
+    }
+    if (e == cudaSuccess && rc == HC_OK && out_bytes) {
+        e = cudaMemcpyAsync(sums.data(), d_sums, (size_t)out_bytes * 4 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)out_bytes * sizeof(uint16_t), cudaMemcpyDeviceToHost, d.stream);
+    }
+    if (e == cudaSuccess && rc == HC_OK && n_seqs) e = cudaMemcpyAsync(lens.data(), d_len, n_seqs * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(d_prob); cudaFree(d_seqs); cudaFree(d_toff); cudaFree(d_add); cudaFree(d_c2q); cudaFree(d_sums); cudaFree(d_cnt); cudaFree(d_len);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_consensus: ") + cudaGetErrorString(e));
+    if (rc != HC_OK) return rc;
+    // ---- host: pow / log10 per column and the column walk, problems in parallel
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t p = 0; p < (int64_t)n_problems; p++)
+        hc_cons_walk(&problems[p], seqs, lens.data(), sums.data(), cnt.data(), min_clique_size, min_qual, cons_seq, cons_qual, &results[p]);
     return HC_OK;
 }
 

@@ -100,6 +100,31 @@ INGEST_STATS = np.dtype([("n_lines", "<u8"), ("n_scored", "<u8"), ("n_filtered",
                          ("first_error_line", "<u8"), ("first_error_offset", "<u8"), ("first_error_length", "<u8"),
                          ("first_error_status", "<u4"), ("device_ms", "<f4")])
 assert INGEST_PARAMS.itemsize == 24 and OVERLAP_REC.itemsize == 48 and INGEST_STATS.itemsize == 72
+CONS_SEQ = np.dtype([("read", "<u4"), ("mate", "u1"), ("rc", "u1"), ("reserved", "<u2"), ("pos", "<i4")])
+CONS_PROBLEM = np.dtype([("seq_begin", "<u8"), ("seq_end", "<u8"), ("out_offset", "<u8"), ("total_len", "<i4"),
+                         ("subreads_needed", "u1"), ("error_correction", "u1"), ("reserved", "u1", (2,))])
+CONS_RESULT = np.dtype([("ret", "<i4"), ("length", "<i4")])
+assert CONS_SEQ.itemsize == 12 and CONS_PROBLEM.itemsize == 32 and CONS_RESULT.itemsize == 8
+
+
+def consensus_arrays(problems) -> tuple:
+    """List of dicts (total_len, subreads_needed, error_correction, entries [(read, mate, rc, pos)]) -> (CONS_PROBLEM, CONS_SEQ)
+    with the outputs laid out back to back."""
+    n_seq = sum(len(p["entries"]) for p in problems)
+    P = np.zeros(len(problems), dtype=CONS_PROBLEM)
+    S = np.zeros(n_seq, dtype=CONS_SEQ)
+    k = off = 0
+    for i, p in enumerate(problems):
+        P[i]["seq_begin"], P[i]["seq_end"] = k, k + len(p["entries"])
+        P[i]["out_offset"], P[i]["total_len"] = off, p["total_len"]
+        P[i]["subreads_needed"], P[i]["error_correction"] = int(p["subreads_needed"]), int(p["error_correction"])
+        for read, mate, rc, pos in p["entries"]:
+            S[k] = (read, mate, int(rc), 0, pos)
+            k += 1
+        off += p["total_len"]
+    return P, S
+
+
 LINE_SCORE, LINE_NONEDGE, LINE_DROPPED, LINE_SKIPPED, LINE_ERROR, LINE_UNKNOWN_ID = 1, 2, 3, 4, 5, 6
 
 

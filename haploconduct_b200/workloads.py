@@ -466,3 +466,75 @@ def fuzz_overlap_text(cands: np.ndarray, ids: np.ndarray, seed: int = 5, allow_s
     if rng.rand() < 0.5:
         text += "\n"
     return text.encode()
+
+
+# ---- consensus problems (SRBuilder::consensus inputs) -------------------------------------------------
+def consensus_problems(seed: int = 1, n_problems: int = 200, read_len=(40, 160), qmax: int = 41, n_rate: float = 0.01):
+    """Pile-ups as SRBuilder::sort_vertices hands them to consensus(): a read set (singles and pairs) and, per problem,
+    entries (read, mate, rc, pos) with pos ascending from 0, total_len, subreads_needed, error_correction.  Reads
+    are error-laden copies of a per-problem template, so most columns agree; some problems have gaps, Q0 / N
+    columns, equal positions, a single read, or too little support for error correction."""
+    rng = np.random.RandomState(seed)
+    singles, pairs, problems = [], [], []
+
+    def emit(seq: str, qual: str) -> tuple:
+        """stores the sequence (forward or as its reverse complement) as a single or as a mate; returns (read, mate, rc)"""
+        rc = bool(rng.rand() < 0.4)
+        s, q = (revcomp(seq), qual[::-1]) if rc else (seq, qual)
+        if rng.rand() < 0.3:
+            other_len = int(rng.randint(read_len[0], read_len[1]))
+            o_s = "".join("ACGT"[k] for k in rng.randint(0, 4, other_len))
+            o_q = "".join(chr(33 + k) for k in rng.randint(2, qmax + 1, other_len))
+            mate = int(rng.randint(0, 2))
+            pairs.append((0, s, q, o_s, o_q) if mate == 0 else (0, o_s, o_q, s, q))
+            return ("p", len(pairs) - 1, mate, rc)
+        singles.append((0, s, q))
+        return ("s", len(singles) - 1, 0, rc)
+
+    for pi in range(n_problems):
+        kind = pi % 10
+        n = 1 if kind == 7 else int(rng.randint(2, 14))
+        T = int(rng.randint(150, 600))
+        tmpl = rng.randint(0, 4, T + 400 + 16 * read_len[1] + 900)
+        pos, entries = 0, []
+        total = 0
+        for j in range(n):
+            L = int(rng.randint(read_len[0], read_len[1]))
+            if j > 0:
+                step = 0 if rng.rand() < 0.15 else int(rng.randint(0, 60))
+                if kind == 5 and j == n // 2:
+                    step += 300                                  # a gap nobody covers
+                pos += step
+            q = np.clip(np.round(rng.normal(33, 7, L)), 2, qmax).astype(int)
+            if kind == 3:
+                q[rng.rand(L) < 0.1] = 0                         # Q0 ('!')
+            err = rng.rand(L) < 10.0 ** (-q / 10.0)
+            b = tmpl[pos:pos + L].copy()
+            b[err] = (b[err] + rng.randint(1, 4, int(err.sum()))) % 4
+            seq = np.array(list("ACGT"))[b]
+            seq[rng.rand(L) < n_rate] = "N"
+            entries.append((emit("".join(seq), "".join(chr(33 + int(x)) for x in q)), pos))
+            total = max(total, pos + L)
+        if kind == 6:
+            total += 25                                          # total_len beyond every read
+        problems.append(dict(total_len=total, subreads_needed=bool(kind == 8), error_correction=bool(pi % 3 != 0), entries=entries))
+    # ids / indices: singles first, then pairs
+    singles = [(i, s, q) for i, (_, s, q) in enumerate(singles)]
+    pairs = [(len(singles) + i, a, b, c, d) for i, (_, a, b, c, d) in enumerate(pairs)]
+    rs = ReadSet.from_lists(singles, pairs)
+    for p in problems:
+        p["entries"] = [((idx if t == "s" else len(singles) + idx), mate, rc, pos) for (t, idx, mate, rc), pos in p["entries"]]
+    return rs, problems
+
+
+def consensus_problem_text(rs, problems) -> str:
+    """The problems as the '--consensus' input of oracle/ref_driver (strings exactly as sort_vertices would pass them)."""
+    out = []
+    for p in problems:
+        out.append("P %d %d %d %d" % (p["total_len"], p["subreads_needed"], p["error_correction"], len(p["entries"])))
+        for read, mate, rc, pos in p["entries"]:
+            s, q = rs.seq(read, mate), rs.qual(read, mate)
+            if rc:
+                s, q = revcomp(s), q[::-1]
+            out.append("%d %s %s" % (pos, s, q))
+    return "\n".join(out) + "\n"

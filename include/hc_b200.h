@@ -417,6 +417,45 @@ int hc_ingest_overlaps_device(const hc_idmap* m, void* stream, const char* d_tex
                               hc_overlap_rec* d_filtered, uint64_t* d_filtered_line, uint64_t filtered_cap,
                               hc_ingest_stats* stats);
 
+/* ------------------------------------------------------------------------------------------
+ * Super-read consensus (third "next" row): SRBuilder::consensus + consensus_pos,
+ * src/SRBuilder.cpp:297-522, for many pile-ups at once.
+ *
+ * A problem is what SRBuilder::sort_vertices hands over (:688-700): sequences of the store (a read's
+ * mate, forward or reverse-complemented) with their start columns, ascending from 0, the length of
+ * the consensus, and the two flags.  For every column the device adds the reference's log10 terms
+ * of the covering bases in list order (:318-341, addends from a host-libm table, so the four
+ * scores are bit-identical); the host part of the call evaluates :349-401 (pow / log10 / round of
+ * the host libm, the same the reference links) and walks the columns like :447-513 (support
+ * trimming under error_correction, give-up cases).  Results are the reference's strings.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint32_t read;            /* store index of the read                                            */
+    uint8_t  mate;            /* 0 / 1                                                              */
+    uint8_t  rc;              /* 1: reverse complement, qualities reversed (src/Read.h:172-201)     */
+    uint16_t reserved;
+    int32_t  pos;             /* start column (pos_list), ascending within a problem                */
+} hc_cons_seq;                /* 12 bytes */
+
+typedef struct {
+    uint64_t seq_begin, seq_end;   /* this problem's entries in the hc_cons_seq array               */
+    uint64_t out_offset;           /* where its characters start in cons_seq / cons_qual; total_len bytes are reserved */
+    int32_t  total_len;            /* consensus length handed to consensus() (:406)                 */
+    uint8_t  subreads_needed, error_correction;
+    uint8_t  reserved[2];
+} hc_cons_problem;            /* 32 bytes */
+
+typedef struct {
+    int32_t ret;              /* consensus()'s return value: trim_pos, 0 (gave up) or -1 (not enough support) */
+    int32_t length;           /* characters written at out_offset (0 where the reference clears the strings)  */
+} hc_cons_result;
+
+/* min_clique_size / min_qual = ProgramSettings::min_clique_size / min_qual (SRBuilder::minQual, src/SRBuilder.h:89).
+ * out_bytes = size of cons_seq and of cons_qual. */
+int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_problems, const hc_cons_seq* seqs, uint64_t n_seqs,
+                 uint32_t min_clique_size, double min_qual, char* cons_seq, char* cons_qual, uint64_t out_bytes,
+                 hc_cons_result* results);
+
 int         hc_device_count(void);
 const char* hc_last_error(void);
 const char* hc_version(void);

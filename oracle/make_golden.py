@@ -127,6 +127,30 @@ def run_ingest_case(name: str, rs: F.ReadSet, cands: np.ndarray, seed: int, allo
           (name, out["lines"], out["scored"], n_f, out["self"], out["perc_dropped"], out["bad"]))
 
 
+def run_consensus_case(name: str, seed: int, n_problems: int, min_clique_size: int, min_qual: float, **kw) -> None:
+    """Pile-ups through the reference's own SRBuilder::consensus (oracle/ref_driver --consensus)."""
+    import subprocess
+    rs, probs = W.consensus_problems(seed=seed, n_problems=n_problems, **kw)
+    d = tempfile.mkdtemp(prefix="hc_golden_cons_")
+    with open(d + "/in.txt", "w") as f:
+        f.write(W.consensus_problem_text(rs, probs))
+    open(d + "/ov.txt", "w").close()
+    F.write_fastq_set(rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    subprocess.run([O.REF_DRIVER, "--overlaps", d + "/ov.txt", "--singles", d + "/s.fastq", "--paired1", d + "/p1.fastq", "--paired2",
+                    d + "/p2.fastq", "--min_clique_size", str(min_clique_size), "--min_qual", repr(min_qual), "--consensus", d + "/in.txt",
+                    d + "/out.txt"], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    ref = [l.rstrip("\n").split("\t") for l in open(d + "/out.txt")]
+    assert len(ref) == len(probs)
+    P, S = F.consensus_arrays(probs)
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"), ids=rs.ids, descs=rs.descs, bases=rs.bases, quals=rs.quals, n_single=np.int64(rs.n_single),
+        problems=P, seqs=S, params=np.array([min_clique_size, min_qual]), ref_ret=np.array([int(r[1]) for r in ref], dtype=np.int32),
+        ref_seq=np.array(["" if r[2] == "0" else r[3] for r in ref], dtype=object).astype(str),
+        ref_qual=np.array(["" if r[2] == "0" else r[4] for r in ref], dtype=object).astype(str))
+    print("%-28s problems=%d reads=%d non-empty=%d ret<0=%d N columns=%d" % (
+        name, len(probs), rs.n_reads, sum(1 for r in ref if r[2] != "0"), sum(1 for r in ref if int(r[1]) < 0), sum(r[3].count("N") for r in ref)))
+
+
 def main() -> None:
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -163,6 +187,10 @@ def main() -> None:
     run_ingest_case("ingest_tabs", ss.rs, c3, 5, False, dict(min_overlap_len=60, min_overlap_perc=30))
     run_ingest_case("ingest_tabs_relaxed", ss5.rs, c5, 6, False, dict(min_overlap_len=150, relax_PE_edges=True))
     run_ingest_case("ingest_spaces", ss.rs, c3, 7, True, dict(min_overlap_len=60, min_overlap_perc=30))
+
+    # ---- super-read consensus: pile-ups through SRBuilder::consensus
+    run_consensus_case("consensus_illumina", 3, 160, 3, 0.9)
+    run_consensus_case("consensus_wide_qualities", 4, 120, 2, 0.99, qmax=93, read_len=(200, 900))
 
     # ---- FindNextOverlaps (FNO1): the reference's overlaps.txt after one merge iteration
     s700 = full.subset(range(0, 700))

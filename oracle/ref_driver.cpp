@@ -98,7 +98,7 @@ int main(int argc, char** argv) {
     ps.fno = 2;
     ps.output_dir = "";
 
-    std::string dump_cands, dump_graph, merge_fno1;
+    std::string dump_cands, dump_graph, merge_fno1, consensus_in, consensus_out;
     bool fno3 = false, use_cliques = false;
     ps.keep_singletons = 0;
     ps.remove_trans = 1;
@@ -137,6 +137,8 @@ int main(int argc, char** argv) {
         else if (a == "--merge-fno3") { merge_fno1 = need("--merge-fno3"); fno3 = true; }
         else if (a == "--cliques") use_cliques = std::atoi(need("--cliques")) != 0;
         else if (a == "--min_clique_size") ps.min_clique_size = std::atoi(need("--min_clique_size"));
+        else if (a == "--min_qual") ps.min_qual = std::atof(need("--min_qual"));
+        else if (a == "--consensus") { consensus_in = need("--consensus"); consensus_out = need("--consensus"); }
         else if (a == "--keep_singletons") ps.keep_singletons = std::atoi(need("--keep_singletons"));
         else if (a == "--remove_branches") ps.remove_branches = std::atoi(need("--remove_branches")) != 0;
         else if (a == "--remove_trans") ps.remove_trans = std::atoi(need("--remove_trans"));
@@ -158,6 +160,41 @@ int main(int argc, char** argv) {
         r->set_vertex_id(true, v);
     }
     EdgeCalculator ec(fastq, graph, ps);
+
+    // --consensus IN OUT: SRBuilder::consensus (src/SRBuilder.cpp:406-522, with consensus_pos :297-402) on the
+    // problems of IN ("P total_len subreads_needed error_correction n", then n lines "pos seq qual"); one line
+    // "R ret length seq qual" per problem in OUT ("-" stands for an empty string, length 0).
+    if (!consensus_in.empty()) {
+        std::shared_ptr<SRBuilder> srb(new SRBuilder(fastq, graph, ps));
+        std::ifstream in(consensus_in.c_str());
+        FILE* fo = std::fopen(consensus_out.c_str(), "w");
+        if (!in.is_open() || !fo) { std::fprintf(stderr, "cannot open the consensus files\n"); return 1; }
+        std::string tag;
+        double t_cons = 0;
+        unsigned long n_prob = 0, n_bases = 0;
+        while (in >> tag) {
+            int total_len, sub, ec_flag, n;
+            in >> total_len >> sub >> ec_flag >> n;
+            std::list<int> pos_list;
+            std::list<std::string> seq_list, qual_list;
+            for (int k = 0; k < n; k++) {
+                int pos;
+                std::string sq, ql;
+                in >> pos >> sq >> ql;
+                pos_list.push_back(pos); seq_list.push_back(sq); qual_list.push_back(ql);
+                n_bases += sq.size();
+            }
+            std::string cs, cq;
+            const double tc0 = now_s();
+            const int ret = srb->consensus(total_len, pos_list, seq_list, qual_list, cs, cq, sub != 0, ec_flag != 0);
+            t_cons += now_s() - tc0;
+            n_prob++;
+            std::fprintf(fo, "R\t%d\t%zu\t%s\t%s\n", ret, cs.size(), cs.empty() ? "-" : cs.c_str(), cq.empty() ? "-" : cq.c_str());
+        }
+        std::fclose(fo);
+        std::printf("{\"consensus_problems\": %lu, \"consensus_bases\": %lu, \"t_consensus_s\": %.6f}\n", n_prob, n_bases, t_cons);
+        return 0;
+    }
 
     // Parse + pre-filter exactly as src/EdgeCalculator.cpp:581-635 (tab-split branch), keeping
     // the 1-based line number of every candidate that reaches process_overlaps.

@@ -35,7 +35,7 @@ class Golden:
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("fno", "insert_", "ingest_")))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("fno", "insert_", "ingest_", "consensus_")))
 
 
 def fno_golden_names():
@@ -201,3 +201,41 @@ class IngestGolden:
 
 def ingest_golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ingest_*.npz")))
+
+
+class ConsensusGolden:
+    """tests/golden/consensus_*.npz: pile-ups and what the reference's SRBuilder::consensus returned for them."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+        self.rs = F.ReadSet(ids=z["ids"], descs=z["descs"], bases=z["bases"], quals=z["quals"], n_single=int(z["n_single"]))
+        self.P, self.S = z["problems"], z["seqs"]
+        self.min_clique_size, self.min_qual = int(z["params"][0]), float(z["params"][1])
+        self.ref = [(int(r), str(s), str(q)) for r, s, q in zip(z["ref_ret"], z["ref_seq"], z["ref_qual"])]
+
+    def problems(self):
+        out = []
+        for p in self.P:
+            ent = [(int(e["read"]), int(e["mate"]), bool(e["rc"]), int(e["pos"])) for e in self.S[int(p["seq_begin"]):int(p["seq_end"])]]
+            out.append(dict(total_len=int(p["total_len"]), subreads_needed=bool(p["subreads_needed"]),
+                            error_correction=bool(p["error_correction"]), entries=ent))
+        return out
+
+
+def consensus_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "consensus_*.npz")))
+
+
+def consensus_oracle_results(rs, problems, min_clique_size, min_qual):
+    from haploconduct_b200.workloads import revcomp
+    from oracle import consensus_oracle as CO
+    out = []
+    for p in problems:
+        pos, seqs, quals = [], [], []
+        for read, mate, rc, ps in p["entries"]:
+            s, q = rs.seq(read, mate), rs.qual(read, mate)
+            if rc:
+                s, q = revcomp(s), q[::-1]
+            pos.append(ps); seqs.append(s); quals.append(q)
+        out.append(CO.consensus(p["total_len"], pos, seqs, quals, p["subreads_needed"], p["error_correction"], min_clique_size, min_qual))
+    return out
