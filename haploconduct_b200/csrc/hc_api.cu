@@ -613,23 +613,38 @@ int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_proble
     for (int k = 0; k <= HC_MAX_CODES; k++) c2q[k] = (int8_t)(k <= s->ncodes && s->code_to_q[k] >= 0 ? s->code_to_q[k] : 0);
     hc_cons_problem* d_prob = nullptr;
     hc_cons_seq* d_seqs = nullptr;
-    unsigned long long* d_toff = nullptr;
-    double *d_add = nullptr, *d_sums = nullptr;
+    unsigned long long *d_toff = nullptr, *d_marked = nullptr, *d_nmarked = nullptr;
+    double *d_add = nullptr, *d_sums = nullptr, *d_msums = nullptr;
     int8_t* d_c2q = nullptr;
     uint16_t* d_cnt = nullptr;
     uint32_t* d_len = nullptr;
-    std::vector<double> sums;
+    char *d_base = nullptr, *d_qual = nullptr;
+    const uint64_t cols = out_bytes ? out_bytes : 1;
+    uint64_t marked_cap = cols / 64 + 4096;
+    unsigned long long n_marked = 0;
     std::vector<uint16_t> cnt;
     std::vector<uint32_t> lens(n_seqs ? n_seqs : 1);
+    std::vector<unsigned long long> marked;
+    std::vector<double> msums;
     int rc = HC_OK;
+    const bool mark_all = getenv("HC_CONS_HOST_ALL") != nullptr;      // tests: every column through the host libm
+    if (mark_all) marked_cap = cols;
     cudaError_t e = cudaMalloc(&d_prob, n_problems * sizeof(hc_cons_problem));
     if (e == cudaSuccess) e = cudaMalloc(&d_seqs, (n_seqs ? n_seqs : 1) * sizeof(hc_cons_seq));
     if (e == cudaSuccess) e = cudaMalloc(&d_toff, (n_problems + 1) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&d_add, sizeof(addend));
     if (e == cudaSuccess) e = cudaMalloc(&d_c2q, sizeof(c2q));
-    if (e == cudaSuccess) e = cudaMalloc(&d_sums, (out_bytes ? out_bytes : 1) * 4 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, (out_bytes ? out_bytes : 1) * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_sums, cols * 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, cols * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_base, cols);
+    if (e == cudaSuccess) e = cudaMalloc(&d_qual, cols);
+    if (e == cudaSuccess) e = cudaMalloc(&d_marked, marked_cap * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&d_nmarked, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&d_len, (n_seqs ? n_seqs : 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_nmarked, 0, sizeof(unsigned long long), d.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_base, 0, cols, d.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_qual, 0, cols, d.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, cols * sizeof(uint16_t), d.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_prob, problems, n_problems * sizeof(hc_cons_problem), cudaMemcpyHostToDevice, d.stream);
     if (e == cudaSuccess && n_seqs) e = cudaMemcpyAsync(d_seqs, seqs, n_seqs * sizeof(hc_cons_seq), cudaMemcpyHostToDevice, d.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_toff, tile_off.data(), (n_problems + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, d.stream);
@@ -638,28 +653,67 @@ int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_proble
     if (e == cudaSuccess) {
         hc_cons_dev D;
         D.pk = d.pk; D.qual = d.qual; D.base2 = d.base2; D.nmask = d.nmask; D.rdesc = d.rdesc; D.packed = s->packed ? 1 : 0;
-        e = hc_launch_cons_sums(D, d_prob, n_problems, d_seqs, d_toff, n_tiles, d_add, d_c2q, d_sums, d_cnt, d.stream);
+        // (a NaN threshold never compares: with HC_CONS_HOST_ALL the min_qual closeness test is replaced by marking everything)
+        e = hc_launch_cons_sums(D, d_prob, n_problems, d_seqs, d_toff, n_tiles, d_add, d_c2q, min_qual, d_sums, d_cnt, d_base, d_qual,
+                                d_marked, mark_all ? 0 : marked_cap, d_nmarked, d.stream);
         if (e == cudaSuccess && n_seqs) {
             cons_lens<<<(unsigned)((n_seqs + 255) / 256), 256, 0, d.stream>>>(d.rdesc, d_seqs, n_seqs, d_len);
             e = cudaGetLastError();
         }
     }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_marked, d_nmarked, sizeof(n_marked), cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     if (e == cudaSuccess) {
-        try { sums.resize((size_t)out_bytes * 4); cnt.resize((size_t)out_bytes); } catch (...) { rc = fail(HC_ERR_NOMEM, "hc_consensus: host allocation failed"); }
+        try { cnt.resize((size_t)cols); } catch (...) { rc = fail(HC_ERR_NOMEM, "hc_consensus: host allocation failed"); }
     }
     if (e == cudaSuccess && rc == HC_OK && out_bytes) {
-        e = cudaMemcpyAsync(sums.data(), d_sums, (size_t)out_bytes * 4 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)out_bytes * sizeof(uint16_t), cudaMemcpyDeviceToHost, d.stream);
+        e = cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)out_bytes * sizeof(uint16_t), cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cons_seq, d_base, (size_t)out_bytes, cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cons_qual, d_qual, (size_t)out_bytes, cudaMemcpyDeviceToHost, d.stream);
     }
     if (e == cudaSuccess && rc == HC_OK && n_seqs) e = cudaMemcpyAsync(lens.data(), d_len, n_seqs * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream);
+    // ---- columns whose outcome is within the error bound of a decision: their scores come back and the host libm decides
+    bool all_cols = mark_all || n_marked > marked_cap;     // (more marked columns than the list holds: redo every column)
+    if (e == cudaSuccess && rc == HC_OK && !all_cols && n_marked) {
+        marked.resize(n_marked);
+        msums.resize(4 * n_marked);
+        e = cudaMalloc(&d_msums, 4 * n_marked * sizeof(double));
+        if (e == cudaSuccess) e = hc_launch_cons_gather(d_marked, n_marked, d_sums, d_msums, d.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(marked.data(), d_marked, n_marked * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(msums.data(), d_msums, 4 * n_marked * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+    }
+    if (e == cudaSuccess && rc == HC_OK && all_cols && out_bytes) {
+        try { msums.resize((size_t)out_bytes * 4); } catch (...) { rc = fail(HC_ERR_NOMEM, "hc_consensus: host allocation failed"); }
+        if (rc == HC_OK) e = cudaMemcpyAsync(msums.data(), d_sums, (size_t)out_bytes * 4 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     cudaFree(d_prob); cudaFree(d_seqs); cudaFree(d_toff); cudaFree(d_add); cudaFree(d_c2q); cudaFree(d_sums); cudaFree(d_cnt); cudaFree(d_len);
+    cudaFree(d_base); cudaFree(d_qual); cudaFree(d_marked); cudaFree(d_nmarked); cudaFree(d_msums);
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_consensus: ") + cudaGetErrorString(e));
     if (rc != HC_OK) return rc;
-    // ---- host: pow / log10 per column and the column walk, problems in parallel
-#pragma omp parallel for schedule(dynamic, 16)
+    if (all_cols) {
+#pragma omp parallel for schedule(static)
+        for (int64_t g = 0; g < (int64_t)out_bytes; g++) {
+            char b = 'N', q = '$';
+            if (!hc_cons_final_pos(msums[4 * g], msums[4 * g + 1], msums[4 * g + 2], msums[4 * g + 3], cnt[g], min_qual, &b, &q)) q = 0;
+            cons_seq[g] = b;
+            cons_qual[g] = q;
+        }
+    } else {
+        for (uint64_t k = 0; k < n_marked; k++) {
+            const uint64_t g = marked[k];
+            char b = 'N', q = '$';
+            if (!hc_cons_final_pos(msums[4 * k], msums[4 * k + 1], msums[4 * k + 2], msums[4 * k + 3], cnt[g], min_qual, &b, &q)) q = 0;
+            cons_seq[g] = b;
+            cons_qual[g] = q;
+        }
+    }
+    // ---- the column walk of :447-513, problems in parallel (their output regions are disjoint)
+#pragma omp parallel for schedule(dynamic, 64)
     for (int64_t p = 0; p < (int64_t)n_problems; p++)
-        hc_cons_walk(&problems[p], seqs, lens.data(), sums.data(), cnt.data(), min_clique_size, min_qual, cons_seq, cons_qual, &results[p]);
+        hc_cons_walk(&problems[p], seqs, lens.data(), cnt.data(), min_clique_size, cons_seq, cons_qual, &results[p]);
+    if (getenv("HC_CONS_VERBOSE")) fprintf(stderr, "hc_consensus: %llu of %llu columns re-evaluated on the host\n",
+                                           all_cols ? (unsigned long long)out_bytes : n_marked, (unsigned long long)out_bytes);
     return HC_OK;
 }
 

@@ -16,7 +16,7 @@ void hc_cons_addends(double* out /* [94][2] */) {
 }
 
 // :349-401 from the four scores; returns 0 when the reference returns 0 (p_incorrect is NaN)
-static int final_pos(double sA, double sC, double sT, double sG, unsigned n_active, double min_qual, char* base, char* qual) {
+int hc_cons_final_pos(double sA, double sC, double sT, double sG, unsigned n_active, double min_qual, char* base, char* qual) {
     const double max_score = std::max({sA, sT, sC, sG});
     const double max_prob = std::pow(10.0, max_score);
     const double total_prob = std::pow(10.0, sA) + std::pow(10.0, sT) + std::pow(10.0, sC) + std::pow(10.0, sG);
@@ -39,9 +39,8 @@ static int final_pos(double sA, double sC, double sT, double sG, unsigned n_acti
     return 1;
 }
 
-void hc_cons_walk(const hc_cons_problem* P, const hc_cons_seq* seqs, const uint32_t* seq_len, const double* sums,
-                  const uint16_t* count, uint32_t min_clique_size, double min_qual, char* cons_seq, char* cons_qual,
-                  hc_cons_result* res) {
+void hc_cons_walk(const hc_cons_problem* P, const hc_cons_seq* seqs, const uint32_t* seq_len, const uint16_t* count,
+                  uint32_t min_clique_size, char* cons_seq, char* cons_qual, hc_cons_result* res) {
     const uint64_t n = P->seq_end - P->seq_begin;
     const hc_cons_seq* e = seqs + P->seq_begin;
     const uint32_t* len = seq_len + P->seq_begin;
@@ -62,22 +61,20 @@ void hc_cons_walk(const hc_cons_problem* P, const hc_cons_seq* seqs, const uint3
         for (uint64_t j = 0; j < n && e[j].pos <= trim; j++)
             if ((uint32_t)(trim - e[j].pos) >= len[j]) return;                   // ret 0, empty strings
     const int last_start = n ? e[n - 1].pos : 0;
-    char* cs = cons_seq + P->out_offset;
+    char* cs = cons_seq + P->out_offset;      // per-column characters on entry, the consensus strings on return
     char* cq = cons_qual + P->out_offset;
     int out = 0;
     for (int c = trim; c < P->total_len; c++) {
-        const uint64_t g = P->out_offset + (uint64_t)c;
-        const unsigned n_active = count[g];
+        const unsigned n_active = count[P->out_offset + (uint64_t)c];
         if (P->error_correction && n_active < min_support && c >= last_start) break;   // suffix without support, :459-462
         if (n_active == 0) { res->ret = 0; res->length = 0; return; }                  // nobody covers the column, :488-491
-        char b, q;
-        if (!final_pos(sums[4 * g], sums[4 * g + 1], sums[4 * g + 2], sums[4 * g + 3], n_active, min_qual, &b, &q)) {
+        if (cq[c] == 0) {                                                               // consensus_pos returned 0 (:366-369)
             res->ret = trim;                                                            // :507-511: strings cleared, trim_pos returned
             res->length = 0;
             return;
         }
-        cs[out] = b;
-        cq[out] = q;
+        cs[out] = cs[c];                     // out <= c: the strings start at the problem's offset
+        cq[out] = cq[c];
         out++;
     }
     res->ret = trim;

@@ -15,8 +15,12 @@ struct hc_cons_dev {          // the store planes of one device
     int packed;
 };
 
-// d_tile_off[p] = first 256-column tile of problem p (n_prob + 1 entries); sums/count are indexed by out_offset + column
+// d_tile_off[p] = first 256-column tile of problem p (n_prob + 1 entries); per-column outputs are indexed by out_offset + column.
+// d_base / d_qual: the consensus character of every column by the device's libm; d_marked: columns the host must redo.
 cudaError_t hc_launch_cons_sums(const hc_cons_dev& D, const hc_cons_problem* d_prob, uint64_t n_prob, const hc_cons_seq* d_seqs,
                                 const unsigned long long* d_tile_off, uint64_t n_tiles, const double* d_addend,
-                                const int8_t* d_code_to_q, double* d_sums, uint16_t* d_count, cudaStream_t st);
+                                const int8_t* d_code_to_q, double min_qual, double* d_sums, uint16_t* d_count, char* d_base,
+                                char* d_qual, unsigned long long* d_marked, uint64_t marked_cap, unsigned long long* d_n_marked,
+                                cudaStream_t st);
+cudaError_t hc_launch_cons_gather(const unsigned long long* d_marked, uint64_t n, const double* d_sums, double* d_out, cudaStream_t st);
 #endif

@@ -16,8 +16,13 @@ def layout(request, monkeypatch):
     return request.param
 
 
+@pytest.mark.parametrize("host_all", [False, True])
 @pytest.mark.parametrize("name", consensus_golden_names())
-def test_consensus_reproduces_reference(built_lib, name):
+def test_consensus_reproduces_reference(built_lib, monkeypatch, name, host_all):
+    """Default: pow / log10 on the device, only columns within the error bound of a decision go back to the host libm.
+    HC_CONS_HOST_ALL: every column through the host libm.  Both must give the reference's strings."""
+    if host_all:
+        monkeypatch.setenv("HC_CONS_HOST_ALL", "1")
     g = ConsensusGolden(name)
     with capi.Store(g.rs) as st:
         got = st.consensus(g.problems(), g.min_clique_size, g.min_qual)
