@@ -425,9 +425,11 @@ int hc_ingest_overlaps_device(const hc_idmap* m, void* stream, const char* d_tex
  * mate, forward or reverse-complemented) with their start columns, ascending from 0, the length of
  * the consensus, and the two flags.  For every column the device adds the reference's log10 terms
  * of the covering bases in list order (:318-341, addends from a host-libm table, so the four
- * scores are bit-identical); the host part of the call evaluates :349-401 (pow / log10 / round of
- * the host libm, the same the reference links) and walks the columns like :447-513 (support
- * trimming under error_correction, give-up cases).  Results are the reference's strings.
+ * scores are bit-identical) and evaluates :349-401 (pow / log10 / round) with its own libm while
+ * bounding the error; columns within that bound of a decision come back with their scores and are
+ * decided by the host libm, the same the reference links.  The host part of the call then walks
+ * the columns like :447-513 (support trimming under error_correction, give-up cases).  Results
+ * are the reference's strings.  Output regions of different problems must not overlap.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     uint32_t read;            /* store index of the read                                            */
