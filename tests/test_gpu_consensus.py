@@ -50,3 +50,18 @@ def test_consensus_rejects_bad_problems(built_lib):
             bad = [dict(probs[1], entries=[e[0], (e[1][0], e[1][1], e[1][2], -1)])]
             with pytest.raises(capi.HcError):
                 st.consensus(bad, 2, 0.9)
+
+
+def test_device_decisions_agree_with_host_libm_at_scale(built_lib, monkeypatch, layout):
+    """A few million columns: the characters decided on the device (unmarked columns) must be the ones the host libm
+    gives for the same scores -- i.e. the marking covers every column whose outcome could differ."""
+    if layout == "planar":
+        pytest.skip("one layout is enough for this one")
+    rs, base = W.consensus_problems(seed=21, n_problems=1500, qmax=60)
+    probs = base * 12
+    with capi.Store(rs) as st:
+        dev = st.consensus(probs, 3, 0.93)
+        monkeypatch.setenv("HC_CONS_HOST_ALL", "1")
+        host = st.consensus(probs, 3, 0.93)
+    assert dev == host
+    assert sum(len(r[1]) for r in dev) > 2_000_000
