@@ -779,15 +779,27 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
 #define HC_CB_THREADS 256
 #define HC_CB_ITEMS 4096   // candidates per block
 
+// class bytes: low two bits = class; per 32-bit word the number of bytes equal to 1 (edge) / 2 (non-edge)
+__device__ __forceinline__ void count_classes4(uint32_t w, uint32_t& e, uint32_t& o) {
+    const uint32_t lo = w & 0x01010101u, hi = (w >> 1) & 0x01010101u;
+    e += __popc(lo & ~hi);
+    o += __popc(hi & ~lo);
+}
+
 __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_count(const uint8_t* __restrict__ cls, u64 n, uint32_t* blockcounts) {
     const u64 base = (u64)blockIdx.x * HC_CB_ITEMS;
     uint32_t e = 0, o = 0;
-    for (uint32_t k = threadIdx.x; k < HC_CB_ITEMS; k += HC_CB_THREADS) {
-        const u64 i = base + k;
-        if (i < n) {
-            const uint32_t c = cls[i] & HC_CLS_MASK;
-            e += c == HC_CLASS_EDGE;
-            o += c == HC_CLASS_NONEDGE;
+    if (base + HC_CB_ITEMS <= n) {            // full block: one 16-byte load per thread (4096 = 256 x 16)
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(cls + base) + threadIdx.x);
+        count_classes4(v.x, e, o); count_classes4(v.y, e, o); count_classes4(v.z, e, o); count_classes4(v.w, e, o);
+    } else {
+        for (uint32_t k = threadIdx.x; k < HC_CB_ITEMS; k += HC_CB_THREADS) {
+            const u64 i = base + k;
+            if (i < n) {
+                const uint32_t c = cls[i] & HC_CLS_MASK;
+                e += c == HC_CLASS_EDGE;
+                o += c == HC_CLASS_NONEDGE;
+            }
         }
     }
     __shared__ uint32_t se[HC_CB_THREADS / 32], so[HC_CB_THREADS / 32];
@@ -849,61 +861,80 @@ __global__ void __launch_bounds__(1024) hc_compact_scan(const uint32_t* blockcou
     if (threadIdx.x == 0) { counters[HC_CNT_EDGES] = carry_e; counters[HC_CNT_NONEDGES] = carry_o; }
 }
 
+// Edge::score (:138, :256-261) and the extra positions for one accepted edge
+__device__ __forceinline__ void emit_edge(const hc_kparams& P, u64 i, uint32_t cfull, u64 cand_offset, hc_edge* dst) {
+    const hc_candidate cd = load_candidate(P, i);
+    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx1));
+    const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx2));
+    const hc_tmp32 t = P.tmp[i];
+    double ov[2], ml[2];
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        if (t.tl[w] == 0) ml[w] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: window not scored
+        else if (cfull & HC_CLS_EXACT) ml[w] = __longlong_as_double((long long)t.S[w]);
+        else ml[w] = fx_mean(t.S[w], t.tl[w]);
+        ov[w] = t.tl[w] ? exp(ml[w]) : 0.0;
+    }
+    const uint32_t two = ((r1.w | r2.w) & HC_LEN_MASK) != 0;
+    hc_edge e;
+    e.cand = i + cand_offset;
+    e.score = combine_score(two, cfull & HC_CLS_BOTH, ov[0], ov[1]);
+    e.mismatch_rate = t.mismatch_rate;
+    extra_pos(cd, r1, r2, e.pos3, e.pos4);
+    e.mean_log[0] = ml[0];
+    e.mean_log[1] = ml[1];
+    *dst = e;
+}
+
+// Each thread owns four consecutive candidates (one 32-bit load of class bytes); ranks come from a warp scan of the
+// packed (edges | non-edges << 16) counts and the per-warp totals, so the lists keep the input order.
 __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kparams P, const u64* __restrict__ blockoffs,
                                                                    hc_edge* edges, u64 edges_cap, uint64_t* nonedge,
                                                                    u64 nonedge_cap, u64 cand_offset) {
-    __shared__ uint32_t we[HC_CB_THREADS / 32], wo[HC_CB_THREADS / 32];
+    __shared__ uint32_t wtot[HC_CB_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 base = (u64)blockIdx.x * HC_CB_ITEMS;
     u64 eoff = blockoffs[2 * blockIdx.x] + (P.run ? P.run[0] : 0ull), ooff = blockoffs[2 * blockIdx.x + 1] + (P.run ? P.run[1] : 0ull);
-    const uint32_t lt = (1u << lane) - 1u;
-    for (uint32_t k0 = 0; k0 < HC_CB_ITEMS; k0 += HC_CB_THREADS) {
-        const u64 i = base + k0 + threadIdx.x;
-        const uint32_t cfull = i < P.n ? P.cls[i] : HC_CLASS_DISCARD;
-        const uint32_t c = cfull & HC_CLS_MASK;
-        const uint32_t be = __ballot_sync(0xffffffffu, c == HC_CLASS_EDGE);
-        const uint32_t bo = __ballot_sync(0xffffffffu, c == HC_CLASS_NONEDGE);
-        if (lane == 0) { we[warp] = __popc(be); wo[warp] = __popc(bo); }
+    for (uint32_t k0 = 0; k0 < HC_CB_ITEMS; k0 += 4 * HC_CB_THREADS) {
+        const u64 i0 = base + k0 + 4ull * threadIdx.x;
+        uint32_t w4 = 0;                                           // class bytes of candidates i0 .. i0+3 (0 = discard beyond n)
+        if (i0 + 4 <= P.n) w4 = __ldg(reinterpret_cast<const uint32_t*>(P.cls + i0));
+        else for (int j = 0; j < 4; j++) if (i0 + j < P.n) w4 |= (uint32_t)P.cls[i0 + j] << (8 * j);
+        uint32_t ce = 0, co = 0;
+        count_classes4(w4, ce, co);
+        const uint32_t mine = ce | (co << 16);
+        uint32_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) wtot[warp] = inc;
         __syncthreads();
-        uint32_t pe = 0, po = 0, te = 0, to = 0;
+        uint32_t before = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < HC_CB_THREADS / 32; w++) {
-            if (w < warp) { pe += we[w]; po += wo[w]; }
-            te += we[w];
-            to += wo[w];
+            if (w < warp) before += wtot[w];
+            total += wtot[w];
         }
-        if (c == HC_CLASS_EDGE) {
-            const u64 dst = eoff + pe + __popc(be & lt);
-            if (dst < edges_cap) {
-                // Edge::score (:138, :256-261) for accepted edges only
-                const hc_candidate cd = load_candidate(P, i);
-                const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx1));
-                const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx2));
-                const hc_tmp32 t = P.tmp[i];
-                double ov[2], ml[2];
+        const uint32_t ex = before + inc - mine;
+        u64 de = eoff + (ex & 0xffffu), dn = ooff + (ex >> 16);
+        if (mine) {
 #pragma unroll
-                for (int w = 0; w < 2; w++) {
-                    if (t.tl[w] == 0) ml[w] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: window not scored
-                    else if (cfull & HC_CLS_EXACT) ml[w] = __longlong_as_double((long long)t.S[w]);
-                    else ml[w] = fx_mean(t.S[w], t.tl[w]);
-                    ov[w] = t.tl[w] ? exp(ml[w]) : 0.0;
+            for (int j = 0; j < 4; j++) {
+                const uint32_t cfull = (w4 >> (8 * j)) & 0xffu;
+                const uint32_t c = cfull & HC_CLS_MASK;
+                if (c == HC_CLASS_EDGE) {
+                    if (de < edges_cap) emit_edge(P, i0 + j, cfull, cand_offset, edges + de);
+                    de++;
+                } else if (c == HC_CLASS_NONEDGE) {
+                    if (dn < nonedge_cap) nonedge[dn] = i0 + j + cand_offset;
+                    dn++;
                 }
-                const uint32_t two = ((r1.w | r2.w) & HC_LEN_MASK) != 0;
-                hc_edge e;
-                e.cand = i + cand_offset;
-                e.score = combine_score(two, cfull & HC_CLS_BOTH, ov[0], ov[1]);
-                e.mismatch_rate = t.mismatch_rate;
-                extra_pos(cd, r1, r2, e.pos3, e.pos4);
-                e.mean_log[0] = ml[0];
-                e.mean_log[1] = ml[1];
-                edges[dst] = e;
             }
-        } else if (c == HC_CLASS_NONEDGE) {
-            const u64 dst = ooff + po + __popc(bo & lt);
-            if (dst < nonedge_cap) nonedge[dst] = i + cand_offset;
         }
-        eoff += te;
-        ooff += to;
+        eoff += total & 0xffffu;
+        ooff += total >> 16;
         __syncthreads();
     }
 }
