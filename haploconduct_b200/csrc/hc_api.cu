@@ -216,7 +216,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
         nl += 2;
     }
     CU(hc_launch_compact(P, d_edges, edges_cap, d_nonedge, nonedge_cap, d.blockcounts, cand_offset, d_run, st));
-    nl += (n > 0 ? 3 : 1) + (d_run ? 1 : 0);
+    nl += (n > 0 ? 4 : 1) + (d_run ? 1 : 0);   // count, scan, scatter, emit_edges (+ advance)
     if (k1) CU(cudaEventRecord(k1, st));
     if (d_counts) {   // {n_edges, n_nonedges, n_exact} are contiguous in the counter block; [3] = invalid candidates
         CU(cudaMemcpyAsync(d_counts, d.counters + HC_CNT_EDGES, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));

@@ -889,12 +889,13 @@ __device__ __forceinline__ void emit_edge(const hc_kparams& P, u64 i, uint32_t c
 // Each thread owns four consecutive candidates (one 32-bit load of class bytes); ranks come from a warp scan of the
 // packed (edges | non-edges << 16) counts and the per-warp totals, so the lists keep the input order.
 __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kparams P, const u64* __restrict__ blockoffs,
-                                                                   hc_edge* edges, u64 edges_cap, uint64_t* nonedge,
-                                                                   u64 nonedge_cap, u64 cand_offset) {
+                                                                   uint32_t* edge_src, uint64_t* nonedge, u64 nonedge_cap,
+                                                                   u64 cand_offset) {
     __shared__ uint32_t wtot[HC_CB_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 base = (u64)blockIdx.x * HC_CB_ITEMS;
-    u64 eoff = blockoffs[2 * blockIdx.x] + (P.run ? P.run[0] : 0ull), ooff = blockoffs[2 * blockIdx.x + 1] + (P.run ? P.run[1] : 0ull);
+    const u64 run_e = P.run ? P.run[0] : 0ull;
+    u64 eoff = blockoffs[2 * blockIdx.x] + run_e, ooff = blockoffs[2 * blockIdx.x + 1] + (P.run ? P.run[1] : 0ull);
     for (uint32_t k0 = 0; k0 < HC_CB_ITEMS; k0 += 4 * HC_CB_THREADS) {
         const u64 i0 = base + k0 + 4ull * threadIdx.x;
         uint32_t w4 = 0;                                           // class bytes of candidates i0 .. i0+3 (0 = discard beyond n)
@@ -925,7 +926,7 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
                 const uint32_t cfull = (w4 >> (8 * j)) & 0xffu;
                 const uint32_t c = cfull & HC_CLS_MASK;
                 if (c == HC_CLASS_EDGE) {
-                    if (de < edges_cap) emit_edge(P, i0 + j, cfull, cand_offset, edges + de);
+                    edge_src[de - run_e] = (uint32_t)(i0 + j);        // rank within this batch -> candidate; emitted by hc_emit_edges
                     de++;
                 } else if (c == HC_CLASS_NONEDGE) {
                     if (dn < nonedge_cap) nonedge[dn] = i0 + j + cand_offset;
@@ -936,6 +937,18 @@ __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kpa
         eoff += total & 0xffffu;
         ooff += total >> 16;
         __syncthreads();
+    }
+}
+
+// One thread per accepted edge of the batch (dense: no idle lanes next to the exp() and the random loads)
+__global__ void __launch_bounds__(256) hc_emit_edges(const hc_kparams P, const uint32_t* __restrict__ edge_src, hc_edge* edges,
+                                                     u64 edges_cap, u64 cand_offset) {
+    const u64 n_edges = P.counters[HC_CNT_EDGES];
+    const u64 run_e = P.run ? P.run[0] : 0ull;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n_edges; k += (u64)gridDim.x * blockDim.x) {
+        if (run_e + k >= edges_cap) break;
+        const u64 i = edge_src[k];
+        emit_edge(P, i, P.cls[i], cand_offset, edges + run_e + k);
     }
 }
 
@@ -994,7 +1007,11 @@ cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t ed
     }
     hc_compact_scan<<<1, 1024, 0, st>>>(d_blockcounts, nb, offs, P.counters);
     if (nb > 0) {
-        hc_compact_scatter<<<nb, HC_CB_THREADS, 0, st>>>(P, offs, d_edges, edges_cap, d_nonedge, nonedge_cap, cand_offset);
+        // P.flagged has been consumed by the reference-order pass; it now carries the source index of every edge
+        hc_compact_scatter<<<nb, HC_CB_THREADS, 0, st>>>(P, offs, P.flagged, d_nonedge, nonedge_cap, cand_offset);
+        const u64 want = (P.n + 255) / 256;
+        const unsigned eb = (unsigned)(want < 148ull * 8 ? want : 148ull * 8);
+        hc_emit_edges<<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
     }
     if (d_run) hc_compact_advance<<<1, 1, 0, st>>>(d_run, P.counters);
     return cudaGetLastError();
