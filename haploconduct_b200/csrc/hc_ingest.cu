@@ -5,8 +5,10 @@
 // one thread per line for the field parse, ordered compaction (count -> scan -> scatter).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/hc_b200.h"
 
@@ -23,6 +25,9 @@ struct hc_idmap {
     void* ws[16];
     size_t ws_cap[16];
     cudaEvent_t e0, e1;
+    // piece pipeline of the host-buffer entry point: copies in / kernels / copies out on three streams
+    cudaStream_t s_main, s_copy, s_out;
+    cudaEvent_t ev_in[2], ev_out[2];
 };
 
 static cudaError_t ws_get(hc_idmap* m, int k, size_t bytes, void** out) {
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(LINES_PER_BLOCK) ing_count(const uint8_t* stat
 
 __global__ void __launch_bounds__(LINES_PER_BLOCK) ing_scatter(const uint8_t* status, const hc_candidate* tmp_c, const hc_overlap_rec* tmp_f, u64 n, const u64* off_s,
                                                                const u64* off_f, hc_candidate* cand, u64* cand_line,
-                                                               hc_overlap_rec* filt, u64* filt_line) {
+                                                               hc_overlap_rec* filt, u64* filt_line, u64 line_base) {
     __shared__ uint32_t ws[32], wf[32];
     const u64 i = (u64)blockIdx.x * LINES_PER_BLOCK + threadIdx.x;
     const uint8_t st = i < n ? status[i] : 0;
@@ -265,11 +270,11 @@ __global__ void __launch_bounds__(LINES_PER_BLOCK) ing_scatter(const uint8_t* st
     if (st == HC_LINE_SCORE) {
         const u64 k = off_s[blockIdx.x] + ps + __popc(bs & lt);
         cand[k] = tmp_c[i];
-        if (cand_line) cand_line[k] = i;
+        if (cand_line) cand_line[k] = line_base + i;
     } else if (st == HC_LINE_NONEDGE) {
         const u64 k = off_f[blockIdx.x] + pf + __popc(bf & lt);
         filt[k] = tmp_f[i];
-        if (filt_line) filt_line[k] = i;
+        if (filt_line) filt_line[k] = line_base + i;
     }
 }
 
@@ -294,6 +299,8 @@ extern "C" hc_idmap* hc_idmap_create(const uint64_t* ids, uint64_t n_reads, int 
     m->device = device; m->n = n_reads; m->slots = nullptr; m->direct = nullptr; m->direct_n = 0; m->mask = 0;
     memset(m->ws, 0, sizeof(m->ws)); memset(m->ws_cap, 0, sizeof(m->ws_cap));
     m->e0 = m->e1 = nullptr;
+    m->s_main = m->s_copy = m->s_out = nullptr;
+    m->ev_in[0] = m->ev_in[1] = m->ev_out[0] = m->ev_out[1] = nullptr;
     u64 max_id = 0;
     for (u64 i = 0; i < n_reads; i++) max_id = std::max<u64>(max_id, ids[i]);
     const bool dense = n_reads > 0 && max_id < 4 * n_reads + 1024;     // rename_fas.py numbers the reads 0..n-1
@@ -322,6 +329,13 @@ extern "C" hc_idmap* hc_idmap_create(const uint64_t* ids, uint64_t n_reads, int 
     ICU(cudaDeviceSynchronize());
     ICU(cudaEventCreate(&m->e0));
     ICU(cudaEventCreate(&m->e1));
+    ICU(cudaStreamCreateWithFlags(&m->s_main, cudaStreamNonBlocking));
+    ICU(cudaStreamCreateWithFlags(&m->s_copy, cudaStreamNonBlocking));
+    ICU(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        ICU(cudaEventCreateWithFlags(&m->ev_in[k], cudaEventDisableTiming));
+        ICU(cudaEventCreateWithFlags(&m->ev_out[k], cudaEventDisableTiming));
+    }
 done:
     cudaFree(d_ids);
     if (rc != HC_OK) { hc_idmap_destroy(m); return nullptr; }
@@ -336,13 +350,17 @@ extern "C" void hc_idmap_destroy(hc_idmap* m) {
     for (int k = 0; k < 16; k++) cudaFree(m->ws[k]);
     if (m->e0) cudaEventDestroy(m->e0);
     if (m->e1) cudaEventDestroy(m->e1);
+    for (int k = 0; k < 2; k++) { if (m->ev_in[k]) cudaEventDestroy(m->ev_in[k]); if (m->ev_out[k]) cudaEventDestroy(m->ev_out[k]); }
+    if (m->s_main) cudaStreamDestroy(m->s_main);
+    if (m->s_copy) cudaStreamDestroy(m->s_copy);
+    if (m->s_out) cudaStreamDestroy(m->s_out);
     delete m;
 }
 
 // Device-side core: text already on the device.  Outputs are device buffers; counts[0..1] land in host memory.
 static int ingest_device(const hc_idmap* cm, const char* d_text, u64 n_bytes, const hc_ingest_params* p, hc_candidate* d_cand,
                          uint64_t* d_cand_line, u64 cand_cap, hc_overlap_rec* d_filt, uint64_t* d_filt_line, u64 filt_cap,
-                         hc_ingest_stats* st, cudaStream_t stream) {
+                         hc_ingest_stats* st, cudaStream_t stream, u64 line_base = 0) {
     hc_idmap* m = const_cast<hc_idmap*>(cm);     // the workspace is the only thing a call changes
     int rc = HC_OK;
     const u64 n_tiles = (n_bytes + TILE - 1) / TILE;
@@ -413,7 +431,7 @@ static int ingest_device(const hc_idmap* cm, const char* d_text, u64 n_bytes, co
     }
     ing_scatter<<<(unsigned)n_blocks, LINES_PER_BLOCK, 0, stream>>>(d_status, d_tmp_c, d_tmp_f, n_lines, d_os, d_of, d_cand,
                                                                     reinterpret_cast<u64*>(d_cand_line), d_filt,
-                                                                    reinterpret_cast<u64*>(d_filt_line));
+                                                                    reinterpret_cast<u64*>(d_filt_line), line_base);
     ICU(cudaEventRecord(m->e1, stream));
     ICU(cudaStreamSynchronize(stream));
     ICU(cudaGetLastError());
@@ -432,6 +450,94 @@ extern "C" int hc_ingest_overlaps_device(const hc_idmap* m, void* stream, const 
                          (cudaStream_t)stream);
 }
 
+// Large buffers are cut into pieces that end at a line end; the copy in of piece i + 1 and the copy out of piece i - 1
+// overlap the kernels of piece i (three streams, two buffer sets).  A line that reaches an output has 13 fields, i.e.
+// at least 26 bytes with its newline, which bounds the records a piece can produce without counting its lines first.
+static int ingest_pipelined(hc_idmap* m, const char* text, u64 n_bytes, const hc_ingest_params* p, hc_candidate* cand,
+                            uint64_t* cand_line, u64 cand_cap, hc_overlap_rec* filtered, uint64_t* filtered_line, u64 filtered_cap,
+                            hc_ingest_stats* stats, u64 piece) {
+    int rc = HC_OK;
+    std::vector<u64> cut(1, 0);
+    while (cut.back() < n_bytes) {
+        u64 end = cut.back() + piece;
+        if (end >= n_bytes) end = n_bytes;
+        else {
+            const void* nl = memrchr(text + cut.back(), '\n', end - cut.back());
+            if (nl) end = (u64)((const char*)nl - text) + 1;
+            else {   // a line longer than a piece: extend to its end
+                const void* fw = memchr(text + end, '\n', n_bytes - end);
+                end = fw ? (u64)((const char*)fw - text) + 1 : n_bytes;
+            }
+        }
+        cut.push_back(end);
+    }
+    const size_t n_pieces = cut.size() - 1;
+    u64 max_piece = 0;
+    for (size_t i = 0; i < n_pieces; i++) max_piece = std::max(max_piece, cut[i + 1] - cut[i]);
+    const u64 rec_cap = max_piece / 26 + 2;
+    const u64 tbytes = (max_piece + 16 + 255) & ~255ull;
+    char* d_text = nullptr;
+    hc_candidate* d_cand = nullptr;
+    hc_overlap_rec* d_filt = nullptr;
+    uint64_t *d_cl = nullptr, *d_fl = nullptr;
+    u64 lines = 0, ns = 0, nf = 0;
+    bool overflow = false;
+    hc_ingest_params pp = *p;
+    ICU(ws_get(m, 11, 2 * tbytes, (void**)&d_text));
+    ICU(ws_get(m, 12, 2 * rec_cap * sizeof(hc_candidate), (void**)&d_cand));
+    ICU(ws_get(m, 13, 2 * rec_cap * sizeof(hc_overlap_rec), (void**)&d_filt));
+    if (cand_line) ICU(ws_get(m, 14, 2 * rec_cap * sizeof(u64), (void**)&d_cl));
+    if (filtered_line) ICU(ws_get(m, 15, 2 * rec_cap * sizeof(u64), (void**)&d_fl));
+    ICU(cudaMemcpyAsync(d_text, text, cut[1] - cut[0], cudaMemcpyHostToDevice, m->s_copy));
+    ICU(cudaEventRecord(m->ev_in[0], m->s_copy));
+    for (size_t i = 0; i < n_pieces && lines < p->max_overlaps; i++) {
+        const int b = (int)(i & 1);
+        if (i + 1 < n_pieces) {   // buffer (i+1)&1 was read by piece i-1, whose kernels have completed (ingest_device returns synchronised)
+            ICU(cudaMemcpyAsync(d_text + (size_t)(b ^ 1) * tbytes, text + cut[i + 1], cut[i + 2] - cut[i + 1], cudaMemcpyHostToDevice, m->s_copy));
+            ICU(cudaEventRecord(m->ev_in[b ^ 1], m->s_copy));
+        }
+        ICU(cudaStreamWaitEvent(m->s_main, m->ev_in[b], 0));
+        if (i >= 2) ICU(cudaEventSynchronize(m->ev_out[b]));          // output set b has been copied out
+        hc_ingest_stats st;
+        pp.max_overlaps = p->max_overlaps - lines;
+        const u64 room_s = overflow ? 0 : std::min<u64>(rec_cap, cand_cap - ns), room_f = overflow ? 0 : std::min<u64>(rec_cap, filtered_cap - nf);
+        int prc = ingest_device(m, d_text + (size_t)b * tbytes, cut[i + 1] - cut[i], &pp, d_cand + (size_t)b * rec_cap,
+                                d_cl ? d_cl + (size_t)b * rec_cap : nullptr, room_s, d_filt + (size_t)b * rec_cap,
+                                d_fl ? d_fl + (size_t)b * rec_cap : nullptr, room_f, &st, m->s_main, lines);
+        if (prc == HC_ERR_CAPACITY) { overflow = true; prc = HC_OK; }   // keep counting: the caller gets the required sizes
+        if (prc != HC_OK) { rc = prc; goto done; }
+        if (st.first_error_line != EMPTY && stats->first_error_line == EMPTY) {
+            stats->first_error_line = lines + st.first_error_line;
+            stats->first_error_offset = cut[i] + st.first_error_offset;
+            stats->first_error_length = st.first_error_length;
+            stats->first_error_status = st.first_error_status;
+        }
+        if (!overflow) {
+            if (st.n_scored) {
+                ICU(cudaMemcpyAsync(cand + ns, d_cand + (size_t)b * rec_cap, st.n_scored * sizeof(hc_candidate), cudaMemcpyDeviceToHost, m->s_out));
+                if (cand_line) ICU(cudaMemcpyAsync(cand_line + ns, d_cl + (size_t)b * rec_cap, st.n_scored * sizeof(u64), cudaMemcpyDeviceToHost, m->s_out));
+            }
+            if (st.n_filtered) {
+                ICU(cudaMemcpyAsync(filtered + nf, d_filt + (size_t)b * rec_cap, st.n_filtered * sizeof(hc_overlap_rec), cudaMemcpyDeviceToHost, m->s_out));
+                if (filtered_line) ICU(cudaMemcpyAsync(filtered_line + nf, d_fl + (size_t)b * rec_cap, st.n_filtered * sizeof(u64), cudaMemcpyDeviceToHost, m->s_out));
+            }
+        }
+        ICU(cudaEventRecord(m->ev_out[b], m->s_out));
+        lines += st.n_lines; ns += st.n_scored; nf += st.n_filtered;
+        stats->n_skipped += st.n_skipped; stats->n_dropped += st.n_dropped; stats->device_ms += st.device_ms;
+    }
+    ICU(cudaStreamSynchronize(m->s_out));
+    ICU(cudaStreamSynchronize(m->s_copy));
+    stats->n_lines = lines; stats->n_scored = ns; stats->n_filtered = nf;
+    if (overflow) {
+        hc_set_last_error("hc_ingest_overlaps: output buffer too small (required sizes returned in stats)");
+        rc = HC_ERR_CAPACITY;
+    }
+done:
+    if (rc != HC_OK && rc != HC_ERR_CAPACITY) { cudaStreamSynchronize(m->s_copy); cudaStreamSynchronize(m->s_out); }
+    return rc;
+}
+
 extern "C" int hc_ingest_overlaps(const hc_idmap* cm, const char* text, uint64_t n_bytes, const hc_ingest_params* p,
                                   hc_candidate* cand, uint64_t* cand_line, uint64_t cand_cap, hc_overlap_rec* filtered,
                                   uint64_t* filtered_line, uint64_t filtered_cap, hc_ingest_stats* stats) {
@@ -446,11 +552,17 @@ extern "C" int hc_ingest_overlaps(const hc_idmap* cm, const char* text, uint64_t
     stats->first_error_line = EMPTY;
     if (n_bytes == 0) return HC_OK;
     ICU(cudaSetDevice(m->device));
+    {
+        u64 piece = 32ull << 20;
+        if (const char* e = getenv("HC_INGEST_PIECE")) { const u64 v = strtoull(e, nullptr, 10); if (v) piece = v; }   // tests
+        if (n_bytes > piece + piece / 2)
+            return ingest_pipelined(m, text, n_bytes, p, cand, cand_line, cand_cap, filtered, filtered_line, filtered_cap, stats, piece);
+    }
     ICU(ws_get(m, 11, n_bytes + 16, (void**)&d_text));
     ICU(cudaMemcpy(d_text, text, n_bytes, cudaMemcpyHostToDevice));
     if (cand_cap) { ICU(ws_get(m, 12, cand_cap * sizeof(hc_candidate), (void**)&d_cand)); if (cand_line) ICU(ws_get(m, 14, cand_cap * sizeof(u64), (void**)&d_cl)); }
     if (filtered_cap) { ICU(ws_get(m, 13, filtered_cap * sizeof(hc_overlap_rec), (void**)&d_filt)); if (filtered_line) ICU(ws_get(m, 15, filtered_cap * sizeof(u64), (void**)&d_fl)); }
-    rc = ingest_device(m, d_text, n_bytes, p, d_cand, d_cl, cand_cap, d_filt, d_fl, filtered_cap, stats, 0);
+    rc = ingest_device(m, d_text, n_bytes, p, d_cand, d_cl, cand_cap, d_filt, d_fl, filtered_cap, stats, m->s_main);
     if (rc != HC_OK) goto done;
     if (stats->n_scored) {
         ICU(cudaMemcpy(cand, d_cand, stats->n_scored * sizeof(hc_candidate), cudaMemcpyDeviceToHost));

@@ -83,3 +83,24 @@ def test_ingest_many_tiles(built_lib):
     text = W.fuzz_overlap_text(np.tile(g.cands, 12), g.rs.ids, seed=21)
     st = _check_against_oracle(text, g.rs.ids, min_overlap_len=70, min_overlap_perc=10)
     assert int(st["n_lines"]) > 60000 and len(text) > 2_500_000
+
+
+@pytest.mark.parametrize("piece", ["700", "5000", "100000"])
+def test_ingest_piece_pipeline(built_lib, monkeypatch, piece):
+    """Large buffers are cut into pieces at line ends and pipelined (copy in / kernels / copy out); the piece size must not
+    change anything: records, order, line numbers, counts, first error, max_overlaps, capacity report."""
+    g = load_golden("synth_all_types")
+    text = W.fuzz_overlap_text(np.tile(g.cands, 2), g.rs.ids, seed=31)
+    monkeypatch.setenv("HC_INGEST_PIECE", piece)
+    _check_against_oracle(text, g.rs.ids, min_overlap_len=80, min_overlap_perc=20)
+    _check_against_oracle(text, g.rs.ids, min_overlap_len=80, max_overlaps=3333)
+    _check_against_oracle(text, g.rs.ids[: len(g.rs.ids) // 2], min_overlap_len=80)          # unknown ids somewhere in the middle
+    lines = text.split(b"\n")
+    lines[len(lines) // 2] = b"1\t2\t-1\t-\t-\t+\t+\t50\t-\t100\t-\ts\ts"                      # a line the reference exits on
+    _check_against_oracle(b"\n".join(lines), g.rs.ids, min_overlap_len=80)
+    _check_against_oracle(text + b"x" * 3000, g.rs.ids, min_overlap_len=80)                   # a last line longer than a piece, no newline
+    m = capi.IdMap(g.rs.ids)
+    with pytest.raises(capi.HcError) as e:
+        m.ingest(text, F.make_ingest_params(80), cand_cap=10, filtered_cap=10)
+    cand, _, filt, _, st = m.ingest(text, F.make_ingest_params(80))
+    assert e.value.code == -5 and e.value.required == (len(cand), len(filt))
