@@ -320,7 +320,7 @@ __global__ void fno3_pass(const u64* off, u64 n, const uint32_t* sr_idx, const h
                     atomicMin(&mins[h], seq);
                     continue;
                 }
-                while (keys[h] != key) h = (h + 1) & mask;
+                if (MODE != 0) while (keys[h] != key) h = (h + 1) & mask;
                 bool ok = mins[h] == seq;                                   // first original wins, :116-121
                 hc_fno_overlap o;
                 if (ok) ok = deduce_overlap(A, B, sr_pos[i], sr_pos[j], o);
