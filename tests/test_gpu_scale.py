@@ -11,9 +11,12 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def c4_small():
-    pr = WT.make_paired_reads(200_000, genome_len=2_000, seed=20261018, device="cuda")
+@pytest.fixture(scope="module", params=[150, 250], ids=["c4_2x150", "c3_2x250"])
+def c4_small(request):
+    """config-4 shaped (2x150) and config-3 shaped (2x250) reads; candidates need half of min_overlap_len per mate"""
+    L = request.param
+    pr = WT.make_paired_reads(200_000 if L == 150 else 120_000, read_len=L, genome_len=2_000, seed=20261018 if L == 150 else 20261017,
+                              insert=(450.0, 50.0) if L == 150 else (600.0, 60.0), device="cuda")
     rec = WT.make_pp_candidates(pr, D=40, shard=0, n_shards=1, max_cands=5_000_000)
     cands = WT.candidates_as_numpy(rec)
     return pr.readset(), cands
@@ -41,8 +44,9 @@ def test_shard_invariance_and_order(built_lib, c4_small):
     assert np.all(np.diff(e_all["cand"].astype(np.int64)) > 0) and np.all(np.diff(n_all.astype(np.int64)) > 0)   # input order
     assert 0 < len(e_all) < n and 0 < len(n_all) < n
     # the kernel's own bookkeeping of algorithmic bytes: 32 + sum_w(2*ceil(L/4) + 2*ceil(L/8) + 2L) + 16 per candidate
-    L1 = 150 - cands["pos1"].astype(np.int64)
-    L2 = 150 - cands["pos2"].astype(np.int64)
+    RL = int(rs.descs["seq_len"][0, 0])       # every mate has the same length in this workload
+    L1 = RL - cands["pos1"].astype(np.int64)
+    L2 = RL - cands["pos2"].astype(np.int64)
     want = (48 * n + sum(int((2 * ((L + 3) // 4) + 2 * ((L + 7) // 8) + 2 * L).sum()) for L in (L1, L2)))
     assert int(s_all["algorithmic_bytes"]) == want and int(s_all["n_positions"]) == int((L1 + L2).sum())
 
