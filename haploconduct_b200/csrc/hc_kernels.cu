@@ -279,18 +279,47 @@ __device__ __forceinline__ void process32(const hc_kparams& P, const uint32_t* _
 // Re-align the A side exactly as in the planar kernel; the XOR of A and (swizzled) B bytes is at
 // once the table column and, in bits 6-7, the base difference.  Mismatch flags of the 8 words are
 // gathered into one 32-bit word (OR_j flags_j >> j) so that a single popc counts them.
+#ifdef HC_NO_LD256
 struct PkRow {          // the raw loads of one packed lane-chunk and what is needed to interpret them
     uint4 q0, q1, q2, y0, y1;
     uint32_t n, off, hasN;
 };
+#else
+// The L1 data pipe moves one 128-byte line per wavefront whatever the access width (tools/micro/l1_wavefronts.cu), and
+// the lanes of a warp sit in about a dozen different lines, so what a lane-chunk costs there is its NUMBER of load
+// instructions: 32-byte loads (LDG.256, sm_100) fetch the B side with one and the A side with two instead of 2 + 3.
+struct PkRow {
+    uint32_t a[16];     // A side: the 64 bytes from the 32-byte boundary below the chunk (upper half zero when not needed)
+    uint32_t y[8];      // B side: the chunk's 32 bytes (32-byte aligned by construction)
+    uint32_t n, off, hasN;   // off = 0..31
+};
+
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* d) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+                 : "l"(p));
+}
+#endif
 
 __device__ __forceinline__ PkRow load32_packed(const hc_kparams& P, u64 xpos, uint32_t ypos16, uint32_t L, uint32_t hasN, uint32_t k) {
     PkRow r;
     const u64 xp = xpos + 32ull * k;
     r.n = min(L - 32u * k, 32u);   // 1..32 valid positions
     const uint32_t yq = ypos16 + 2u * k;
-    r.off = (uint32_t)xp & 15u;
     r.hasN = hasN;
+#ifndef HC_NO_LD256
+    r.off = (uint32_t)xp & 31u;
+    const uint8_t* xb = P.pk + (xp & ~31ull);
+    ldg256(xb, r.a);
+    if (r.off + r.n > 32u) ldg256(xb + 32, r.a + 8);   // never beyond the slot: it holds window positions
+    else {
+#pragma unroll
+        for (int i = 8; i < 16; i++) r.a[i] = 0u;
+    }
+    ldg256(P.pk + 16ull * yq, r.y);                    // slots are padded by >= 32 zero bytes
+    return r;
+#else
+    r.off = (uint32_t)xp & 15u;
     const bool two = r.n > 16u, x1 = r.off + r.n > 16u, x2 = r.off + r.n > 32u;
     const uint4 z4 = make_uint4(0, 0, 0, 0);
     const uint4* xq = reinterpret_cast<const uint4*>(P.pk + (xp & ~15ull));
@@ -301,14 +330,27 @@ __device__ __forceinline__ PkRow load32_packed(const hc_kparams& P, u64 xpos, ui
     r.y0 = __ldg(yqp);
     r.y1 = two ? __ldg(yqp + 1) : z4;
     return r;
+#endif
 }
 
 template <bool HAS_VOID>
 __device__ __forceinline__ void compute32_packed(const uint32_t* __restrict__ T, const uint32_t* __restrict__ VM, const PkRow& r,
                                                  uint32_t& sum, uint32_t& mm, uint32_t& ncnt, uint32_t& vd) {
-    const uint4 q0 = r.q0, q1 = r.q1, q2 = r.q2, y0 = r.y0, y1 = r.y1;
     const uint32_t n = r.n, off = r.off, hasN = r.hasN;
     const uint32_t vm = VM[n];
+#ifndef HC_NO_LD256
+    const bool s4 = (off & 16u) != 0, s2 = (off & 8u) != 0, s1 = (off & 4u) != 0;
+    uint32_t V2[12], V1[10], V[9];
+#pragma unroll
+    for (int i = 0; i < 12; i++) V2[i] = s4 ? r.a[i + 4] : r.a[i];
+#pragma unroll
+    for (int i = 0; i < 10; i++) V1[i] = s2 ? V2[i + 2] : V2[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t* wy = r.y;
+#else
+    const uint4 q0 = r.q0, q1 = r.q1, q2 = r.q2, y0 = r.y0, y1 = r.y1;
     const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
     const bool s2 = (off & 8u) != 0, s1 = (off & 4u) != 0;
     uint32_t V1[10], V[9];
@@ -318,6 +360,7 @@ __device__ __forceinline__ void compute32_packed(const uint32_t* __restrict__ T,
     for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
     const uint32_t sh = (off & 3u) * 8u;
     const uint32_t wy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#endif
     uint32_t acc = 0, orv = 0, flags = 0, vw = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
