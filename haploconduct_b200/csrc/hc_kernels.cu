@@ -182,6 +182,15 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
+// 32-byte load (LDG.256, sm_100): the L1 data pipe moves one 128-byte line per wavefront whatever the access width
+// (tools/micro/l1_wavefronts.cu) and the lanes of a warp sit in about a dozen different lines, so what a lane-chunk
+// costs there is its NUMBER of load instructions, not its bytes.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* d) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+        : "l"(p));
+}
+
 // 16 positions: (A codes ^ swizzle(B codes)) | mismatch<<7 -> column byte, B code -> row byte,
 // one PRMT per position builds the table index (upper bytes zero through PRMT's sign-replicate
 // mode on the row byte, whose msb is always 0), 16 shared-memory lookups.
@@ -216,6 +225,19 @@ __device__ __forceinline__ void process32(const hc_kparams& P, const uint32_t* _
     const bool two = n > 16u, x1 = off + n > 16u, x2 = off + n > 32u;
     const uint4 z4 = make_uint4(0, 0, 0, 0);
     // ---- loads, all issued before first use; blocks beyond the window are not touched
+#ifndef HC_NO_LD256
+    const uint32_t off32 = (uint32_t)xp & 31u;
+    uint32_t QA[16], wy[8];
+    const uint8_t* xb = P.qual + (xp & ~31ull);
+    ldg256(xb, QA);
+    if (off32 + n > 32u) ldg256(xb + 32, QA + 8);   // never beyond the slot: it holds window positions
+    else {
+#pragma unroll
+        for (int i = 8; i < 16; i++) QA[i] = 0u;
+    }
+    ldg256(P.qual + 16ull * yq, wy);               // slots are padded by >= 32 zero bytes
+    (void)two; (void)z4;
+#else
     const uint4* xq = reinterpret_cast<const uint4*>(P.qual + (xp & ~15ull));
     const uint4 q0 = __ldg(xq);
     const uint4 q1 = x1 ? __ldg(xq + 1) : z4;
@@ -223,6 +245,7 @@ __device__ __forceinline__ void process32(const hc_kparams& P, const uint32_t* _
     const uint4* yqp = reinterpret_cast<const uint4*>(P.qual) + yq;
     const uint4 y0 = __ldg(yqp);
     const uint4 y1 = two ? __ldg(yqp + 1) : z4;
+#endif
     const uint32_t* bxp = P.base2 + (xp >> 4);
     const uint32_t b0 = __ldg(bxp);
     const uint32_t b1 = x1 ? __ldg(bxp + 1) : 0u;
@@ -256,18 +279,27 @@ __device__ __forceinline__ void process32(const hc_kparams& P, const uint32_t* _
     }
     mm = __popc(m0) + __popc(m1);
     // ---- A-side quality codes: select 9 of the 12 loaded words (word offset 0..3), then funnel by bytes
-    const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
     const bool s2 = (off & 8u) != 0, s1 = (off & 4u) != 0;
     uint32_t V1[10], V[9];
+#ifndef HC_NO_LD256
+    const bool s4 = (off32 & 16u) != 0;
+    uint32_t V2[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) V2[i] = s4 ? QA[i + 4] : QA[i];
+#pragma unroll
+    for (int i = 0; i < 10; i++) V1[i] = s2 ? V2[i + 2] : V2[i];
+#else
+    const uint32_t W[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
     for (int i = 0; i < 10; i++) V1[i] = s2 ? W[i + 2] : W[i];
+    const uint32_t wy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#endif
 #pragma unroll
     for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
     const uint32_t sh = (off & 3u) * 8u;
     uint32_t wa[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) wa[i] = __funnelshift_r(V[i], V[i + 1], sh);
-    const uint32_t wy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
     uint32_t acc = 0, orv = 0;
     lookup16<HAS_VOID>(T, wa, wy, m0, acc, orv);
     lookup16<HAS_VOID>(T, wa + 4, wy + 4, m1, acc, orv);
@@ -285,20 +317,13 @@ struct PkRow {          // the raw loads of one packed lane-chunk and what is ne
     uint32_t n, off, hasN;
 };
 #else
-// The L1 data pipe moves one 128-byte line per wavefront whatever the access width (tools/micro/l1_wavefronts.cu), and
-// the lanes of a warp sit in about a dozen different lines, so what a lane-chunk costs there is its NUMBER of load
-// instructions: 32-byte loads (LDG.256, sm_100) fetch the B side with one and the A side with two instead of 2 + 3.
+// 32-byte loads (ldg256) fetch the B side with one instruction and the A side with two instead of 2 + 3.
 struct PkRow {
     uint32_t a[16];     // A side: the 64 bytes from the 32-byte boundary below the chunk (upper half zero when not needed)
     uint32_t y[8];      // B side: the chunk's 32 bytes (32-byte aligned by construction)
     uint32_t n, off, hasN;   // off = 0..31
 };
 
-__device__ __forceinline__ void ldg256(const void* p, uint32_t* d) {
-    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
-                 : "l"(p));
-}
 #endif
 
 __device__ __forceinline__ PkRow load32_packed(const hc_kparams& P, u64 xpos, uint32_t ypos16, uint32_t L, uint32_t hasN, uint32_t k) {
