@@ -13,6 +13,7 @@
 #include "../../include/hc_b200.h"
 #include "hc_layout.h"
 #include "hc_tables.h"
+#include "hc_stage.h"
 #include "hc_kernels.cuh"
 #include "hc_pack.cuh"
 #include "hc_consensus.cuh"
@@ -476,9 +477,9 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
     cudaError_t e = cudaSetDevice(first_device);
     if (e == cudaSuccess) e = cudaMalloc(&d_text, 2 * qbase + 16);
     if (e == cudaSuccess) e = cudaMalloc(&d_src, 2 * n_reads * sizeof(hc_pack_src));
-    if (e == cudaSuccess) e = cudaMemcpy(d_text, bases, blob, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_text + qbase, quals, blob, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_src, src.data(), 2 * n_reads * sizeof(hc_pack_src), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = hc_copy_h2d(d_text, bases, blob);
+    if (e == cudaSuccess) e = hc_copy_h2d(d_text + qbase, quals, blob);
+    if (e == cudaSuccess) e = hc_copy_h2d(d_src, src.data(), 2 * n_reads * sizeof(hc_pack_src));
     int rc = HC_OK;
     if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_store_create: ") + cudaGetErrorString(e));
     else rc = build_store(s, rd, d_text, d_src, 0, first_device, n_devices);
@@ -517,7 +518,7 @@ hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, con
     cudaError_t e = cudaSetDevice(first_device);
     if (e == cudaSuccess) e = cudaMalloc(&d_text, off[3] + 16);
     for (int k = 0; k < 3 && e == cudaSuccess; k++)
-        if (bytes[k]) e = cudaMemcpy(d_text + off[k], file[k], bytes[k], cudaMemcpyHostToDevice);
+        if (bytes[k]) e = hc_copy_h2d(d_text + off[k], file[k], bytes[k]);
     for (int k = 0; k < 3 && e == cudaSuccess; k++) e = hc_fastq_index(d_text + off[k], bytes[k], max_reads, &d_ls[k], &nl[k], &nrec[k], 0);
     if (e == cudaSuccess) {
         n_single = nrec[0];

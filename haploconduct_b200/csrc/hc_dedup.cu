@@ -4,6 +4,7 @@
 #include <string>
 #include <cuda_runtime.h>
 #include "../../include/hc_b200.h"
+#include "hc_stage.h"
 
 void hc_set_last_error(const char* msg);   // hc_api.cu
 
@@ -110,11 +111,11 @@ extern "C" int hc_dedup_edges(const hc_dedup_edge* edges, uint64_t n, int ignore
     DCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); DCU(cudaMemset(d_best, 0xff, cap * sizeof(u64)));
     DCU(cudaMemset(d_first, 0xff, cap * sizeof(u64))); DCU(cudaMemset(d_counts, 0, 2 * sizeof(u64)));
     if (inclusions && n_vertices) { DCU(cudaMalloc(&d_inc, n_vertices)); DCU(cudaMemcpy(d_inc, inclusions, n_vertices, cudaMemcpyHostToDevice)); }
-    DCU(cudaMemcpy(d_e, edges, n * sizeof(hc_dedup_edge), cudaMemcpyHostToDevice));
+    DCU(hc_copy_h2d(d_e, edges, n * sizeof(hc_dedup_edge)));
     dd_claim<<<blocks, threads>>>(d_e, n, d_keys, d_best, d_first, cap - 1, d_counts);
     dd_resolve<<<blocks, threads>>>(d_e, n, d_keys, d_best, d_first, cap - 1, ignore_inclusions, d_win, d_inc, d_counts);
     DCU(cudaGetLastError());
-    DCU(cudaMemcpy(winner, d_win, n, cudaMemcpyDeviceToHost));
+    DCU(hc_copy_d2h(winner, d_win, n));
     DCU(cudaMemcpy(counts, d_counts, 2 * sizeof(u64), cudaMemcpyDeviceToHost));
     if (d_inc) DCU(cudaMemcpy(inclusions, d_inc, n_vertices, cudaMemcpyDeviceToHost));
 done:

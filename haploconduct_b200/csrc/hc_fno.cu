@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include "../../include/hc_b200.h"
 #include "hc_scan.cuh"
+#include "hc_stage.h"
 
 namespace {
 
@@ -357,11 +358,14 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     if (!in || !n_out || (n_edges && !edges) || (out_cap && !out)) { hc_set_last_error("hc_fno1: NULL argument"); return HC_ERR_ARG; }
     *n_out = 0;
     const u64 V = in->n_vertices, NS = in->n_superreads;
-    for (u64 i = 0; i < n_edges; i++)
-        if (edges[i].u >= V || edges[i].v >= V) { hc_set_last_error("hc_fno1: edge vertex out of range"); return HC_ERR_ARG; }
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (long long i = 0; i < (long long)n_edges; i++) bad |= (edges[i].u >= V || edges[i].v >= V);
+    if (bad) { hc_set_last_error("hc_fno1: edge vertex out of range"); return HC_ERR_ARG; }
     const u64 nsr = V ? in->sr_off[V] : 0;
-    for (u64 i = 0; i < nsr; i++)
-        if (in->sr_idx[i] >= NS) { hc_set_last_error("hc_fno1: super-read index out of range"); return HC_ERR_ARG; }
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (long long i = 0; i < (long long)nsr; i++) bad |= (in->sr_idx[i] >= NS);
+    if (bad) { hc_set_last_error("hc_fno1: super-read index out of range"); return HC_ERR_ARG; }
     int rc = HC_OK;
     uint8_t *d_vis = nullptr, *d_lab = nullptr;
     hc_fno_read *d_vr = nullptr, *d_sr = nullptr;
@@ -377,49 +381,49 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     FCU(cudaSetDevice(device));
     if (n_edges == 0) goto done;
     blocks = (int)((n_edges + threads - 1) / threads < 4096 ? (n_edges + threads - 1) / threads : 4096);
-    FCU(cudaMalloc(&d_vis, V ? V : 1)); FCU(cudaMalloc(&d_lab, V ? V : 1));
-    FCU(cudaMalloc(&d_vr, (V ? V : 1) * sizeof(hc_fno_read))); FCU(cudaMalloc(&d_sr, (NS ? NS : 1) * sizeof(hc_fno_read)));
-    FCU(cudaMalloc(&d_sroff, (V + 1) * sizeof(u64))); FCU(cudaMalloc(&d_sridx, (nsr ? nsr : 1) * sizeof(uint32_t)));
-    FCU(cudaMalloc(&d_sub, (nsr ? nsr : 1) * sizeof(hc_fno_subread)));
-    FCU(cudaMalloc(&d_edges, n_edges * sizeof(hc_fno_edge))); FCU(cudaMalloc(&d_cnt, n_edges * sizeof(uint32_t)));
-    FCU(cudaMalloc(&d_off, n_edges * sizeof(u64))); FCU(cudaMalloc(&d_total, sizeof(u64)));
-    FCU(cudaMemcpy(d_vis, in->visited, V, cudaMemcpyHostToDevice)); FCU(cudaMemcpy(d_lab, in->label, V, cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_vr, in->vertex_read, V * sizeof(hc_fno_read), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_sr, in->superread, NS * sizeof(hc_fno_read), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_sroff, in->sr_off, (V + 1) * sizeof(u64), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_sridx, in->sr_idx, nsr * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_sub, in->sr_sub, nsr * sizeof(hc_fno_subread), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_edges, edges, n_edges * sizeof(hc_fno_edge), cudaMemcpyHostToDevice));
+    FCU(hc_scratch_alloc((void**)&d_vis, V ? V : 1)); FCU(hc_scratch_alloc((void**)&d_lab, V ? V : 1));
+    FCU(hc_scratch_alloc((void**)&d_vr, (V ? V : 1) * sizeof(hc_fno_read))); FCU(hc_scratch_alloc((void**)&d_sr, (NS ? NS : 1) * sizeof(hc_fno_read)));
+    FCU(hc_scratch_alloc((void**)&d_sroff, (V + 1) * sizeof(u64))); FCU(hc_scratch_alloc((void**)&d_sridx, (nsr ? nsr : 1) * sizeof(uint32_t)));
+    FCU(hc_scratch_alloc((void**)&d_sub, (nsr ? nsr : 1) * sizeof(hc_fno_subread)));
+    FCU(hc_scratch_alloc((void**)&d_edges, n_edges * sizeof(hc_fno_edge))); FCU(hc_scratch_alloc((void**)&d_cnt, n_edges * sizeof(uint32_t)));
+    FCU(hc_scratch_alloc((void**)&d_off, n_edges * sizeof(u64))); FCU(hc_scratch_alloc((void**)&d_total, sizeof(u64)));
+    FCU(hc_copy_h2d(d_vis, in->visited, V)); FCU(hc_copy_h2d(d_lab, in->label, V));
+    FCU(hc_copy_h2d(d_vr, in->vertex_read, V * sizeof(hc_fno_read)));
+    FCU(hc_copy_h2d(d_sr, in->superread, NS * sizeof(hc_fno_read)));
+    FCU(hc_copy_h2d(d_sroff, in->sr_off, (V + 1) * sizeof(u64)));
+    FCU(hc_copy_h2d(d_sridx, in->sr_idx, nsr * sizeof(uint32_t)));
+    FCU(hc_copy_h2d(d_sub, in->sr_sub, nsr * sizeof(hc_fno_subread)));
+    FCU(hc_copy_h2d(d_edges, edges, n_edges * sizeof(hc_fno_edge)));
     D.n_vertices = V; D.visited = d_vis; D.label = d_lab; D.vertex_read = d_vr; D.sr_off = d_sroff; D.sr_idx = d_sridx;
     D.sr_sub = d_sub; D.superread = d_sr; D.resolve_orientations = in->resolve_orientations; D.no_inclusions = in->no_inclusions;
     fno_count<<<blocks, threads>>>(D, d_edges, n_edges, d_cnt);
-    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(n_edges) * sizeof(u64)));
+    FCU(hc_scratch_alloc((void**)&d_bsum, hc_scan::blocks_for(n_edges) * sizeof(u64)));
     hc_scan::exclusive_u32(d_cnt, n_edges, d_off, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     if (attempts == 0) goto done;
     while (cap < 2 * attempts + 2) cap <<= 1;
-    FCU(cudaMalloc(&d_keys, cap * sizeof(u64))); FCU(cudaMalloc(&d_mins, cap * sizeof(u64)));
+    FCU(hc_scratch_alloc((void**)&d_keys, cap * sizeof(u64))); FCU(hc_scratch_alloc((void**)&d_mins, cap * sizeof(u64)));
     FCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); FCU(cudaMemset(d_mins, 0xff, cap * sizeof(u64)));
-    FCU(cudaMalloc(&d_flags, attempts * sizeof(uint32_t))); FCU(cudaMalloc(&d_outpos, attempts * sizeof(u64)));
+    FCU(hc_scratch_alloc((void**)&d_flags, attempts * sizeof(uint32_t))); FCU(hc_scratch_alloc((void**)&d_outpos, attempts * sizeof(u64)));
     FCU(cudaMemset(d_flags, 0, attempts * sizeof(uint32_t)));
     fno_claim<<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1);
     fno_resolve<false><<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
-    cudaFree(d_bsum); d_bsum = nullptr;
-    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
+    hc_scratch_free(d_bsum); d_bsum = nullptr;
+    FCU(hc_scratch_alloc((void**)&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
     hc_scan::exclusive_u32(d_flags, attempts, d_outpos, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&produced, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     *n_out = produced;
     if (produced > out_cap) { hc_set_last_error("hc_fno1: output buffer too small (required size returned in n_out)"); rc = HC_ERR_CAPACITY; goto done; }
     if (produced == 0) goto done;
     ncopy = produced;
-    FCU(cudaMalloc(&d_out, ncopy * sizeof(hc_fno_overlap)));
+    FCU(hc_scratch_alloc((void**)&d_out, ncopy * sizeof(hc_fno_overlap)));
     fno_resolve<true><<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, d_outpos, d_out, ncopy);
     FCU(cudaGetLastError());
-    FCU(cudaMemcpy(out, d_out, ncopy * sizeof(hc_fno_overlap), cudaMemcpyDeviceToHost));
+    FCU(hc_copy_d2h(out, d_out, ncopy * sizeof(hc_fno_overlap)));
 done:
-    cudaFree(d_vis); cudaFree(d_lab); cudaFree(d_vr); cudaFree(d_sr); cudaFree(d_sroff); cudaFree(d_sridx); cudaFree(d_sub);
-    cudaFree(d_edges); cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_total); cudaFree(d_keys); cudaFree(d_mins);
-    cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out); cudaFree(d_bsum);
+    hc_scratch_free(d_vis); hc_scratch_free(d_lab); hc_scratch_free(d_vr); hc_scratch_free(d_sr); hc_scratch_free(d_sroff); hc_scratch_free(d_sridx); hc_scratch_free(d_sub);
+    hc_scratch_free(d_edges); hc_scratch_free(d_cnt); hc_scratch_free(d_off); hc_scratch_free(d_total); hc_scratch_free(d_keys); hc_scratch_free(d_mins);
+    hc_scratch_free(d_flags); hc_scratch_free(d_outpos); hc_scratch_free(d_out); hc_scratch_free(d_bsum);
     return rc;
 }
 
@@ -434,8 +438,10 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     *n_out = 0;
     if (n_originals == 0) return HC_OK;
     const u64 nent = off[n_originals];
-    for (u64 i = 0; i < nent; i++)
-        if (sr_idx[i] >= n_reads) { hc_set_last_error("hc_fno3: read index out of range"); return HC_ERR_ARG; }
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (long long i = 0; i < (long long)nent; i++) bad |= (sr_idx[i] >= n_reads);
+    if (bad) { hc_set_last_error("hc_fno3: read index out of range"); return HC_ERR_ARG; }
     int rc = HC_OK;
     u64 *d_off = nullptr, *d_seq = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr, *d_bsum = nullptr;
     uint32_t *d_idx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
@@ -446,38 +452,38 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     const int threads = 128;
     const int blocks = (int)((n_originals + threads - 1) / threads < 8192 ? (n_originals + threads - 1) / threads : 8192);
     FCU(cudaSetDevice(device));
-    FCU(cudaMalloc(&d_off, (n_originals + 1) * sizeof(u64))); FCU(cudaMalloc(&d_idx, (nent ? nent : 1) * sizeof(uint32_t)));
-    FCU(cudaMalloc(&d_pos, (nent ? nent : 1) * sizeof(hc_fno3_pos))); FCU(cudaMalloc(&d_reads, (n_reads ? n_reads : 1) * sizeof(hc_fno_read)));
-    FCU(cudaMalloc(&d_cnt, n_originals * sizeof(uint32_t))); FCU(cudaMalloc(&d_seq, n_originals * sizeof(u64)));
-    FCU(cudaMalloc(&d_total, sizeof(u64)));
-    FCU(cudaMemcpy(d_off, off, (n_originals + 1) * sizeof(u64), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_idx, sr_idx, nent * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_pos, sr_pos, nent * sizeof(hc_fno3_pos), cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(d_reads, reads, n_reads * sizeof(hc_fno_read), cudaMemcpyHostToDevice));
+    FCU(hc_scratch_alloc((void**)&d_off, (n_originals + 1) * sizeof(u64))); FCU(hc_scratch_alloc((void**)&d_idx, (nent ? nent : 1) * sizeof(uint32_t)));
+    FCU(hc_scratch_alloc((void**)&d_pos, (nent ? nent : 1) * sizeof(hc_fno3_pos))); FCU(hc_scratch_alloc((void**)&d_reads, (n_reads ? n_reads : 1) * sizeof(hc_fno_read)));
+    FCU(hc_scratch_alloc((void**)&d_cnt, n_originals * sizeof(uint32_t))); FCU(hc_scratch_alloc((void**)&d_seq, n_originals * sizeof(u64)));
+    FCU(hc_scratch_alloc((void**)&d_total, sizeof(u64)));
+    FCU(hc_copy_h2d(d_off, off, (n_originals + 1) * sizeof(u64)));
+    FCU(hc_copy_h2d(d_idx, sr_idx, nent * sizeof(uint32_t)));
+    FCU(hc_copy_h2d(d_pos, sr_pos, nent * sizeof(hc_fno3_pos)));
+    FCU(hc_copy_h2d(d_reads, reads, n_reads * sizeof(hc_fno_read)));
     fno3_count<<<blocks, threads>>>(d_off, n_originals, d_cnt);
-    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(n_originals) * sizeof(u64)));
+    FCU(hc_scratch_alloc((void**)&d_bsum, hc_scan::blocks_for(n_originals) * sizeof(u64)));
     hc_scan::exclusive_u32(d_cnt, n_originals, d_seq, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     if (attempts == 0) goto done;
     while (cap < 2 * attempts + 2) cap <<= 1;
-    FCU(cudaMalloc(&d_keys, cap * sizeof(u64))); FCU(cudaMalloc(&d_mins, cap * sizeof(u64)));
+    FCU(hc_scratch_alloc((void**)&d_keys, cap * sizeof(u64))); FCU(hc_scratch_alloc((void**)&d_mins, cap * sizeof(u64)));
     FCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); FCU(cudaMemset(d_mins, 0xff, cap * sizeof(u64)));
-    FCU(cudaMalloc(&d_flags, attempts * sizeof(uint32_t))); FCU(cudaMalloc(&d_outpos, attempts * sizeof(u64)));
+    FCU(hc_scratch_alloc((void**)&d_flags, attempts * sizeof(uint32_t))); FCU(hc_scratch_alloc((void**)&d_outpos, attempts * sizeof(u64)));
     fno3_pass<0><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, nullptr, nullptr, nullptr, 0);
     fno3_pass<1><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
-    cudaFree(d_bsum); d_bsum = nullptr;
-    FCU(cudaMalloc(&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
+    hc_scratch_free(d_bsum); d_bsum = nullptr;
+    FCU(hc_scratch_alloc((void**)&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
     hc_scan::exclusive_u32(d_flags, attempts, d_outpos, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&produced, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     *n_out = produced;
     if (produced > out_cap) { hc_set_last_error("hc_fno3: output buffer too small (required size returned in n_out)"); rc = HC_ERR_CAPACITY; goto done; }
     if (produced == 0) goto done;
-    FCU(cudaMalloc(&d_out, produced * sizeof(hc_fno_overlap)));
+    FCU(hc_scratch_alloc((void**)&d_out, produced * sizeof(hc_fno_overlap)));
     fno3_pass<2><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, d_outpos, d_out, produced);
     FCU(cudaGetLastError());
-    FCU(cudaMemcpy(out, d_out, produced * sizeof(hc_fno_overlap), cudaMemcpyDeviceToHost));
+    FCU(hc_copy_d2h(out, d_out, produced * sizeof(hc_fno_overlap)));
 done:
-    cudaFree(d_off); cudaFree(d_idx); cudaFree(d_pos); cudaFree(d_reads); cudaFree(d_cnt); cudaFree(d_seq); cudaFree(d_total);
-    cudaFree(d_keys); cudaFree(d_mins); cudaFree(d_flags); cudaFree(d_outpos); cudaFree(d_out); cudaFree(d_bsum);
+    hc_scratch_free(d_off); hc_scratch_free(d_idx); hc_scratch_free(d_pos); hc_scratch_free(d_reads); hc_scratch_free(d_cnt); hc_scratch_free(d_seq); hc_scratch_free(d_total);
+    hc_scratch_free(d_keys); hc_scratch_free(d_mins); hc_scratch_free(d_flags); hc_scratch_free(d_outpos); hc_scratch_free(d_out); hc_scratch_free(d_bsum);
     return rc;
 }

@@ -1,0 +1,153 @@
+// hc_stage.cu -- see hc_stage.h
+#include "hc_stage.h"
+
+#include <omp.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+
+namespace {
+
+constexpr size_t kChunkMax = 8u << 20;     // bytes per pinned staging buffer
+constexpr int kRing = 4;                   // buffers in flight
+constexpr size_t kBlock = 256u << 10;      // bytes per host thread task
+
+size_t env_size(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const unsigned long long x = strtoull(v, nullptr, 0);
+    return x ? (size_t)x : dflt;
+}
+// HC_STAGE_MIN: copies below this many bytes take the driver's own path (default 2 MB); HC_STAGE_CHUNK: bytes per
+// ring buffer (default and maximum 8 MB).  The tests set both to small values to run small inputs through the ring.
+const size_t kDirectBelow = env_size("HC_STAGE_MIN", 2u << 20);
+const size_t kChunk = [] { size_t c = env_size("HC_STAGE_CHUNK", kChunkMax); return c > kChunkMax ? kChunkMax : c; }();
+
+struct Ring {
+    unsigned char* buf[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kRing];
+    cudaStream_t stream = nullptr;         // blocking stream: ordered with the legacy default stream
+    bool ok = false;
+};
+
+std::mutex g_mu;            // one staged copy at a time per process (the ring is shared)
+Ring g_ring[16];            // per device
+
+cudaError_t ring_for(int dev, Ring** out) {
+    Ring& r = g_ring[dev & 15];
+    if (!r.ok) {
+        cudaError_t e = cudaStreamCreate(&r.stream);
+        if (e != cudaSuccess) return e;
+        for (int i = 0; i < kRing; i++) {
+            e = cudaHostAlloc(reinterpret_cast<void**>(&r.buf[i]), kChunkMax, cudaHostAllocPortable);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        r.ok = true;
+    }
+    *out = &r;
+    return cudaSuccess;
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int host_threads() {
+    int t = omp_get_max_threads();
+    if (t > 8) t = 8;
+    return t < 1 ? 1 : t;
+}
+
+void par_memcpy(void* dst, const void* src, size_t bytes, int threads) {
+    const long nb = (long)((bytes + kBlock - 1) / kBlock);
+    if (threads <= 1 || nb <= 1 || omp_in_parallel()) { memcpy(dst, src, bytes); return; }
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (long b = 0; b < nb; b++) {
+        const size_t o = (size_t)b * kBlock;
+        memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, bytes - o < kBlock ? bytes - o : kBlock);
+    }
+}
+
+}  // namespace
+
+cudaError_t hc_copy_h2d(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < kDirectBelow || is_pinned(src)) return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ring* r;
+    if ((e = ring_for(dev, &r)) != cudaSuccess) return e;
+    const int T = host_threads();
+    size_t done = 0;
+    for (int i = 0; done < bytes; i++) {
+        const int b = i % kRing;
+        const size_t n = bytes - done < kChunk ? bytes - done : kChunk;
+        if (i >= kRing && (e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;   // the DMA that read this buffer
+        par_memcpy(r->buf[b], static_cast<const char*>(src) + done, n, T);
+        if ((e = cudaMemcpyAsync(static_cast<char*>(dst) + done, r->buf[b], n, cudaMemcpyHostToDevice, r->stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(r->ev[b], r->stream)) != cudaSuccess) return e;
+        done += n;
+    }
+    return cudaStreamSynchronize(r->stream);
+}
+
+cudaError_t hc_copy_d2h(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < kDirectBelow || is_pinned(dst)) return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ring* r;
+    if ((e = ring_for(dev, &r)) != cudaSuccess) return e;
+    const int T = host_threads();
+    const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+    size_t issued = 0, drained = 0;
+    while (drained < nchunks) {
+        while (issued < nchunks && issued < drained + kRing) {   // keep the ring full of DMAs
+            const int b = (int)(issued % kRing);
+            const size_t o = issued * kChunk, n = bytes - o < kChunk ? bytes - o : kChunk;
+            if ((e = cudaMemcpyAsync(r->buf[b], static_cast<const char*>(src) + o, n, cudaMemcpyDeviceToHost, r->stream)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(r->ev[b], r->stream)) != cudaSuccess) return e;
+            issued++;
+        }
+        const int b = (int)(drained % kRing);
+        const size_t o = drained * kChunk, n = bytes - o < kChunk ? bytes - o : kChunk;
+        if ((e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;
+        par_memcpy(static_cast<char*>(dst) + o, r->buf[b], n, T);
+        drained++;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t hc_scratch_alloc(void** p, size_t bytes) {
+    static std::mutex mu;
+    static bool tuned[16] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!tuned[dev & 15]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = 16ull << 30;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            tuned[dev & 15] = true;
+        }
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 1, 0);
+}
+
+void hc_scratch_free(void* p) {
+    if (p) cudaFreeAsync(p, 0);
+}

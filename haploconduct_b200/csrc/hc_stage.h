@@ -1,0 +1,21 @@
+// hc_stage.h -- host<->device copies of large PAGEABLE buffers and stream-ordered device scratch for the
+// host-buffer entry points (hc_fno1/3, hc_dedup_edges, hc_store_create*).  cudaMemcpy on pageable memory moves
+// ~10 GB/s (one driver thread staging through one pinned buffer); the callers of the reference-facing ABI hold
+// std::vector / numpy memory, so the library stages itself: several host threads copy into a ring of pinned
+// buffers while the copy engine drains the previous one.  Pinned or registered buffers go straight to cudaMemcpy.
+#ifndef HC_STAGE_H_
+#define HC_STAGE_H_
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+// Synchronous like cudaMemcpy: ordered after all earlier work of the device, complete on return.
+cudaError_t hc_copy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+cudaError_t hc_copy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+
+// Device scratch from the device's default memory pool, ordered on the legacy default stream (the stream the
+// host-buffer entry points launch on); freed memory stays in the pool (up to 16 GB), so that a call does not pay
+// cudaMalloc / cudaFree for each of its dozen temporaries.
+cudaError_t hc_scratch_alloc(void** p, size_t bytes);
+void hc_scratch_free(void* p);
+
+#endif
