@@ -7,8 +7,9 @@ per step ("weak" scaling: N GPUs score N shards; N = 8 is the whole list).
 
   value     candidates/s with the candidate records already resident in HBM (CUDA events on the
             launching stream, barrier + synchronize on both sides, max over ranks)
-  e2e       the same step through hc_score_batch() on HOST buffers: pinned host candidates -> device,
-            kernels, accepted edges + non-edge indices -> host, inside the timed region
+  e2e       the same step through hc_score_batch_runs() on HOST buffers: pinned host candidates (run-encoded 8-byte
+            records; --e2e-records short|compact for the 12- / 16-byte ones) -> device, kernels, accepted edges +
+            non-edge indices -> host, inside the timed region
   roofline  hc_score_kernel: algorithmic bytes per launch / its CUDA-event duration vs the measured
             HBM copy bandwidth of MEASURED_PEAKS.json
   cpu_baseline  the UNMODIFIED reference's scoring region (oracle/_ref/ref_driver --time-scoring,
@@ -191,8 +192,9 @@ def main() -> None:
     ap.add_argument("--binned-qualities", action="store_true",
                     help="diagnostic workload: qualities quantised to the four bins of current Illumina instruments")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-records", default="short", choices=["short", "compact"],
-                    help="host record of the e2e leg: 12-byte hc_candidate_short (reads < 16384 bases) or 16-byte hc_candidate_compact")
+    ap.add_argument("--e2e-records", default="runs", choices=["runs", "short", "compact"],
+                    help="host record of the e2e leg: run-encoded 8-byte hc_candidate_entry, 12-byte hc_candidate_short (both: reads "
+                         "< 16384 bases) or 16-byte hc_candidate_compact")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--exact-edge-scores", action="store_true",
                     help="HC_FLAG_EXACT_EDGE_SCORES: re-sum every accepted edge in the reference's order (diagnostic)")
@@ -310,11 +312,33 @@ def main() -> None:
         # position is below 2^14, else the 16-byte compact record (idx1, idx2, pos1|ori|ord, pos2)
         r32 = rec.view(torch.int32).reshape(-1, 8)
         ordc = torch.where(((r32[:, 6] >> 16) & 0xff) == ord("1"), 1, 2)
-        short = args.e2e_records == "short" and args.read_len < (1 << 14)
-        rec_bytes = 12 if short else 16
+        short = args.e2e_records in ("short", "runs") and args.read_len < (1 << 14)
+        use_runs = short and args.e2e_records == "runs"
+        rec_bytes = 8 if use_runs else (12 if short else 16)
         cc = torch.empty((n, rec_bytes // 4), dtype=torch.int32, device=dev)
-        cc[:, 0] = r32[:, 0]; cc[:, 1] = r32[:, 1]
-        if short:
+        run_bytes = 0
+        if use_runs:
+            # run-encoded 8-byte records (hc_score_batch_runs): the list is sorted by (min id, max id), so the candidates of
+            # one read-pair form a run; the run holds that read, the record the other one (+ bit 31 when the anchor is ID2)
+            i1, i2 = r32[:, 0], r32[:, 1]
+            key = torch.minimum(i1, i2)
+            first = torch.ones(n, dtype=torch.bool, device=dev)
+            first[1:] = key[1:] != key[:-1]
+            cut = torch.nonzero(first).flatten()
+            h_anchor = torch.empty(len(cut), dtype=torch.int32, pin_memory=True)
+            h_anchor.copy_(key[cut])
+            h_start = torch.empty(len(cut) + 1, dtype=torch.int64, pin_memory=True)
+            h_start[:-1].copy_(cut)
+            h_start[-1] = n
+            cc[:, 0] = torch.where(i1 == key, i2, i1 | (-(1 << 31)))
+            cc[:, 1] = r32[:, 2] | (r32[:, 3] << 14) | (3 << 28) | (ordc << 30).to(torch.int32)
+            run_bytes = len(cut) * 4 + (len(cut) + 1) * 4      # what the library sends per step: anchors + relative starts
+            del i1, i2, key, first, cut
+        else:
+            cc[:, 0] = r32[:, 0]; cc[:, 1] = r32[:, 1]
+        if use_runs:
+            pass
+        elif short:
             cc[:, 2] = r32[:, 2] | (r32[:, 3] << 14) | (3 << 28) | (ordc << 30).to(torch.int32)   # POS1 | POS2 | ORI '+','+' | ORD
         else:
             cc[:, 3] = r32[:, 3]
@@ -330,6 +354,13 @@ def main() -> None:
         c_ne, c_nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
 
         def e2e_step():
+            if use_runs:
+                rc = L.hc_score_batch_runs(store.handle, params.ctypes.data, h_anchor.data_ptr(), h_start.data_ptr(), h_anchor.shape[0],
+                                           h_cand.data_ptr(), n, None, h_edges.data_ptr(), h_edges.shape[0], ctypes.byref(c_ne),
+                                           h_nonedge.data_ptr(), h_nonedge.shape[0], ctypes.byref(c_nn), None)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+                return
             fn = L.hc_score_batch_short if short else L.hc_score_batch_compact
             rc = fn(store.handle, params.ctypes.data, h_cand.data_ptr(), n, None, h_edges.data_ptr(),
                                   h_edges.shape[0], ctypes.byref(c_ne), h_nonedge.data_ptr(), h_nonedge.shape[0],
@@ -346,7 +377,8 @@ def main() -> None:
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert c_ne.value == ne and c_nn.value == nn
-        e2e = (e2e_ms, n * rec_bytes, ne * 48 + nn * 8 + 64, "hc_candidate_short (12 B)" if short else "hc_candidate_compact (16 B)")
+        e2e = (e2e_ms, n * rec_bytes + run_bytes, ne * 48 + nn * 8 + 64,
+               "hc_candidate_entry (8 B, run-encoded)" if use_runs else ("hc_candidate_short (12 B)" if short else "hc_candidate_compact (16 B)"))
 
     ms_step = ms_total / args.steps
     tvals = torch.tensor([ms_step, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("HC_B200_LIB") or os.path.join(HERE, "lib", "libhc_b20
 # every symbol include/hc_b200.h declares
 EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
-    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_device",
+    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
     "hc_store_create_fastq", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
@@ -66,6 +66,8 @@ def lib() -> ctypes.CDLL:
         L.hc_score_batch_compact.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
         L.hc_score_batch_short.restype = i32
         L.hc_score_batch_short.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
+        L.hc_score_batch_runs.restype = i32
+        L.hc_score_batch_runs.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
         L.hc_score_batch_device.restype = i32
         L.hc_score_batch_device.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, u64, vp, u64, vp, vp]
         L.hc_overlap_score.restype = dbl
@@ -191,8 +193,28 @@ class Store:
     def score_batch(self, params: np.ndarray, cands: np.ndarray, per_candidate: bool = True, edges_cap: Optional[int] = None,
                     nonedge_cap: Optional[int] = None, compact: bool = False):
         """hc_score_batch on HOST buffers; compact=True -> hc_score_batch_compact (16-byte records), compact="short" ->
-        hc_score_batch_short (12-byte records).  Returns (edges, nonedge_idx, per_cand or None, stats)."""
+        hc_score_batch_short (12-byte records), compact="runs" -> hc_score_batch_runs (run-encoded 8-byte records).
+        Returns (edges, nonedge_idx, per_cand or None, stats)."""
         L = lib()
+        if compact == "runs":
+            anchor, start, entries = F.run_encode(cands)
+            n = len(entries)
+            ecap = n if edges_cap is None else edges_cap
+            ncap = n if nonedge_cap is None else nonedge_cap
+            edges = np.zeros(max(ecap, 1), dtype=F.EDGE)
+            nonedge = np.zeros(max(ncap, 1), dtype=np.uint64)
+            per = np.zeros(n, dtype=F.RESULT) if per_candidate else None
+            ne, nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
+            stats = np.zeros(1, dtype=F.BATCH_STATS)
+            rc = L.hc_score_batch_runs(self._h, params.ctypes.data, anchor.ctypes.data if n else None, start.ctypes.data, len(anchor),
+                                       entries.ctypes.data if n else None, n, per.ctypes.data if per is not None and n else None,
+                                       edges.ctypes.data, ecap, ctypes.byref(ne), nonedge.ctypes.data, ncap, ctypes.byref(nn),
+                                       stats.ctypes.data)
+            if rc != 0:
+                err = HcError(rc, last_error())
+                err.required = (int(ne.value), int(nn.value))
+                raise err
+            return edges[: ne.value], nonedge[: nn.value], per, stats[0]
         if compact == "short":
             cands = F.short_candidates(cands)
         elif compact:

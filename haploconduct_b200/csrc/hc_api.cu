@@ -65,6 +65,12 @@ struct DevCtx {
     void* d_cand[2] = {nullptr, nullptr};
     uint64_t pc_cap = 0;
     hc_result* d_per_cand[2] = {nullptr, nullptr};
+    // run-encoded candidates (hc_score_batch_runs): per slot the chunk's run anchors + relative run starts
+    // ([anchor x cap][start x (cap + 1)], host copy pinned) and the tile -> run table
+    uint64_t runs_cap = 0, tile_cap = 0;
+    uint32_t* d_runs[2] = {nullptr, nullptr};
+    uint32_t* h_runs[2] = {nullptr, nullptr};
+    uint32_t* d_tile_run[2] = {nullptr, nullptr};
     uint64_t acc_e_cap = 0, acc_n_cap = 0;
     hc_edge* d_acc_edges = nullptr;
     uint64_t* d_acc_nonedge = nullptr;
@@ -107,6 +113,8 @@ void free_ctx(DevCtx& d) {
     cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts); cudaFree(d.counters);
     for (int k = 0; k < 2; k++) {
         cudaFree(d.d_cand[k]); cudaFree(d.d_per_cand[k]);
+        cudaFree(d.d_runs[k]); cudaFree(d.d_tile_run[k]);
+        if (d.h_runs[k]) cudaFreeHost(d.h_runs[k]);
         if (d.ev_in[k]) cudaEventDestroy(d.ev_in[k]);
         if (d.ev_done[k]) cudaEventDestroy(d.ev_done[k]);
         if (d.ev_out[k]) cudaEventDestroy(d.ev_out[k]);
@@ -166,12 +174,20 @@ DevCtx* find_ctx(hc_store* s, int device) {
     return nullptr;
 }
 
+struct RunDev {                 // device-side run arrays of one batch of hc_candidate_entry records
+    const uint32_t* anchor;     // [n_runs]
+    const uint32_t* start;      // [n_runs + 1], relative to the batch
+    uint32_t n_runs;
+    uint32_t* tile_run;         // [ceil(n / 32)] scratch
+};
+
 // Enqueue the whole scoring pipeline for one shard on (d, st).
 int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, const void* d_cand, int compact, uint64_t n,
                   hc_result* d_per_cand, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge, uint64_t nonedge_cap,
                   uint64_t* d_counts, uint64_t cand_offset, unsigned long long* d_run, cudaEvent_t k0, cudaEvent_t k1,
-                  uint32_t* launches) {
+                  uint32_t* launches, const RunDev* runs = nullptr) {
     if (n > 0xffffffffull) return fail(HC_ERR_ARG, "more than 2^32-1 candidates in one device batch");
+    if (compact == 3 && !runs) return fail(HC_ERR_ARG, "run-encoded candidates without run arrays");
     int rc = ensure_tables(s, d, p->mismatch, st);
     if (rc != HC_OK) return rc;
     rc = ensure_workspace(d, n);
@@ -185,6 +201,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     P.fx_table = d.fx_table; P.dbl_table = d.dbl_table; P.ncodes = (uint32_t)s->ncodes; P.has_void = d.has_void ? 1u : 0u;
     P.cand = d_cand; P.cand_compact = (uint32_t)compact; P.run = d_run; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
     P.counters = d.counters;
+    if (runs) { P.run_anchor = runs->anchor; P.run_start = runs->start; P.tile_run = runs->tile_run; }
     P.t_edge = hc_tables_exp_threshold(p->edge_threshold, &mono);
     if (!mono) return fail(HC_ERR_ARG, "host exp() is not monotone around edge_threshold");
     P.t_ov = hc_tables_exp_threshold(p->ov_threshold, &mono);
@@ -210,6 +227,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
         const uint64_t warps_per_block = cfg.threads / 32;
         const uint64_t need_blocks = (ntiles + warps_per_block - 1) / warps_per_block;
         if ((uint64_t)cfg.blocks > need_blocks) cfg.blocks = (int)need_blocks;
+        if (runs) { CU(hc_launch_tile_runs(runs->start, runs->n_runs, runs->tile_run, st)); nl += 1; }
         if (k0) CU(cudaEventRecord(d.ev[4], st));
         CU(hc_launch_score(P, cfg, st));
         if (k0) CU(cudaEventRecord(d.ev[5], st));
@@ -745,14 +763,21 @@ int hc_score_batch_device(hc_store* s, int device, void* stream, const hc_params
 // (stream) and D2H of what chunk k-1 produced (s_out) overlap.  Outputs are compacted on the device
 // behind the outputs of the earlier chunks (running totals stay on the device), so the host sees
 // one ordered list per device.
+struct RunsHost {               // caller's run arrays (hc_score_batch_runs)
+    const uint32_t* anchor;     // [n_runs]
+    const uint64_t* start;      // [n_runs + 1]
+    uint64_t n_runs;
+};
+
 static int score_host(hc_store* s, const hc_params* p, const void* cand, int compact, uint64_t n, hc_result* per_cand,
                       hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
-                      uint64_t* n_nonedges, hc_batch_stats* stats) {
+                      uint64_t* n_nonedges, hc_batch_stats* stats, const RunsHost* runs = nullptr) {
     if (!s || !p || !n_edges || !n_nonedges || (n && !cand)) return fail(HC_ERR_ARG, "hc_score_batch: NULL argument");
     if (stats) memset(stats, 0, sizeof(*stats));
     *n_edges = 0;
     *n_nonedges = 0;
-    const size_t rec = compact == 2 ? sizeof(hc_candidate_short) : (compact ? sizeof(hc_candidate_compact) : sizeof(hc_candidate));
+    const size_t rec = compact == 3 ? sizeof(hc_candidate_entry)
+                                    : (compact == 2 ? sizeof(hc_candidate_short) : (compact ? sizeof(hc_candidate_compact) : sizeof(hc_candidate)));
     const int G = (int)s->devs.size();
     uint64_t chunk = 8ull << 20;   // candidates per pipeline step (measured: 8 M beats 2, 4 and 16 M end to end)
     if (const char* e = getenv("HC_HOST_CHUNK")) { const uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }   // tests
@@ -778,6 +803,13 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
             d.pc_cap = 0;
             for (int k = 0; k < 2; k++) CU(cudaMalloc(&d.d_per_cand[k], cap * sizeof(hc_result)));
             d.pc_cap = cap;
+        }
+        if (runs && cap > d.tile_cap * 32) {
+            const uint64_t tiles = (cap + 31) / 32;
+            for (int k = 0; k < 2; k++) { cudaFree(d.d_tile_run[k]); d.d_tile_run[k] = nullptr; }
+            d.tile_cap = 0;
+            for (int k = 0; k < 2; k++) CU(cudaMalloc(&d.d_tile_run[k], tiles * sizeof(uint32_t)));
+            d.tile_cap = tiles;
         }
         const uint64_t need_e = std::max<uint64_t>(std::min<uint64_t>(m, edges_cap), 1), need_n = std::max<uint64_t>(std::min<uint64_t>(m, nonedge_cap), 1);
         if (need_e > d.acc_e_cap) { cudaFree(d.d_acc_edges); d.d_acc_edges = nullptr; d.acc_e_cap = 0; CU(cudaMalloc(&d.d_acc_edges, need_e * sizeof(hc_edge))); d.acc_e_cap = need_e; }
@@ -829,12 +861,41 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
                 CU(cudaStreamWaitEvent(d.stream, d.ev_out[slot], 0));
             }
             CU(cudaMemcpyAsync(d.d_cand[slot], (const char*)cand + c0 * rec, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
+            RunDev rdv{nullptr, nullptr, 0, nullptr};
+            if (runs) {   // the runs that overlap [c0, c0 + cm): anchors as they are, starts clipped and made relative
+                const uint64_t* st = runs->start;
+                const uint64_t r0 = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, c0) - st) - 1;
+                const uint64_t r1 = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, c0 + cm - 1) - st) - 1;
+                const uint64_t nr = r1 - r0 + 1;
+                if (nr > d.runs_cap) {   // both slots grow together; the other slot's copy-in has long completed (finalize_chunk)
+                    CU(cudaStreamSynchronize(d.s_copy));
+                    CU(cudaStreamSynchronize(d.stream));
+                    const uint64_t want = nr + nr / 4 + 1024;
+                    for (int q = 0; q < 2; q++) {
+                        cudaFree(d.d_runs[q]); d.d_runs[q] = nullptr;
+                        if (d.h_runs[q]) { cudaFreeHost(d.h_runs[q]); d.h_runs[q] = nullptr; }
+                    }
+                    d.runs_cap = 0;
+                    for (int q = 0; q < 2; q++) {
+                        CU(cudaMalloc(&d.d_runs[q], (2 * want + 1) * sizeof(uint32_t)));
+                        CU(cudaMallocHost(&d.h_runs[q], (2 * want + 1) * sizeof(uint32_t)));
+                    }
+                    d.runs_cap = want;
+                }
+                uint32_t* h = d.h_runs[slot];
+                memcpy(h, runs->anchor + r0, nr * sizeof(uint32_t));
+                for (uint64_t j = 0; j < nr; j++) h[nr + j] = (uint32_t)(std::max<uint64_t>(st[r0 + j], c0) - c0);
+                h[2 * nr] = (uint32_t)cm;
+                CU(cudaMemcpyAsync(d.d_runs[slot], h, (2 * nr + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, d.s_copy));
+                rdv.anchor = d.d_runs[slot]; rdv.start = d.d_runs[slot] + nr; rdv.n_runs = (uint32_t)nr; rdv.tile_run = d.d_tile_run[slot];
+            }
             CU(cudaEventRecord(d.ev_in[slot], d.s_copy));
             CU(cudaStreamWaitEvent(d.stream, d.ev_in[slot], 0));
             uint32_t nl = 0;
             int rc = enqueue_batch(s, d, d.stream, p, d.d_cand[slot], compact, cm, per_cand ? d.d_per_cand[slot] : nullptr,
                                    d.d_acc_edges, d.acc_e_cap, d.d_acc_nonedge, d.acc_n_cap, nullptr, c0, d.d_run,
-                                   (stats && k == 0) ? d.ev[0] : nullptr, (stats && k == 0) ? d.ev[1] : nullptr, &nl);
+                                   (stats && k == 0) ? d.ev[0] : nullptr, (stats && k == 0) ? d.ev[1] : nullptr, &nl,
+                                   runs ? &rdv : nullptr);
             if (rc != HC_OK) return rc;
             launches += nl;
             CU(cudaMemcpyAsync(d.h_cnt + slot * HC_CNT_N, d.counters, HC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
@@ -900,6 +961,23 @@ int hc_score_batch_short(hc_store* s, const hc_params* p, const hc_candidate_sho
                          hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
                          uint64_t* n_nonedges, hc_batch_stats* stats) {
     return score_host(s, p, cand, 2, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats);
+}
+
+int hc_score_batch_runs(hc_store* s, const hc_params* p, const uint32_t* run_anchor, const uint64_t* run_start, uint64_t n_runs,
+                        const hc_candidate_entry* entries, uint64_t n, hc_result* per_cand, hc_edge* edges, uint64_t edges_cap,
+                        uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges, hc_batch_stats* stats) {
+    if (n && (!run_anchor || !run_start || n_runs == 0)) return fail(HC_ERR_ARG, "hc_score_batch_runs: NULL run arrays");
+    if (s && s->n_reads > 0x7fffffffull) return fail(HC_ERR_ARG, "hc_score_batch_runs: more than 2^31-1 reads in the store");
+    if (n) {
+        if (run_start[0] != 0 || run_start[n_runs] != n) return fail(HC_ERR_ARG, "hc_score_batch_runs: run_start must begin at 0 and end at n");
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (long long r = 0; r < (long long)n_runs; r++) bad |= (run_start[r] >= run_start[r + 1]);
+        if (bad) return fail(HC_ERR_ARG, "hc_score_batch_runs: run_start must be strictly increasing (no empty runs)");
+    }
+    const RunsHost rh{run_anchor, run_start, n_runs};
+    return score_host(s, p, entries, 3, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats,
+                      n ? &rh : nullptr);
 }
 
 int hc_overlap_score_multi(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,

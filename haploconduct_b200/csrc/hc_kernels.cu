@@ -46,6 +46,22 @@ struct CandSetup {
 
 __device__ __forceinline__ hc_candidate load_candidate(const hc_kparams& P, u64 i) {
     hc_candidate c;
+    if (P.cand_compact == 3u) {   // hc_candidate_entry: 8 bytes, the other read comes from the run the candidate lies in
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(P.cand) + i);
+        uint32_t r = __ldg(P.tile_run + (i >> 5));
+        while ((uint32_t)i >= __ldg(P.run_start + r + 1)) r++;     // runs are rarely shorter than a tile
+        const uint32_t anchor = __ldg(P.run_anchor + r), other = e.x & 0x7fffffffu;
+        const bool anchor_is_2 = (e.x >> 31) != 0u;
+        c.idx1 = anchor_is_2 ? other : anchor;
+        c.idx2 = anchor_is_2 ? anchor : other;
+        const uint32_t w = e.y;
+        c.pos1 = w & 0x3fffu; c.pos2 = (w >> 14) & 0x3fffu;
+        c.len1 = c.len2 = 0; c.perc1 = c.perc2 = 0; c.type1 = c.type2 = 0; c.reserved = 0;
+        c.ori1 = (w >> 28) & 1u; c.ori2 = (w >> 29) & 1u;
+        const uint32_t o = w >> 30;
+        c.ord = o == 1 ? '1' : (o == 2 ? '2' : '-');
+        return c;
+    }
     if (P.cand_compact == 2u) {   // hc_candidate_short: 12 bytes, positions below 2^14
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(P.cand) + 3 * i;
         const uint32_t w = __ldg(sp + 2);
@@ -1022,6 +1038,14 @@ __global__ void __launch_bounds__(256) hc_emit_edges(const hc_kparams P, const u
     }
 }
 
+// tile_run[t] = the run that holds candidate 32 * t; one thread per run writes the tiles that start inside it
+__global__ void hc_tile_runs(const uint32_t* __restrict__ run_start, uint32_t n_runs, uint32_t* __restrict__ tile_run) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += gridDim.x * blockDim.x) {
+        const uint32_t s = run_start[r], e = run_start[r + 1];
+        for (uint32_t t = (s + 31u) >> 5; ((u64)t << 5) < e; t++) tile_run[t] = r;
+    }
+}
+
 __global__ void hc_compact_advance(unsigned long long* run, const unsigned long long* counters) {
     run[0] += counters[HC_CNT_EDGES];
     run[1] += counters[HC_CNT_NONEDGES];
@@ -1056,6 +1080,13 @@ cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaS
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     fn<<<cfg.blocks, cfg.threads, cfg.smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint32_t* tile_run, cudaStream_t st) {
+    if (n_runs == 0) return cudaSuccess;
+    const unsigned blocks = (n_runs + 255u) / 256u;
+    hc_tile_runs<<<blocks < 148u * 8u ? blocks : 148u * 8u, 256, 0, st>>>(run_start, n_runs, tile_run);
     return cudaGetLastError();
 }
 

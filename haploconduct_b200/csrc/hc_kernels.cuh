@@ -52,8 +52,11 @@ struct hc_kparams {
     uint32_t ncodes;
     uint32_t has_void;
     // batch
-    const void* cand;           // hc_candidate[n] (cand_compact == 0), hc_candidate_compact[n] (1) or hc_candidate_short[n] (2)
-    uint32_t cand_compact;
+    const void* cand;           // hc_candidate[n] (cand_compact == 0), hc_candidate_compact[n] (1), hc_candidate_short[n] (2)
+    uint32_t cand_compact;      // or hc_candidate_entry[n] (3) with the three run arrays below
+    const uint32_t* run_anchor; // [n_runs] read shared by the candidates of a run
+    const uint32_t* run_start;  // [n_runs + 1] first candidate of each run within this batch, run_start[n_runs] = n
+    const uint32_t* tile_run;   // [ceil(n / 32)] run that holds candidate 32 * t (hc_tile_runs)
     const unsigned long long* run;   // nullable: running {edges, non-edges} totals of earlier chunks = output base offsets
     uint64_t n;
     hc_tmp32* tmp;
@@ -96,6 +99,7 @@ struct hc_launch_cfg {
 // host-callable launchers (hc_kernels.cu)
 cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaStream_t st);
 cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st);
+cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint32_t* tile_run, cudaStream_t st);
 cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge,
                               uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, unsigned long long* d_run,
                               cudaStream_t st);

@@ -53,6 +53,38 @@ def short_candidates(c: np.ndarray) -> np.ndarray:
     return out
 
 
+CANDIDATE_ENTRY = np.dtype([("other", "<u4"), ("pos", "<u4")])
+assert CANDIDATE_ENTRY.itemsize == 8
+
+
+def run_encode(c: np.ndarray):
+    """hc_candidate -> (run_anchor uint32[n_runs], run_start uint64[n_runs + 1], hc_candidate_entry[n]) for
+    hc_score_batch_runs.  A run is a stretch of consecutive candidates that share one read; two vectorised cuts are
+    tried (runs of equal ID1, runs of equal min(ID1, ID2) -- the sort key of scripts/sfo2overlaps.py:52) and the one with
+    fewer runs is kept.  The candidate order is not changed."""
+    n = len(c)
+    if n == 0:
+        return np.zeros(0, np.uint32), np.zeros(1, np.uint64), np.zeros(0, CANDIDATE_ENTRY)
+    sc = short_candidates(c)
+    i1, i2 = sc["idx1"], sc["idx2"]
+    if int(max(i1.max(), i2.max())) >= (1 << 31):
+        raise ValueError("read indices do not fit the 8-byte candidate record")
+    best = None
+    for key in (i1, np.minimum(i1, i2)):
+        cut = np.flatnonzero(np.concatenate(([True], key[1:] != key[:-1])))
+        if best is None or len(cut) < len(best[0]):
+            best = (cut, key)
+    cut, key = best
+    start = np.concatenate((cut, [n])).astype(np.uint64)
+    anchor = key[cut].astype(np.uint32)
+    per_cand_anchor = key
+    out = np.zeros(n, dtype=CANDIDATE_ENTRY)
+    is1 = i1 == per_cand_anchor                      # the anchor is ID1 -> store ID2, flag 0
+    out["other"] = np.where(is1, i2, i1 | np.uint32(1 << 31))
+    out["pos"] = sc["pos"]
+    return anchor, start, out
+
+
 PARAMS = np.dtype(
     [
         ("edge_threshold", "<f8"), ("ov_threshold", "<f8"), ("merge_contigs", "<f8"), ("mismatch", "<f8"),

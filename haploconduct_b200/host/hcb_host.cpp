@@ -411,7 +411,37 @@ void EdgeCalculator::process_overlaps(std::vector<Overlap>& batch) {
     const double ts0 = wall_s();
     bool fits = fastq_->max_read_len < (1u << 14);
     for (size_t i = 0; i < n && fits; i++) fits = cand[i].pos1 < (1u << 14) && cand[i].pos2 < (1u << 14);
-    if (fits) {   // 12-byte records: the device reads nothing else of a candidate, and the copy in is what bounds the call
+    if (fits && fastq_->m_read_vec.size() < (1ull << 31)) {
+        // run-encoded 8-byte records: the copy in is what bounds the call, and the overlaps of one read follow each other
+        // in the file.  Greedy cut: a run grows while the next candidate still contains one of the reads every
+        // candidate of the run has contained so far.
+        std::vector<hc_candidate_entry> en(n);
+        std::vector<uint32_t> anchor;
+        std::vector<uint64_t> start;
+        for (size_t i = 0; i < n;) {
+            const uint32_t a = cand[i].idx1, b = cand[i].idx2;
+            bool a_ok = true, b_ok = true;
+            size_t j = i + 1;
+            for (; j < n; j++) {
+                const bool ha = a_ok && (cand[j].idx1 == a || cand[j].idx2 == a), hb = b_ok && (cand[j].idx1 == b || cand[j].idx2 == b);
+                if (!ha && !hb) break;
+                a_ok = ha; b_ok = hb;
+            }
+            const uint32_t anc = a_ok ? a : b;
+            start.push_back(i);
+            anchor.push_back(anc);
+            for (size_t k = i; k < j; k++) {
+                const hc_candidate& c = cand[k];
+                const uint32_t o = c.ord == '1' ? 1u : (c.ord == '2' ? 2u : 0u);
+                en[k].other = c.idx1 == anc ? c.idx2 : (c.idx1 | 0x80000000u);
+                en[k].pos = c.pos1 | (c.pos2 << 14) | ((uint32_t)(c.ori1 != 0) << 28) | ((uint32_t)(c.ori2 != 0) << 29) | (o << 30);
+            }
+            i = j;
+        }
+        start.push_back(n);
+        rc = hc_score_batch_runs(fastq_->device_store(), &p, anchor.data(), start.data(), anchor.size(), en.data(), n, nullptr, edges, n,
+                                 &ne, nonedge, n, &nn, &st);
+    } else if (fits) {   // 12-byte records
         std::vector<hc_candidate_short> sc(n);
         for (size_t i = 0; i < n; i++) {
             const hc_candidate& c = cand[i];

@@ -209,6 +209,25 @@ int hc_score_batch_short(hc_store* s, const hc_params* p,
                          uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
                          hc_batch_stats* stats /* nullable */);
 
+/* hc_score_batch on run-encoded 8-byte records.  An overlaps file lists the overlaps of one read one after the other
+ * (scripts/sfo2overlaps.py:52 sorts its lines by read; rust-overlaps emits them per read), so consecutive candidates
+ * share a read: a RUN is a stretch of consecutive candidates that all contain the read run_anchor[r], as ID1 or as ID2,
+ * and each candidate then only names the other read.  Any list can be cut into runs (a run may have length 1; the
+ * order of the candidates is not changed).  run_start has n_runs + 1 entries, run_start[0] = 0, run_start[n_runs] = n,
+ * strictly increasing.  Needs a store of fewer than 2^31 reads whose reads are shorter than 16384 bases; two thirds of
+ * the host->device traffic of hc_score_batch_short.  Results are those of hc_score_batch on the decoded records. */
+typedef struct {
+    uint32_t other;          /* bits 0-30: dense index of the read that is not the run's anchor; bit 31: the anchor is ID2 */
+    uint32_t pos;            /* as hc_candidate_short.pos */
+} hc_candidate_entry;        /* 8 bytes */
+int hc_score_batch_runs(hc_store* s, const hc_params* p,
+                        const uint32_t* run_anchor, const uint64_t* run_start, uint64_t n_runs,
+                        const hc_candidate_entry* entries, uint64_t n,
+                        hc_result* per_cand,
+                        hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges,
+                        uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
+                        hc_batch_stats* stats /* nullable */);
+
 /* Same, but every buffer is DEVICE memory on device `device` (one of the store's devices) and the
  * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream).
  * d_counts receives {n_edges, n_nonedges, n_exact, 0} as uint64_t[4].  Asynchronous unless stats != NULL.

@@ -276,6 +276,59 @@ def test_chunked_pipeline_and_compact_records(built_lib, monkeypatch, chunk):
     assert np.array_equal(per1["cls"], ref["cls"])
 
 
+@pytest.mark.parametrize("chunk", ["33", "777", "100000000"])
+@pytest.mark.parametrize("order", ["file", "by_read", "by_min_id"])
+def test_run_encoded_records(built_lib, monkeypatch, chunk, order):
+    """hc_score_batch_runs (8-byte records, the shared read of a run held once): same edges, non-edge indices and
+    per-candidate results as the 12-byte records, whatever the order of the list (long runs when it is sorted by
+    read, runs of length 1 otherwise) and wherever the pipeline cuts it."""
+    g = load_golden("synth_all_types")
+    cands = np.tile(g.scored(), 3)
+    cands = cands[(cands["pos1"] < (1 << 14)) & (cands["pos2"] < (1 << 14))]
+    if order == "by_read":
+        cands = cands[np.argsort(cands["idx1"], kind="stable")]
+    elif order == "by_min_id":
+        lo, hi = np.minimum(cands["idx1"], cands["idx2"]), np.maximum(cands["idx1"], cands["idx2"])
+        cands = cands[np.lexsort((hi, lo))]
+    anchor, start, entries = F.run_encode(cands)
+    assert start[0] == 0 and start[-1] == len(cands) and (np.diff(start.astype(np.int64)) > 0).all()
+    if order != "file":
+        assert len(anchor) < len(cands) // 2
+    other = entries["other"] & 0x7fffffff
+    flip = (entries["other"] >> 31).astype(bool)
+    per_anchor = np.repeat(anchor, np.diff(start.astype(np.int64)))
+    assert np.array_equal(np.where(flip, other, per_anchor), cands["idx1"]) and np.array_equal(np.where(flip, per_anchor, other), cands["idx2"])
+    p = g.params()
+    with capi.Store(g.rs) as st:
+        monkeypatch.setenv("HC_HOST_CHUNK", "100000000")
+        e0, n0, per0, s0 = st.score_batch(p, cands, compact="short")
+        monkeypatch.setenv("HC_HOST_CHUNK", chunk)
+        e1, n1, per1, s1 = st.score_batch(p, cands, compact="runs")
+        e2, n2, _, _ = st.score_batch(p, cands, compact="runs", per_candidate=False)
+        ez, nz, _, _ = st.score_batch(p, cands[:0], compact="runs")
+    assert e1.tobytes() == e0.tobytes() and np.array_equal(n1, n0) and per1.tobytes() == per0.tobytes()
+    assert e2.tobytes() == e0.tobytes() and np.array_equal(n2, n0)
+    assert int(s1["n_positions"]) == int(s0["n_positions"]) and len(ez) == 0 and len(nz) == 0
+
+
+def test_run_encoded_records_bad_runs(built_lib):
+    g = load_golden("synth_all_types")
+    cands = g.scored()[:50]
+    cands = cands[(cands["pos1"] < (1 << 14)) & (cands["pos2"] < (1 << 14))]
+    anchor, start, entries = F.run_encode(cands)
+    L = capi.lib()
+    import ctypes
+    with capi.Store(g.rs) as st:
+        ne, nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        edges = np.zeros(len(cands), dtype=F.EDGE); nonedge = np.zeros(len(cands), dtype=np.uint64)
+        p = g.params()
+        for bad in (start[::-1].copy(), np.concatenate((start[:1], start[:-1])), start + 1):
+            rc = L.hc_score_batch_runs(st._h, p.ctypes.data, anchor.ctypes.data, bad.ctypes.data, len(anchor), entries.ctypes.data,
+                                       len(entries), None, edges.ctypes.data, len(edges), ctypes.byref(ne), nonedge.ctypes.data,
+                                       len(nonedge), ctypes.byref(nn), None)
+            assert rc == -1 and "run_start" in capi.last_error()
+
+
 def test_overlap_score_multi_self_overlap_scan(built_lib):
     """The scan of SRBuilder::merge_self_overlap (src/SRBuilder.cpp:880-888): seq2 slid over seq1 from
     pos = len1-15 downwards; first position whose score exceeds 0.99 -- same position as the oracle's loop."""

@@ -49,6 +49,9 @@ def one(seed: int) -> str:
             fits = (cands["pos1"] < (1 << 14)) & (cands["pos2"] < (1 << 14))
             e3, n3, per3, _ = st.score_batch(p, cands[fits], compact="short")
             assert per3.tobytes() == per[fits].tobytes()
+            if ss.rs.n_reads < (1 << 31):
+                e4, n4, per4, _ = st.score_batch(p, cands[fits], compact="runs")
+                assert per4.tobytes() == per3.tobytes() and e4.tobytes() == e3.tobytes() and np.array_equal(n4, n3)
             px = p.copy()
             px["flags"] = F.FLAG_EXACT_EDGE_SCORES
             ex, nx, perx, _ = st.score_batch(px, cands)
