@@ -192,6 +192,13 @@ def main() -> None:
     ap.add_argument("--binned-qualities", action="store_true",
                     help="diagnostic workload: qualities quantised to the four bins of current Illumina instruments")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-no-output", action="store_true",
+                    help="diagnostic: the e2e leg with zero output capacity (nothing is copied back; INVALID as an e2e number)")
+    ap.add_argument("--dma-load", action="store_true",
+                    help="diagnostic: run the device-resident steps while both copy engines are busy (1 GB in, 0.8 GB out per step)")
+    ap.add_argument("--device-chunk", type=int, default=0,
+                    help="diagnostic: split the device-resident step into launches of this many candidates (what the host pipeline's "
+                         "steps cost without any copies)")
     ap.add_argument("--e2e-records", default="runs", choices=["runs", "short", "compact"],
                     help="host record of the e2e leg: run-encoded 8-byte hc_candidate_entry, 12-byte hc_candidate_short (both: reads "
                          "< 16384 bases) or 16-byte hc_candidate_compact")
@@ -271,6 +278,12 @@ def main() -> None:
     stream = torch.cuda.current_stream(dev)
 
     def step(want_stats=False):
+        if args.device_chunk and not want_stats:   # diagnostic: the same work as launches of `device_chunk` candidates
+            for i0 in range(0, n, args.device_chunk):
+                m = min(args.device_chunk, n - i0)
+                store.score_batch_device(local_rank, stream.cuda_stream, params, rec[i0:i0 + m].data_ptr(), m, 0, d_edges.data_ptr(), n,
+                                         d_nonedge.data_ptr(), n, d_counts.data_ptr(), False)
+            return None
         return store.score_batch_device(local_rank, stream.cuda_stream, params, rec.data_ptr(), n, 0, d_edges.data_ptr(), n,
                                         d_nonedge.data_ptr(), n, d_counts.data_ptr(), want_stats)
 
@@ -288,6 +301,22 @@ def main() -> None:
         time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.dma_load:   # diagnostic: the device step while the copy engines move what an e2e step moves (1 GB in, 0.6 GB out)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        h_in = torch.empty(1 << 28, dtype=torch.int32, pin_memory=True); d_in = torch.empty(1 << 28, dtype=torch.int32, device=dev)
+        h_out = torch.empty(3 << 26, dtype=torch.int32, pin_memory=True); d_out = torch.empty(3 << 26, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        ci0, ci1, co0, co1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        with torch.cuda.stream(s_in):
+            ci0.record(s_in)
+            for _ in range(args.steps):
+                d_in.copy_(h_in, non_blocking=True)
+            ci1.record(s_in)
+        with torch.cuda.stream(s_out):
+            co0.record(s_out)
+            for _ in range(args.steps):
+                h_out.copy_(d_out, non_blocking=True)
+            co1.record(s_out)
     tw0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
@@ -296,6 +325,9 @@ def main() -> None:
     barrier()
     tw1 = time.time()
     ms_total = e0.elapsed_time(e1)
+    if args.dma_load:
+        log("[dma-load] host->device %.1f GB/s, device->host %.1f GB/s while the kernels ran" %
+            (args.steps * h_in.numel() * 4 / ci0.elapsed_time(ci1) / 1e6, args.steps * h_out.numel() * 4 / co0.elapsed_time(co1) / 1e6))
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     # dominant-kernel duration, measured live with CUDA events around hc_score_kernel on its stream
     kms, stats = [], None
@@ -355,10 +387,11 @@ def main() -> None:
 
         def e2e_step():
             if use_runs:
+                ecap, ncap = (0, 0) if args.e2e_no_output else (h_edges.shape[0], h_nonedge.shape[0])
                 rc = L.hc_score_batch_runs(store.handle, params.ctypes.data, h_anchor.data_ptr(), h_start.data_ptr(), h_anchor.shape[0],
-                                           h_cand.data_ptr(), n, None, h_edges.data_ptr(), h_edges.shape[0], ctypes.byref(c_ne),
-                                           h_nonedge.data_ptr(), h_nonedge.shape[0], ctypes.byref(c_nn), None)
-                if rc != 0:
+                                           h_cand.data_ptr(), n, None, h_edges.data_ptr(), ecap, ctypes.byref(c_ne),
+                                           h_nonedge.data_ptr(), ncap, ctypes.byref(c_nn), None)
+                if rc != 0 and not (args.e2e_no_output and rc == -5):
                     raise RuntimeError(capi.last_error())
                 return
             fn = L.hc_score_batch_short if short else L.hc_score_batch_compact

@@ -65,6 +65,13 @@ struct DevCtx {
     void* d_cand[2] = {nullptr, nullptr};
     uint64_t pc_cap = 0;
     hc_result* d_per_cand[2] = {nullptr, nullptr};
+    // whole-shard mode: the shard's records in one device buffer, copied in step by step ahead of the kernels
+    size_t whole_cap = 0;                  // bytes
+    unsigned char* d_whole = nullptr;
+    std::vector<cudaEvent_t> ev_step;      // one "copied in" event per pipeline step
+    uint64_t runs_all_cap = 0;             // 32-bit words: every step's [anchors][starts] one after the other
+    uint32_t* d_runs_all = nullptr;
+    uint32_t* h_runs_all = nullptr;        // pinned
     // run-encoded candidates (hc_score_batch_runs): per slot the chunk's run anchors + relative run starts
     // ([anchor x cap][start x (cap + 1)], host copy pinned) and the tile -> run table
     uint64_t runs_cap = 0, tile_cap = 0;
@@ -120,6 +127,9 @@ void free_ctx(DevCtx& d) {
         if (d.ev_out[k]) cudaEventDestroy(d.ev_out[k]);
     }
     cudaFree(d.d_acc_edges); cudaFree(d.d_acc_nonedge); cudaFree(d.d_run); cudaFree(d.d_counts);
+    cudaFree(d.d_whole); cudaFree(d.d_runs_all);
+    if (d.h_runs_all) cudaFreeHost(d.h_runs_all);
+    for (cudaEvent_t e : d.ev_step) cudaEventDestroy(e);
     if (d.h_cnt) cudaFreeHost(d.h_cnt);
     for (int k = 0; k < 6; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -779,10 +789,36 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
     const size_t rec = compact == 3 ? sizeof(hc_candidate_entry)
                                     : (compact == 2 ? sizeof(hc_candidate_short) : (compact ? sizeof(hc_candidate_compact) : sizeof(hc_candidate)));
     const int G = (int)s->devs.size();
-    uint64_t chunk = 8ull << 20;   // candidates per pipeline step (measured: 8 M beats 2, 4 and 16 M end to end)
+    uint64_t chunk = 0;            // candidates per pipeline step; 0 = the tapered default schedule
     if (const char* e = getenv("HC_HOST_CHUNK")) { const uint64_t v = strtoull(e, nullptr, 10); if (v) chunk = v; }   // tests
+    size_t whole_max = (size_t)2 << 30;   // shards up to this many bytes of records are copied in ahead of the kernels
+    if (const char* e = getenv("HC_HOST_WHOLE_MAX")) whole_max = (size_t)strtoull(e, nullptr, 10);                   // tests
     std::vector<uint64_t> lo(G + 1);
     for (int g = 0; g <= G; g++) lo[g] = n * (uint64_t)g / (uint64_t)G;   // contiguous index ranges
+    // Pipeline steps of device g: [cs[g][k], cs[g][k+1]).  Whole-shard mode (the shard's records fit `whole_max`): all
+    // copies in are issued up front into one device buffer and run ahead of the kernels, so the steps can start small
+    // (the first kernel waits for 1 M candidates, not 8 M), grow to 16 M (fewer launches) and end small (little left to
+    // copy out after the last kernel).  Otherwise: two slots, the copy in of step k+1 behind the kernels of step k-1,
+    // uniform steps of 8 M (measured: beats 2, 4 and 16 M in that mode).
+    std::vector<std::vector<uint64_t>> cs(G);
+    std::vector<char> whole(G, 0);
+    for (int g = 0; g < G; g++) {
+        const uint64_t m = lo[g + 1] - lo[g];
+        whole[g] = m > 0 && m * rec <= whole_max;
+        std::vector<uint64_t>& c = cs[g];
+        c.push_back(lo[g]);
+        const uint64_t big = 16ull << 20, small = 1ull << 20;
+        if (chunk || !whole[g] || m <= 2 * small) {
+            const uint64_t step = chunk ? chunk : (8ull << 20);
+            for (uint64_t o = step; o < m; o += step) c.push_back(lo[g] + o);
+        } else {
+            uint64_t done = 0, sz = small;
+            while (sz < big && m - done > 4 * sz) { done += sz; c.push_back(lo[g] + done); sz *= 2; }          // 1, 2, 4, 8 M
+            while (m - done > 2 * big) { done += big; c.push_back(lo[g] + done); }                            // 16 M ...
+            while (m - done > 2 * small) { done += (m - done + 1) / 2; c.push_back(lo[g] + done); }           // halves
+        }
+        if (m > 0) c.push_back(lo[g + 1]);
+    }
     uint32_t launches = 0;
     std::vector<uint64_t> dev_e(G, 0), dev_n(G, 0);
     int result = HC_OK;
@@ -790,9 +826,21 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
     for (int g = 0; g < G; g++) {
         DevCtx& d = s->devs[g];
         const uint64_t m = lo[g + 1] - lo[g];
-        const uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(m, 1), chunk);
+        uint64_t cap = 1;
+        for (size_t k = 0; k + 1 < cs[g].size(); k++) cap = std::max<uint64_t>(cap, cs[g][k + 1] - cs[g][k]);
         CU(cudaSetDevice(d.device));
-        if (cap > d.slot_cap) {
+        if (whole[g]) {
+            if (m * rec > d.whole_cap) {
+                cudaFree(d.d_whole); d.d_whole = nullptr; d.whole_cap = 0;
+                CU(cudaMalloc(&d.d_whole, m * rec));
+                d.whole_cap = m * rec;
+            }
+            while (d.ev_step.size() + 1 < cs[g].size()) {
+                cudaEvent_t ev;
+                CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                d.ev_step.push_back(ev);
+            }
+        } else if (cap > d.slot_cap) {
             for (int k = 0; k < 2; k++) { cudaFree(d.d_cand[k]); d.d_cand[k] = nullptr; }
             d.slot_cap = 0;
             for (int k = 0; k < 2; k++) CU(cudaMalloc(&d.d_cand[k], cap * sizeof(hc_candidate)));
@@ -817,14 +865,59 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         CU(cudaMemsetAsync(d.d_run, 0, 2 * sizeof(unsigned long long), d.stream));
         CU(cudaEventRecord(d.ev[2], d.stream));
     }
+    // ---- whole-shard mode: the copy in of step k (and its run arrays) is queued a few steps ahead of its kernels
+    std::vector<std::vector<uint64_t>> run_off(G);    // per issued step: offset of its [anchors][starts] in d_runs_all (words), n_runs
+    std::vector<uint64_t> run_words(G, 0);
+    std::vector<size_t> copied(G, 0);
+    for (int g = 0; g < G; g++) {
+        if (!whole[g] || !runs) continue;
+        DevCtx& d = s->devs[g];
+        CU(cudaSetDevice(d.device));
+        const uint64_t* st = runs->start;
+        const size_t nsteps = cs[g].size() - 1;
+        const uint64_t ra = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, lo[g]) - st) - 1;
+        const uint64_t rb = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, lo[g + 1] - 1) - st) - 1;
+        const uint64_t words = 2 * (rb - ra + 1 + nsteps) + nsteps;      // every step boundary may cut one run in two
+        if (words > d.runs_all_cap) {
+            cudaFree(d.d_runs_all); d.d_runs_all = nullptr;
+            if (d.h_runs_all) { cudaFreeHost(d.h_runs_all); d.h_runs_all = nullptr; }
+            d.runs_all_cap = 0;
+            const uint64_t want = words + words / 8 + 1024;
+            CU(cudaMalloc(&d.d_runs_all, want * sizeof(uint32_t)));
+            CU(cudaMallocHost(&d.h_runs_all, want * sizeof(uint32_t)));
+            d.runs_all_cap = want;
+        }
+    }
+    auto issue_copy = [&](int g, size_t k) -> int {   // the current device is d.device
+        DevCtx& d = s->devs[g];
+        const uint64_t c0 = cs[g][k], cm = cs[g][k + 1] - c0;
+        if (runs) {   // the runs that overlap [c0, c0 + cm): anchors as they are, starts clipped and made relative
+            const uint64_t* st = runs->start;
+            const uint64_t r0 = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, c0) - st) - 1;
+            const uint64_t nr = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, c0 + cm - 1) - st) - r0;
+            const uint64_t o = run_words[g];
+            uint32_t* h = d.h_runs_all + o;
+            memcpy(h, runs->anchor + r0, nr * sizeof(uint32_t));
+            for (uint64_t j = 0; j < nr; j++) h[nr + j] = (uint32_t)(std::max<uint64_t>(st[r0 + j], c0) - c0);
+            h[2 * nr] = (uint32_t)cm;
+            run_off[g].push_back(o);
+            run_off[g].push_back(nr);
+            run_words[g] += 2 * nr + 1;
+            CU(cudaMemcpyAsync(d.d_runs_all + o, h, (2 * nr + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, d.s_copy));
+        }
+        CU(cudaMemcpyAsync(d.d_whole + (c0 - lo[g]) * rec, (const char*)cand + c0 * rec, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
+        CU(cudaEventRecord(d.ev_step[k], d.s_copy));
+        return HC_OK;
+    };
+    const size_t copy_ahead = 3;
     // ---- chunk loop, all devices interleaved
     uint64_t max_chunks = 0;
-    for (int g = 0; g < G; g++) max_chunks = std::max<uint64_t>(max_chunks, (lo[g + 1] - lo[g] + chunk - 1) / chunk);
+    for (int g = 0; g < G; g++) max_chunks = std::max<uint64_t>(max_chunks, cs[g].empty() ? 0 : cs[g].size() - 1);
     std::vector<uint64_t> out_e(G, 0), out_n(G, 0);   // already copied out (G == 1 streams results out while computing)
     auto finalize_chunk = [&](int g, uint64_t k) -> int {   // chunk k of device g has been enqueued; wait for it, account, copy out
         DevCtx& d = s->devs[g];
         const int slot = (int)(k & 1);
-        const uint64_t c0 = lo[g] + k * chunk, cm = std::min<uint64_t>(chunk, lo[g + 1] - c0);
+        const uint64_t c0 = cs[g][k], cm = cs[g][k + 1] - c0;
         CU(cudaSetDevice(d.device));
         CU(cudaEventSynchronize(d.ev_done[slot]));
         const unsigned long long* h = d.h_cnt + slot * HC_CNT_N;
@@ -851,17 +944,30 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
     for (uint64_t k = 0; k < max_chunks; k++) {
         for (int g = 0; g < G; g++) {
             DevCtx& d = s->devs[g];
-            const uint64_t c0 = lo[g] + k * chunk;
-            if (c0 >= lo[g + 1]) continue;
-            const uint64_t cm = std::min<uint64_t>(chunk, lo[g + 1] - c0);
+            if (k + 1 >= cs[g].size()) continue;
+            const uint64_t c0 = cs[g][k], cm = cs[g][k + 1] - c0;
             const int slot = (int)(k & 1);
             CU(cudaSetDevice(d.device));
             if (k >= 2) {   // the slot's previous user (chunk k-2) must have been computed and copied out
-                CU(cudaStreamWaitEvent(d.s_copy, d.ev_done[slot], 0));
+                if (!whole[g]) CU(cudaStreamWaitEvent(d.s_copy, d.ev_done[slot], 0));
                 CU(cudaStreamWaitEvent(d.stream, d.ev_out[slot], 0));
             }
-            CU(cudaMemcpyAsync(d.d_cand[slot], (const char*)cand + c0 * rec, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
             RunDev rdv{nullptr, nullptr, 0, nullptr};
+            const void* d_cand_k = d.d_cand[slot];
+            if (whole[g]) {   // nothing to wait for before queueing copies: the whole shard has its own place on the device
+                while (copied[g] < cs[g].size() - 1 && copied[g] <= k + copy_ahead) {
+                    const int rc = issue_copy(g, copied[g]);
+                    if (rc != HC_OK) return rc;
+                    copied[g]++;
+                }
+                d_cand_k = d.d_whole + (c0 - lo[g]) * rec;
+                if (runs) {
+                    const uint64_t o = run_off[g][2 * k], nr = run_off[g][2 * k + 1];
+                    rdv.anchor = d.d_runs_all + o; rdv.start = d.d_runs_all + o + nr; rdv.n_runs = (uint32_t)nr; rdv.tile_run = d.d_tile_run[slot];
+                }
+                CU(cudaStreamWaitEvent(d.stream, d.ev_step[k], 0));
+            } else {
+            CU(cudaMemcpyAsync(d.d_cand[slot], (const char*)cand + c0 * rec, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
             if (runs) {   // the runs that overlap [c0, c0 + cm): anchors as they are, starts clipped and made relative
                 const uint64_t* st = runs->start;
                 const uint64_t r0 = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, c0) - st) - 1;
@@ -891,8 +997,9 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
             }
             CU(cudaEventRecord(d.ev_in[slot], d.s_copy));
             CU(cudaStreamWaitEvent(d.stream, d.ev_in[slot], 0));
+            }
             uint32_t nl = 0;
-            int rc = enqueue_batch(s, d, d.stream, p, d.d_cand[slot], compact, cm, per_cand ? d.d_per_cand[slot] : nullptr,
+            int rc = enqueue_batch(s, d, d.stream, p, d_cand_k, compact, cm, per_cand ? d.d_per_cand[slot] : nullptr,
                                    d.d_acc_edges, d.acc_e_cap, d.d_acc_nonedge, d.acc_n_cap, nullptr, c0, d.d_run,
                                    (stats && k == 0) ? d.ev[0] : nullptr, (stats && k == 0) ? d.ev[1] : nullptr, &nl,
                                    runs ? &rdv : nullptr);
@@ -903,11 +1010,11 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         }
         if (k >= 1)
             for (int g = 0; g < G; g++)
-                if (lo[g] + (k - 1) * chunk < lo[g + 1]) { int rc = finalize_chunk(g, k - 1); if (rc != HC_OK) result = rc; }
+                if (k < cs[g].size()) { int rc = finalize_chunk(g, k - 1); if (rc != HC_OK) result = rc; }
     }
     if (max_chunks >= 1)
         for (int g = 0; g < G; g++)
-            if (lo[g] + (max_chunks - 1) * chunk < lo[g + 1]) { int rc = finalize_chunk(g, max_chunks - 1); if (rc != HC_OK) result = rc; }
+            if (max_chunks < cs[g].size()) { int rc = finalize_chunk(g, max_chunks - 1); if (rc != HC_OK) result = rc; }
     // ---- gather: rank order = input order
     uint64_t te = 0, tn = 0;
     for (int g = 0; g < G; g++) {

@@ -820,9 +820,69 @@ __device__ void exact_window(const hc_kparams& P, const Win& w, double& mean, do
     mean = __dmul_rn(__ddiv_rn(1.0, dl), total);                         // :137
 }
 
+// The same window by a whole warp: the lanes fetch 32 positions' addends at once, the additions still run in position
+// order (every lane repeats the chain on shuffled values).  Used when only a few candidates are queued -- the usual
+// case, a few dozen per batch -- where one thread per candidate means a chain of ~265 dependent loads.
+__device__ void exact_window_warp(const hc_kparams& P, const Win& w, int lane, double& mean, double& mmrate, uint32_t& mmc,
+                                  uint32_t& cmp, uint32_t& status) {
+    mean = 0.0;
+    mmrate = 1.0;
+    mmc = 0;
+    cmp = 0;
+    status = w.status;
+    if (w.status != HC_WIN_SCORED) return;
+    const uint32_t n1 = P.ncodes + 1u;
+    double total = 0.0;
+    uint32_t tl = 0, mm = 0;
+    const u64 yp = 16ull * w.ypos16;
+    for (uint32_t i0 = 0; i0 < w.L; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool valid = false;
+        uint32_t mis = 0;
+        double lp = 0.0;
+        if (i < w.L) {
+            const u64 xa = w.xpos + i, xb = yp + i;
+            if (P.packed) {
+                const uint32_t a = P.pk[xa], b = P.pk[xb];
+                if (a != 0 && b != 0) {                                               // N, :35-39,:122-124
+                    valid = true;
+                    mis = (a >> 6) != (b >> 6);
+                    lp = __ldg(P.dbl_table + hc_dbl_index(a & 63u, b & 63u, mis, n1));
+                }
+            } else {
+                const uint32_t nA = (P.nmask[xa >> 5] >> (xa & 31)) & 1u, nB = (P.nmask[xb >> 5] >> (xb & 31)) & 1u;
+                if (!(nA | nB)) {
+                    valid = true;
+                    const uint32_t a = (P.base2[xa >> 4] >> (2 * (xa & 15))) & 3u, b = (P.base2[xb >> 4] >> (2 * (xb & 15))) & 3u;
+                    mis = a != b;
+                    lp = P.dbl_table[hc_dbl_index(P.qual[xa], P.qual[xb], mis, n1)];
+                }
+            }
+        }
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t mmask = __ballot_sync(0xffffffffu, valid && mis);
+        if (__any_sync(0xffffffffu, valid && lp > 0.0)) { status = HC_WIN_VOID; return; }   // :125-127
+        mm += __popc(mmask);
+        tl += __popc(vmask);
+        for (uint32_t rem = vmask; rem; rem &= rem - 1)
+            total = __dadd_rn(total, __shfl_sync(0xffffffffu, lp, __ffs(rem) - 1));           // :119, position order
+    }
+    if (tl == 0) { status = HC_WIN_EMPTY; return; }                      // :129-131
+    mmc = mm;
+    cmp = tl;
+    const double dl = (double)tl;
+    mmrate = __ddiv_rn((double)(float)(int)mm, dl);                      // :132
+    mean = __dmul_rn(__ddiv_rn(1.0, dl), total);                         // :137
+}
+
 __global__ void hc_exact_kernel(const hc_kparams P) {
     const u64 nf = P.counters[HC_CNT_FLAGGED];
-    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nf; t += (u64)gridDim.x * blockDim.x) {
+    const u64 nthreads = (u64)gridDim.x * blockDim.x;
+    const bool warp_mode = nf * 32ull <= nthreads;     // every queued candidate can have a warp of its own
+    const int lane = threadIdx.x & 31;
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool writer = !warp_mode || lane == 0;
+    for (u64 t = warp_mode ? tid >> 5 : tid; t < nf; t += warp_mode ? nthreads >> 5 : nthreads) {
         const u64 i = P.flagged[t];
         const hc_candidate c = load_candidate(P, i);
         CandSetup s;
@@ -833,7 +893,8 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
         uint32_t mmc[2], cmp[2], stt[2];
 #pragma unroll
         for (int w = 0; w < 2; w++) {
-            exact_window(P, s.w[w], mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
+            if (warp_mode) exact_window_warp(P, s.w[w], lane, mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
+            else exact_window(P, s.w[w], mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
             if (stt[w] == HC_WIN_SCORED) {
                 ae[w] = mean[w] >= P.t_edge;   // <=> host-libm exp(mean) > edge_threshold
                 ao[w] = mean[w] >= P.t_ov;
@@ -844,6 +905,7 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
         }
         double mmrate;
         const uint32_t cls = classify(P, s.two, mmr, ae, ao, mmrate) | HC_CLS_EXACT;
+        if (!writer) continue;
         P.cls[i] = (uint8_t)cls;
         if ((cls & HC_CLS_MASK) == HC_CLASS_EDGE) {
             hc_tmp32 tm;

@@ -82,6 +82,23 @@ def test_golden_exact_edge_scores(built_lib, name):
     assert np.allclose(per["score"][e], ref["score"][e], rtol=1e-15, atol=0)
 
 
+def test_reference_order_pass_many_and_few(built_lib):
+    """The reference-order pass runs one warp per queued candidate when few are queued and one thread each when many
+    are (every accepted edge under HC_FLAG_EXACT_EDGE_SCORES): both give the oracle's sums (scores to 1e-14: device exp)."""
+    ss = W.synth_readset(400, 400, seed=777, n_rate=0.002)
+    c = W.geometry_candidates(ss, 40000, seed=778)
+    px = F.make_params(edge_threshold=0.9, mismatch=0.0, flags=F.FLAG_EXACT_EDGE_SCORES)
+    per, ref, stats = _against_oracle(ss.rs, px, c)
+    edges = ref["cls"] == F.CLASS_EDGE
+    assert edges.sum() > 6000 and (per["exact"][edges] == 1).all()          # more than 148*8*128/32 queued: thread mode
+    assert np.allclose(per["score"][edges], ref["score"][edges], rtol=1e-14, atol=0)
+    per2, ref2, _ = _against_oracle(ss.rs, px, c[:3000])                      # few queued: warp mode
+    e2 = ref2["cls"] == F.CLASS_EDGE
+    assert 0 < e2.sum() < 4000 and (per2["exact"][e2] == 1).all()
+    assert np.allclose(per2["score"][e2], ref2["score"][e2], rtol=1e-14, atol=0)
+    assert per2.tobytes() == per[:3000].tobytes()
+
+
 def test_fresh_inputs_all_types(built_lib):
     ss = W.synth_readset(400, 400, seed=4242, n_rate=0.002)
     c = W.geometry_candidates(ss, 20000, seed=4243)
@@ -246,10 +263,14 @@ def test_larger_random_batch_and_determinism(built_lib):
     assert np.array_equal(per1, per) and np.array_equal(per2[::-1], per1)
 
 
+@pytest.mark.parametrize("whole_max", ["0", ""])
 @pytest.mark.parametrize("chunk", ["777", "100000000"])
-def test_chunked_pipeline_and_compact_records(built_lib, monkeypatch, chunk):
-    """hc_score_batch streams the batch through the device in chunks (3 streams, 2 slots); the chunk
+def test_chunked_pipeline_and_compact_records(built_lib, monkeypatch, chunk, whole_max):
+    """hc_score_batch streams the batch through the device in steps (3 streams; the records either all copied ahead into
+    one buffer -- the default up to 2 GB -- or through two slots, forced here with HC_HOST_WHOLE_MAX=0); the step
     size must not change anything, and the 16-byte compact records give the same results."""
+    if whole_max:
+        monkeypatch.setenv("HC_HOST_WHOLE_MAX", whole_max)
     g = load_golden("synth_all_types")
     cands = np.tile(g.scored(), 3)
     p = g.params()
@@ -276,12 +297,15 @@ def test_chunked_pipeline_and_compact_records(built_lib, monkeypatch, chunk):
     assert np.array_equal(per1["cls"], ref["cls"])
 
 
+@pytest.mark.parametrize("whole_max", ["0", ""])
 @pytest.mark.parametrize("chunk", ["33", "777", "100000000"])
 @pytest.mark.parametrize("order", ["file", "by_read", "by_min_id"])
-def test_run_encoded_records(built_lib, monkeypatch, chunk, order):
+def test_run_encoded_records(built_lib, monkeypatch, chunk, order, whole_max):
     """hc_score_batch_runs (8-byte records, the shared read of a run held once): same edges, non-edge indices and
     per-candidate results as the 12-byte records, whatever the order of the list (long runs when it is sorted by
     read, runs of length 1 otherwise) and wherever the pipeline cuts it."""
+    if whole_max:
+        monkeypatch.setenv("HC_HOST_WHOLE_MAX", whole_max)
     g = load_golden("synth_all_types")
     cands = np.tile(g.scored(), 3)
     cands = cands[(cands["pos1"] < (1 << 14)) & (cands["pos2"] < (1 << 14))]

@@ -39,6 +39,7 @@ def one(seed: int) -> str:
     for layout in ("auto", "planar"):
         os.environ["HC_STORE_LAYOUT"] = layout
         os.environ["HC_HOST_CHUNK"] = str(int(rng.choice([777, 4096, 10 ** 8])))
+        os.environ["HC_HOST_WHOLE_MAX"] = str(int(rng.choice([0, 1 << 31])))       # two-slot / copy-ahead pipeline
         with capi.Store(ss.rs) as st:
             edges, nonedge, per, stats = st.score_batch(p, cands)
             assert_results_match(per, ref["score"], ref["mismatch_rate"], ref["pos3"], ref["pos4"], ref["cls"], what="seed %d %s" % (seed, layout))
