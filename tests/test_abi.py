@@ -49,3 +49,38 @@ def test_no_cpu_fallback_without_gpu(built_lib):
     with pytest.raises(capi.HcError) as e:
         capi.Store(rs)
     assert "no CPU fallback" in str(e.value)
+
+
+def _decode_runs(anchor, start, entries):
+    per_anchor = np.repeat(anchor, np.diff(start.astype(np.int64)))
+    other = entries["other"] & 0x7fffffff
+    anchor_is_2 = (entries["other"] >> 31).astype(bool)
+    return np.where(anchor_is_2, other, per_anchor), np.where(anchor_is_2, per_anchor, other)
+
+
+@pytest.mark.parametrize("order", ["file", "by_read", "by_min_id"])
+def test_run_encoding_round_trip(order):
+    """hc_candidate -> run-encoded 8-byte records (formats.run_encode) -> the same (ID1, ID2, POS, ORI, ORD), in the same order."""
+    rng = np.random.RandomState(5)
+    n = 5000
+    c = np.zeros(n, dtype=F.CANDIDATE)
+    c["idx1"], c["idx2"] = rng.randint(0, 300, size=n), rng.randint(0, 300, size=n)
+    c["pos1"], c["pos2"] = rng.randint(0, 1 << 14, size=n), rng.randint(0, 1 << 14, size=n)
+    c["ori1"], c["ori2"] = rng.randint(0, 2, size=n), rng.randint(0, 2, size=n)
+    c["ord"] = rng.choice([ord("-"), ord("1"), ord("2")], size=n)
+    if order == "by_read":
+        c = c[np.argsort(c["idx1"], kind="stable")]
+    elif order == "by_min_id":
+        c = c[np.lexsort((np.maximum(c["idx1"], c["idx2"]), np.minimum(c["idx1"], c["idx2"])))]
+    anchor, start, entries = F.run_encode(c)
+    assert entries.dtype.itemsize == 8 and start[0] == 0 and start[-1] == n and (np.diff(start.astype(np.int64)) > 0).all()
+    assert len(anchor) == len(start) - 1 and (order == "file" or len(anchor) <= 300)
+    i1, i2 = _decode_runs(anchor, start, entries)
+    assert np.array_equal(i1, c["idx1"]) and np.array_equal(i2, c["idx2"])
+    assert np.array_equal(entries["pos"], F.short_candidates(c)["pos"])
+    a0, s0, e0 = F.run_encode(c[:0])
+    assert len(a0) == 0 and len(e0) == 0 and s0.tolist() == [0]
+    big = c.copy()
+    big["pos1"][7] = 1 << 14
+    with pytest.raises(ValueError):
+        F.run_encode(big)
