@@ -13,12 +13,18 @@
 // All integer / float32 arithmetic, bit-identical to the reference (perc uses IEEE float division,
 // max, multiplication and floor, :375,:429,:487,:549).
 #include <cstdio>
+#include <cstdlib>
+#include <time.h>
 #include <cstring>
 #include <string>
 #include <cuda_runtime.h>
 #include "../../include/hc_b200.h"
 #include "hc_scan.cuh"
 #include "hc_stage.h"
+
+#ifndef HC_FNO_CELL
+#define HC_FNO_CELL 1   // 1: keys and minima in two arrays; 2: {key, min} cells of 16 bytes -- measured slower (claim 19.8 vs 17.1 ms, resolve 15.9 vs 12.3 ms)
+#endif
 
 namespace {
 
@@ -159,18 +165,20 @@ __global__ void fno_claim(FnoDev D, const hc_fno_edge* edges, u64 n, const u64* 
             const u64 key = (min(id1, id2) << 32) | max(id1, id2);
             u64 h = hash_slot(key, mask);
             while (true) {
-                const u64 prev = atomicCAS(&keys[h], ~0ull, key);
+                const u64 prev = atomicCAS(&keys[HC_FNO_CELL * h], ~0ull, key);
                 if (prev == ~0ull || prev == key) break;
                 h = (h + 1) & mask;
             }
-            atomicMin(&mins[h], seq);
+            atomicMin(&mins[HC_FNO_CELL * h], seq);
         });
     }
 }
 
-template <bool EMIT>
+// One pass: flags[seq] = "attempt seq yields an overlap" and, when it does, its record at rec[seq] (attempt order);
+// fno_compact then moves the records to their ranks.  (Deriving everything a second time for the emission cost as
+// much as the first pass: the gathers through vertex -> super-read lists are what these kernels spend their time on.)
 __global__ void fno_resolve(FnoDev D, const hc_fno_edge* edges, u64 n, const u64* off, const u64* keys, const u64* mins, u64 mask,
-                            uint32_t* flags, const u64* outpos, hc_fno_overlap* out, u64 out_cap) {
+                            uint32_t* flags, hc_fno_overlap* rec) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const hc_fno_edge e = edges[i];
         char ori1 = '+', ori2 = '+';
@@ -183,13 +191,13 @@ __global__ void fno_resolve(FnoDev D, const hc_fno_edge* edges, u64 n, const u64
         if (!D.visited[e.u] && !D.visited[e.v]) {                   // :46-72
             const u64 seq = off[i];
             const bool ok = !(D.no_inclusions && e.perc == 100);
-            if (!EMIT) flags[seq] = ok;
-            else if (ok && outpos[seq] < out_cap) {
+            flags[seq] = ok;
+            if (ok) {
                 hc_fno_overlap o;
                 memset(&o, 0, sizeof(o));
                 o.id1 = ru.id; o.id2 = rv.id; o.pos1 = e.pos1; o.pos2 = e.pos2; o.ord = e.ord; o.ori1 = ori1; o.ori2 = ori2;
                 o.perc = e.perc; o.len1 = e.len1; o.len2 = e.len2; o.type1 = pu ? 'p' : 's'; o.type2 = pv ? 'p' : 's';
-                out[outpos[seq]] = o;
+                rec[seq] = o;
             }
             continue;
         }
@@ -201,8 +209,8 @@ __global__ void fno_resolve(FnoDev D, const hc_fno_edge* edges, u64 n, const u64
             if (ok) {
                 const u64 key = (min(s1.id, s2.id) << 32) | max(s1.id, s2.id);
                 u64 h = hash_slot(key, mask);
-                while (keys[h] != key) h = (h + 1) & mask;
-                ok = mins[h] == seq;                                // first found wins, even if it fails below
+                while (keys[HC_FNO_CELL * h] != key) h = (h + 1) & mask;
+                ok = mins[HC_FNO_CELL * h] == seq;                                // first found wins, even if it fails below
             }
             if (ok) {
                 int i1l = 0, i1r = 0, i2l = 0, i2r = 0;
@@ -219,18 +227,25 @@ __global__ void fno_resolve(FnoDev D, const hc_fno_edge* edges, u64 n, const u64
                 ok = compute_overlap_data(s1, s2, i1l, i1r, i2l, i2r, e, d);
                 if (ok && D.no_inclusions && d.perc == 100) ok = false;
             }
-            if (!EMIT) flags[seq] = ok;
-            else if (ok && outpos[seq] < out_cap) {
+            flags[seq] = ok;
+            if (ok) {
                 hc_fno_overlap o;
                 memset(&o, 0, sizeof(o));
                 if (d.ord1 == '1') { o.id1 = s1.id; o.id2 = s2.id; o.type1 = d.t1; o.type2 = d.t2; }
                 else { o.id1 = s2.id; o.id2 = s1.id; o.type1 = d.t2; o.type2 = d.t1; }
                 o.pos1 = d.pos1; o.pos2 = d.pos2; o.ord = d.ord2; o.ori1 = ori1; o.ori2 = ori2;
                 o.perc = d.perc; o.len1 = d.ol1; o.len2 = d.ol2;
-                out[outpos[seq]] = o;
+                rec[seq] = o;
             }
         });
     }
+}
+
+// records of the successful attempts, attempt order -> output order (ranks from the scan of the flags)
+__global__ void fno_compact(const uint32_t* __restrict__ flags, const u64* __restrict__ outpos, const hc_fno_overlap* __restrict__ rec,
+                            u64 attempts, hc_fno_overlap* __restrict__ out, u64 out_cap) {
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < attempts; t += (u64)gridDim.x * blockDim.x)
+        if (flags[t] && outpos[t] < out_cap) out[outpos[t]] = rec[t];
 }
 
 
@@ -314,23 +329,24 @@ __global__ void fno3_pass(const u64* off, u64 n, const uint32_t* sr_idx, const h
                 u64 h = hash_slot(key, mask);
                 if (MODE == 0) {
                     while (true) {
-                        const u64 prev = atomicCAS(&keys[h], ~0ull, key);
+                        const u64 prev = atomicCAS(&keys[HC_FNO_CELL * h], ~0ull, key);
                         if (prev == ~0ull || prev == key) break;
                         h = (h + 1) & mask;
                     }
-                    atomicMin(&mins[h], seq);
+                    atomicMin(&mins[HC_FNO_CELL * h], seq);
                     continue;
                 }
-                if (MODE != 0) while (keys[h] != key) h = (h + 1) & mask;
-                bool ok = mins[h] == seq;                                   // first original wins, :116-121
+                if (MODE != 0) while (keys[HC_FNO_CELL * h] != key) h = (h + 1) & mask;
+                bool ok = mins[HC_FNO_CELL * h] == seq;                                   // first original wins, :116-121
                 hc_fno_overlap o;
                 if (ok) ok = deduce_overlap(A, B, sr_pos[i], sr_pos[j], o);
                 if (ok) {
                     const unsigned perc = o.perc2 > 0 ? (unsigned)(0.5 * (o.perc + o.perc2)) : (unsigned)o.perc;   // Overlap::get_perc
                     ok = !(no_inclusions && perc == 100) && o.len1 > 0;      // :157-165
                 }
-                if (MODE == 1) flags[seq] = ok;
-                else if (ok && outpos[seq] < out_cap) out[outpos[seq]] = o;
+                // MODE 1: flag + record at the attempt's index; fno_compact moves the records to their ranks
+                flags[seq] = ok;
+                if (ok) out[seq] = o;
             }
         }
     }
@@ -353,6 +369,21 @@ void hc_set_last_error(const char* msg);   // hc_api.cu
         }                                                                                 \
     } while (0)
 
+// HC_FNO_TIMING=1: phase times of hc_fno1 on stderr (synchronises the device at every mark)
+struct FnoPhase {
+    bool on;
+    double t0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    FnoPhase() : on(getenv("HC_FNO_TIMING") != nullptr), t0(0) { if (on) t0 = now(); }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const double t = now();
+        fprintf(stderr, "[hc_fno1] %-28s %8.2f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
+
 extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_t n_edges, hc_fno_overlap* out, uint64_t out_cap,
                        uint64_t* n_out, int device) {
     if (!in || !n_out || (n_edges && !edges) || (out_cap && !out)) { hc_set_last_error("hc_fno1: NULL argument"); return HC_ERR_ARG; }
@@ -367,13 +398,15 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     for (long long i = 0; i < (long long)nsr; i++) bad |= (in->sr_idx[i] >= NS);
     if (bad) { hc_set_last_error("hc_fno1: super-read index out of range"); return HC_ERR_ARG; }
     int rc = HC_OK;
+    FnoPhase ph;
+    ph.mark("argument checks");
     uint8_t *d_vis = nullptr, *d_lab = nullptr;
     hc_fno_read *d_vr = nullptr, *d_sr = nullptr;
     u64 *d_sroff = nullptr, *d_off = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr, *d_bsum = nullptr;
     uint32_t *d_sridx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
     hc_fno_subread* d_sub = nullptr;
     hc_fno_edge* d_edges = nullptr;
-    hc_fno_overlap* d_out = nullptr;
+    hc_fno_overlap *d_out = nullptr, *d_rec = nullptr;
     u64 attempts = 0, produced = 0, cap = 64, ncopy;
     FnoDev D;
     const int threads = 256;
@@ -394,20 +427,28 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     FCU(hc_copy_h2d(d_sridx, in->sr_idx, nsr * sizeof(uint32_t)));
     FCU(hc_copy_h2d(d_sub, in->sr_sub, nsr * sizeof(hc_fno_subread)));
     FCU(hc_copy_h2d(d_edges, edges, n_edges * sizeof(hc_fno_edge)));
+    ph.mark("allocations + copies in");
     D.n_vertices = V; D.visited = d_vis; D.label = d_lab; D.vertex_read = d_vr; D.sr_off = d_sroff; D.sr_idx = d_sridx;
     D.sr_sub = d_sub; D.superread = d_sr; D.resolve_orientations = in->resolve_orientations; D.no_inclusions = in->no_inclusions;
     fno_count<<<blocks, threads>>>(D, d_edges, n_edges, d_cnt);
     FCU(hc_scratch_alloc((void**)&d_bsum, hc_scan::blocks_for(n_edges) * sizeof(u64)));
     hc_scan::exclusive_u32(d_cnt, n_edges, d_off, d_total, d_bsum, 0);
     FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
+    ph.mark("count + scan");
     if (attempts == 0) goto done;
     while (cap < 2 * attempts + 2) cap <<= 1;
-    FCU(hc_scratch_alloc((void**)&d_keys, cap * sizeof(u64))); FCU(hc_scratch_alloc((void**)&d_mins, cap * sizeof(u64)));
-    FCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); FCU(cudaMemset(d_mins, 0xff, cap * sizeof(u64)));
+    // open-addressing table: pair key -> smallest sequence number (both arrays indexed [HC_FNO_CELL * slot])
+    FCU(hc_scratch_alloc((void**)&d_keys, 2 * cap * sizeof(u64)));
+    d_mins = d_keys + (HC_FNO_CELL == 2 ? 1 : cap);
+    FCU(cudaMemset(d_keys, 0xff, 2 * cap * sizeof(u64)));
     FCU(hc_scratch_alloc((void**)&d_flags, attempts * sizeof(uint32_t))); FCU(hc_scratch_alloc((void**)&d_outpos, attempts * sizeof(u64)));
     FCU(cudaMemset(d_flags, 0, attempts * sizeof(uint32_t)));
+    ph.mark("tables: alloc + memset");
     fno_claim<<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1);
-    fno_resolve<false><<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
+    ph.mark("fno_claim");
+    FCU(hc_scratch_alloc((void**)&d_rec, attempts * sizeof(hc_fno_overlap)));
+    fno_resolve<<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, d_rec);
+    ph.mark("fno_resolve");
     hc_scratch_free(d_bsum); d_bsum = nullptr;
     FCU(hc_scratch_alloc((void**)&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
     hc_scan::exclusive_u32(d_flags, attempts, d_outpos, d_total, d_bsum, 0);
@@ -417,13 +458,16 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
     if (produced == 0) goto done;
     ncopy = produced;
     FCU(hc_scratch_alloc((void**)&d_out, ncopy * sizeof(hc_fno_overlap)));
-    fno_resolve<true><<<blocks, threads>>>(D, d_edges, n_edges, d_off, d_keys, d_mins, cap - 1, d_flags, d_outpos, d_out, ncopy);
+    ph.mark("scan of flags");
+    fno_compact<<<148 * 16, 256>>>(d_flags, d_outpos, d_rec, attempts, d_out, ncopy);
     FCU(cudaGetLastError());
+    ph.mark("fno_compact");
     FCU(hc_copy_d2h(out, d_out, ncopy * sizeof(hc_fno_overlap)));
+    ph.mark("copy out");
 done:
     hc_scratch_free(d_vis); hc_scratch_free(d_lab); hc_scratch_free(d_vr); hc_scratch_free(d_sr); hc_scratch_free(d_sroff); hc_scratch_free(d_sridx); hc_scratch_free(d_sub);
-    hc_scratch_free(d_edges); hc_scratch_free(d_cnt); hc_scratch_free(d_off); hc_scratch_free(d_total); hc_scratch_free(d_keys); hc_scratch_free(d_mins);
-    hc_scratch_free(d_flags); hc_scratch_free(d_outpos); hc_scratch_free(d_out); hc_scratch_free(d_bsum);
+    hc_scratch_free(d_edges); hc_scratch_free(d_cnt); hc_scratch_free(d_off); hc_scratch_free(d_total); hc_scratch_free(d_keys);
+    hc_scratch_free(d_flags); hc_scratch_free(d_outpos); hc_scratch_free(d_out); hc_scratch_free(d_bsum); hc_scratch_free(d_rec);
     return rc;
 }
 
@@ -447,7 +491,7 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     uint32_t *d_idx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;
     hc_fno3_pos* d_pos = nullptr;
     hc_fno_read* d_reads = nullptr;
-    hc_fno_overlap* d_out = nullptr;
+    hc_fno_overlap *d_out = nullptr, *d_rec = nullptr;
     u64 attempts = 0, produced = 0, cap = 64;
     const int threads = 128;
     const int blocks = (int)((n_originals + threads - 1) / threads < 8192 ? (n_originals + threads - 1) / threads : 8192);
@@ -466,11 +510,14 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     FCU(cudaMemcpy(&attempts, d_total, sizeof(u64), cudaMemcpyDeviceToHost));
     if (attempts == 0) goto done;
     while (cap < 2 * attempts + 2) cap <<= 1;
-    FCU(hc_scratch_alloc((void**)&d_keys, cap * sizeof(u64))); FCU(hc_scratch_alloc((void**)&d_mins, cap * sizeof(u64)));
-    FCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); FCU(cudaMemset(d_mins, 0xff, cap * sizeof(u64)));
+    // open-addressing table: pair key -> smallest sequence number (both arrays indexed [HC_FNO_CELL * slot])
+    FCU(hc_scratch_alloc((void**)&d_keys, 2 * cap * sizeof(u64)));
+    d_mins = d_keys + (HC_FNO_CELL == 2 ? 1 : cap);
+    FCU(cudaMemset(d_keys, 0xff, 2 * cap * sizeof(u64)));
     FCU(hc_scratch_alloc((void**)&d_flags, attempts * sizeof(uint32_t))); FCU(hc_scratch_alloc((void**)&d_outpos, attempts * sizeof(u64)));
     fno3_pass<0><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, nullptr, nullptr, nullptr, 0);
-    fno3_pass<1><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, nullptr, nullptr, 0);
+    FCU(hc_scratch_alloc((void**)&d_rec, attempts * sizeof(hc_fno_overlap)));
+    fno3_pass<1><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, nullptr, d_rec, attempts);
     hc_scratch_free(d_bsum); d_bsum = nullptr;
     FCU(hc_scratch_alloc((void**)&d_bsum, hc_scan::blocks_for(attempts) * sizeof(u64)));
     hc_scan::exclusive_u32(d_flags, attempts, d_outpos, d_total, d_bsum, 0);
@@ -479,11 +526,12 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
     if (produced > out_cap) { hc_set_last_error("hc_fno3: output buffer too small (required size returned in n_out)"); rc = HC_ERR_CAPACITY; goto done; }
     if (produced == 0) goto done;
     FCU(hc_scratch_alloc((void**)&d_out, produced * sizeof(hc_fno_overlap)));
-    fno3_pass<2><<<blocks, threads>>>(d_off, n_originals, d_idx, d_pos, d_reads, no_inclusions, d_seq, d_keys, d_mins, cap - 1, d_flags, d_outpos, d_out, produced);
+    fno_compact<<<148 * 16, 256>>>(d_flags, d_outpos, d_rec, attempts, d_out, produced);
     FCU(cudaGetLastError());
     FCU(hc_copy_d2h(out, d_out, produced * sizeof(hc_fno_overlap)));
 done:
     hc_scratch_free(d_off); hc_scratch_free(d_idx); hc_scratch_free(d_pos); hc_scratch_free(d_reads); hc_scratch_free(d_cnt); hc_scratch_free(d_seq); hc_scratch_free(d_total);
-    hc_scratch_free(d_keys); hc_scratch_free(d_mins); hc_scratch_free(d_flags); hc_scratch_free(d_outpos); hc_scratch_free(d_out); hc_scratch_free(d_bsum);
+    hc_scratch_free(d_keys); hc_scratch_free(d_flags); hc_scratch_free(d_outpos); hc_scratch_free(d_out); hc_scratch_free(d_bsum);
+    hc_scratch_free(d_rec);
     return rc;
 }
