@@ -81,7 +81,7 @@ def test_permutation_equivariance(built_lib, c4_small):
     assert a[perm].tobytes() == b.tobytes()
 
 
-def test_store_replicated_on_two_devices(built_lib):
+def test_store_replicated_on_two_devices(built_lib, monkeypatch):
     """n_devices = 2 in one process: the planes packed on the first device are copied to the second, the batch is cut into
     two contiguous shards and the lists come back in input order -- identical to the one-device result."""
     if capi.device_count() < 2:
@@ -93,7 +93,17 @@ def test_store_replicated_on_two_devices(built_lib):
         e1, n1, p1, _ = st1.score_batch(g.params(), cands)
     with capi.Store(g.rs, first_device=0, n_devices=2) as st2:
         e2, n2, p2, _ = st2.score_batch(g.params(), cands)
+        fits = (cands["pos1"] < (1 << 14)) & (cands["pos2"] < (1 << 14))
+        er, nr, pr, _ = st2.score_batch(g.params(), cands[fits], compact="runs")     # run-encoded records, two shards
+        monkeypatch.setenv("HC_HOST_CHUNK", "1000")
+        er2, nr2, pr2, _ = st2.score_batch(g.params(), cands[fits], compact="runs")
+        monkeypatch.setenv("HC_HOST_WHOLE_MAX", "0")                                # two-slot pipeline
+        er3, nr3, pr3, _ = st2.score_batch(g.params(), cands[fits], compact="runs")
+        monkeypatch.delenv("HC_HOST_CHUNK"); monkeypatch.delenv("HC_HOST_WHOLE_MAX")
     assert p1.tobytes() == p2.tobytes() and e1.tobytes() == e2.tobytes() and np.array_equal(n1, n2)
+    assert pr.tobytes() == p1[fits].tobytes() and pr2.tobytes() == pr.tobytes() and pr3.tobytes() == pr.tobytes()
+    assert er2.tobytes() == er.tobytes() and er3.tobytes() == er.tobytes() and np.array_equal(nr2, nr) and np.array_equal(nr3, nr)
+    assert len(er) == int((p1["cls"][fits] == 1).sum())
     with capi.Store(g.rs, first_device=1, n_devices=1) as st3:           # a store that lives on the second device only
         e3, n3, p3, _ = st3.score_batch(g.params(), cands)
     assert p1.tobytes() == p3.tobytes() and e1.tobytes() == e3.tobytes()
