@@ -7,7 +7,9 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <memory>
 #include <mutex>
+#include <new>
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "../../include/hc_b200.h"
@@ -651,25 +653,25 @@ int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_proble
     const uint64_t cols = out_bytes ? out_bytes : 1;
     uint64_t marked_cap = cols / 64 + 4096;
     unsigned long long n_marked = 0;
-    std::vector<uint16_t> cnt;
+    std::unique_ptr<uint16_t[]> cnt;      // not zero-filled: the copy out writes every element that is read
     std::vector<uint32_t> lens(n_seqs ? n_seqs : 1);
     std::vector<unsigned long long> marked;
     std::vector<double> msums;
     int rc = HC_OK;
     const bool mark_all = getenv("HC_CONS_HOST_ALL") != nullptr;      // tests: every column through the host libm
     if (mark_all) marked_cap = cols;
-    cudaError_t e = cudaMalloc(&d_prob, n_problems * sizeof(hc_cons_problem));
-    if (e == cudaSuccess) e = cudaMalloc(&d_seqs, (n_seqs ? n_seqs : 1) * sizeof(hc_cons_seq));
-    if (e == cudaSuccess) e = cudaMalloc(&d_toff, (n_problems + 1) * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&d_add, sizeof(addend));
-    if (e == cudaSuccess) e = cudaMalloc(&d_c2q, sizeof(c2q));
-    if (e == cudaSuccess) e = cudaMalloc(&d_sums, cols * 4 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, cols * sizeof(uint16_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_base, cols);
-    if (e == cudaSuccess) e = cudaMalloc(&d_qual, cols);
-    if (e == cudaSuccess) e = cudaMalloc(&d_marked, marked_cap * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&d_nmarked, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc(&d_len, (n_seqs ? n_seqs : 1) * sizeof(uint32_t));
+    cudaError_t e = hc_scratch_alloc_on((void**)&d_prob, n_problems * sizeof(hc_cons_problem), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_seqs, (n_seqs ? n_seqs : 1) * sizeof(hc_cons_seq), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_toff, (n_problems + 1) * sizeof(unsigned long long), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_add, sizeof(addend), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_c2q, sizeof(c2q), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_sums, cols * 4 * sizeof(double), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_cnt, cols * sizeof(uint16_t), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_base, cols, d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_qual, cols, d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_marked, marked_cap * sizeof(unsigned long long), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_nmarked, sizeof(unsigned long long), d.stream);
+    if (e == cudaSuccess) e = hc_scratch_alloc_on((void**)&d_len, (n_seqs ? n_seqs : 1) * sizeof(uint32_t), d.stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_nmarked, 0, sizeof(unsigned long long), d.stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_base, 0, cols, d.stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_qual, 0, cols, d.stream);
@@ -693,12 +695,14 @@ int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_proble
     if (e == cudaSuccess) e = cudaMemcpyAsync(&n_marked, d_nmarked, sizeof(n_marked), cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     if (e == cudaSuccess) {
-        try { cnt.resize((size_t)cols); } catch (...) { rc = fail(HC_ERR_NOMEM, "hc_consensus: host allocation failed"); }
+        cnt.reset(new (std::nothrow) uint16_t[(size_t)cols]);
+        if (!cnt) rc = fail(HC_ERR_NOMEM, "hc_consensus: host allocation failed");
     }
     if (e == cudaSuccess && rc == HC_OK && out_bytes) {
-        e = cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)out_bytes * sizeof(uint16_t), cudaMemcpyDeviceToHost, d.stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(cons_seq, d_base, (size_t)out_bytes, cudaMemcpyDeviceToHost, d.stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(cons_qual, d_qual, (size_t)out_bytes, cudaMemcpyDeviceToHost, d.stream);
+        // the stream has just been synchronised: the staged copies (pinned ring, several host threads) may run beside it
+        e = hc_copy_d2h(cnt.get(), d_cnt, (size_t)out_bytes * sizeof(uint16_t));
+        if (e == cudaSuccess) e = hc_copy_d2h(cons_seq, d_base, (size_t)out_bytes);
+        if (e == cudaSuccess) e = hc_copy_d2h(cons_qual, d_qual, (size_t)out_bytes);
     }
     if (e == cudaSuccess && rc == HC_OK && n_seqs) e = cudaMemcpyAsync(lens.data(), d_len, n_seqs * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream);
     // ---- columns whose outcome is within the error bound of a decision: their scores come back and the host libm decides
@@ -706,7 +710,7 @@ int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_proble
     if (e == cudaSuccess && rc == HC_OK && !all_cols && n_marked) {
         marked.resize(n_marked);
         msums.resize(4 * n_marked);
-        e = cudaMalloc(&d_msums, 4 * n_marked * sizeof(double));
+        e = hc_scratch_alloc_on((void**)&d_msums, 4 * n_marked * sizeof(double), d.stream);
         if (e == cudaSuccess) e = hc_launch_cons_gather(d_marked, n_marked, d_sums, d_msums, d.stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(marked.data(), d_marked, n_marked * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(msums.data(), d_msums, 4 * n_marked * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
@@ -716,8 +720,8 @@ int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_proble
         if (rc == HC_OK) e = cudaMemcpyAsync(msums.data(), d_sums, (size_t)out_bytes * 4 * sizeof(double), cudaMemcpyDeviceToHost, d.stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
-    cudaFree(d_prob); cudaFree(d_seqs); cudaFree(d_toff); cudaFree(d_add); cudaFree(d_c2q); cudaFree(d_sums); cudaFree(d_cnt); cudaFree(d_len);
-    cudaFree(d_base); cudaFree(d_qual); cudaFree(d_marked); cudaFree(d_nmarked); cudaFree(d_msums);
+    hc_scratch_free_on(d_prob, d.stream); hc_scratch_free_on(d_seqs, d.stream); hc_scratch_free_on(d_toff, d.stream); hc_scratch_free_on(d_add, d.stream); hc_scratch_free_on(d_c2q, d.stream); hc_scratch_free_on(d_sums, d.stream); hc_scratch_free_on(d_cnt, d.stream); hc_scratch_free_on(d_len, d.stream);
+    hc_scratch_free_on(d_base, d.stream); hc_scratch_free_on(d_qual, d.stream); hc_scratch_free_on(d_marked, d.stream); hc_scratch_free_on(d_nmarked, d.stream); hc_scratch_free_on(d_msums, d.stream);
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_consensus: ") + cudaGetErrorString(e));
     if (rc != HC_OK) return rc;
     if (all_cols) {
@@ -740,7 +744,7 @@ int hc_consensus(hc_store* s, const hc_cons_problem* problems, uint64_t n_proble
     // ---- the column walk of :447-513, problems in parallel (their output regions are disjoint)
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t p = 0; p < (int64_t)n_problems; p++)
-        hc_cons_walk(&problems[p], seqs, lens.data(), cnt.data(), min_clique_size, cons_seq, cons_qual, &results[p]);
+        hc_cons_walk(&problems[p], seqs, lens.data(), cnt.get(), min_clique_size, cons_seq, cons_qual, &results[p]);
     if (getenv("HC_CONS_VERBOSE")) fprintf(stderr, "hc_consensus: %llu of %llu columns re-evaluated on the host\n",
                                            all_cols ? (unsigned long long)out_bytes : n_marked, (unsigned long long)out_bytes);
     return HC_OK;

@@ -127,7 +127,11 @@ cudaError_t hc_copy_d2h(void* dst, const void* src, size_t bytes) {
     return cudaSuccess;
 }
 
-cudaError_t hc_scratch_alloc(void** p, size_t bytes) {
+cudaError_t hc_scratch_alloc(void** p, size_t bytes) { return hc_scratch_alloc_on(p, bytes, 0); }
+
+void hc_scratch_free(void* p) { hc_scratch_free_on(p, 0); }
+
+cudaError_t hc_scratch_alloc_on(void** p, size_t bytes, cudaStream_t st) {
     static std::mutex mu;
     static bool tuned[16] = {false};
     int dev = 0;
@@ -145,9 +149,9 @@ cudaError_t hc_scratch_alloc(void** p, size_t bytes) {
             tuned[dev & 15] = true;
         }
     }
-    return cudaMallocAsync(p, bytes ? bytes : 1, 0);
+    return cudaMallocAsync(p, bytes ? bytes : 1, st);
 }
 
-void hc_scratch_free(void* p) {
-    if (p) cudaFreeAsync(p, 0);
+void hc_scratch_free_on(void* p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
 }

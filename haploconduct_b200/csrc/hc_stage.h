@@ -17,5 +17,8 @@ cudaError_t hc_copy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 // cudaMalloc / cudaFree for each of its dozen temporaries.
 cudaError_t hc_scratch_alloc(void** p, size_t bytes);
 void hc_scratch_free(void* p);
+// the same on a stream of the caller's (the store's streams are non-blocking: they do not order with the default stream)
+cudaError_t hc_scratch_alloc_on(void** p, size_t bytes, cudaStream_t st);
+void hc_scratch_free_on(void* p, cudaStream_t st);
 
 #endif
