@@ -105,12 +105,12 @@ extern "C" int hc_dedup_edges(const hc_dedup_edge* edges, uint64_t n, int ignore
     const int blocks = (int)std::min<u64>((n + threads - 1) / threads, 148 * 16);
     while (cap < 2 * n + 2) cap <<= 1;
     DCU(cudaSetDevice(device));
-    DCU(cudaMalloc(&d_e, n * sizeof(hc_dedup_edge)));
-    DCU(cudaMalloc(&d_keys, cap * sizeof(u64))); DCU(cudaMalloc(&d_best, cap * sizeof(u64))); DCU(cudaMalloc(&d_first, cap * sizeof(u64)));
-    DCU(cudaMalloc(&d_counts, 2 * sizeof(u64))); DCU(cudaMalloc(&d_win, n));
+    DCU(hc_scratch_alloc((void**)&d_e, n * sizeof(hc_dedup_edge)));
+    DCU(hc_scratch_alloc((void**)&d_keys, cap * sizeof(u64))); DCU(hc_scratch_alloc((void**)&d_best, cap * sizeof(u64))); DCU(hc_scratch_alloc((void**)&d_first, cap * sizeof(u64)));
+    DCU(hc_scratch_alloc((void**)&d_counts, 2 * sizeof(u64))); DCU(hc_scratch_alloc((void**)&d_win, n));
     DCU(cudaMemset(d_keys, 0xff, cap * sizeof(u64))); DCU(cudaMemset(d_best, 0xff, cap * sizeof(u64)));
     DCU(cudaMemset(d_first, 0xff, cap * sizeof(u64))); DCU(cudaMemset(d_counts, 0, 2 * sizeof(u64)));
-    if (inclusions && n_vertices) { DCU(cudaMalloc(&d_inc, n_vertices)); DCU(cudaMemcpy(d_inc, inclusions, n_vertices, cudaMemcpyHostToDevice)); }
+    if (inclusions && n_vertices) { DCU(hc_scratch_alloc((void**)&d_inc, n_vertices)); DCU(cudaMemcpy(d_inc, inclusions, n_vertices, cudaMemcpyHostToDevice)); }
     DCU(hc_copy_h2d(d_e, edges, n * sizeof(hc_dedup_edge)));
     dd_claim<<<blocks, threads>>>(d_e, n, d_keys, d_best, d_first, cap - 1, d_counts);
     dd_resolve<<<blocks, threads>>>(d_e, n, d_keys, d_best, d_first, cap - 1, ignore_inclusions, d_win, d_inc, d_counts);
@@ -119,6 +119,6 @@ extern "C" int hc_dedup_edges(const hc_dedup_edge* edges, uint64_t n, int ignore
     DCU(cudaMemcpy(counts, d_counts, 2 * sizeof(u64), cudaMemcpyDeviceToHost));
     if (d_inc) DCU(cudaMemcpy(inclusions, d_inc, n_vertices, cudaMemcpyDeviceToHost));
 done:
-    cudaFree(d_e); cudaFree(d_keys); cudaFree(d_best); cudaFree(d_first); cudaFree(d_counts); cudaFree(d_win); cudaFree(d_inc);
+    hc_scratch_free(d_e); hc_scratch_free(d_keys); hc_scratch_free(d_best); hc_scratch_free(d_first); hc_scratch_free(d_counts); hc_scratch_free(d_win); hc_scratch_free(d_inc);
     return rc;
 }
