@@ -811,7 +811,9 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         whole[g] = m > 0 && m * rec <= whole_max;
         std::vector<uint64_t>& c = cs[g];
         c.push_back(lo[g]);
-        const uint64_t big = 16ull << 20, small = 1ull << 20;
+        uint64_t big = 16ull << 20;
+        const uint64_t small = 1ull << 20;
+        if (const char* e = getenv("HC_HOST_BIG")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 2 * small) big = v; }   // experiments
         if (chunk || !whole[g] || m <= 2 * small) {
             const uint64_t step = chunk ? chunk : (8ull << 20);
             for (uint64_t o = step; o < m; o += step) c.push_back(lo[g] + o);
