@@ -7,9 +7,10 @@
 // processing order -- whether or not that attempt then succeeds (:84-97 precede :115-118).  Here:
 //   1. fno_count      attempts per edge                       -> exclusive scan = sequence numbers
 //   2. fno_claim      every keyed attempt does atomicMin(sequence number) on its pair's hash slot
-//   3. fno_flag       an attempt survives if it is a plain copy (:46-72) or holds its pair's minimum,
-//                     and computeOverlapData succeeds          -> exclusive scan = output positions
-//   4. fno_emit       survivors are written in processing order
+//   3. fno_resolve    an attempt survives if it is a plain copy (:46-72) or holds its pair's minimum,
+//                     and computeOverlapData succeeds; its record is written at its sequence number
+//                                                                -> exclusive scan of the flags = output positions
+//   4. fno_compact    survivors are moved to their positions: processing order
 // All integer / float32 arithmetic, bit-identical to the reference (perc uses IEEE float division,
 // max, multiplication and floor, :375,:429,:487,:549).
 #include <cstdio>
