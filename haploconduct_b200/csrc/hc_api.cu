@@ -43,7 +43,8 @@ struct DevCtx {
     int sm_count = 0;
     size_t smem_per_sm = 0;
     // store planes
-    uint8_t* pk = nullptr;       // packed layout (code | base << 6), or
+    uint8_t* pk = nullptr;       // packed layout (code | base << 6): pk_alloc + HC_PLANE_GUARD (zero bytes in front), or
+    uint8_t* pk_alloc = nullptr;
     uint8_t* qual = nullptr;     // planar layout: quality codes, 2-bit bases, N mask
     uint32_t* base2 = nullptr;
     uint32_t* nmask = nullptr;
@@ -54,6 +55,7 @@ struct DevCtx {
     bool tables_valid = false;
     double tables_mismatch = 0.0;
     bool has_void = false;
+    bool void_exact = false;
     // workspace (grown on demand)
     uint64_t ws_cap = 0;
     hc_tmp32* tmp = nullptr;
@@ -117,7 +119,7 @@ namespace {
 void free_ctx(DevCtx& d) {
     if (d.device < 0) return;
     cudaSetDevice(d.device);
-    cudaFree(d.pk); cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc);
+    cudaFree(d.pk_alloc); cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc);
     cudaFree(d.fx_table); cudaFree(d.dbl_table);
     cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts); cudaFree(d.counters);
     for (int k = 0; k < 2; k++) {
@@ -155,13 +157,16 @@ int ensure_tables(hc_store* s, DevCtx& d, double mismatch, cudaStream_t st) {
     // synchronous upload: tables change only when ps.mismatch changes (it never does in the drivers)
     CU(cudaStreamSynchronize(st));
     const std::vector<uint32_t>& fx = s->packed ? s->tables.fx_packed : s->tables.fx;
-    if (!d.fx_table) CU(cudaMalloc(&d.fx_table, fx.size() * sizeof(uint32_t)));
+    const std::vector<uint32_t>& fa = s->tables.fx_anchor;          // packed layout: the anchor-walk table follows
+    if (!d.fx_table) CU(cudaMalloc(&d.fx_table, (fx.size() + (s->packed ? fa.size() : 0)) * sizeof(uint32_t)));
     if (!d.dbl_table) CU(cudaMalloc(&d.dbl_table, s->tables.dbl.size() * sizeof(double)));
     CU(cudaMemcpy(d.fx_table, fx.data(), fx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (s->packed) CU(cudaMemcpy(d.fx_table + fx.size(), fa.data(), fa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.dbl_table, s->tables.dbl.data(), s->tables.dbl.size() * sizeof(double), cudaMemcpyHostToDevice));
     d.tables_valid = true;
     d.tables_mismatch = mismatch;
     d.has_void = s->tables.has_void;
+    d.void_exact = s->tables.void_asymmetric;
     return HC_OK;
 }
 
@@ -230,6 +235,12 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     P.zero_above_edge = 0.0 > p->edge_threshold;
     P.zero_above_ov = 0.0 > p->ov_threshold;
     P.exact_edges = (p->flags & HC_FLAG_EXACT_EDGE_SCORES) ? 1u : 0u;
+    // anchor walk: on for the packed layout, started for tiles in which at least HC_ANCHOR_WALK_MIN lanes (default 12) take
+    // part; HC_NO_ANCHOR_WALK: lane-chunk rounds only (tests, A/B timing)
+    uint32_t walk_min = 12;
+    if (const char* e = getenv("HC_ANCHOR_WALK_MIN")) walk_min = (uint32_t)std::max(1l, std::min(32l, strtol(e, nullptr, 10)));
+    P.anchor_walk = (s->packed && !getenv("HC_NO_ANCHOR_WALK")) ? walk_min : 0u;
+    P.void_exact = d.void_exact ? 1u : 0u;
     CU(cudaMemsetAsync(d.counters, 0, HC_CNT_N * sizeof(unsigned long long), st));
     if (k0) CU(cudaEventRecord(k0, st));
     uint32_t nl = 0;
@@ -370,11 +381,19 @@ cudaError_t init_ctx(hc_store* s, DevCtx& d, int device, bool* not_sm100) {
 
 cudaError_t alloc_planes(hc_store* s, DevCtx& d, cudaStream_t st) {
     const uint64_t total = s->total_positions;
-    uint8_t** qplane = s->packed ? &d.pk : &d.qual;
-    cudaError_t e = cudaMalloc(qplane, total + 64);
+    // The packed plane has HC_PLANE_GUARD zero bytes in front: the anchor walk of hc_score_kernel reads up to 32 bytes
+    // before a sequence (the zero padding of the slot before it; for the first slot, this guard).
+    cudaError_t e;
+    if (s->packed) {
+        e = cudaMalloc(&d.pk_alloc, total + 64 + HC_PLANE_GUARD);
+        if (e == cudaSuccess) d.pk = d.pk_alloc + HC_PLANE_GUARD;
+        if (e == cudaSuccess) e = cudaMemsetAsync(d.pk_alloc, 0, total + 64 + HC_PLANE_GUARD, st);
+    } else {
+        e = cudaMalloc(&d.qual, total + 64);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d.qual, 0, total + 64, st);
+    }
     if (e == cudaSuccess && !s->packed) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
     if (e == cudaSuccess && !s->packed) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);
-    if (e == cudaSuccess) e = cudaMemsetAsync(*qplane, 0, total + 64, st);
     if (e == cudaSuccess && !s->packed) e = cudaMemsetAsync(d.base2, 0, (total / 16 + 16) * 4, st);
     if (e == cudaSuccess && !s->packed) e = cudaMemsetAsync(d.nmask, 0, (total / 32 + 16) * 4, st);
     return e;
@@ -394,20 +413,21 @@ int build_store(hc_store* s, std::vector<hc_rdesc>& rd, const uint8_t* d_text, c
     }
     DevCtx& d0 = s->devs[0];
     CU(cudaSetDevice(d0.device));
-    uint32_t* d_flags = nullptr;    // [0..7] quality characters seen, [8] error bits
+    unsigned long long* d_flags = nullptr;    // [0..127] occurrences of every quality character, [128] error bits
     uint8_t* d_lut = nullptr;
-    uint32_t h_flags[9];
+    unsigned long long h_flags[129];
     uint8_t lut[256];
-    cudaError_t e = cudaMalloc(&d_flags, 9 * sizeof(uint32_t));
+    cudaError_t e = cudaMalloc(&d_flags, sizeof(h_flags));
     if (e == cudaSuccess) e = cudaMalloc(&d_lut, 256);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, 9 * sizeof(uint32_t), d0.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, sizeof(h_flags), d0.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d0.rdesc, rd.data(), n_reads * sizeof(hc_rdesc), cudaMemcpyHostToDevice, d0.stream);
-    if (e == cudaSuccess) e = hc_pack_validate_launch(d_text, d_src, d0.rdesc, n_reads, n_upper, d_flags, d_flags + 8, d0.stream);
+    if (e == cudaSuccess)
+        e = hc_pack_validate_launch(d_text, d_src, d0.rdesc, n_reads, n_upper, d_flags, reinterpret_cast<uint32_t*>(d_flags + 128), d0.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, d0.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d0.stream);
     int rc = HC_OK;
-    if (e == cudaSuccess && h_flags[8]) {
-        rc = fail(HC_ERR_INPUT, (h_flags[8] & 1u)
+    if (e == cudaSuccess && h_flags[128]) {
+        rc = fail(HC_ERR_INPUT, (h_flags[128] & 1u)
                                     ? "invalid nucleotide (only upper-case A,C,G,T,N are accepted; the reference asserts in "
                                       "EdgeCalculator::score, src/EdgeCalculator.cpp:29-30)"
                                     : "quality character outside '!'..'~' (Phred 0..93; src/EdgeCalculator.cpp:61,93-98)");
@@ -417,13 +437,16 @@ int build_store(hc_store* s, std::vector<hc_rdesc>& rd, const uint8_t* d_text, c
         memset(lut, 0, sizeof(lut));
         s->ncodes = 0;
         s->code_to_q[0] = -1;
-        for (int c = 33; c <= 33 + 93; c++) {
-            if ((h_flags[c >> 5] >> (c & 31)) & 1u) {
-                s->ncodes++;
-                s->code_to_q[s->ncodes] = c - 33;
-                s->q_to_code[c] = s->ncodes;
-                lut[c] = (uint8_t)s->ncodes;
-            }
+        // quality codes ranked by frequency, the most frequent value first (ties: the smaller Phred value): the codes that
+        // share a shared-memory bank in the anchor-walk table, c and c + 32, are then the rare ones (hc_layout.h)
+        std::vector<int> present;
+        for (int c = 33; c <= 33 + 93; c++) if (h_flags[c]) present.push_back(c);
+        std::stable_sort(present.begin(), present.end(), [&](int a, int b) { return h_flags[a] > h_flags[b]; });
+        for (int c : present) {
+            s->ncodes++;
+            s->code_to_q[s->ncodes] = c - 33;
+            s->q_to_code[c] = s->ncodes;
+            lut[c] = (uint8_t)s->ncodes;
         }
         const char* layout = getenv("HC_STORE_LAYOUT");   // "planar" forces the three-plane layout (tests)
         s->packed = s->ncodes <= HC_PACKED_MAX_CODES && !(layout && strcmp(layout, "planar") == 0);
@@ -441,7 +464,7 @@ int build_store(hc_store* s, std::vector<hc_rdesc>& rd, const uint8_t* d_text, c
     for (int k = 0; k < n_devices && e == cudaSuccess; k++) {
         DevCtx& d = s->devs[k];
         e = cudaSetDevice(d.device);
-        if (e == cudaSuccess) e = hc_score_occupancy((uint32_t)s->ncodes, d.sm_count, d.smem_per_sm, &d.cfg);
+        if (e == cudaSuccess) e = hc_score_occupancy((uint32_t)s->ncodes, s->packed ? 1 : 0, d.sm_count, d.smem_per_sm, &d.cfg);
         if (k == 0 || e != cudaSuccess) continue;
         e = alloc_planes(s, d, d.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);

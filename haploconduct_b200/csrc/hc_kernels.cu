@@ -36,6 +36,8 @@ struct Win {
     uint32_t L;       // window length (src/EdgeCalculator.cpp:88); 0 when not scored
     uint32_t status;  // HC_WIN_*
     uint32_t hasN;
+    uint32_t pos;     // start of the window in A (xpos = start of A's strand slot + pos)
+    uint32_t a_read;  // 1 / 2: the A side belongs to read 1 / read 2 of the candidate
 };
 
 struct CandSetup {
@@ -44,14 +46,16 @@ struct CandSetup {
     uint32_t err;
 };
 
-__device__ __forceinline__ hc_candidate load_candidate(const hc_kparams& P, u64 i) {
+__device__ __forceinline__ hc_candidate load_candidate(const hc_kparams& P, u64 i, uint32_t* anchor_read = nullptr) {
     hc_candidate c;
+    if (anchor_read) *anchor_read = 0u;   // 1 / 2: the run's shared read is ID1 / ID2 (run-encoded records only)
     if (P.cand_compact == 3u) {   // hc_candidate_entry: 8 bytes, the other read comes from the run the candidate lies in
         const uint2 e = __ldg(reinterpret_cast<const uint2*>(P.cand) + i);
         uint32_t r = __ldg(P.tile_run + (i >> 5));
         while ((uint32_t)i >= __ldg(P.run_start + r + 1)) r++;     // runs are rarely shorter than a tile
         const uint32_t anchor = __ldg(P.run_anchor + r), other = e.x & 0x7fffffffu;
         const bool anchor_is_2 = (e.x >> 31) != 0u;
+        if (anchor_read) *anchor_read = anchor_is_2 ? 2u : 1u;
         c.idx1 = anchor_is_2 ? other : anchor;
         c.idx2 = anchor_is_2 ? anchor : other;
         const uint32_t w = e.y;
@@ -99,6 +103,7 @@ __device__ __forceinline__ void make_window(const hc_kparams& P, uint32_t rawA, 
     w.xpos = 0;
     w.ypos16 = 0;
     w.hasN = 0;
+    w.pos = pos;
     if (pos >= lenA) { w.status = HC_WIN_POS_OOR; return; }
     if (lenA < P.min_read_len || lenB < P.min_read_len) { w.status = HC_WIN_SHORT; return; }
     const u64 sa = 16ull * slotA + (rcA ? hc_slot_size(lenA) : 0u);
@@ -127,6 +132,7 @@ __device__ __forceinline__ void setup_windows(const hc_kparams& P, const hc_cand
     s.two = (p1 | p2) ? 1u : 0u;
     s.err = 0;
     s.w[1].L = 0; s.w[1].xpos = 0; s.w[1].ypos16 = 0; s.w[1].hasN = 0; s.w[1].status = HC_WIN_UNUSED;
+    s.w[1].pos = 0; s.w[0].a_read = 1u; s.w[1].a_read = 1u;
     if (p1 && p2) { if (c.ord != '1' && c.ord != '2') s.err = 1; }            // assert :369
     else if (P.n_single == 0) s.err = 1;                                        // :197, "Read types not recognized" :381
     make_window(P, f1 ? r1.w : r1.z, f1 ? r1.y : r1.x, rc1, f2 ? r2.w : r2.z, f2 ? r2.y : r2.x, rc2, c.pos1, s.w[0]);
@@ -136,6 +142,7 @@ __device__ __forceinline__ void setup_windows(const hc_kparams& P, const hc_cand
         const bool swapped = p1 && (!p2 || c.ord == '2');
         if (swapped) make_window(P, rb, sb, rc2, ra, sa, rc1, c.pos2, s.w[1]);
         else make_window(P, ra, sa, rc1, rb, sb, rc2, c.pos2, s.w[1]);
+        s.w[1].a_read = swapped ? 2u : 1u;
     }
     if (s.err) { s.w[0].L = s.w[1].L = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED; }
 }
@@ -159,6 +166,7 @@ __device__ __forceinline__ bool load_and_setup(const hc_kparams& P, const hc_can
         s.err = 1; s.two = 0;
         s.w[0].L = s.w[1].L = 0; s.w[0].xpos = s.w[1].xpos = 0; s.w[0].ypos16 = s.w[1].ypos16 = 0;
         s.w[0].hasN = s.w[1].hasN = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED;
+        s.w[0].pos = s.w[1].pos = 0; s.w[0].a_read = s.w[1].a_read = 1u;
         r1 = r2 = make_uint4(0, 0, 0, 0);
         return false;
     }
@@ -521,15 +529,195 @@ __device__ __noinline__ void write_per_cand(const hc_kparams& P, u64 i, double s
     P.per_cand[i] = r;
 }
 
+// ---- anchor walk (packed layout) ---------------------------------------------------------------------
+// An overlaps file lists the overlaps of one read one after the other, so the 32 candidates of a tile share a read --
+// the ANCHOR -- or a few of them.  The lanes (= candidates) then walk the anchor's sequence together, 32 positions per
+// step: every lane looks at the SAME anchor position at the same time, so all table lookups of one instruction fall into
+// one table row (row = anchor code) and distinct columns are distinct shared-memory banks -- no bank conflicts, where the
+// lane-chunk scheme below pays 2.9 wavefronts per lookup -- and what depends on the anchor only (row offsets, base bits)
+// is prepared once per tile in shared memory instead of once per lane and word.  Each lane streams its own other read
+// through registers (one 256-bit load per step, re-aligned to the anchor's coordinates).  The table is symmetric
+// (hc_tables.cpp), so it does not matter whether the anchor is the A or the B side of a window.
+// Windows the walk does not take (N in either read, more anchors in the tile than the staging area holds, long windows)
+// go through the lane-chunk rounds; sums are integers, so which path scored a window does not show in the result.
+#ifndef HC_AS_STAGE_WORDS
+#define HC_AS_STAGE_WORDS 256u     // staged anchor words per warp and window pass, 16 bytes each (the part[] area of the scratch)
+#endif
+#define HC_AS_MAXBLK 16u           // windows that end beyond 512 anchor positions are left to the lane-chunk rounds
+
+// staged entry of one anchor word (4 positions): .x/.y = table row offsets (bytes) of positions 0,2 / 1,3 in 16-bit halves,
+// .z = the word's base bits (0xc0 of every byte), .w = .z >> 8
+__device__ __forceinline__ uint4 as_stage_entry(uint32_t aw) {
+    uint4 e;
+    e.x = (aw & 0x003f003fu) << 10;
+    e.y = ((aw >> 8) & 0x003f003fu) << 10;
+    e.z = aw & 0xc0c0c0c0u;
+    e.w = e.z >> 8;
+    return e;
+}
+
+// (a ^ b) & c as one LOP3 the compiler does not take apart again
+__device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t lds_byteoff(const unsigned char* base, uint32_t off) {
+    return *reinterpret_cast<const uint32_t*>(base + off);
+}
+
+// One step: the lane's other-read bytes under anchor positions [32k, 32k+32) are the 32 bytes at byte offset `off` of
+// S = {lo[8], hi[8]}.  Adds the fixed-point sum to acc and ORs the base-difference bits into mE (words 0,2,4,6) / mO.
+template <bool HAS_VOID>
+__device__ __forceinline__ void as_block(const unsigned char* __restrict__ TA, const uint4* __restrict__ stg, const uint32_t* lo,
+                                         const uint32_t* hi, uint32_t off, uint32_t& acc, uint32_t& orv, uint32_t& mE,
+                                         uint32_t& mO) {
+    const bool s4 = (off & 16u) != 0, s2 = (off & 8u) != 0, s1 = (off & 4u) != 0;
+    uint32_t V2[12], V1[10], V[9];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint32_t a = i < 8 ? lo[i] : hi[i - 8];
+        const uint32_t b = i + 4 < 8 ? lo[i + 4] : hi[i - 4];
+        V2[i] = s4 ? b : a;
+    }
+#pragma unroll
+    for (int i = 0; i < 10; i++) V1[i] = s2 ? V2[i + 2] : V2[i];
+#pragma unroll
+    for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
+    const uint32_t sh = (off & 3u) * 8u;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t wo = __funnelshift_r(V[j], V[j + 1], sh);
+        const uint4 st = stg[j];
+        const uint32_t X = wo ^ st.z;                               // code of the other read | base difference << 6, per byte
+        // byte offsets into the anchor rows: (X & 0x00ff00ff) * 4 + row offsets, positions 0,2 / 1,3 -- one LOP3 + one LEA each
+        const uint32_t E2 = xor_and(wo, st.z, 0x00ff00ffu) * 4u + st.x;
+        const uint32_t O2 = xor_and(wo >> 8, st.w, 0x00ff00ffu) * 4u + st.y;
+        const uint32_t t0 = lds_byteoff(TA, E2 & 0xffffu);
+        const uint32_t t1 = lds_byteoff(TA, O2 & 0xffffu);
+        const uint32_t t2 = lds_byteoff(TA, E2 >> 16);
+        const uint32_t t3 = lds_byteoff(TA, O2 >> 16);
+        acc += (t0 + t1) + (t2 + t3);
+        if (HAS_VOID) orv |= (t0 | t1) | (t2 | t3);
+        if (j & 1) mO |= (X >> (j - 1)) & (0xc0c0c0c0u >> (j - 1));
+        else mE |= (X >> j) & (0xc0c0c0c0u >> j);
+    }
+}
+
+// Mask of the positions < n of a step in the bit order as_block leaves the mismatch flags in: position p = 4j + t sits on
+// bit 8t + 7 - j of the even-word flags (j even) resp. bit 8t + 8 - j of the odd-word flags.
+HC_HD uint2 hc_as_vmask(uint32_t n) {
+    uint2 m;
+    m.x = 0; m.y = 0;
+    for (uint32_t p = 0; p < n && p < 32u; p++) {
+        const uint32_t j = p >> 2, t = p & 3u;
+        if (j & 1u) m.y |= 1u << (8u * t + 8u - j);
+        else m.x |= 1u << (8u * t + 7u - j);
+    }
+    return m;
+}
+
+// The windows `w` of the tile's candidates.  elig: this lane has such a window and the walk may take it.  Returns true
+// if the lane's window was scored (out holds its sums).
+//   akey    store position of the first base of the anchor's sequence (strand slot): lanes with equal akey share the anchor
+//   ostart  store position of the first base of the other sequence
+//   delta   other index = anchor index - delta  (delta = +pos if the anchor is the A side, -pos if it is the B side)
+//   [jb,je) the window in anchor coordinates
+template <bool HAS_VOID>
+__device__ __forceinline__ bool as_window(const hc_kparams& P, const unsigned char* __restrict__ TA, const uint2* __restrict__ VMT,
+                                          uint4* stg, int lane, bool elig, u64 akey, u64 ostart, int delta, uint32_t jb,
+                                          uint32_t je, WinAcc& out) {
+    const uint32_t FULL = 0xffffffffu;
+    // ---- groups of lanes with the same anchor sequence; the staging area is dealt out in lane order
+    const u64 key = elig ? akey : (~0ull - (u64)lane);
+    const uint32_t mset = __match_any_sync(FULL, key);
+    const int leader = __ffs(mset) - 1;
+    const uint32_t nblk = elig ? ((je + 31u) >> 5) : 0u;
+    const uint32_t gblk = __reduce_max_sync(mset, nblk);
+    const bool is_leader = elig && lane == leader;
+    const uint32_t words = is_leader ? gblk * 8u : 0u;
+    const uint32_t offs = warp_incl_scan(words, lane) - words;
+    const bool fits = is_leader && offs + words <= HC_AS_STAGE_WORDS;
+    const uint32_t goff = __shfl_sync(FULL, offs, leader);
+    const bool handled = elig && __shfl_sync(FULL, (int)fits, leader);
+    uint32_t todo = __ballot_sync(FULL, fits);
+    // a walk keeps the whole warp busy for as long as its longest window: not worth it for a few lanes (lists without runs)
+    if ((uint32_t)__popc(__ballot_sync(FULL, handled)) < P.anchor_walk) return false;
+    while (todo) {
+        const int L = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t klo = __shfl_sync(FULL, (uint32_t)key, L), khi = __shfl_sync(FULL, (uint32_t)(key >> 32), L);
+        const uint32_t gw = __shfl_sync(FULL, words, L), go = __shfl_sync(FULL, offs, L);
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(P.pk + (((u64)khi << 32) | klo));
+        for (uint32_t i = lane; i < gw; i += 32) stg[go + i] = as_stage_entry(__ldg(ap + i));
+    }
+    __syncwarp();
+    // ---- the walk
+    const int kb = handled ? (int)(jb >> 5) : 0x7fffffff, ke = handled ? (int)((je - 1u) >> 5) : -1;
+    const int kmin = __reduce_min_sync(FULL, kb), kmax = __reduce_max_sync(FULL, ke);
+    const long long o0 = (long long)ostart - (long long)delta;      // other byte under anchor position 0
+    const uint32_t off = (uint32_t)o0 & 31u;
+    const uint8_t* ob = P.pk + (o0 - (long long)off);               // aligned block b = ob + 32 b
+    const int bb = handled ? (int)((off + jb) >> 5) : 0x7fffffff, be = handled ? (int)((off + je - 1u) >> 5) : -1;
+    const uint4* mystg = stg + goff;
+    uint32_t b0[8], b1[8], b2[8];       // three block buffers in rotating roles (this step's low half, its high half, the next load)
+#pragma unroll
+    for (int i = 0; i < 8; i++) { b0[i] = 0u; b1[i] = 0u; }
+    if (kmin >= bb && kmin <= be) ldg256(ob + 32ll * kmin, b0);
+    if (kmin + 1 >= bb && kmin + 1 <= be) ldg256(ob + 32ll * (kmin + 1), b1);
+    u64 S = 0;
+    uint32_t mm = 0, vd = 0;
+    // one step: block k + 2 is requested (it is consumed by the next step), then anchor positions [32k, 32k+32) are scored
+    // from lo = block k and hi = block k + 1.  A block outside [bb, be] is all zeros: it lies outside the window.
+#define HC_AS_STEP(LO, HI, NX)                                                                                        \
+    {                                                                                                                 \
+        _Pragma("unroll") for (int i = 0; i < 8; i++) NX[i] = 0u;                                                     \
+        if (k + 2 >= bb && k + 2 <= be) ldg256(ob + 32ll * (k + 2), NX);                                              \
+        if (k >= kb && k <= ke) {                                                                                     \
+            uint32_t acc = 0, orv = 0, mE = 0, mO = 0;                                                                \
+            as_block<HAS_VOID>(TA, mystg + 8 * k, LO, HI, off, acc, orv, mE, mO);                                     \
+            S += acc;                                                                                                 \
+            const int k32 = 32 * k;                                                                                   \
+            const uint32_t s0 = (uint32_t)max((int)jb - k32, 0), e0 = (uint32_t)min((int)je - k32, 32);               \
+            const uint2 vs = VMT[s0], ve = VMT[e0];                                                                   \
+            mE = (mE | (mE << 1)) & 0xaaaaaaaau & ve.x & ~vs.x;                                                       \
+            mO = (mO | (mO << 1)) & 0xaaaaaaaau & ve.y & ~vs.y;                                                       \
+            mm += __popc(mE) + __popc(mO);                                                                            \
+            if (HAS_VOID) vd |= (orv & HC_VOID_BIT) ? 1u : 0u;                                                        \
+        }                                                                                                             \
+    }
+    for (int k = kmin;;) {
+        HC_AS_STEP(b0, b1, b2)
+        if (++k > kmax) break;
+        HC_AS_STEP(b1, b2, b0)
+        if (++k > kmax) break;
+        HC_AS_STEP(b2, b0, b1)
+        if (++k > kmax) break;
+    }
+#undef HC_AS_STEP
+    __syncwarp();
+    if (handled) { out.S = S; out.mm = mm; out.nn = 0; out.vd = vd; }
+    return handled;
+}
+
 template <bool HAS_VOID, bool PACKED>
 __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kernel(const hc_kparams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* T = reinterpret_cast<uint32_t*>(smem);
-    const uint32_t tbl_entries = (P.ncodes + 1u) * 256u + HC_VM_WORDS;   // score table, then the tail masks
-    uint32_t* VM = T + (tbl_entries - HC_VM_WORDS);
-    for (uint32_t i = threadIdx.x; i < tbl_entries - HC_VM_WORDS; i += blockDim.x) T[i] = P.fx_table[i];
+    const uint32_t ntab = (P.ncodes + 1u) * 256u;                     // score table, then the tail masks,
+    uint32_t* VM = T + ntab;
+    uint32_t* TAw = VM + HC_VM_WORDS;                                  // then (packed layout) the anchor-walk table and its masks
+    uint2* VMT = reinterpret_cast<uint2*>(TAw + (PACKED ? ntab : 0u));
+    const uint32_t tbl_entries = ntab + HC_VM_WORDS + (PACKED ? ntab + HC_AS_VMT_WORDS : 0u);
+    for (uint32_t i = threadIdx.x; i < ntab; i += blockDim.x) T[i] = P.fx_table[i];
     if (threadIdx.x < HC_VM_WORDS) VM[threadIdx.x] = hc_packed_vmask(threadIdx.x);
+    if (PACKED) {
+        for (uint32_t i = threadIdx.x; i < ntab; i += blockDim.x) TAw[i] = P.fx_table[ntab + i];
+        if (threadIdx.x < 33u) VMT[threadIdx.x] = hc_as_vmask(threadIdx.x);
+    }
     __syncthreads();
+    const unsigned char* TA = reinterpret_cast<const unsigned char*>(TAw);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -556,18 +744,47 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
         s.err = 0; s.two = 0;
         s.w[0].L = s.w[1].L = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED;
         s.w[0].xpos = s.w[1].xpos = 0; s.w[0].ypos16 = s.w[1].ypos16 = 0; s.w[0].hasN = s.w[1].hasN = 0;
+        s.w[0].pos = s.w[1].pos = 0; s.w[0].a_read = s.w[1].a_read = 1u;
+        uint32_t anch = 0;
         if (valid) {
-            c = load_candidate(P, i);
+            c = load_candidate(P, i, &anch);
             load_and_setup(P, c, s, r1, r2);
 #ifndef HC_NO_PREFETCH
             prefetch_window(P, s.w[0]);
             prefetch_window(P, s.w[1]);
 #endif
         }
-        const uint32_t c0 = (s.w[0].L + 31u) >> 5, c1 = (s.w[1].L + 31u) >> 5;
-        const uint32_t ct = c0 + c1;
         WinAcc acc[2];
         acc[0].S = acc[1].S = 0; acc[0].mm = acc[1].mm = 0; acc[0].nn = acc[1].nn = 0; acc[0].vd = acc[1].vd = 0;
+        uint32_t c0 = (s.w[0].L + 31u) >> 5, c1 = (s.w[1].L + 31u) >> 5;     // lane-chunks left to the rounds below
+
+        // ---- anchor walk: windows of candidates that share a read with their neighbours (packed layout)
+        if (PACKED && P.anchor_walk) {
+            const uint32_t id1 = valid ? c.idx1 : 0xffffffffu, id2 = valid ? c.idx2 : 0xfffffffeu;
+            if (anch == 0u) {   // records without run information: the read shared with the neighbouring candidates, else the smaller index
+                const uint32_t p1 = __shfl_up_sync(0xffffffffu, id1, 1), p2 = __shfl_up_sync(0xffffffffu, id2, 1);
+                const uint32_t n1 = __shfl_down_sync(0xffffffffu, id1, 1), n2 = __shfl_down_sync(0xffffffffu, id2, 1);
+                const int up = lane > 0, dn = lane < 31;
+                const int sc1 = (up && (id1 == p1 || id1 == p2)) + (dn && (id1 == n1 || id1 == n2));
+                const int sc2 = (up && (id2 == p1 || id2 == p2)) + (dn && (id2 == n1 || id2 == n2));
+                anch = sc1 > sc2 ? 1u : (sc2 > sc1 ? 2u : (id1 <= id2 ? 1u : 2u));
+            }
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const Win& W = s.w[w];
+                const bool a_side = W.a_read == anch;                          // the anchor is the window's A side
+                const u64 sa = W.xpos - W.pos, sb = 16ull * W.ypos16;
+                const uint32_t jb = a_side ? W.pos : 0u, je = jb + W.L;
+                const bool elig = valid && !s.err && W.status == HC_WIN_SCORED && W.L > 0u && !W.hasN && je <= 32u * HC_AS_MAXBLK;
+                if (__any_sync(0xffffffffu, elig)) {
+                    if (as_window<HAS_VOID>(P, TA, VMT, reinterpret_cast<uint4*>(scratch), lane, elig, a_side ? sa : sb, a_side ? sb : sa,
+                                            a_side ? (int)W.pos : -(int)W.pos, jb, je, acc[w])) {
+                        if (w == 0) c0 = 0u; else c1 = 0u;
+                    }
+                }
+            }
+        }
+        const uint32_t ct = c0 + c1;
 
         // ---- big candidates (>= 64 lane-chunks): the whole warp walks one window at a time
         uint32_t bigmask = __ballot_sync(0xffffffffu, ct >= HC_BIG_CHUNKS);
@@ -652,10 +869,10 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
                 u64 S = 0;
                 uint32_t pk = 0;
                 for (uint32_t k = 0; k < c0; k++) { const uint2 e = part[start0 + k]; S += e.x; pk += e.y; }
-                acc[0].S = S; acc[0].mm = pk & 0xfffu; acc[0].nn = (pk >> 12) & 0xfffu; acc[0].vd = pk >> 24;
+                if (c0) { acc[0].S = S; acc[0].mm = pk & 0xfffu; acc[0].nn = (pk >> 12) & 0xfffu; acc[0].vd = pk >> 24; }
                 S = 0; pk = 0;
                 for (uint32_t k = 0; k < c1; k++) { const uint2 e = part[start1 + k]; S += e.x; pk += e.y; }
-                acc[1].S = S; acc[1].mm = pk & 0xfffu; acc[1].nn = (pk >> 12) & 0xfffu; acc[1].vd = pk >> 24;
+                if (c1) { acc[1].S = S; acc[1].mm = pk & 0xfffu; acc[1].nn = (pk >> 12) & 0xfffu; acc[1].vd = pk >> 24; }
             }
             __syncwarp();
             pending &= ~take;
@@ -685,6 +902,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
                         const uint32_t tl = s.w[w].L - acc[w].nn;
                         if (acc[w].vd) {
                             status = HC_WIN_VOID;               // :125-127, mismatch_rate stays 1.0
+                            if (P.void_exact) flag = true;      // void in one order of the quality pair only: the reference's order decides
                         } else if (tl == 0) {
                             status = HC_WIN_EMPTY;              // :129-131
                         } else {
@@ -1116,15 +1334,15 @@ __global__ void hc_compact_advance(unsigned long long* run, const unsigned long 
 }  // namespace
 
 // ---- launchers ----------------------------------------------------------------------------------------
-cudaError_t hc_score_occupancy(uint32_t ncodes, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg) {
-    const size_t table = (size_t)(ncodes + 1u) * 1024u + HC_VM_WORDS * 4u;
+cudaError_t hc_score_occupancy(uint32_t ncodes, int packed, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg) {
+    // score table (+ the anchor-walk table and its masks in the packed layout) + the tail masks, per CTA
+    const size_t table = (size_t)(ncodes + 1u) * 1024u * (packed ? 2u : 1u) + HC_VM_WORDS * 4u + (packed ? HC_AS_VMT_WORDS * 4u : 0u);
     int best_warps = 0, best_nw = 0, best_ctas = 0;
-    const int options[2] = {HC_WARPS_MAX, 8};
-    for (int o = 0; o < 2; o++) {
-        const int nw = options[o];
+    for (int nw = HC_WARPS_MAX; nw >= 4; nw -= 4) {     // the tables are per CTA: prefer few large CTAs
         const size_t per_cta = table + (size_t)nw * HC_WARP_SCRATCH + 1024u;   // +1 KB the driver reserves per CTA
         if (per_cta > 227u * 1024u) continue;
         int ctas = (int)(smem_per_sm / per_cta);
+        if (ctas > HC_MIN_CTAS) ctas = HC_MIN_CTAS;                            // what the register allocation allows
         if (ctas * nw * 32 > 2048) ctas = 2048 / (nw * 32);
         if (ctas < 1) continue;
         if (ctas * nw > best_warps) { best_warps = ctas * nw; best_nw = nw; best_ctas = ctas; }
@@ -1148,7 +1366,7 @@ cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaS
 cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint32_t* tile_run, cudaStream_t st) {
     if (n_runs == 0) return cudaSuccess;
     const unsigned blocks = (n_runs + 255u) / 256u;
-    hc_tile_runs<<<blocks < 148u * 8u ? blocks : 148u * 8u, 256, 0, st>>>(run_start, n_runs, tile_run);
+    hc_tile_runs<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>(run_start, n_runs, tile_run);
     return cudaGetLastError();
 }
 

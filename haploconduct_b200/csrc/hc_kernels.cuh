@@ -8,10 +8,10 @@
 #include "hc_layout.h"
 
 #ifndef HC_WARPS_MAX
-#define HC_WARPS_MAX 12
+#define HC_WARPS_MAX 24          // warps per CTA (one CTA per SM: the score tables are per CTA)
 #endif
 #ifndef HC_MIN_CTAS
-#define HC_MIN_CTAS 2             // resident CTAs per SM the register allocation aims at
+#define HC_MIN_CTAS 1             // resident CTAs per SM the register allocation aims at
 #endif
 #define HC_LANE_CHUNK 32u        // positions one lane handles per step (two 16-position halves)
 #ifndef HC_PARTMAX
@@ -20,6 +20,7 @@
 //                            // lane-chunk partials per warp round (x 8 B = 4 KB of shared memory)
 #define HC_BIG_CHUNKS 64u        // candidates with >= this many lane-chunks are scored warp-cooperatively
 #define HC_WINSLOTS 64u          // 2 windows x 32 candidates
+#define HC_AS_VMT_WORDS 72u      // anchor walk: 33 x 2 words of position masks (hc_as_vmask), padded
 #define HC_VM_WORDS 64u          // tail-mask table of the packed layout (33 used), kept behind the score table
 // per-warp scratch: partials + window descriptors (16 B + 8 B per slot) + head bitmap
 #define HC_WARP_SCRATCH (HC_PARTMAX * 8u + HC_WINSLOTS * 16u + HC_WINSLOTS * 8u + (HC_PARTMAX / 32u) * 4u)
@@ -76,6 +77,9 @@ struct hc_kparams {
     uint32_t never_edge;        // t_edge > 0: a mean (<= 0) can never reach it
     uint32_t never_ov;
     uint32_t exact_edges;       // HC_FLAG_EXACT_EDGE_SCORES
+    uint32_t anchor_walk;       // packed layout: candidates that share a read walk it together (fx_table holds both tables);
+                                // 0 = off, else the least number of lanes of a tile a walk is started for
+    uint32_t void_exact;        // hc_tables::void_asymmetric: void hits are decided by the reference-order pass
 };
 
 enum {
@@ -103,7 +107,7 @@ cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint
 cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge,
                               uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, unsigned long long* d_run,
                               cudaStream_t st);
-cudaError_t hc_score_occupancy(uint32_t ncodes, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg);
+cudaError_t hc_score_occupancy(uint32_t ncodes, int packed, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg);
 uint32_t hc_compact_blocks(uint64_t n);
 
 #endif

@@ -26,17 +26,17 @@ __device__ __forceinline__ int dev_base_code(unsigned char c) {
 
 __device__ __forceinline__ unsigned char dev_upper(unsigned char c) { return (c >= 'a' && c <= 'z') ? (unsigned char)(c - 32) : c; }
 
-// seen[8]: bitmap of the quality characters present; err: 1 invalid nucleotide, 2 quality out of range (max wins nothing: any)
+// hist[128]: how often every quality character occurs (quality codes are ranked by frequency, see hc_layout.h);
+// err: 1 invalid nucleotide, 2 quality out of range
 __global__ void __launch_bounds__(256) pack_validate(const uint8_t* __restrict__ text, const hc_pack_src* __restrict__ src,
-                                                     const hc_rdesc* __restrict__ rd, u64 n_reads, u64 n_upper, uint32_t* seen,
-                                                     uint32_t* err) {
-    __shared__ uint32_t sseen[8];
-    if (threadIdx.x < 8) sseen[threadIdx.x] = 0;
+                                                     const hc_rdesc* __restrict__ rd, u64 n_reads, u64 n_upper,
+                                                     unsigned long long* hist, uint32_t* err) {
+    __shared__ uint32_t shist[128];
+    if (threadIdx.x < 128) shist[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const u64 gw = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((u64)gridDim.x * blockDim.x) >> 5;
     uint32_t lerr = 0;
-    uint32_t mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (u64 t = gw; t < 2 * n_reads; t += nw) {
         const u64 r = t >> 1;
         const int m = (int)(t & 1);
@@ -50,13 +50,11 @@ __global__ void __launch_bounds__(256) pack_validate(const uint8_t* __restrict__
             const unsigned char qc = q[i];
             if (dev_base_code(bc) < 0) lerr |= 1u;
             if (qc < 33 || qc > 33 + 93) lerr |= 2u;
-            mine[qc >> 5] |= 1u << (qc & 31);
+            else atomicAdd(&shist[qc], 1u);          // a block sees far fewer than 2^32 characters between two flushes
         }
     }
-#pragma unroll
-    for (int k = 0; k < 8; k++) if (mine[k]) atomicOr(&sseen[k], mine[k]);
     __syncthreads();
-    if (threadIdx.x < 8 && sseen[threadIdx.x]) atomicOr(&seen[threadIdx.x], sseen[threadIdx.x]);
+    if (threadIdx.x < 128 && shist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)shist[threadIdx.x]);
     if (lerr) atomicOr(err, lerr);
 }
 
@@ -150,10 +148,10 @@ __global__ void __launch_bounds__(256) fq_records(const char* __restrict__ text,
 }  // namespace
 
 cudaError_t hc_pack_validate_launch(const uint8_t* d_text, const hc_pack_src* d_src, const hc_rdesc* d_rd, uint64_t n_reads,
-                                    uint64_t n_upper, uint32_t* d_seen, uint32_t* d_err, cudaStream_t stream) {
+                                    uint64_t n_upper, unsigned long long* d_hist, uint32_t* d_err, cudaStream_t stream) {
     const u64 warps = 2 * n_reads;
     const unsigned blocks = (unsigned)std::min<u64>((warps + 7) / 8, 148ull * 32);
-    pack_validate<<<blocks ? blocks : 1, 256, 0, stream>>>(d_text, d_src, d_rd, n_reads, n_upper, d_seen, d_err);
+    pack_validate<<<blocks ? blocks : 1, 256, 0, stream>>>(d_text, d_src, d_rd, n_reads, n_upper, d_hist, d_err);
     return cudaGetLastError();
 }
 

@@ -9,10 +9,10 @@ struct hc_pack_src {      // per (read, mate): where its bases and its quality c
     unsigned long long boff, qoff;
 };
 
-// quality alphabet (256-bit map in d_seen[8]) and validity (d_err: bit 0 invalid nucleotide, bit 1 quality out of range)
-// of all reads; the first n_upper reads are upper-cased first (singles, src/FastqStorage.cpp:123)
+// quality alphabet (d_hist[128]: occurrences of every quality character) and validity (d_err: bit 0 invalid nucleotide,
+// bit 1 quality out of range) of all reads; the first n_upper reads are upper-cased first (singles, src/FastqStorage.cpp:123)
 cudaError_t hc_pack_validate_launch(const uint8_t* d_text, const hc_pack_src* d_src, const hc_rdesc* d_rd, uint64_t n_reads,
-                                    uint64_t n_upper, uint32_t* d_seen, uint32_t* d_err, cudaStream_t stream);
+                                    uint64_t n_upper, unsigned long long* d_hist, uint32_t* d_err, cudaStream_t stream);
 // both strands of every read into the (zeroed) planes; sets HC_HASN_BIT in d_rd
 cudaError_t hc_pack_write_launch(const uint8_t* d_text, const hc_pack_src* d_src, hc_rdesc* d_rd, uint64_t n_reads, uint64_t n_upper,
                                  const uint8_t* d_q2code, int packed, uint8_t* qplane, uint32_t* base2, uint32_t* nmask,

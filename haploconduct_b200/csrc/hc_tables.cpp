@@ -17,6 +17,17 @@
 
 double hc_tables_phred_to_prob(int phred) { return pow(10, -phred / 10.0); }
 
+// fixed-point addend of one ordered pair of codes; *is_void when p < ps.mismatch (:49-51)
+static double pair_log(int qa, int qb, int mm, double mismatch_param, bool* is_void) {
+    double p1 = hc_tables_phred_to_prob(qa);
+    double p2 = hc_tables_phred_to_prob(qb);
+    double p;
+    if (!mm) p = (1 - p1) * (1 - p2) + (p1 * p2) / 3.0;
+    else p = p1 * (1 - p2) / 3.0 + p2 * (1 - p1) / 3.0 + (2 / 9.0) * p1 * p2;
+    *is_void = p < mismatch_param;
+    return *is_void ? 2.0 : log(p);   // sentinel > 0: "unacceptable mismatch", the whole overlap is void
+}
+
 void hc_build_tables(const int* code_to_q, int ncodes, double mismatch_param, hc_tables* out) {
     const int n1 = ncodes + 1;
     out->ncodes = ncodes;
@@ -24,32 +35,46 @@ void hc_build_tables(const int* code_to_q, int ncodes, double mismatch_param, hc
     out->fx.assign((size_t)n1 * 256, 0u);
     const bool packed = ncodes <= HC_PACKED_MAX_CODES;
     out->fx_packed.assign(packed ? (size_t)n1 * 256 : 0, 0u);
+    out->fx_anchor.assign(packed ? (size_t)n1 * 256 : 0, 0u);
     out->has_void = false;
+    out->void_asymmetric = false;
     for (int ca = 1; ca <= ncodes; ca++) {
         for (int cb = 1; cb <= ncodes; cb++) {
-            double p1 = hc_tables_phred_to_prob(code_to_q[ca]);
-            double p2 = hc_tables_phred_to_prob(code_to_q[cb]);
             for (int mm = 0; mm < 2; mm++) {
-                double p;
-                if (!mm) p = (1 - p1) * (1 - p2) + (p1 * p2) / 3.0;
-                else p = p1 * (1 - p2) / 3.0 + p2 * (1 - p1) / 3.0 + (2 / 9.0) * p1 * p2;
-                double lp;
+                bool v_ab, v_ba;
+                const double lp = pair_log(code_to_q[ca], code_to_q[cb], mm, mismatch_param, &v_ab);
+                // The fixed-point table is SYMMETRIC: both orders take the value of (min code, max code).  The reference's
+                // expression :44 is not bit-symmetric, but the two orders differ by a few ulp of a double, far below the
+                // 2^-23 rounding of the table (HC_FX_MARGIN keeps 1e-9 of slack for it).  A void decision that differs
+                // between the two orders (ps.mismatch within an ulp of some p) sends void hits to the reference-order pass.
+                const int lo = ca < cb ? ca : cb, hi = ca < cb ? cb : ca;
+                const double lps = pair_log(code_to_q[lo], code_to_q[hi], mm, mismatch_param, &v_ba);
+                bool v_other;
+                pair_log(code_to_q[cb], code_to_q[ca], mm, mismatch_param, &v_other);
+                if (v_ab != v_other) out->void_asymmetric = true;
+                const bool v_any = v_ab || v_other;
                 uint32_t fx;
-                if (p < mismatch_param) {
-                    lp = 2.0;  // sentinel > 0: "unacceptable mismatch", the whole overlap is void
+                if (v_any) {
                     fx = HC_VOID_BIT;
                     out->has_void = true;
                 } else {
-                    lp = log(p);
-                    double v = -lp * HC_FX_SCALE;
+                    double v = -lps * HC_FX_SCALE;
                     fx = (uint32_t)llround(v);
                     if (fx >= HC_VOID_BIT) fx = HC_VOID_BIT - 1;  // cannot happen for Q in [0,93]
                 }
+                (void)v_ba;
                 out->dbl[hc_dbl_index(ca, cb, mm, n1)] = lp;
                 out->fx[hc_fx_index(ca, cb, mm)] = fx;
                 if (packed) {
-                    if (!mm) out->fx_packed[hc_fx_index_packed(ca, cb, 0)] = fx;
-                    else for (uint32_t bx = 1; bx < 4; bx++) out->fx_packed[hc_fx_index_packed(ca, cb, bx)] = fx;
+                    if (!mm) {
+                        out->fx_packed[hc_fx_index_packed(ca, cb, 0)] = fx;
+                        out->fx_anchor[hc_fx_index_anchor(ca, cb, 0)] = fx;
+                    } else {
+                        for (uint32_t bx = 1; bx < 4; bx++) {
+                            out->fx_packed[hc_fx_index_packed(ca, cb, bx)] = fx;
+                            out->fx_anchor[hc_fx_index_anchor(ca, cb, bx)] = fx;
+                        }
+                    }
                 }
             }
         }
