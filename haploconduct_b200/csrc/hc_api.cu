@@ -49,6 +49,7 @@ struct DevCtx {
     uint32_t* base2 = nullptr;
     uint32_t* nmask = nullptr;
     hc_rdesc* rdesc = nullptr;
+    hc_nlist* nlist = nullptr;   // packed layout: N positions per read
     // tables
     uint32_t* fx_table = nullptr;
     double* dbl_table = nullptr;
@@ -119,7 +120,7 @@ namespace {
 void free_ctx(DevCtx& d) {
     if (d.device < 0) return;
     cudaSetDevice(d.device);
-    cudaFree(d.pk_alloc); cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc);
+    cudaFree(d.pk_alloc); cudaFree(d.qual); cudaFree(d.base2); cudaFree(d.nmask); cudaFree(d.rdesc); cudaFree(d.nlist);
     cudaFree(d.fx_table); cudaFree(d.dbl_table);
     cudaFree(d.tmp); cudaFree(d.cls); cudaFree(d.flagged); cudaFree(d.blockcounts); cudaFree(d.counters);
     for (int k = 0; k < 2; k++) {
@@ -213,7 +214,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     hc_kparams P;
     memset(&P, 0, sizeof(P));
     P.qual = d.qual; P.base2 = d.base2; P.nmask = d.nmask; P.rdesc = d.rdesc;
-    P.pk = d.pk; P.packed = s->packed ? 1u : 0u;
+    P.pk = d.pk; P.packed = s->packed ? 1u : 0u; P.nlist = d.nlist;
     P.n_reads = (uint32_t)s->n_reads; P.n_single = (uint32_t)s->n_single;
     P.fx_table = d.fx_table; P.dbl_table = d.dbl_table; P.ncodes = (uint32_t)s->ncodes; P.has_void = d.has_void ? 1u : 0u;
     P.cand = d_cand; P.cand_compact = (uint32_t)compact; P.run = d_run; P.n = n; P.tmp = d.tmp; P.cls = d.cls; P.per_cand = d_per_cand; P.flagged = d.flagged;
@@ -342,7 +343,7 @@ int layout_slots(const uint32_t* len2, uint64_t n_reads, std::vector<hc_rdesc>& 
         if (len2[2 * r] == 0) bad = 2;                      // empty sequence (src/FastqStorage.cpp:143-146)
         for (int m = 0; m < 2; m++) {
             const uint32_t len = len2[2 * r + m];
-            if (len > HC_LEN_MASK / 2) bad = 3;
+            if (len > HC_LEN_MAX) bad = 3;
             rd[r].slot16[m] = (uint32_t)(pos >> 4);
             rd[r].len[m] = len;
             if (len) pos += 2ull * hc_slot_size(len);
@@ -392,6 +393,8 @@ cudaError_t alloc_planes(hc_store* s, DevCtx& d, cudaStream_t st) {
         e = cudaMalloc(&d.qual, total + 64);
         if (e == cudaSuccess) e = cudaMemsetAsync(d.qual, 0, total + 64, st);
     }
+    if (e == cudaSuccess && s->packed) e = cudaMalloc(&d.nlist, s->n_reads * sizeof(hc_nlist));
+    if (e == cudaSuccess && s->packed) e = cudaMemsetAsync(d.nlist, 0xff, s->n_reads * sizeof(hc_nlist), st);
     if (e == cudaSuccess && !s->packed) e = cudaMalloc(&d.base2, (total / 16 + 16) * 4);
     if (e == cudaSuccess && !s->packed) e = cudaMalloc(&d.nmask, (total / 32 + 16) * 4);
     if (e == cudaSuccess && !s->packed) e = cudaMemsetAsync(d.base2, 0, (total / 16 + 16) * 4, st);
@@ -454,7 +457,7 @@ int build_store(hc_store* s, std::vector<hc_rdesc>& rd, const uint8_t* d_text, c
         if (e == cudaSuccess) e = alloc_planes(s, d0, d0.stream);
         if (e == cudaSuccess)
             e = hc_pack_write_launch(d_text, d_src, d0.rdesc, n_reads, n_upper, d_lut, s->packed, s->packed ? d0.pk : d0.qual, d0.base2,
-                                     d0.nmask, d0.stream);
+                                     d0.nmask, d0.nlist, d0.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(d0.stream);
     }
     cudaFree(d_flags);
@@ -472,6 +475,7 @@ int build_store(hc_store* s, std::vector<hc_rdesc>& rd, const uint8_t* d_text, c
         if (e == cudaSuccess && !s->packed) e = cudaMemcpyPeer(d.base2, d.device, d0.base2, d0.device, total / 16 * 4);
         if (e == cudaSuccess && !s->packed) e = cudaMemcpyPeer(d.nmask, d.device, d0.nmask, d0.device, total / 32 * 4);
         if (e == cudaSuccess) e = cudaMemcpyPeer(d.rdesc, d.device, d0.rdesc, d0.device, n_reads * sizeof(hc_rdesc));
+        if (e == cudaSuccess && s->packed) e = cudaMemcpyPeer(d.nlist, d.device, d0.nlist, d0.device, n_reads * sizeof(hc_nlist));
     }
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? HC_ERR_NOMEM : HC_ERR_CUDA, std::string("hc_store_create: ") + cudaGetErrorString(e));
     return HC_OK;

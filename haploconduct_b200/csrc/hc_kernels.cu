@@ -35,7 +35,7 @@ struct Win {
     uint32_t ypos16;  // position of B[0] / 16
     uint32_t L;       // window length (src/EdgeCalculator.cpp:88); 0 when not scored
     uint32_t status;  // HC_WIN_*
-    uint32_t hasN;
+    uint32_t hasN;    // bit 0: a read of the window contains N; bit 1: more than hc_nlist holds
     uint32_t pos;     // start of the window in A (xpos = start of A's strand slot + pos)
     uint32_t a_read;  // 1 / 2: the A side belongs to read 1 / read 2 of the candidate
 };
@@ -112,7 +112,7 @@ __device__ __forceinline__ void make_window(const hc_kparams& P, uint32_t rawA, 
     w.ypos16 = (uint32_t)(sb >> 4);
     w.L = min(lenA - pos, lenB);
     w.status = HC_WIN_SCORED;
-    w.hasN = ((rawA | rawB) & HC_HASN_BIT) ? 1u : 0u;
+    w.hasN = (((rawA | rawB) & HC_HASN_BIT) ? 1u : 0u) | (((rawA | rawB) & HC_MANYN_BIT) ? 2u : 0u);   // bit 1: not in hc_nlist
 }
 
 // Window selection of EdgeCalculator::compute_overlap, src/EdgeCalculator.cpp:199-351, written
@@ -629,33 +629,46 @@ __device__ __forceinline__ bool as_window(const hc_kparams& P, const unsigned ch
                                           uint4* stg, int lane, bool elig, u64 akey, u64 ostart, int delta, uint32_t jb,
                                           uint32_t je, WinAcc& out) {
     const uint32_t FULL = 0xffffffffu;
-    // ---- groups of lanes with the same anchor sequence; the staging area is dealt out in lane order
-    const u64 key = elig ? akey : (~0ull - (u64)lane);
-    const uint32_t mset = __match_any_sync(FULL, key);
-    const int leader = __ffs(mset) - 1;
-    const uint32_t nblk = elig ? ((je + 31u) >> 5) : 0u;
-    const uint32_t gblk = __reduce_max_sync(mset, nblk);
-    const bool is_leader = elig && lane == leader;
-    const uint32_t words = is_leader ? gblk * 8u : 0u;
-    const uint32_t offs = warp_incl_scan(words, lane) - words;
-    const bool fits = is_leader && offs + words <= HC_AS_STAGE_WORDS;
-    const uint32_t goff = __shfl_sync(FULL, offs, leader);
-    const bool handled = elig && __shfl_sync(FULL, (int)fits, leader);
-    uint32_t todo = __ballot_sync(FULL, fits);
-    // a walk keeps the whole warp busy for as long as its longest window: not worth it for a few lanes (lists without runs)
-    if ((uint32_t)__popc(__ballot_sync(FULL, handled)) < P.anchor_walk) return false;
-    while (todo) {
-        const int L = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t klo = __shfl_sync(FULL, (uint32_t)key, L), khi = __shfl_sync(FULL, (uint32_t)(key >> 32), L);
-        const uint32_t gw = __shfl_sync(FULL, words, L), go = __shfl_sync(FULL, offs, L);
-        const uint32_t* ap = reinterpret_cast<const uint32_t*>(P.pk + (((u64)khi << 32) | klo));
-        for (uint32_t i = lane; i < gw; i += 32) stg[go + i] = as_stage_entry(__ldg(ap + i));
+    // ---- groups of lanes with the same anchor sequence, in lane order; each group's anchor words are staged while the
+    // staging area lasts (lanes of the groups that do not fit stay with the lane-chunk rounds)
+    {   // lists without runs: do not even start (a group's lanes are neighbours in a list sorted by read)
+        const uint32_t klo = (uint32_t)akey, khi = (uint32_t)(akey >> 32);
+        const uint32_t plo = __shfl_up_sync(FULL, klo, 1), phi = __shfl_up_sync(FULL, khi, 1);
+        const uint32_t nlo = __shfl_down_sync(FULL, klo, 1), nhi = __shfl_down_sync(FULL, khi, 1);
+        const uint32_t pe = __shfl_up_sync(FULL, (uint32_t)elig, 1), ne = __shfl_down_sync(FULL, (uint32_t)elig, 1);
+        const bool adj = elig && ((lane > 0 && pe && plo == klo && phi == khi) || (lane < 31 && ne && nlo == klo && nhi == khi));
+        if ((uint32_t)__popc(__ballot_sync(FULL, adj)) + 1u < P.anchor_walk) return false;
     }
+    const uint32_t nblk = elig ? ((je + 31u) >> 5) : 0u;
+    uint32_t rem = __ballot_sync(FULL, elig), running = 0, goff = 0;
+    bool handled = false;
+    for (int groups = 0; rem != 0u && groups < 8 && running + 8u <= HC_AS_STAGE_WORDS; groups++) {
+        const int L = __ffs(rem) - 1;
+        const uint32_t klo = __shfl_sync(FULL, (uint32_t)akey, L), khi = __shfl_sync(FULL, (uint32_t)(akey >> 32), L);
+        const u64 gkey = ((u64)khi << 32) | klo;
+        const bool member = elig && akey == gkey;
+        rem &= ~__ballot_sync(FULL, member);
+        uint32_t gblk = member ? nblk : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) gblk = max(gblk, __shfl_xor_sync(FULL, gblk, d));
+        const uint32_t words = gblk * 8u;
+        if (running + words > HC_AS_STAGE_WORDS) continue;
+        if (member) { handled = true; goff = running; }
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(P.pk + gkey);
+        for (uint32_t i = lane; i < words; i += 32) stg[running + i] = as_stage_entry(__ldg(ap + i));
+        running += words;
+    }
+    // a walk keeps the whole warp busy for as long as its longest window: not worth it for a few lanes
+    if ((uint32_t)__popc(__ballot_sync(FULL, handled)) < P.anchor_walk) return false;
     __syncwarp();
     // ---- the walk
     const int kb = handled ? (int)(jb >> 5) : 0x7fffffff, ke = handled ? (int)((je - 1u) >> 5) : -1;
-    const int kmin = __reduce_min_sync(FULL, kb), kmax = __reduce_max_sync(FULL, ke);
+    int kmin = kb, kmax = ke;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(FULL, kmin, d));
+        kmax = max(kmax, __shfl_xor_sync(FULL, kmax, d));
+    }
     const long long o0 = (long long)ostart - (long long)delta;      // other byte under anchor position 0
     const uint32_t off = (uint32_t)o0 & 31u;
     const uint8_t* ob = P.pk + (o0 - (long long)off);               // aligned block b = ob + 32 b
@@ -699,6 +712,52 @@ __device__ __forceinline__ bool as_window(const hc_kparams& P, const unsigned ch
     __syncwarp();
     if (handled) { out.S = S; out.mm = mm; out.nn = 0; out.vd = vd; }
     return handled;
+}
+
+// N positions of a window the anchor walk scored without looking for them.  An N is a zero byte: it added nothing to the
+// sum, but it is not a compared position (:35-39,:122-124) and it was flagged as a mismatch iff the base across it is not
+// 'A' (base bits 0).  The window is A[pos..pos+L) over B[0..L); sides as in setup_windows.  Rare path: the candidate and its
+// read descriptors are loaded again rather than kept alive across the walk.
+__device__ __noinline__ void as_fix_n(const hc_kparams& P, u64 i, int w, uint32_t a_read, u64 sa, u64 sb, uint32_t pos, uint32_t L,
+                                      uint32_t& nn_out, uint32_t& mm_fix) {
+    const hc_candidate c = load_candidate(P, i);
+    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx1));
+    const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx2));
+    const int p1 = (r1.w & HC_LEN_MASK) != 0, p2 = (r2.w & HC_LEN_MASK) != 0;
+    const int rc1 = c.ori1 ? 0 : 1, rc2 = c.ori2 ? 0 : 1;
+    const int m1 = w == 0 ? (p1 ? rc1 : 0) : (p1 ? 1 - rc1 : 0);      // mate slot of read 1 / read 2 this window uses
+    const int m2 = w == 0 ? (p2 ? rc2 : 0) : (p2 ? 1 - rc2 : 0);
+    const uint32_t l1 = (m1 ? r1.w : r1.z) & HC_LEN_MASK, l2 = (m2 ? r2.w : r2.z) & HC_LEN_MASK;
+    const bool a1 = a_read == 1u;
+    const uint32_t lenA = a1 ? l1 : l2, lenB = a1 ? l2 : l1;
+    const int rcA = a1 ? rc1 : rc2, rcB = a1 ? rc2 : rc1;
+    const uint2 qA = __ldg(reinterpret_cast<const uint2*>(P.nlist + (a1 ? c.idx1 : c.idx2)));
+    const uint2 qB = __ldg(reinterpret_cast<const uint2*>(P.nlist + (a1 ? c.idx2 : c.idx1)));
+    const uint32_t nA = (a1 ? m1 : m2) ? qA.y : qA.x, nB = (a1 ? m2 : m1) ? qB.y : qB.x;     // two 16-bit positions of the mate used
+    uint32_t nn = 0, fix = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t pf = (nA >> (16 * k)) & 0xffffu;
+        if (pf == 0xffffu) continue;
+        const uint32_t a = rcA ? lenA - 1u - pf : pf;
+        if (a < pos || a - pos >= L) continue;
+        nn++;
+        const uint32_t other = P.pk[sb + (a - pos)];
+        if ((other & 0x3fu) != 0u && (other >> 6) != 0u) fix++;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t pf = (nB >> (16 * k)) & 0xffffu;
+        if (pf == 0xffffu) continue;
+        const uint32_t b = rcB ? lenB - 1u - pf : pf;
+        if (b >= L) continue;
+        const uint32_t other = P.pk[sa + pos + b];
+        if ((other & 0x3fu) == 0u) continue;                            // N on both sides: counted above
+        nn++;
+        if ((other >> 6) != 0u) fix++;
+    }
+    nn_out = nn;
+    mm_fix = fix;
 }
 
 template <bool HAS_VOID, bool PACKED>
@@ -775,11 +834,17 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
                 const bool a_side = W.a_read == anch;                          // the anchor is the window's A side
                 const u64 sa = W.xpos - W.pos, sb = 16ull * W.ypos16;
                 const uint32_t jb = a_side ? W.pos : 0u, je = jb + W.L;
-                const bool elig = valid && !s.err && W.status == HC_WIN_SCORED && W.L > 0u && !W.hasN && je <= 32u * HC_AS_MAXBLK;
+                const bool elig = valid && !s.err && W.status == HC_WIN_SCORED && W.L > 0u && !(W.hasN & 2u) && je <= 32u * HC_AS_MAXBLK;
                 if (__any_sync(0xffffffffu, elig)) {
                     if (as_window<HAS_VOID>(P, TA, VMT, reinterpret_cast<uint4*>(scratch), lane, elig, a_side ? sa : sb, a_side ? sb : sa,
                                             a_side ? (int)W.pos : -(int)W.pos, jb, je, acc[w])) {
                         if (w == 0) c0 = 0u; else c1 = 0u;
+                        if (W.hasN) {
+                            uint32_t nn, fix;
+                            as_fix_n(P, i, w, W.a_read, sa, sb, W.pos, W.L, nn, fix);
+                            acc[w].nn = nn;
+                            acc[w].mm -= fix;
+                        }
                     }
                 }
             }

@@ -44,6 +44,7 @@ struct hc_kparams {
     const uint32_t* nmask;
     const uint8_t* pk;          // packed layout: code | base << 6 per position (qual/base2/nmask are NULL then)
     const hc_rdesc* rdesc;
+    const hc_nlist* nlist;      // packed layout
     uint32_t packed;
     uint32_t n_reads;
     uint32_t n_single;

@@ -34,8 +34,10 @@
 // |mean_fx - mean_ref| <= 2^-23 (table rounding, 0.5 ulp per term) + double-rounding slack
 #define HC_FX_MARGIN (1.1920928955078125e-07 + 1.0e-9)
 #define HC_VOID_BIT 0x08000000u // 2^27 > any real entry (max -log p = 22.6 -> 9.5e7 < 2^27)
-#define HC_LEN_MASK 0x7fffffffu
-#define HC_HASN_BIT 0x80000000u
+#define HC_LEN_MASK 0x3fffffffu  // sequence lengths are below 2^30
+#define HC_LEN_MAX 0x3fffffffu
+#define HC_HASN_BIT 0x80000000u  // the sequence contains an N
+#define HC_MANYN_BIT 0x40000000u // ... more than two of them (or it is too long for 16-bit positions): not in hc_nlist
 
 #if defined(__CUDACC__)
 #define HC_HD __host__ __device__ __forceinline__
@@ -45,7 +47,14 @@
 
 struct hc_rdesc {          // device read descriptor
     uint32_t slot16[2];    // forward-slot start / 16 for mate 0 / 1
-    uint32_t len[2];       // length | HC_HASN_BIT ; len[1] == 0 <=> single-end read
+    uint32_t len[2];       // length | HC_HASN_BIT | HC_MANYN_BIT ; len[1] == 0 <=> single-end read
+};
+
+// Packed layout: where the (at most two) N of a sequence are, forward-strand positions, 0xffff = none.  The anchor walk
+// of hc_score_kernel scores windows without looking for N (an N is a zero byte: it adds nothing) and corrects the
+// compared-length and mismatch counts afterwards from this list.
+struct alignas(8) hc_nlist {
+    uint16_t pos[2][2];    // [mate][k]
 };
 
 HC_HD uint32_t hc_slot_size(uint32_t len) {
