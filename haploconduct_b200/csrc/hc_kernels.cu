@@ -618,35 +618,42 @@ HC_HD uint2 hc_as_vmask(uint32_t n) {
     return m;
 }
 
-// The windows `w` of the tile's candidates.  elig: this lane has such a window and the walk may take it.  Returns true
-// if the lane's window was scored (out holds its sums).
-//   akey    store position of the first base of the anchor's sequence (strand slot): lanes with equal akey share the anchor
-//   ostart  store position of the first base of the other sequence
-//   delta   other index = anchor index - delta  (delta = +pos if the anchor is the A side, -pos if it is the B side)
-//   [jb,je) the window in anchor coordinates
-template <bool HAS_VOID>
-__device__ __forceinline__ bool as_window(const hc_kparams& P, const unsigned char* __restrict__ TA, const uint2* __restrict__ VMT,
-                                          uint4* stg, int lane, bool elig, u64 akey, u64 ostart, int delta, uint32_t jb,
-                                          uint32_t je, WinAcc& out) {
+// One window of one lane in the anchor's coordinates.
+struct AsWin {
+    u64 akey;        // store position of the first base of the anchor's sequence (strand slot): equal for lanes that share it
+    u64 ostart;      // store position of the first base of the other sequence
+    int delta;       // other index = anchor index - delta  (+pos: the anchor is the window's A side, -pos: its B side)
+    uint32_t jb, je; // the window [jb, je) in anchor coordinates
+    bool elig;       // scored window the walk may take (no more N than hc_nlist holds, not beyond HC_AS_MAXBLK blocks)
+};
+
+__device__ __forceinline__ AsWin as_win_of(const Win& W, uint32_t anch, bool lane_ok) {
+    AsWin a;
+    const bool a_side = W.a_read == anch;
+    const u64 sa = W.xpos - W.pos, sb = 16ull * W.ypos16;
+    a.akey = a_side ? sa : sb;
+    a.ostart = a_side ? sb : sa;
+    a.delta = a_side ? (int)W.pos : -(int)W.pos;
+    a.jb = a_side ? W.pos : 0u;
+    a.je = a.jb + W.L;
+    a.elig = lane_ok && W.status == HC_WIN_SCORED && W.L > 0u && !(W.hasN & 2u) && a.je <= 32u * HC_AS_MAXBLK;
+    return a;
+}
+
+// Groups of lanes with the same anchor sequence, in lane order; every group's anchor words are staged behind the
+// `running` entries already there while the staging area lasts (lanes of groups that do not fit stay with the lane-chunk
+// rounds).  Returns whether the walk takes this lane's window; goff = where its group is staged.
+__device__ __forceinline__ bool as_stage(const hc_kparams& P, uint4* stg, int lane, const AsWin& w, uint32_t& running, uint32_t& goff) {
     const uint32_t FULL = 0xffffffffu;
-    // ---- groups of lanes with the same anchor sequence, in lane order; each group's anchor words are staged while the
-    // staging area lasts (lanes of the groups that do not fit stay with the lane-chunk rounds)
-    {   // lists without runs: do not even start (a group's lanes are neighbours in a list sorted by read)
-        const uint32_t klo = (uint32_t)akey, khi = (uint32_t)(akey >> 32);
-        const uint32_t plo = __shfl_up_sync(FULL, klo, 1), phi = __shfl_up_sync(FULL, khi, 1);
-        const uint32_t nlo = __shfl_down_sync(FULL, klo, 1), nhi = __shfl_down_sync(FULL, khi, 1);
-        const uint32_t pe = __shfl_up_sync(FULL, (uint32_t)elig, 1), ne = __shfl_down_sync(FULL, (uint32_t)elig, 1);
-        const bool adj = elig && ((lane > 0 && pe && plo == klo && phi == khi) || (lane < 31 && ne && nlo == klo && nhi == khi));
-        if ((uint32_t)__popc(__ballot_sync(FULL, adj)) + 1u < P.anchor_walk) return false;
-    }
-    const uint32_t nblk = elig ? ((je + 31u) >> 5) : 0u;
-    uint32_t rem = __ballot_sync(FULL, elig), running = 0, goff = 0;
+    const uint32_t nblk = w.elig ? ((w.je + 31u) >> 5) : 0u;
+    uint32_t rem = __ballot_sync(FULL, w.elig);
     bool handled = false;
-    for (int groups = 0; rem != 0u && groups < 8 && running + 8u <= HC_AS_STAGE_WORDS; groups++) {
+    goff = 0;
+    for (int groups = 0; rem != 0u && groups < 6 && running + 8u <= HC_AS_STAGE_WORDS; groups++) {
         const int L = __ffs(rem) - 1;
-        const uint32_t klo = __shfl_sync(FULL, (uint32_t)akey, L), khi = __shfl_sync(FULL, (uint32_t)(akey >> 32), L);
+        const uint32_t klo = __shfl_sync(FULL, (uint32_t)w.akey, L), khi = __shfl_sync(FULL, (uint32_t)(w.akey >> 32), L);
         const u64 gkey = ((u64)khi << 32) | klo;
-        const bool member = elig && akey == gkey;
+        const bool member = w.elig && w.akey == gkey;
         rem &= ~__ballot_sync(FULL, member);
         uint32_t gblk = member ? nblk : 0u;
 #pragma unroll
@@ -659,81 +666,80 @@ __device__ __forceinline__ bool as_window(const hc_kparams& P, const unsigned ch
         running += words;
     }
     // a walk keeps the whole warp busy for as long as its longest window: not worth it for a few lanes
-    if ((uint32_t)__popc(__ballot_sync(FULL, handled)) < P.anchor_walk) return false;
-    __syncwarp();
-    // ---- the walk
-    const int kb = handled ? (int)(jb >> 5) : 0x7fffffff, ke = handled ? (int)((je - 1u) >> 5) : -1;
+    if ((uint32_t)__popc(__ballot_sync(FULL, handled)) < P.anchor_walk) handled = false;
+    return handled;
+}
+
+// The walk over one window of every lane that takes part (on).  Block b of the lane's other read = the 32 bytes at
+// ob + 32 b; step k scores anchor positions [32k, 32k+32) from blocks k and k+1 and requests block k+2.
+template <bool HAS_VOID>
+__device__ __forceinline__ void as_walk(const hc_kparams& P, const unsigned char* __restrict__ TA, const uint2* __restrict__ VMT,
+                                        const uint4* __restrict__ mystg, const AsWin& w, bool on, u64& S_out, uint32_t& mm_out,
+                                        uint32_t& vd_out) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t jb = w.jb, je = w.je;
+    const int kb = on ? (int)(jb >> 5) : 0x7fffffff, ke = on ? (int)((je - 1u) >> 5) : -1;
     int kmin = kb, kmax = ke;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         kmin = min(kmin, __shfl_xor_sync(FULL, kmin, d));
         kmax = max(kmax, __shfl_xor_sync(FULL, kmax, d));
     }
-    const long long o0 = (long long)ostart - (long long)delta;      // other byte under anchor position 0
+    const long long o0 = (long long)w.ostart - (long long)w.delta;      // other byte under anchor position 0
     const uint32_t off = (uint32_t)o0 & 31u;
-    const uint8_t* ob = P.pk + (o0 - (long long)off);               // aligned block b = ob + 32 b
-    const int bb = handled ? (int)((off + jb) >> 5) : 0x7fffffff, be = handled ? (int)((off + je - 1u) >> 5) : -1;
-    const uint4* mystg = stg + goff;
-    uint32_t b0[8], b1[8], b2[8];       // three block buffers in rotating roles (this step's low half, its high half, the next load)
+    const uint8_t* ob = P.pk + (o0 - (long long)off);
+    const int bb = on ? (int)((off + jb) >> 5) : 0x7fffffff, be = on ? (int)((off + je - 1u) >> 5) : -1;   // blocks the window touches
+    uint32_t lo[8], hi[8], nx[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { b0[i] = 0u; b1[i] = 0u; }
-    if (kmin >= bb && kmin <= be) ldg256(ob + 32ll * kmin, b0);
-    if (kmin + 1 >= bb && kmin + 1 <= be) ldg256(ob + 32ll * (kmin + 1), b1);
+    for (int i = 0; i < 8; i++) { lo[i] = 0u; hi[i] = 0u; }
+    if (kmin >= bb && kmin <= be) ldg256(ob + 32ll * kmin, lo);
+    if (kmin + 1 >= bb && kmin + 1 <= be) ldg256(ob + 32ll * (kmin + 1), hi);
     u64 S = 0;
     uint32_t mm = 0, vd = 0;
-    // one step: block k + 2 is requested (it is consumed by the next step), then anchor positions [32k, 32k+32) are scored
-    // from lo = block k and hi = block k + 1.  A block outside [bb, be] is all zeros: it lies outside the window.
-#define HC_AS_STEP(LO, HI, NX)                                                                                        \
-    {                                                                                                                 \
-        _Pragma("unroll") for (int i = 0; i < 8; i++) NX[i] = 0u;                                                     \
-        if (k + 2 >= bb && k + 2 <= be) ldg256(ob + 32ll * (k + 2), NX);                                              \
-        if (k >= kb && k <= ke) {                                                                                     \
-            uint32_t acc = 0, orv = 0, mE = 0, mO = 0;                                                                \
-            as_block<HAS_VOID>(TA, mystg + 8 * k, LO, HI, off, acc, orv, mE, mO);                                     \
-            S += acc;                                                                                                 \
-            const int k32 = 32 * k;                                                                                   \
-            const uint32_t s0 = (uint32_t)max((int)jb - k32, 0), e0 = (uint32_t)min((int)je - k32, 32);               \
-            const uint2 vs = VMT[s0], ve = VMT[e0];                                                                   \
-            mE = (mE | (mE << 1)) & 0xaaaaaaaau & ve.x & ~vs.x;                                                       \
-            mO = (mO | (mO << 1)) & 0xaaaaaaaau & ve.y & ~vs.y;                                                       \
-            mm += __popc(mE) + __popc(mO);                                                                            \
-            if (HAS_VOID) vd |= (orv & HC_VOID_BIT) ? 1u : 0u;                                                        \
-        }                                                                                                             \
+#pragma unroll 1
+    for (int k = kmin; k <= kmax; k++) {
+        // a block outside [bb, be] counts as zeros: it lies outside the window
+#pragma unroll
+        for (int i = 0; i < 8; i++) nx[i] = 0u;
+        if (k + 2 >= bb && k + 2 <= be) ldg256(ob + 32ll * (k + 2), nx);
+        if (k >= kb && k <= ke) {
+            uint32_t acc = 0, orv = 0, mE = 0, mO = 0;
+            as_block<HAS_VOID>(TA, mystg + 8 * k, lo, hi, off, acc, orv, mE, mO);
+            S += acc;
+            const int k32 = 32 * k;
+            const uint32_t s0 = (uint32_t)max((int)jb - k32, 0), e0 = (uint32_t)min((int)je - k32, 32);
+            const uint2 vs = VMT[s0], ve = VMT[e0];
+            mE = (mE | (mE << 1)) & 0xaaaaaaaau & ve.x & ~vs.x;
+            mO = (mO | (mO << 1)) & 0xaaaaaaaau & ve.y & ~vs.y;
+            mm += __popc(mE) + __popc(mO);
+            if (HAS_VOID) vd |= (orv & HC_VOID_BIT) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { lo[i] = hi[i]; hi[i] = nx[i]; }
     }
-    for (int k = kmin;;) {
-        HC_AS_STEP(b0, b1, b2)
-        if (++k > kmax) break;
-        HC_AS_STEP(b1, b2, b0)
-        if (++k > kmax) break;
-        HC_AS_STEP(b2, b0, b1)
-        if (++k > kmax) break;
-    }
-#undef HC_AS_STEP
-    __syncwarp();
-    if (handled) { out.S = S; out.mm = mm; out.nn = 0; out.vd = vd; }
-    return handled;
+    S_out = S; mm_out = mm; vd_out = vd;
 }
 
-// N positions of a window the anchor walk scored without looking for them.  An N is a zero byte: it added nothing to the
-// sum, but it is not a compared position (:35-39,:122-124) and it was flagged as a mismatch iff the base across it is not
-// 'A' (base bits 0).  The window is A[pos..pos+L) over B[0..L); sides as in setup_windows.  Rare path: the candidate and its
-// read descriptors are loaded again rather than kept alive across the walk.
-__device__ __noinline__ void as_fix_n(const hc_kparams& P, u64 i, int w, uint32_t a_read, u64 sa, u64 sb, uint32_t pos, uint32_t L,
-                                      uint32_t& nn_out, uint32_t& mm_fix) {
-    const hc_candidate c = load_candidate(P, i);
-    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx1));
-    const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + c.idx2));
+// N positions of a window the anchor walk scores without looking for them.  An N is a zero byte: it adds nothing to the
+// sum, but it is not a compared position (:35-39,:122-124) and the walk flags it as a mismatch iff the base across it is
+// not 'A' (base bits 0).  The window is A[pos..pos+L) over B[0..L); sides as in setup_windows.  Returns
+// (number of N positions in the window) | (wrongly flagged mismatches) << 16.  Called while the tile is set up, so that the
+// few loads it needs are long back when the walk ends.
+__device__ __forceinline__ uint32_t as_n_counts(const hc_kparams& P, const hc_candidate& c, const uint4& r1, const uint4& r2, int w,
+                                                const Win& W) {
     const int p1 = (r1.w & HC_LEN_MASK) != 0, p2 = (r2.w & HC_LEN_MASK) != 0;
     const int rc1 = c.ori1 ? 0 : 1, rc2 = c.ori2 ? 0 : 1;
     const int m1 = w == 0 ? (p1 ? rc1 : 0) : (p1 ? 1 - rc1 : 0);      // mate slot of read 1 / read 2 this window uses
     const int m2 = w == 0 ? (p2 ? rc2 : 0) : (p2 ? 1 - rc2 : 0);
     const uint32_t l1 = (m1 ? r1.w : r1.z) & HC_LEN_MASK, l2 = (m2 ? r2.w : r2.z) & HC_LEN_MASK;
-    const bool a1 = a_read == 1u;
+    const bool a1 = W.a_read == 1u;
     const uint32_t lenA = a1 ? l1 : l2, lenB = a1 ? l2 : l1;
     const int rcA = a1 ? rc1 : rc2, rcB = a1 ? rc2 : rc1;
     const uint2 qA = __ldg(reinterpret_cast<const uint2*>(P.nlist + (a1 ? c.idx1 : c.idx2)));
     const uint2 qB = __ldg(reinterpret_cast<const uint2*>(P.nlist + (a1 ? c.idx2 : c.idx1)));
     const uint32_t nA = (a1 ? m1 : m2) ? qA.y : qA.x, nB = (a1 ? m2 : m1) ? qB.y : qB.x;     // two 16-bit positions of the mate used
+    const u64 sa = W.xpos - W.pos, sb = 16ull * W.ypos16;
+    const uint32_t pos = W.pos, L = W.L;
     uint32_t nn = 0, fix = 0;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -756,8 +762,7 @@ __device__ __noinline__ void as_fix_n(const hc_kparams& P, u64 i, int w, uint32_
         nn++;
         if ((other >> 6) != 0u) fix++;
     }
-    nn_out = nn;
-    mm_fix = fix;
+    return nn | (fix << 16);
 }
 
 template <bool HAS_VOID, bool PACKED>
@@ -804,14 +809,26 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
         s.w[0].L = s.w[1].L = 0; s.w[0].status = s.w[1].status = HC_WIN_UNUSED;
         s.w[0].xpos = s.w[1].xpos = 0; s.w[0].ypos16 = s.w[1].ypos16 = 0; s.w[0].hasN = s.w[1].hasN = 0;
         s.w[0].pos = s.w[1].pos = 0; s.w[0].a_read = s.w[1].a_read = 1u;
-        uint32_t anch = 0;
+        uint32_t anch = 0, nfix0 = 0, nfix1 = 0;
         if (valid) {
             c = load_candidate(P, i, &anch);
             load_and_setup(P, c, s, r1, r2);
 #ifndef HC_NO_PREFETCH
-            prefetch_window(P, s.w[0]);
-            prefetch_window(P, s.w[1]);
+#ifdef HC_PREFETCH_LIGHT
+            if (PACKED && P.anchor_walk) {   // the walk requests its blocks a step ahead itself: only what it needs first
+                if (s.w[0].L) { prefetch_l2(P.pk + (s.w[0].xpos & ~127ull)); prefetch_l2(P.pk + 16ull * s.w[0].ypos16); }
+                if (s.w[1].L) { prefetch_l2(P.pk + (s.w[1].xpos & ~127ull)); prefetch_l2(P.pk + 16ull * s.w[1].ypos16); }
+            } else
 #endif
+            {
+                prefetch_window(P, s.w[0]);
+                prefetch_window(P, s.w[1]);
+            }
+#endif
+            if (PACKED && P.anchor_walk && !s.err) {   // N counts of windows the walk may take (rare: a read with one or two N)
+                if (s.w[0].hasN == 1u && s.w[0].L) nfix0 = as_n_counts(P, c, r1, r2, 0, s.w[0]);
+                if (s.w[1].hasN == 1u && s.w[1].L) nfix1 = as_n_counts(P, c, r1, r2, 1, s.w[1]);
+            }
         }
         WinAcc acc[2];
         acc[0].S = acc[1].S = 0; acc[0].mm = acc[1].mm = 0; acc[0].nn = acc[1].nn = 0; acc[0].vd = acc[1].vd = 0;
@@ -820,33 +837,37 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
         // ---- anchor walk: windows of candidates that share a read with their neighbours (packed layout)
         if (PACKED && P.anchor_walk) {
             const uint32_t id1 = valid ? c.idx1 : 0xffffffffu, id2 = valid ? c.idx2 : 0xfffffffeu;
-            if (anch == 0u) {   // records without run information: the read shared with the neighbouring candidates, else the smaller index
-                const uint32_t p1 = __shfl_up_sync(0xffffffffu, id1, 1), p2 = __shfl_up_sync(0xffffffffu, id2, 1);
-                const uint32_t n1 = __shfl_down_sync(0xffffffffu, id1, 1), n2 = __shfl_down_sync(0xffffffffu, id2, 1);
-                const int up = lane > 0, dn = lane < 31;
-                const int sc1 = (up && (id1 == p1 || id1 == p2)) + (dn && (id1 == n1 || id1 == n2));
-                const int sc2 = (up && (id2 == p1 || id2 == p2)) + (dn && (id2 == n1 || id2 == n2));
-                anch = sc1 > sc2 ? 1u : (sc2 > sc1 ? 2u : (id1 <= id2 ? 1u : 2u));
-            }
-#pragma unroll
-            for (int w = 0; w < 2; w++) {
-                const Win& W = s.w[w];
-                const bool a_side = W.a_read == anch;                          // the anchor is the window's A side
-                const u64 sa = W.xpos - W.pos, sb = 16ull * W.ypos16;
-                const uint32_t jb = a_side ? W.pos : 0u, je = jb + W.L;
-                const bool elig = valid && !s.err && W.status == HC_WIN_SCORED && W.L > 0u && !(W.hasN & 2u) && je <= 32u * HC_AS_MAXBLK;
-                if (__any_sync(0xffffffffu, elig)) {
-                    if (as_window<HAS_VOID>(P, TA, VMT, reinterpret_cast<uint4*>(scratch), lane, elig, a_side ? sa : sb, a_side ? sb : sa,
-                                            a_side ? (int)W.pos : -(int)W.pos, jb, je, acc[w])) {
-                        if (w == 0) c0 = 0u; else c1 = 0u;
-                        if (W.hasN) {
-                            uint32_t nn, fix;
-                            as_fix_n(P, i, w, W.a_read, sa, sb, W.pos, W.L, nn, fix);
-                            acc[w].nn = nn;
-                            acc[w].mm -= fix;
-                        }
+            const uint32_t p1 = __shfl_up_sync(0xffffffffu, id1, 1), p2 = __shfl_up_sync(0xffffffffu, id2, 1);
+            const uint32_t n1 = __shfl_down_sync(0xffffffffu, id1, 1), n2 = __shfl_down_sync(0xffffffffu, id2, 1);
+            const int up = lane > 0, dn = lane < 31;
+            const int sc1 = (up && (id1 == p1 || id1 == p2)) + (dn && (id1 == n1 || id1 == n2));
+            const int sc2 = (up && (id2 == p1 || id2 == p2)) + (dn && (id2 == n1 || id2 == n2));
+            // records without run information: the anchor is the read shared with the neighbouring candidates, else the smaller index
+            if (P.cand_compact != 3u) anch = sc1 > sc2 ? 1u : (sc2 > sc1 ? 2u : (id1 <= id2 ? 1u : 2u));
+            const bool lane_ok = valid && !s.err;
+            // lists without runs: do not even start (the lanes of a group are neighbours in a list sorted by read)
+            if ((uint32_t)__popc(__ballot_sync(0xffffffffu, lane_ok && (sc1 | sc2))) + 1u >= P.anchor_walk) {
+                uint4* stg = reinterpret_cast<uint4*>(scratch);
+                uint32_t running = 0, goff0, goff1;
+                const bool on0 = as_stage(P, stg, lane, as_win_of(s.w[0], anch, lane_ok), running, goff0);
+                const bool on1 = as_stage(P, stg, lane, as_win_of(s.w[1], anch, lane_ok), running, goff1);
+                __syncwarp();
+#pragma unroll 1
+                for (int w = 0; w < 2; w++) {
+                    const bool on = w ? on1 : on0;
+                    if (!__any_sync(0xffffffffu, on)) continue;
+                    const Win W = w ? s.w[1] : s.w[0];
+                    u64 S;
+                    uint32_t mm, vd;
+                    as_walk<HAS_VOID>(P, TA, VMT, stg + (w ? goff1 : goff0), as_win_of(W, anch, lane_ok), on, S, mm, vd);
+                    if (on) {
+                        const uint32_t nf = w ? nfix1 : nfix0;
+                        WinAcc r;
+                        r.S = S; r.mm = mm - (nf >> 16); r.nn = nf & 0xffffu; r.vd = vd;
+                        if (w) { acc[1] = r; c1 = 0u; } else { acc[0] = r; c0 = 0u; }
                     }
                 }
+                __syncwarp();
             }
         }
         const uint32_t ct = c0 + c1;
