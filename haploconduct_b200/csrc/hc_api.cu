@@ -232,6 +232,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     P.never_edge = P.t_edge > 0.0;   // a mean log-likelihood is <= 0
     P.never_ov = P.t_ov > 0.0;
     P.merge_contigs = p->merge_contigs;
+    P.merge_contigs_sign = p->merge_contigs > 0.0 ? 1 : (p->merge_contigs < 0.0 ? -1 : 0);
     P.min_read_len = p->min_read_len;
     P.zero_above_edge = 0.0 > p->edge_threshold;
     P.zero_above_ov = 0.0 > p->ov_threshold;

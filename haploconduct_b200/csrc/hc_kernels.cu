@@ -475,24 +475,39 @@ struct WinAcc {
     uint32_t vd;    // void
 };
 
-// src/EdgeCalculator.cpp:254-261 (two windows) and :404-413, on per-window "above threshold" flags.
-__device__ __forceinline__ uint32_t classify(const hc_kparams& P, uint32_t two, const double mmr[2], const int ae[2],
-                                             const int ao[2], double& mmrate) {
+// Mismatch rate of one window, src/EdgeCalculator.cpp:132: float(mismatch_count)/total_len as a double; 1.0 for a window
+// that was not scored (:71), exact on every device and host (an IEEE division of two small integers).
+__device__ __forceinline__ double window_mm_rate(uint32_t mm, uint32_t tl) {
+    if (tl == 0u) return 1.0;
+    return mm ? (double)(float)(int)mm / (double)tl : 0.0;
+}
+
+// src/EdgeCalculator.cpp:254-261 (two windows) and :404-413, on per-window "above threshold" flags.  The rate itself is
+// only divided out when merge_contigs is positive: "rate <= 0" is "no mismatch in any window", "rate <= negative" is never.
+__device__ __forceinline__ uint32_t classify(const hc_kparams& P, uint32_t two, const uint32_t mmc[2], const uint32_t cmp[2],
+                                             const int ae[2], const int ao[2]) {
     int both, ov_ok;
     if (two) {
-        mmrate = fmax(mmr[0], mmr[1]);
         both = ae[0] && ae[1];
         ov_ok = ao[0] && ao[1];
     } else {
-        mmrate = mmr[0];
         both = ae[0];
         ov_ok = ao[0];
     }
     uint32_t cls;
     if (both) cls = HC_CLASS_EDGE;
-    else if (mmrate <= P.merge_contigs) cls = HC_CLASS_EDGE;
-    else if (ov_ok) cls = HC_CLASS_NONEDGE;
-    else cls = HC_CLASS_DISCARD;
+    else {
+        bool low;
+        if (P.merge_contigs_sign == 0) low = cmp[0] != 0u && mmc[0] == 0u && (!two || (cmp[1] != 0u && mmc[1] == 0u));
+        else if (P.merge_contigs_sign < 0) low = false;
+        else {
+            const double r0 = window_mm_rate(mmc[0], cmp[0]), r1 = window_mm_rate(mmc[1], cmp[1]);
+            low = (two ? fmax(r0, r1) : r0) <= P.merge_contigs;
+        }
+        if (low) cls = HC_CLASS_EDGE;
+        else if (ov_ok) cls = HC_CLASS_NONEDGE;
+        else cls = HC_CLASS_DISCARD;
+    }
     return cls | (both ? HC_CLS_BOTH : 0u);
 }
 
@@ -621,8 +636,8 @@ HC_HD uint2 hc_as_vmask(uint32_t n) {
 // One window of one lane in the anchor's coordinates.
 struct AsWin {
     u64 akey;        // store position of the first base of the anchor's sequence (strand slot): equal for lanes that share it
-    u64 ostart;      // store position of the first base of the other sequence
-    int delta;       // other index = anchor index - delta  (+pos: the anchor is the window's A side, -pos: its B side)
+    long long o0;    // store position of the other read's byte that lies under anchor position 0 (other index = anchor index - delta,
+                     // delta = +pos if the anchor is the window's A side, -pos if it is the B side)
     uint32_t jb, je; // the window [jb, je) in anchor coordinates
     bool elig;       // scored window the walk may take (no more N than hc_nlist holds, not beyond HC_AS_MAXBLK blocks)
 };
@@ -632,8 +647,7 @@ __device__ __forceinline__ AsWin as_win_of(const Win& W, uint32_t anch, bool lan
     const bool a_side = W.a_read == anch;
     const u64 sa = W.xpos - W.pos, sb = 16ull * W.ypos16;
     a.akey = a_side ? sa : sb;
-    a.ostart = a_side ? sb : sa;
-    a.delta = a_side ? (int)W.pos : -(int)W.pos;
+    a.o0 = a_side ? (long long)sb - (long long)W.pos : (long long)W.xpos;
     a.jb = a_side ? W.pos : 0u;
     a.je = a.jb + W.L;
     a.elig = lane_ok && W.status == HC_WIN_SCORED && W.L > 0u && !(W.hasN & 2u) && a.je <= 32u * HC_AS_MAXBLK;
@@ -674,10 +688,9 @@ __device__ __forceinline__ bool as_stage(const hc_kparams& P, uint4* stg, int la
 // ob + 32 b; step k scores anchor positions [32k, 32k+32) from blocks k and k+1 and requests block k+2.
 template <bool HAS_VOID>
 __device__ __forceinline__ void as_walk(const hc_kparams& P, const unsigned char* __restrict__ TA, const uint2* __restrict__ VMT,
-                                        const uint4* __restrict__ mystg, const AsWin& w, bool on, u64& S_out, uint32_t& mm_out,
-                                        uint32_t& vd_out) {
+                                        const uint4* __restrict__ mystg, long long o0, uint32_t jb, uint32_t je, bool on, u64& S_out,
+                                        uint32_t& mm_out, uint32_t& vd_out) {
     const uint32_t FULL = 0xffffffffu;
-    const uint32_t jb = w.jb, je = w.je;
     const int kb = on ? (int)(jb >> 5) : 0x7fffffff, ke = on ? (int)((je - 1u) >> 5) : -1;
     int kmin = kb, kmax = ke;
 #pragma unroll
@@ -685,35 +698,46 @@ __device__ __forceinline__ void as_walk(const hc_kparams& P, const unsigned char
         kmin = min(kmin, __shfl_xor_sync(FULL, kmin, d));
         kmax = max(kmax, __shfl_xor_sync(FULL, kmax, d));
     }
-    const long long o0 = (long long)w.ostart - (long long)w.delta;      // other byte under anchor position 0
     const uint32_t off = (uint32_t)o0 & 31u;
-    const uint8_t* ob = P.pk + (o0 - (long long)off);
-    const int bb = on ? (int)((off + jb) >> 5) : 0x7fffffff, be = on ? (int)((off + je - 1u) >> 5) : -1;   // blocks the window touches
+    // per lane, relative to step kmin: the steps in which it scores (act) and the blocks its window touches (ld); at most
+    // HC_AS_MAXBLK + 1 bits each
+    uint32_t act = 0, ld = 0;
+    if (on) {
+        const int bb = (int)((off + jb) >> 5), be = (int)((off + je - 1u) >> 5);
+        act = ((2u << (ke - kmin)) - 1u) & ~((1u << (kb - kmin)) - 1u);
+        ld = ((2u << (be - kmin)) - 1u) & ~((1u << (bb - kmin)) - 1u);
+    }
+    const uint8_t* bp = P.pk + (o0 - (long long)off) + 32ll * kmin;      // block kmin
+    const uint4* sp = mystg + 8 * kmin;
+    int sb = (int)jb - 32 * kmin, eb = (int)je - 32 * kmin;              // the window relative to the step's first position
     uint32_t lo[8], hi[8], nx[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { lo[i] = 0u; hi[i] = 0u; }
-    if (kmin >= bb && kmin <= be) ldg256(ob + 32ll * kmin, lo);
-    if (kmin + 1 >= bb && kmin + 1 <= be) ldg256(ob + 32ll * (kmin + 1), hi);
+    if (ld & 1u) ldg256(bp, lo);
+    if (ld & 2u) ldg256(bp + 32, hi);
+    ld >>= 2;
+    bp += 64;
     u64 S = 0;
     uint32_t mm = 0, vd = 0;
 #pragma unroll 1
-    for (int k = kmin; k <= kmax; k++) {
-        // a block outside [bb, be] counts as zeros: it lies outside the window
+    for (int n = kmax - kmin + 1; n > 0; n--) {
+        // a block the window does not touch counts as zeros
 #pragma unroll
         for (int i = 0; i < 8; i++) nx[i] = 0u;
-        if (k + 2 >= bb && k + 2 <= be) ldg256(ob + 32ll * (k + 2), nx);
-        if (k >= kb && k <= ke) {
+        if (ld & 1u) ldg256(bp, nx);
+        if (act & 1u) {
             uint32_t acc = 0, orv = 0, mE = 0, mO = 0;
-            as_block<HAS_VOID>(TA, mystg + 8 * k, lo, hi, off, acc, orv, mE, mO);
+            as_block<HAS_VOID>(TA, sp, lo, hi, off, acc, orv, mE, mO);
             S += acc;
-            const int k32 = 32 * k;
-            const uint32_t s0 = (uint32_t)max((int)jb - k32, 0), e0 = (uint32_t)min((int)je - k32, 32);
-            const uint2 vs = VMT[s0], ve = VMT[e0];
+            const uint2 vs = VMT[max(sb, 0)], ve = VMT[min(eb, 32)];
             mE = (mE | (mE << 1)) & 0xaaaaaaaau & ve.x & ~vs.x;
             mO = (mO | (mO << 1)) & 0xaaaaaaaau & ve.y & ~vs.y;
             mm += __popc(mE) + __popc(mO);
             if (HAS_VOID) vd |= (orv & HC_VOID_BIT) ? 1u : 0u;
         }
+        act >>= 1; ld >>= 1;
+        bp += 32; sp += 8;
+        sb -= 32; eb -= 32;
 #pragma unroll
         for (int i = 0; i < 8; i++) { lo[i] = hi[i]; hi[i] = nx[i]; }
     }
@@ -849,17 +873,21 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
             if ((uint32_t)__popc(__ballot_sync(0xffffffffu, lane_ok && (sc1 | sc2))) + 1u >= P.anchor_walk) {
                 uint4* stg = reinterpret_cast<uint4*>(scratch);
                 uint32_t running = 0, goff0, goff1;
-                const bool on0 = as_stage(P, stg, lane, as_win_of(s.w[0], anch, lane_ok), running, goff0);
-                const bool on1 = as_stage(P, stg, lane, as_win_of(s.w[1], anch, lane_ok), running, goff1);
+                const AsWin a0 = as_win_of(s.w[0], anch, lane_ok), a1 = as_win_of(s.w[1], anch, lane_ok);
+                const bool on0 = as_stage(P, stg, lane, a0, running, goff0);
+                const bool on1 = as_stage(P, stg, lane, a1, running, goff1);
+                // what the walks need: 4 registers per window
+                const long long o00 = a0.o0, o01 = a1.o0;
+                const uint32_t jj0 = a0.jb | (a0.je << 16), jj1 = a1.jb | (a1.je << 16);
                 __syncwarp();
 #pragma unroll 1
                 for (int w = 0; w < 2; w++) {
                     const bool on = w ? on1 : on0;
                     if (!__any_sync(0xffffffffu, on)) continue;
-                    const Win W = w ? s.w[1] : s.w[0];
+                    const uint32_t jj = w ? jj1 : jj0;
                     u64 S;
                     uint32_t mm, vd;
-                    as_walk<HAS_VOID>(P, TA, VMT, stg + (w ? goff1 : goff0), as_win_of(W, anch, lane_ok), on, S, mm, vd);
+                    as_walk<HAS_VOID>(P, TA, VMT, stg + (w ? goff1 : goff0), w ? o01 : o00, jj & 0xffffu, jj >> 16, on, S, mm, vd);
                     if (on) {
                         const uint32_t nf = w ? nfix1 : nfix0;
                         WinAcc r;
@@ -976,7 +1004,6 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
                     write_per_cand(P, i, 0.0, 1.0, HC_CLASS_DISCARD, z, z, stt, 0);
                 }
             } else {
-                double mmr[2] = {1.0, 1.0};
                 int ae[2], ao[2];
                 uint32_t mmc[2] = {0, 0}, cmp[2] = {0, 0}, stt[2];
 #pragma unroll
@@ -995,7 +1022,6 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
                             cmp[w] = tl;
                             mmc[w] = acc[w].mm;
                             const double dl = (double)tl, dS = (double)acc[w].S;
-                            mmr[w] = acc[w].mm ? (double)(float)(int)acc[w].mm / dl : 0.0;    // :132
                             // mean = -S / (2^22 * tl) compared in the multiplied-out form (no division)
                             const bool up_e = !P.never_edge && (dS <= P.ce_up * dl);
                             const bool dn_e = P.never_edge || (dS > P.ce_dn * dl);
@@ -1012,21 +1038,21 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
                     stt[w] = status;
                 }
                 st_bytes += 48;
-                double mmrate;
-                const uint32_t cls = classify(P, s.two, mmr, ae, ao, mmrate);
+                const uint32_t cls = classify(P, s.two, mmc, cmp, ae, ao);
                 if (P.exact_edges && (cls & HC_CLS_MASK) == HC_CLASS_EDGE) flag = true;
                 P.cls[i] = (uint8_t)cls;
                 if ((cls & HC_CLS_MASK) == HC_CLASS_EDGE) {
                     hc_tmp32 t;
                     t.S[0] = acc[0].S; t.S[1] = acc[1].S;
                     t.tl[0] = cmp[0]; t.tl[1] = cmp[1];
-                    t.mismatch_rate = mmrate;
+                    t.mm[0] = mmc[0]; t.mm[1] = mmc[1];
                     P.tmp[i] = t;
                 }
                 if (P.per_cand) {
                     const double ov0 = cmp[0] ? exp(fx_mean(acc[0].S, cmp[0])) : 0.0;
                     const double ov1 = cmp[1] ? exp(fx_mean(acc[1].S, cmp[1])) : 0.0;
-                    write_per_cand(P, i, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), mmrate, cls, mmc, cmp, stt, 0);
+                    const double r0 = window_mm_rate(mmc[0], cmp[0]), r1 = window_mm_rate(mmc[1], cmp[1]);
+                    write_per_cand(P, i, combine_score(s.two, cls & HC_CLS_BOTH, ov0, ov1), s.two ? fmax(r0, r1) : r0, cls, mmc, cmp, stt, 0);
                 }
             }
         }
@@ -1207,8 +1233,8 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
                 ao[w] = P.zero_above_ov;
             }
         }
-        double mmrate;
-        const uint32_t cls = classify(P, s.two, mmr, ae, ao, mmrate) | HC_CLS_EXACT;
+        const uint32_t cls = classify(P, s.two, mmc, cmp, ae, ao) | HC_CLS_EXACT;
+        const double mmrate = s.two ? fmax(mmr[0], mmr[1]) : mmr[0];
         if (!writer) continue;
         P.cls[i] = (uint8_t)cls;
         if ((cls & HC_CLS_MASK) == HC_CLASS_EDGE) {
@@ -1216,7 +1242,7 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
             tm.S[0] = (u64)__double_as_longlong(mean[0]);
             tm.S[1] = (u64)__double_as_longlong(mean[1]);
             tm.tl[0] = cmp[0]; tm.tl[1] = cmp[1];
-            tm.mismatch_rate = mmrate;
+            tm.mm[0] = mmc[0]; tm.mm[1] = mmc[1];
             P.tmp[i] = tm;
         }
         if (P.per_cand) {
@@ -1331,7 +1357,8 @@ __device__ __forceinline__ void emit_edge(const hc_kparams& P, u64 i, uint32_t c
     hc_edge e;
     e.cand = i + cand_offset;
     e.score = combine_score(two, cfull & HC_CLS_BOTH, ov[0], ov[1]);
-    e.mismatch_rate = t.mismatch_rate;
+    const double mr0 = window_mm_rate(t.mm[0], t.tl[0]), mr1 = window_mm_rate(t.mm[1], t.tl[1]);
+    e.mismatch_rate = two ? fmax(mr0, mr1) : mr0;                              // :132, :254
     extra_pos(cd, r1, r2, e.pos3, e.pos4);
     e.mean_log[0] = ml[0];
     e.mean_log[1] = ml[1];

@@ -8,7 +8,7 @@
 #include "hc_layout.h"
 
 #ifndef HC_WARPS_MAX
-#define HC_WARPS_MAX 24          // warps per CTA (one CTA per SM: the score tables are per CTA)
+#define HC_WARPS_MAX 20          // warps per CTA (one CTA per SM: the score tables are per CTA); 96 registers per thread
 #endif
 #ifndef HC_MIN_CTAS
 #define HC_MIN_CTAS 1             // resident CTAs per SM the register allocation aims at
@@ -33,8 +33,8 @@
 // Scratch record, written for accepted edges only: what the ordered compaction needs to emit hc_edge.
 struct hc_tmp32 {
     unsigned long long S[2];     // fixed-point sum of -log p per window, or bits of the exact mean log (HC_CLS_EXACT)
-    uint32_t tl[2];              // compared (non-N) positions per window; 0 = window not scored (score 0)
-    double mismatch_rate;
+    uint32_t tl[2];              // compared (non-N) positions per window; 0 = window not scored (score 0, mismatch rate 1.0)
+    uint32_t mm[2];              // mismatches per window (the rate, an IEEE division, is taken when the edge is emitted)
 };
 
 struct hc_kparams {
@@ -72,6 +72,7 @@ struct hc_kparams {
     // fixed-point form: S <= c_up * total_len  <=>  surely above;  S > c_dn * total_len  <=>  surely below
     double ce_up, ce_dn, co_up, co_dn;
     double merge_contigs;
+    int32_t merge_contigs_sign; // -1 / 0 / +1: with 0 (every driver's default) "mismatch rate <= merge_contigs" is "no mismatch at all"
     uint32_t min_read_len;
     uint32_t zero_above_edge;   // 0 > edge_threshold ?
     uint32_t zero_above_ov;     // 0 > ov_threshold ?
