@@ -113,15 +113,58 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def kernel_source_sha() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("hc_kernels.cu", "hc_kernels.cuh", "hc_layout.h"):
+        with open(os.path.join(ROOT, "haploconduct_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(n_candidates: int, default_config: bool):
-    """dram__bytes_read.sum + dram__bytes_write.sum of hc_score_kernel per launch, from the committed
-    ncu --set full capture of this same configuration (bench.py cannot run under a profiler itself)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of hc_score_kernel per launch, from the committed ncu --set full
+    capture of this same configuration (bench.py cannot run under a profiler itself).  The capture names the kernel
+    sources it was taken with; if they have changed since, the number is withheld rather than repeated."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)
-        return (float(t["dram_bytes_per_candidate"]) * n_candidates, t["source"]) if default_config else (None, None)
-    except Exception:
-        return None, None
+        if not default_config:
+            return None, "not the captured configuration"
+        if t.get("kernel_source_sha") != kernel_source_sha():
+            return None, "stale: %s was captured with kernel sources %s, these are %s" % (t["source"], t.get("kernel_source_sha"), kernel_source_sha())
+        return float(t["dram_bytes_per_candidate"]) * n_candidates, t["source"]
+    except Exception as ex:
+        return None, "unavailable: %r" % (ex,)
+
+
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process (and so its first-touch / pinned host allocations) to the CPUs of the NUMA node the GPU hangs
+    off: at 8 ranks the host-side copies otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": node, "bound": False, "why": "no NUMA information for the device"}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"node": node, "bound": False, "why": "none of the node's CPUs is available to this process"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "bound": True, "cpus": len(allowed)}
+    except Exception as ex:
+        return {"bound": False, "why": repr(ex)}
 
 
 def measured_hbm_peak():
@@ -202,6 +245,11 @@ def main() -> None:
     ap.add_argument("--e2e-records", default="runs", choices=["runs", "short", "compact"],
                     help="host record of the e2e leg: run-encoded 8-byte hc_candidate_entry, 12-byte hc_candidate_short (both: reads "
                          "< 16384 bases) or 16-byte hc_candidate_compact")
+    ap.add_argument("--e2e-output", default="small", choices=["small", "full"],
+                    help="what the e2e leg brings back: hc_edge_small records + one bit per candidate (hc_score_batch_runs_small), "
+                         "or 48-byte hc_edge records + 8-byte non-edge indices (hc_score_batch_runs)")
+    ap.add_argument("--no-exchange", action="store_true", help="N > 1: leave the all-gather of the accepted edges out of the timed region")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--exact-edge-scores", action="store_true",
                     help="HC_FLAG_EXACT_EDGE_SCORES: re-sum every accepted edge in the reference's order (diagnostic)")
@@ -222,18 +270,30 @@ def main() -> None:
         if rank != 0:
             return
         t0 = time.time()
-        n_pairs_s = min(args.pairs, 400_000)
-        genome_s = max(1000, 100_000 * n_pairs_s // max(args.pairs, 1))   # same coverage as the full configuration
-        pr = WT.make_paired_reads(n_pairs_s, read_len=args.read_len, genome_len=genome_s, seed=args.seed, device="cpu")
-        rec = WT.make_pp_candidates(pr, D=args.partners, shard=0, n_shards=N_SHARDS, max_cands=args.cpu_sample)
-        cands = WT.candidates_as_numpy(rec)
+        if torch.cuda.is_available():
+            # the very workload of the GPU arm (torch generates it on the device: plumbing, none of this repo's kernels), and of
+            # it the same prefix of shard 0 the GPU arm's cpu_baseline leg scores
+            torch.cuda.set_device(local_rank)
+            pr = WT.make_paired_reads(args.pairs, read_len=args.read_len, seed=args.seed, device="cuda:%d" % local_rank)
+            rec = WT.make_pp_candidates(pr, D=args.partners, shard=0, n_shards=N_SHARDS, max_cands=args.cands)
+            cands = WT.candidates_as_numpy(rec[: args.cpu_sample])
+            del rec
+            torch.cuda.empty_cache()
+            what = "the first %d candidates of shard 0 of this workload" % len(cands)
+        else:
+            n_pairs_s = min(args.pairs, 400_000)
+            genome_s = max(1000, 100_000 * n_pairs_s // max(args.pairs, 1))   # same coverage as the full configuration
+            pr = WT.make_paired_reads(n_pairs_s, read_len=args.read_len, genome_len=genome_s, seed=args.seed, device="cpu")
+            rec = WT.make_pp_candidates(pr, D=args.partners, shard=0, n_shards=N_SHARDS, max_cands=args.cpu_sample)
+            cands = WT.candidates_as_numpy(rec)
+            what = "%d candidates of the same generator at the same coverage (%d pairs on a %d bp genome; no GPU to generate the full read set)" % (
+                len(cands), n_pairs_s, genome_s)
         threads = os.cpu_count() or 1
         out, n_reads = run_cpu_reference(pr.bases.numpy(), pr.quals.numpy(), args.read_len, cands, args.warmup + args.steps, threads)
         times = out["rep_times_s"][args.warmup:]
         ms = 1e3 * float(np.mean(times))
         v = len(cands) / (ms / 1e3)
-        sample = ("%d candidates of the same generator at the same coverage (%d pairs on a %d bp genome), scoring region "
-                  "src/EdgeCalculator.cpp:395-423 only, per step" % (len(cands), n_pairs_s, genome_s))
+        sample = "%s (%d read pairs), scoring region src/EdgeCalculator.cpp:395-423 of the unmodified reference only, per step" % (what, n_reads)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args), "sample": sample},
@@ -250,6 +310,7 @@ def main() -> None:
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    numa = {"bound": False, "why": "--no-numa-bind"} if args.no_numa_bind else bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -292,8 +353,40 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    # N > 1: the accepted-edge lists of all ranks are concatenated in rank order (= input order) by an NCCL all-gather of the
+    # device-resident lists, on a side stream so that the gather of step k runs next to the kernels of step k + 1
+    exchange = None
+    if world > 1 and not args.no_exchange:
+        from haploconduct_b200 import dist as HD
         step()
+        torch.cuda.synchronize()
+        cap_e = int(int(d_counts[0].item()) * 1.02) + 1024
+        gather = HD.DeviceGather(48, cap_e, dev)
+        xs = torch.cuda.Stream(dev)
+        x_done = torch.cuda.Event()
+        k_done = torch.cuda.Event()
+        d_edges_x = torch.empty((cap_e, 48), dtype=torch.uint8, device=dev)       # the list being gathered (step k) while step k+1 writes d_edges
+        d_cnt_x = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def exchange():
+            stream.wait_event(x_done)                       # the previous gather has read its snapshot
+            d_edges_x.copy_(d_edges[:cap_e], non_blocking=True)
+            d_cnt_x.copy_(d_counts[:1], non_blocking=True)
+            k_done.record(stream)
+            with torch.cuda.stream(xs):
+                xs.wait_event(k_done)
+                gather.gather(d_edges_x, d_cnt_x)
+                x_done.record(xs)
+
+    def full_step():
+        step()
+        if exchange:
+            exchange()
+
+    for _ in range(args.warmup):
+        full_step()
+    if exchange:
+        stream.wait_event(x_done)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -320,7 +413,9 @@ def main() -> None:
     tw0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
-        step()
+        full_step()
+    if exchange:
+        stream.wait_event(x_done)                           # the last gather ends inside the timed region
     e1.record(stream)
     barrier()
     tw1 = time.time()
@@ -379,13 +474,22 @@ def main() -> None:
         h_cand.copy_(cc)
         del cc
         ne, nn = int(counts[0]), int(counts[1])
-        h_edges = torch.empty((max(ne, 1) + 1024, 48), dtype=torch.uint8, pin_memory=True)
-        h_nonedge = torch.empty(max(nn, 1) + 1024, dtype=torch.int64, pin_memory=True)
+        small = use_runs and args.e2e_output == "small"
+        erec = (32 if args.exact_edge_scores else 24) if small else 48
+        h_edges = torch.empty((max(ne, 1) + 1024, erec), dtype=torch.uint8, pin_memory=True)
+        h_nonedge = torch.empty(((n + 63) // 64 + 1) if small else (max(nn, 1) + 1024), dtype=torch.int64, pin_memory=True)
         import ctypes
         L = capi.lib()
         c_ne, c_nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
 
         def e2e_step():
+            if small:     # hc_edge_small records + one bit per candidate
+                rc = L.hc_score_batch_runs_small(store.handle, params.ctypes.data, h_anchor.data_ptr(), h_start.data_ptr(), h_anchor.shape[0],
+                                                 h_cand.data_ptr(), n, h_edges.data_ptr(), h_edges.shape[0], ctypes.byref(c_ne),
+                                                 h_nonedge.data_ptr(), ctypes.byref(c_nn), None)
+                if rc != 0:
+                    raise RuntimeError(capi.last_error())
+                return
             if use_runs:
                 ecap, ncap = (0, 0) if args.e2e_no_output else (h_edges.shape[0], h_nonedge.shape[0])
                 rc = L.hc_score_batch_runs(store.handle, params.ctypes.data, h_anchor.data_ptr(), h_start.data_ptr(), h_anchor.shape[0],
@@ -410,8 +514,29 @@ def main() -> None:
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert c_ne.value == ne and c_nn.value == nn
-        e2e = (e2e_ms, n * rec_bytes + run_bytes, ne * 48 + nn * 8 + 64,
-               "hc_candidate_entry (8 B, run-encoded)" if use_runs else ("hc_candidate_short (12 B)" if short else "hc_candidate_compact (16 B)"))
+        if small:      # the bit map really says what the index list says
+            bits = h_nonedge[: (n + 63) // 64].numpy().view(np.uint8)
+            assert int(np.unpackbits(bits).sum()) == nn
+        e2e = (e2e_ms, n * rec_bytes + run_bytes, (ne * erec + ((n + 63) // 64) * 8 + 64) if small else (ne * 48 + nn * 8 + 64),
+               ("hc_candidate_entry (8 B, run-encoded)" if use_runs else ("hc_candidate_short (12 B)" if short else "hc_candidate_compact (16 B)"))
+               + (" in; hc_edge_small (%d B) + 1 bit per candidate out" % erec if small else " in; hc_edge (48 B) + 8-byte non-edge indices out"))
+
+    # the mode the drop-in host mirror runs in (HC_FLAG_EXACT_EDGE_SCORES: every accepted edge re-summed in the reference's
+    # order), as an extra number next to the default line
+    exact_ms = None
+    if not args.exact_edge_scores:
+        px = F.make_params(flags=F.FLAG_EXACT_EDGE_SCORES, **PARAMS)
+        for _ in range(2):
+            store.score_batch_device(local_rank, stream.cuda_stream, px, rec.data_ptr(), n, 0, d_edges.data_ptr(), n, d_nonedge.data_ptr(), n,
+                                     d_counts.data_ptr(), False)
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(stream)
+        for _ in range(3):
+            store.score_batch_device(local_rank, stream.cuda_stream, px, rec.data_ptr(), n, 0, d_edges.data_ptr(), n, d_nonedge.data_ptr(), n,
+                                     d_counts.data_ptr(), False)
+        x1.record(stream)
+        torch.cuda.synchronize()
+        exact_ms = x0.elapsed_time(x1) / 3
 
     ms_step = ms_total / args.steps
     tvals = torch.tensor([ms_step, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
@@ -442,6 +567,12 @@ def main() -> None:
             "gpu_launches": int(stats["kernel_launches"]) * args.steps,
             "clocks": clocks,
             "results": {"edges": int(counts[0]), "nonedges": int(counts[1]), "reference_order_pass": int(counts[2])},
+            "exchange": ("NCCL all-gather (counts, then lists padded to the longest) of every rank's accepted edges, 48-byte records, "
+                         "inside the timed region on a side stream; rank order = input order" if exchange else
+                         ("none (one rank)" if world == 1 else "left out (--no-exchange)")),
+            "exact_edge_scores": (None if exact_ms is None else {"ms_per_step": exact_ms, "value": n / (exact_ms * 1e-3), "unit": UNIT + " per GPU",
+                                                                 "note": "HC_FLAG_EXACT_EDGE_SCORES: the mode of the drop-in host mirror"}),
+            "numa": numa,
             "setup_s": round(time.time() - t_setup, 1), "store_build_s": round(store_build_s, 2),
         }
         if e2e:

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("HC_B200_LIB") or os.path.join(HERE, "lib", "libhc_b20
 # every symbol include/hc_b200.h declares
 EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
-    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_device",
+    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_runs_small", "hc_score_batch_short_small", "hc_edge_extra_pos", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
     "hc_store_create_fastq", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
@@ -68,6 +68,12 @@ def lib() -> ctypes.CDLL:
         L.hc_score_batch_short.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
         L.hc_score_batch_runs.restype = i32
         L.hc_score_batch_runs.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
+        L.hc_score_batch_runs_small.restype = i32
+        L.hc_score_batch_runs_small.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
+        L.hc_score_batch_short_small.restype = i32
+        L.hc_score_batch_short_small.argtypes = [vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
+        L.hc_edge_extra_pos.restype = None
+        L.hc_edge_extra_pos.argtypes = [u32, u32, ctypes.c_char, u32, u32, u32, u32, vp, vp]
         L.hc_score_batch_device.restype = i32
         L.hc_score_batch_device.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, u64, vp, u64, vp, vp]
         L.hc_overlap_score.restype = dbl
@@ -237,6 +243,38 @@ class Store:
             err.required = (int(ne.value), int(nn.value))
             raise err
         return edges[: ne.value], nonedge[: nn.value], per, stats[0]
+
+    def score_batch_small(self, params: np.ndarray, cands: np.ndarray, runs: bool = True, edges_cap: Optional[int] = None):
+        """hc_score_batch_runs_small / hc_score_batch_short_small: small outputs.  Returns (edges as EDGE_SMALL or
+        EDGE_SMALL_EXACT records, non-edge flags as a bool array over the candidates, stats)."""
+        L = lib()
+        exact = bool(int(params["flags"][0]) & F.FLAG_EXACT_EDGE_SCORES)
+        dt = F.EDGE_SMALL_EXACT if exact else F.EDGE_SMALL
+        ne, nn = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        stats = np.zeros(1, dtype=F.BATCH_STATS)
+        if runs:
+            anchor, start, entries = F.run_encode(cands)
+            n = len(entries)
+        else:
+            entries = np.ascontiguousarray(F.short_candidates(cands))
+            n = len(entries)
+        ecap = n if edges_cap is None else edges_cap
+        edges = np.zeros(max(ecap, 1), dtype=dt)
+        bits = np.full((n + 63) // 64 + 1, 0xdeadbeefdeadbeef, dtype=np.uint64)     # the call must write every word it owns
+        if runs:
+            rc = L.hc_score_batch_runs_small(self._h, params.ctypes.data, anchor.ctypes.data if n else None, start.ctypes.data, len(anchor),
+                                             entries.ctypes.data if n else None, n, edges.ctypes.data, ecap, ctypes.byref(ne),
+                                             bits.ctypes.data, ctypes.byref(nn), stats.ctypes.data)
+        else:
+            rc = L.hc_score_batch_short_small(self._h, params.ctypes.data, entries.ctypes.data if n else None, n, edges.ctypes.data, ecap,
+                                              ctypes.byref(ne), bits.ctypes.data, ctypes.byref(nn), stats.ctypes.data)
+        if rc != 0:
+            err = HcError(rc, last_error())
+            err.required = (int(ne.value), int(nn.value))
+            raise err
+        flags = np.unpackbits(bits[: (n + 63) // 64].view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert int(flags.sum()) == int(nn.value)
+        return edges[: ne.value], flags, stats[0]
 
     def score_batch_device(self, device: int, stream: int, params: np.ndarray, d_cand: int, n: int, d_per_cand: int,
                            d_edges: int, edges_cap: int, d_nonedge: int, nonedge_cap: int, d_counts: int, want_stats: bool):

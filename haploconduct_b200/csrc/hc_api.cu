@@ -86,13 +86,15 @@ struct DevCtx {
     uint64_t acc_e_cap = 0, acc_n_cap = 0;
     hc_edge* d_acc_edges = nullptr;
     uint64_t* d_acc_nonedge = nullptr;
+    uint64_t acc_b_cap = 0;                // small outputs: one bit per candidate of the shard (32-bit words)
+    uint32_t* d_acc_bits = nullptr;
     unsigned long long* d_run = nullptr;   // {edges, non-edges} emitted so far in this call
     unsigned long long* h_cnt = nullptr;   // pinned: [2][HC_CNT_N] counter snapshots per slot
     uint64_t* d_counts = nullptr;
     cudaStream_t stream = nullptr, s_copy = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    hc_launch_cfg cfg{};
+    hc_launch_cfg cfg{}, cfg_walk{};
 };
 
 }  // namespace
@@ -131,7 +133,7 @@ void free_ctx(DevCtx& d) {
         if (d.ev_done[k]) cudaEventDestroy(d.ev_done[k]);
         if (d.ev_out[k]) cudaEventDestroy(d.ev_out[k]);
     }
-    cudaFree(d.d_acc_edges); cudaFree(d.d_acc_nonedge); cudaFree(d.d_run); cudaFree(d.d_counts);
+    cudaFree(d.d_acc_edges); cudaFree(d.d_acc_nonedge); cudaFree(d.d_acc_bits); cudaFree(d.d_run); cudaFree(d.d_counts);
     cudaFree(d.d_whole); cudaFree(d.d_runs_all);
     if (d.h_runs_all) cudaFreeHost(d.h_runs_all);
     for (cudaEvent_t e : d.ev_step) cudaEventDestroy(e);
@@ -203,7 +205,7 @@ struct RunDev {                 // device-side run arrays of one batch of hc_can
 int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, const void* d_cand, int compact, uint64_t n,
                   hc_result* d_per_cand, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge, uint64_t nonedge_cap,
                   uint64_t* d_counts, uint64_t cand_offset, unsigned long long* d_run, cudaEvent_t k0, cudaEvent_t k1,
-                  uint32_t* launches, const RunDev* runs = nullptr) {
+                  uint32_t* launches, const RunDev* runs = nullptr, int small_out = 0, uint32_t* d_bits = nullptr) {
     if (n > 0xffffffffull) return fail(HC_ERR_ARG, "more than 2^32-1 candidates in one device batch");
     if (compact == 3 && !runs) return fail(HC_ERR_ARG, "run-encoded candidates without run arrays");
     int rc = ensure_tables(s, d, p->mismatch, st);
@@ -237,17 +239,20 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
     P.zero_above_edge = 0.0 > p->edge_threshold;
     P.zero_above_ov = 0.0 > p->ov_threshold;
     P.exact_edges = (p->flags & HC_FLAG_EXACT_EDGE_SCORES) ? 1u : 0u;
-    // anchor walk: on for the packed layout, started for tiles in which at least HC_ANCHOR_WALK_MIN lanes (default 12) take
-    // part; HC_NO_ANCHOR_WALK: lane-chunk rounds only (tests, A/B timing)
+    // Anchor walk (hc_kernels.cu): an alternative schedule for lists with runs, packed layout only.  Measured on config 4
+    // it removes the bank conflicts of the table lookups but does not beat the lane-chunk rounds (per-tile set-up cost,
+    // DESIGN.md section 6), so it is opt-in: HC_ANCHOR_WALK=1 (tests, experiments); a walk is started for tiles in which
+    // at least HC_ANCHOR_WALK_MIN lanes (default 12) take part.
     uint32_t walk_min = 12;
     if (const char* e = getenv("HC_ANCHOR_WALK_MIN")) walk_min = (uint32_t)std::max(1l, std::min(32l, strtol(e, nullptr, 10)));
-    P.anchor_walk = (s->packed && !getenv("HC_NO_ANCHOR_WALK")) ? walk_min : 0u;
+    const char* walk_env = getenv("HC_ANCHOR_WALK");
+    P.anchor_walk = (s->packed && walk_env && atoi(walk_env) != 0) ? walk_min : 0u;
     P.void_exact = d.void_exact ? 1u : 0u;
     CU(cudaMemsetAsync(d.counters, 0, HC_CNT_N * sizeof(unsigned long long), st));
     if (k0) CU(cudaEventRecord(k0, st));
     uint32_t nl = 0;
     if (n > 0) {
-        hc_launch_cfg cfg = d.cfg;
+        hc_launch_cfg cfg = P.anchor_walk ? d.cfg_walk : d.cfg;
         const uint64_t ntiles = (n + 31) / 32;
         const uint64_t warps_per_block = cfg.threads / 32;
         const uint64_t need_blocks = (ntiles + warps_per_block - 1) / warps_per_block;
@@ -259,8 +264,8 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
         CU(hc_launch_exact(P, st));
         nl += 2;
     }
-    CU(hc_launch_compact(P, d_edges, edges_cap, d_nonedge, nonedge_cap, d.blockcounts, cand_offset, d_run, st));
-    nl += (n > 0 ? 4 : 1) + (d_run ? 1 : 0);   // count, scan, scatter, emit_edges (+ advance)
+    CU(hc_launch_compact(P, d_edges, edges_cap, d_nonedge, nonedge_cap, d.blockcounts, cand_offset, d_run, st, small_out, d_bits));
+    nl += (n > 0 ? 4 : 1) + (d_run ? 1 : 0) + ((n > 0 && small_out && d_bits) ? 1 : 0);   // count, scan, scatter, emit_edges (+ advance, + bit map)
     if (k1) CU(cudaEventRecord(k1, st));
     if (d_counts) {   // {n_edges, n_nonedges, n_exact} are contiguous in the counter block; [3] = invalid candidates
         CU(cudaMemcpyAsync(d_counts, d.counters + HC_CNT_EDGES, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
@@ -314,6 +319,18 @@ int hc_device_count(void) {
 }
 
 double hc_phred_to_prob(int phred) { return hc_tables_phred_to_prob(phred); }
+
+void hc_edge_extra_pos(uint32_t pos1, uint32_t pos2, char ord, uint32_t len1a, uint32_t len1b, uint32_t len2a, uint32_t len2b,
+                       int32_t* pos3, int32_t* pos4) {
+    const int p1 = len1b != 0, p2 = len2b != 0;     // src/EdgeCalculator.cpp:222, :262-263, :300-301, :361-372
+    if (!p1 && !p2) { *pos3 = (int32_t)(len1a - pos1 - len2a); *pos4 = 0; }
+    else if (!p1) { *pos3 = (int32_t)(len1a - pos2 - len2b); *pos4 = (int32_t)(len1a - pos1 - len2a); }
+    else if (!p2) { *pos3 = (int32_t)(len1b + pos2 - len2a); *pos4 = (int32_t)(len2a + pos1 - len1a); }
+    else {
+        *pos3 = ord == '1' ? (int32_t)(len1b - pos2 - len2b) : (int32_t)(len1b + pos2 - len2b);
+        *pos4 = (int32_t)(len1a - pos1 - len2a);
+    }
+}
 double hc_exp_threshold(double threshold) { return hc_tables_exp_threshold(threshold, nullptr); }
 
 uint64_t hc_store_n_reads(const hc_store* s) { return s ? s->n_reads : 0; }
@@ -468,7 +485,8 @@ int build_store(hc_store* s, std::vector<hc_rdesc>& rd, const uint8_t* d_text, c
     for (int k = 0; k < n_devices && e == cudaSuccess; k++) {
         DevCtx& d = s->devs[k];
         e = cudaSetDevice(d.device);
-        if (e == cudaSuccess) e = hc_score_occupancy((uint32_t)s->ncodes, s->packed ? 1 : 0, d.sm_count, d.smem_per_sm, &d.cfg);
+        if (e == cudaSuccess) e = hc_score_occupancy((uint32_t)s->ncodes, 0, d.sm_count, d.smem_per_sm, &d.cfg);
+        if (e == cudaSuccess && s->packed) e = hc_score_occupancy((uint32_t)s->ncodes, 1, d.sm_count, d.smem_per_sm, &d.cfg_walk);
         if (k == 0 || e != cudaSuccess) continue;
         e = alloc_planes(s, d, d.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
@@ -813,7 +831,7 @@ struct RunsHost {               // caller's run arrays (hc_score_batch_runs)
 
 static int score_host(hc_store* s, const hc_params* p, const void* cand, int compact, uint64_t n, hc_result* per_cand,
                       hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_idx, uint64_t nonedge_cap,
-                      uint64_t* n_nonedges, hc_batch_stats* stats, const RunsHost* runs = nullptr) {
+                      uint64_t* n_nonedges, hc_batch_stats* stats, const RunsHost* runs = nullptr, int small_out = 0) {
     if (!s || !p || !n_edges || !n_nonedges || (n && !cand)) return fail(HC_ERR_ARG, "hc_score_batch: NULL argument");
     if (stats) memset(stats, 0, sizeof(*stats));
     *n_edges = 0;
@@ -826,7 +844,12 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
     size_t whole_max = (size_t)2 << 30;   // shards up to this many bytes of records are copied in ahead of the kernels
     if (const char* e = getenv("HC_HOST_WHOLE_MAX")) whole_max = (size_t)strtoull(e, nullptr, 10);                   // tests
     std::vector<uint64_t> lo(G + 1);
-    for (int g = 0; g <= G; g++) lo[g] = n * (uint64_t)g / (uint64_t)G;   // contiguous index ranges
+    for (int g = 0; g <= G; g++) lo[g] = g == G ? n : (n * (uint64_t)g / (uint64_t)G) & ~63ull;   // contiguous index ranges, cut at multiples of 64
+    // size of an edge record on its way out, and (small outputs) the caller's bit map as 32-bit words
+    const size_t erec = !small_out ? sizeof(hc_edge) : ((p->flags & HC_FLAG_EXACT_EDGE_SCORES) ? sizeof(hc_edge_small_exact) : sizeof(hc_edge_small));
+    char* const edges_b = reinterpret_cast<char*>(edges);
+    uint32_t* const bits_out = reinterpret_cast<uint32_t*>(nonedge_idx);
+    if (small_out) nonedge_cap = 0;
     // Pipeline steps of device g: [cs[g][k], cs[g][k+1]).  Whole-shard mode (the shard's records fit `whole_max`): all
     // copies in are issued up front into one device buffer and run ahead of the kernels, so the steps can start small
     // (the first kernel waits for 1 M candidates, not 8 M), grow to 16 M (fewer launches) and end small (little left to
@@ -843,13 +866,13 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         const uint64_t small = 1ull << 20;
         if (const char* e = getenv("HC_HOST_BIG")) { const uint64_t v = strtoull(e, nullptr, 10); if (v >= 2 * small) big = v; }   // experiments
         if (chunk || !whole[g] || m <= 2 * small) {
-            const uint64_t step = chunk ? chunk : (8ull << 20);
+            const uint64_t step = ((chunk ? chunk : (8ull << 20)) + 63) & ~63ull;     // steps start at multiples of 64 (bit-map words)
             for (uint64_t o = step; o < m; o += step) c.push_back(lo[g] + o);
         } else {
             uint64_t done = 0, sz = small;
             while (sz < big && m - done > 4 * sz) { done += sz; c.push_back(lo[g] + done); sz *= 2; }          // 1, 2, 4, 8 M
             while (m - done > 2 * big) { done += big; c.push_back(lo[g] + done); }                            // 16 M ...
-            while (m - done > 2 * small) { done += (m - done + 1) / 2; c.push_back(lo[g] + done); }           // halves
+            while (m - done > 2 * small) { done += ((m - done + 1) / 2 + 63) & ~63ull; c.push_back(lo[g] + done); }   // halves (multiples of 64)
         }
         if (m > 0) c.push_back(lo[g + 1]);
     }
@@ -895,6 +918,11 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         }
         const uint64_t need_e = std::max<uint64_t>(std::min<uint64_t>(m, edges_cap), 1), need_n = std::max<uint64_t>(std::min<uint64_t>(m, nonedge_cap), 1);
         if (need_e > d.acc_e_cap) { cudaFree(d.d_acc_edges); d.d_acc_edges = nullptr; d.acc_e_cap = 0; CU(cudaMalloc(&d.d_acc_edges, need_e * sizeof(hc_edge))); d.acc_e_cap = need_e; }
+        if (small_out && (m + 31) / 32 + 4 > d.acc_b_cap) {
+            cudaFree(d.d_acc_bits); d.d_acc_bits = nullptr; d.acc_b_cap = 0;
+            CU(cudaMalloc(&d.d_acc_bits, ((m + 31) / 32 + 4) * sizeof(uint32_t)));
+            d.acc_b_cap = (m + 31) / 32 + 4;
+        }
         if (need_n > d.acc_n_cap) { cudaFree(d.d_acc_nonedge); d.d_acc_nonedge = nullptr; d.acc_n_cap = 0; CU(cudaMalloc(&d.d_acc_nonedge, need_n * sizeof(uint64_t))); d.acc_n_cap = need_n; }
         CU(cudaMemsetAsync(d.d_run, 0, 2 * sizeof(unsigned long long), d.stream));
         CU(cudaEventRecord(d.ev[2], d.stream));
@@ -966,9 +994,11 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
             const uint64_t e1 = std::min<uint64_t>(dev_e[g], d.acc_e_cap), n1 = std::min<uint64_t>(dev_n[g], d.acc_n_cap);
             CU(cudaStreamWaitEvent(d.s_out, d.ev_done[slot], 0));
             if (e1 > out_e[g] && e1 <= edges_cap)
-                CU(cudaMemcpyAsync(edges + out_e[g], d.d_acc_edges + out_e[g], (e1 - out_e[g]) * sizeof(hc_edge), cudaMemcpyDeviceToHost, d.s_out));
-            if (n1 > out_n[g] && n1 <= nonedge_cap)
+                CU(cudaMemcpyAsync(edges_b + out_e[g] * erec, reinterpret_cast<char*>(d.d_acc_edges) + out_e[g] * erec, (e1 - out_e[g]) * erec, cudaMemcpyDeviceToHost, d.s_out));
+            if (!small_out && n1 > out_n[g] && n1 <= nonedge_cap)
                 CU(cudaMemcpyAsync(nonedge_idx + out_n[g], d.d_acc_nonedge + out_n[g], (n1 - out_n[g]) * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.s_out));
+            if (small_out && cm)     // this chunk's words of the bit map (chunks start at multiples of 64)
+                CU(cudaMemcpyAsync(bits_out + c0 / 32, d.d_acc_bits + (c0 - lo[g]) / 32, ((cm + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.s_out));
             out_e[g] = std::max(out_e[g], e1);
             out_n[g] = std::max(out_n[g], n1);
         }
@@ -1034,9 +1064,10 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
             }
             uint32_t nl = 0;
             int rc = enqueue_batch(s, d, d.stream, p, d_cand_k, compact, cm, per_cand ? d.d_per_cand[slot] : nullptr,
-                                   d.d_acc_edges, d.acc_e_cap, d.d_acc_nonedge, d.acc_n_cap, nullptr, c0, d.d_run,
+                                   d.d_acc_edges, d.acc_e_cap * sizeof(hc_edge) / erec, small_out ? nullptr : d.d_acc_nonedge,
+                                   small_out ? 0 : d.acc_n_cap, nullptr, c0, d.d_run,
                                    (stats && k == 0) ? d.ev[0] : nullptr, (stats && k == 0) ? d.ev[1] : nullptr, &nl,
-                                   runs ? &rdv : nullptr);
+                                   runs ? &rdv : nullptr, small_out, small_out ? d.d_acc_bits + (c0 - lo[g]) / 32 : nullptr);
             if (rc != HC_OK) return rc;
             launches += nl;
             CU(cudaMemcpyAsync(d.h_cnt + slot * HC_CNT_N, d.counters, HC_CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
@@ -1056,8 +1087,10 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         CU(cudaSetDevice(d.device));
         if (G > 1) {
             const uint64_t e1 = std::min<uint64_t>(dev_e[g], d.acc_e_cap), n1 = std::min<uint64_t>(dev_n[g], d.acc_n_cap);
-            if (e1 && te + e1 <= edges_cap) CU(cudaMemcpyAsync(edges + te, d.d_acc_edges, e1 * sizeof(hc_edge), cudaMemcpyDeviceToHost, d.s_out));
-            if (n1 && tn + n1 <= nonedge_cap) CU(cudaMemcpyAsync(nonedge_idx + tn, d.d_acc_nonedge, n1 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.s_out));
+            if (e1 && te + e1 <= edges_cap) CU(cudaMemcpyAsync(edges_b + te * erec, d.d_acc_edges, e1 * erec, cudaMemcpyDeviceToHost, d.s_out));
+            if (!small_out && n1 && tn + n1 <= nonedge_cap) CU(cudaMemcpyAsync(nonedge_idx + tn, d.d_acc_nonedge, n1 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.s_out));
+            if (small_out && lo[g + 1] > lo[g])
+                CU(cudaMemcpyAsync(bits_out + lo[g] / 32, d.d_acc_bits, ((lo[g + 1] - lo[g] + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.s_out));
         }
         te += dev_e[g];
         tn += dev_n[g];
@@ -1081,7 +1114,11 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
     *n_nonedges = tn;
     if (stats) { stats->total_ms = total_ms; stats->kernel_launches = launches; }
     if (result != HC_OK) return result;
-    if (te > edges_cap || tn > nonedge_cap)
+    if (small_out && (n & 63)) {   // the last word of the bit map is written whole by the host: bits beyond n are 0
+        const uint64_t last = n >> 6;
+        nonedge_idx[last] &= (1ull << (n & 63)) - 1ull;
+    }
+    if (te > edges_cap || (!small_out && tn > nonedge_cap))
         return fail(HC_ERR_CAPACITY, "hc_score_batch: output buffer too small (required sizes returned in n_edges/n_nonedges)");
     return HC_OK;
 }
@@ -1119,6 +1156,32 @@ int hc_score_batch_runs(hc_store* s, const hc_params* p, const uint32_t* run_anc
     const RunsHost rh{run_anchor, run_start, n_runs};
     return score_host(s, p, entries, 3, n, per_cand, edges, edges_cap, n_edges, nonedge_idx, nonedge_cap, n_nonedges, stats,
                       n ? &rh : nullptr);
+}
+
+int hc_score_batch_runs_small(hc_store* s, const hc_params* p, const uint32_t* run_anchor, const uint64_t* run_start, uint64_t n_runs,
+                              const hc_candidate_entry* entries, uint64_t n, void* edges, uint64_t edges_cap, uint64_t* n_edges,
+                              uint64_t* nonedge_bits, uint64_t* n_nonedges, hc_batch_stats* stats) {
+    if (n && (!run_anchor || !run_start || n_runs == 0)) return fail(HC_ERR_ARG, "hc_score_batch_runs_small: NULL run arrays");
+    if (n && !nonedge_bits) return fail(HC_ERR_ARG, "hc_score_batch_runs_small: NULL bit map");
+    if (s && s->n_reads > 0x7fffffffull) return fail(HC_ERR_ARG, "hc_score_batch_runs_small: more than 2^31-1 reads in the store");
+    if (n > 0xffffffffull) return fail(HC_ERR_ARG, "hc_score_batch_runs_small: a call takes fewer than 2^32 candidates");
+    if (n) {
+        if (run_start[0] != 0 || run_start[n_runs] != n) return fail(HC_ERR_ARG, "hc_score_batch_runs_small: run_start must begin at 0 and end at n");
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (long long r = 0; r < (long long)n_runs; r++) bad |= (run_start[r] >= run_start[r + 1]);
+        if (bad) return fail(HC_ERR_ARG, "hc_score_batch_runs_small: run_start must be strictly increasing (no empty runs)");
+    }
+    const RunsHost rh{run_anchor, run_start, n_runs};
+    return score_host(s, p, entries, 3, n, nullptr, reinterpret_cast<hc_edge*>(edges), edges_cap, n_edges, nonedge_bits, 0, n_nonedges, stats,
+                      n ? &rh : nullptr, 1);
+}
+
+int hc_score_batch_short_small(hc_store* s, const hc_params* p, const hc_candidate_short* cand, uint64_t n, void* edges,
+                               uint64_t edges_cap, uint64_t* n_edges, uint64_t* nonedge_bits, uint64_t* n_nonedges, hc_batch_stats* stats) {
+    if (n && !nonedge_bits) return fail(HC_ERR_ARG, "hc_score_batch_short_small: NULL bit map");
+    if (n > 0xffffffffull) return fail(HC_ERR_ARG, "hc_score_batch_short_small: a call takes fewer than 2^32 candidates");
+    return score_host(s, p, cand, 2, n, nullptr, reinterpret_cast<hc_edge*>(edges), edges_cap, n_edges, nonedge_bits, 0, n_nonedges, stats, nullptr, 1);
 }
 
 int hc_overlap_score_multi(const char* seq1, uint32_t len1, const char* seq2, uint32_t len2, const char* qual1,

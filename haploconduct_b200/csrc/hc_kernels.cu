@@ -789,18 +789,20 @@ __device__ __forceinline__ uint32_t as_n_counts(const hc_kparams& P, const hc_ca
     return nn | (fix << 16);
 }
 
-template <bool HAS_VOID, bool PACKED>
-__global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kernel(const hc_kparams P) {
+// WALK: the instantiation with the anchor walk in front of the lane-chunk rounds (one CTA of HC_WALK_WARPS warps per SM, it
+// keeps a second table in shared memory); without it two CTAs of HC_WARPS_MAX warps.
+template <bool HAS_VOID, bool PACKED, bool WALK>
+__global__ void __launch_bounds__((WALK ? HC_WALK_WARPS : HC_WARPS_MAX) * 32, WALK ? 1 : HC_MIN_CTAS) hc_score_kernel(const hc_kparams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t* T = reinterpret_cast<uint32_t*>(smem);
     const uint32_t ntab = (P.ncodes + 1u) * 256u;                     // score table, then the tail masks,
     uint32_t* VM = T + ntab;
     uint32_t* TAw = VM + HC_VM_WORDS;                                  // then (packed layout) the anchor-walk table and its masks
-    uint2* VMT = reinterpret_cast<uint2*>(TAw + (PACKED ? ntab : 0u));
-    const uint32_t tbl_entries = ntab + HC_VM_WORDS + (PACKED ? ntab + HC_AS_VMT_WORDS : 0u);
+    uint2* VMT = reinterpret_cast<uint2*>(TAw + (WALK ? ntab : 0u));
+    const uint32_t tbl_entries = ntab + HC_VM_WORDS + (WALK ? ntab + HC_AS_VMT_WORDS : 0u);
     for (uint32_t i = threadIdx.x; i < ntab; i += blockDim.x) T[i] = P.fx_table[i];
     if (threadIdx.x < HC_VM_WORDS) VM[threadIdx.x] = hc_packed_vmask(threadIdx.x);
-    if (PACKED) {
+    if (WALK) {
         for (uint32_t i = threadIdx.x; i < ntab; i += blockDim.x) TAw[i] = P.fx_table[ntab + i];
         if (threadIdx.x < 33u) VMT[threadIdx.x] = hc_as_vmask(threadIdx.x);
     }
@@ -839,7 +841,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
             load_and_setup(P, c, s, r1, r2);
 #ifndef HC_NO_PREFETCH
 #ifdef HC_PREFETCH_LIGHT
-            if (PACKED && P.anchor_walk) {   // the walk requests its blocks a step ahead itself: only what it needs first
+            if (WALK && P.anchor_walk) {   // the walk requests its blocks a step ahead itself: only what it needs first
                 if (s.w[0].L) { prefetch_l2(P.pk + (s.w[0].xpos & ~127ull)); prefetch_l2(P.pk + 16ull * s.w[0].ypos16); }
                 if (s.w[1].L) { prefetch_l2(P.pk + (s.w[1].xpos & ~127ull)); prefetch_l2(P.pk + 16ull * s.w[1].ypos16); }
             } else
@@ -849,7 +851,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
                 prefetch_window(P, s.w[1]);
             }
 #endif
-            if (PACKED && P.anchor_walk && !s.err) {   // N counts of windows the walk may take (rare: a read with one or two N)
+            if (WALK && P.anchor_walk && !s.err) {   // N counts of windows the walk may take (rare: a read with one or two N)
                 if (s.w[0].hasN == 1u && s.w[0].L) nfix0 = as_n_counts(P, c, r1, r2, 0, s.w[0]);
                 if (s.w[1].hasN == 1u && s.w[1].L) nfix1 = as_n_counts(P, c, r1, r2, 1, s.w[1]);
             }
@@ -859,7 +861,7 @@ __global__ void __launch_bounds__(HC_WARPS_MAX * 32, HC_MIN_CTAS) hc_score_kerne
         uint32_t c0 = (s.w[0].L + 31u) >> 5, c1 = (s.w[1].L + 31u) >> 5;     // lane-chunks left to the rounds below
 
         // ---- anchor walk: windows of candidates that share a read with their neighbours (packed layout)
-        if (PACKED && P.anchor_walk) {
+        if (WALK && P.anchor_walk) {
             const uint32_t id1 = valid ? c.idx1 : 0xffffffffu, id2 = valid ? c.idx2 : 0xfffffffeu;
             const uint32_t p1 = __shfl_up_sync(0xffffffffu, id1, 1), p2 = __shfl_up_sync(0xffffffffu, id2, 1);
             const uint32_t n1 = __shfl_down_sync(0xffffffffu, id1, 1), n2 = __shfl_down_sync(0xffffffffu, id2, 1);
@@ -1365,6 +1367,44 @@ __device__ __forceinline__ void emit_edge(const hc_kparams& P, u64 i, uint32_t c
     *dst = e;
 }
 
+// The same edge as a small record (hc_edge_small / hc_edge_small_exact): what a host that keeps the candidate list cannot
+// derive itself -- counts, flags and the score resp. the exact mean logs.
+template <bool EXACT>
+__device__ __forceinline__ void emit_edge_small(const hc_kparams& P, u64 i, uint32_t cfull, u64 cand_offset, void* dst_base, u64 k) {
+    const hc_candidate cd = load_candidate(P, i);
+    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx1));
+    const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(P.rdesc + cd.idx2));
+    const hc_tmp32 t = P.tmp[i];
+    double ml[2];
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        if (t.tl[w] == 0) ml[w] = __longlong_as_double(0x7ff8000000000000LL);   // NaN: window not scored
+        else if (cfull & HC_CLS_EXACT) ml[w] = __longlong_as_double((long long)t.S[w]);
+        else ml[w] = fx_mean(t.S[w], t.tl[w]);
+    }
+    const uint32_t two = ((r1.w | r2.w) & HC_LEN_MASK) != 0;
+    const uint32_t flags = ((cfull & HC_CLS_BOTH) ? HC_EDGE_BOTH : 0u) | (two ? HC_EDGE_TWO : 0u) | ((cfull & HC_CLS_EXACT) ? HC_EDGE_EXACT : 0u);
+    const uint32_t m0 = min(t.mm[0], 0xffffu), m1 = min(t.mm[1], 0xffffu), l0 = min(t.tl[0], 0xffffu), l1 = min(t.tl[1], 0xffffu);
+    if (EXACT) {
+        hc_edge_small_exact e;
+        e.cand = (uint32_t)(i + cand_offset);
+        e.mismatches[0] = (uint16_t)m0; e.mismatches[1] = (uint16_t)m1;
+        e.compared[0] = (uint16_t)l0; e.compared[1] = (uint16_t)l1;
+        e.flags = flags | ((t.tl[0] > 0xffffu || t.tl[1] > 0xffffu) ? HC_EDGE_OVERFLOW : 0u);
+        e.mean_log[0] = ml[0];
+        e.mean_log[1] = ml[1];
+        reinterpret_cast<hc_edge_small_exact*>(dst_base)[k] = e;
+    } else {
+        hc_edge_small e;
+        e.cand = (uint32_t)(i + cand_offset);
+        e.mismatches[0] = (uint16_t)m0; e.mismatches[1] = (uint16_t)m1;
+        e.compared[0] = (uint16_t)l0; e.compared[1] = (uint16_t)l1;
+        e.flags = flags | ((t.tl[0] > 0xffffu || t.tl[1] > 0xffffu) ? HC_EDGE_OVERFLOW : 0u);
+        e.score = combine_score(two, cfull & HC_CLS_BOTH, t.tl[0] ? exp(ml[0]) : 0.0, t.tl[1] ? exp(ml[1]) : 0.0);
+        reinterpret_cast<hc_edge_small*>(dst_base)[k] = e;
+    }
+}
+
 // Each thread owns four consecutive candidates (one 32-bit load of class bytes); ranks come from a warp scan of the
 // packed (edges | non-edges << 16) counts and the per-warp totals, so the lists keep the input order.
 __global__ void __launch_bounds__(HC_CB_THREADS) hc_compact_scatter(const hc_kparams P, const u64* __restrict__ blockoffs,
@@ -1431,6 +1471,39 @@ __global__ void __launch_bounds__(256) hc_emit_edges(const hc_kparams P, const u
     }
 }
 
+template <bool EXACT>
+__global__ void __launch_bounds__(256) hc_emit_edges_small(const hc_kparams P, const uint32_t* __restrict__ edge_src, void* edges,
+                                                           u64 edges_cap, u64 cand_offset) {
+    const u64 n_edges = P.counters[HC_CNT_EDGES];
+    const u64 run_e = P.run ? P.run[0] : 0ull;
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n_edges; k += (u64)gridDim.x * blockDim.x) {
+        if (run_e + k >= edges_cap) break;
+        const u64 i = edge_src[k];
+        emit_edge_small<EXACT>(P, i, P.cls[i], cand_offset, edges, run_e + k);
+    }
+}
+
+// One bit per candidate: 1 = non-edge overlap (:410-413).  One thread per 32 candidates; bits[w] covers candidates 32w..32w+31.
+__global__ void __launch_bounds__(256) hc_nonedge_bits(const uint8_t* __restrict__ cls, u64 n, uint32_t* __restrict__ bits) {
+    const u64 words = (n + 31) >> 5;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (u64)gridDim.x * blockDim.x) {
+        const u64 i0 = w << 5;
+        uint32_t out = 0;
+        if (i0 + 32 <= n) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(cls + i0)), b = __ldg(reinterpret_cast<const uint4*>(cls + i0) + 1);
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t ne = (v[q] >> 1) & ~v[q] & 0x01010101u;          // class bits 10 = non-edge
+                out |= (((ne * 0x01020408u) >> 24) & 0xfu) << (4 * q);          // bits 0, 8, 16, 24 -> bits 0..3 of a nibble
+            }
+        } else {
+            for (u64 j = i0; j < n; j++) out |= (uint32_t)((cls[j] & HC_CLS_MASK) == HC_CLASS_NONEDGE) << (j - i0);
+        }
+        bits[w] = out;
+    }
+}
+
 // tile_run[t] = the run that holds candidate 32 * t; one thread per run writes the tiles that start inside it
 __global__ void hc_tile_runs(const uint32_t* __restrict__ run_start, uint32_t n_runs, uint32_t* __restrict__ tile_run) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += gridDim.x * blockDim.x) {
@@ -1447,15 +1520,16 @@ __global__ void hc_compact_advance(unsigned long long* run, const unsigned long 
 }  // namespace
 
 // ---- launchers ----------------------------------------------------------------------------------------
-cudaError_t hc_score_occupancy(uint32_t ncodes, int packed, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg) {
-    // score table (+ the anchor-walk table and its masks in the packed layout) + the tail masks, per CTA
-    const size_t table = (size_t)(ncodes + 1u) * 1024u * (packed ? 2u : 1u) + HC_VM_WORDS * 4u + (packed ? HC_AS_VMT_WORDS * 4u : 0u);
+cudaError_t hc_score_occupancy(uint32_t ncodes, int walk, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg) {
+    // score table + tail masks (+ the anchor-walk table and its masks), per CTA
+    const size_t table = (size_t)(ncodes + 1u) * 1024u * (walk ? 2u : 1u) + HC_VM_WORDS * 4u + (walk ? HC_AS_VMT_WORDS * 4u : 0u);
+    const int max_ctas = walk ? 1 : HC_MIN_CTAS;                                 // what the register allocation allows
     int best_warps = 0, best_nw = 0, best_ctas = 0;
-    for (int nw = HC_WARPS_MAX; nw >= 4; nw -= 4) {     // the tables are per CTA: prefer few large CTAs
+    for (int nw = walk ? HC_WALK_WARPS : HC_WARPS_MAX; nw >= 4; nw -= 4) {       // the tables are per CTA: prefer large CTAs
         const size_t per_cta = table + (size_t)nw * HC_WARP_SCRATCH + 1024u;   // +1 KB the driver reserves per CTA
         if (per_cta > 227u * 1024u) continue;
         int ctas = (int)(smem_per_sm / per_cta);
-        if (ctas > HC_MIN_CTAS) ctas = HC_MIN_CTAS;                            // what the register allocation allows
+        if (ctas > max_ctas) ctas = max_ctas;
         if (ctas * nw * 32 > 2048) ctas = 2048 / (nw * 32);
         if (ctas < 1) continue;
         if (ctas * nw > best_warps) { best_warps = ctas * nw; best_nw = nw; best_ctas = ctas; }
@@ -1468,8 +1542,10 @@ cudaError_t hc_score_occupancy(uint32_t ncodes, int packed, int sm_count, size_t
 }
 
 cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaStream_t st) {
-    void (*fn)(const hc_kparams) = P.packed ? (P.has_void ? hc_score_kernel<true, true> : hc_score_kernel<false, true>)
-                                            : (P.has_void ? hc_score_kernel<true, false> : hc_score_kernel<false, false>);
+    void (*fn)(const hc_kparams);
+    if (P.packed && P.anchor_walk) fn = P.has_void ? hc_score_kernel<true, true, true> : hc_score_kernel<false, true, true>;
+    else if (P.packed) fn = P.has_void ? hc_score_kernel<true, true, false> : hc_score_kernel<false, true, false>;
+    else fn = P.has_void ? hc_score_kernel<true, false, false> : hc_score_kernel<false, false, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return e;
     fn<<<cfg.blocks, cfg.threads, cfg.smem, st>>>(P);
@@ -1484,7 +1560,7 @@ cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint
 }
 
 cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st) {
-    hc_exact_kernel<<<148 * 8, 128, 0, st>>>(P);
+    hc_exact_kernel<<<1184, 128, 0, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -1493,7 +1569,7 @@ uint32_t hc_compact_blocks(uint64_t n) { return (uint32_t)((n + HC_CB_ITEMS - 1)
 // d_blockcounts: uint32[2*nblocks] followed (8-byte aligned) by uint64[2*nblocks] block offsets
 cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge,
                               uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, unsigned long long* d_run,
-                              cudaStream_t st) {
+                              cudaStream_t st, int small_out, uint32_t* d_bits) {
     const uint32_t nb = hc_compact_blocks(P.n);
     u64* offs = reinterpret_cast<u64*>(d_blockcounts + 2ull * nb + (2ull * nb & 1ull));
     if (nb > 0) {
@@ -1504,8 +1580,14 @@ cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t ed
         // P.flagged has been consumed by the reference-order pass; it now carries the source index of every edge
         hc_compact_scatter<<<nb, HC_CB_THREADS, 0, st>>>(P, offs, P.flagged, d_nonedge, nonedge_cap, cand_offset);
         const u64 want = (P.n + 255) / 256;
-        const unsigned eb = (unsigned)(want < 148ull * 8 ? want : 148ull * 8);
-        hc_emit_edges<<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
+        const unsigned eb = (unsigned)(want < 1184ull ? want : 1184ull);
+        if (!small_out) hc_emit_edges<<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
+        else if (P.exact_edges) hc_emit_edges_small<true><<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
+        else hc_emit_edges_small<false><<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
+        if (small_out && d_bits) {
+            const u64 wantb = (((P.n + 31) >> 5) + 255) / 256;
+            hc_nonedge_bits<<<(unsigned)(wantb < 1184ull ? wantb : 1184ull), 256, 0, st>>>(P.cls, P.n, d_bits);
+        }
     }
     if (d_run) hc_compact_advance<<<1, 1, 0, st>>>(d_run, P.counters);
     return cudaGetLastError();

@@ -8,10 +8,13 @@
 #include "hc_layout.h"
 
 #ifndef HC_WARPS_MAX
-#define HC_WARPS_MAX 20          // warps per CTA (one CTA per SM: the score tables are per CTA); 96 registers per thread
+#define HC_WARPS_MAX 12          // warps per CTA of the lane-chunk kernel
 #endif
 #ifndef HC_MIN_CTAS
-#define HC_MIN_CTAS 1             // resident CTAs per SM the register allocation aims at
+#define HC_MIN_CTAS 2             // ... and resident CTAs per SM the register allocation aims at
+#endif
+#ifndef HC_WALK_WARPS
+#define HC_WALK_WARPS 20         // anchor-walk instantiation: one CTA per SM (two tables in shared memory), 96 registers per thread
 #endif
 #define HC_LANE_CHUNK 32u        // positions one lane handles per step (two 16-position halves)
 #ifndef HC_PARTMAX
@@ -106,10 +109,12 @@ struct hc_launch_cfg {
 cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaStream_t st);
 cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st);
 cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint32_t* tile_run, cudaStream_t st);
+// small_out: d_edges receives hc_edge_small (hc_edge_small_exact with P.exact_edges) records and d_bits one bit per candidate
+// of the batch (1 = non-edge overlap) instead of the index list
 cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t edges_cap, uint64_t* d_nonedge,
                               uint64_t nonedge_cap, uint32_t* d_blockcounts, uint64_t cand_offset, unsigned long long* d_run,
-                              cudaStream_t st);
-cudaError_t hc_score_occupancy(uint32_t ncodes, int packed, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg);
+                              cudaStream_t st, int small_out = 0, uint32_t* d_bits = nullptr);
+cudaError_t hc_score_occupancy(uint32_t ncodes, int walk, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg);
 uint32_t hc_compact_blocks(uint64_t n);
 
 #endif

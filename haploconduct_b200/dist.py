@@ -38,6 +38,36 @@ def _gather_bytes(local: np.ndarray, device: torch.device, group=None) -> np.nda
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(outs, sizes)]) if sum(sizes) else np.zeros(0, np.uint8)
 
 
+class DeviceGather:
+    """Ordered concatenation of per-rank record lists that stay in device memory (no host hop): an all-gather of the
+    counts, then one all-gather of the lists padded to the longest one (NCCL over NVLink on GPUs; every rank ends up
+    with all lists, the consumer slices them in rank order = input order).  Buffers are allocated once and reused, so
+    a call is two collectives on the given stream."""
+
+    def __init__(self, rec_bytes: int, max_records: int, device: torch.device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rec = rec_bytes
+        self.cap = max_records
+        self.device = device
+        self.counts = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self.padded = torch.zeros((self.world, max_records * rec_bytes), dtype=torch.uint8, device=device)
+
+    def gather(self, records: torch.Tensor, count: torch.Tensor) -> None:
+        """records: uint8 tensor holding this rank's list (at least cap * rec bytes are readable), count: int64[1] on the
+        device.  Asynchronous on the current stream; results in self.counts / self.padded."""
+        dist.all_gather_into_tensor(self.counts, count.reshape(1), group=self.group)
+        dist.all_gather_into_tensor(self.padded.reshape(-1), records.reshape(-1)[: self.cap * self.rec], group=self.group)
+
+    def lists(self):
+        """Per-rank views of the gathered records (device tensors), rank order; synchronises to read the counts."""
+        c = self.counts.cpu().tolist()
+        return [self.padded[r, : c[r] * self.rec] for r in range(self.world)]
+
+    def concatenated(self) -> torch.Tensor:
+        return torch.cat(self.lists())
+
+
 def gather_results(edges: np.ndarray, nonedge_idx: np.ndarray, shard_start: int, device: Optional[torch.device] = None,
                    group=None) -> Tuple[np.ndarray, np.ndarray]:
     """`edges` (formats.EDGE) / `nonedge_idx` (uint64) hold indices local to this rank's shard;

@@ -100,6 +100,11 @@ RESULT = np.dtype(
 )
 EDGE = np.dtype([("cand", "<u8"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos3", "<i4"), ("pos4", "<i4"),
                  ("mean_log", "<f8", (2,))])
+EDGE_SMALL = np.dtype([("cand", "<u4"), ("mismatches", "<u2", (2,)), ("compared", "<u2", (2,)), ("flags", "<u4"), ("score", "<f8")])
+EDGE_SMALL_EXACT = np.dtype([("cand", "<u4"), ("mismatches", "<u2", (2,)), ("compared", "<u2", (2,)), ("flags", "<u4"),
+                             ("mean_log", "<f8", (2,))])
+EDGE_BOTH, EDGE_TWO, EDGE_EXACT, EDGE_OVERFLOW = 1, 2, 4, 8
+assert EDGE_SMALL.itemsize == 24 and EDGE_SMALL_EXACT.itemsize == 32
 BATCH_STATS = np.dtype(
     [
         ("n_candidates", "<u8"), ("n_edges", "<u8"), ("n_nonedges", "<u8"), ("n_exact", "<u8"),

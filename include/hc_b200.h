@@ -162,6 +162,40 @@ typedef struct {
                                   bit-identical to the reference evaluates exp() with its own libm (:138).  */
 } hc_edge;                     /* 48 bytes */
 
+/* Small outputs, for a host that keeps its candidate list (every real caller does: the non-edge overlaps are written
+ * to nonedge_overlaps.txt from the host's own records, src/EdgeCalculator.cpp:546-555, and an Edge is built from the
+ * overlap it came from, :415-422).  What travels back is one BIT per candidate for the non-edge overlaps and a 24-byte
+ * record per accepted edge (32 bytes with HC_FLAG_EXACT_EDGE_SCORES) -- a third of the device->host bytes of hc_edge +
+ * index lists.  Everything else of hc_edge follows from the candidate:
+ *   mismatch_rate = max over the scored windows of (double)(float)mismatches[w] / compared[w]   (0 mismatches: 0.0;
+ *                   a window with compared == 0 counts as 1.0; one window only unless HC_EDGE_TWO)          (:132,:254)
+ *   score (exact) = HC_EDGE_TWO ? (HC_EDGE_BOTH ? 0.5*(exp(m0)+exp(m1)) : min(exp(m0), exp(m1))) : exp(m0), a window
+ *                   with compared == 0 scoring 0                                                             (:138,:256-261)
+ *   pos3 / pos4   = hc_edge_extra_pos() below                                                      (:222,:262-263,:300-301,:361-372) */
+#define HC_EDGE_BOTH     1u   /* every window is above edge_threshold                                          */
+#define HC_EDGE_TWO      2u   /* the candidate has two windows (a paired read is involved)                     */
+#define HC_EDGE_EXACT    4u   /* decided / summed in the reference's order                                     */
+#define HC_EDGE_OVERFLOW 8u   /* a count does not fit 16 bits (windows of 65536+ positions): use hc_score_batch* */
+typedef struct {
+    uint32_t cand;             /* index into the candidate array of the call (a call takes fewer than 2^32)    */
+    uint16_t mismatches[2];    /* mismatch_count per window (src/EdgeCalculator.cpp:105)                       */
+    uint16_t compared[2];      /* total_len per window (:104); 0 = window not scored                           */
+    uint32_t flags;            /* HC_EDGE_*                                                                    */
+    double   score;            /* Edge::score, device exp()                                                    */
+} hc_edge_small;               /* 24 bytes */
+typedef struct {
+    uint32_t cand;
+    uint16_t mismatches[2];
+    uint16_t compared[2];
+    uint32_t flags;
+    double   mean_log[2];      /* (1.0/total_len)*total_score per window, the reference's doubles bit for bit (:137) */
+} hc_edge_small_exact;         /* 32 bytes */
+
+/* Edge::pos3 / pos4 of a candidate (size_t arithmetic truncated to int, as the reference's assignments do); host
+ * arithmetic.  len1a/len1b: sequence lengths of read 1 (/1, /2; len1b == 0 for a single-end read), likewise read 2. */
+void hc_edge_extra_pos(uint32_t pos1, uint32_t pos2, char ord, uint32_t len1a, uint32_t len1b, uint32_t len2a, uint32_t len2b,
+                       int32_t* pos3, int32_t* pos4);
+
 typedef struct {
     uint64_t n_candidates;
     uint64_t n_edges;
@@ -227,6 +261,22 @@ int hc_score_batch_runs(hc_store* s, const hc_params* p,
                         hc_edge* edges, uint64_t edges_cap, uint64_t* n_edges,
                         uint64_t* nonedge_idx, uint64_t nonedge_cap, uint64_t* n_nonedges,
                         hc_batch_stats* stats /* nullable */);
+
+/* hc_score_batch_runs with small outputs: `edges` receives hc_edge_small records (hc_edge_small_exact when
+ * p->flags has HC_FLAG_EXACT_EDGE_SCORES), in input order; nonedge_bits must hold ceil(n / 64) words and receives
+ * bit (i % 64) of word i / 64 = 1 iff candidate i is a non-edge overlap (:410-413); *n_nonedges = their number. */
+int hc_score_batch_runs_small(hc_store* s, const hc_params* p,
+                              const uint32_t* run_anchor, const uint64_t* run_start, uint64_t n_runs,
+                              const hc_candidate_entry* entries, uint64_t n,
+                              void* edges, uint64_t edges_cap, uint64_t* n_edges,
+                              uint64_t* nonedge_bits, uint64_t* n_nonedges,
+                              hc_batch_stats* stats /* nullable */);
+/* The same on 12-byte records (lists that were not cut into runs). */
+int hc_score_batch_short_small(hc_store* s, const hc_params* p,
+                               const hc_candidate_short* cand, uint64_t n,
+                               void* edges, uint64_t edges_cap, uint64_t* n_edges,
+                               uint64_t* nonedge_bits, uint64_t* n_nonedges,
+                               hc_batch_stats* stats /* nullable */);
 
 /* Same, but every buffer is DEVICE memory on device `device` (one of the store's devices) and the
  * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream).

@@ -53,6 +53,21 @@ def run_case(name: str, rs: F.ReadSet, cands: np.ndarray, ps: dict) -> None:
           (name, rs.n_reads, len(cands), len(out["cands"]), cls.tolist(), out["graph_edges"]))
 
 
+def save_fno_state(name: str, rs: F.ReadSet, d: str) -> None:
+    """What the product's C++ binding (haploconduct_b200/host/hcb_fno.h, hc_fno) starts from: the reads, the state the
+    reference's findNextOverlaps* started from (ref_driver --fno-state) and nonedge_overlaps.txt; the expected output
+    is ref_lines of <name>.npz."""
+    with open(d + "/state.txt", "rb") as f:
+        state = f.read()
+    nonedge = b""
+    if os.path.exists(d + "/nonedge_overlaps.txt"):
+        with open(d + "/nonedge_overlaps.txt", "rb") as f:
+            nonedge = f.read()
+    np.savez_compressed(os.path.join(GOLDEN, "fnostate_" + name + ".npz"), ids=rs.ids, descs=rs.descs, bases=rs.bases, quals=rs.quals,
+                        n_single=np.int64(rs.n_single), state=np.frombuffer(state, dtype=np.uint8),
+                        nonedge=np.frombuffer(nonedge, dtype=np.uint8))
+
+
 def run_fno_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> None:
     """Merge iteration + the reference's own findNextOverlaps(): keeps its inputs (array form) and its overlaps.txt."""
     import subprocess
@@ -60,7 +75,7 @@ def run_fno_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> Non
     d = tempfile.mkdtemp(prefix="hc_golden_fno_")
     F.write_fastq_set(rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", cands, rs.ids)
-    cmd = [O.REF_DRIVER, "--overlaps", d + "/ov.txt", "--run", "--merge-fno1", d + "/fno_in.txt"] + args
+    cmd = [O.REF_DRIVER, "--overlaps", d + "/ov.txt", "--run", "--merge-fno1", d + "/fno_in.txt", "--fno-state", d + "/state.txt"] + args
     if rs.n_single:
         cmd += ["--singles", d + "/s.fastq"]
     if rs.n_reads > rs.n_single:
@@ -72,6 +87,7 @@ def run_fno_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> Non
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), visited=fi.visited, label=fi.label, vertex_read=fi.vertex_read,
                         sr_off=fi.sr_off, sr_idx=fi.sr_idx, sr_sub=fi.sr_sub, superread=fi.superread,
                         flags=np.array([fi.resolve_orientations, fi.no_inclusions]), edges=fi.edges, ref_lines=np.array(ref))
+    save_fno_state(name, rs, d)
     print("%-28s vertices=%d superreads=%d (paired %d) edges=%d -> %d overlap lines" %
           (name, len(fi.visited), len(fi.superread), int((fi.superread["len2"] > 0).sum()), len(fi.edges), len(ref)))
 
@@ -83,8 +99,8 @@ def run_fno3_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> No
     d = tempfile.mkdtemp(prefix="hc_golden_fno3_")
     F.write_fastq_set(rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", cands, rs.ids)
-    cmd = [O.REF_DRIVER, "--overlaps", d + "/ov.txt", "--run", "--merge-fno3", d + "/fno3_in.txt", "--cliques", "1",
-           "--remove_branches", "0"] + args
+    cmd = [O.REF_DRIVER, "--overlaps", d + "/ov.txt", "--run", "--merge-fno3", d + "/fno3_in.txt", "--fno-state", d + "/state.txt",
+           "--cliques", "1", "--remove_branches", "0"] + args
     if rs.n_single:
         cmd += ["--singles", d + "/s.fastq"]
     if rs.n_reads > rs.n_single:
@@ -95,6 +111,7 @@ def run_fno3_case(name: str, rs: F.ReadSet, cands: np.ndarray, args: list) -> No
         ref = f.read().split("\n")[:-1]
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), off=fi.off, sr_idx=fi.sr_idx, sr_pos=fi.sr_pos, reads=fi.reads,
                         flags=np.array([fi.no_inclusions]), ref_lines=np.array(ref))
+    save_fno_state(name, rs, d)
     print("%-28s originals=%d reads=%d -> %d overlap lines" % (name, len(fi.off) - 1, len(fi.reads), len(ref)))
 
 
@@ -151,9 +168,36 @@ def run_consensus_case(name: str, seed: int, n_problems: int, min_clique_size: i
         name, len(probs), rs.n_reads, sum(1 for r in ref if r[2] != "0"), sum(1 for r in ref if int(r[1]) < 0), sum(r[3].count("N") for r in ref)))
 
 
+def fno_cases(full: F.ReadSet) -> None:
+    # ---- FindNextOverlaps (FNO1): the reference's overlaps.txt after one merge iteration
+    s700 = full.subset(range(0, 700))
+    cs = W.seed_candidates(s700, k=24, orientations=((1, 1),))
+    run_fno_case("fno1_savage_singles", s700, cs, ["--edge_threshold", "0.97", "--min_overlap_len", "200", "--keep_singletons", "200"])
+    for k, (seed, ns, npair, div) in enumerate(((5, 150, 250, (0.0, 0.0, 0.0)), (6, 0, 400, (0.0, 0.0)), (7, 300, 100, (0.0, 0.01)))):
+        sx = W.synth_readset(ns, npair, genome_len=1500, n_strains=len(div), divergence=div, seed=seed, n_rate=0.0002, flip_fraction=0.2)
+        cx = W.geometry_candidates(sx, 6000, seed=seed + 1, junk_fraction=0.02, min_ov=40)
+        run_fno_case("fno1_synth_paired_%d" % k, sx.rs, cx, ["--edge_threshold", "0.9", "--min_overlap_len", "80", "--keep_singletons", "0"]
+                     + (["--no_inclusion_overlaps", "1"] if k == 2 else []))
+        if k != 1:
+            run_fno3_case("fno3_synth_cliques_%d" % k, sx.rs, cx, ["--edge_threshold", "0.9", "--min_overlap_len", "80", "--keep_singletons", "0"]
+                          + (["--no_inclusion_overlaps", "1"] if k == 2 else []))
+    # config 5: contigs of 1-10 kb (Phred up to 93) tiled over 3 strains, S-S overlaps, the flags of SAVAGE stage b
+    # (scripts/pipeline_per_stage.py:214-247: FNO=1, remove_trans=1, optimize=false, ignore_inclusions, keep_singletons =
+    # max(min_overlap_len, min_read_len)), one merge iteration + FNO1
+    sc = W.synth_readset(500, 0, genome_len=60000, read_len=(1000, 10000), qmax=93, q_lo=30, n_strains=3, divergence=(0.0, 0.01, 0.02),
+                         seed=20261019, n_rate=0.0)
+    cc = W.geometry_candidates(sc, 30000, seed=11, junk_fraction=0.02, min_ov=100)
+    run_fno_case("fno1_contigs_stage_b", sc.rs, cc, ["--edge_threshold", "0.995", "--min_overlap_len", "100", "--keep_singletons", "100",
+                                                      "--ignore_inclusions", "1", "--min_read_len", "100"])
+
+
 def main() -> None:
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--only-fno" in sys.argv:
+        R = REF + "/savage/example/input_fas/"
+        fno_cases(F.load_fastq_set(R + "singles.fastq", R + "paired1.fastq", R + "paired2.fastq"))
+        return
     # C1: savage/example, stage-a parameters (savage.py:384-385, savage/README.md:303: -m 200)
     R = REF + "/savage/example/input_fas/"
     full = F.load_fastq_set(R + "singles.fastq", R + "paired1.fastq", R + "paired2.fastq")
@@ -192,18 +236,7 @@ def main() -> None:
     run_consensus_case("consensus_illumina", 3, 160, 3, 0.9)
     run_consensus_case("consensus_wide_qualities", 4, 120, 2, 0.99, qmax=93, read_len=(200, 900))
 
-    # ---- FindNextOverlaps (FNO1): the reference's overlaps.txt after one merge iteration
-    s700 = full.subset(range(0, 700))
-    cs = W.seed_candidates(s700, k=24, orientations=((1, 1),))
-    run_fno_case("fno1_savage_singles", s700, cs, ["--edge_threshold", "0.97", "--min_overlap_len", "200", "--keep_singletons", "200"])
-    for k, (seed, ns, npair, div) in enumerate(((5, 150, 250, (0.0, 0.0, 0.0)), (6, 0, 400, (0.0, 0.0)), (7, 300, 100, (0.0, 0.01)))):
-        sx = W.synth_readset(ns, npair, genome_len=1500, n_strains=len(div), divergence=div, seed=seed, n_rate=0.0002, flip_fraction=0.2)
-        cx = W.geometry_candidates(sx, 6000, seed=seed + 1, junk_fraction=0.02, min_ov=40)
-        run_fno_case("fno1_synth_paired_%d" % k, sx.rs, cx, ["--edge_threshold", "0.9", "--min_overlap_len", "80", "--keep_singletons", "0"]
-                     + (["--no_inclusion_overlaps", "1"] if k == 2 else []))
-        if k != 1:
-            run_fno3_case("fno3_synth_cliques_%d" % k, sx.rs, cx, ["--edge_threshold", "0.9", "--min_overlap_len", "80", "--keep_singletons", "0"]
-                          + (["--no_inclusion_overlaps", "1"] if k == 2 else []))
+    fno_cases(full)
 
 if __name__ == "__main__":
     main()

@@ -23,6 +23,11 @@
 //                    state, super-reads with sub-read indices, and the edge stream in the order the
 //                    reference processes it -- then run the reference's findNextOverlaps() itself,
 //                    which writes overlaps.txt into the cwd.
+//   --fno-state F    with --merge-fno1 / --merge-fno3: also dump to F the STATE SRBuilder::findNextOverlaps /
+//                    findNextOverlaps3 start from -- adjacency lists, branching and inclusion edges, vertex labels,
+//                    visited, new ids, super-reads with cliques, sub-read indices and original reads -- i.e. the input
+//                    of the product's C++ binding (haploconduct_b200/host/hcb_fno.h), which produces the edge stream
+//                    itself.
 //   --merge-fno3 F   same iteration, but for SRBuilder::findNextOverlaps3 (src/FindNextOverlaps3.cpp:20-173):
 //                    dumps the original-read -> super-read lists in the iteration order of the
 //                    reference's std::unordered_map, then runs findNextOverlaps3() itself.
@@ -98,7 +103,7 @@ int main(int argc, char** argv) {
     ps.fno = 2;
     ps.output_dir = "";
 
-    std::string dump_cands, dump_graph, merge_fno1, consensus_in, consensus_out;
+    std::string dump_cands, dump_graph, merge_fno1, consensus_in, consensus_out, fno_state;
     bool fno3 = false, use_cliques = false;
     ps.keep_singletons = 0;
     ps.remove_trans = 1;
@@ -135,6 +140,7 @@ int main(int argc, char** argv) {
         else if (a == "--dump-graph") dump_graph = need("--dump-graph");
         else if (a == "--merge-fno1") merge_fno1 = need("--merge-fno1");
         else if (a == "--merge-fno3") { merge_fno1 = need("--merge-fno3"); fno3 = true; }
+        else if (a == "--fno-state") fno_state = need("--fno-state");
         else if (a == "--cliques") use_cliques = std::atoi(need("--cliques")) != 0;
         else if (a == "--min_clique_size") ps.min_clique_size = std::atoi(need("--min_clique_size"));
         else if (a == "--min_qual") ps.min_qual = std::atof(need("--min_qual"));
@@ -376,6 +382,47 @@ int main(int argc, char** argv) {
             srb->cliquesToSuperreads();                                   // :422
         } else {
             srb->mergeAlongEdges();                                       // :441
+        }
+        if (!fno_state.empty()) {
+            // the state both FindNextOverlaps variants start from (input of hcb::SRBuilder, hcb_fno.h)
+            FILE* fs = std::fopen(fno_state.c_str(), "w");
+            if (!fs) { std::fprintf(stderr, "cannot write %s\n", fno_state.c_str()); return 1; }
+            const size_t Vn = graph->getVertexCount();
+            std::fprintf(fs, "P\t%d\t%d\t%d\t%a\t%lu\n", (int)ps.resolve_orientations, (int)ps.no_inclusions, (int)ps.optimize,
+                         ps.edge_threshold, (unsigned long)Vn);
+            for (size_t v = 0; v < Vn; v++) {
+                long nid = -1;
+                if (srb->nodes_to_new_IDs.count(v)) nid = (long)srb->nodes_to_new_IDs.at(v);
+                const int label = v < graph->vertex_orientations.size() ? (int)graph->getOrientation(v) : 1;
+                std::fprintf(fs, "V\t%lu\t%d\t%ld\t%d\n", (unsigned long)v, (int)srb->visited[v], nid, label);
+            }
+            auto put_edge = [&](const char* tag, long k, const Edge& e) {
+                std::fprintf(fs, "%s\t%ld\t%lu\t%lu\t%d\t%d\t%c\t%d\t%d\t%a\t%d\t%d\t%d\n", tag, k, e.get_vertex(1), e.get_vertex(2),
+                             e.get_pos(1), e.get_pos(2), e.get_ord(), (int)e.get_ori(1), (int)e.get_ori(2), e.get_score(), e.get_perc(),
+                             e.get_len(1), e.get_len(2));
+            };
+            for (auto& lst : graph->adj_out) for (auto& e : lst) put_edge("A", 0, e);
+            for (auto& e : graph->branching_edges) put_edge("B", 0, e);
+            for (size_t k = 0; k < graph->inclusion_edges.size(); k++) for (auto& e : graph->inclusion_edges[k]) put_edge("I", (long)k, e);
+            auto put_sr = [&](char kind, const Read& r) {
+                const unsigned long l1 = r.is_paired() ? r.get_seq(1).size() : r.get_seq(0).size();
+                const unsigned long l2 = r.is_paired() ? r.get_seq(2).size() : 0;
+                std::fprintf(fs, "S\t%c\t%lu\t%lu\t%lu", kind, r.get_read_id(), l1, l2);
+                if (kind != 't') {
+                    for (auto node : r.get_sorted_clique(kind == 'p' ? 1 : 0)) {
+                        const SubreadInfo si = r.get_subread_info(node);
+                        std::fprintf(fs, "\t%lu:%d:%d:%d:%d", (unsigned long)node, si.index1, si.index2, si.startpos1, si.startpos2);
+                    }
+                }
+                std::fprintf(fs, "\nO");
+                const std::unordered_map<read_id_t, OriginalIndex> originals = r.get_original_reads();   // the copy the reference iterates
+                for (auto it : originals) std::fprintf(fs, "\t%lu:%ld:%ld", it.first, it.second.index1, it.second.index2);
+                std::fprintf(fs, "\n");
+            };
+            for (auto& r : srb->single_SR_vec) put_sr('s', r);
+            for (auto& r : srb->paired_SR_vec) put_sr('p', r);
+            for (auto& r : srb->trivial_SR_vec) put_sr('t', r);
+            std::fclose(fs);
         }
         if (fno3) {
             // what findNextOverlaps3 builds (src/FindNextOverlaps3.cpp:26-76), with the same container

@@ -68,3 +68,36 @@ def test_shard_ranges_tile_the_batch():
             r = [D.shard_range(n, k, w) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+
+
+def _gather_worker(rank, world, port, outdir):
+    import torch
+    import torch.distributed as dist
+    from haploconduct_b200 import dist as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rec, cap = 24, 50
+    g = D.DeviceGather(rec, cap, torch.device("cpu"))
+    for rnd in range(2):                      # buffers are reused between calls
+        n = (7 * rank + 3 + rnd) % cap
+        mine = torch.zeros((cap, rec), dtype=torch.uint8)
+        mine[:n] = torch.arange(n * rec, dtype=torch.int64).reshape(n, rec).to(torch.uint8) + rank
+        mine[n:] = 255                        # beyond the count: must not show up
+        g.gather(mine, torch.tensor([n], dtype=torch.int64))
+        got = g.concatenated()
+        want = []
+        for r in range(world):
+            k = (7 * r + 3 + rnd) % cap
+            want.append((torch.arange(k * rec, dtype=torch.int64).reshape(k, rec).to(torch.uint8) + r).reshape(-1))
+        assert torch.equal(got, torch.cat(want)), (rank, rnd)
+    open(os.path.join(outdir, "ok%d" % rank), "w").close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_device_gather_concatenates_in_rank_order(tmp_path, world):
+    """DeviceGather (the all-gather bench.py times at N > 1; NCCL there, gloo here): ragged lists, rank order."""
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))

@@ -19,10 +19,10 @@ from oracle import oracle as O  # noqa: E402
 
 
 def run(st, p, cands, walk, walk_min=None, compact=False):
-    os.environ.pop("HC_NO_ANCHOR_WALK", None)
+    os.environ.pop("HC_ANCHOR_WALK", None)
     os.environ.pop("HC_ANCHOR_WALK_MIN", None)
-    if not walk:
-        os.environ["HC_NO_ANCHOR_WALK"] = "1"
+    if walk:
+        os.environ["HC_ANCHOR_WALK"] = "1"
     if walk_min is not None:
         os.environ["HC_ANCHOR_WALK_MIN"] = str(walk_min)
     return st.score_batch(p, cands, compact=compact)
