@@ -886,6 +886,11 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         uint64_t cap = 1;
         for (size_t k = 0; k + 1 < cs[g].size(); k++) cap = std::max<uint64_t>(cap, cs[g][k + 1] - cs[g][k]);
         CU(cudaSetDevice(d.device));
+        {   // the kernels' workspace for the largest step, once: growing it step by step would free and reallocate
+            // (a device-wide synchronisation each) right in the warm-up steps of the pipeline
+            const int rcw = ensure_workspace(d, cap);
+            if (rcw != HC_OK) return rcw;
+        }
         if (whole[g]) {
             if (m * rec > d.whole_cap) {
                 cudaFree(d.d_whole); d.d_whole = nullptr; d.whole_cap = 0;

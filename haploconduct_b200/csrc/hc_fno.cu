@@ -398,6 +398,14 @@ extern "C" int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_
 #pragma omp parallel for schedule(static) reduction(| : bad)
     for (long long i = 0; i < (long long)nsr; i++) bad |= (in->sr_idx[i] >= NS);
     if (bad) { hc_set_last_error("hc_fno1: super-read index out of range"); return HC_ERR_ARG; }
+    // the first-found-wins table keys a pair of new reads as (min id << 32 | max id): every id that can appear in a key
+    // -- a super-read's, an unmerged vertex' -- must fit 32 bits (rename_fas.py numbers reads from 0), else distinct
+    // pairs would collide and overlaps the reference finds would be dropped silently
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (long long i = 0; i < (long long)NS; i++) bad |= (in->superread[i].id >> 32) != 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (long long v = 0; v < (long long)V; v++) bad |= (!in->visited[v] && in->vertex_read[v].id != ~0ull && (in->vertex_read[v].id >> 32) != 0);
+    if (bad) { hc_set_last_error("hc_fno1: a new read id does not fit 32 bits (ids of new reads must be below 2^32)"); return HC_ERR_ARG; }
     int rc = HC_OK;
     FnoPhase ph;
     ph.mark("argument checks");
@@ -487,6 +495,9 @@ extern "C" int hc_fno3(uint64_t n_originals, const uint64_t* off, const uint32_t
 #pragma omp parallel for schedule(static) reduction(| : bad)
     for (long long i = 0; i < (long long)nent; i++) bad |= (sr_idx[i] >= n_reads);
     if (bad) { hc_set_last_error("hc_fno3: read index out of range"); return HC_ERR_ARG; }
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (long long i = 0; i < (long long)n_reads; i++) bad |= (reads[i].id >> 32) != 0;      // pair keys are (min id << 32 | max id)
+    if (bad) { hc_set_last_error("hc_fno3: a new read id does not fit 32 bits (ids of new reads must be below 2^32)"); return HC_ERR_ARG; }
     int rc = HC_OK;
     u64 *d_off = nullptr, *d_seq = nullptr, *d_total = nullptr, *d_keys = nullptr, *d_mins = nullptr, *d_outpos = nullptr, *d_bsum = nullptr;
     uint32_t *d_idx = nullptr, *d_cnt = nullptr, *d_flags = nullptr;

@@ -303,6 +303,11 @@ extern "C" hc_idmap* hc_idmap_create(const uint64_t* ids, uint64_t n_reads, int 
     m->ev_in[0] = m->ev_in[1] = m->ev_out[0] = m->ev_out[1] = nullptr;
     u64 max_id = 0;
     for (u64 i = 0; i < n_reads; i++) max_id = std::max<u64>(max_id, ids[i]);
+    if (n_reads && max_id == ~0ull) {   // the hash slots use this value as "empty" (strtoul yields it for "-1" or an overflowing header)
+        hc_set_last_error("hc_idmap_create: read id 18446744073709551615 (ULONG_MAX) is not supported");
+        delete m;
+        return nullptr;
+    }
     const bool dense = n_reads > 0 && max_id < 4 * n_reads + 1024;     // rename_fas.py numbers the reads 0..n-1
     int rc = HC_OK;
     u64* d_ids = nullptr;

@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(256) fq_records(const char* __restrict__ text,
         ls[j] = line_start[li];
         le[j] = li < n_newlines ? line_start[li + 1] - 1 : n_bytes;
     }
-    bool bad = le[0] == ls[0] || f[ls[0]] != '@';
+    // the reference tests the '@' of the first file's header only (src/FastqStorage.cpp:107-110,:181-184); mate 2's is just skipped
+    bool bad = le[0] == ls[0] || (mate == 0 && f[ls[0]] != '@');
     // stringstream(line.substr(1)) >> token: skip white space, read up to the next white space (:111-113)
     u64 p = ls[0] + 1;
     while (p < le[0] && c_isspace(f[p])) p++;

@@ -61,7 +61,9 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
  * src/FastqStorage.cpp:42-235) on the device: at most 4 * max_reads lines per file (:46), records of four lines,
  * header = '@' + id token (first white-space delimited token, strtoul(.., 0), src/Types.h:99-102), single-end
  * sequences upper-cased (:123), mates taken verbatim (:196-197) with equal header tokens (:189-192); singles
- * first, then pairs.  Records the reference exits on give NULL + HC_ERR_INPUT.  Pass NULL / 0 for an absent
+ * first, then pairs.  Records the reference exits on give NULL + HC_ERR_INPUT; so does -- a deliberate deviation -- a
+ * record whose sequence and quality lines differ in length, which the reference loads and only trips over when the
+ * read is scored (src/EdgeCalculator.cpp:93-98).  Only the first file's header is tested for '@' (:181).  Pass NULL / 0 for an absent
  * file.  The id_correspondence table of the reference (--IDs) is not applied: use hc_store_create for that. */
 hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, const char* paired1, uint64_t paired1_bytes,
                                 const char* paired2, uint64_t paired2_bytes, uint64_t max_reads,
@@ -498,7 +500,8 @@ int hc_ingest_overlaps_device(const hc_idmap* m, void* stream, const char* d_tex
  * bounding the error; columns within that bound of a decision come back with their scores and are
  * decided by the host libm, the same the reference links.  The host part of the call then walks
  * the columns like :447-513 (support trimming under error_correction, give-up cases).  Results
- * are the reference's strings.  Output regions of different problems must not overlap.
+ * are the reference's strings.  Output regions of different problems must not overlap; the call owns the whole of
+ * cons_seq / cons_qual [0, out_bytes): bytes between the regions of two problems are overwritten too (with zeros).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     uint32_t read;            /* store index of the read                                            */

@@ -194,6 +194,19 @@ def fno_cases(full: F.ReadSet) -> None:
 def main() -> None:
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--only-full" in sys.argv:
+        # the two example data sets at their full size: every read, every seed-enumerated candidate of all read types
+        R = REF + "/savage/example/input_fas/"
+        full = F.load_fastq_set(R + "singles.fastq", R + "paired1.fastq", R + "paired2.fastq")
+        c = W.seed_candidates(full, k=24, seed=3)
+        run_case("c1_savage_example_full", full, c, dict(edge_threshold=0.97, min_overlap_len=200))
+        Rp = REF + "/polyte/example/input/"
+        fw = F._read_fastq_records(Rp + "forward.fastq")
+        rv = F._read_fastq_records(Rp + "reverse.fastq")
+        rs2 = F.ReadSet.from_lists([(i, s.upper(), q) for i, (_, s, q) in enumerate(fw + rv)], [])
+        c2 = W.seed_candidates(rs2, k=20, seed=4, orientations=((1, 1), (1, 0)))
+        run_case("c2_polyte_example_full", rs2, c2, dict(edge_threshold=0.95, min_overlap_len=126))
+        return
     if "--only-fno" in sys.argv:
         R = REF + "/savage/example/input_fas/"
         fno_cases(F.load_fastq_set(R + "singles.fastq", R + "paired1.fastq", R + "paired2.fastq"))

@@ -107,3 +107,37 @@ def test_store_replicated_on_two_devices(built_lib, monkeypatch):
     with capi.Store(g.rs, first_device=1, n_devices=1) as st3:           # a store that lives on the second device only
         e3, n3, p3, _ = st3.score_batch(g.params(), cands)
     assert p1.tobytes() == p3.tobytes() and e1.tobytes() == e3.tobytes()
+
+
+def test_million_candidates_against_the_reference_binary(built_lib, c4_small, tmp_path):
+    """One million candidates of the config-4 / config-3 shaped workload through the UNMODIFIED reference itself
+    (oracle/_ref/ref_driver --dump-cands = EdgeCalculator::compute_overlap per candidate, not the C restatement): classes,
+    mismatch rates, pos3 / pos4 bit for bit; scores within 1e-6 relative in the default mode and within 1e-14 (the device
+    exp) with HC_FLAG_EXACT_EDGE_SCORES."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/ref_driver has not travelled to this box")
+    rs, cands = c4_small
+    sub = cands[:1_000_000]
+    used = np.unique(np.concatenate([sub["idx1"], sub["idx2"]]))
+    small = rs.subset(used.tolist())
+    c = sub.copy()
+    c["idx1"] = np.searchsorted(used, sub["idx1"]).astype(np.uint32)
+    c["idx2"] = np.searchsorted(used, sub["idx2"]).astype(np.uint32)
+    d = str(tmp_path)
+    F.write_fastq_set(small, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
+    F.write_overlaps(d + "/ov.txt", c, small.ids)
+    RL = int(rs.descs["seq_len"][0, 0])
+    out = O.run_ref(d, d + "/ov.txt", paired1=d + "/p1.fastq", paired2=d + "/p2.fastq", dump_cands=True, threads=1, edge_threshold=0.97,
+                    min_overlap_len=RL)
+    ref = out["cands"]
+    assert len(ref) == len(c)                                    # every candidate passes the pre-filter (both mates overlap >= L/2)
+    with capi.Store(small) as st:
+        _, _, per, _ = st.score_batch(F.make_params(edge_threshold=0.97), c)
+        ex, _, _, _ = st.score_batch(F.make_params(edge_threshold=0.97, flags=F.FLAG_EXACT_EDGE_SCORES), c, per_candidate=False)
+    assert np.array_equal(per["cls"], ref["cls"])
+    assert np.array_equal(per["mismatch_rate"], ref["mismatch_rate"])
+    assert np.array_equal(per["pos3"], ref["pos3"]) and np.array_equal(per["pos4"], ref["pos4"])
+    assert np.allclose(per["score"], ref["score"], rtol=1e-6, atol=0)
+    ei = np.nonzero(ref["cls"] == F.CLASS_EDGE)[0]
+    assert np.array_equal(ex["cand"], ei.astype(np.uint64)) and len(ei) > 10_000
+    assert np.allclose(ex["score"], ref["score"][ei], rtol=1e-14, atol=0)
