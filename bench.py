@@ -242,9 +242,9 @@ def main() -> None:
     ap.add_argument("--device-chunk", type=int, default=0,
                     help="diagnostic: split the device-resident step into launches of this many candidates (what the host pipeline's "
                          "steps cost without any copies)")
-    ap.add_argument("--e2e-records", default="runs", choices=["runs", "short", "compact"],
-                    help="host record of the e2e leg: run-encoded 8-byte hc_candidate_entry, 12-byte hc_candidate_short (both: reads "
-                         "< 16384 bases) or 16-byte hc_candidate_compact")
+    ap.add_argument("--e2e-records", default="runs6", choices=["runs6", "runs", "short", "compact"],
+                    help="host record of the e2e leg: run-encoded 6-byte hc_candidate_entry6 (reads < 512 bases, <= 2^25 reads), run-encoded "
+                         "8-byte hc_candidate_entry, 12-byte hc_candidate_short (both: reads < 16384 bases) or 16-byte hc_candidate_compact")
     ap.add_argument("--e2e-output", default="small", choices=["small", "full"],
                     help="what the e2e leg brings back: hc_edge_small records + one bit per candidate (hc_score_batch_runs_small), "
                          "or 48-byte hc_edge records + 8-byte non-edge indices (hc_score_batch_runs)")
@@ -439,10 +439,13 @@ def main() -> None:
         # position is below 2^14, else the 16-byte compact record (idx1, idx2, pos1|ori|ord, pos2)
         r32 = rec.view(torch.int32).reshape(-1, 8)
         ordc = torch.where(((r32[:, 6] >> 16) & 0xff) == ord("1"), 1, 2)
-        short = args.e2e_records in ("short", "runs") and args.read_len < (1 << 14)
-        use_runs = short and args.e2e_records == "runs"
-        rec_bytes = 8 if use_runs else (12 if short else 16)
-        cc = torch.empty((n, rec_bytes // 4), dtype=torch.int32, device=dev)
+        runs6 = args.e2e_records == "runs6" and args.read_len < 512 and args.pairs <= (1 << 25) and args.e2e_output == "small"
+        if args.e2e_records == "runs6" and not runs6:
+            args.e2e_records = "runs"
+        short = args.e2e_records in ("short", "runs", "runs6") and args.read_len < (1 << 14)
+        use_runs = short and args.e2e_records in ("runs", "runs6")
+        rec_bytes = 6 if runs6 else (8 if use_runs else (12 if short else 16))
+        cc = torch.empty((n, 2 if use_runs else rec_bytes // 4), dtype=torch.int32, device=dev)
         run_bytes = 0
         if use_runs:
             # run-encoded 8-byte records (hc_score_batch_runs): the list is sorted by (min id, max id), so the candidates of
@@ -470,8 +473,18 @@ def main() -> None:
         else:
             cc[:, 3] = r32[:, 3]
             cc[:, 2] = r32[:, 2] | (3 << 28) | (ordc << 30).to(torch.int32)      # POS1 | ORI1 '+' | ORI2 '+' | ORD
-        h_cand = torch.empty((n, rec_bytes // 4), dtype=torch.int32, pin_memory=True)
-        h_cand.copy_(cc)
+        if runs6:     # the 8-byte entry squeezed into 48 bits: other (25) | anchor-is-ID2 | ORI1 | ORI2 | ORD (2) | POS1 (9) | POS2 (9)
+            other = (cc[:, 0] & 0x7fffffff).to(torch.int64)
+            role = ((cc[:, 0] >> 31) & 1).to(torch.int64)
+            pw = cc[:, 1].to(torch.int64) & 0xffffffff
+            v = other | (role << 25) | (((pw >> 28) & 0xf) << 26) | ((pw & 0x3fff) << 30) | (((pw >> 14) & 0x3fff) << 39)
+            c6 = v.view(torch.uint8).reshape(n, 8)[:, :6].contiguous()
+            h_cand = torch.empty((n, 6), dtype=torch.uint8, pin_memory=True)
+            h_cand.copy_(c6)
+            del other, role, pw, v, c6
+        else:
+            h_cand = torch.empty((n, rec_bytes // 4), dtype=torch.int32, pin_memory=True)
+            h_cand.copy_(cc)
         del cc
         ne, nn = int(counts[0]), int(counts[1])
         small = use_runs and args.e2e_output == "small"
@@ -484,7 +497,8 @@ def main() -> None:
 
         def e2e_step():
             if small:     # hc_edge_small records + one bit per candidate
-                rc = L.hc_score_batch_runs_small(store.handle, params.ctypes.data, h_anchor.data_ptr(), h_start.data_ptr(), h_anchor.shape[0],
+                fn_small = L.hc_score_batch_runs6_small if runs6 else L.hc_score_batch_runs_small
+                rc = fn_small(store.handle, params.ctypes.data, h_anchor.data_ptr(), h_start.data_ptr(), h_anchor.shape[0],
                                                  h_cand.data_ptr(), n, h_edges.data_ptr(), h_edges.shape[0], ctypes.byref(c_ne),
                                                  h_nonedge.data_ptr(), ctypes.byref(c_nn), None)
                 if rc != 0:
@@ -518,7 +532,7 @@ def main() -> None:
             bits = h_nonedge[: (n + 63) // 64].numpy().view(np.uint8)
             assert int(np.unpackbits(bits).sum()) == nn
         e2e = (e2e_ms, n * rec_bytes + run_bytes, (ne * erec + ((n + 63) // 64) * 8 + 64) if small else (ne * 48 + nn * 8 + 64),
-               ("hc_candidate_entry (8 B, run-encoded)" if use_runs else ("hc_candidate_short (12 B)" if short else "hc_candidate_compact (16 B)"))
+               ("hc_candidate_entry6 (6 B, run-encoded)" if runs6 else "hc_candidate_entry (8 B, run-encoded)" if use_runs else ("hc_candidate_short (12 B)" if short else "hc_candidate_compact (16 B)"))
                + (" in; hc_edge_small (%d B) + 1 bit per candidate out" % erec if small else " in; hc_edge (48 B) + 8-byte non-edge indices out"))
 
     # the mode the drop-in host mirror runs in (HC_FLAG_EXACT_EDGE_SCORES: every accepted edge re-summed in the reference's

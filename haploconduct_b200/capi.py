@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("HC_B200_LIB") or os.path.join(HERE, "lib", "libhc_b20
 # every symbol include/hc_b200.h declares
 EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
-    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_runs_small", "hc_score_batch_short_small", "hc_edge_extra_pos", "hc_score_batch_device",
+    "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_runs_small", "hc_score_batch_runs6_small", "hc_score_batch_short_small", "hc_edge_extra_pos", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
     "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
     "hc_store_create_fastq", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
@@ -70,6 +70,8 @@ def lib() -> ctypes.CDLL:
         L.hc_score_batch_runs.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, vp, u64, vp, vp, u64, vp, vp]
         L.hc_score_batch_runs_small.restype = i32
         L.hc_score_batch_runs_small.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
+        L.hc_score_batch_runs6_small.restype = i32
+        L.hc_score_batch_runs6_small.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, u64, vp, vp, vp, vp]
         L.hc_score_batch_short_small.restype = i32
         L.hc_score_batch_short_small.argtypes = [vp, vp, vp, u64, vp, u64, vp, vp, vp, vp]
         L.hc_edge_extra_pos.restype = None
@@ -255,13 +257,19 @@ class Store:
         if runs:
             anchor, start, entries = F.run_encode(cands)
             n = len(entries)
+            if runs == 6:
+                entries = F.entries6(entries)
         else:
             entries = np.ascontiguousarray(F.short_candidates(cands))
             n = len(entries)
         ecap = n if edges_cap is None else edges_cap
         edges = np.zeros(max(ecap, 1), dtype=dt)
         bits = np.full((n + 63) // 64 + 1, 0xdeadbeefdeadbeef, dtype=np.uint64)     # the call must write every word it owns
-        if runs:
+        if runs == 6:
+            rc = L.hc_score_batch_runs6_small(self._h, params.ctypes.data, anchor.ctypes.data if n else None, start.ctypes.data, len(anchor),
+                                              entries.ctypes.data if n else None, n, edges.ctypes.data, ecap, ctypes.byref(ne),
+                                              bits.ctypes.data, ctypes.byref(nn), stats.ctypes.data)
+        elif runs:
             rc = L.hc_score_batch_runs_small(self._h, params.ctypes.data, anchor.ctypes.data if n else None, start.ctypes.data, len(anchor),
                                              entries.ctypes.data if n else None, n, edges.ctypes.data, ecap, ctypes.byref(ne),
                                              bits.ctypes.data, ctypes.byref(nn), stats.ctypes.data)

@@ -207,7 +207,7 @@ int enqueue_batch(hc_store* s, DevCtx& d, cudaStream_t st, const hc_params* p, c
                   uint64_t* d_counts, uint64_t cand_offset, unsigned long long* d_run, cudaEvent_t k0, cudaEvent_t k1,
                   uint32_t* launches, const RunDev* runs = nullptr, int small_out = 0, uint32_t* d_bits = nullptr) {
     if (n > 0xffffffffull) return fail(HC_ERR_ARG, "more than 2^32-1 candidates in one device batch");
-    if (compact == 3 && !runs) return fail(HC_ERR_ARG, "run-encoded candidates without run arrays");
+    if (compact >= 3 && !runs) return fail(HC_ERR_ARG, "run-encoded candidates without run arrays");
     int rc = ensure_tables(s, d, p->mismatch, st);
     if (rc != HC_OK) return rc;
     rc = ensure_workspace(d, n);
@@ -836,7 +836,7 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
     if (stats) memset(stats, 0, sizeof(*stats));
     *n_edges = 0;
     *n_nonedges = 0;
-    const size_t rec = compact == 3 ? sizeof(hc_candidate_entry)
+    const size_t rec = compact == 4 ? sizeof(hc_candidate_entry6) : compact == 3 ? sizeof(hc_candidate_entry)
                                     : (compact == 2 ? sizeof(hc_candidate_short) : (compact ? sizeof(hc_candidate_compact) : sizeof(hc_candidate)));
     const int G = (int)s->devs.size();
     uint64_t chunk = 0;            // candidates per pipeline step; 0 = the tapered default schedule
@@ -1179,6 +1179,25 @@ int hc_score_batch_runs_small(hc_store* s, const hc_params* p, const uint32_t* r
     }
     const RunsHost rh{run_anchor, run_start, n_runs};
     return score_host(s, p, entries, 3, n, nullptr, reinterpret_cast<hc_edge*>(edges), edges_cap, n_edges, nonedge_bits, 0, n_nonedges, stats,
+                      n ? &rh : nullptr, 1);
+}
+
+int hc_score_batch_runs6_small(hc_store* s, const hc_params* p, const uint32_t* run_anchor, const uint64_t* run_start, uint64_t n_runs,
+                               const hc_candidate_entry6* entries, uint64_t n, void* edges, uint64_t edges_cap, uint64_t* n_edges,
+                               uint64_t* nonedge_bits, uint64_t* n_nonedges, hc_batch_stats* stats) {
+    if (n && (!run_anchor || !run_start || n_runs == 0)) return fail(HC_ERR_ARG, "hc_score_batch_runs6_small: NULL run arrays");
+    if (n && !nonedge_bits) return fail(HC_ERR_ARG, "hc_score_batch_runs6_small: NULL bit map");
+    if (s && s->n_reads > (1ull << 25)) return fail(HC_ERR_ARG, "hc_score_batch_runs6_small: more than 2^25 reads in the store");
+    if (n > 0xffffffffull) return fail(HC_ERR_ARG, "hc_score_batch_runs6_small: a call takes fewer than 2^32 candidates");
+    if (n) {
+        if (run_start[0] != 0 || run_start[n_runs] != n) return fail(HC_ERR_ARG, "hc_score_batch_runs6_small: run_start must begin at 0 and end at n");
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (long long r = 0; r < (long long)n_runs; r++) bad |= (run_start[r] >= run_start[r + 1]);
+        if (bad) return fail(HC_ERR_ARG, "hc_score_batch_runs6_small: run_start must be strictly increasing (no empty runs)");
+    }
+    const RunsHost rh{run_anchor, run_start, n_runs};
+    return score_host(s, p, entries, 4, n, nullptr, reinterpret_cast<hc_edge*>(edges), edges_cap, n_edges, nonedge_bits, 0, n_nonedges, stats,
                       n ? &rh : nullptr, 1);
 }
 

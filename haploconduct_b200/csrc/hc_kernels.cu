@@ -49,6 +49,25 @@ struct CandSetup {
 __device__ __forceinline__ hc_candidate load_candidate(const hc_kparams& P, u64 i, uint32_t* anchor_read = nullptr) {
     hc_candidate c;
     if (anchor_read) *anchor_read = 0u;   // 1 / 2: the run's shared read is ID1 / ID2 (run-encoded records only)
+    if (P.cand_compact == 4u) {   // hc_candidate_entry6: 6 bytes (three 16-bit loads), run-encoded like hc_candidate_entry
+        const uint16_t* hp = reinterpret_cast<const uint16_t*>(P.cand) + 3 * i;
+        const uint32_t h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2);
+        const uint32_t lo = h0 | (h1 << 16);               // bits 0-31 of the 48-bit record
+        uint32_t r = __ldg(P.tile_run + (i >> 5));
+        while ((uint32_t)i >= __ldg(P.run_start + r + 1)) r++;
+        const uint32_t anchor = __ldg(P.run_anchor + r), other = lo & 0x01ffffffu;
+        const bool anchor_is_2 = ((lo >> 25) & 1u) != 0u;
+        if (anchor_read) *anchor_read = anchor_is_2 ? 2u : 1u;
+        c.idx1 = anchor_is_2 ? other : anchor;
+        c.idx2 = anchor_is_2 ? anchor : other;
+        c.pos1 = (lo >> 30) | ((h2 & 0x7fu) << 2);         // bits 30-38
+        c.pos2 = h2 >> 7;                                  // bits 39-47
+        c.len1 = c.len2 = 0; c.perc1 = c.perc2 = 0; c.type1 = c.type2 = 0; c.reserved = 0;
+        c.ori1 = (lo >> 26) & 1u; c.ori2 = (lo >> 27) & 1u;
+        const uint32_t o = (lo >> 28) & 3u;
+        c.ord = o == 1 ? '1' : (o == 2 ? '2' : '-');
+        return c;
+    }
     if (P.cand_compact == 3u) {   // hc_candidate_entry: 8 bytes, the other read comes from the run the candidate lies in
         const uint2 e = __ldg(reinterpret_cast<const uint2*>(P.cand) + i);
         uint32_t r = __ldg(P.tile_run + (i >> 5));
@@ -869,7 +888,7 @@ __global__ void __launch_bounds__((WALK ? HC_WALK_WARPS : HC_WARPS_MAX) * 32, WA
             const int sc1 = (up && (id1 == p1 || id1 == p2)) + (dn && (id1 == n1 || id1 == n2));
             const int sc2 = (up && (id2 == p1 || id2 == p2)) + (dn && (id2 == n1 || id2 == n2));
             // records without run information: the anchor is the read shared with the neighbouring candidates, else the smaller index
-            if (P.cand_compact != 3u) anch = sc1 > sc2 ? 1u : (sc2 > sc1 ? 2u : (id1 <= id2 ? 1u : 2u));
+            if (P.cand_compact < 3u) anch = sc1 > sc2 ? 1u : (sc2 > sc1 ? 2u : (id1 <= id2 ? 1u : 2u));
             const bool lane_ok = valid && !s.err;
             // lists without runs: do not even start (the lanes of a group are neighbours in a list sorted by read)
             if ((uint32_t)__popc(__ballot_sync(0xffffffffu, lane_ok && (sc1 | sc2))) + 1u >= P.anchor_walk) {

@@ -56,6 +56,8 @@ class DeviceGather:
     def gather(self, records: torch.Tensor, count: torch.Tensor) -> None:
         """records: uint8 tensor holding this rank's list (at least cap * rec bytes are readable), count: int64[1] on the
         device.  Asynchronous on the current stream; results in self.counts / self.padded."""
+        if records.numel() < self.cap * self.rec:
+            raise ValueError("DeviceGather: the record buffer must hold cap = %d records (lists are padded to it)" % self.cap)
         dist.all_gather_into_tensor(self.counts, count.reshape(1), group=self.group)
         dist.all_gather_into_tensor(self.padded.reshape(-1), records.reshape(-1)[: self.cap * self.rec], group=self.group)
 

@@ -85,6 +85,21 @@ def run_encode(c: np.ndarray):
     return anchor, start, out
 
 
+def entries6(en: np.ndarray) -> np.ndarray:
+    """hc_candidate_entry (8 bytes) -> hc_candidate_entry6 (6 bytes, uint8[n, 6]): a 48-bit little-endian number, bits 0-24
+    other read, 25 anchor-is-ID2, 26 ORI1 '+', 27 ORI2 '+', 28-29 ORD, 30-38 POS1, 39-47 POS2 (reads shorter than 512 bases,
+    at most 2^25 reads)."""
+    other = (en["other"] & np.uint32(0x7fffffff)).astype(np.uint64)
+    role = (en["other"] >> np.uint32(31)).astype(np.uint64)
+    pos = en["pos"].astype(np.uint64)
+    p1, p2 = pos & np.uint64(0x3fff), (pos >> np.uint64(14)) & np.uint64(0x3fff)
+    flags = (pos >> np.uint64(28)) & np.uint64(0xf)                     # ORI1, ORI2, ORD (2 bits)
+    if len(en) and (int(other.max()) >= (1 << 25) or int(p1.max()) >= 512 or int(p2.max()) >= 512):
+        raise ValueError("records do not fit the 6-byte candidate entry")
+    v = other | (role << np.uint64(25)) | (flags << np.uint64(26)) | (p1 << np.uint64(30)) | (p2 << np.uint64(39))
+    return np.ascontiguousarray(v.astype("<u8").view(np.uint8).reshape(-1, 8)[:, :6])
+
+
 PARAMS = np.dtype(
     [
         ("edge_threshold", "<f8"), ("ov_threshold", "<f8"), ("merge_contigs", "<f8"), ("mismatch", "<f8"),

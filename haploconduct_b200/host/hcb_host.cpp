@@ -1,6 +1,7 @@
 // hcb_host.cpp -- see hcb_host.h.  Host plumbing around the C ABI: FASTQ / overlaps-file parsing,
 // id -> index mapping, the ordered graph insert.  No score is computed here.
 #include "hcb_host.h"
+#include <omp.h>
 
 #include <algorithm>
 #include <cmath>
@@ -124,11 +125,19 @@ void FastqStorage::read_pairs(const std::string& p1, const std::string& p2, unsi
 
 static std::string slurp_file(const std::string& path) {
     if (path.empty() || path == "None") return std::string();
-    std::ifstream f(path.c_str(), std::ios::binary);
-    if (!f.is_open()) die("Unable to open fastq file " + path);                   // src/FastqStorage.cpp:54-56
-    std::stringstream ss;
-    ss << f.rdbuf();
-    return ss.str();
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) die("Unable to open fastq file " + path);                             // src/FastqStorage.cpp:54-56
+    std::string s;
+    std::fseek(f, 0, SEEK_END);
+    const long size = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    if (size > 0) {
+        s.resize((size_t)size);
+        const size_t got = std::fread(&s[0], 1, (size_t)size, f);
+        s.resize(got);
+    }
+    std::fclose(f);
+    return s;
 }
 
 FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
@@ -146,11 +155,13 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         m_readcount_single = (unsigned int)hc_store_n_single(store_);
         m_readcount_paired = (unsigned int)(n - m_readcount_single);
         m_read_vec.resize(n);
+        mate_len = lens;
         for (uint64_t i = 0; i < n; i++) {
             m_read_vec[i].read_id = ids[i];
             m_read_vec[i].is_paired = i >= m_readcount_single;
             max_read_len = std::max(max_read_len, std::max(lens[2 * i], lens[2 * i + 1]));
-            m_ID_to_index.insert(std::make_pair((read_id_t)ids[i], (unsigned int)i));
+            // with the overlaps file parsed on the device too, nothing on the host looks an id up (the device map does)
+            if (!ps.gpu_parse) m_ID_to_index.insert(std::make_pair((read_id_t)ids[i], (unsigned int)i));
         }
         if (ps.verbose) {
             std::cout << "Singles: " << m_readcount_single << std::endl;
@@ -181,6 +192,8 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         if (r.seq1.size() != r.phred1.size() || r.seq2.size() != r.phred2.size())
             die("read with ID " + std::to_string(r.read_id) + ": sequence and quality lengths differ");   // string::at would throw, :93-94
         max_read_len = std::max(max_read_len, (unsigned int)std::max(r.seq1.size(), r.seq2.size()));
+        mate_len.push_back((uint32_t)r.seq1.size());
+        mate_len.push_back((uint32_t)r.seq2.size());
         descs[i].seq_off[0] = bases.size();
         descs[i].seq_len[0] = (uint32_t)r.seq1.size();
         bases += r.seq1;
@@ -644,12 +657,234 @@ void EdgeCalculator::ingest_on_device(std::vector<Overlap>& batch, std::vector<O
     }
 }
 
+// ---- the stage on arrays ------------------------------------------------------------------------------------
+// What the reference does line by line and object by object (:561-666 with process_overlaps :389-557) on flat arrays:
+// the order of everything observable is the file order -- accepted edges are inserted in file order, nonedge_overlaps.txt
+// holds the scored non-edges in file order followed by the pre-filtered lines in file order (the batches of 10^6 of :571
+// do not change either) -- so one parse call, one scoring call and loops over arrays that every host thread takes a
+// share of reproduce it.
+namespace {
+
+inline void put_cand_line(std::string& b, const hc_candidate& c, read_id_t id1, read_id_t id2) {            // src/Overlap.h:234-237
+    put_u64(b, id1); b.push_back('\t'); put_u64(b, id2); b.push_back('\t'); put_u64(b, c.pos1); b.push_back('\t'); put_u64(b, c.pos2);
+    b.push_back('\t'); b.push_back((char)c.ord); b.push_back('\t'); b.push_back(c.ori1 ? '+' : '-'); b.push_back('\t');
+    b.push_back(c.ori2 ? '+' : '-'); b.push_back('\t');
+    put_u64(b, c.perc1); b.push_back('\t'); put_u64(b, c.perc2); b.push_back('\t'); put_u64(b, c.len1); b.push_back('\t'); put_u64(b, c.len2);
+    b.push_back('\t'); b.push_back((char)c.type1); b.push_back('\t'); b.push_back((char)c.type2); b.push_back('\n');
+}
+
+inline void put_rec_line(std::string& b, const hc_overlap_rec& r) {
+    put_u64(b, r.id1); b.push_back('\t'); put_u64(b, r.id2); b.push_back('\t'); put_u64(b, r.pos1); b.push_back('\t'); put_u64(b, r.pos2);
+    b.push_back('\t'); b.push_back((char)r.ord); b.push_back('\t'); b.push_back((char)r.ori1); b.push_back('\t'); b.push_back((char)r.ori2);
+    b.push_back('\t');
+    put_u64(b, r.perc1); b.push_back('\t'); put_u64(b, r.perc2); b.push_back('\t'); put_u64(b, r.len1); b.push_back('\t'); put_u64(b, r.len2);
+    b.push_back('\t'); b.push_back((char)r.type1); b.push_back('\t'); b.push_back((char)r.type2); b.push_back('\n');
+}
+
+}  // namespace
+
+bool EdgeCalculator::construct_edges_arrays() {
+    if (fastq_->max_read_len >= (1u << 14) || fastq_->m_read_vec.size() >= (1ull << 31)) return false;   // needs the 8-byte records
+    const int T = std::max(1, omp_get_max_threads());
+    // ---- the file, in one read
+    const double t0 = wall_s();
+    FILE* f = std::fopen(ps_.overlaps_file.c_str(), "rb");
+    if (!f) { std::cerr << "Unable to open overlaps file"; std::exit(1); }
+    std::fseek(f, 0, SEEK_END);
+    const size_t size = (size_t)std::max(0l, std::ftell(f));
+    std::fseek(f, 0, SEEK_SET);
+    std::unique_ptr<char[]> text(new char[size + 1]);
+    const size_t got = size ? std::fread(text.get(), 1, size, f) : 0;
+    std::fclose(f);
+    size_t lines = 1;
+#pragma omp parallel for schedule(static) reduction(+ : lines)
+    for (long long i = 0; i < (long long)got; i++) lines += text[i] == '\n';
+    // ---- parse + pre-filter + id lookup on the device
+    std::unique_ptr<hc_candidate[]> cand(new hc_candidate[lines]);
+    size_t filt_cap = std::max<size_t>(lines / 8, 4096);
+    std::unique_ptr<hc_overlap_rec[]> filt(new hc_overlap_rec[filt_cap]);
+    hc_ingest_params ip;
+    memset(&ip, 0, sizeof(ip));
+    ip.max_overlaps = ps_.max_overlaps;
+    ip.min_overlap_len = ps_.min_overlap_len; ip.min_overlap_perc = ps_.min_overlap_perc;
+    ip.relax_PE_edges = ps_.relax_PE_edges; ip.allow_spaces = ps_.allow_spaces;
+    hc_ingest_stats st;
+    hc_idmap* idmap = fastq_->device_idmap();
+    int rc = hc_ingest_overlaps(idmap, text.get(), got, &ip, cand.get(), nullptr, lines, filt.get(), nullptr, filt_cap, &st);
+    if (rc == HC_ERR_CAPACITY) {
+        filt_cap = st.n_filtered + 1;
+        filt.reset(new hc_overlap_rec[filt_cap]);
+        rc = hc_ingest_overlaps(idmap, text.get(), got, &ip, cand.get(), nullptr, lines, filt.get(), nullptr, filt_cap, &st);
+    }
+    if (rc != HC_OK) die(std::string("hc_ingest_overlaps: ") + hc_last_error());
+    parse_device_ms += st.device_ms;
+    if (st.first_error_line != ~0ull) return false;      // the line-by-line path reproduces what the reference does up to that line
+    for (uint64_t k = 0; k < st.n_skipped; k++) std::cout << "incorrect overlap; skipping" << std::endl;   // :600-603
+    const size_t n = st.n_scored;
+    const double t1 = wall_s();
+    t_ingest_s += t1 - t0;
+    bool fits = true;
+#pragma omp parallel for schedule(static) reduction(&& : fits)
+    for (long long i = 0; i < (long long)n; i++) fits = fits && cand[i].pos1 < (1u << 14) && cand[i].pos2 < (1u << 14);
+    if (!fits) return false;
+    // ---- run-encoded records: a run = a stretch of candidates with the same smaller read index (an overlaps file sorted by
+    // read gives long runs; any list gives valid ones), cut by every thread in its own share
+    std::unique_ptr<hc_candidate_entry[]> en(new hc_candidate_entry[n ? n : 1]);
+    std::vector<std::vector<uint64_t>> t_start(T);
+    std::vector<uint32_t> anchor;
+    std::vector<uint64_t> start;
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        const size_t lo = n * (size_t)t / (size_t)T, hi = n * (size_t)(t + 1) / (size_t)T;
+        std::vector<uint64_t>& mine = t_start[t];
+        for (size_t i = lo; i < hi; i++) {
+            const hc_candidate& c = cand[i];
+            const uint32_t key = std::min(c.idx1, c.idx2);
+            if (i == 0 || key != std::min(cand[i - 1].idx1, cand[i - 1].idx2)) mine.push_back(i);
+            const uint32_t o = c.ord == '1' ? 1u : (c.ord == '2' ? 2u : 0u);
+            en[i].other = c.idx1 == key ? c.idx2 : (c.idx1 | 0x80000000u);
+            en[i].pos = c.pos1 | (c.pos2 << 14) | ((uint32_t)(c.ori1 != 0) << 28) | ((uint32_t)(c.ori2 != 0) << 29) | (o << 30);
+        }
+    }
+    for (int t = 0; t < T; t++) start.insert(start.end(), t_start[t].begin(), t_start[t].end());
+    anchor.resize(start.size());
+#pragma omp parallel for schedule(static)
+    for (long long r = 0; r < (long long)start.size(); r++) anchor[r] = std::min(cand[start[r]].idx1, cand[start[r]].idx2);
+    start.push_back(n);
+    // ---- scoring: small outputs
+    const hc_params p = to_params(ps_);
+    const size_t erec = ps_.exact_scores ? sizeof(hc_edge_small_exact) : sizeof(hc_edge_small);
+    size_t ecap = std::max<size_t>(n / 4, 1024);
+    std::unique_ptr<char[]> ebuf(new char[ecap * erec]);
+    std::unique_ptr<uint64_t[]> bits(new uint64_t[n / 64 + 2]);
+    uint64_t ne = 0, nn = 0;
+    hc_batch_stats bst;
+    memset(&bst, 0, sizeof(bst));
+    if (n) {
+        rc = hc_score_batch_runs_small(fastq_->device_store(), &p, anchor.data(), start.data(), anchor.size(), en.get(), n, ebuf.get(), ecap, &ne,
+                                       bits.get(), &nn, &bst);
+        if (rc == HC_ERR_CAPACITY) {
+            ecap = ne;
+            ebuf.reset(new char[ecap * erec]);
+            rc = hc_score_batch_runs_small(fastq_->device_store(), &p, anchor.data(), start.data(), anchor.size(), en.get(), n, ebuf.get(), ecap,
+                                           &ne, bits.get(), &nn, &bst);
+        }
+        if (rc != HC_OK) die(std::string("hc_score_batch_runs_small: ") + hc_last_error());
+    }
+    scored_candidates += n;
+    device_ms += bst.total_ms;
+    const double t2 = wall_s();
+    t_score_s += t2 - t1;
+    // ---- accepted edges: Edge fields from the candidate + the small record, every thread a share
+    std::vector<Edge> es(ne);
+    const uint32_t* ml = fastq_->mate_len.data();
+    bool overflow = false;
+#pragma omp parallel for schedule(static) reduction(|| : overflow)
+    for (long long k = 0; k < (long long)ne; k++) {
+        const hc_edge_small* hs = reinterpret_cast<const hc_edge_small*>(ebuf.get() + (size_t)k * erec);   // the common head of both records
+        const hc_candidate& c = cand[hs->cand];
+        const Read& r1 = fastq_->m_read_vec[c.idx1];
+        const Read& r2 = fastq_->m_read_vec[c.idx2];
+        const bool two = r1.is_paired || r2.is_paired;
+        overflow = overflow || (hs->flags & HC_EDGE_OVERFLOW);
+        Edge& e = es[(size_t)k];
+        if (ps_.exact_scores) {   // :138 and :256-261 with the host libm on the reference's own mean logs
+            const hc_edge_small_exact* hx = reinterpret_cast<const hc_edge_small_exact*>(hs);
+            const double ov1 = hx->compared[0] ? exp(hx->mean_log[0]) : 0.0;
+            if (two) {
+                const double ov2 = hx->compared[1] ? exp(hx->mean_log[1]) : 0.0;
+                e.score = (ov1 > ps_.edge_threshold && ov2 > ps_.edge_threshold) ? 0.5 * (ov1 + ov2) : std::min(ov1, ov2);
+            } else {
+                e.score = ov1;
+            }
+        } else {
+            e.score = hs->score;
+        }
+        double r0 = hs->compared[0] ? (hs->mismatches[0] ? (double)(float)(int)hs->mismatches[0] / (double)hs->compared[0] : 0.0) : 1.0;   // :132
+        if (two) {
+            const double rb = hs->compared[1] ? (hs->mismatches[1] ? (double)(float)(int)hs->mismatches[1] / (double)hs->compared[1] : 0.0) : 1.0;
+            r0 = std::max(r0, rb);                                                                                                         // :254
+        }
+        e.mismatch_rate = r0;
+        int32_t p3, p4;
+        hc_edge_extra_pos(c.pos1, c.pos2, (char)c.ord, ml[2 * c.idx1], ml[2 * c.idx1 + 1], ml[2 * c.idx2], ml[2 * c.idx2 + 1], &p3, &p4);
+        e.pos1 = (int)c.pos1; e.pos2 = (int)c.pos2; e.pos3 = p3; e.pos4 = p4;
+        e.ori1 = c.ori1 != 0; e.ori2 = c.ori2 != 0;
+        e.ord = (char)c.ord;
+        e.vertex1 = r1.vertex_id; e.vertex2 = r2.vertex_id;
+        e.overlap_perc = (int)(c.perc2 > 0 ? (unsigned int)(0.5 * (c.perc1 + c.perc2)) : c.perc1);            // Overlap::get_perc, :203-210
+        e.overlap_len1 = (int)c.len1;
+        e.overlap_len2 = two ? (int)c.len2 : 0;                                                                // set_len(len1, 0) for S-S, :227
+        e.overlap_len = e.overlap_len1 + e.overlap_len2;
+        if (e.pos1 == 0 && e.vertex1 > e.vertex2) e.swap_reads();                                              // :443-448
+    }
+    if (overflow) die("a window of 65536 or more positions: not representable in the small edge records");
+    unsigned int doubles = 0;
+    if (ps_.gpu_dedup && ne) {
+        std::vector<hc_dedup_edge> de(ne);
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < (long long)ne; k++) {
+            const Edge& e = es[(size_t)k];
+            hc_dedup_edge& d = de[(size_t)k];
+            memset(&d, 0, sizeof(d));
+            d.vertex1 = (uint32_t)e.vertex1; d.vertex2 = (uint32_t)e.vertex2; d.score = e.score; d.mismatch_rate = e.mismatch_rate;
+            d.pos1 = e.pos1; d.pos2 = e.pos2; d.pos3 = e.pos3; d.overlap_len = e.overlap_len; d.perc = e.overlap_perc;
+            d.ori1 = e.ori1; d.ori2 = e.ori2;
+        }
+        std::vector<uint8_t> win(ne);
+        uint64_t counts[2] = {0, 0};
+        rc = hc_dedup_edges(de.data(), de.size(), ps_.ignore_inclusions, win.data(), (uint8_t*)graph_->inclusions.data(),
+                            graph_->inclusions.size(), counts, ps_.first_device);
+        if (rc != HC_OK) die(std::string("hc_dedup_edges: ") + hc_last_error());
+        for (size_t k = 0; k < ne; k++) if (win[k]) graph_->addEdge(es[k]);
+        dup_count += (unsigned int)counts[0];
+        inclusion_count += (unsigned int)counts[1];
+    } else {
+        for (size_t k = 0; k < ne; k++) insert_edge(es[k], doubles);
+        dup_count += doubles;
+    }
+    const double t3 = wall_s();
+    t_edges_s += t3 - t2;
+    if (ps_.verbose) {
+        std::cout << "Number of self-overlapping reads: " << self_overlap_count << "\n";
+        std::cout << "Number of inclusion edges: " << inclusion_count << "\n";
+    }
+    // ---- nonedge_overlaps.txt: the scored non-edges (bit map) in file order, then the pre-filtered lines (:546-555, :654-660);
+    // every thread formats a share of the words into its own buffer, the buffers are written in order
+    const size_t words = (n + 63) / 64;
+    std::vector<std::string> part(T + 1);
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        const size_t lo = words * (size_t)t / (size_t)T, hi = words * (size_t)(t + 1) / (size_t)T;
+        std::string& b = part[t];
+        for (size_t w = lo; w < hi; w++) {
+            uint64_t m = bits[w];
+            while (m) {
+                const size_t i = w * 64 + (size_t)__builtin_ctzll(m);
+                m &= m - 1;
+                const hc_candidate& c = cand[i];
+                put_cand_line(b, c, fastq_->m_read_vec[c.idx1].read_id, fastq_->m_read_vec[c.idx2].read_id);
+            }
+        }
+    }
+    for (uint64_t k = 0; k < st.n_filtered; k++) put_rec_line(part[T], filt[k]);
+    FILE* out = std::fopen((ps_.output_dir + "nonedge_overlaps.txt").c_str(), "ab");
+    if (!out) die("Unable to open nonedge_overlaps.txt");
+    for (const std::string& b : part) if (!b.empty()) std::fwrite(b.data(), 1, b.size(), out);
+    std::fclose(out);
+    t_write_s += wall_s() - t3;
+    return true;
+}
+
 void EdgeCalculator::construct_edges() {                                          // src/EdgeCalculator.cpp:561-666
     if (ps_.add_duplicates) die("add_duplicates=true is not supported by this build (no driver script uses it)");
     std::remove("nonedge_overlaps.txt");                                          // :566 (cwd, like the reference)
     const size_t per_batch = 1000000;                                             // :571
     std::vector<Overlap> batch, filtered;
     batch.reserve(per_batch);
+    if (ps_.gpu_parse && construct_edges_arrays()) return;
     if (ps_.gpu_parse) {
         ingest_on_device(batch, filtered);
     } else {

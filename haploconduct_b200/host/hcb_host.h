@@ -83,6 +83,7 @@ public:
     std::map<read_id_t, unsigned int> m_ID_to_index;  // src/FastqStorage.h:54
     unsigned int m_readcount_single = 0, m_readcount_paired = 0;
     unsigned int max_read_len = 0;                    // longest mate (decides the candidate record size)
+    std::vector<uint32_t> mate_len;                   // 2 per read: sequence lengths (/1, /2; 0 for the missing mate of a single)
 
     unsigned int get_readcount() const { return (unsigned int)m_read_vec.size(); }
     hc_store* device_store() const { return store_; }
@@ -170,6 +171,9 @@ private:
     // one line of the text loop (:583-635): 0 skipped / dropped, 1 appended to batch, 2 appended to filtered
     int handle_line(const std::string& line, std::vector<Overlap>& batch, std::vector<Overlap>& filtered);
     void ingest_on_device(std::vector<Overlap>& batch, std::vector<Overlap>& filtered);
+    // --gpu_parse: the whole stage on arrays -- the file in one read, one parse call, run-encoded records, small outputs,
+    // edges and non-edge lines built by all host threads; false if the records do not fit (then the path above runs)
+    bool construct_edges_arrays();
     std::vector<Edge> pending_;   // gpu_dedup: accepted edges of all batches, normalised, in order
     ProgramSettings ps_;
     std::shared_ptr<FastqStorage> fastq_;

@@ -273,6 +273,17 @@ int hc_score_batch_runs_small(hc_store* s, const hc_params* p,
                               void* edges, uint64_t edges_cap, uint64_t* n_edges,
                               uint64_t* nonedge_bits, uint64_t* n_nonedges,
                               hc_batch_stats* stats /* nullable */);
+/* The same on 6-byte run-encoded records, for stores of at most 2^25 reads whose reads are shorter than 512 bases (every
+ * Illumina read set): the host->device copy of the records is what bounds a call on host buffers, so their size is
+ * its speed.  A record is a 48-bit little-endian number: bits 0-24 the other read, 25 "the anchor is ID2", 26 ORI1 is
+ * '+', 27 ORI2 is '+', 28-29 ORD (0 '-', 1 '1', 2 '2'), 30-38 POS1, 39-47 POS2. */
+typedef struct { uint8_t b[6]; } hc_candidate_entry6;
+int hc_score_batch_runs6_small(hc_store* s, const hc_params* p,
+                               const uint32_t* run_anchor, const uint64_t* run_start, uint64_t n_runs,
+                               const hc_candidate_entry6* entries, uint64_t n,
+                               void* edges, uint64_t edges_cap, uint64_t* n_edges,
+                               uint64_t* nonedge_bits, uint64_t* n_nonedges,
+                               hc_batch_stats* stats /* nullable */);
 /* The same on 12-byte records (lists that were not cut into runs). */
 int hc_score_batch_short_small(hc_store* s, const hc_params* p,
                                const hc_candidate_short* cand, uint64_t n,

@@ -64,13 +64,14 @@ def _rank(rank, world, port, name, outdir):
     n = len(mine)
     with capi.Store(g.rs, first_device=rank, n_devices=1) as st:
         d_c = torch.from_numpy(mine.view(np.uint8).reshape(-1)).to(dev)
-        d_e = torch.zeros((n + 1, 48), dtype=torch.uint8, device=dev)
+        cap = len(cands) // world + 2                                   # the same on every rank: the lists are padded to it
+        d_e = torch.zeros((cap, 48), dtype=torch.uint8, device=dev)
         d_n = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         d_cnt = torch.zeros(4, dtype=torch.int64, device=dev)
         stream = torch.cuda.current_stream(dev)
         st.score_batch_device(rank, stream.cuda_stream, g.params(), d_c.data_ptr(), n, 0, d_e.data_ptr(), n, d_n.data_ptr(), n, d_cnt.data_ptr(), False)
-        d_e.view(torch.int64).reshape(n + 1, 6)[:, 0] += lo            # hc_edge.cand: local -> global index
-        gather = D.DeviceGather(48, len(cands) // world + 2, dev)
+        d_e.view(torch.int64).reshape(cap, 6)[:, 0] += lo              # hc_edge.cand: local -> global index
+        gather = D.DeviceGather(48, cap, dev)
         gather.gather(d_e, d_cnt[:1])
         allv = gather.concatenated().cpu().numpy().view(F.EDGE)
     np.save(os.path.join(outdir, "r%d.npy" % rank), allv)

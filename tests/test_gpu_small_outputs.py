@@ -31,7 +31,8 @@ def test_small_outputs_equal_full_outputs(built_lib, monkeypatch, name, exact, c
     p = g.params(flags=F.FLAG_EXACT_EDGE_SCORES if exact else 0)
     with capi.Store(g.rs) as st:
         edges, nonedge, per, _ = st.score_batch(p, cands)
-        for runs in (True, False):
+        small6 = g.rs.n_reads < (1 << 25) and int(g.rs.descs["seq_len"].max()) < 512
+        for runs in (True, False) + ((6,) if small6 else ()):
             se, flags, stats = st.score_batch_small(p, cands, runs=runs)
             assert np.array_equal(np.nonzero(flags)[0].astype(np.uint64), nonedge)
             assert np.array_equal(se["cand"].astype(np.uint64), edges["cand"])

@@ -87,6 +87,19 @@ def main():
             if os.path.exists(d + "/ref1.tsv"):
                 g1 = O.parse_graph_dump(d + "/ref1.tsv")
                 res[name]["identical_to_1_thread_reference"] = bool(len(g1) == len(g_own) and g1.tobytes() == g_own.tobytes())
+    # where the mirror's time goes, next to what each part would take at the machine's rates (a roofline for the host side)
+    m = res.get("mirror_device_ingest", {})
+    if m and "reference" in res:
+        ov, fq = res["overlaps_file_bytes"], sum(os.path.getsize(d + "/" + f) for f in ("p1.fastq", "p2.fastq"))
+        res["breakdown"] = {
+            "speedup_construct_edges_vs_reference": res["reference"]["t_construct_edges_s"] / max(m.get("t_construct_edges_s", 0), 1e-9),
+            "speedup_wall_vs_reference": res["reference"]["wall_s"] / max(m["wall_s"], 1e-9),
+            "phases_s": {k: m.get(k) for k in ("t_fastq_s", "t_ingest_s", "t_score_s", "t_edges_s", "t_write_s")},
+            "device_busy_ms": {"parse": m.get("parse_device_ms"), "score": m.get("device_ms")},
+            "bytes": {"overlaps_file": ov, "fastq_files": fq},
+            "floors_s": {"read both inputs once at 3 GB/s (page cache)": (ov + fq) / 3e9, "copy them to the device at 25 GB/s": (ov + fq) / 25e9},
+            "note": "t_fastq_s includes the creation of the CUDA context (a few tenths of a second per process)",
+        }
     print(json.dumps(res))
 
 
