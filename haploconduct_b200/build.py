@@ -61,14 +61,14 @@ def build_host(verbose: bool = False) -> str:
     host = os.path.join(HERE, "host")
     exe = os.path.join(LIBDIR, "hc_edgecalc")
     cmd = [HOST_CXX, "-O2", "-std=c++14", "-Wall", "-fopenmp", "-o", exe, os.path.join(host, "hc_edgecalc_main.cpp"),
-           os.path.join(host, "hcb_host.cpp"), "-L" + LIBDIR, "-lhc_b200", "-Wl,-rpath,$ORIGIN"]
+           os.path.join(host, "hcb_host.cpp"), "-L" + LIBDIR, "-lhc_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     # hc_fno: the FindNextOverlaps step (hcb::SRBuilder, hcb_fno.h) on the C ABI
     fno = os.path.join(LIBDIR, "hc_fno")
     cmd = [HOST_CXX, "-O2", "-std=c++14", "-Wall", "-fopenmp", "-o", fno, os.path.join(host, "hc_fno_main.cpp"), os.path.join(host, "hcb_fno.cpp"),
-           os.path.join(host, "hcb_host.cpp"), "-L" + LIBDIR, "-lhc_b200", "-Wl,-rpath,$ORIGIN"]
+           os.path.join(host, "hcb_host.cpp"), "-L" + LIBDIR, "-lhc_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -318,6 +318,16 @@ int hc_device_count(void) {
     return n;
 }
 
+int hc_warm_up(int device) {
+    if (hc_device_count() == 0) return fail(HC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    CU(cudaFree(nullptr));                 // creates the context
+    void* p = nullptr;                      // first use of the pinned / device allocators
+    CU(cudaMallocHost(&p, 1 << 20));
+    CU(cudaFreeHost(p));
+    return HC_OK;
+}
+
 double hc_phred_to_prob(int phred) { return hc_tables_phred_to_prob(phred); }
 
 void hc_edge_extra_pos(uint32_t pos1, uint32_t pos2, char ord, uint32_t len1a, uint32_t len1b, uint32_t len2a, uint32_t len2b,

@@ -12,6 +12,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 namespace hcb {
 
@@ -143,11 +144,18 @@ static std::string slurp_file(const std::string& path) {
 FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
     if (ps.gpu_fastq) {
         if (!ps.id_correspondence.empty()) die("--IDs is not supported together with --gpu_fastq");
+        const double tf0 = wall_s();
+        std::thread warm([&ps]() { hc_warm_up(ps.first_device); });      // the CUDA context comes up while the files are read
         const std::string s = slurp_file(ps.singles_file), p1 = slurp_file(ps.paired1_file), p2 = slurp_file(ps.paired2_file);
+        warm.join();
+        const double tf1 = wall_s();
+        t_read_s = tf1 - tf0;
         first_device_ = ps.first_device;
         store_ = hc_store_create_fastq(s.data(), s.size(), p1.data(), p1.size(), p2.data(), p2.size(), ps.max_reads, ps.first_device,
                                        ps.n_devices);
         if (!store_) die(std::string("hc_store_create_fastq: ") + hc_last_error());
+        const double tf2 = wall_s();
+        t_store_s = tf2 - tf1;
         const uint64_t n = hc_store_n_reads(store_);
         std::vector<uint64_t> ids(n);
         std::vector<uint32_t> lens(2 * n);
@@ -163,6 +171,7 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
             // with the overlaps file parsed on the device too, nothing on the host looks an id up (the device map does)
             if (!ps.gpu_parse) m_ID_to_index.insert(std::make_pair((read_id_t)ids[i], (unsigned int)i));
         }
+        t_index_s = wall_s() - tf2;
         if (ps.verbose) {
             std::cout << "Singles: " << m_readcount_single << std::endl;
             std::cout << "Pairs: " << m_readcount_paired << std::endl;
@@ -719,7 +728,6 @@ bool EdgeCalculator::construct_edges_arrays() {
     if (rc != HC_OK) die(std::string("hc_ingest_overlaps: ") + hc_last_error());
     parse_device_ms += st.device_ms;
     if (st.first_error_line != ~0ull) return false;      // the line-by-line path reproduces what the reference does up to that line
-    for (uint64_t k = 0; k < st.n_skipped; k++) std::cout << "incorrect overlap; skipping" << std::endl;   // :600-603
     const size_t n = st.n_scored;
     const double t1 = wall_s();
     t_ingest_s += t1 - t0;
@@ -727,6 +735,7 @@ bool EdgeCalculator::construct_edges_arrays() {
 #pragma omp parallel for schedule(static) reduction(&& : fits)
     for (long long i = 0; i < (long long)n; i++) fits = fits && cand[i].pos1 < (1u << 14) && cand[i].pos2 < (1u << 14);
     if (!fits) return false;
+    for (uint64_t k = 0; k < st.n_skipped; k++) std::cout << "incorrect overlap; skipping" << std::endl;   // :600-603
     // ---- run-encoded records: a run = a stretch of candidates with the same smaller read index (an overlaps file sorted by
     // read gives long runs; any list gives valid ones), cut by every thread in its own share
     std::unique_ptr<hc_candidate_entry[]> en(new hc_candidate_entry[n ? n : 1]);

@@ -322,6 +322,10 @@ int hc_overlap_score_multi(const char* seq1, uint32_t len1, const char* seq2, ui
                            const char* qual1, const char* qual2, const uint32_t* pos, uint32_t n_pos,
                            const hc_params* p, double* scores, double* mismatch_rates, uint8_t* above);
 
+/* Creates the CUDA context of `device` (a few tenths of a second per process).  Optional: every call does it on demand;
+ * a host calls this from a second thread while it reads its input files, so that the two overlap. */
+int hc_warm_up(int device);
+
 /* EdgeCalculator::phred_to_prob (src/EdgeCalculator.cpp:59-63), host arithmetic: pow(10, -Q/10.0). */
 double hc_phred_to_prob(int phred);
 

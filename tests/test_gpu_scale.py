@@ -126,9 +126,8 @@ def test_million_candidates_against_the_reference_binary(built_lib, c4_small, tm
     d = str(tmp_path)
     F.write_fastq_set(small, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", c, small.ids)
-    RL = int(rs.descs["seq_len"][0, 0])
     out = O.run_ref(d, d + "/ov.txt", paired1=d + "/p1.fastq", paired2=d + "/p2.fastq", dump_cands=True, threads=1, edge_threshold=0.97,
-                    min_overlap_len=RL)
+                    min_overlap_len=150)        # the generator keeps candidates whose mates overlap by >= 75 = half of it each
     ref = out["cands"]
     assert len(ref) == len(c)                                    # every candidate passes the pre-filter (both mates overlap >= L/2)
     with capi.Store(small) as st:
