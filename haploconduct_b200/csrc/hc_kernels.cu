@@ -559,7 +559,7 @@ __device__ __noinline__ void write_per_cand(const hc_kparams& P, u64 i, double s
     r.status[0] = (uint8_t)st[0];
     r.status[1] = (uint8_t)st[1];
     r.exact = (uint8_t)exact;
-    r.reserved = 0;
+    r.indel_count = 0;
     P.per_cand[i] = r;
 }
 
@@ -1110,7 +1110,7 @@ __global__ void __launch_bounds__((WALK ? HC_WALK_WARPS : HC_WARPS_MAX) * 32, WA
 // One thread re-adds one window exactly like src/EdgeCalculator.cpp:103-138: same double addends
 // (host-built with the reference's expressions and libm), same order, IEEE add/mul/div with
 // explicit _rn intrinsics so nothing is contracted into an FMA.
-__device__ void exact_window(const hc_kparams& P, const Win& w, double& mean, double& mmrate, uint32_t& mmc,
+__device__ void exact_window(const hc_kparams& P, const double* __restrict__ sdbl, const Win& w, double& mean, double& mmrate, uint32_t& mmc,
                              uint32_t& cmp, uint32_t& status) {
     mean = 0.0;
     mmrate = 1.0;
@@ -1123,25 +1123,32 @@ __device__ void exact_window(const hc_kparams& P, const Win& w, double& mean, do
     uint32_t tl = 0, mm = 0;
     const u64 yp = 16ull * w.ypos16;
     if (P.packed) {
-        // 16 positions per step: B side one aligned 128-bit load, A side five words + funnel shifts;
-        // the additions stay strictly sequential in position order (:106-121).
-        const uint32_t sh = ((uint32_t)w.xpos & 3u) * 8u;
-        for (uint32_t i0 = 0; i0 < w.L; i0 += 16) {
-            const uint32_t* xa = reinterpret_cast<const uint32_t*>(P.pk + ((w.xpos + i0) & ~3ull));
-            const uint32_t x0 = __ldg(xa), x1 = __ldg(xa + 1), x2 = __ldg(xa + 2), x3 = __ldg(xa + 3), x4 = __ldg(xa + 4);
-            const uint4 yv = __ldg(reinterpret_cast<const uint4*>(P.pk + yp + i0));
-            const uint32_t A[4] = {__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
-                                   __funnelshift_r(x3, x4, sh)};
-            const uint32_t B[4] = {yv.x, yv.y, yv.z, yv.w};
-            const uint32_t lim = min(16u, w.L - i0);
+        // 32 positions per step, fetched like a lane-chunk of the score kernel (three 256-bit loads: a thread's window is its
+        // own, so every load instruction of a warp costs 32 wavefronts -- few, wide ones); the addends come from the copy of
+        // the double table in shared memory when there is one (sdbl); the additions stay strictly sequential in position
+        // order (:106-121).
+        const uint32_t nblk = (w.L + 31u) >> 5;
+        for (uint32_t k = 0; k < nblk; k++) {
+            const PkRow r = load32_packed(P, w.xpos, w.ypos16, w.L, 0u, k);
+            const bool s4 = (r.off & 16u) != 0, s2 = (r.off & 8u) != 0, s1 = (r.off & 4u) != 0;
+            uint32_t V2[12], V1[10], V[9];
 #pragma unroll
-            for (uint32_t j = 0; j < 16; j++) {
-                if (j < lim) {
-                    const uint32_t a = (A[j >> 2] >> (8 * (j & 3))) & 0xffu, b = (B[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            for (int i = 0; i < 12; i++) V2[i] = s4 ? r.a[i + 4] : r.a[i];
+#pragma unroll
+            for (int i = 0; i < 10; i++) V1[i] = s2 ? V2[i + 2] : V2[i];
+#pragma unroll
+            for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
+            const uint32_t sh = (r.off & 3u) * 8u;
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j++) {
+                if (j < r.n) {
+                    const uint32_t wa = __funnelshift_r(V[j >> 2], V[(j >> 2) + 1], sh);
+                    const uint32_t a = (wa >> (8 * (j & 3))) & 0xffu, b = (r.y[j >> 2] >> (8 * (j & 3))) & 0xffu;
                     if (a != 0 && b != 0) {                                           // N, :35-39,:122-124
                         const uint32_t mis = (a >> 6) != (b >> 6);
                         mm += mis;
-                        const double lp = __ldg(P.dbl_table + hc_dbl_index(a & 63u, b & 63u, mis, n1));
+                        const uint32_t ti = hc_dbl_index(a & 63u, b & 63u, mis, n1);
+                        const double lp = sdbl ? sdbl[ti] : __ldg(P.dbl_table + ti);
                         if (lp > 0.0) { status = HC_WIN_VOID; return; }              // :125-127
                         total = __dadd_rn(total, lp);                                 // :119
                         tl++;
@@ -1226,10 +1233,22 @@ __device__ void exact_window_warp(const hc_kparams& P, const Win& w, int lane, d
     mean = __dmul_rn(__ddiv_rn(1.0, dl), total);                         // :137
 }
 
-__global__ void hc_exact_kernel(const hc_kparams P) {
+__global__ void hc_exact_kernel(const hc_kparams P, uint32_t table_in_smem) {
+    extern __shared__ __align__(16) unsigned char smem[];
     const u64 nf = P.counters[HC_CNT_FLAGGED];
     const u64 nthreads = (u64)gridDim.x * blockDim.x;
     const bool warp_mode = nf * 32ull <= nthreads;     // every queued candidate can have a warp of its own
+    // many queued candidates (HC_FLAG_EXACT_EDGE_SCORES: every accepted edge): one thread each, and the table of addends in
+    // shared memory -- the lookups of a warp are 32 different addresses, which the global-memory path pays with up to 32
+    // wavefronts each and shared memory with a few
+    const double* sdbl = nullptr;
+    if (table_in_smem && !warp_mode && nf > 0) {
+        double* t = reinterpret_cast<double*>(smem);
+        const uint32_t nent = (P.ncodes + 1u) * (P.ncodes + 1u) * 2u;
+        for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x) t[k] = P.dbl_table[k];
+        __syncthreads();
+        sdbl = t;
+    }
     const int lane = threadIdx.x & 31;
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const bool writer = !warp_mode || lane == 0;
@@ -1245,7 +1264,7 @@ __global__ void hc_exact_kernel(const hc_kparams P) {
 #pragma unroll
         for (int w = 0; w < 2; w++) {
             if (warp_mode) exact_window_warp(P, s.w[w], lane, mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
-            else exact_window(P, s.w[w], mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
+            else exact_window(P, sdbl, s.w[w], mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
             if (stt[w] == HC_WIN_SCORED) {
                 ae[w] = mean[w] >= P.t_edge;   // <=> host-libm exp(mean) > edge_threshold
                 ao[w] = mean[w] >= P.t_ov;
@@ -1579,7 +1598,14 @@ cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint
 }
 
 cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st) {
-    hc_exact_kernel<<<1184, 128, 0, st>>>(P);
+    // packed layout: room for the double table ((K+1)^2 * 2 addends, 18 KB for 33 quality values) next to 128 threads
+    const size_t tbl = (size_t)(P.ncodes + 1u) * (P.ncodes + 1u) * 2u * sizeof(double);
+    const bool in_smem = P.packed && tbl <= 96u * 1024u;
+    if (in_smem) {
+        cudaError_t e = cudaFuncSetAttribute(hc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl);
+        if (e != cudaSuccess) return e;
+    }
+    hc_exact_kernel<<<1184, 128, in_smem ? tbl : 0, st>>>(P, in_smem ? 1u : 0u);
     return cudaGetLastError();
 }
 

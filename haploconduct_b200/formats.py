@@ -110,7 +110,7 @@ RESULT = np.dtype(
     [
         ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos3", "<i4"), ("pos4", "<i4"),
         ("mismatches", "<u4", (2,)), ("compared", "<u4", (2,)),
-        ("cls", "u1"), ("status", "u1", (2,)), ("exact", "u1"), ("reserved", "<u4"),
+        ("cls", "u1"), ("status", "u1", (2,)), ("exact", "u1"), ("indel_count", "<u4"),
     ]
 )
 EDGE = np.dtype([("cand", "<u8"), ("score", "<f8"), ("mismatch_rate", "<f8"), ("pos3", "<i4"), ("pos4", "<i4"),

@@ -69,8 +69,8 @@ int main(int argc, char** argv) {
     if (!dump_graph.empty()) graph->dumpAdjacency(dump_graph);
     if (!digraph.empty()) graph->writeDiGraphToFile(digraph);
     printf("{\"reads_single\": %u, \"reads_paired\": %u, \"scored\": %lu, \"t_fastq_s\": %.6f, \"t_construct_edges_s\": %.6f, "
-           "\"t_fastq_read_s\": %.3f, \"t_fastq_store_s\": %.3f, \"t_fastq_index_s\": %.3f, \"device_ms\": %.3f, \"parse_device_ms\": %.3f, \"t_ingest_s\": %.3f, \"t_score_s\": %.3f, \"t_edges_s\": %.3f, \"t_write_s\": %.3f, \"graph_edges\": %u, \"dup_count\": %u, \"inclusion_count\": %u}\n",
-           fastq->m_readcount_single, fastq->m_readcount_paired, ec.scored_candidates, t_fastq, t_ce, fastq->t_read_s, fastq->t_store_s, fastq->t_index_s, ec.device_ms, ec.parse_device_ms, ec.t_ingest_s, ec.t_score_s, ec.t_edges_s, ec.t_write_s,
+           "\"t_fastq_read_s\": %.3f, \"t_cuda_init_s\": %.3f, \"t_fastq_store_s\": %.3f, \"t_fastq_index_s\": %.3f, \"device_ms\": %.3f, \"parse_device_ms\": %.3f, \"t_ingest_s\": %.3f, \"t_score_s\": %.3f, \"t_edges_s\": %.3f, \"t_write_s\": %.3f, \"graph_edges\": %u, \"dup_count\": %u, \"inclusion_count\": %u}\n",
+           fastq->m_readcount_single, fastq->m_readcount_paired, ec.scored_candidates, t_fastq, t_ce, fastq->t_read_s, fastq->t_cuda_init_s, fastq->t_store_s, fastq->t_index_s, ec.device_ms, ec.parse_device_ms, ec.t_ingest_s, ec.t_score_s, ec.t_edges_s, ec.t_write_s,
            graph->getEdgeCount(), ec.dup_count, ec.inclusion_count);
     return 0;
 }

@@ -12,7 +12,6 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
-#include <thread>
 
 namespace hcb {
 
@@ -144,12 +143,15 @@ static std::string slurp_file(const std::string& path) {
 FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
     if (ps.gpu_fastq) {
         if (!ps.id_correspondence.empty()) die("--IDs is not supported together with --gpu_fastq");
+        // (creating the CUDA context from a second thread while this one reads the files was measured and is slower: the
+        // context creation and the page faults of the file buffers contend for the address-space lock)
         const double tf0 = wall_s();
-        std::thread warm([&ps]() { hc_warm_up(ps.first_device); });      // the CUDA context comes up while the files are read
         const std::string s = slurp_file(ps.singles_file), p1 = slurp_file(ps.paired1_file), p2 = slurp_file(ps.paired2_file);
-        warm.join();
+        const double tfr = wall_s();
+        t_read_s = tfr - tf0;
+        if (hc_warm_up(ps.first_device) != HC_OK) die(std::string("hc_warm_up: ") + hc_last_error());
         const double tf1 = wall_s();
-        t_read_s = tf1 - tf0;
+        t_cuda_init_s = tf1 - tfr;
         first_device_ = ps.first_device;
         store_ = hc_store_create_fastq(s.data(), s.size(), p1.data(), p1.size(), p2.data(), p2.size(), ps.max_reads, ps.first_device,
                                        ps.n_devices);

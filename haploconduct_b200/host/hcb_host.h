@@ -84,7 +84,7 @@ public:
     unsigned int m_readcount_single = 0, m_readcount_paired = 0;
     unsigned int max_read_len = 0;                    // longest mate (decides the candidate record size)
     std::vector<uint32_t> mate_len;                   // 2 per read: sequence lengths (/1, /2; 0 for the missing mate of a single)
-    double t_read_s = 0, t_store_s = 0, t_index_s = 0;  // wall clock of the constructor's phases (not in the reference)
+    double t_read_s = 0, t_cuda_init_s = 0, t_store_s = 0, t_index_s = 0;  // wall clock of the constructor's phases (not in the reference)
 
     unsigned int get_readcount() const { return (unsigned int)m_read_vec.size(); }
     hc_store* device_store() const { return store_; }

@@ -149,7 +149,9 @@ typedef struct {
     uint8_t  cls;              /* HC_CLASS_*                                                        */
     uint8_t  status[2];        /* HC_WIN_* per window                                               */
     uint8_t  exact;            /* 1 if the reference-order re-summation decided this candidate      */
-    uint32_t reserved;
+    uint32_t indel_count;      /* always 0: the reference compares the windows gaplessly, position by position
+                                  (src/EdgeCalculator.cpp:106-117); indels exist only upstream, in the candidate
+                                  producers (OLA != OLB of rust-overlaps, CIGAR I/D of sam2overlaps.py)            */
 } hc_result;                   /* 48 bytes */
 
 /* One accepted edge, emitted in INPUT ORDER (= the reference's 1-thread order). */

@@ -74,8 +74,9 @@ def overlap_score(seq1: str, seq2: str, q1: str, q2: str, pos: int, params: np.n
 
 
 def window_lengths(res: np.ndarray) -> np.ndarray:
-    """sum of window lengths per candidate (the oracle parks it in RESULT.reserved)."""
-    return res["reserved"].astype(np.int64)
+    """sum of window lengths per candidate (the oracle parks it in the last word of its RESULT record -- the field the
+    product reports as indel_count = 0)."""
+    return res["indel_count"].astype(np.int64)
 
 
 # ---- the compiled reference ------------------------------------------------------------------------

@@ -199,7 +199,8 @@ def test_long_contigs_and_wide_quality_alphabet(built_lib):
     with capi.Store(rs) as st:
         assert st.quality_alphabet == 94
         per, ref, stats = _against_oracle(rs, F.make_params(edge_threshold=0.995, min_read_len=100), c, store=st)
-    assert int(ref["reserved"].max()) > 4096
+    assert int(O.window_lengths(ref).max()) > 4096
+    assert not per["indel_count"].any()            # the path compares gaplessly: no indels
 
 
 def test_empty_single_and_capacity(built_lib):
