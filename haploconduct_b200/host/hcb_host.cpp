@@ -12,6 +12,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 namespace hcb {
 
@@ -787,6 +788,37 @@ bool EdgeCalculator::construct_edges_arrays() {
     device_ms += bst.total_ms;
     const double t2 = wall_s();
     t_score_s += t2 - t1;
+    // ---- nonedge_overlaps.txt: the scored non-edges (bit map) in file order, then the pre-filtered lines (:546-555, :654-660);
+    // every thread formats a share of the words into its own buffer; the buffers are written in order by a thread of their own
+    // while this one builds the edges (both only read the candidates)
+    const size_t words = (n + 63) / 64;
+    std::vector<std::string> part(T + 1);
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        const size_t lo = words * (size_t)t / (size_t)T, hi = words * (size_t)(t + 1) / (size_t)T;
+        std::string& b = part[t];
+        for (size_t w = lo; w < hi; w++) {
+            uint64_t m = bits[w];
+            while (m) {
+                const size_t i = w * 64 + (size_t)__builtin_ctzll(m);
+                m &= m - 1;
+                const hc_candidate& c = cand[i];
+                put_cand_line(b, c, fastq_->m_read_vec[c.idx1].read_id, fastq_->m_read_vec[c.idx2].read_id);
+            }
+        }
+    }
+    for (uint64_t k = 0; k < st.n_filtered; k++) put_rec_line(part[T], filt[k]);
+    bool write_failed = false;
+    const std::string nonedge_path = ps_.output_dir + "nonedge_overlaps.txt";
+    std::thread writer([&part, &write_failed, &nonedge_path]() {
+        FILE* out = std::fopen(nonedge_path.c_str(), "ab");
+        if (!out) { write_failed = true; return; }
+        for (const std::string& b : part) if (!b.empty()) std::fwrite(b.data(), 1, b.size(), out);
+        std::fclose(out);
+    });
+    const double t2b = wall_s();
+    t_write_s += t2b - t2;
     // ---- accepted edges: Edge fields from the candidate + the small record, every thread a share
     std::vector<Edge> es(ne);
     const uint32_t* ml = fastq_->mate_len.data();
@@ -856,35 +888,13 @@ bool EdgeCalculator::construct_edges_arrays() {
         dup_count += doubles;
     }
     const double t3 = wall_s();
-    t_edges_s += t3 - t2;
+    t_edges_s += t3 - t2b;
     if (ps_.verbose) {
         std::cout << "Number of self-overlapping reads: " << self_overlap_count << "\n";
         std::cout << "Number of inclusion edges: " << inclusion_count << "\n";
     }
-    // ---- nonedge_overlaps.txt: the scored non-edges (bit map) in file order, then the pre-filtered lines (:546-555, :654-660);
-    // every thread formats a share of the words into its own buffer, the buffers are written in order
-    const size_t words = (n + 63) / 64;
-    std::vector<std::string> part(T + 1);
-#pragma omp parallel num_threads(T)
-    {
-        const int t = omp_get_thread_num();
-        const size_t lo = words * (size_t)t / (size_t)T, hi = words * (size_t)(t + 1) / (size_t)T;
-        std::string& b = part[t];
-        for (size_t w = lo; w < hi; w++) {
-            uint64_t m = bits[w];
-            while (m) {
-                const size_t i = w * 64 + (size_t)__builtin_ctzll(m);
-                m &= m - 1;
-                const hc_candidate& c = cand[i];
-                put_cand_line(b, c, fastq_->m_read_vec[c.idx1].read_id, fastq_->m_read_vec[c.idx2].read_id);
-            }
-        }
-    }
-    for (uint64_t k = 0; k < st.n_filtered; k++) put_rec_line(part[T], filt[k]);
-    FILE* out = std::fopen((ps_.output_dir + "nonedge_overlaps.txt").c_str(), "ab");
-    if (!out) die("Unable to open nonedge_overlaps.txt");
-    for (const std::string& b : part) if (!b.empty()) std::fwrite(b.data(), 1, b.size(), out);
-    std::fclose(out);
+    writer.join();
+    if (write_failed) die("Unable to open nonedge_overlaps.txt");
     t_write_s += wall_s() - t3;
     return true;
 }
