@@ -22,7 +22,7 @@ EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_runs_small", "hc_score_batch_runs6_small", "hc_score_batch_short_small", "hc_edge_extra_pos", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
-    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_warm_up", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3",
+    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_warm_up", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3", "hc_fno1_small", "hc_fno3_small",
     "hc_store_create_fastq", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
 ]
 
@@ -94,6 +94,10 @@ def lib() -> ctypes.CDLL:
         L.hc_fno1.argtypes = [vp, vp, u64, vp, u64, ctypes.POINTER(u64), i32]
         L.hc_fno3.restype = i32
         L.hc_fno3.argtypes = [u64, vp, vp, vp, u64, vp, i32, vp, u64, ctypes.POINTER(u64), i32]
+        L.hc_fno1_small.restype = i32
+        L.hc_fno1_small.argtypes = L.hc_fno1.argtypes
+        L.hc_fno3_small.restype = i32
+        L.hc_fno3_small.argtypes = L.hc_fno3.argtypes
         L.hc_dedup_edges.restype = i32
         L.hc_dedup_edges.argtypes = [vp, u64, i32, vp, vp, u64, vp, i32]
         L.hc_idmap_create.restype = vp
@@ -332,37 +336,59 @@ class _FnoInputC(ctypes.Structure):     # hc_fno_input
                 ("resolve_orientations", ctypes.c_uint8), ("no_inclusions", ctypes.c_uint8)]
 
 
-def fno1(fi: "F.FnoInput", device: int = 0) -> np.ndarray:
-    """hc_fno1: next-iteration overlaps derived on the GPU, in processing order (formats.FNO_OVERLAP)."""
+FNO_OVERLAP_SMALL = np.dtype([("id1", "<u4"), ("id2", "<u4"), ("pos1_perc", "<u4"), ("pos2_perc2", "<u4"), ("len1_flags", "<u4"),
+                              ("len2", "<u4")])     # hc_fno_overlap_small, 24 bytes
+
+
+def fno_small_to_overlaps(r: np.ndarray) -> np.ndarray:
+    """hc_fno_overlap_small records -> formats.FNO_OVERLAP (what hc_fno1 / hc_fno3 return)."""
+    o = np.zeros(len(r), dtype=F.FNO_OVERLAP)
+    fl = r["len1_flags"] >> 24
+    o["id1"], o["id2"] = r["id1"], r["id2"]
+    o["pos1"], o["perc"] = r["pos1_perc"] & 0xffffff, r["pos1_perc"] >> 24
+    o["pos2"], o["perc2"] = r["pos2_perc2"] & 0xffffff, r["pos2_perc2"] >> 24
+    o["len1"], o["len2"] = r["len1_flags"] & 0xffffff, r["len2"] & 0xffffff
+    o["ord"] = np.where((fl & 3) == 1, ord("1"), np.where((fl & 3) == 2, ord("2"), ord("-")))
+    o["ori1"] = np.where(fl & 4, ord("+"), ord("-"))
+    o["ori2"] = np.where(fl & 8, ord("+"), ord("-"))
+    o["type1"] = np.where(fl & 16, ord("p"), ord("s"))
+    o["type2"] = np.where(fl & 32, ord("p"), ord("s"))
+    return o
+
+
+def fno1(fi: "F.FnoInput", device: int = 0, small: bool = False) -> np.ndarray:
+    """hc_fno1 (small: hc_fno1_small, decoded): next-iteration overlaps derived on the GPU, in processing order
+    (formats.FNO_OVERLAP)."""
     keep = [np.ascontiguousarray(a) for a in (fi.visited, fi.label, fi.vertex_read, fi.sr_off, fi.sr_idx, fi.sr_sub, fi.superread)]
     st = _FnoInputC(len(fi.visited), keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
                     keep[4].ctypes.data, keep[5].ctypes.data, len(fi.superread), keep[6].ctypes.data, fi.resolve_orientations,
                     fi.no_inclusions)
     edges = np.ascontiguousarray(fi.edges)
     cap = max(2 * len(edges), 1024)
+    fn = lib().hc_fno1_small if small else lib().hc_fno1
     while True:
-        out = np.zeros(cap, dtype=F.FNO_OVERLAP)
+        out = np.zeros(cap, dtype=FNO_OVERLAP_SMALL if small else F.FNO_OVERLAP)
         n = ctypes.c_uint64(0)
-        rc = lib().hc_fno1(ctypes.byref(st), edges.ctypes.data if len(edges) else None, len(edges), out.ctypes.data, cap,
-                           ctypes.byref(n), device)
+        rc = fn(ctypes.byref(st), edges.ctypes.data if len(edges) else None, len(edges), out.ctypes.data, cap, ctypes.byref(n), device)
         if rc == 0:
-            return out[: n.value]
+            return fno_small_to_overlaps(out[: n.value]) if small else out[: n.value]
         if rc != -5:
             raise HcError(rc, last_error())
         cap = int(n.value)
 
 
-def fno3(fi: "F.Fno3Input", device: int = 0) -> np.ndarray:
-    """hc_fno3: overlaps between new reads sharing an original read, in discovery order."""
+def fno3(fi: "F.Fno3Input", device: int = 0, small: bool = False) -> np.ndarray:
+    """hc_fno3 (small: hc_fno3_small, decoded): overlaps between new reads sharing an original read, in discovery order."""
     off, idx, pos, reads = (np.ascontiguousarray(a) for a in (fi.off, fi.sr_idx, fi.sr_pos, fi.reads))
     cap = 4096
+    fn = lib().hc_fno3_small if small else lib().hc_fno3
     while True:
-        out = np.zeros(cap, dtype=F.FNO_OVERLAP)
+        out = np.zeros(cap, dtype=FNO_OVERLAP_SMALL if small else F.FNO_OVERLAP)
         n = ctypes.c_uint64(0)
-        rc = lib().hc_fno3(len(off) - 1, off.ctypes.data, idx.ctypes.data, pos.ctypes.data, len(reads), reads.ctypes.data,
-                           fi.no_inclusions, out.ctypes.data, cap, ctypes.byref(n), device)
+        rc = fn(len(off) - 1, off.ctypes.data, idx.ctypes.data, pos.ctypes.data, len(reads), reads.ctypes.data,
+                fi.no_inclusions, out.ctypes.data, cap, ctypes.byref(n), device)
         if rc == 0:
-            return out[: n.value]
+            return fno_small_to_overlaps(out[: n.value]) if small else out[: n.value]
         if rc != -5:
             raise HcError(rc, last_error())
         cap = int(n.value)

@@ -57,9 +57,10 @@ bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-int host_threads() {
+int host_threads() {      // HC_STAGE_THREADS: host threads that copy between the caller's buffer and the pinned ring (default: up to 16)
+    static const int cap = (int)env_size("HC_STAGE_THREADS", 16);
     int t = omp_get_max_threads();
-    if (t > 8) t = 8;
+    if (t > cap) t = cap;
     return t < 1 ? 1 : t;
 }
 

@@ -27,6 +27,45 @@ void append_line(std::string& out, const hc_fno_overlap& o) {
     out.append(buf, (size_t)n);
 }
 
+// 24-byte device record -> the fields of an overlap line (include/hc_b200.h: hc_fno_overlap_small)
+hc_fno_overlap expand(const hc_fno_overlap_small& r) {
+    hc_fno_overlap o;
+    std::memset(&o, 0, sizeof(o));
+    const uint32_t fl = r.len1_flags >> 24;
+    o.id1 = r.id1; o.id2 = r.id2;
+    o.pos1 = (int32_t)(r.pos1_perc & 0xffffffu); o.perc = (int32_t)(r.pos1_perc >> 24);
+    o.pos2 = (int32_t)(r.pos2_perc2 & 0xffffffu); o.perc2 = (int32_t)(r.pos2_perc2 >> 24);
+    o.len1 = (int32_t)(r.len1_flags & 0xffffffu); o.len2 = (int32_t)(r.len2 & 0xffffffu);
+    o.ord = (uint8_t)HC_FNO_SMALL_ORD(fl); o.ori1 = (uint8_t)HC_FNO_SMALL_ORI1(fl); o.ori2 = (uint8_t)HC_FNO_SMALL_ORI2(fl);
+    o.type1 = (uint8_t)HC_FNO_SMALL_TYPE1(fl); o.type2 = (uint8_t)HC_FNO_SMALL_TYPE2(fl);
+    return o;
+}
+
+// Runs `small` (24-byte records, half the bytes off the device) and, if a value does not fit them, `big` (48-byte records).
+template <class Small, class Big>
+void run_fno(Small small, Big big, size_t guess, std::vector<hc_fno_overlap>& out, uint64_t& n_out, const char* what) {
+    std::vector<hc_fno_overlap_small> s(std::max<size_t>(guess, 1024));
+    int rc = small(s.data(), s.size(), &n_out);
+    if (rc == HC_ERR_CAPACITY) {
+        s.resize(n_out);
+        rc = small(s.data(), s.size(), &n_out);
+    }
+    if (rc == HC_OK) {
+        out.resize(n_out);
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < (long long)n_out; k++) out[k] = expand(s[k]);
+        return;
+    }
+    std::vector<hc_fno_overlap_small>().swap(s);
+    out.resize(std::max<size_t>(guess, 1024));
+    rc = big(out.data(), out.size(), &n_out);
+    if (rc == HC_ERR_CAPACITY) {
+        out.resize(n_out);
+        rc = big(out.data(), out.size(), &n_out);
+    }
+    if (rc != HC_OK) die(std::string(what) + ": " + hc_last_error());
+}
+
 hc_fno_edge to_fno_edge(const Edge& e) {
     hc_fno_edge f;
     std::memset(&f, 0, sizeof(f));
@@ -206,14 +245,12 @@ unsigned long SRBuilder::findNextOverlaps() {
     in.superread = superread.data();
     in.resolve_orientations = ps_.resolve_orientations ? 1 : 0;
     in.no_inclusions = no_inclusions ? 1 : 0;
-    std::vector<hc_fno_overlap> out(std::max<size_t>(stream.size(), 1024));
+    std::vector<hc_fno_overlap> out;
     uint64_t n_out = 0;
-    int rc = hc_fno1(&in, stream.data(), stream.size(), out.data(), out.size(), &n_out, ps_.first_device);
-    if (rc == HC_ERR_CAPACITY) {
-        out.resize(n_out);
-        rc = hc_fno1(&in, stream.data(), stream.size(), out.data(), out.size(), &n_out, ps_.first_device);
-    }
-    if (rc != HC_OK) die(std::string("hc_fno1: ") + hc_last_error());
+    const int dev = ps_.first_device;
+    run_fno([&](hc_fno_overlap_small* o, uint64_t cap, uint64_t* n) { return hc_fno1_small(&in, stream.data(), stream.size(), o, cap, n, dev); },
+            [&](hc_fno_overlap* o, uint64_t cap, uint64_t* n) { return hc_fno1(&in, stream.data(), stream.size(), o, cap, n, dev); },
+            stream.size(), out, n_out, "hc_fno1");
     n_device_overlaps = n_out;
     const double t2 = now_s();
     // ---- the reference's std::set<std::string>: sorted, unique lines (:918,:946-948)
@@ -286,16 +323,14 @@ void SRBuilder::findNextOverlaps3() {
     const double t1 = now_s();
     uint64_t attempts = 0;
     for (size_t o = 0; o + 1 < off.size(); o++) { const uint64_t c = off[o + 1] - off[o]; attempts += c * (c - 1) / 2; }
-    std::vector<hc_fno_overlap> out(std::max<uint64_t>(attempts, 1024));
+    std::vector<hc_fno_overlap> out;
     uint64_t n_out = 0;
-    int rc = hc_fno3(off.size() - 1, off.data(), sr_idx.data(), sr_pos.data(), reads.size(), reads.data(), no_inclusions ? 1 : 0,
-                     out.data(), out.size(), &n_out, ps_.first_device);
-    if (rc == HC_ERR_CAPACITY) {
-        out.resize(n_out);
-        rc = hc_fno3(off.size() - 1, off.data(), sr_idx.data(), sr_pos.data(), reads.size(), reads.data(), no_inclusions ? 1 : 0,
-                     out.data(), out.size(), &n_out, ps_.first_device);
-    }
-    if (rc != HC_OK) die(std::string("hc_fno3: ") + hc_last_error());
+    const int dev = ps_.first_device, noinc = no_inclusions ? 1 : 0;
+    run_fno([&](hc_fno_overlap_small* o, uint64_t cap, uint64_t* n) {
+                return hc_fno3_small(off.size() - 1, off.data(), sr_idx.data(), sr_pos.data(), reads.size(), reads.data(), noinc, o, cap, n, dev); },
+            [&](hc_fno_overlap* o, uint64_t cap, uint64_t* n) {
+                return hc_fno3(off.size() - 1, off.data(), sr_idx.data(), sr_pos.data(), reads.size(), reads.data(), noinc, o, cap, n, dev); },
+            (size_t)attempts, out, n_out, "hc_fno3");
     n_stream_edges = attempts;
     n_device_overlaps = n_out;
     const double t2 = now_s();

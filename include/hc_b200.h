@@ -391,6 +391,22 @@ typedef struct {
 int hc_fno1(const hc_fno_input* in, const hc_fno_edge* edges, uint64_t n_edges,
             hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out, int device);
 
+/* The same derivation with 24-byte result records (half the device->host bytes of hc_fno_overlap; the caller formats the
+ * line from them): ids below 2^32, positions and lengths below 2^24, percentages below 256.  Returns HC_ERR_ARG (and
+ * hc_last_error() says so) when a value of the result does not fit -- hc_fno1 / hc_fno3 take any input.
+ *   pos1_perc  = pos1 | perc  << 24      pos2_perc2 = pos2 | perc2 << 24
+ *   len1_flags = len1 | flags << 24      flags: bits 0-1 ord (0 '-', 1 '1', 2 '2'), bit 2 ori1 == '+', bit 3 ori2 == '+',
+ *   len2                                        bit 4 type1 == 'p', bit 5 type2 == 'p'                                  */
+typedef struct { uint32_t id1, id2, pos1_perc, pos2_perc2, len1_flags, len2; } hc_fno_overlap_small;   /* 24 bytes */
+#define HC_FNO_SMALL_ORD(f)   (((f) & 3u) == 1u ? '1' : (((f) & 3u) == 2u ? '2' : '-'))
+#define HC_FNO_SMALL_ORI1(f)  (((f) & 4u) ? '+' : '-')
+#define HC_FNO_SMALL_ORI2(f)  (((f) & 8u) ? '+' : '-')
+#define HC_FNO_SMALL_TYPE1(f) (((f) & 16u) ? 'p' : 's')
+#define HC_FNO_SMALL_TYPE2(f) (((f) & 32u) ? 'p' : 's')
+
+int hc_fno1_small(const hc_fno_input* in, const hc_fno_edge* edges, uint64_t n_edges,
+                  hc_fno_overlap_small* out, uint64_t out_cap, uint64_t* n_out, int device);
+
 /* FindNextOverlaps3: SRBuilder::findNextOverlaps3 / nodeDictApproach / deduceOverlap,
  * src/FindNextOverlaps3.cpp:20-406.  Two new reads that share an ORIGINAL read overlap; the overlap
  * is deduced from the position of that original read inside both (OriginalIndex::index1/2,
@@ -403,6 +419,9 @@ typedef struct { int32_t index1, index2; } hc_fno3_pos;
 int hc_fno3(uint64_t n_originals, const uint64_t* off /* [n_originals+1] */, const uint32_t* sr_idx, const hc_fno3_pos* sr_pos,
             uint64_t n_reads, const hc_fno_read* reads /* super-reads and trivial reads */, int no_inclusions,
             hc_fno_overlap* out, uint64_t out_cap, uint64_t* n_out, int device);
+int hc_fno3_small(uint64_t n_originals, const uint64_t* off, const uint32_t* sr_idx, const hc_fno3_pos* sr_pos,
+                  uint64_t n_reads, const hc_fno_read* reads, int no_inclusions,
+                  hc_fno_overlap_small* out, uint64_t out_cap, uint64_t* n_out, int device);
 
 /* ------------------------------------------------------------------------------------------
  * Duplicate-edge resolution of the graph insert (first "next" row):
