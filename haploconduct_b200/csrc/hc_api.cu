@@ -86,12 +86,6 @@ struct DevCtx {
     uint64_t acc_e_cap = 0, acc_n_cap = 0;
     hc_edge* d_acc_edges = nullptr;
     uint64_t* d_acc_nonedge = nullptr;
-    // pageable caller buffers: the records of a pipeline step are copied into one of these pinned slots by all host
-    // threads and go to the device from there (a cudaMemcpyAsync from pageable memory is staged by the driver, on the
-    // calling thread, at a fraction of the link's speed)
-    static const int kStageSlots = 5;
-    size_t stage_cap = 0;
-    char* h_stage[kStageSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t acc_b_cap = 0;                // small outputs: one bit per candidate of the shard (32-bit words)
     uint32_t* d_acc_bits = nullptr;
     unsigned long long* d_run = nullptr;   // {edges, non-edges} emitted so far in this call
@@ -142,7 +136,6 @@ void free_ctx(DevCtx& d) {
     cudaFree(d.d_acc_edges); cudaFree(d.d_acc_nonedge); cudaFree(d.d_acc_bits); cudaFree(d.d_run); cudaFree(d.d_counts);
     cudaFree(d.d_whole); cudaFree(d.d_runs_all);
     if (d.h_runs_all) cudaFreeHost(d.h_runs_all);
-    for (int k = 0; k < DevCtx::kStageSlots; k++) if (d.h_stage[k]) cudaFreeHost(d.h_stage[k]);
     for (cudaEvent_t e : d.ev_step) cudaEventDestroy(e);
     if (d.h_cnt) cudaFreeHost(d.h_cnt);
     for (int k = 0; k < 6; k++) if (d.ev[k]) cudaEventDestroy(d.ev[k]);
@@ -956,23 +949,6 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         if (cudaPointerGetAttributes(&at, cand) != cudaSuccess) { cudaGetLastError(); pageable = true; }
         else pageable = at.type == cudaMemoryTypeUnregistered;
     }
-    if (pageable) {
-        for (int g = 0; g < G; g++) {
-            if (!whole[g]) continue;
-            DevCtx& d = s->devs[g];
-            size_t need = 0;
-            for (size_t k = 0; k + 1 < cs[g].size(); k++) need = std::max<size_t>(need, (cs[g][k + 1] - cs[g][k]) * rec);
-            if (need > d.stage_cap) {
-                CU(cudaSetDevice(d.device));
-                for (int q = 0; q < DevCtx::kStageSlots; q++) {
-                    if (d.h_stage[q]) { cudaFreeHost(d.h_stage[q]); d.h_stage[q] = nullptr; }
-                }
-                d.stage_cap = 0;
-                for (int q = 0; q < DevCtx::kStageSlots; q++) CU(cudaMallocHost(&d.h_stage[q], need));
-                d.stage_cap = need;
-            }
-        }
-    }
     // ---- whole-shard mode: the copy in of step k (and its run arrays) is queued a few steps ahead of its kernels
     std::vector<std::vector<uint64_t>> run_off(G);    // per issued step: offset of its [anchors][starts] in d_runs_all (words), n_runs
     std::vector<uint64_t> run_words(G, 0);
@@ -1014,16 +990,9 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
             CU(cudaMemcpyAsync(d.d_runs_all + o, h, (2 * nr + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, d.s_copy));
         }
         const char* src = (const char*)cand + c0 * rec;
-        if (pageable) {   // slot k % kStageSlots: its previous user, step k - kStageSlots, has left it (copy-ahead is smaller than the ring)
-            char* slot = d.h_stage[k % DevCtx::kStageSlots];
-            if (k >= (size_t)DevCtx::kStageSlots) CU(cudaEventSynchronize(d.ev_step[k - DevCtx::kStageSlots]));
-            const size_t bytes = cm * rec, piece = (size_t)1 << 20;
-            const long long np = (long long)((bytes + piece - 1) / piece);
-#pragma omp parallel for schedule(static)
-            for (long long q = 0; q < np; q++) memcpy(slot + (size_t)q * piece, src + (size_t)q * piece, std::min(piece, bytes - (size_t)q * piece));
-            src = slot;
-        }
-        CU(cudaMemcpyAsync(d.d_whole + (c0 - lo[g]) * rec, src, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
+        // pageable records (a std::vector, a numpy array) go through the pinned ring of hc_stage.cu, copied by several host threads
+        if (pageable) CU(hc_copy_h2d_on(d.d_whole + (c0 - lo[g]) * rec, src, cm * rec, d.s_copy));
+        else CU(cudaMemcpyAsync(d.d_whole + (c0 - lo[g]) * rec, src, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
         CU(cudaEventRecord(d.ev_step[k], d.s_copy));
         return HC_OK;
     };
@@ -1044,17 +1013,17 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
         dev_n[g] += h[HC_CNT_NONEDGES];
         if (per_cand) {
             CU(cudaStreamWaitEvent(d.s_out, d.ev_done[slot], 0));
-            CU(cudaMemcpyAsync(per_cand + c0, d.d_per_cand[slot], cm * sizeof(hc_result), cudaMemcpyDeviceToHost, d.s_out));
+            CU(hc_copy_d2h_on(per_cand + c0, d.d_per_cand[slot], cm * sizeof(hc_result), d.s_out, nullptr));
         }
         if (G == 1) {   // offsets in the caller's arrays are known: stream this chunk's results out now
             const uint64_t e1 = std::min<uint64_t>(dev_e[g], d.acc_e_cap), n1 = std::min<uint64_t>(dev_n[g], d.acc_n_cap);
             CU(cudaStreamWaitEvent(d.s_out, d.ev_done[slot], 0));
             if (e1 > out_e[g] && e1 <= edges_cap)
-                CU(cudaMemcpyAsync(edges_b + out_e[g] * erec, reinterpret_cast<char*>(d.d_acc_edges) + out_e[g] * erec, (e1 - out_e[g]) * erec, cudaMemcpyDeviceToHost, d.s_out));
+                CU(hc_copy_d2h_on(edges_b + out_e[g] * erec, reinterpret_cast<char*>(d.d_acc_edges) + out_e[g] * erec, (e1 - out_e[g]) * erec, d.s_out, nullptr));
             if (!small_out && n1 > out_n[g] && n1 <= nonedge_cap)
-                CU(cudaMemcpyAsync(nonedge_idx + out_n[g], d.d_acc_nonedge + out_n[g], (n1 - out_n[g]) * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.s_out));
+                CU(hc_copy_d2h_on(nonedge_idx + out_n[g], d.d_acc_nonedge + out_n[g], (n1 - out_n[g]) * sizeof(uint64_t), d.s_out, nullptr));
             if (small_out && cm)     // this chunk's words of the bit map (chunks start at multiples of 64)
-                CU(cudaMemcpyAsync(bits_out + c0 / 32, d.d_acc_bits + (c0 - lo[g]) / 32, ((cm + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.s_out));
+                CU(hc_copy_d2h_on(bits_out + c0 / 32, d.d_acc_bits + (c0 - lo[g]) / 32, ((cm + 31) / 32) * sizeof(uint32_t), d.s_out, nullptr));
             out_e[g] = std::max(out_e[g], e1);
             out_n[g] = std::max(out_n[g], n1);
         }
@@ -1087,7 +1056,8 @@ static int score_host(hc_store* s, const hc_params* p, const void* cand, int com
                 }
                 CU(cudaStreamWaitEvent(d.stream, d.ev_step[k], 0));
             } else {
-            CU(cudaMemcpyAsync(d.d_cand[slot], (const char*)cand + c0 * rec, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
+            if (pageable) CU(hc_copy_h2d_on(d.d_cand[slot], (const char*)cand + c0 * rec, cm * rec, d.s_copy));
+            else CU(cudaMemcpyAsync(d.d_cand[slot], (const char*)cand + c0 * rec, cm * rec, cudaMemcpyHostToDevice, d.s_copy));
             if (runs) {   // the runs that overlap [c0, c0 + cm): anchors as they are, starts clipped and made relative
                 const uint64_t* st = runs->start;
                 const uint64_t r0 = (uint64_t)(std::upper_bound(st, st + runs->n_runs + 1, c0) - st) - 1;

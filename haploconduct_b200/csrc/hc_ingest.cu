@@ -45,6 +45,7 @@ static cudaError_t ws_get(hc_idmap* m, int k, size_t bytes, void** out) {
 }
 
 #include "hc_text.cuh"
+#include "hc_stage.h"
 #include "hc_scan.cuh"
 
 namespace {
@@ -493,12 +494,14 @@ static int ingest_pipelined(hc_idmap* m, const char* text, u64 n_bytes, const hc
     ICU(ws_get(m, 13, 2 * rec_cap * sizeof(hc_overlap_rec), (void**)&d_filt));
     if (cand_line) ICU(ws_get(m, 14, 2 * rec_cap * sizeof(u64), (void**)&d_cl));
     if (filtered_line) ICU(ws_get(m, 15, 2 * rec_cap * sizeof(u64), (void**)&d_fl));
-    ICU(cudaMemcpyAsync(d_text, text, cut[1] - cut[0], cudaMemcpyHostToDevice, m->s_copy));
+    // pageable text / result buffers (a file read into memory, a std::vector) go through the pinned ring of hc_stage.cu,
+    // copied by several host threads; pinned ones are handed to the copy engine as they are
+    ICU(hc_copy_h2d_on(d_text, text, cut[1] - cut[0], m->s_copy));
     ICU(cudaEventRecord(m->ev_in[0], m->s_copy));
     for (size_t i = 0; i < n_pieces && lines < p->max_overlaps; i++) {
         const int b = (int)(i & 1);
         if (i + 1 < n_pieces) {   // buffer (i+1)&1 was read by piece i-1, whose kernels have completed (ingest_device returns synchronised)
-            ICU(cudaMemcpyAsync(d_text + (size_t)(b ^ 1) * tbytes, text + cut[i + 1], cut[i + 2] - cut[i + 1], cudaMemcpyHostToDevice, m->s_copy));
+            ICU(hc_copy_h2d_on(d_text + (size_t)(b ^ 1) * tbytes, text + cut[i + 1], cut[i + 2] - cut[i + 1], m->s_copy));
             ICU(cudaEventRecord(m->ev_in[b ^ 1], m->s_copy));
         }
         ICU(cudaStreamWaitEvent(m->s_main, m->ev_in[b], 0));
@@ -519,12 +522,12 @@ static int ingest_pipelined(hc_idmap* m, const char* text, u64 n_bytes, const hc
         }
         if (!overflow) {
             if (st.n_scored) {
-                ICU(cudaMemcpyAsync(cand + ns, d_cand + (size_t)b * rec_cap, st.n_scored * sizeof(hc_candidate), cudaMemcpyDeviceToHost, m->s_out));
-                if (cand_line) ICU(cudaMemcpyAsync(cand_line + ns, d_cl + (size_t)b * rec_cap, st.n_scored * sizeof(u64), cudaMemcpyDeviceToHost, m->s_out));
+                ICU(hc_copy_d2h_on(cand + ns, d_cand + (size_t)b * rec_cap, st.n_scored * sizeof(hc_candidate), m->s_out, nullptr));
+                if (cand_line) ICU(hc_copy_d2h_on(cand_line + ns, d_cl + (size_t)b * rec_cap, st.n_scored * sizeof(u64), m->s_out, nullptr));
             }
             if (st.n_filtered) {
-                ICU(cudaMemcpyAsync(filtered + nf, d_filt + (size_t)b * rec_cap, st.n_filtered * sizeof(hc_overlap_rec), cudaMemcpyDeviceToHost, m->s_out));
-                if (filtered_line) ICU(cudaMemcpyAsync(filtered_line + nf, d_fl + (size_t)b * rec_cap, st.n_filtered * sizeof(u64), cudaMemcpyDeviceToHost, m->s_out));
+                ICU(hc_copy_d2h_on(filtered + nf, d_filt + (size_t)b * rec_cap, st.n_filtered * sizeof(hc_overlap_rec), m->s_out, nullptr));
+                if (filtered_line) ICU(hc_copy_d2h_on(filtered_line + nf, d_fl + (size_t)b * rec_cap, st.n_filtered * sizeof(u64), m->s_out, nullptr));
             }
         }
         ICU(cudaEventRecord(m->ev_out[b], m->s_out));
@@ -564,18 +567,18 @@ extern "C" int hc_ingest_overlaps(const hc_idmap* cm, const char* text, uint64_t
             return ingest_pipelined(m, text, n_bytes, p, cand, cand_line, cand_cap, filtered, filtered_line, filtered_cap, stats, piece);
     }
     ICU(ws_get(m, 11, n_bytes + 16, (void**)&d_text));
-    ICU(cudaMemcpy(d_text, text, n_bytes, cudaMemcpyHostToDevice));
+    ICU(hc_copy_h2d(d_text, text, n_bytes));
     if (cand_cap) { ICU(ws_get(m, 12, cand_cap * sizeof(hc_candidate), (void**)&d_cand)); if (cand_line) ICU(ws_get(m, 14, cand_cap * sizeof(u64), (void**)&d_cl)); }
     if (filtered_cap) { ICU(ws_get(m, 13, filtered_cap * sizeof(hc_overlap_rec), (void**)&d_filt)); if (filtered_line) ICU(ws_get(m, 15, filtered_cap * sizeof(u64), (void**)&d_fl)); }
     rc = ingest_device(m, d_text, n_bytes, p, d_cand, d_cl, cand_cap, d_filt, d_fl, filtered_cap, stats, m->s_main);
     if (rc != HC_OK) goto done;
     if (stats->n_scored) {
-        ICU(cudaMemcpy(cand, d_cand, stats->n_scored * sizeof(hc_candidate), cudaMemcpyDeviceToHost));
-        if (cand_line) ICU(cudaMemcpy(cand_line, d_cl, stats->n_scored * sizeof(u64), cudaMemcpyDeviceToHost));
+        ICU(hc_copy_d2h(cand, d_cand, stats->n_scored * sizeof(hc_candidate)));
+        if (cand_line) ICU(hc_copy_d2h(cand_line, d_cl, stats->n_scored * sizeof(u64)));
     }
     if (stats->n_filtered) {
-        ICU(cudaMemcpy(filtered, d_filt, stats->n_filtered * sizeof(hc_overlap_rec), cudaMemcpyDeviceToHost));
-        if (filtered_line) ICU(cudaMemcpy(filtered_line, d_fl, stats->n_filtered * sizeof(u64), cudaMemcpyDeviceToHost));
+        ICU(hc_copy_d2h(filtered, d_filt, stats->n_filtered * sizeof(hc_overlap_rec)));
+        if (filtered_line) ICU(hc_copy_d2h(filtered_line, d_fl, stats->n_filtered * sizeof(u64)));
     }
 done:
     return rc;

@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <stdio.h>
+#include <time.h>
 
 namespace {
 
@@ -29,9 +31,25 @@ struct Ring {
     cudaEvent_t ev[kRing];
     cudaStream_t stream = nullptr;         // blocking stream: ordered with the legacy default stream
     bool ok = false;
+    bool used[kRing] = {false, false, false, false};   // ev[b] has been recorded at least once
+    int next = 0;                          // the buffers are handed out round robin, whichever call comes next
 };
 
 std::mutex g_mu;            // one staged copy at a time per process (the ring is shared)
+
+// HC_STAGE_TIMING=1: where the staged copies spend their time (host memcpy / waiting for a ring buffer's DMA), on stderr at exit
+struct StageTimes {
+    bool on = getenv("HC_STAGE_TIMING") != nullptr;
+    double copy_s[2] = {0, 0}, wait_s[2] = {0, 0}, bytes[2] = {0, 0};
+    long calls[2] = {0, 0};
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+    ~StageTimes() {
+        if (!on) return;
+        for (int d = 0; d < 2; d++)
+            fprintf(stderr, "[hc_stage] %s: %ld calls, %.1f MB, host memcpy %.1f ms, waiting for DMAs %.1f ms\n", d ? "device->host" : "host->device",
+                    calls[d], bytes[d] / 1e6, copy_s[d] * 1e3, wait_s[d] * 1e3);
+    }
+} g_times;
 Ring g_ring[16];            // per device
 
 cudaError_t ring_for(int dev, Ring** out) {
@@ -88,12 +106,14 @@ cudaError_t hc_copy_h2d(void* dst, const void* src, size_t bytes) {
     const int T = host_threads();
     size_t done = 0;
     for (int i = 0; done < bytes; i++) {
-        const int b = i % kRing;
+        const int b = r->next;
+        r->next = (r->next + 1) % kRing;
         const size_t n = bytes - done < kChunk ? bytes - done : kChunk;
-        if (i >= kRing && (e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;   // the DMA that read this buffer
+        if (r->used[b] && (e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;   // the DMA that read this buffer
         par_memcpy(r->buf[b], static_cast<const char*>(src) + done, n, T);
         if ((e = cudaMemcpyAsync(static_cast<char*>(dst) + done, r->buf[b], n, cudaMemcpyHostToDevice, r->stream)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(r->ev[b], r->stream)) != cudaSuccess) return e;
+        r->used[b] = true;
         done += n;
     }
     return cudaStreamSynchronize(r->stream);
@@ -111,20 +131,94 @@ cudaError_t hc_copy_d2h(void* dst, const void* src, size_t bytes) {
     const int T = host_threads();
     const size_t nchunks = (bytes + kChunk - 1) / kChunk;
     size_t issued = 0, drained = 0;
+    int slot[kRing];
     while (drained < nchunks) {
         while (issued < nchunks && issued < drained + kRing) {   // keep the ring full of DMAs
-            const int b = (int)(issued % kRing);
+            const int b = r->next;
+            r->next = (r->next + 1) % kRing;
+            slot[issued % kRing] = b;
             const size_t o = issued * kChunk, n = bytes - o < kChunk ? bytes - o : kChunk;
+            if (r->used[b] && (e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;   // a DMA of an earlier call may still use it
             if ((e = cudaMemcpyAsync(r->buf[b], static_cast<const char*>(src) + o, n, cudaMemcpyDeviceToHost, r->stream)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(r->ev[b], r->stream)) != cudaSuccess) return e;
+            r->used[b] = true;
             issued++;
         }
-        const int b = (int)(drained % kRing);
+        const int b = slot[drained % kRing];
         const size_t o = drained * kChunk, n = bytes - o < kChunk ? bytes - o : kChunk;
         if ((e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;
         par_memcpy(static_cast<char*>(dst) + o, r->buf[b], n, T);
         drained++;
     }
+    return cudaSuccess;
+}
+
+cudaError_t hc_copy_h2d_on(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < (256u << 10) || is_pinned(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ring* r;
+    if ((e = ring_for(dev, &r)) != cudaSuccess) return e;
+    const int T = host_threads();
+    // a buffer is free again when the DMA that read it -- on whichever stream it was issued last -- has completed: the
+    // events are recorded on that stream, so waiting on them is enough whatever stream comes next
+    size_t done = 0;
+    for (int i = 0; done < bytes; i++) {
+        const int b = r->next;
+        r->next = (r->next + 1) % kRing;
+        const size_t n = bytes - done < kChunk ? bytes - done : kChunk;
+        const double ta = g_times.on ? StageTimes::now() : 0;
+        if (r->used[b] && (e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;
+        const double tb = g_times.on ? StageTimes::now() : 0;
+        par_memcpy(r->buf[b], static_cast<const char*>(src) + done, n, T);
+        if (g_times.on) { const double tc = StageTimes::now(); g_times.wait_s[0] += tb - ta; g_times.copy_s[0] += tc - tb; g_times.bytes[0] += n; g_times.calls[0] += i == 0; }
+        if ((e = cudaMemcpyAsync(static_cast<char*>(dst) + done, r->buf[b], n, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(r->ev[b], st)) != cudaSuccess) return e;
+        r->used[b] = true;
+        done += n;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t hc_copy_d2h_on(void* dst, const void* src, size_t bytes, cudaStream_t st, bool* completed) {
+    if (completed) *completed = false;
+    if (bytes == 0) return cudaSuccess;
+    if (bytes < (256u << 10) || is_pinned(dst)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ring* r;
+    if ((e = ring_for(dev, &r)) != cudaSuccess) return e;
+    const int T = host_threads();
+    const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+    size_t issued = 0, drained = 0;
+    int slot[kRing];
+    while (drained < nchunks) {
+        while (issued < nchunks && issued < drained + kRing) {   // keep the ring full of DMAs
+            const int b = r->next;
+            r->next = (r->next + 1) % kRing;
+            slot[issued % kRing] = b;
+            const size_t o = issued * kChunk, n = bytes - o < kChunk ? bytes - o : kChunk;
+            if (r->used[b] && (e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;   // a host->device DMA may still read it
+            if ((e = cudaMemcpyAsync(r->buf[b], static_cast<const char*>(src) + o, n, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(r->ev[b], st)) != cudaSuccess) return e;
+            r->used[b] = true;
+            issued++;
+        }
+        const int b = slot[drained % kRing];
+        const size_t o = drained * kChunk, n = bytes - o < kChunk ? bytes - o : kChunk;
+        const double ta = g_times.on ? StageTimes::now() : 0;
+        if ((e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;
+        const double tb = g_times.on ? StageTimes::now() : 0;
+        par_memcpy(static_cast<char*>(dst) + o, r->buf[b], n, T);
+        if (g_times.on) { const double tc = StageTimes::now(); g_times.wait_s[1] += tb - ta; g_times.copy_s[1] += tc - tb; g_times.bytes[1] += n; g_times.calls[1] += drained == 0; }
+        drained++;
+    }
+    if (completed) *completed = true;
     return cudaSuccess;
 }
 

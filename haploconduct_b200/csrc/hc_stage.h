@@ -12,6 +12,15 @@
 cudaError_t hc_copy_h2d(void* dst_dev, const void* src_host, size_t bytes);
 cudaError_t hc_copy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 
+// The same through the ring, but with the device side of the copy on a stream of the caller's (the pipelines of
+// hc_ingest_overlaps and hc_score_batch*): pinned / registered host memory is handed to cudaMemcpyAsync as it is.
+//   hc_copy_h2d_on returns when the last piece has been handed to the copy engine: `src` may be reused, the copies
+//                  complete in stream order on `st` (the caller orders its kernels behind them with an event);
+//   hc_copy_d2h_on returns when `dst` holds the data if `dst` is pageable; for pinned memory it only enqueues
+//                  (cudaMemcpyAsync semantics) -- *completed says which.
+cudaError_t hc_copy_h2d_on(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
+cudaError_t hc_copy_d2h_on(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st, bool* completed);
+
 // Device scratch from the device's default memory pool, ordered on the legacy default stream (the stream the
 // host-buffer entry points launch on); freed memory stays in the pool (up to 16 GB), so that a call does not pay
 // cudaMalloc / cudaFree for each of its dozen temporaries.

@@ -13,6 +13,10 @@
 #include <iostream>
 #include <sstream>
 #include <thread>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace hcb {
 
@@ -124,22 +128,55 @@ void FastqStorage::read_pairs(const std::string& p1, const std::string& p2, unsi
     }
 }
 
-static std::string slurp_file(const std::string& path) {
-    if (path.empty() || path == "None") return std::string();
-    FILE* f = std::fopen(path.c_str(), "rb");
-    if (!f) die("Unable to open fastq file " + path);                             // src/FastqStorage.cpp:54-56
-    std::string s;
-    std::fseek(f, 0, SEEK_END);
-    const long size = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    if (size > 0) {
-        s.resize((size_t)size);
-        const size_t got = std::fread(&s[0], 1, (size_t)size, f);
-        s.resize(got);
+FileBuf& FileBuf::operator=(FileBuf&& o) noexcept {
+    if (this != &o) {
+        if (data) munmap(data, mapped);
+        data = o.data; size = o.size; mapped = o.mapped;
+        o.data = nullptr; o.size = o.mapped = 0;
     }
-    std::fclose(f);
-    return s;
+    return *this;
 }
+FileBuf::~FileBuf() { if (data) munmap(data, mapped); }
+
+bool read_whole_file(const std::string& path, FileBuf& out, int threads) {
+    out = FileBuf();
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) { close(fd); return true; }      // empty (or not a regular file): no bytes
+    const size_t size = (size_t)st.st_size, mapped = (size + (2u << 20)) & ~((size_t)(2u << 20) - 1);
+    void* p = mmap(nullptr, mapped, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) { close(fd); die("out of memory reading " + path); }
+    madvise(p, mapped, MADV_HUGEPAGE);
+    out.data = static_cast<char*>(p); out.mapped = mapped;
+    const size_t blk = 8u << 20;
+    const long long nb = (long long)((size + blk - 1) / blk);
+    int T = threads > 0 ? threads : omp_get_max_threads();
+    if (T > 16) T = 16;
+    size_t got_min = size;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T) reduction(min : got_min)
+    for (long long b = 0; b < nb; b++) {
+        size_t o = (size_t)b * blk;
+        const size_t end = std::min(size, o + blk);
+        while (o < end) {
+            const ssize_t r = pread(fd, out.data + o, end - o, (off_t)o);
+            if (r <= 0) { got_min = std::min(got_min, o); break; }               // shorter than fstat said: keep what is there
+            o += (size_t)r;
+        }
+    }
+    close(fd);
+    out.size = got_min;
+    return true;
+}
+
+static FileBuf slurp_buf(const std::string& path) {
+    FileBuf b;
+    if (path.empty() || path == "None") return b;
+    if (!read_whole_file(path, b)) die("Unable to open fastq file " + path);      // src/FastqStorage.cpp:54-56
+    return b;
+}
+
+std::function<void()> FastqStorage::device_ready_hook;
 
 FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
     if (ps.gpu_fastq) {
@@ -147,10 +184,13 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         // (creating the CUDA context from a second thread while this one reads the files was measured and is slower: the
         // context creation and the page faults of the file buffers contend for the address-space lock)
         const double tf0 = wall_s();
-        const std::string s = slurp_file(ps.singles_file), p1 = slurp_file(ps.paired1_file), p2 = slurp_file(ps.paired2_file);
+        const FileBuf sb = slurp_buf(ps.singles_file), p1b = slurp_buf(ps.paired1_file), p2b = slurp_buf(ps.paired2_file);
+        struct View { const char* p; size_t n; const char* data() const { return p; } size_t size() const { return n; } };
+        const View s{sb.data, sb.size}, p1{p1b.data, p1b.size}, p2{p2b.data, p2b.size};
         const double tfr = wall_s();
         t_read_s = tfr - tf0;
         if (hc_warm_up(ps.first_device) != HC_OK) die(std::string("hc_warm_up: ") + hc_last_error());
+        if (device_ready_hook) device_ready_hook();      // e.g. start reading the overlaps file: from here on nothing maps memory at CUDA's pace
         const double tf1 = wall_s();
         t_cuda_init_s = tf1 - tfr;
         first_device_ = ps.first_device;
@@ -167,6 +207,7 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         m_readcount_paired = (unsigned int)(n - m_readcount_single);
         m_read_vec.resize(n);
         mate_len = lens;
+        read_ids = ids;
         for (uint64_t i = 0; i < n; i++) {
             m_read_vec[i].read_id = ids[i];
             m_read_vec[i].is_paired = i >= m_readcount_single;
@@ -191,6 +232,8 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         std::cout << "Pairs: " << m_readcount_paired << std::endl;
     }
     for (unsigned int i = 0; i < m_read_vec.size(); i++) m_ID_to_index.insert(std::make_pair(m_read_vec[i].read_id, i));
+    read_ids.resize(m_read_vec.size());
+    for (size_t i = 0; i < m_read_vec.size(); i++) read_ids[i] = m_read_vec[i].read_id;
     if (m_read_vec.empty()) return;
     // ---- device replica: concatenate, describe, hand to the C ABI
     std::vector<hc_read_desc> descs(m_read_vec.size());
@@ -326,11 +369,44 @@ node_id_t OverlapGraph::addVertex(read_id_t id) {
 
 void OverlapGraph::addEdge(const Edge& e) {
     adj_out[e.vertex1].push_back(e);
-    owner_[key(e.vertex1, e.vertex2, e.ori1 == e.ori2)] = e.vertex1;
+    if (!owner_stale_) owner_[key(e.vertex1, e.vertex2, e.ori1 == e.ori2)] = e.vertex1;
     edge_count_++;
 }
 
+void OverlapGraph::addEdges(const std::vector<Edge>& es, const unsigned char* keep) {
+    const size_t n = es.size(), V = adj_out.size();
+    if (n < 4096) { for (size_t k = 0; k < n; k++) if (!keep || keep[k]) addEdge(es[k]); return; }
+    // stable counting sort of the kept edges by vertex1 (input order inside a list = the order the reference appends in)
+    std::vector<uint32_t> off(V + 1, 0);
+    for (size_t k = 0; k < n; k++) if (!keep || keep[k]) off[es[k].vertex1 + 1]++;
+    for (size_t v = 0; v < V; v++) off[v + 1] += off[v];
+    const size_t kept = off[V];
+    std::vector<uint32_t> order(kept), cur(off.begin(), off.end() - 1);
+    for (size_t k = 0; k < n; k++) if (!keep || keep[k]) order[cur[es[k].vertex1]++] = (uint32_t)k;
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (long long v = 0; v < (long long)V; v++) {
+        const uint32_t a = off[v], b = off[v + 1];
+        if (a == b) continue;
+        std::vector<Edge>& lst = adj_out[(size_t)v];
+        lst.reserve(lst.size() + (b - a));
+        for (uint32_t j = a; j < b; j++) lst.push_back(es[order[j]]);
+    }
+    edge_count_ += (unsigned int)kept;
+    owner_stale_ = true;
+    owner_.clear();
+}
+
+void OverlapGraph::ensure_owner() const {
+    if (!owner_stale_) return;
+    owner_.clear();
+    owner_.reserve(edge_count_ * 2u);
+    for (const auto& lst : adj_out)
+        for (const Edge& e : lst) owner_[key(e.vertex1, e.vertex2, e.ori1 == e.ori2)] = e.vertex1;
+    owner_stale_ = false;
+}
+
 const Edge* OverlapGraph::getEdgeInfoWithOri(node_id_t v, node_id_t w, bool same_ori) const {
+    ensure_owner();
     auto it = owner_.find(key(v, w, same_ori));
     if (it == owner_.end()) return nullptr;
     const node_id_t from = it->second, to = from == v ? w : v;
@@ -345,6 +421,7 @@ double OverlapGraph::checkEdgeWithOri(node_id_t v, node_id_t w, bool same_ori) c
 }
 
 void OverlapGraph::removeEdgeWithOri(node_id_t v, node_id_t w, bool same_ori) {
+    ensure_owner();
     std::vector<Edge>& lst = adj_out[v];
     for (size_t i = 0; i < lst.size(); i++) {
         if (lst[i].vertex2 == w && (lst[i].ori1 == lst[i].ori2) == same_ori) {
@@ -677,12 +754,25 @@ void EdgeCalculator::ingest_on_device(std::vector<Overlap>& batch, std::vector<O
 // share of reproduce it.
 namespace {
 
-inline void put_cand_line(std::string& b, const hc_candidate& c, read_id_t id1, read_id_t id2) {            // src/Overlap.h:234-237
-    put_u64(b, id1); b.push_back('\t'); put_u64(b, id2); b.push_back('\t'); put_u64(b, c.pos1); b.push_back('\t'); put_u64(b, c.pos2);
-    b.push_back('\t'); b.push_back((char)c.ord); b.push_back('\t'); b.push_back(c.ori1 ? '+' : '-'); b.push_back('\t');
-    b.push_back(c.ori2 ? '+' : '-'); b.push_back('\t');
-    put_u64(b, c.perc1); b.push_back('\t'); put_u64(b, c.perc2); b.push_back('\t'); put_u64(b, c.len1); b.push_back('\t'); put_u64(b, c.len2);
-    b.push_back('\t'); b.push_back((char)c.type1); b.push_back('\t'); b.push_back((char)c.type2); b.push_back('\n');
+// the same line through a raw pointer (no capacity check per character; the caller reserves HC_LINE_MAX bytes per line)
+#define HC_LINE_MAX 160
+inline char* put_u(char* p, unsigned long v) {
+    static const char d2[] = "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+    char tmp[24];
+    int k = 24;
+    while (v >= 100) { const unsigned long q = v / 100; const unsigned r = (unsigned)(v - q * 100); v = q; tmp[--k] = d2[2 * r + 1]; tmp[--k] = d2[2 * r]; }
+    if (v >= 10) { tmp[--k] = d2[2 * v + 1]; tmp[--k] = d2[2 * v]; }
+    else tmp[--k] = (char)('0' + v);
+    const int n = 24 - k;
+    memcpy(p, tmp + k, (size_t)n);
+    return p + n;
+}
+inline char* put_cand_line(char* p, const hc_candidate& c, read_id_t id1, read_id_t id2) {                  // src/Overlap.h:234-237
+    p = put_u(p, id1); *p++ = '\t'; p = put_u(p, id2); *p++ = '\t'; p = put_u(p, c.pos1); *p++ = '\t'; p = put_u(p, c.pos2);
+    *p++ = '\t'; *p++ = (char)c.ord; *p++ = '\t'; *p++ = c.ori1 ? '+' : '-'; *p++ = '\t'; *p++ = c.ori2 ? '+' : '-'; *p++ = '\t';
+    p = put_u(p, c.perc1); *p++ = '\t'; p = put_u(p, c.perc2); *p++ = '\t'; p = put_u(p, c.len1); *p++ = '\t'; p = put_u(p, c.len2);
+    *p++ = '\t'; *p++ = (char)c.type1; *p++ = '\t'; *p++ = (char)c.type2; *p++ = '\n';
+    return p;
 }
 
 inline void put_rec_line(std::string& b, const hc_overlap_rec& r) {
@@ -698,19 +788,28 @@ inline void put_rec_line(std::string& b, const hc_overlap_rec& r) {
 bool EdgeCalculator::construct_edges_arrays() {
     if (fastq_->max_read_len >= (1u << 14) || fastq_->m_read_vec.size() >= (1ull << 31)) return false;   // needs the 8-byte records
     const int T = std::max(1, omp_get_max_threads());
-    // ---- the file, in one read
+    // HC_MIRROR_TIMING=1: wall clock of every step of this function on stderr
+    const bool timing = getenv("HC_MIRROR_TIMING") != nullptr;
+    double t_mark = wall_s();
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        const double t = wall_s();
+        fprintf(stderr, "[construct_edges] %-34s %8.2f ms\n", what, (t - t_mark) * 1e3);
+        t_mark = t;
+    };
+    // ---- the file, in one read (several threads; or already read by the caller while the read store was built)
     const double t0 = wall_s();
-    FILE* f = std::fopen(ps_.overlaps_file.c_str(), "rb");
-    if (!f) { std::cerr << "Unable to open overlaps file"; std::exit(1); }
-    std::fseek(f, 0, SEEK_END);
-    const size_t size = (size_t)std::max(0l, std::ftell(f));
-    std::fseek(f, 0, SEEK_SET);
-    std::unique_ptr<char[]> text(new char[size + 1]);
-    const size_t got = size ? std::fread(text.get(), 1, size, f) : 0;
-    std::fclose(f);
+    FileBuf fb;
+    if (have_preloaded) { fb = std::move(preloaded_overlaps); have_preloaded = false; }
+    else if (!read_whole_file(ps_.overlaps_file, fb)) { std::cerr << "Unable to open overlaps file"; std::exit(1); }
+    struct { char* p; char* get() const { return p; } char operator[](long long i) const { return p[i]; } } text{fb.data};
+    const size_t got = fb.size;
+    const double t0r = wall_s();
     size_t lines = 1;
 #pragma omp parallel for schedule(static) reduction(+ : lines)
     for (long long i = 0; i < (long long)got; i++) lines += text[i] == '\n';
+    (void)t0r;
+    mark("file read + line count");
     // ---- parse + pre-filter + id lookup on the device
     std::unique_ptr<hc_candidate[]> cand(new hc_candidate[lines]);
     size_t filt_cap = std::max<size_t>(lines / 8, 4096);
@@ -732,6 +831,7 @@ bool EdgeCalculator::construct_edges_arrays() {
     parse_device_ms += st.device_ms;
     if (st.first_error_line != ~0ull) return false;      // the line-by-line path reproduces what the reference does up to that line
     const size_t n = st.n_scored;
+    mark("hc_ingest_overlaps");
     const double t1 = wall_s();
     t_ingest_s += t1 - t0;
     bool fits = true;
@@ -764,6 +864,7 @@ bool EdgeCalculator::construct_edges_arrays() {
 #pragma omp parallel for schedule(static)
     for (long long r = 0; r < (long long)start.size(); r++) anchor[r] = std::min(cand[start[r]].idx1, cand[start[r]].idx2);
     start.push_back(n);
+    mark("run-encoded records");
     // ---- scoring: small outputs
     const hc_params p = to_params(ps_);
     const size_t erec = ps_.exact_scores ? sizeof(hc_edge_small_exact) : sizeof(hc_edge_small);
@@ -786,37 +887,47 @@ bool EdgeCalculator::construct_edges_arrays() {
     }
     scored_candidates += n;
     device_ms += bst.total_ms;
+    mark("hc_score_batch_runs_small");
     const double t2 = wall_s();
     t_score_s += t2 - t1;
     // ---- nonedge_overlaps.txt: the scored non-edges (bit map) in file order, then the pre-filtered lines (:546-555, :654-660);
     // every thread formats a share of the words into its own buffer; the buffers are written in order by a thread of their own
     // while this one builds the edges (both only read the candidates)
     const size_t words = (n + 63) / 64;
-    std::vector<std::string> part(T + 1);
+    std::vector<std::unique_ptr<char[]>> part(T);
+    std::vector<size_t> part_len(T, 0);
+    std::string filt_lines;
+    const uint64_t* rid = fastq_->read_ids.data();       // 8 bytes per read instead of a walk over the Read objects
 #pragma omp parallel num_threads(T)
     {
         const int t = omp_get_thread_num();
         const size_t lo = words * (size_t)t / (size_t)T, hi = words * (size_t)(t + 1) / (size_t)T;
-        std::string& b = part[t];
+        size_t mine = 0;
+        for (size_t w = lo; w < hi; w++) mine += (size_t)__builtin_popcountll(bits[w]);
+        part[t].reset(new char[mine * HC_LINE_MAX + 16]);
+        char* p = part[t].get();
         for (size_t w = lo; w < hi; w++) {
             uint64_t m = bits[w];
             while (m) {
                 const size_t i = w * 64 + (size_t)__builtin_ctzll(m);
                 m &= m - 1;
                 const hc_candidate& c = cand[i];
-                put_cand_line(b, c, fastq_->m_read_vec[c.idx1].read_id, fastq_->m_read_vec[c.idx2].read_id);
+                p = put_cand_line(p, c, rid[c.idx1], rid[c.idx2]);
             }
         }
+        part_len[t] = (size_t)(p - part[t].get());
     }
-    for (uint64_t k = 0; k < st.n_filtered; k++) put_rec_line(part[T], filt[k]);
+    for (uint64_t k = 0; k < st.n_filtered; k++) put_rec_line(filt_lines, filt[k]);
     bool write_failed = false;
     const std::string nonedge_path = ps_.output_dir + "nonedge_overlaps.txt";
-    std::thread writer([&part, &write_failed, &nonedge_path]() {
+    std::thread writer([&part, &part_len, &filt_lines, &write_failed, &nonedge_path]() {
         FILE* out = std::fopen(nonedge_path.c_str(), "ab");
         if (!out) { write_failed = true; return; }
-        for (const std::string& b : part) if (!b.empty()) std::fwrite(b.data(), 1, b.size(), out);
+        for (size_t t = 0; t < part.size(); t++) if (part_len[t]) std::fwrite(part[t].get(), 1, part_len[t], out);
+        if (!filt_lines.empty()) std::fwrite(filt_lines.data(), 1, filt_lines.size(), out);
         std::fclose(out);
     });
+    mark("non-edge lines formatted");
     const double t2b = wall_s();
     t_write_s += t2b - t2;
     // ---- accepted edges: Edge fields from the candidate + the small record, every thread a share
@@ -863,6 +974,7 @@ bool EdgeCalculator::construct_edges_arrays() {
         if (e.pos1 == 0 && e.vertex1 > e.vertex2) e.swap_reads();                                              // :443-448
     }
     if (overflow) die("a window of 65536 or more positions: not representable in the small edge records");
+    mark("Edge objects");
     unsigned int doubles = 0;
     if (ps_.gpu_dedup && ne) {
         std::vector<hc_dedup_edge> de(ne);
@@ -880,7 +992,9 @@ bool EdgeCalculator::construct_edges_arrays() {
         rc = hc_dedup_edges(de.data(), de.size(), ps_.ignore_inclusions, win.data(), (uint8_t*)graph_->inclusions.data(),
                             graph_->inclusions.size(), counts, ps_.first_device);
         if (rc != HC_OK) die(std::string("hc_dedup_edges: ") + hc_last_error());
-        for (size_t k = 0; k < ne; k++) if (win[k]) graph_->addEdge(es[k]);
+        mark("hc_dedup_edges");
+        graph_->addEdges(es, win.data());
+        mark("addEdges");
         dup_count += (unsigned int)counts[0];
         inclusion_count += (unsigned int)counts[1];
     } else {
@@ -895,6 +1009,7 @@ bool EdgeCalculator::construct_edges_arrays() {
     }
     writer.join();
     if (write_failed) die("Unable to open nonedge_overlaps.txt");
+    mark("non-edge file written (join)");
     t_write_s += wall_s() - t3;
     return true;
 }

@@ -16,6 +16,7 @@
 #define HCB_HOST_H_
 
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -79,10 +80,16 @@ public:
     FastqStorage(const FastqStorage&) = delete;
     FastqStorage& operator=(const FastqStorage&) = delete;
 
+    // --gpu_fastq: called once the CUDA context exists (the page faults of a file being read by another thread and the
+    // context creation slow each other down -- both live on the address-space lock -- so a caller that wants to read
+    // its next input in the background starts here, not earlier)
+    static std::function<void()> device_ready_hook;
+
     std::vector<Read> m_read_vec;                     // singles first, then pairs (src/FastqStorage.h:88-97)
     std::map<read_id_t, unsigned int> m_ID_to_index;  // src/FastqStorage.h:54
     unsigned int m_readcount_single = 0, m_readcount_paired = 0;
     unsigned int max_read_len = 0;                    // longest mate (decides the candidate record size)
+    std::vector<uint64_t> read_ids;                   // read_id of m_read_vec[i], packed (line formatting reads two per candidate)
     std::vector<uint32_t> mate_len;                   // 2 per read: sequence lengths (/1, /2; 0 for the missing mate of a single)
     double t_read_s = 0, t_cuda_init_s = 0, t_store_s = 0, t_index_s = 0;  // wall clock of the constructor's phases (not in the reference)
 
@@ -133,6 +140,9 @@ public:
     explicit OverlapGraph(unsigned int V);
     node_id_t addVertex(read_id_t id);                                                   // src/OverlapGraph.cpp:88-92
     void addEdge(const Edge& e);                                                         // :94-101
+    // addEdge for es[k] with keep[k] != 0 (all of es if keep is null), in order: the lists are sized first and filled by
+    // all host threads; the edges must have distinct (vertex pair, orientation) keys, as the survivors of the insert have
+    void addEdges(const std::vector<Edge>& es, const unsigned char* keep);
     double checkEdgeWithOri(node_id_t v, node_id_t w, bool same_ori) const;              // :198-229
     const Edge* getEdgeInfoWithOri(node_id_t v, node_id_t w, bool same_ori) const;       // :285-307
     void removeEdgeWithOri(node_id_t v, node_id_t w, bool same_ori);                     // :150-195
@@ -147,10 +157,27 @@ public:
 
 private:
     // (min vertex, max vertex, same-orientation flag) -> owner vertex of the unique edge of that key
-    std::unordered_map<uint64_t, node_id_t> owner_;
+    // (built when the first lookup / removal asks for it: a stage that only inserts never pays for it)
+    mutable std::unordered_map<uint64_t, node_id_t> owner_;
+    mutable bool owner_stale_ = false;
+    void ensure_owner() const;
     static uint64_t key(node_id_t a, node_id_t b, bool same_ori);
     unsigned int edge_count_ = 0;
 };
+
+// A whole file in memory: anonymous mapping (huge pages where the kernel gives them), filled by several threads with pread.
+struct FileBuf {
+    char* data = nullptr;
+    size_t size = 0, mapped = 0;
+    FileBuf() {}
+    FileBuf(const FileBuf&) = delete;
+    FileBuf& operator=(const FileBuf&) = delete;
+    FileBuf(FileBuf&& o) noexcept : data(o.data), size(o.size), mapped(o.mapped) { o.data = nullptr; o.size = o.mapped = 0; }
+    FileBuf& operator=(FileBuf&& o) noexcept;
+    ~FileBuf();
+};
+// false if the file cannot be opened; threads <= 0: all host threads
+bool read_whole_file(const std::string& path, FileBuf& out, int threads = 0);
 
 class EdgeCalculator {             // src/EdgeCalculator.h:26-63
 public:
@@ -165,6 +192,10 @@ public:
     unsigned long scored_candidates = 0;
     double device_ms = 0, parse_device_ms = 0;
     double t_ingest_s = 0, t_score_s = 0, t_edges_s = 0, t_write_s = 0;   // host wall clock per phase
+    // --gpu_parse: the text of the overlaps file, if the caller has read it already (hc_edgecalc reads it while the read
+    // store is being built); construct_edges() reads the file itself otherwise
+    FileBuf preloaded_overlaps;
+    bool have_preloaded = false;
 
 private:
     void process_overlaps(std::vector<Overlap>& batch);                                          // :389-557
