@@ -235,6 +235,7 @@ def main() -> None:
     ap.add_argument("--binned-qualities", action="store_true",
                     help="diagnostic workload: qualities quantised to the four bins of current Illumina instruments")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the files-in -> graph-out leg (tools/bench_pipeline.py, about 20 s)")
     ap.add_argument("--e2e-no-output", action="store_true",
                     help="diagnostic: the e2e leg with zero output capacity (nothing is copied back; INVALID as an e2e number)")
     ap.add_argument("--dma-load", action="store_true",
@@ -644,6 +645,24 @@ def main() -> None:
                                                   % (len(cs), n_reads), "one_thread_value": t1, "cpu": cpu_model()}
             except Exception as ex:   # the baseline is a reported number, never a reason to lose the GPU line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (ex,)}
+        if world == 1 and not args.no_cpu and not args.no_pipeline:
+            # files in -> overlap graph out through the reference's own interface (construct_edges of the unmodified reference on
+            # all host threads next to the host mirror over the C ABI, same files, graphs compared): tools/bench_pipeline.py
+            try:
+                import subprocess
+                pr_out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_pipeline.py"), "--pairs", "300000", "--partners", "20",
+                                         "--one-thread-limit", "0", "--skip-host-parsers"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                        text=True, timeout=300).stdout
+                pj = json.loads([l for l in pr_out.split("\n") if l.startswith("{")][-1])
+                m, r, b = pj.get("mirror_device_ingest", {}), pj.get("reference", {}), pj.get("breakdown", {})
+                line["files_to_graph"] = {
+                    "workload": "%d read pairs, %d candidates, %.0f MB overlaps file + FASTQ files on disk" % (pj["pairs"], pj["candidates"], pj["overlaps_file_bytes"] / 1e6),
+                    "reference_construct_edges_s": r.get("t_construct_edges_s"), "reference_threads": r.get("threads"), "reference_wall_s": r.get("wall_s"),
+                    "mirror_construct_edges_s": m.get("t_construct_edges_s"), "mirror_wall_s": m.get("wall_s"), "mirror_cuda_context_s": m.get("t_cuda_init_s"),
+                    "speedup_construct_edges": b.get("speedup_construct_edges_vs_reference"), "speedup_wall": b.get("speedup_wall_vs_reference"),
+                    "same_edges_as_reference": m.get("same_edges_as_reference"), "mirror_phases_s": b.get("phases_s")}
+            except Exception as ex:
+                line["files_to_graph"] = {"failed": repr(ex)[:200]}
         emit(line)
     store.close()
     if world > 1:

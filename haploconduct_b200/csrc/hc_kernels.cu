@@ -1178,6 +1178,66 @@ __device__ void exact_window(const hc_kparams& P, const double* __restrict__ sdb
     mean = __dmul_rn(__ddiv_rn(1.0, dl), total);                         // :137
 }
 
+// The same sum with the addends in a WIDE shared-memory table, row = B code, column = A code | mismatch << 7 (256 doubles per
+// row, like the fixed-point table of the score kernel): one PRMT builds an index, nothing is decided per position -- a
+// position outside the window or with an N has a zero byte on one side (slots are zero padded) and its table entry is
+// +0.0, which leaves a sum of non-positive addends bit for bit as it is; void entries (positive) are noticed per 32
+// positions; compared and mismatching positions are counted on flag words.  Packed layout, one thread per window.
+// (The first version decided j < n, N and void per position: 42 instructions per position, 5.3 ms for the 7.1 M edges of
+// the benchmark step.)
+__device__ void exact_window_wide(const hc_kparams& P, const double* __restrict__ T2, const Win& w, double& mean, double& mmrate,
+                                  uint32_t& mmc, uint32_t& cmp, uint32_t& status) {
+    mean = 0.0;
+    mmrate = 1.0;
+    mmc = 0;
+    cmp = 0;
+    status = w.status;
+    if (w.status != HC_WIN_SCORED) return;
+    double total = 0.0;
+    uint32_t tl = 0, mm = 0;
+    const uint32_t nblk = (w.L + 31u) >> 5;
+    for (uint32_t k = 0; k < nblk; k++) {
+        const PkRow r = load32_packed(P, w.xpos, w.ypos16, w.L, 0u, k);
+        const bool s4 = (r.off & 16u) != 0, s2 = (r.off & 8u) != 0, s1 = (r.off & 4u) != 0;
+        uint32_t V2[12], V1[10], V[9];
+#pragma unroll
+        for (int i = 0; i < 12; i++) V2[i] = s4 ? r.a[i + 4] : r.a[i];
+#pragma unroll
+        for (int i = 0; i < 10; i++) V1[i] = s2 ? V2[i + 2] : V2[i];
+#pragma unroll
+        for (int i = 0; i < 9; i++) V[i] = s1 ? V1[i + 1] : V1[i];
+        const uint32_t sh = (r.off & 3u) * 8u;
+        uint32_t flags = 0, vw = 0;
+        bool vd = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t wa = __funnelshift_r(V[j], V[j + 1], sh), wb = r.y[j];
+            const uint32_t x = wa ^ wb;                                         // bits 6-7 of a byte: base difference
+            const uint32_t mf = (x | (x << 1)) & 0x80808080u;
+            const uint32_t col = (wa & 0x3f3f3f3fu) | mf, row = wb & 0x3f3f3f3fu;
+            const uint32_t nzA = (((wa & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wa), nzB = (((wb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wb);
+            flags |= mf >> j;
+            vw |= ((nzA & nzB) & 0x80808080u) >> j;
+            const double l0 = T2[prmt(col, row, 0xCC40u)], l1 = T2[prmt(col, row, 0xDD51u)];
+            const double l2 = T2[prmt(col, row, 0xEE62u)], l3 = T2[prmt(col, row, 0xFF73u)];
+            vd = vd || l0 > 0.0 || l1 > 0.0 || l2 > 0.0 || l3 > 0.0;
+            total = __dadd_rn(total, l0);                                       // :119, position order
+            total = __dadd_rn(total, l1);
+            total = __dadd_rn(total, l2);
+            total = __dadd_rn(total, l3);
+        }
+        if (vd) { status = HC_WIN_VOID; return; }                               // :125-127
+        tl += __popc(vw);
+        mm += __popc(flags & vw);
+    }
+    if (tl == 0) { status = HC_WIN_EMPTY; return; }                      // :129-131
+    mmc = mm;
+    cmp = tl;
+    const double dl = (double)tl;
+    mmrate = __ddiv_rn((double)(float)(int)mm, dl);                      // :132
+    mean = __dmul_rn(__ddiv_rn(1.0, dl), total);                         // :137
+}
+
 // The same window by a whole warp: the lanes fetch 32 positions' addends at once, the additions still run in position
 // order (every lane repeats the chain on shuffled values).  Used when only a few candidates are queued -- the usual
 // case, a few dozen per batch -- where one thread per candidate means a chain of ~265 dependent loads.
@@ -1242,12 +1302,23 @@ __global__ void hc_exact_kernel(const hc_kparams P, uint32_t table_in_smem) {
     // shared memory -- the lookups of a warp are 32 different addresses, which the global-memory path pays with up to 32
     // wavefronts each and shared memory with a few
     const double* sdbl = nullptr;
-    if (table_in_smem && !warp_mode && nf > 0) {
+    const double* swide = nullptr;
+    if (table_in_smem == 1u && !warp_mode && nf > 0) {
         double* t = reinterpret_cast<double*>(smem);
         const uint32_t nent = (P.ncodes + 1u) * (P.ncodes + 1u) * 2u;
         for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x) t[k] = P.dbl_table[k];
         __syncthreads();
         sdbl = t;
+    }
+    if (table_in_smem == 2u && !warp_mode && nf > 0) {   // wide table: [B code][A code | mismatch << 7]; N / padding (code 0) adds +0.0
+        double* t = reinterpret_cast<double*>(smem);
+        const uint32_t n1 = P.ncodes + 1u, nent = n1 * 256u;
+        for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x) {
+            const uint32_t b = k >> 8, a = k & 63u, m = (k >> 7) & 1u;
+            t[k] = (a == 0u || b == 0u || a >= n1 || (k & 64u)) ? 0.0 : P.dbl_table[hc_dbl_index(a, b, m, n1)];
+        }
+        __syncthreads();
+        swide = t;
     }
     const int lane = threadIdx.x & 31;
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1264,6 +1335,7 @@ __global__ void hc_exact_kernel(const hc_kparams P, uint32_t table_in_smem) {
 #pragma unroll
         for (int w = 0; w < 2; w++) {
             if (warp_mode) exact_window_warp(P, s.w[w], lane, mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
+            else if (swide) exact_window_wide(P, swide, s.w[w], mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
             else exact_window(P, sdbl, s.w[w], mean[w], mmr[w], mmc[w], cmp[w], stt[w]);
             if (stt[w] == HC_WIN_SCORED) {
                 ae[w] = mean[w] >= P.t_edge;   // <=> host-libm exp(mean) > edge_threshold
@@ -1598,7 +1670,21 @@ cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint
 }
 
 cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st) {
-    // packed layout: room for the double table ((K+1)^2 * 2 addends, 18 KB for 33 quality values) next to 128 threads
+    // Every accepted edge is queued (HC_FLAG_EXACT_EDGE_SCORES), packed layout: the wide double table, (K+1) * 2 KB -- 68 KB
+    // for 33 quality values --, blocks of 256 threads, as many per SM as the table leaves room for.
+    const size_t wide = (size_t)(P.ncodes + 1u) * 256u * sizeof(double);
+    if (P.packed && P.exact_edges && wide <= 200u * 1024u) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(hc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide);
+        if (e != cudaSuccess) return e;
+        const size_t per_sm = 224u * 1024u / (wide + 1024u);
+        const unsigned bps = (unsigned)(per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+        hc_exact_kernel<<<(unsigned)sms * bps, 256, wide, st>>>(P, 2u);
+        return cudaGetLastError();
+    }
+    // a few boundary candidates (one warp each) or, rarely, many: the compact table ((K+1)^2 * 2 addends, 18 KB for 33
+    // quality values) next to 128 threads
     const size_t tbl = (size_t)(P.ncodes + 1u) * (P.ncodes + 1u) * 2u * sizeof(double);
     const bool in_smem = P.packed && tbl <= 96u * 1024u;
     if (in_smem) {

@@ -97,6 +97,14 @@ def test_reference_order_pass_many_and_few(built_lib):
     assert 0 < e2.sum() < 4000 and (per2["exact"][e2] == 1).all()
     assert np.allclose(per2["score"][e2], ref2["score"][e2], rtol=1e-14, atol=0)
     assert per2.tobytes() == per[:3000].tobytes()
+    # the same with void quality pairs (p < mismatch) and a high N rate: the wide-table thread mode decides neither per position
+    ss3 = W.synth_readset(400, 400, seed=779, n_rate=0.02)
+    c3 = W.geometry_candidates(ss3, 40000, seed=780)
+    for kw in (dict(edge_threshold=0.8, mismatch=0.02), dict(edge_threshold=0.5, ov_threshold=0.3, mismatch=0.0)):
+        per3, ref3, _ = _against_oracle(ss3.rs, F.make_params(flags=F.FLAG_EXACT_EDGE_SCORES, **kw), c3)
+        e3 = ref3["cls"] == F.CLASS_EDGE
+        assert e3.sum() > 4000 and (per3["exact"][e3] == 1).all()
+        assert np.allclose(per3["score"][e3], ref3["score"][e3], rtol=1e-14, atol=0)
 
 
 def test_fresh_inputs_all_types(built_lib):
