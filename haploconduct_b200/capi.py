@@ -22,8 +22,8 @@ EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_runs_small", "hc_score_batch_runs6_small", "hc_score_batch_short_small", "hc_edge_extra_pos", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
-    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_warm_up", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3", "hc_fno1_small", "hc_fno3_small",
-    "hc_store_create_fastq", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
+    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_warm_up", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3", "hc_fno1_small", "hc_fno3_small", "hc_build_adjacency",
+    "hc_store_create_fastq", "hc_store_create_fastq_files", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -48,6 +48,8 @@ def lib() -> ctypes.CDLL:
         L.hc_store_create.argtypes = [vp, u64, u64, vp, vp, i32, i32]
         L.hc_store_create_fastq.restype = vp
         L.hc_store_create_fastq.argtypes = [vp, u64, vp, u64, vp, u64, u64, i32, i32]
+        L.hc_store_create_fastq_files.restype = vp
+        L.hc_store_create_fastq_files.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, u64, i32, i32]
         L.hc_store_read_ids.restype = i32
         L.hc_store_read_ids.argtypes = [vp, vp, vp]
         L.hc_consensus.restype = i32
@@ -94,6 +96,8 @@ def lib() -> ctypes.CDLL:
         L.hc_fno1.argtypes = [vp, vp, u64, vp, u64, ctypes.POINTER(u64), i32]
         L.hc_fno3.restype = i32
         L.hc_fno3.argtypes = [u64, vp, vp, vp, u64, vp, i32, vp, u64, ctypes.POINTER(u64), i32]
+        L.hc_build_adjacency.restype = i32
+        L.hc_build_adjacency.argtypes = [vp, u64, vp, u64, i32, vp, vp, vp, vp, vp, ctypes.POINTER(u64), i32]
         L.hc_fno1_small.restype = i32
         L.hc_fno1_small.argtypes = L.hc_fno1.argtypes
         L.hc_fno3_small.restype = i32
@@ -145,6 +149,19 @@ class Store:
         self = cls.__new__(cls)
         self._h = L.hc_store_create_fastq(*[x for b in bufs for x in ((b.ctypes.data, len(b)) if b is not None else (None, 0))],
                                           max_reads, first_device, n_devices)
+        if not self._h:
+            raise HcError(-4, last_error())
+        self.first_device, self.n_devices = first_device, n_devices
+        return self
+
+    @classmethod
+    def from_fastq_files(cls, singles: Optional[str] = None, paired1: Optional[str] = None, paired2: Optional[str] = None,
+                         max_reads: int = 2 ** 62, first_device: int = 0, n_devices: int = 1) -> "Store":
+        """hc_store_create_fastq_files: the store from the FASTQ files themselves, streamed to the device."""
+        L = lib()
+        self = cls.__new__(cls)
+        enc = [p.encode() if p else None for p in (singles, paired1, paired2)]
+        self._h = L.hc_store_create_fastq_files(enc[0], enc[1], enc[2], max_reads, first_device, n_devices)
         if not self._h:
             raise HcError(-4, last_error())
         self.first_device, self.n_devices = first_device, n_devices
@@ -392,6 +409,28 @@ def fno3(fi: "F.Fno3Input", device: int = 0, small: bool = False) -> np.ndarray:
         if rc != -5:
             raise HcError(rc, last_error())
         cap = int(n.value)
+
+
+ADJ_EDGE = np.dtype([("vertex1", "<u4"), ("vertex2", "<u4"), ("nonoverlap_len", "<u4"), ("reserved", "<u4")])   # hc_adj_edge
+
+
+def build_adjacency(edges: np.ndarray, n_vertices: int, keep: Optional[np.ndarray] = None, sort: bool = False, device: int = 0):
+    """hc_build_adjacency: (out_off, out_perm, in_off, in_src, ties) -- adjacency lists in insertion order or, sort=True,
+    in the order of OverlapGraph::sortEdges, and the adj_in lists that walk produces."""
+    edges = np.ascontiguousarray(edges, dtype=ADJ_EDGE)
+    n = len(edges)
+    k = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+    out_off = np.zeros(n_vertices + 1, dtype=np.uint64)
+    in_off = np.zeros(n_vertices + 1, dtype=np.uint64)
+    out_perm = np.zeros(max(n, 1), dtype=np.uint32)
+    in_src = np.zeros(max(n, 1), dtype=np.uint32)
+    ties = np.zeros(max(n_vertices, 1), dtype=np.uint8)
+    kept = ctypes.c_uint64(0)
+    _check(lib().hc_build_adjacency(edges.ctypes.data if n else None, n, k.ctypes.data if k is not None else None, n_vertices, int(sort),
+                                    out_off.ctypes.data, out_perm.ctypes.data, in_off.ctypes.data, in_src.ctypes.data, ties.ctypes.data,
+                                    ctypes.byref(kept), device))
+    m = int(kept.value)
+    return out_off, out_perm[:m], in_off, in_src[:m], ties[:n_vertices]
 
 
 def dedup_edges(edges: np.ndarray, n_vertices: int, ignore_inclusions: bool = False, inclusions: Optional[np.ndarray] = None,

@@ -16,6 +16,9 @@
 #include "hc_layout.h"
 #include "hc_tables.h"
 #include "hc_stage.h"
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "hc_kernels.cuh"
 #include "hc_pack.cuh"
 #include "hc_consensus.cuh"
@@ -578,15 +581,10 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
 
 // FastqStorage::FastqStorage (src/FastqStorage.h:58-98) from the text of the FASTQ files: the files go to the first
 // device as they are; line index, record scan (ids, lengths), validation and packing all run there.
-hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, const char* paired1, uint64_t paired1_bytes,
-                                const char* paired2, uint64_t paired2_bytes, uint64_t max_reads, int first_device, int n_devices) {
-    if ((singles_bytes && !singles) || (paired1_bytes && !paired1) || (paired2_bytes && !paired2)) {
-        fail(HC_ERR_ARG, "hc_store_create_fastq: NULL argument");
-        return nullptr;
-    }
+// file[k] != NULL: the text is in host memory; else fd[k] >= 0: it is streamed from the file (bytes[k] = its size)
+static hc_store* store_from_fastq(const char* const file[3], const int fd[3], uint64_t bytes[3], uint64_t max_reads, int first_device,
+                                  int n_devices) {
     if (!check_devices(first_device, n_devices)) return nullptr;
-    const char* file[3] = {singles, paired1, paired2};
-    const uint64_t bytes[3] = {singles_bytes, paired1_bytes, paired2_bytes};
     uint64_t off[4] = {0, 0, 0, 0};
     for (int k = 0; k < 3; k++) off[k + 1] = off[k] + ((bytes[k] + 15) & ~15ull);
     hc_store* s = new hc_store();
@@ -603,8 +601,11 @@ hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, con
     int rc = HC_OK;
     cudaError_t e = cudaSetDevice(first_device);
     if (e == cudaSuccess) e = cudaMalloc(&d_text, off[3] + 16);
-    for (int k = 0; k < 3 && e == cudaSuccess; k++)
-        if (bytes[k]) e = hc_copy_h2d(d_text + off[k], file[k], bytes[k]);
+    for (int k = 0; k < 3 && e == cudaSuccess; k++) {
+        if (!bytes[k]) continue;
+        if (file[k]) e = hc_copy_h2d(d_text + off[k], file[k], bytes[k]);
+        else { size_t got = 0; e = hc_copy_file_h2d(d_text + off[k], fd[k], bytes[k], &got); bytes[k] = got; }   // a file that shrank: what is there
+    }
     for (int k = 0; k < 3 && e == cudaSuccess; k++) e = hc_fastq_index(d_text + off[k], bytes[k], max_reads, &d_ls[k], &nl[k], &nrec[k], 0);
     if (e == cudaSuccess) {
         n_single = nrec[0];
@@ -652,6 +653,42 @@ hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, con
     cudaFree(d_text); cudaFree(d_ids); cudaFree(d_len); cudaFree(d_src); cudaFree(d_tok); cudaFree(d_first);
     for (int k = 0; k < 3; k++) cudaFree(d_ls[k]);
     if (rc != HC_OK) { const std::string keep = g_err; hc_store_destroy(s); g_err = keep; return nullptr; }
+    return s;
+}
+
+hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, const char* paired1, uint64_t paired1_bytes,
+                                const char* paired2, uint64_t paired2_bytes, uint64_t max_reads, int first_device, int n_devices) {
+    if ((singles_bytes && !singles) || (paired1_bytes && !paired1) || (paired2_bytes && !paired2)) {
+        fail(HC_ERR_ARG, "hc_store_create_fastq: NULL argument");
+        return nullptr;
+    }
+    const char* file[3] = {singles_bytes ? singles : nullptr, paired1_bytes ? paired1 : nullptr, paired2_bytes ? paired2 : nullptr};
+    const int fd[3] = {-1, -1, -1};
+    uint64_t bytes[3] = {singles_bytes, paired1_bytes, paired2_bytes};
+    return store_from_fastq(file, fd, bytes, max_reads, first_device, n_devices);
+}
+
+// The same from the files themselves, streamed: pieces of a file are read into a ring of pinned buffers by several host
+// threads and go to the device from there, so the host never holds a file (src/FastqStorage.cpp:42-57 reads every line
+// into a vector of strings first: twice the file in host memory).  A path that is NULL, "" or "None" is
+// an absent file (src/FastqStorage.h:66-75); a file that cannot be opened is the reference's "Unable to open" exit.
+hc_store* hc_store_create_fastq_files(const char* singles_path, const char* paired1_path, const char* paired2_path, uint64_t max_reads,
+                                      int first_device, int n_devices) {
+    const char* path[3] = {singles_path, paired1_path, paired2_path};
+    const char* file[3] = {nullptr, nullptr, nullptr};
+    int fd[3] = {-1, -1, -1};
+    uint64_t bytes[3] = {0, 0, 0};
+    hc_store* s = nullptr;
+    bool ok = true;
+    for (int k = 0; k < 3 && ok; k++) {
+        if (!path[k] || !*path[k] || !strcmp(path[k], "None")) continue;
+        fd[k] = open(path[k], O_RDONLY);
+        struct stat st;
+        if (fd[k] < 0 || fstat(fd[k], &st) != 0) { fail(HC_ERR_INPUT, std::string("Unable to open fastq file ") + path[k]); ok = false; break; }
+        bytes[k] = st.st_size > 0 ? (uint64_t)st.st_size : 0;
+    }
+    if (ok) s = store_from_fastq(file, fd, bytes, max_reads, first_device, n_devices);
+    for (int k = 0; k < 3; k++) if (fd[k] >= 0) close(fd[k]);
     return s;
 }
 

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <unistd.h>
 #include <stdio.h>
 #include <time.h>
 
@@ -151,6 +152,53 @@ cudaError_t hc_copy_d2h(void* dst, const void* src, size_t bytes) {
         drained++;
     }
     return cudaSuccess;
+}
+
+cudaError_t hc_copy_file_h2d(void* dst, int fd, size_t bytes, size_t* got) {
+    if (got) *got = 0;
+    if (bytes == 0) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ring* r;
+    if ((e = ring_for(dev, &r)) != cudaSuccess) return e;
+    const int T = host_threads();
+    size_t done = 0;
+    bool eof = false;
+    while (done < bytes && !eof) {
+        const int b = r->next;
+        r->next = (r->next + 1) % kRing;
+        const size_t n = bytes - done < kChunk ? bytes - done : kChunk;
+        if (r->used[b] && (e = cudaEventSynchronize(r->ev[b])) != cudaSuccess) return e;
+        const long nb = (long)((n + kBlock - 1) / kBlock);
+        long short_at = nb;                      // first block that came back short (end of file before `bytes`)
+        size_t short_len = 0;
+#pragma omp parallel for schedule(static) num_threads(T)
+        for (long q = 0; q < nb; q++) {
+            const size_t o = (size_t)q * kBlock, want = n - o < kBlock ? n - o : kBlock;
+            size_t have = 0;
+            while (have < want) {
+                const ssize_t k = pread(fd, r->buf[b] + o + have, want - have, (off_t)(done + o + have));
+                if (k <= 0) break;
+                have += (size_t)k;
+            }
+            if (have < want) {
+#pragma omp critical
+                if (q < short_at) { short_at = q; short_len = have; }
+            }
+        }
+        size_t valid = n;
+        if (short_at < nb) { valid = (size_t)short_at * kBlock + short_len; eof = true; }
+        if (valid) {
+            if ((e = cudaMemcpyAsync(static_cast<char*>(dst) + done, r->buf[b], valid, cudaMemcpyHostToDevice, r->stream)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(r->ev[b], r->stream)) != cudaSuccess) return e;
+            r->used[b] = true;
+        }
+        done += valid;
+    }
+    if (got) *got = done;
+    return cudaStreamSynchronize(r->stream);
 }
 
 cudaError_t hc_copy_h2d_on(void* dst, const void* src, size_t bytes, cudaStream_t st) {

@@ -21,6 +21,11 @@ cudaError_t hc_copy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 cudaError_t hc_copy_h2d_on(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
 cudaError_t hc_copy_d2h_on(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st, bool* completed);
 
+// A file straight to the device: several host threads pread pieces of it into the pinned ring, the copy engine drains
+// them -- the host never holds more than the ring (32 MB) of the file.  Reads `bytes` from offset 0 of `fd`; *got = bytes
+// that arrived (less if the file is shorter).  Synchronous: the data is on the device on return.
+cudaError_t hc_copy_file_h2d(void* dst_dev, int fd, size_t bytes, size_t* got);
+
 // Device scratch from the device's default memory pool, ordered on the legacy default stream (the stream the
 // host-buffer entry points launch on); freed memory stays in the pool (up to 16 GB), so that a call does not pay
 // cudaMalloc / cudaFree for each of its dozen temporaries.

@@ -20,7 +20,7 @@ static double now_s() {
 
 int main(int argc, char** argv) {
     hcb::ProgramSettings ps;
-    std::string dump_graph, digraph;
+    std::string dump_graph, digraph, dump_sorted;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         std::string v;
@@ -55,6 +55,7 @@ int main(int argc, char** argv) {
         else if (a == "--gpu_fastq") ps.gpu_fastq = b(v);
         else if (a == "--gpus") ps.n_devices = atoi(v.c_str());
         else if (a == "--dump-graph") dump_graph = v;
+        else if (a == "--dump-sorted") dump_sorted = v;        // OverlapGraph::sortEdges() (src/ViralQuasispecies.cpp:297), then the same dump + adj_in
         else if (a == "--digraph") digraph = v;
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -83,9 +84,18 @@ int main(int argc, char** argv) {
     const double t_ce_end = now_s();
     if (!dump_graph.empty()) graph->dumpAdjacency(dump_graph);
     if (!digraph.empty()) graph->writeDiGraphToFile(digraph);
-    printf("{\"t_main_s\": %.6f, \"t_graph_files_s\": %.6f, \"reads_single\": %u, \"reads_paired\": %u, \"scored\": %lu, \"t_fastq_s\": %.6f, \"t_construct_edges_s\": %.6f, "
+    double t_sort = 0;
+    if (!dump_sorted.empty()) {
+        std::vector<uint32_t> read_len(fastq->mate_len.size() / 2);
+        for (size_t i = 0; i < read_len.size(); i++) read_len[i] = fastq->mate_len[2 * i] + fastq->mate_len[2 * i + 1];   // Read::get_len(), src/Read.h:203-212
+        const double ts0 = now_s();
+        graph->sortEdges(read_len, ps.gpu_dedup ? ps.first_device : -1);
+        t_sort = now_s() - ts0;
+        graph->dumpAdjacency(dump_sorted, true);
+    }
+    printf("{\"t_sort_edges_s\": %.6f, \"t_main_s\": %.6f, \"t_graph_files_s\": %.6f, \"reads_single\": %u, \"reads_paired\": %u, \"scored\": %lu, \"t_fastq_s\": %.6f, \"t_construct_edges_s\": %.6f, "
            "\"t_fastq_read_s\": %.3f, \"t_cuda_init_s\": %.3f, \"t_fastq_store_s\": %.3f, \"t_fastq_index_s\": %.3f, \"device_ms\": %.3f, \"parse_device_ms\": %.3f, \"t_ingest_s\": %.3f, \"t_score_s\": %.3f, \"t_edges_s\": %.3f, \"t_write_s\": %.3f, \"graph_edges\": %u, \"dup_count\": %u, \"inclusion_count\": %u}\n",
-           t_ce_end - t_start, now_s() - t_ce_end, fastq->m_readcount_single, fastq->m_readcount_paired, ec.scored_candidates, t_fastq, t_ce, fastq->t_read_s, fastq->t_cuda_init_s, fastq->t_store_s, fastq->t_index_s, ec.device_ms, ec.parse_device_ms, ec.t_ingest_s, ec.t_score_s, ec.t_edges_s, ec.t_write_s,
+           t_sort, t_ce_end - t_start, now_s() - t_ce_end, fastq->m_readcount_single, fastq->m_readcount_paired, ec.scored_candidates, t_fastq, t_ce, fastq->t_read_s, fastq->t_cuda_init_s, fastq->t_store_s, fastq->t_index_s, ec.device_ms, ec.parse_device_ms, ec.t_ingest_s, ec.t_score_s, ec.t_edges_s, ec.t_write_s,
            graph->getEdgeCount(), ec.dup_count, ec.inclusion_count);
     // the process ends here: no destructor walk over millions of adjacency entries, no piecewise release of the device
     fflush(stdout);

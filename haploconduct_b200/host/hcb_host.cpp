@@ -169,34 +169,22 @@ bool read_whole_file(const std::string& path, FileBuf& out, int threads) {
     return true;
 }
 
-static FileBuf slurp_buf(const std::string& path) {
-    FileBuf b;
-    if (path.empty() || path == "None") return b;
-    if (!read_whole_file(path, b)) die("Unable to open fastq file " + path);      // src/FastqStorage.cpp:54-56
-    return b;
-}
-
 std::function<void()> FastqStorage::device_ready_hook;
 
 FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
     if (ps.gpu_fastq) {
         if (!ps.id_correspondence.empty()) die("--IDs is not supported together with --gpu_fastq");
-        // (creating the CUDA context from a second thread while this one reads the files was measured and is slower: the
-        // context creation and the page faults of the file buffers contend for the address-space lock)
-        const double tf0 = wall_s();
-        const FileBuf sb = slurp_buf(ps.singles_file), p1b = slurp_buf(ps.paired1_file), p2b = slurp_buf(ps.paired2_file);
-        struct View { const char* p; size_t n; const char* data() const { return p; } size_t size() const { return n; } };
-        const View s{sb.data, sb.size}, p1{p1b.data, p1b.size}, p2{p2b.data, p2b.size};
+        // the files are streamed to the device by the library (pinned ring, several reading threads): no host copy of them
         const double tfr = wall_s();
-        t_read_s = tfr - tf0;
+        t_read_s = 0;
         if (hc_warm_up(ps.first_device) != HC_OK) die(std::string("hc_warm_up: ") + hc_last_error());
         if (device_ready_hook) device_ready_hook();      // e.g. start reading the overlaps file: from here on nothing maps memory at CUDA's pace
         const double tf1 = wall_s();
         t_cuda_init_s = tf1 - tfr;
         first_device_ = ps.first_device;
-        store_ = hc_store_create_fastq(s.data(), s.size(), p1.data(), p1.size(), p2.data(), p2.size(), ps.max_reads, ps.first_device,
-                                       ps.n_devices);
-        if (!store_) die(std::string("hc_store_create_fastq: ") + hc_last_error());
+        store_ = hc_store_create_fastq_files(ps.singles_file.c_str(), ps.paired1_file.c_str(), ps.paired2_file.c_str(), ps.max_reads,
+                                             ps.first_device, ps.n_devices);
+        if (!store_) die(hc_last_error());                // "Unable to open fastq file ...", src/FastqStorage.cpp:54-56, or what is wrong with a record
         const double tf2 = wall_s();
         t_store_s = tf2 - tf1;
         const uint64_t n = hc_store_n_reads(store_);
@@ -434,13 +422,79 @@ void OverlapGraph::removeEdgeWithOri(node_id_t v, node_id_t w, bool same_ori) {
     die("Edge to be removed not found...\n" + std::to_string(v) + " " + std::to_string(w));
 }
 
+void OverlapGraph::sortEdges(const std::vector<uint32_t>& read_len, int device) {
+    const size_t V = adj_out.size();
+    auto nonoverlap = [&](const Edge& e) -> unsigned int {                       // Edge::get_nonoverlap_len, src/Edge.h:58-63
+        return (unsigned int)read_len[e.vertex1] + (unsigned int)read_len[e.vertex2] - (unsigned int)(2 * e.overlap_len);
+    };
+    auto std_sort_list = [&](std::vector<Edge>& lst) {                           // :726-747, the reference's own call
+        std::vector<std::pair<Edge, unsigned int>> pairs;
+        pairs.reserve(lst.size());
+        for (const Edge& e : lst) pairs.push_back(std::make_pair(e, nonoverlap(e)));
+        std::sort(pairs.begin(), pairs.end(), [](const std::pair<Edge, unsigned int>& a, const std::pair<Edge, unsigned int>& b) {
+            if (a.second == b.second) return a.first.vertex2 < b.first.vertex2;
+            return a.second < b.second;
+        });
+        for (size_t k = 0; k < lst.size(); k++) lst[k] = pairs[k].first;
+    };
+    bool in_done = false;
+    if (device >= 0 && edge_count_ > 0) {
+        std::vector<uint64_t> start(V + 1, 0);
+        for (size_t v = 0; v < V; v++) start[v + 1] = start[v] + adj_out[v].size();
+        const size_t n = start[V];
+        std::vector<hc_adj_edge> ae(n);
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (long long v = 0; v < (long long)V; v++) {
+            size_t k = start[(size_t)v];
+            for (const Edge& e : adj_out[(size_t)v]) {
+                ae[k].vertex1 = (uint32_t)e.vertex1; ae[k].vertex2 = (uint32_t)e.vertex2; ae[k].nonoverlap_len = nonoverlap(e); ae[k].reserved = 0;
+                k++;
+            }
+        }
+        std::vector<uint64_t> out_off(V + 1), in_off(V + 1);
+        std::vector<uint32_t> perm(n ? n : 1), in_src(n ? n : 1);
+        std::vector<uint8_t> ties(V ? V : 1);
+        uint64_t kept = 0;
+        const int rc = hc_build_adjacency(ae.data(), n, nullptr, V, 1, out_off.data(), perm.data(), in_off.data(), in_src.data(), ties.data(), &kept, device);
+        if (rc != HC_OK) die(std::string("hc_build_adjacency: ") + hc_last_error());
+        bool any_tie = false;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(|| : any_tie)
+        for (long long v = 0; v < (long long)V; v++) {
+            std::vector<Edge>& lst = adj_out[(size_t)v];
+            if (lst.size() < 2) continue;
+            if (ties[(size_t)v]) { std_sort_list(lst); any_tie = true; continue; }
+            std::vector<Edge> sorted(lst.size());
+            const size_t base = start[(size_t)v];                                 // out_off == start: every edge is kept
+            for (size_t k = 0; k < lst.size(); k++) sorted[k] = lst[perm[base + k] - base];
+            lst.swap(sorted);
+        }
+        if (!any_tie) {
+            adj_in.assign(V, std::vector<node_id_t>());
+#pragma omp parallel for schedule(dynamic, 4096)
+            for (long long w = 0; w < (long long)V; w++) {
+                std::vector<node_id_t>& in = adj_in[(size_t)w];
+                in.reserve(in_off[(size_t)w + 1] - in_off[(size_t)w]);
+                for (uint64_t k = in_off[(size_t)w]; k < in_off[(size_t)w + 1]; k++) in.push_back(in_src[k]);
+            }
+            in_done = true;
+        }
+    } else {
+        for (auto& lst : adj_out) if (lst.size() > 1) std_sort_list(lst);
+    }
+    if (!in_done) {                                                               // :752-763
+        adj_in.assign(V, std::vector<node_id_t>());
+        for (const auto& lst : adj_out)
+            for (const Edge& e : lst) adj_in[e.vertex2].push_back(e.vertex1);
+    }
+}
+
 void OverlapGraph::writeDiGraphToFile(const std::string& path) const {
     std::ofstream f(path.c_str());
     for (size_t v = 0; v < adj_out.size(); v++)
         for (const Edge& e : adj_out[v]) f << v << "\t" << e.vertex2 << "\n";
 }
 
-void OverlapGraph::dumpAdjacency(const std::string& path) const {
+void OverlapGraph::dumpAdjacency(const std::string& path, bool with_in) const {
     FILE* fo = fopen(path.c_str(), "w");
     if (!fo) die("cannot write " + path);
     fprintf(fo, "#v1\tv2\tscore\tmm_rate\tpos1\tpos2\tpos3\tpos4\tori1\tori2\tord\tperc\tlen1\tlen2\n");
@@ -449,6 +503,14 @@ void OverlapGraph::dumpAdjacency(const std::string& path) const {
             fprintf(fo, "%lu\t%lu\t%a\t%a\t%d\t%d\t%d\t%d\t%d\t%d\t%c\t%d\t%d\t%d\n", e.vertex1, e.vertex2, e.score,
                     e.mismatch_rate, e.pos1, e.pos2, e.pos3, e.pos4, (int)e.ori1, (int)e.ori2, e.ord, e.overlap_perc,
                     e.overlap_len1, e.overlap_len2);
+    for (size_t v = 0; v < inclusions.size(); v++) if (inclusions[v]) fprintf(fo, "#I\t%zu\n", v);
+    if (with_in)
+        for (size_t v = 0; v < adj_in.size(); v++) {
+            if (adj_in[v].empty()) continue;
+            fprintf(fo, "#IN\t%zu", v);
+            for (node_id_t s : adj_in[v]) fprintf(fo, "\t%lu", s);
+            fprintf(fo, "\n");
+        }
     fclose(fo);
 }
 

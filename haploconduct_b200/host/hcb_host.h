@@ -148,12 +148,17 @@ public:
     void removeEdgeWithOri(node_id_t v, node_id_t w, bool same_ori);                     // :150-195
     unsigned int getEdgeCount() const { return edge_count_; }
     unsigned int getVertexCount() const { return (unsigned int)vertex_to_read.size(); }
+    // sort every adjacency list by (non-overlap length, vertex2) and rebuild adj_in, :722-764.  read_len[v] = Read::get_len()
+    // of vertex v (src/Read.h:203-212).  device >= 0: the order comes from hc_build_adjacency, lists std::sort may order
+    // differently (equal keys in a list of more than 16 edges) are settled by std::sort itself; device < 0: std::sort only.
+    void sortEdges(const std::vector<uint32_t>& read_len, int device);
     void writeDiGraphToFile(const std::string& path) const;                              // :388-409
-    void dumpAdjacency(const std::string& path) const;   // every Edge field, adjacency order (test aid)
+    void dumpAdjacency(const std::string& path, bool with_in = false) const;   // every Edge field, adjacency order (test aid)
 
     std::vector<read_id_t> vertex_to_read;
     std::vector<char> inclusions;                        // src/OverlapGraph.h:80
     std::vector<std::vector<Edge>> adj_out;              // same order as the reference's std::list<Edge>
+    std::vector<std::vector<node_id_t>> adj_in;          // filled by sortEdges (:752-763)
 
 private:
     // (min vertex, max vertex, same-orientation flag) -> owner vertex of the unique edge of that key

@@ -68,7 +68,12 @@ hc_store* hc_store_create(const hc_read_desc* reads, uint64_t n_reads, uint64_t 
 hc_store* hc_store_create_fastq(const char* singles, uint64_t singles_bytes, const char* paired1, uint64_t paired1_bytes,
                                 const char* paired2, uint64_t paired2_bytes, uint64_t max_reads,
                                 int first_device, int n_devices);
-/* ids (n_reads) and mate lengths (2 * n_reads) of a store built by hc_store_create_fastq; either may be NULL */
+/* The same from the files themselves, streamed through a ring of pinned buffers (the host never holds a file; the
+ * reference reads every line into a vector of strings first, src/FastqStorage.cpp:42-57).  NULL, "" or "None" = absent
+ * file; a file that cannot be opened gives NULL + HC_ERR_INPUT ("Unable to open fastq file", :54-56). */
+hc_store* hc_store_create_fastq_files(const char* singles_path, const char* paired1_path, const char* paired2_path,
+                                      uint64_t max_reads, int first_device, int n_devices);
+/* ids (n_reads) and mate lengths (2 * n_reads) of a store built by hc_store_create_fastq*; either may be NULL */
 int       hc_store_read_ids(const hc_store* s, uint64_t* ids, uint32_t* mate_lengths);
 void      hc_store_destroy(hc_store* s);
 
@@ -454,6 +459,29 @@ typedef struct {
  * counts[0] = dup_count increment (:472,:537,:544), counts[1] = inclusion_count increment (:449-451). */
 int hc_dedup_edges(const hc_dedup_edge* edges, uint64_t n, int ignore_inclusions, uint8_t* winner,
                    uint8_t* inclusions, uint64_t n_vertices, uint64_t counts[2], int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Adjacency lists of the overlap graph (second half of the first "next" row):
+ * OverlapGraph::addEdge in insertion order (src/OverlapGraph.cpp:94-101) and OverlapGraph::sortEdges
+ * (:722-764): every adjacency list ordered by Edge::get_nonoverlap_len() (src/Edge.h:58-63:
+ * len(read1) + len(read2) - 2 * overlap_len, unsigned), then vertex2; adj_in rebuilt by walking the
+ * sorted lists vertex by vertex.
+ *
+ * edges[i] with keep[i] != 0 (all if keep is NULL) are grouped by vertex1:
+ *   out_off[v] .. out_off[v+1]   range of vertex v's list in out_perm            (out_off: n_vertices + 1)
+ *   out_perm[p]                  index into edges[] of the p-th edge; inside a list: input order (sort == 0)
+ *                                or (nonoverlap_len, vertex2, input order) (sort != 0)
+ *   in_off / in_src              (optional) adj_in: in_src[in_off[w] ..] = the vertex1 of every edge into w, in the
+ *                                order the walk over the lists meets them (:752-763)
+ *   ties[v]                      (optional, n_vertices) 1 if a list of more than 16 edges holds two edges with equal
+ *                                (nonoverlap_len, vertex2): std::sort does not say in which order it leaves them --
+ *                                the host mirror sorts such a list with std::sort itself
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t vertex1, vertex2, nonoverlap_len, reserved; } hc_adj_edge;   /* 16 bytes */
+
+int hc_build_adjacency(const hc_adj_edge* edges, uint64_t n, const uint8_t* keep, uint64_t n_vertices, int sort,
+                       uint64_t* out_off, uint32_t* out_perm, uint64_t* in_off, uint32_t* in_src, uint8_t* ties,
+                       uint64_t* n_kept, int device);
 
 /* ------------------------------------------------------------------------------------------
  * Candidate ingestion (second "next" row): the text loop of

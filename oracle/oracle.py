@@ -86,7 +86,7 @@ def have_ref() -> bool:
 
 def run_ref(workdir: str, overlaps: str, singles: Optional[str] = None, paired1: Optional[str] = None,
             paired2: Optional[str] = None, threads: int = 1, dump_cands: bool = False, run: bool = False,
-            dump_graph: bool = False, time_scoring: bool = False, reps: int = 1, **ps) -> Dict:
+            dump_graph: bool = False, time_scoring: bool = False, reps: int = 1, dump_sorted: bool = False, **ps) -> Dict:
     """Runs oracle/_ref/ref_driver with cwd=workdir (the reference writes nonedge_overlaps.txt into
     its cwd, src/EdgeCalculator.cpp:566,549).  Returns the JSON summary plus parsed dumps."""
     cmd = [REF_DRIVER, "--overlaps", overlaps, "--threads", str(threads)]
@@ -102,6 +102,8 @@ def run_ref(workdir: str, overlaps: str, singles: Optional[str] = None, paired1:
         cmd += ["--run"]
     if dump_graph:
         cmd += ["--dump-graph", os.path.join(workdir, "ref_graph.tsv")]
+    if dump_sorted:
+        cmd += ["--dump-sorted", os.path.join(workdir, "ref_sorted.tsv")]
     if time_scoring:
         cmd += ["--time-scoring", "--reps", str(reps)]
     out = subprocess.run(cmd, cwd=workdir, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
@@ -114,6 +116,9 @@ def run_ref(workdir: str, overlaps: str, singles: Optional[str] = None, paired1:
     if dump_graph:
         summary["graph"] = parse_graph_dump(os.path.join(workdir, "ref_graph.tsv"))
         summary["inclusions"] = parse_graph_inclusions(os.path.join(workdir, "ref_graph.tsv"))
+    if dump_sorted:
+        summary["sorted_graph"] = parse_graph_dump(os.path.join(workdir, "ref_sorted.tsv"))
+        summary["adj_in"] = parse_adj_in(os.path.join(workdir, "ref_sorted.tsv"))
     if run and os.path.exists(os.path.join(workdir, "nonedge_overlaps.txt")):
         with open(os.path.join(workdir, "nonedge_overlaps.txt")) as f:
             summary["nonedge_lines"] = f.read().split("\n")[:-1]
@@ -152,6 +157,43 @@ def parse_graph_dump(path: str) -> np.ndarray:
             rows.append((int(t[0]), int(t[1]), float.fromhex(t[2]), float.fromhex(t[3]), int(t[4]), int(t[5]), int(t[6]),
                          int(t[7]), int(t[8]), int(t[9]), ord(t[10]) if t[10] else 0, int(t[11]), int(t[12]), int(t[13])))
     return np.array(rows, dtype=REF_EDGE)
+
+
+def parse_adj_in(path: str):
+    """The '#IN' lines of a --dump-sorted file as CSR-like arrays: (vertices with in-edges, offsets, sources)."""
+    vs, off, src = [], [0], []
+    with open(path) as f:
+        for l in f:
+            if l.startswith("#IN\t"):
+                t = l.rstrip("\n").split("\t")
+                vs.append(int(t[1]))
+                src.extend(int(x) for x in t[2:])
+                off.append(len(src))
+    return np.array(vs, dtype=np.int64), np.array(off, dtype=np.int64), np.array(src, dtype=np.int64)
+
+
+def sort_edges(graph: np.ndarray, read_len: np.ndarray):
+    """OverlapGraph::sortEdges, src/OverlapGraph.cpp:722-764, restated on arrays: `graph` = REF_EDGE rows in adjacency order
+    (vertex by vertex, list order), `read_len[v]` = Read::get_len() of vertex v (both mates of a pair, src/Read.h:203-212).
+    Every list is ordered by (non-overlap length, vertex2) -- src/Edge.h:58-63: len1 + len2 - 2 * overlap_len in unsigned
+    arithmetic.  std::sort is not stable; this restatement keeps the list order among equal keys, which is what std::sort
+    does for lists of at most 16 edges (insertion sort) -- `ties_in_long_lists` counts the lists for which it may not hold.
+    Returns (sorted rows, adj_in as (vertices, offsets, sources), ties_in_long_lists)."""
+    ov = (graph["len1"].astype(np.int64) + graph["len2"].astype(np.int64))
+    nol = ((read_len[graph["v1"].astype(np.int64)].astype(np.int64) + read_len[graph["v2"].astype(np.int64)].astype(np.int64) - 2 * ov)
+           & 0xffffffff).astype(np.int64)
+    order = np.lexsort((np.arange(len(graph)), graph["v2"], nol, graph["v1"]))
+    out = graph[order]
+    k = np.stack([out["v1"].astype(np.int64), nol[order], out["v2"].astype(np.int64)], axis=1)
+    same = (k[1:] == k[:-1]).all(axis=1) if len(k) > 1 else np.zeros(0, bool)
+    deg = np.bincount(out["v1"].astype(np.int64), minlength=int(len(read_len)))
+    ties_long = int(np.unique(out["v1"][1:][same & (deg[out["v1"][1:].astype(np.int64)] > 16)]).size) if len(k) > 1 else 0
+    # adj_in: for every vertex in order, for every edge of its sorted list: adj_in[v2].push_back(v1)  (:752-763)
+    o2 = np.argsort(out["v2"].astype(np.int64), kind="stable")
+    v2s = out["v2"].astype(np.int64)[o2]
+    vs, first = np.unique(v2s, return_index=True)
+    off = np.append(first, len(v2s)).astype(np.int64)
+    return out, (vs.astype(np.int64), off, out["v1"].astype(np.int64)[o2]), ties_long
 
 
 def parse_graph_inclusions(path: str) -> np.ndarray:

@@ -103,7 +103,7 @@ int main(int argc, char** argv) {
     ps.fno = 2;
     ps.output_dir = "";
 
-    std::string dump_cands, dump_graph, merge_fno1, consensus_in, consensus_out, fno_state;
+    std::string dump_cands, dump_graph, dump_sorted, merge_fno1, consensus_in, consensus_out, fno_state;
     bool fno3 = false, use_cliques = false;
     ps.keep_singletons = 0;
     ps.remove_trans = 1;
@@ -138,6 +138,7 @@ int main(int argc, char** argv) {
         else if (a == "--max_ov") ps.max_overlaps = std::strtoul(need("--max_ov"), NULL, 10);
         else if (a == "--dump-cands") dump_cands = need("--dump-cands");
         else if (a == "--dump-graph") dump_graph = need("--dump-graph");
+        else if (a == "--dump-sorted") dump_sorted = need("--dump-sorted");   // the same dump after OverlapGraph::sortEdges(), plus adj_in
         else if (a == "--merge-fno1") merge_fno1 = need("--merge-fno1");
         else if (a == "--merge-fno3") { merge_fno1 = need("--merge-fno3"); fno3 = true; }
         else if (a == "--fno-state") fno_state = need("--fno-state");
@@ -311,9 +312,9 @@ int main(int argc, char** argv) {
         double ts = now_s();
         ec.construct_edges();
         t_construct = now_s() - ts;
-        if (!dump_graph.empty()) {
-            FILE* fo = std::fopen(dump_graph.c_str(), "w");
-            if (!fo) { std::fprintf(stderr, "cannot write %s\n", dump_graph.c_str()); return 1; }
+        auto dump = [&](const std::string& path, bool with_in) -> bool {
+            FILE* fo = std::fopen(path.c_str(), "w");
+            if (!fo) { std::fprintf(stderr, "cannot write %s\n", path.c_str()); return false; }
             std::fprintf(fo, "#v1\tv2\tscore\tmm_rate\tpos1\tpos2\tpos3\tpos4\tori1\tori2\tord\tperc\tlen1\tlen2\n");
             for (size_t v = 0; v < graph->adj_out.size(); v++) {
                 for (std::list<Edge>::iterator it = graph->adj_out[v].begin(); it != graph->adj_out[v].end(); ++it) {
@@ -327,7 +328,21 @@ int main(int argc, char** argv) {
             // OverlapGraph::inclusions (src/OverlapGraph.h:80) as '#I' lines, set only under ignore_inclusions
             for (size_t v = 0; v < graph->inclusions.size(); v++)
                 if (graph->inclusions[v]) std::fprintf(fo, "#I\t%zu\n", v);
+            if (with_in) {   // adj_in as sortEdges rebuilds it (src/OverlapGraph.cpp:752-763): '#IN v src src ...'
+                for (size_t v = 0; v < graph->adj_in.size(); v++) {
+                    if (graph->adj_in[v].empty()) continue;
+                    std::fprintf(fo, "#IN\t%zu", v);
+                    for (std::list<node_id_t>::iterator it = graph->adj_in[v].begin(); it != graph->adj_in[v].end(); ++it) std::fprintf(fo, "\t%lu", *it);
+                    std::fprintf(fo, "\n");
+                }
+            }
             std::fclose(fo);
+            return true;
+        };
+        if (!dump_graph.empty() && !dump(dump_graph, false)) return 1;
+        if (!dump_sorted.empty()) {
+            graph->sortEdges();                                   // src/OverlapGraph.cpp:722-764
+            if (!dump(dump_sorted, true)) return 1;
         }
     }
 

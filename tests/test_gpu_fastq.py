@@ -69,3 +69,26 @@ def test_fastq_edge_cases(built_lib):
     for s_, a_, b_ in bad:
         with pytest.raises(capi.HcError):
             capi.Store.from_fastq(s_, a_, b_)
+
+
+def test_store_streamed_from_files(built_lib, tmp_path, monkeypatch):
+    """hc_store_create_fastq_files: the files go through the pinned ring piece by piece (here with 64 KB ring buffers, so that
+    a few hundred reads are many pieces); the store must be the one built from the same text in memory."""
+    monkeypatch.setenv("HC_STAGE_CHUNK", "65536")
+    g = load_golden("c1_savage_example_full") if "c1_savage_example_full" in golden_names() else load_golden(golden_names()[0])
+    s, p1, p2 = _fastq_text(g.rs)
+    paths = []
+    for name, text in (("s.fastq", s), ("p1.fastq", p1), ("p2.fastq", p2)):
+        f = tmp_path / name
+        f.write_bytes(text)
+        paths.append(str(f) if len(text) else None)
+    cands = g.scored()[:20000]
+    with capi.Store.from_fastq(s, p1, p2) as a, capi.Store.from_fastq_files(*paths) as b:
+        L = capi.lib()
+        assert L.hc_store_n_reads(a.handle) == L.hc_store_n_reads(b.handle) and L.hc_store_n_single(a.handle) == L.hc_store_n_single(b.handle)
+        ra, rb = a.score_batch(g.params(), cands), b.score_batch(g.params(), cands)
+        assert ra[2].tobytes() == rb[2].tobytes() and ra[0].tobytes() == rb[0].tobytes()
+        ia, ib = a.read_ids(), b.read_ids()
+        assert all(np.array_equal(x, y) for x, y in zip(ia, ib))
+    with pytest.raises(capi.HcError):
+        capi.Store.from_fastq_files(str(tmp_path / "missing.fastq"))

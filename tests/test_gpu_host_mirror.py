@@ -19,13 +19,15 @@ pytestmark = pytest.mark.gpu
 EXE = os.path.join(B.LIBDIR, "hc_edgecalc")
 
 
-def _run(g, tmp_path, exact, gpu_dedup=False, gpu_parse=False, gpu_fastq=False):
+def _run(g, tmp_path, exact, gpu_dedup=False, gpu_parse=False, gpu_fastq=False, dump_sorted=False):
     d = str(tmp_path)
     F.write_fastq_set(g.rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", g.cands, g.rs.ids)
     cmd = [EXE, "--overlaps", d + "/ov.txt", "--dump-graph", d + "/graph.tsv", "--digraph", d + "/digraph.txt",
            "--exact_scores=" + ("true" if exact else "false"), "--gpu_dedup=" + ("true" if gpu_dedup else "false"), "--gpu_parse=" + ("true" if gpu_parse else "false"),
            "--gpu_fastq=" + ("true" if gpu_fastq else "false")]
+    if dump_sorted:
+        cmd += ["--dump-sorted", d + "/sorted.tsv"]
     if g.rs.n_single:
         cmd += ["--singles", d + "/s.fastq"]
     if g.rs.n_reads > g.rs.n_single:
@@ -140,3 +142,20 @@ def test_graph_fast_mode(built_lib, tmp_path, name):
         else:
             assert abs(mine[k]["score"] - e["score"]) <= 1e-6 * e["score"]
     assert n_checked > 0
+
+
+SORTED = sorted(f[len("sorted_"):-4] for f in os.listdir(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")) if f.startswith("sorted_"))
+
+
+@pytest.mark.parametrize("gpu", [False, True])
+@pytest.mark.parametrize("name", SORTED)
+def test_sort_edges_like_the_reference(built_lib, tmp_path, name, gpu):
+    """OverlapGraph::sortEdges() after construct_edges() (src/ViralQuasispecies.cpp:297): adjacency lists and adj_in as the
+    unmodified reference leaves them -- with the order taken from hc_build_adjacency (gpu) and with std::sort on the host."""
+    g = load_golden(name)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sorted_" + name + ".npz"))
+    _run(g, tmp_path, exact=True, gpu_dedup=gpu, gpu_parse=gpu, gpu_fastq=gpu, dump_sorted=True)
+    d = str(tmp_path)
+    assert O.parse_graph_dump(d + "/sorted.tsv").tobytes() == z["ref_sorted"].tobytes()
+    vs, off, src = O.parse_adj_in(d + "/sorted.tsv")
+    assert np.array_equal(vs, z["in_vertices"]) and np.array_equal(off, z["in_off"]) and np.array_equal(src, z["in_src"])
