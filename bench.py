@@ -249,6 +249,9 @@ def main() -> None:
     ap.add_argument("--e2e-output", default="small", choices=["small", "full"],
                     help="what the e2e leg brings back: hc_edge_small records + one bit per candidate (hc_score_batch_runs_small), "
                          "or 48-byte hc_edge records + 8-byte non-edge indices (hc_score_batch_runs)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: how the accepted-edge lists are gathered: one-sided puts over NVLink peer memory on the copy engines (peer), "
+                         "NCCL all-gather (nccl), or peer where it can be set up (auto)")
     ap.add_argument("--no-exchange", action="store_true", help="N > 1: leave the all-gather of the accepted edges out of the timed region")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--seed", type=int, default=20261018)
@@ -357,12 +360,21 @@ def main() -> None:
     # N > 1: the accepted-edge lists of all ranks are concatenated in rank order (= input order) by an NCCL all-gather of the
     # device-resident lists, on a side stream so that the gather of step k runs next to the kernels of step k + 1
     exchange = None
+    exchange_kind = None
     if world > 1 and not args.no_exchange:
         from haploconduct_b200 import dist as HD
         step()
         torch.cuda.synchronize()
-        cap_e = int(int(d_counts[0].item()) * 1.02) + 1024
-        gather = HD.DeviceGather(48, cap_e, dev)
+        cap_t = torch.tensor([int(int(d_counts[0].item()) * 1.02) + 1024], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)      # the lists are padded to ONE length: the longest rank's
+        cap_e = int(cap_t.item())
+        if args.exchange == "nccl":
+            gather, exchange_kind = HD.DeviceGather(48, cap_e, dev), "nccl"
+        else:
+            gather, exchange_kind = HD.make_device_gather(48, cap_e, dev)
+            if args.exchange == "peer" and exchange_kind != "peer":
+                raise RuntimeError("--exchange peer: peer memory could not be set up on this box")
+        log("[rank %d] accepted-edge gather: %s, lists padded to %d records" % (rank, exchange_kind, cap_e))
         xs = torch.cuda.Stream(dev)
         x_done = torch.cuda.Event()
         k_done = torch.cuda.Event()
@@ -614,8 +626,10 @@ def main() -> None:
             "gpu_launches": int(stats["kernel_launches"]) * args.steps,
             "clocks": clocks,
             "results": {"edges": int(counts[0]), "nonedges": int(counts[1]), "reference_order_pass": int(counts[2])},
-            "exchange": ("NCCL all-gather (counts, then lists padded to the longest) of every rank's accepted edges, 48-byte records, "
-                         "inside the timed region on a side stream; rank order = input order" if exchange else
+            "exchange": ((("one-sided puts over NVLink peer memory (copy engines; device-side barriers before and after) of every rank's accepted "
+                           "edges into every peer's buffer" if exchange_kind == "peer" else
+                           "NCCL all-gather (counts, then lists padded to the longest) of every rank's accepted edges") +
+                          ", 48-byte records, inside the timed region on a side stream; rank order = input order") if exchange else
                          ("none (one rank)" if world == 1 else "left out (--no-exchange)")),
             "exact_edge_scores": (None if exact_ms is None else {"ms_per_step": exact_ms, "value": n / (exact_ms * 1e-3), "unit": UNIT + " per GPU",
                                                                  "note": "HC_FLAG_EXACT_EDGE_SCORES: the mode of the drop-in host mirror"}),
