@@ -72,6 +72,12 @@ def build_host(verbose: bool = False) -> str:
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    # hc_sfo2overlaps: scripts/sfo2overlaps.py of the reference in C++ (host only)
+    conv = os.path.join(LIBDIR, "hc_sfo2overlaps")
+    cmd = [HOST_CXX, "-O2", "-std=c++14", "-Wall", "-fopenmp", "-o", conv, os.path.join(host, "hcb_sfo2overlaps.cpp")]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
     return exe
 
 

@@ -1630,6 +1630,19 @@ __global__ void hc_compact_advance(unsigned long long* run, const unsigned long 
 }  // namespace
 
 // ---- launchers ----------------------------------------------------------------------------------------
+// grid cap of the streaming helper kernels (grid-stride loops): eight blocks per SM of the current device
+static unsigned hc_grid_cap() {
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148u * 8u;
+    if (!sms[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms[dev] = n;
+    }
+    return (unsigned)sms[dev] * 8u;
+}
+
 cudaError_t hc_score_occupancy(uint32_t ncodes, int walk, int sm_count, size_t smem_per_sm, hc_launch_cfg* cfg) {
     // score table + tail masks (+ the anchor-walk table and its masks), per CTA
     const size_t table = (size_t)(ncodes + 1u) * 1024u * (walk ? 2u : 1u) + HC_VM_WORDS * 4u + (walk ? HC_AS_VMT_WORDS * 4u : 0u);
@@ -1665,7 +1678,7 @@ cudaError_t hc_launch_score(const hc_kparams& P, const hc_launch_cfg& cfg, cudaS
 cudaError_t hc_launch_tile_runs(const uint32_t* run_start, uint32_t n_runs, uint32_t* tile_run, cudaStream_t st) {
     if (n_runs == 0) return cudaSuccess;
     const unsigned blocks = (n_runs + 255u) / 256u;
-    hc_tile_runs<<<blocks < 1184u ? blocks : 1184u, 256, 0, st>>>(run_start, n_runs, tile_run);
+    hc_tile_runs<<<blocks < hc_grid_cap() ? blocks : hc_grid_cap(), 256, 0, st>>>(run_start, n_runs, tile_run);
     return cudaGetLastError();
 }
 
@@ -1691,7 +1704,7 @@ cudaError_t hc_launch_exact(const hc_kparams& P, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(hc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbl);
         if (e != cudaSuccess) return e;
     }
-    hc_exact_kernel<<<1184, 128, in_smem ? tbl : 0, st>>>(P, in_smem ? 1u : 0u);
+    hc_exact_kernel<<<hc_grid_cap(), 128, in_smem ? tbl : 0, st>>>(P, in_smem ? 1u : 0u);
     return cudaGetLastError();
 }
 
@@ -1711,13 +1724,13 @@ cudaError_t hc_launch_compact(const hc_kparams& P, hc_edge* d_edges, uint64_t ed
         // P.flagged has been consumed by the reference-order pass; it now carries the source index of every edge
         hc_compact_scatter<<<nb, HC_CB_THREADS, 0, st>>>(P, offs, P.flagged, d_nonedge, nonedge_cap, cand_offset);
         const u64 want = (P.n + 255) / 256;
-        const unsigned eb = (unsigned)(want < 1184ull ? want : 1184ull);
+        const unsigned eb = (unsigned)(want < (unsigned long long)hc_grid_cap() ? want : (unsigned long long)hc_grid_cap());
         if (!small_out) hc_emit_edges<<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
         else if (P.exact_edges) hc_emit_edges_small<true><<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
         else hc_emit_edges_small<false><<<eb, 256, 0, st>>>(P, P.flagged, d_edges, edges_cap, cand_offset);
         if (small_out && d_bits) {
             const u64 wantb = (((P.n + 31) >> 5) + 255) / 256;
-            hc_nonedge_bits<<<(unsigned)(wantb < 1184ull ? wantb : 1184ull), 256, 0, st>>>(P.cls, P.n, d_bits);
+            hc_nonedge_bits<<<(unsigned)(wantb < (unsigned long long)hc_grid_cap() ? wantb : (unsigned long long)hc_grid_cap()), 256, 0, st>>>(P.cls, P.n, d_bits);
         }
     }
     if (d_run) hc_compact_advance<<<1, 1, 0, st>>>(d_run, P.counters);
