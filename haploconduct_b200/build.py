@@ -78,6 +78,12 @@ def build_host(verbose: bool = False) -> str:
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    # hc_sam2overlaps: scripts/sam2overlaps.py of the reference in C++ (host only)
+    conv = os.path.join(LIBDIR, "hc_sam2overlaps")
+    cmd = [HOST_CXX, "-O2", "-std=c++14", "-Wall", "-fopenmp", "-o", conv, os.path.join(host, "hcb_sam2overlaps.cpp")]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
     return exe
 
 
