@@ -173,7 +173,30 @@ std::function<void()> FastqStorage::device_ready_hook;
 
 FastqStorage::FastqStorage(const ProgramSettings& ps) {                           // src/FastqStorage.h:58-98
     if (ps.gpu_fastq) {
-        if (!ps.id_correspondence.empty()) die("--IDs is not supported together with --gpu_fastq");
+        // --IDs: the table maps the header token (a string) to the id; the device scan reads ids as numbers, so the tokens are
+        // taken from the headers by the host (every fourth line of the singles file and of the first paired file, like
+        // :113-121,:186-195) and the ids of the store's reads replaced below
+        std::vector<std::string> header_tokens;
+        if (!ps.id_correspondence.empty()) {
+            read_new_ids(ps.id_correspondence);
+            for (const std::string* path : {&ps.singles_file, &ps.paired1_file}) {
+                if (path->empty() || *path == "None") continue;
+                FileBuf fb;
+                if (!read_whole_file(*path, fb)) die("Unable to open fastq file " + *path);
+                size_t line = 0, b = 0;
+                const size_t max_lines = ps.max_reads > (~0ul) / 4 ? ~0ul : 4 * ps.max_reads;
+                std::vector<std::string> toks;
+                while (b < fb.size && line < max_lines) {
+                    const void* nl = memchr(fb.data + b, '\n', fb.size - b);
+                    const size_t e = nl ? (size_t)((const char*)nl - fb.data) : fb.size;
+                    if (line % 4 == 0) toks.push_back(first_token(std::string(fb.data + b + (e > b ? 1 : 0), fb.data + e)));
+                    line++;
+                    b = e + 1;
+                }
+                toks.resize(line / 4);                          // complete records only
+                header_tokens.insert(header_tokens.end(), toks.begin(), toks.end());
+            }
+        }
         // the files are streamed to the device by the library (pinned ring, several reading threads): no host copy of them
         const double tfr = wall_s();
         t_read_s = 0;
@@ -191,6 +214,14 @@ FastqStorage::FastqStorage(const ProgramSettings& ps) {                         
         std::vector<uint64_t> ids(n);
         std::vector<uint32_t> lens(2 * n);
         if (hc_store_read_ids(store_, ids.data(), lens.data()) != HC_OK) die(hc_last_error());
+        if (have_new_ids_) {
+            if (header_tokens.size() < n) die("--IDs: fewer FASTQ headers than reads in the store");
+            for (uint64_t i = 0; i < n; i++) {
+                const auto it = new_ids_.find(header_tokens[i]);
+                if (it == new_ids_.end()) die("read name " + header_tokens[i] + " is not in the read-to-overlapID file");   // std::map::at throws in the reference
+                ids[i] = str_to_read_id(it->second);
+            }
+        }
         m_readcount_single = (unsigned int)hc_store_n_single(store_);
         m_readcount_paired = (unsigned int)(n - m_readcount_single);
         m_read_vec.resize(n);

@@ -101,3 +101,39 @@ def test_device_gather_concatenates_in_rank_order(tmp_path, world):
     """DeviceGather (the all-gather bench.py times at N > 1; NCCL there, gloo here): ragged lists, rank order."""
     mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+def _worker_padded(rank, world, port, outdir):
+    import torch
+    import torch.distributed as dist
+    from haploconduct_b200 import dist as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cpu")
+    rec, cap = 48, 40
+    n = 7 + 11 * rank                                   # lists of different lengths, padded to one capacity
+    mine = torch.zeros((cap, rec), dtype=torch.uint8)
+    mine[:n] = torch.arange(n * rec, dtype=torch.int64).reshape(n, rec).remainder(251).to(torch.uint8) + rank
+    g, kind = D.make_device_gather(rec, cap, dev)       # no peer memory on CPU tensors: the collective gather
+    assert kind == "nccl" and isinstance(g, D.DeviceGather)
+    for _ in range(2):
+        g.gather(mine, torch.tensor([n], dtype=torch.int64))
+        got = g.concatenated().numpy()
+    np.save(os.path.join(outdir, "p%d.npy" % rank), got)
+    dist.destroy_process_group()
+
+
+def test_padded_list_gather_factory_on_cpu(tmp_path):
+    """dist.make_device_gather hands back the collective gather where peer memory is not available (CPU tensors here; a box
+    without P2P on GPUs): counts first, lists padded to the agreed capacity, concatenated in rank order."""
+    world = 3
+    mp.spawn(_worker_padded, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = []
+    for r in range(world):
+        n = 7 + 11 * r
+        want.append((np.arange(n * 48, dtype=np.int64).reshape(n, 48) % 251).astype(np.uint8) + r)
+    want = np.concatenate(want).reshape(-1)
+    for r in range(world):
+        assert np.array_equal(np.load(str(tmp_path / ("p%d.npy" % r))), want)

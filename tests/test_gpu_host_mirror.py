@@ -19,15 +19,30 @@ pytestmark = pytest.mark.gpu
 EXE = os.path.join(B.LIBDIR, "hc_edgecalc")
 
 
-def _run(g, tmp_path, exact, gpu_dedup=False, gpu_parse=False, gpu_fastq=False, dump_sorted=False):
+def _run(g, tmp_path, exact, gpu_dedup=False, gpu_parse=False, gpu_fastq=False, dump_sorted=False, ids_table=False):
     d = str(tmp_path)
     F.write_fastq_set(g.rs, d + "/s.fastq", d + "/p1.fastq", d + "/p2.fastq")
     F.write_overlaps(d + "/ov.txt", g.cands, g.rs.ids)
+    if ids_table:   # headers become names ("@r<id>x some text"), the --IDs table maps the names back to the ids (src/FastqStorage.cpp:60-90)
+        for fn in ("s.fastq", "p1.fastq", "p2.fastq"):
+            if not os.path.exists(d + "/" + fn):
+                continue
+            with open(d + "/" + fn) as f:
+                lines = f.read().split("\n")
+            for k in range(0, len(lines) - 1, 4):
+                lines[k] = "@r%sx extra" % lines[k][1:].split()[0]
+            with open(d + "/" + fn, "w") as f:
+                f.write("\n".join(lines))
+        with open(d + "/ids.txt", "w") as f:
+            for i in g.rs.ids:
+                f.write("%d\t%sr%dx\n" % (int(i), ">" if int(i) % 2 else "", int(i)))
     cmd = [EXE, "--overlaps", d + "/ov.txt", "--dump-graph", d + "/graph.tsv", "--digraph", d + "/digraph.txt",
            "--exact_scores=" + ("true" if exact else "false"), "--gpu_dedup=" + ("true" if gpu_dedup else "false"), "--gpu_parse=" + ("true" if gpu_parse else "false"),
            "--gpu_fastq=" + ("true" if gpu_fastq else "false")]
     if dump_sorted:
         cmd += ["--dump-sorted", d + "/sorted.tsv"]
+    if ids_table:
+        cmd += ["--IDs", d + "/ids.txt"]
     if g.rs.n_single:
         cmd += ["--singles", d + "/s.fastq"]
     if g.rs.n_reads > g.rs.n_single:
@@ -159,3 +174,13 @@ def test_sort_edges_like_the_reference(built_lib, tmp_path, name, gpu):
     assert O.parse_graph_dump(d + "/sorted.tsv").tobytes() == z["ref_sorted"].tobytes()
     vs, off, src = O.parse_adj_in(d + "/sorted.tsv")
     assert np.array_equal(vs, z["in_vertices"]) and np.array_equal(off, z["in_off"]) and np.array_equal(src, z["in_src"])
+
+
+@pytest.mark.parametrize("gpu", [False, True])
+def test_read_names_through_the_ids_table(built_lib, tmp_path, gpu):
+    """--IDs (src/FastqStorage.cpp:60-90): FASTQ headers are names, the table gives the ids the overlaps file uses -- with the
+    host FASTQ reader and with the device one (--gpu_fastq), same graph as the fixture with numeric headers."""
+    g = load_golden("synth_all_types")
+    summary, graph, nonedge, digraph = _run(g, tmp_path, exact=True, gpu_dedup=gpu, gpu_parse=gpu, gpu_fastq=gpu, ids_table=True)
+    assert np.array_equal(graph, g.ref_graph)
+    assert nonedge == g.ref_nonedge
