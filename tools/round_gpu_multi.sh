@@ -1,6 +1,6 @@
 #!/bin/bash
-# eight GPUs: bench.py with the peer-memory gather (default) and with NCCL, e2e included in the first
-T=${1:-r02aa}
+# Eight GPUs of one box: bench.py with the peer-memory gather (default) and with NCCL, the multi-GPU tests.   gpurun --gpus 8 -- bash tools/round_gpu_multi.sh <tag>
+T=${1:-rXX}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 timeout 900 $TR --master-port 29531 bench.py --gpus 8 --steps 10 --warmup 3 2> gpurun_out/${T}_bench8.err | tail -1 > gpurun_out/${T}_bench_8gpu.json
