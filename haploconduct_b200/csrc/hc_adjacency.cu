@@ -180,3 +180,95 @@ done:
     hc_scratch_free(d_off); hc_scratch_free(d_total); hc_scratch_free(d_bsum); hc_scratch_free(d_items);
     return rc;
 }
+
+// ---- SRBuilder::calcSubreadInfo (src/SRBuilder.cpp:536-595) for many super-reads at once -------------------------------
+// A super-read is built from a clique whose vertices were ordered left to right (sort_vertices) with their start columns
+// (pos_list); consensus() says where the consensus sequence starts (trim_pos).  Per vertex the reference records where the
+// vertex' read lies in the trimmed consensus: index = pos - trim_pos (startpos = 0) or, for a read that starts in the
+// trimmed-away part, startpos = trim_pos - pos (index = 0) -- for the /1 sequence from list 1, for the /2 sequence from
+// list 2 (paired-end super-read, trim_pos2 >= 0) or from a LATER entry of the same vertex in list 1 (single-end super-read
+// built from a paired read: both mates are in list 1).  These records are the sr_sub input of hc_fno1.
+// One thread per list-1 entry: the first entry of a vertex owns the record; it takes index2 / startpos2 from the last later
+// entry of its vertex in list 1, then from the last entry of its vertex in list 2.
+namespace {
+__global__ void subread_info_kernel(const hc_subread_problem* __restrict__ prob, const uint32_t* __restrict__ entry_problem, u64 n_entries,
+                                    const int32_t* __restrict__ pos, const uint32_t* __restrict__ vertex, hc_fno_subread* __restrict__ info,
+                                    uint8_t* __restrict__ first) {
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < n_entries; k += (u64)gridDim.x * blockDim.x) {
+        const uint32_t pi = entry_problem[k];
+        hc_fno_subread r;
+        r.index1 = r.index2 = r.startpos1 = r.startpos2 = 0;
+        if (pi == 0xffffffffu) { first[k] = 0; info[k] = r; continue; }            // an entry of a list 2
+        const hc_subread_problem P = prob[pi];
+        const uint32_t v = vertex[k];
+        bool own = true;
+        for (u64 j = P.begin1; j < k; j++) if (vertex[j] == v) { own = false; break; }
+        first[k] = own ? 1 : 0;
+        if (!own) { info[k] = r; continue; }
+        const int32_t p = pos[k];
+        if (P.trim_pos1 > p) { r.startpos1 = P.trim_pos1 - p; r.index1 = 0; }
+        else { r.startpos1 = 0; r.index1 = p - P.trim_pos1; }
+        r.index2 = -1;
+        r.startpos2 = -1;
+        for (u64 j = k + 1; j < P.end1; j++) {                                    // :543-556, a later entry of the same vertex: last one wins
+            if (vertex[j] != v) continue;
+            const int32_t q = pos[j];
+            if (P.trim_pos1 > q) { r.startpos2 = P.trim_pos1 - q; r.index2 = 0; }
+            else { r.startpos2 = 0; r.index2 = q - P.trim_pos1; }
+        }
+        if (P.trim_pos2 >= 0) {                                                    // :574-592
+            for (u64 j = P.begin2; j < P.end2; j++) {
+                if (vertex[j] != v) continue;
+                const int32_t q = pos[j];
+                if (P.trim_pos2 > q) { r.startpos2 = P.trim_pos2 - q; r.index2 = 0; }
+                else { r.startpos2 = 0; r.index2 = q - P.trim_pos2; }
+            }
+        }
+        info[k] = r;
+    }
+}
+}  // namespace
+
+extern "C" int hc_subread_info(const hc_subread_problem* problems, uint64_t n_problems, const int32_t* pos, const uint32_t* vertex,
+                               uint64_t n_entries, hc_fno_subread* info, uint8_t* first, int device) {
+    if ((n_problems && !problems) || (n_entries && (!pos || !vertex || !info || !first))) { hc_set_last_error("hc_subread_info: NULL argument"); return HC_ERR_ARG; }
+    if (n_entries == 0) return HC_OK;
+    if (n_problems >= 0xffffffffull) { hc_set_last_error("hc_subread_info: too many problems"); return HC_ERR_ARG; }
+    // which problem an entry belongs to (list 1) -- also the range check: lists inside [0, n_entries), list 1 ranges disjoint
+    std::string err;
+    uint32_t* h_ep = (uint32_t*)malloc(n_entries * sizeof(uint32_t));
+    if (!h_ep) { hc_set_last_error("hc_subread_info: out of memory"); return HC_ERR_NOMEM; }
+    memset(h_ep, 0xff, n_entries * sizeof(uint32_t));
+    for (u64 p = 0; p < n_problems && err.empty(); p++) {
+        const hc_subread_problem& P = problems[p];
+        if (P.begin1 > P.end1 || P.end1 > n_entries || P.begin2 > P.end2 || P.end2 > n_entries) { err = "hc_subread_info: problem " + std::to_string(p) + ": list out of range"; break; }
+        if (P.trim_pos2 >= 0 && P.end2 - P.begin2 != P.end1 - P.begin1) { err = "hc_subread_info: problem " + std::to_string(p) + ": the two lists of a paired-end super-read differ in length (the reference asserts, :575)"; break; }
+        for (u64 k = P.begin1; k < P.end1; k++) {
+            if (h_ep[k] != 0xffffffffu) { err = "hc_subread_info: problem " + std::to_string(p) + ": list 1 overlaps another problem's"; break; }
+            h_ep[k] = (uint32_t)p;
+        }
+    }
+    int rc = HC_OK;
+    hc_subread_problem* d_prob = nullptr;
+    uint32_t *d_ep = nullptr, *d_v = nullptr;
+    int32_t* d_pos = nullptr;
+    hc_fno_subread* d_info = nullptr;
+    uint8_t* d_first = nullptr;
+    if (!err.empty()) { hc_set_last_error(err.c_str()); free(h_ep); return HC_ERR_ARG; }
+    ACU(cudaSetDevice(device));
+    ACU(hc_scratch_alloc((void**)&d_prob, (n_problems ? n_problems : 1) * sizeof(hc_subread_problem))); ACU(hc_scratch_alloc((void**)&d_ep, n_entries * sizeof(uint32_t)));
+    ACU(hc_scratch_alloc((void**)&d_v, n_entries * sizeof(uint32_t))); ACU(hc_scratch_alloc((void**)&d_pos, n_entries * sizeof(int32_t)));
+    ACU(hc_scratch_alloc((void**)&d_info, n_entries * sizeof(hc_fno_subread))); ACU(hc_scratch_alloc((void**)&d_first, n_entries));
+    ACU(hc_copy_h2d(d_prob, problems, n_problems * sizeof(hc_subread_problem)));
+    ACU(hc_copy_h2d(d_ep, h_ep, n_entries * sizeof(uint32_t)));
+    ACU(hc_copy_h2d(d_v, vertex, n_entries * sizeof(uint32_t)));
+    ACU(hc_copy_h2d(d_pos, pos, n_entries * sizeof(int32_t)));
+    subread_info_kernel<<<(unsigned)((n_entries + 255) / 256 < 148 * 16 ? (n_entries + 255) / 256 : 148 * 16), 256>>>(d_prob, d_ep, n_entries, d_pos, d_v, d_info, d_first);
+    ACU(cudaGetLastError());
+    ACU(hc_copy_d2h(info, d_info, n_entries * sizeof(hc_fno_subread)));
+    ACU(hc_copy_d2h(first, d_first, n_entries));
+done:
+    free(h_ep);
+    hc_scratch_free(d_prob); hc_scratch_free(d_ep); hc_scratch_free(d_v); hc_scratch_free(d_pos); hc_scratch_free(d_info); hc_scratch_free(d_first);
+    return rc;
+}

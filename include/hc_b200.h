@@ -483,6 +483,20 @@ int hc_build_adjacency(const hc_adj_edge* edges, uint64_t n, const uint8_t* keep
                        uint64_t* out_off, uint32_t* out_perm, uint64_t* in_off, uint32_t* in_src, uint8_t* ties,
                        uint64_t* n_kept, int device);
 
+/* SRBuilder::calcSubreadInfo (src/SRBuilder.cpp:536-595) for many super-reads at once (third "next" row, SURVEY 8f:
+ * the sub-read index records that hc_fno1 reads as sr_sub).  pos[] / vertex[] hold the pos_list / sorted_vertices lists of all
+ * super-reads; a problem names its list 1 [begin1, end1), its list 2 [begin2, end2) (empty for a single-end super-read) and
+ * what consensus() returned for the two sequences (trim_pos2 = -1: single-end).  For every entry k of a list 1:
+ * first[k] = 1 if it is the first entry of its vertex in that list, and then info[k] = the SubreadInfo the reference's map
+ * holds for that vertex ({index1, index2, startpos1, startpos2}, index2 = startpos2 = -1 when nothing sets them); entries of
+ * a list 2 and repeated vertices get first[k] = 0.  List-1 ranges of different problems must not overlap. */
+typedef struct {
+    uint64_t begin1, end1, begin2, end2;
+    int32_t  trim_pos1, trim_pos2;
+} hc_subread_problem;            /* 40 bytes */
+int hc_subread_info(const hc_subread_problem* problems, uint64_t n_problems, const int32_t* pos, const uint32_t* vertex,
+                    uint64_t n_entries, hc_fno_subread* info, uint8_t* first, int device);
+
 /* ------------------------------------------------------------------------------------------
  * Candidate ingestion (second "next" row): the text loop of
  * EdgeCalculator::construct_edges, src/EdgeCalculator.cpp:581-645, on the device.

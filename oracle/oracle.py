@@ -196,6 +196,22 @@ def sort_edges(graph: np.ndarray, read_len: np.ndarray):
     return out, (vs.astype(np.int64), off, out["v1"].astype(np.int64)[o2]), ties_long
 
 
+def calc_subread_info(trim_pos1, trim_pos2, pos1, vertices1, pos2, vertices2):
+    """SRBuilder::calcSubreadInfo, src/SRBuilder.cpp:536-595, restated: {vertex: (index1, index2, startpos1, startpos2)}."""
+    m = {}
+    for p, v in zip(pos1, vertices1):
+        if v in m:                                   # left index already there: a single-end super-read (:543-556)
+            i1, _, s1, _ = m[v]
+            m[v] = (i1, 0, s1, trim_pos1 - p) if trim_pos1 > p else (i1, p - trim_pos1, s1, 0)
+        else:
+            m[v] = (0, -1, trim_pos1 - p, -1) if trim_pos1 > p else (p - trim_pos1, -1, 0, -1)
+    if trim_pos2 >= 0:                               # paired-end super-read: the /2 positions (:574-592)
+        for p, v in zip(pos2, vertices2):
+            i1, _, s1, _ = m[v]
+            m[v] = (i1, 0, s1, trim_pos2 - p) if trim_pos2 > p else (i1, p - trim_pos2, s1, 0)
+    return m
+
+
 def parse_graph_inclusions(path: str) -> np.ndarray:
     """The '#I' lines of a --dump-graph file: vertices with OverlapGraph::inclusions set."""
     with open(path) as f:

@@ -103,7 +103,7 @@ int main(int argc, char** argv) {
     ps.fno = 2;
     ps.output_dir = "";
 
-    std::string dump_cands, dump_graph, dump_sorted, merge_fno1, consensus_in, consensus_out, fno_state;
+    std::string dump_cands, dump_graph, dump_sorted, merge_fno1, consensus_in, consensus_out, fno_state, subread_in, subread_out;
     bool fno3 = false, use_cliques = false;
     ps.keep_singletons = 0;
     ps.remove_trans = 1;
@@ -146,6 +146,7 @@ int main(int argc, char** argv) {
         else if (a == "--min_clique_size") ps.min_clique_size = std::atoi(need("--min_clique_size"));
         else if (a == "--min_qual") ps.min_qual = std::atof(need("--min_qual"));
         else if (a == "--consensus") { consensus_in = need("--consensus"); consensus_out = need("--consensus"); }
+        else if (a == "--subread-info") { subread_in = need("--subread-info"); subread_out = need("--subread-info"); }
         else if (a == "--keep_singletons") ps.keep_singletons = std::atoi(need("--keep_singletons"));
         else if (a == "--remove_branches") ps.remove_branches = std::atoi(need("--remove_branches")) != 0;
         else if (a == "--remove_trans") ps.remove_trans = std::atoi(need("--remove_trans"));
@@ -200,6 +201,36 @@ int main(int argc, char** argv) {
         }
         std::fclose(fo);
         std::printf("{\"consensus_problems\": %lu, \"consensus_bases\": %lu, \"t_consensus_s\": %.6f}\n", n_prob, n_bases, t_cons);
+        return 0;
+    }
+
+    // --subread-info IN OUT: SRBuilder::calcSubreadInfo (src/SRBuilder.cpp:536-595) on the problems of IN
+    // ("S trim_pos1 trim_pos2 n1 n2", then n1 "pos vertex" pairs of list 1 and n2 of list 2); per problem in OUT one line
+    // "R m" and m lines "vertex index1 index2 startpos1 startpos2", vertices ascending.
+    if (!subread_in.empty()) {
+        std::shared_ptr<SRBuilder> srb(new SRBuilder(fastq, graph, ps));
+        std::ifstream in(subread_in.c_str());
+        FILE* fo = std::fopen(subread_out.c_str(), "w");
+        if (!in.is_open() || !fo) { std::fprintf(stderr, "cannot open the subread-info files\n"); return 1; }
+        std::string tag;
+        while (in >> tag) {
+            int t1, t2, n1, n2;
+            in >> t1 >> t2 >> n1 >> n2;
+            std::list<int> p1, p2;
+            std::list<node_id_t> v1, v2;
+            for (int k = 0; k < n1; k++) { int p; unsigned long v; in >> p >> v; p1.push_back(p); v1.push_back(v); }
+            for (int k = 0; k < n2; k++) { int p; unsigned long v; in >> p >> v; p2.push_back(p); v2.push_back(v); }
+            std::unordered_map<node_id_t, SubreadInfo> m = srb->calcSubreadInfo(t1, t2, p1, p2, v1, v2);
+            std::vector<node_id_t> keys;
+            for (std::unordered_map<node_id_t, SubreadInfo>::iterator it = m.begin(); it != m.end(); ++it) keys.push_back(it->first);
+            std::sort(keys.begin(), keys.end());
+            std::fprintf(fo, "R\t%zu\n", keys.size());
+            for (size_t k = 0; k < keys.size(); k++) {
+                const SubreadInfo& si = m[keys[k]];
+                std::fprintf(fo, "%lu\t%d\t%d\t%d\t%d\n", keys[k], si.index1, si.index2, si.startpos1, si.startpos2);
+            }
+        }
+        std::fclose(fo);
         return 0;
     }
 

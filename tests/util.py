@@ -35,7 +35,7 @@ class Golden:
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("fno", "insert_", "ingest_", "consensus_", "sorted_", "sfo_", "sam_")))
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("fno", "insert_", "ingest_", "consensus_", "sorted_", "sfo_", "sam_", "subread_")))
 
 
 def fno_golden_names():
