@@ -193,7 +193,12 @@ void parallel_sort(std::vector<Rec>& v) {
 
 }  // namespace
 
+static double now_s() { return omp_get_wtime(); }
+
 int main(int argc, char** argv) {
+    const bool timing = getenv("HC_TIMING") != nullptr;
+    double t_mark = now_s();
+    auto mark = [&](const char* what) { if (timing) { const double t = now_s(); std::fprintf(stderr, "[hc_sfo2overlaps] %-28s %8.1f ms\n", what, (t - t_mark) * 1e3); t_mark = t; } };
     std::string in, out;
     long ns = -1, np = -1;
     for (int i = 1; i < argc; i++) {
@@ -231,10 +236,12 @@ int main(int argc, char** argv) {
         }
     }
     close(fd);
+    mark("file read");
     std::vector<size_t> ls(1, 0);                               // line starts
     for (size_t i = 0; i < text.size(); i++) if (text[i] == '\n' && i + 1 < text.size()) ls.push_back(i + 1);
     if (text.empty()) ls.clear();
     const size_t nl = ls.size();
+    mark("line starts");
     // ---- 1. original ids in front, smaller one first
     std::vector<Rec> recs(nl);
 #pragma omp parallel for schedule(static)
@@ -273,8 +280,10 @@ int main(int argc, char** argv) {
         r.ori = ori.size() == 1 ? ori[0] : '?';
     }
     std::string().swap(text);
+    mark("parse + flip");
     // ---- 2. sort | uniq
     parallel_sort(recs);
+    mark("sort");
     {
         size_t w = 0;
         for (size_t k = 0; k < recs.size(); k++)
@@ -282,6 +291,7 @@ int main(int argc, char** argv) {
         recs.resize(w);
     }
     const size_t n = recs.size();
+    mark("uniq");
     // ---- 3. the pass: classes of the lines, groups of the lines that involve a paired-end read
     std::vector<unsigned char> kind(n, 0);                      // 0 self-overlap (skipped), 1 single-single, 2 paired involved
 #pragma omp parallel for schedule(static)
@@ -308,6 +318,7 @@ int main(int argc, char** argv) {
         }
         groups.back().lines.push_back(k);
     }
+    mark("kinds + groups");
     std::vector<std::string> line_out(n), group_out(groups.size());
     long s_s_count = 0, p_count = 0;
 #pragma omp parallel for schedule(dynamic, 4096) reduction(+ : s_s_count)
@@ -331,6 +342,7 @@ int main(int argc, char** argv) {
                 if (b.size() != before) p_count++;
             }
     }
+    mark("overlaps");
     // ---- 4. stitch in the script's order (a group's lines come out when the next group's first line is read), uniq
     FILE* fo = std::fopen(out.c_str(), "w");
     if (!fo) die("IOError: cannot write " + out);
@@ -352,6 +364,7 @@ int main(int argc, char** argv) {
     }
     std::fwrite(buf.data(), 1, buf.size(), fo);
     std::fclose(fo);
+    mark("stitch + write");
     std::printf("total overlap count: %ld\nof which single-single: %ld\n", s_s_count + p_count, s_s_count);
     return 0;
 }
