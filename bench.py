@@ -543,7 +543,7 @@ def main() -> None:
         e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert c_ne.value == ne and c_nn.value == nn
         # the same call on PAGEABLE buffers (what a std::vector / numpy caller hands over): the library stages the records
-        # through its own pinned slots; reported next to the pinned number
+        # through its ring of pinned buffers; reported next to the pinned number
         e2e_pageable = None
         if small:
             try:
@@ -569,7 +569,7 @@ def main() -> None:
                 pg_ms = 1e3 * (time.perf_counter() - tp0) / 3
                 assert c_ne.value == ne and c_nn.value == nn and p_edges[:ne].tobytes() == h_edges[:ne].numpy().tobytes()
                 e2e_pageable = {"ms_per_step": pg_ms, "value_per_gpu": n / (pg_ms * 1e-3), "unit": UNIT,
-                                "note": "same call, pageable host buffers (numpy): records staged through the library's pinned slots by %d host threads" % (os.cpu_count() or 1)}
+                                "note": "same call, pageable host buffers (numpy): records and results staged through the library's ring of pinned buffers by up to 16 of the %d host threads" % (os.cpu_count() or 1)}
                 del p_cand, p_edges, p_bits
             except Exception as ex:
                 e2e_pageable = {"failed": repr(ex)}
