@@ -493,7 +493,10 @@ def main() -> None:
             pw = cc[:, 1].to(torch.int64) & 0xffffffff
             v = other | (role << 25) | (((pw >> 28) & 0xf) << 26) | ((pw & 0x3fff) << 30) | (((pw >> 14) & 0x3fff) << 39)
             c6 = v.view(torch.uint8).reshape(n, 8)[:, :6].contiguous()
-            h_cand = torch.empty((n, 6), dtype=torch.uint8, pin_memory=True)
+            if os.environ.get("HC_BENCH_WC"):      # experiment: the records in write-combined pinned memory (the host only writes them)
+                h_cand = torch.from_numpy(capi.host_alloc(n * 6, write_combined=True)).reshape(n, 6)
+            else:
+                h_cand = torch.empty((n, 6), dtype=torch.uint8, pin_memory=True)
             h_cand.copy_(c6)
             del other, role, pw, v, c6
         else:
@@ -545,7 +548,7 @@ def main() -> None:
         # the same call on PAGEABLE buffers (what a std::vector / numpy caller hands over): the library stages the records
         # through its ring of pinned buffers; reported next to the pinned number
         e2e_pageable = None
-        if small:
+        if small and not os.environ.get("HC_BENCH_WC"):   # (the leg copies the records back out of h_cand: not out of write-combined memory)
             try:
                 p_cand = np.empty(h_cand.shape, dtype=np.uint8 if runs6 else np.int32)
                 p_cand[...] = h_cand.numpy()

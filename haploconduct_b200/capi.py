@@ -22,7 +22,7 @@ EXPORTED = [
     "hc_store_create", "hc_store_destroy", "hc_store_n_reads", "hc_store_n_single", "hc_store_n_devices",
     "hc_store_device_bytes", "hc_store_quality_alphabet", "hc_score_batch", "hc_score_batch_compact", "hc_score_batch_short", "hc_score_batch_runs", "hc_score_batch_runs_small", "hc_score_batch_runs6_small", "hc_score_batch_short_small", "hc_edge_extra_pos", "hc_score_batch_device",
     "hc_overlap_score", "hc_overlap_score_multi",
-    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_warm_up", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3", "hc_fno1_small", "hc_fno3_small", "hc_build_adjacency", "hc_subread_info",
+    "hc_phred_to_prob", "hc_exp_threshold", "hc_device_count", "hc_warm_up", "hc_last_error", "hc_version", "hc_fno1", "hc_fno3", "hc_fno1_small", "hc_fno3_small", "hc_build_adjacency", "hc_subread_info", "hc_host_alloc", "hc_host_free",
     "hc_store_create_fastq", "hc_store_create_fastq_files", "hc_store_read_ids", "hc_consensus", "hc_dedup_edges", "hc_idmap_create", "hc_idmap_destroy", "hc_ingest_overlaps", "hc_ingest_overlaps_device",
 ]
 
@@ -98,6 +98,10 @@ def lib() -> ctypes.CDLL:
         L.hc_fno3.argtypes = [u64, vp, vp, vp, u64, vp, i32, vp, u64, ctypes.POINTER(u64), i32]
         L.hc_build_adjacency.restype = i32
         L.hc_build_adjacency.argtypes = [vp, u64, vp, u64, i32, vp, vp, vp, vp, vp, ctypes.POINTER(u64), i32]
+        L.hc_host_alloc.restype = vp
+        L.hc_host_alloc.argtypes = [u64, i32]
+        L.hc_host_free.restype = None
+        L.hc_host_free.argtypes = [vp]
         L.hc_subread_info.restype = i32
         L.hc_subread_info.argtypes = [vp, u64, vp, vp, u64, vp, vp, i32]
         L.hc_fno1_small.restype = i32
@@ -449,6 +453,14 @@ def subread_info(problems: np.ndarray, pos: np.ndarray, vertex: np.ndarray, devi
     _check(lib().hc_subread_info(P.ctypes.data if len(P) else None, len(P), pos.ctypes.data if n else None, vertex.ctypes.data if n else None, n,
                                  info.ctypes.data, first.ctypes.data, device))
     return info[:n], first[:n]
+
+
+def host_alloc(nbytes: int, write_combined: bool = False) -> np.ndarray:
+    """hc_host_alloc as a uint8 numpy array (pinned; the memory lives until the process ends or hc_host_free on its address)."""
+    p = lib().hc_host_alloc(nbytes, int(write_combined))
+    if not p:
+        raise HcError(-3, "hc_host_alloc failed")
+    return np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(p))
 
 
 def dedup_edges(edges: np.ndarray, n_vertices: int, ignore_inclusions: bool = False, inclusions: Optional[np.ndarray] = None,

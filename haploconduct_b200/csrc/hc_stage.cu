@@ -298,3 +298,15 @@ cudaError_t hc_scratch_alloc_on(void** p, size_t bytes, cudaStream_t st) {
 void hc_scratch_free_on(void* p, cudaStream_t st) {
     if (p) cudaFreeAsync(p, st);
 }
+
+// ---- pinned host memory for callers of the host-buffer entry points (include/hc_b200.h) -----------------------------------
+extern "C" void* hc_host_alloc(unsigned long long bytes, int write_combined) {
+    void* p = nullptr;
+    const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    if (cudaHostAlloc(&p, bytes ? (size_t)bytes : 1, flags) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void hc_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}

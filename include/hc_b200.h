@@ -333,6 +333,13 @@ int hc_overlap_score_multi(const char* seq1, uint32_t len1, const char* seq2, ui
  * a host calls this from a second thread while it reads its input files, so that the two overlap. */
 int hc_warm_up(int device);
 
+/* Pinned host memory for the host-buffer entry points.  They accept any host memory (pageable buffers are staged through the
+ * library's own pinned ring); buffers from here go to the copy engines as they are.  write_combined != 0: write-combined
+ * memory, for buffers the host only WRITES front to back (candidate records on their way in) -- reading it back is slow.
+ * NULL if the allocation fails. */
+void* hc_host_alloc(uint64_t bytes, int write_combined);
+void  hc_host_free(void* p);
+
 /* EdgeCalculator::phred_to_prob (src/EdgeCalculator.cpp:59-63), host arithmetic: pow(10, -Q/10.0). */
 double hc_phred_to_prob(int phred);
 

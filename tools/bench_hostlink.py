@@ -18,6 +18,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--numa-bind", action="store_true")
+    ap.add_argument("--write-combined", action="store_true", help="the host->device source in write-combined pinned memory (hc_host_alloc)")
     ap.add_argument("--mb-in", type=int, default=1024)
     ap.add_argument("--mb-out", type=int, default=256)
     ap.add_argument("--reps", type=int, default=8)
@@ -33,7 +34,12 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    h_in = torch.empty(a.mb_in << 20, dtype=torch.uint8, pin_memory=True); h_in.fill_(1)
+    if a.write_combined:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from haploconduct_b200 import capi
+        h_in = torch.from_numpy(capi.host_alloc(a.mb_in << 20, write_combined=True)); h_in.fill_(1)
+    else:
+        h_in = torch.empty(a.mb_in << 20, dtype=torch.uint8, pin_memory=True); h_in.fill_(1)
     d_in = torch.empty(a.mb_in << 20, dtype=torch.uint8, device=dev)
     h_out = torch.empty(a.mb_out << 20, dtype=torch.uint8, pin_memory=True); h_out.fill_(1)
     d_out = torch.empty(a.mb_out << 20, dtype=torch.uint8, device=dev)
@@ -73,7 +79,7 @@ def main():
     leg(True, True)   # warm-up
     res = {"h2d_only": leg(True, False), "d2h_only": leg(False, True), "both": leg(True, True)}
     if rank == 0:
-        print(json.dumps({"ranks": world, "numa_bind": bool(a.numa_bind), "numa_rank0": numa, "unit": "GB/s", "mb_in": a.mb_in, "mb_out": a.mb_out,
+        print(json.dumps({"ranks": world, "write_combined": bool(a.write_combined), "numa_bind": bool(a.numa_bind), "numa_rank0": numa, "unit": "GB/s", "mb_in": a.mb_in, "mb_out": a.mb_out,
                           "legs": res, "cpus": os.cpu_count(),
                           "e2e_step_bytes": {"h2d": 1002909812, "d2h_small": 186000000, "d2h_full": 611642544}}))
     if world > 1:
