@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,8 +40,16 @@ struct Rec {                 // one line of the temporary file: idA idB sfoA sfo
     long idA, idB, sfoA, sfoB;
     char ori;
     long OHA, OHB, OLA, OLB;
-    std::string text;        // the line as the script writes it (without '\n'): sort's last-resort key, uniq's identity
+    const char* text;        // the line as the script writes it (without '\n'): sort's last-resort key, uniq's identity --
+    uint32_t text_len;       // bytes in the arena of the thread that parsed the line
 };
+
+int text_cmp(const Rec& a, const Rec& b) {                    // bytes as unsigned char, shorter first on a common prefix (LC_ALL=C)
+    const uint32_t n = a.text_len < b.text_len ? a.text_len : b.text_len;
+    const int c = std::memcmp(a.text, b.text, n);
+    if (c) return c;
+    return a.text_len < b.text_len ? -1 : (a.text_len > b.text_len ? 1 : 0);
+}
 
 bool parse_long(const char* b, const char* e, long& v) {       // Python int() on a whitespace-free token
     if (b == e) return false;
@@ -118,8 +127,11 @@ SS s_s_overlap(const Rec& r) {
 
 void put_long(std::string& b, long v) {
     char tmp[24];
-    const int n = std::snprintf(tmp, sizeof(tmp), "%ld", v);
-    b.append(tmp, (size_t)n);
+    int k = 24;
+    unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+    do { tmp[--k] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) tmp[--k] = '-';
+    b.append(tmp + k, (size_t)(24 - k));
 }
 
 void put_ss_line(std::string& b, const SS& o) {                // ID1 ID2 POS1 - - ORI1 ORI2 PERC1 - LEN1 - s s
@@ -171,7 +183,7 @@ bool rec_less(const Rec& a, const Rec& b) {                   // sort -k1,1n -k2
     if (a.idB != b.idB) return a.idB < b.idB;
     if (a.sfoA != b.sfoA) return a.sfoA < b.sfoA;
     if (a.sfoB != b.sfoB) return a.sfoB < b.sfoB;
-    return a.text < b.text;                                     // std::string compares bytes as unsigned char
+    return text_cmp(a, b) < 0;
 }
 
 void parallel_sort(std::vector<Rec>& v) {
@@ -244,8 +256,20 @@ int main(int argc, char** argv) {
     mark("line starts");
     // ---- 1. original ids in front, smaller one first
     std::vector<Rec> recs(nl);
-#pragma omp parallel for schedule(static)
-    for (long k = 0; k < (long)nl; k++) {
+    // the temporary file's lines live in one arena per thread (a flipped line is at most a few bytes longer than the original
+    // plus the two ids in front: 48 bytes of headroom per line)
+    const int T = std::max(1, omp_get_max_threads());
+    std::vector<std::vector<char>> arena(T);
+#pragma omp parallel num_threads(T)
+    {
+    const int tid = omp_get_thread_num();
+    const size_t klo = nl * (size_t)tid / (size_t)T, khi = nl * (size_t)(tid + 1) / (size_t)T;
+    const size_t span = klo < khi ? ((khi < nl ? ls[khi] : text.size()) - ls[klo]) : 0;
+    std::vector<char>& A = arena[tid];
+    A.resize(span + 64 * (khi - klo) + 64);
+    char* ap = A.data();
+    std::string t;
+    for (long k = (long)klo; k < (long)khi; k++) {
         const char* b = text.data() + ls[(size_t)k];
         const char* e = (size_t)k + 1 < nl ? text.data() + ls[(size_t)k + 1] : text.data() + text.size();
         const char* le = e;                                     // the line without its '\n' (line.strip('\n') strips all of them)
@@ -262,7 +286,7 @@ int main(int argc, char** argv) {
         if (!parse_long(fb[3], fe[3], oha) || !parse_long(fb[4], fe[4], ohb) || !parse_long(fb[5], fe[5], ola) || !parse_long(fb[6], fe[6], olb))
             die("ValueError: invalid literal for int()");
         const std::string ori(fb[2], fe[2]), K(fb[7], fe[7]);
-        std::string& t = r.text;
+        t.clear();
         if (flip) {
             long foha = oha, fohb = ohb;
             if (ori == "I") { foha = ohb; fohb = oha; }          // flip_I swaps the overhangs, flip_N negates them
@@ -278,6 +302,11 @@ int main(int argc, char** argv) {
             r.idA = na; r.idB = nb; r.sfoA = sa; r.sfoB = sb; r.OHA = oha; r.OHB = ohb; r.OLA = ola; r.OLB = olb;
         }
         r.ori = ori.size() == 1 ? ori[0] : '?';
+        if ((size_t)(ap - A.data()) + t.size() > A.size()) die("internal: line arena too small");
+        std::memcpy(ap, t.data(), t.size());
+        r.text = ap; r.text_len = (uint32_t)t.size();
+        ap += t.size();
+    }
     }
     std::string().swap(text);
     mark("parse + flip");
@@ -287,7 +316,7 @@ int main(int argc, char** argv) {
     {
         size_t w = 0;
         for (size_t k = 0; k < recs.size(); k++)
-            if (k == 0 || recs[k].text != recs[w - 1].text) { if (w != k) recs[w] = std::move(recs[k]); w++; }
+            if (k == 0 || text_cmp(recs[k], recs[w - 1]) != 0) { if (w != k) recs[w] = recs[k]; w++; }
         recs.resize(w);
     }
     const size_t n = recs.size();
