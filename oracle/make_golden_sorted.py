@@ -19,8 +19,8 @@ from util import load_golden  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def main():
-    for name in ("c1_savage_example_full", "c2_polyte_example_full", "synth_all_types", "synth_stage_c_contigs"):
+def main(names=("c1_savage_example_full", "c2_polyte_example_full", "synth_all_types", "synth_stage_c_contigs")):
+    for name in names:
         try:
             g = load_golden(name)
         except Exception as ex:
