@@ -84,3 +84,19 @@ def test_run_encoding_round_trip(order):
     big["pos1"][7] = 1 << 14
     with pytest.raises(ValueError):
         F.run_encode(big)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/hc_b200.h must compile as C99 (no C++ types, no torch types)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc on this box")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "hc_b200.h"\nint main(void) { return (int)sizeof(hc_candidate) + (int)sizeof(hc_fno_overlap_small) + (int)sizeof(hc_adj_edge); }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert capi.FNO_OVERLAP_SMALL.itemsize == 24 and capi.ADJ_EDGE.itemsize == 16 and capi.SUBREAD_PROBLEM.itemsize == 40
